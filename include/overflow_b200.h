@@ -1,0 +1,150 @@
+/*
+ * overflow_b200.h -- C ABI of liboverflow_b200.so: the D8 flow-routing hot path of
+ * Denver-Automation-Analytics/overflow, hand-written CUDA for NVIDIA B200 (sm_100a).
+ *
+ * The reference has no FFI: its replaceable seam is two numba-jitted Python functions.
+ * Each entry point below names the reference interface it stands in for (paths relative
+ * to the reference tree):
+ *
+ *   ofl_flow_direction_f32        src/overflow/flow_direction.py:14-69   flow_direction_for_tile
+ *                                 (+ calculate_slope :72-96; driver loop :121-124)
+ *   ofl_flow_accumulation_u8      src/overflow/flow_accumulation.py:95-158 single_tile_flow_accumulation
+ *                                 (get_next_cell :13-37, perimeter_indices :40-51, follow_path :54-92)
+ *   ofl_check_accumulation_u8     no reference counterpart: exactness check of the accumulation recurrence
+ *   ofl_strip_*                   no reference counterpart: row-strip (multi-GPU) decomposition in the
+ *                                 structure of Barnes 2016 (arXiv 1608.04431), the paper cited at
+ *                                 src/overflow/flow_accumulation.py:61,100
+ *   ofl_synth_dem_f32             no reference counterpart: seeded synthetic DEM for benchmarks
+ *
+ * Conventions
+ *   - plain pointers and sizes only; rasters are row-major with an explicit leading dimension in ELEMENTS
+ *   - mem_kind says where the raster pointers live (OFL_MEM_HOST: the library stages through device
+ *     buffers it owns and copies results back; OFL_MEM_DEVICE: pointers are CUDA device pointers)
+ *   - `stream` is a cudaStream_t (NULL = the legacy default stream); device-pointer calls are
+ *     asynchronous on it unless stated, host-pointer calls return after the results are in host memory
+ *   - every function returns OFL_OK (0) or a negative ofl_status; ofl_last_error() gives the message
+ *     for the calling thread
+ *   - there is no CPU fallback: without a usable CUDA device every compute entry point fails
+ */
+#ifndef OVERFLOW_B200_H
+#define OVERFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFL_ABI_VERSION 1
+
+typedef enum ofl_status {
+  OFL_OK = 0,
+  OFL_ERR_INVALID = -1,   /* bad argument (NULL pointer, negative size, unknown enum) */
+  OFL_ERR_ALIGNMENT = -2, /* device raster violates the alignment contract below */
+  OFL_ERR_CUDA = -3,      /* a CUDA call failed; message carries cudaGetErrorString */
+  OFL_ERR_NOMEM = -4,     /* device or host allocation failed */
+  OFL_ERR_CYCLE = -5,     /* flow-direction raster contains a cycle (never produced by flow direction) */
+  OFL_ERR_WORKSPACE = -6  /* caller-provided workspace too small */
+} ofl_status;
+
+typedef enum ofl_mem_kind { OFL_MEM_HOST = 0, OFL_MEM_DEVICE = 1 } ofl_mem_kind;
+
+/* Direction codes and sentinels: src/overflow/constants.py:15-24,57-59 */
+#define OFL_DIR_EAST 0
+#define OFL_DIR_NORTH_EAST 1
+#define OFL_DIR_NORTH 2
+#define OFL_DIR_NORTH_WEST 3
+#define OFL_DIR_WEST 4
+#define OFL_DIR_SOUTH_WEST 5
+#define OFL_DIR_SOUTH 6
+#define OFL_DIR_SOUTH_EAST 7
+#define OFL_DIR_UNDEFINED 8
+#define OFL_DIR_NODATA 9
+#define OFL_FAC_NODATA (-9999)
+/* what the reference actually leaves in NODATA cells (flow_accumulation.py:119-121,129-137) */
+#define OFL_FAC_NODATA_EMITTED (-9998)
+#define OFL_LINK_TERMINATES (-1)
+#define OFL_LINK_EXTERNAL (-2)
+
+/* How ofl_flow_direction_f32 treats the input array. */
+typedef enum ofl_dir_mode {
+  /* flow_direction_for_tile semantics: dem carries its own one-cell ring; interior cells are
+   * computed, the ring of `fdr` (uninitialised in the reference) is set to OFL_DIR_NODATA. */
+  OFL_DIR_MODE_TILE = 0,
+  /* whole raster: every cell is computed and cells outside the array read as the band nodata
+   * value cast to float32 -- what flow_direction()'s chunk loop with raster_chunker(buffer=1)
+   * produces for the whole file (flow_direction.py:121-124, util/raster.py:67). */
+  OFL_DIR_MODE_RASTER = 1,
+  /* row strip with halo: dem has rows+2 rows (row 0 and row rows+1 are the neighbours' rows or
+   * nodata at the raster top/bottom); fdr has `rows` rows; columns behave as in RASTER mode. */
+  OFL_DIR_MODE_STRIP = 2
+} ofl_dir_mode;
+
+const char* ofl_last_error(void);
+int ofl_abi_version(void);
+
+/* Select the CUDA device for the calling thread's subsequent calls and create library state on it. */
+int ofl_init(int device);
+/* Free cached staging buffers and workspaces. */
+int ofl_shutdown(void);
+/* Number of kernels this library has launched since ofl_init / the last reset (bench accounting). */
+int64_t ofl_launch_count(void);
+void ofl_launch_count_reset(void);
+
+/*
+ * D8 steepest-descent flow direction.
+ *   dem      float32, `rows` x `cols` (STRIP mode: rows+2 x cols), leading dimension ld_dem
+ *   nodata   the band nodata value as a double; a cell is nodata iff (double)cell == nodata
+ *   fdr      uint8 out, `rows` x `cols`, leading dimension ld_fdr
+ * Device-pointer alignment contract: dem 16-byte aligned with ld_dem % 4 == 0;
+ * fdr 4-byte aligned with ld_fdr % 4 == 0.  Host pointers have no alignment requirement.
+ */
+int ofl_flow_direction_f32(const float* dem, int64_t rows, int64_t cols, int64_t ld_dem, double nodata,
+                           uint8_t* fdr, int64_t ld_fdr, int mode, int mem_kind, void* stream);
+
+/* Perimeter entries of `links` in perimeter_indices order (flow_accumulation.py:40-51). */
+int64_t ofl_perimeter_count(int64_t rows, int64_t cols);
+
+/* Device workspace ofl_flow_accumulation_u8 needs for a rows x cols raster (bytes). */
+size_t ofl_accumulation_workspace_bytes(int64_t rows, int64_t cols);
+
+/*
+ * Flow accumulation of a whole flow-direction raster (one "tile" in the reference's terms).
+ *   fdr          uint8 codes, rows x cols, leading dimension ld_fdr; 9 = NODATA, 8 or >= 10 = no downstream
+ *   fac          int64 out, rows x cols, leading dimension ld_fac; NODATA cells get -9998
+ *   perim_links  nullable; int64 [ofl_perimeter_count][2] in perimeter_indices order:
+ *                (-2,-2) drains straight out, (-1,-1) terminates inside, else (row,col) of the exit cell
+ *   workspace    device scratch of at least ofl_accumulation_workspace_bytes (NULL: library-owned, cached)
+ * Device-pointer alignment contract: fdr 16-byte aligned with ld_fdr % 16 == 0; fac 16-byte aligned
+ * with ld_fac % 2 == 0; perim_links is a device pointer when mem_kind is OFL_MEM_DEVICE.
+ * Synchronous with respect to the host (the pointer-jumping phase reads a device flag).
+ */
+int ofl_flow_accumulation_u8(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, int64_t* fac,
+                             int64_t ld_fac, int64_t* perim_links, void* workspace, size_t workspace_bytes,
+                             int mem_kind, void* stream);
+
+/*
+ * Exactness check: counts cells where fac != 1 + sum(fac of upstream neighbours) (data cells) or
+ * fac != -9998 (NODATA cells).  On an acyclic raster zero violations prove fac is THE answer.
+ */
+int ofl_check_accumulation_u8(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, const int64_t* fac,
+                              int64_t ld_fac, int64_t* n_bad, int mem_kind, void* stream);
+
+/* Set the one-cell ring of a device uint8 raster to `value` (TILE mode helper for device callers). */
+int ofl_fill_border_u8(uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, int value, void* stream);
+
+/*
+ * Seeded synthetic DEM written straight into device memory (benchmarks / large parity runs).
+ * Cell (row0 + r, c) depends only on its global coordinates and the seed, so every rank of a
+ * row-strip run can synthesise its own strip and halo rows.
+ *   kind 0: multi-octave value-noise fractal in [0, relief]   kind 1: same, quantised to 1.0 (terraces)
+ *   kind 2: tilted plane draining south-east                   holes_permille: nodata rectangles
+ */
+int ofl_synth_dem_f32(float* dem, int64_t rows, int64_t cols, int64_t ld_dem, int64_t row0, int64_t total_rows,
+                      uint64_t seed, int kind, float relief, int holes_permille, float nodata, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OVERFLOW_B200_H */

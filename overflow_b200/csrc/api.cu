@@ -1,0 +1,185 @@
+// api.cu -- the extern "C" surface declared in include/overflow_b200.h.
+// Host-pointer calls stage through library-owned device buffers; device-pointer calls launch directly.
+#include "common.cuh"
+
+namespace ofl {
+const char* last_error();
+int init_device(int device);
+int ensure_init();
+int shutdown();
+int64_t launch_count();
+void launch_count_reset();
+
+int launch_direction(const float* dem, int64_t in_rows, int64_t cols, int64_t ld_dem, double nodata, uint8_t* fdr,
+                     int64_t rows, int64_t ld_fdr, int y_off, cudaStream_t st);
+int launch_fill_border(uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld, int value, cudaStream_t st);
+int64_t perimeter_count(int64_t rows, int64_t cols);
+size_t accumulation_workspace_bytes(int64_t rows, int64_t cols);
+int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, long long* fac, int64_t ld_fac,
+                        long long* perim_links_dev, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int launch_check(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, const long long* fac, int64_t ld_fac,
+                 unsigned long long* n_bad_dev, cudaStream_t st);
+int launch_synth(float* dem, int64_t rows, int64_t cols, int64_t ld, int64_t row0, int64_t total_rows, uint64_t seed,
+                 int kind, float relief, int holes_permille, float nodata, cudaStream_t st);
+}  // namespace ofl
+
+using namespace ofl;
+
+static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+extern "C" {
+
+const char* ofl_last_error(void) { return last_error(); }
+int ofl_abi_version(void) { return OFL_ABI_VERSION; }
+int ofl_init(int device) { return init_device(device); }
+int ofl_shutdown(void) { return shutdown(); }
+int64_t ofl_launch_count(void) { return launch_count(); }
+void ofl_launch_count_reset(void) { launch_count_reset(); }
+int64_t ofl_perimeter_count(int64_t rows, int64_t cols) { return perimeter_count(rows, cols); }
+size_t ofl_accumulation_workspace_bytes(int64_t rows, int64_t cols) { return accumulation_workspace_bytes(rows, cols); }
+
+int ofl_flow_direction_f32(const float* dem, int64_t rows, int64_t cols, int64_t ld_dem, double nodata, uint8_t* fdr,
+                           int64_t ld_fdr, int mode, int mem_kind, void* stream) {
+  OFL_REQUIRE(rows >= 0 && cols >= 0, OFL_ERR_INVALID, "negative raster size");
+  OFL_REQUIRE(mode == OFL_DIR_MODE_TILE || mode == OFL_DIR_MODE_RASTER || mode == OFL_DIR_MODE_STRIP, OFL_ERR_INVALID,
+              "unknown direction mode %d", mode);
+  OFL_REQUIRE(mem_kind == OFL_MEM_HOST || mem_kind == OFL_MEM_DEVICE, OFL_ERR_INVALID, "unknown mem_kind %d", mem_kind);
+  if (rows == 0 || cols == 0) return OFL_OK;
+  OFL_REQUIRE(dem != nullptr && fdr != nullptr, OFL_ERR_INVALID, "null raster pointer");
+  OFL_REQUIRE(ld_dem >= cols && ld_fdr >= cols, OFL_ERR_INVALID, "leading dimension smaller than cols");
+  int rc = ensure_init();
+  if (rc != OFL_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int y_off = (mode == OFL_DIR_MODE_STRIP) ? 1 : 0;
+  const int64_t in_rows = rows + 2 * y_off;
+
+  if (mem_kind == OFL_MEM_DEVICE) {
+    rc = launch_direction(dem, in_rows, cols, ld_dem, nodata, fdr, rows, ld_fdr, y_off, st);
+    if (rc != OFL_OK) return rc;
+    if (mode == OFL_DIR_MODE_TILE) return launch_fill_border(fdr, rows, cols, ld_fdr, OFL_DIR_NODATA, st);
+    return OFL_OK;
+  }
+
+  // host rasters: pitched device staging, one H2D, kernel, one D2H
+  const int64_t ldd = round_up(cols, 4), ldo = round_up(cols, 16);
+  void *d_dem = nullptr, *d_fdr = nullptr;
+  rc = scratch_get(SCRATCH_DEM, (size_t)in_rows * ldd * sizeof(float), &d_dem);
+  if (rc != OFL_OK) return rc;
+  rc = scratch_get(SCRATCH_FDR, (size_t)rows * ldo, &d_fdr);
+  if (rc != OFL_OK) return rc;
+  OFL_CUDA(cudaMemcpy2DAsync(d_dem, ldd * sizeof(float), dem, ld_dem * sizeof(float), cols * sizeof(float), in_rows,
+                             cudaMemcpyHostToDevice, st));
+  rc = launch_direction(static_cast<const float*>(d_dem), in_rows, cols, ldd, nodata, static_cast<uint8_t*>(d_fdr),
+                        rows, ldo, y_off, st);
+  if (rc != OFL_OK) return rc;
+  if (mode == OFL_DIR_MODE_TILE) {
+    rc = launch_fill_border(static_cast<uint8_t*>(d_fdr), rows, cols, ldo, OFL_DIR_NODATA, st);
+    if (rc != OFL_OK) return rc;
+  }
+  OFL_CUDA(cudaMemcpy2DAsync(fdr, ld_fdr, d_fdr, ldo, cols, rows, cudaMemcpyDeviceToHost, st));
+  OFL_CUDA(cudaStreamSynchronize(st));
+  return OFL_OK;
+}
+
+int ofl_fill_border_u8(uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, int value, void* stream) {
+  OFL_REQUIRE(fdr != nullptr || rows * cols == 0, OFL_ERR_INVALID, "null raster pointer");
+  int rc = ensure_init();
+  if (rc != OFL_OK) return rc;
+  return launch_fill_border(fdr, rows, cols, ld_fdr, value, static_cast<cudaStream_t>(stream));
+}
+
+int ofl_flow_accumulation_u8(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, int64_t* fac,
+                             int64_t ld_fac, int64_t* perim_links, void* workspace, size_t workspace_bytes,
+                             int mem_kind, void* stream) {
+  OFL_REQUIRE(rows >= 0 && cols >= 0, OFL_ERR_INVALID, "negative raster size");
+  OFL_REQUIRE(mem_kind == OFL_MEM_HOST || mem_kind == OFL_MEM_DEVICE, OFL_ERR_INVALID, "unknown mem_kind %d", mem_kind);
+  if (rows == 0 || cols == 0) return OFL_OK;
+  OFL_REQUIRE(fdr != nullptr && fac != nullptr, OFL_ERR_INVALID, "null raster pointer");
+  OFL_REQUIRE(ld_fdr >= cols && ld_fac >= cols, OFL_ERR_INVALID, "leading dimension smaller than cols");
+  int rc = ensure_init();
+  if (rc != OFL_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t need = accumulation_workspace_bytes(rows, cols);
+  if (workspace == nullptr) {
+    rc = scratch_get(SCRATCH_WORK, need, &workspace);
+    if (rc != OFL_OK) return rc;
+    workspace_bytes = need;
+  }
+  if (mem_kind == OFL_MEM_DEVICE)
+    return launch_accumulation(fdr, rows, cols, ld_fdr, reinterpret_cast<long long*>(fac), ld_fac,
+                               reinterpret_cast<long long*>(perim_links), workspace, workspace_bytes, st);
+
+  const int64_t ldi = round_up(cols, 16), ldo = round_up(cols, 2);
+  void *d_fdr = nullptr, *d_fac = nullptr, *d_links = nullptr;
+  rc = scratch_get(SCRATCH_FDR, (size_t)rows * ldi, &d_fdr);
+  if (rc != OFL_OK) return rc;
+  rc = scratch_get(SCRATCH_FAC, (size_t)rows * ldo * sizeof(int64_t), &d_fac);
+  if (rc != OFL_OK) return rc;
+  const int64_t n_perim = perimeter_count(rows, cols);
+  if (perim_links) {
+    rc = scratch_get(SCRATCH_LINKS, (size_t)n_perim * 2 * sizeof(int64_t), &d_links);
+    if (rc != OFL_OK) return rc;
+  }
+  OFL_CUDA(cudaMemcpy2DAsync(d_fdr, ldi, fdr, ld_fdr, cols, rows, cudaMemcpyHostToDevice, st));
+  rc = launch_accumulation(static_cast<const uint8_t*>(d_fdr), rows, cols, ldi, static_cast<long long*>(d_fac), ldo,
+                           static_cast<long long*>(d_links), workspace, workspace_bytes, st);
+  if (rc != OFL_OK) return rc;
+  OFL_CUDA(cudaMemcpy2DAsync(fac, ld_fac * sizeof(int64_t), d_fac, ldo * sizeof(int64_t), cols * sizeof(int64_t), rows,
+                             cudaMemcpyDeviceToHost, st));
+  if (perim_links)
+    OFL_CUDA(cudaMemcpyAsync(perim_links, d_links, (size_t)n_perim * 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  OFL_CUDA(cudaStreamSynchronize(st));
+  return OFL_OK;
+}
+
+int ofl_check_accumulation_u8(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, const int64_t* fac,
+                              int64_t ld_fac, int64_t* n_bad, int mem_kind, void* stream) {
+  OFL_REQUIRE(rows >= 0 && cols >= 0 && n_bad != nullptr, OFL_ERR_INVALID, "bad argument");
+  OFL_REQUIRE(mem_kind == OFL_MEM_HOST || mem_kind == OFL_MEM_DEVICE, OFL_ERR_INVALID, "unknown mem_kind %d", mem_kind);
+  *n_bad = 0;
+  if (rows == 0 || cols == 0) return OFL_OK;
+  OFL_REQUIRE(fdr != nullptr && fac != nullptr, OFL_ERR_INVALID, "null raster pointer");
+  int rc = ensure_init();
+  if (rc != OFL_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void* d_cnt = nullptr;
+  rc = scratch_get(SCRATCH_MISC, 256, &d_cnt);
+  if (rc != OFL_OK) return rc;
+  const uint8_t* dfdr = fdr;
+  const long long* dfac = reinterpret_cast<const long long*>(fac);
+  int64_t ldi = ld_fdr, ldo = ld_fac;
+  if (mem_kind == OFL_MEM_HOST) {
+    void *b0 = nullptr, *b1 = nullptr;
+    ldi = round_up(cols, 16);
+    ldo = cols;
+    rc = scratch_get(SCRATCH_FDR, (size_t)rows * ldi, &b0);
+    if (rc != OFL_OK) return rc;
+    rc = scratch_get(SCRATCH_FAC, (size_t)rows * ldo * sizeof(int64_t), &b1);
+    if (rc != OFL_OK) return rc;
+    OFL_CUDA(cudaMemcpy2DAsync(b0, ldi, fdr, ld_fdr, cols, rows, cudaMemcpyHostToDevice, st));
+    OFL_CUDA(cudaMemcpy2DAsync(b1, ldo * sizeof(int64_t), fac, ld_fac * sizeof(int64_t), cols * sizeof(int64_t), rows,
+                               cudaMemcpyHostToDevice, st));
+    dfdr = static_cast<const uint8_t*>(b0);
+    dfac = static_cast<const long long*>(b1);
+  }
+  rc = launch_check(dfdr, rows, cols, ldi, dfac, ldo, static_cast<unsigned long long*>(d_cnt), st);
+  if (rc != OFL_OK) return rc;
+  unsigned long long h = 0;
+  OFL_CUDA(cudaMemcpyAsync(&h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, st));
+  OFL_CUDA(cudaStreamSynchronize(st));
+  *n_bad = (int64_t)h;
+  return OFL_OK;
+}
+
+int ofl_synth_dem_f32(float* dem, int64_t rows, int64_t cols, int64_t ld_dem, int64_t row0, int64_t total_rows,
+                      uint64_t seed, int kind, float relief, int holes_permille, float nodata, void* stream) {
+  OFL_REQUIRE(rows >= 0 && cols >= 0 && ld_dem >= cols, OFL_ERR_INVALID, "bad raster size");
+  OFL_REQUIRE(dem != nullptr || rows * cols == 0, OFL_ERR_INVALID, "null raster pointer");
+  OFL_REQUIRE(kind >= 0 && kind <= 2, OFL_ERR_INVALID, "unknown synthetic DEM kind %d", kind);
+  int rc = ensure_init();
+  if (rc != OFL_OK) return rc;
+  return launch_synth(dem, rows, cols, ld_dem, row0, total_rows, seed, kind, relief, holes_permille, nodata,
+                      static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+// common.cuh -- shared host/device helpers for liboverflow_b200 (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/overflow_b200.h"
+
+namespace ofl {
+
+// ---------------------------------------------------------------- error handling
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+void count_launch(int n = 1);
+
+#define OFL_CUDA(expr)                                                        \
+  do {                                                                        \
+    cudaError_t _e = (expr);                                                  \
+    if (_e != cudaSuccess) return ::ofl::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define OFL_CHECK_LAUNCH()                                                    \
+  do {                                                                        \
+    ::ofl::count_launch();                                                    \
+    cudaError_t _e = cudaGetLastError();                                      \
+    if (_e != cudaSuccess) return ::ofl::cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+
+#define OFL_REQUIRE(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      ::ofl::set_error(__VA_ARGS__);  \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+// ---------------------------------------------------------------- device properties / scratch
+int sm_count();
+
+// Library-owned device scratch, grown on demand and kept until ofl_shutdown (slot-indexed).
+enum ScratchSlot { SCRATCH_DEM = 0, SCRATCH_FDR, SCRATCH_FAC, SCRATCH_WORK, SCRATCH_LINKS, SCRATCH_MISC, SCRATCH_SLOTS };
+int scratch_get(int slot, size_t bytes, void** out);
+// Pinned host scratch (slot-indexed) for small read-backs.
+int pinned_get(size_t bytes, void** out);
+
+// ---------------------------------------------------------------- TMA tensor maps (host)
+// 2-D row-major tensor, element size `esz`, `cols` x `rows`, row pitch in bytes, box_w x box_h tile.
+int make_tensor_map_2d(CUtensorMap* tm, const void* base, int esz, uint64_t cols, uint64_t rows,
+                       uint64_t pitch_bytes, uint32_t box_w, uint32_t box_h);
+
+// ---------------------------------------------------------------- device-side PTX wrappers
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+// TMA 2-D tile load global -> shared, completion signalled on an mbarrier (tx bytes).
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(tm), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+#endif  // __CUDACC__
+
+}  // namespace ofl

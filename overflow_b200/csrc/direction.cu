@@ -1,0 +1,355 @@
+// direction.cu -- D8 steepest-descent flow direction for sm_100a.
+//
+// Replaces flow_direction_for_tile + calculate_slope
+// (reference src/overflow/flow_direction.py:14-96).
+//
+// Layout.  The raster is cut into column bands of 128 cells and row chunks of
+// `chunk_rows`; one warp owns one (band, chunk) work item at a time and streams
+// down its rows.  Each warp runs a private TMA pipeline: lane 0 issues
+// cp.async.bulk.tensor.2d loads of [8 rows x 136 floats] boxes (the band plus a
+// 4-float apron each side, so every lane's float4 stays 16-byte aligned) into a
+// ring of shared-memory stages guarded by mbarriers; out-of-raster box elements
+// are zero-filled by TMA and replaced in registers by the nodata fill.  A lane
+// owns 4 adjacent cells.  Per new input row it forms the 19 float32 differences
+// its cells share with their south / south-east / south-west / east neighbours
+// once (a - b == -(b - a) exactly in IEEE arithmetic), so every cell costs
+// 4.75 subtractions instead of 8, and writes its four uint8 codes as one 32-bit
+// store: a warp stores one full 128-byte line per output row.
+//
+// Arithmetic (bit-exact with the reference).  The reference subtracts in
+// float32, divides diagonals by sqrt(2) in float64 and keeps the first strict
+// maximum in scan order E,NE,N,NW,W,SW,S,SE; a nodata neighbour is slope +inf.
+//  * nodata inputs are rewritten to -inf on load, so (z - n) is +inf for them;
+//  * within the four cardinals (or the four diagonals) the float64 slopes order
+//    exactly like the float32 differences (division by a positive constant is
+//    monotone and injective on float32 inputs), so each class maximum and its
+//    first index come from float32 max / compares;
+//  * cardinal best c against diagonal best d: the float64 test d/sqrt(2) > c is
+//    decided by u = fma(d, 1/sqrt(2), -c) whenever |u| > 2^-21 |d| (the float32
+//    evaluation error is below 2^-23 |d|); an exact tie d/sqrt(2) == c cannot
+//    happen for finite non-zero float32 inputs (sqrt(2) is irrational and the
+//    float64 constant is 2^-53-close to it);
+//  * everything else -- a +inf maximum (nodata neighbour), a non-finite centre,
+//    NaNs, or |u| inside the guard band -- takes d8_exact(), which re-reads the
+//    3x3 window from shared memory and runs the reference algorithm literally in
+//    float64.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ofl {
+
+constexpr int DIR_RB = 8;        // rows per TMA box / pipeline stage
+constexpr int DIR_STAGES = 4;    // stages per warp
+constexpr int DIR_BOXW = 136;    // 4 apron + 128 band + 4 apron floats
+constexpr int DIR_BAND = 128;    // columns per warp band
+constexpr int DIR_WARPS = 4;     // warps per CTA
+constexpr int DIR_STAGE_FLOATS = DIR_RB * DIR_BOXW;
+constexpr uint32_t DIR_STAGE_BYTES = DIR_STAGE_FLOATS * 4;
+constexpr size_t DIR_SMEM_BYTES = size_t(DIR_WARPS) * DIR_STAGES * DIR_STAGE_BYTES + DIR_WARPS * DIR_STAGES * 8;
+
+struct DirParams {
+  uint8_t* out;
+  int64_t ld_out;
+  int H, W;        // output rows / cols
+  int y_off;       // input row of output row y is y + y_off
+  int in_rows;     // rows of the input tensor
+  float nd;        // float32 nodata value, NaN when no float32 can equal the band nodata
+  float fillv;     // what a cell outside the input array reads as (already nodata-transformed)
+  float fill_raw;  // same, before the nodata transform (for the exact path)
+  int n_bands, n_chunks, chunk_rows;
+};
+
+// The reference algorithm, literally, on one 3x3 window (flow_direction.py:49-67, :91-96).
+// n[] is in scan order E,NE,N,NW,W,SW,S,SE.
+__device__ __noinline__ uint32_t d8_exact(float z, const float* n, float nd) {
+  if (z == nd) return OFL_DIR_NODATA;
+  float d[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d[i] = (n[i] == nd) ? INFINITY : __fsub_rn(z, n[i]);
+  // a +inf slope is maximal and the first one in scan order wins; division keeps +inf
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (d[i] == INFINITY) return i;
+  double best = -INFINITY;
+  int bi = -1;
+  bool any_pos = false;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    double s = (i & 1) ? __ddiv_rn((double)d[i], 1.4142135623730951) : (double)d[i];
+    if (s > best) {
+      best = s;
+      bi = i;
+    }
+    if (s > 0.0) any_pos = true;
+  }
+  return any_pos ? (uint32_t)bi : (uint32_t)OFL_DIR_UNDEFINED;
+}
+
+// Fast path for one cell.  Differences are (centre - neighbour) in float32.
+// Returns the code; sets `special` when the exact path must decide instead.
+__device__ __forceinline__ uint32_t d8_fast(float dE, float dNE, float dN, float dNW, float dW, float dSW,
+                                            float dS, float dSE, bool& special) {
+  // fmaxf ignores NaN operands, like the reference's `slope > max_slope` scan
+  const float c = fmaxf(fmaxf(dE, dN), fmaxf(dW, dS));
+  const float d = fmaxf(fmaxf(dNE, dNW), fmaxf(dSW, dSE));
+  const int ic = (dE == c) ? 0 : (dN == c) ? 2 : (dW == c) ? 4 : 6;
+  const int id = (dNE == d) ? 1 : (dNW == d) ? 3 : (dSW == d) ? 5 : 7;
+  const float m = fmaxf(c, d);
+  const float u = __fmaf_rn(d, 0.70710678118654752f, -c);
+  const float thr = fabsf(d) * 4.76837158203125e-07f;  // 2^-21
+  const bool decided = fabsf(u) > thr;
+  const bool pos = m > 0.0f;
+  uint32_t code = (u > 0.0f) ? id : ic;
+  code = pos ? code : (uint32_t)OFL_DIR_UNDEFINED;
+  special = !(fabsf(m) < INFINITY) || (pos && !decided);
+  return code;
+}
+
+__global__ void __launch_bounds__(DIR_WARPS * 32) direction_kernel(const __grid_constant__ CUtensorMap tm,
+                                                                    const DirParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* tiles = reinterpret_cast<float*>(smem_raw) + warp * (DIR_STAGES * DIR_STAGE_FLOATS);
+  uint64_t* bars =
+      reinterpret_cast<uint64_t*>(smem_raw + size_t(DIR_WARPS) * DIR_STAGES * DIR_STAGE_BYTES) + warp * DIR_STAGES;
+  if (lane == 0) {
+    tma_prefetch_desc(&tm);
+#pragma unroll
+    for (int s = 0; s < DIR_STAGES; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+
+  const float nd = p.nd;
+  const float NINF = -INFINITY;
+  const int gwarp = blockIdx.x * DIR_WARPS + warp;
+  const int nwarps = gridDim.x * DIR_WARPS;
+  const int n_items = p.n_bands * p.n_chunks;
+  uint32_t g0 = 0;  // boxes this warp has consumed so far (stage = g % STAGES, parity = (g / STAGES) & 1)
+
+  for (int item = gwarp; item < n_items; item += nwarps) {
+    const int chunk = item / p.n_bands;
+    const int band = item - chunk * p.n_bands;
+    const int x0 = band * DIR_BAND;
+    const int y0 = chunk * p.chunk_rows;
+    const int y1 = min(y0 + p.chunk_rows, p.H);
+    const int iy0 = y0 + p.y_off - 1;  // first input row this item reads
+    const int n_in = (y1 - y0) + 2;
+    const int nblk = (n_in + DIR_RB - 1) / DIR_RB;
+    const int xl = x0 + 4 * lane;  // first of this lane's 4 columns
+    const bool edge_band = (x0 == 0) || (x0 + DIR_BAND + 1 > p.W);
+
+    // A box may be refilled only after the NEXT box has been consumed (the exact path re-reads up to
+    // two rows back), so STAGES-1 boxes are in flight.
+    if (lane == 0) {
+      const int pre = min(DIR_STAGES - 1, nblk);
+      for (int k = 0; k < pre; ++k) {
+        const uint32_t s = (g0 + k) % DIR_STAGES;
+        mbar_arrive_expect_tx(&bars[s], DIR_STAGE_BYTES);
+        tma_load_2d(tiles + s * DIR_STAGE_FLOATS, &tm, x0 - 4, iy0 + k * DIR_RB, &bars[s]);
+      }
+    }
+
+    // raw window read for the exact path: rel = row relative to iy0, cx = absolute column
+    auto raw_at = [&](int rel, int cx) -> float {
+      const int iy = iy0 + rel;
+      if (iy < 0 || iy >= p.in_rows || cx < 0 || cx >= p.W) return p.fill_raw;
+      const uint32_t s = (g0 + rel / DIR_RB) % DIR_STAGES;
+      return tiles[s * DIR_STAGE_FLOATS + (rel % DIR_RB) * DIR_BOXW + (cx - x0 + 4)];
+    };
+
+    // rolling state: centre row b (cols -1..4) and the differences carried from the row above
+    float b[6];
+    float nS[4], nSE[5], nSW[5];  // carried: (row above) - (centre row) pairs
+#pragma unroll
+    for (int j = 0; j < 6; ++j) b[j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) nS[j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) nSE[j] = nSW[j] = 0.f;
+
+    for (int k = 0; k < nblk; ++k) {
+      const uint32_t s = (g0 + k) % DIR_STAGES;
+      mbar_wait(&bars[s], ((g0 + k) / DIR_STAGES) & 1);
+      const float* t = tiles + s * DIR_STAGE_FLOATS + 4 * lane;
+#pragma unroll
+      for (int rr = 0; rr < DIR_RB; ++rr) {
+        const int i = k * DIR_RB + rr;
+        if (i >= n_in) break;
+        const int iy = iy0 + i;
+        // ---- load the new row (cols -1..4 of this lane), patch out-of-array cells, nodata -> -inf
+        float c[6];
+        {
+          const float4 v = *reinterpret_cast<const float4*>(t + rr * DIR_BOXW + 4);
+          c[0] = t[rr * DIR_BOXW + 3];
+          c[1] = v.x;
+          c[2] = v.y;
+          c[3] = v.z;
+          c[4] = v.w;
+          c[5] = t[rr * DIR_BOXW + 8];
+        }
+        if (iy < 0 || iy >= p.in_rows) {
+#pragma unroll
+          for (int j = 0; j < 6; ++j) c[j] = p.fillv;
+        } else if (edge_band) {
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            const int cx = xl - 1 + j;
+            if (cx < 0 || cx >= p.W) c[j] = p.fillv;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) c[j] = (c[j] == nd) ? NINF : c[j];
+
+        if (i >= 1) {
+          // ---- differences between centre row b and the new row c (shared by both rows)
+          float vS[4], pSE[5], pSW[5];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) vS[j] = __fsub_rn(b[j + 1], c[j + 1]);  // cell j -> S
+#pragma unroll
+          for (int j = 0; j < 5; ++j) pSE[j] = __fsub_rn(b[j], c[j + 1]);  // cell j-1 -> SE
+#pragma unroll
+          for (int j = 0; j < 5; ++j) pSW[j] = __fsub_rn(b[j + 1], c[j]);  // cell j -> SW
+          if (i >= 2) {
+            const int y = y0 + i - 2;
+            float hE[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) hE[j] = __fsub_rn(b[j], b[j + 1]);  // cell j-1 -> E
+            uint32_t packed = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              bool special;
+              uint32_t code = d8_fast(/*E*/ hE[j + 1], /*NE*/ -nSW[j + 1], /*N*/ -nS[j], /*NW*/ -nSE[j],
+                                      /*W*/ -hE[j], /*SW*/ pSW[j], /*S*/ vS[j], /*SE*/ pSE[j + 1], special);
+              if (special) {
+                const int cx = xl + j;
+                float n[8];
+                n[0] = raw_at(i - 1, cx + 1);
+                n[1] = raw_at(i - 2, cx + 1);
+                n[2] = raw_at(i - 2, cx);
+                n[3] = raw_at(i - 2, cx - 1);
+                n[4] = raw_at(i - 1, cx - 1);
+                n[5] = raw_at(i, cx - 1);
+                n[6] = raw_at(i, cx);
+                n[7] = raw_at(i, cx + 1);
+                code = d8_exact(raw_at(i - 1, cx), n, nd);
+              }
+              packed |= code << (8 * j);
+            }
+            uint8_t* orow = p.out + (int64_t)y * p.ld_out + xl;
+            if (xl + 3 < p.W) {
+              *reinterpret_cast<uint32_t*>(orow) = packed;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (xl + j < p.W) orow[j] = (uint8_t)(packed >> (8 * j));
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) nS[j] = vS[j];
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            nSE[j] = pSE[j];
+            nSW[j] = pSW[j];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) b[j] = c[j];
+      }
+      __syncwarp();
+      // box k-1 is no longer needed by the exact path: its stage takes box k+STAGES-1
+      if (lane == 0 && (k + DIR_STAGES - 1) < nblk) {
+        const int kn = k + DIR_STAGES - 1;
+        const uint32_t sn = (g0 + kn) % DIR_STAGES;
+        mbar_arrive_expect_tx(&bars[sn], DIR_STAGE_BYTES);
+        tma_load_2d(tiles + sn * DIR_STAGE_FLOATS, &tm, x0 - 4, iy0 + kn * DIR_RB, &bars[sn]);
+      }
+    }
+    g0 += nblk;
+    __syncwarp();
+  }
+}
+
+__global__ void fill_border_kernel(uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld, uint8_t value) {
+  const int64_t n = 2 * (rows + cols);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r, c;
+    if (i < cols) {
+      r = 0;
+      c = i;
+    } else if (i < 2 * cols) {
+      r = rows - 1;
+      c = i - cols;
+    } else if (i < 2 * cols + rows) {
+      r = i - 2 * cols;
+      c = 0;
+    } else {
+      r = i - 2 * cols - rows;
+      c = cols - 1;
+    }
+    fdr[r * ld + c] = value;
+  }
+}
+
+int launch_fill_border(uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld, int value, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return OFL_OK;
+  const int64_t n = 2 * (rows + cols);
+  const int blocks = (int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024);
+  fill_border_kernel<<<blocks, 256, 0, st>>>(fdr, rows, cols, ld, (uint8_t)value);
+  OFL_CHECK_LAUNCH();
+  return OFL_OK;
+}
+
+// Device-pointer launcher.  `dem` has in_rows x cols floats; `fdr` has rows x cols codes;
+// input row of output row y is y + y_off (0 for raster mode, 1 for a strip with halo rows).
+int launch_direction(const float* dem, int64_t in_rows, int64_t cols, int64_t ld_dem, double nodata, uint8_t* fdr,
+                     int64_t rows, int64_t ld_fdr, int y_off, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return OFL_OK;
+  OFL_REQUIRE(rows < (1ll << 30) && cols < (1ll << 30) && in_rows < (1ll << 30), OFL_ERR_INVALID,
+              "raster dimension too large");
+  OFL_REQUIRE((reinterpret_cast<uintptr_t>(dem) & 15) == 0 && (ld_dem % 4) == 0 && ld_dem >= cols,
+              OFL_ERR_ALIGNMENT, "dem must be 16-byte aligned with ld_dem %% 4 == 0 (ld_dem=%lld)", (long long)ld_dem);
+  OFL_REQUIRE((reinterpret_cast<uintptr_t>(fdr) & 3) == 0 && (ld_fdr % 4) == 0 && ld_fdr >= cols, OFL_ERR_ALIGNMENT,
+              "fdr must be 4-byte aligned with ld_fdr %% 4 == 0 (ld_fdr=%lld)", (long long)ld_fdr);
+  CUtensorMap tm;
+  int rc = make_tensor_map_2d(&tm, dem, 4, (uint64_t)cols, (uint64_t)in_rows, (uint64_t)ld_dem * 4, DIR_BOXW, DIR_RB);
+  if (rc != OFL_OK) return rc;
+
+  DirParams p;
+  p.out = fdr;
+  p.ld_out = ld_fdr;
+  p.H = (int)rows;
+  p.W = (int)cols;
+  p.y_off = y_off;
+  p.in_rows = (int)in_rows;
+  const float nd32 = (float)nodata;
+  const bool representable = ((double)nd32 == nodata);  // false for NaN and for values float32 cannot hold
+  p.nd = representable ? nd32 : NAN;
+  p.fill_raw = nd32;  // util/raster.py:67 fills the out-of-raster halo with nodata cast to the band dtype
+  p.fillv = representable ? -INFINITY : nd32;
+  p.n_bands = (int)((cols + DIR_BAND - 1) / DIR_BAND);
+  // rows per work item: long enough to amortise the 2-row prologue, short enough to balance the grid
+  const int sms = sm_count();
+  int chunk_rows = 512;
+  while (chunk_rows > 32 && (int64_t)p.n_bands * ((rows + chunk_rows - 1) / chunk_rows) < (int64_t)sms * 3 * DIR_WARPS * 4)
+    chunk_rows >>= 1;
+  p.chunk_rows = chunk_rows;
+  p.n_chunks = (int)((rows + chunk_rows - 1) / chunk_rows);
+  const int64_t n_items = (int64_t)p.n_bands * p.n_chunks;
+  OFL_REQUIRE(n_items < (1ll << 31), OFL_ERR_INVALID, "too many work items");
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    OFL_CUDA(cudaFuncSetAttribute(direction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIR_SMEM_BYTES));
+    attr_set = true;
+  }
+  int ctas = (int)((n_items + DIR_WARPS - 1) / DIR_WARPS);
+  const int max_ctas = sms * 3;
+  if (ctas > max_ctas) ctas = max_ctas;
+  direction_kernel<<<ctas, DIR_WARPS * 32, DIR_SMEM_BYTES, st>>>(tm, p);
+  OFL_CHECK_LAUNCH();
+  return OFL_OK;
+}
+
+}  // namespace ofl

@@ -1,0 +1,166 @@
+// runtime.cu -- library state: error strings, device scratch, tensor-map encoding.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace ofl {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+const char* last_error() { return g_err; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  return e == cudaErrorMemoryAllocation ? OFL_ERR_NOMEM : OFL_ERR_CUDA;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int64_t launch_count() { return g_launches.load(); }
+void launch_count_reset() { g_launches.store(0); }
+
+// ---------------------------------------------------------------- device state
+struct State {
+  int device = -1;
+  int sms = 0;
+  void* scratch[SCRATCH_SLOTS] = {};
+  size_t scratch_bytes[SCRATCH_SLOTS] = {};
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+};
+static State g_state;
+static std::mutex g_mu;
+
+int init_device(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error("no usable CUDA device (%s); liboverflow_b200 has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return OFL_ERR_CUDA;
+  }
+  OFL_REQUIRE(device >= 0 && device < n, OFL_ERR_INVALID, "device %d out of range (have %d)", device, n);
+  OFL_CUDA(cudaSetDevice(device));
+  if (g_state.device != device) {
+    cudaDeviceProp prop;
+    OFL_CUDA(cudaGetDeviceProperties(&prop, device));
+    OFL_REQUIRE(prop.major >= 10, OFL_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                prop.major, prop.minor);
+    for (int i = 0; i < SCRATCH_SLOTS; ++i) {
+      if (g_state.scratch[i]) cudaFree(g_state.scratch[i]);
+      g_state.scratch[i] = nullptr;
+      g_state.scratch_bytes[i] = 0;
+    }
+    g_state.device = device;
+    g_state.sms = prop.multiProcessorCount;
+  }
+  return OFL_OK;
+}
+
+int ensure_init() {
+  if (g_state.device >= 0) return OFL_OK;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) dev = 0;
+  return init_device(dev);
+}
+
+int shutdown() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (int i = 0; i < SCRATCH_SLOTS; ++i) {
+    if (g_state.scratch[i]) cudaFree(g_state.scratch[i]);
+    g_state.scratch[i] = nullptr;
+    g_state.scratch_bytes[i] = 0;
+  }
+  if (g_state.pinned) cudaFreeHost(g_state.pinned);
+  g_state.pinned = nullptr;
+  g_state.pinned_bytes = 0;
+  return OFL_OK;
+}
+
+int sm_count() { return g_state.sms > 0 ? g_state.sms : 148; }
+
+int scratch_get(int slot, size_t bytes, void** out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (bytes == 0) bytes = 256;
+  if (g_state.scratch_bytes[slot] < bytes) {
+    if (g_state.scratch[slot]) cudaFree(g_state.scratch[slot]);
+    g_state.scratch[slot] = nullptr;
+    g_state.scratch_bytes[slot] = 0;
+    cudaError_t e = cudaMalloc(&g_state.scratch[slot], bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)", __FILE__, __LINE__);
+    g_state.scratch_bytes[slot] = bytes;
+  }
+  *out = g_state.scratch[slot];
+  return OFL_OK;
+}
+
+int pinned_get(size_t bytes, void** out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_state.pinned_bytes < bytes) {
+    if (g_state.pinned) cudaFreeHost(g_state.pinned);
+    g_state.pinned = nullptr;
+    g_state.pinned_bytes = 0;
+    cudaError_t e = cudaMallocHost(&g_state.pinned, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__);
+    g_state.pinned_bytes = bytes;
+  }
+  *out = g_state.pinned;
+  return OFL_OK;
+}
+
+// ---------------------------------------------------------------- tensor maps
+// cuTensorMapEncodeTiled is a driver API; it is resolved through the runtime so the library
+// needs no link-time dependency on libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tensor_map_2d(CUtensorMap* tm, const void* base, int esz, uint64_t cols, uint64_t rows, uint64_t pitch_bytes,
+                       uint32_t box_w, uint32_t box_h) {
+  EncodeTiledFn fn = get_encode_fn();
+  OFL_REQUIRE(fn != nullptr, OFL_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  CUtensorMapDataType dt;
+  switch (esz) {
+    case 1: dt = CU_TENSOR_MAP_DATA_TYPE_UINT8; break;
+    case 4: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; break;
+    case 8: dt = CU_TENSOR_MAP_DATA_TYPE_UINT64; break;
+    default: set_error("unsupported tensor-map element size %d", esz); return OFL_ERR_INVALID;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_w, box_h};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  OFL_REQUIRE(r == CUDA_SUCCESS, OFL_ERR_CUDA,
+              "cuTensorMapEncodeTiled failed (%d) for %llux%llu esz=%d pitch=%llu box=%ux%u", (int)r,
+              (unsigned long long)cols, (unsigned long long)rows, esz, (unsigned long long)pitch_bytes, box_w, box_h);
+  return OFL_OK;
+}
+
+}  // namespace ofl

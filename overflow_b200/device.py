@@ -1,0 +1,113 @@
+"""Device-resident entry points: torch CUDA tensors in, torch CUDA tensors out.
+
+PyTorch is only the owner of device memory and streams here; every kernel is in
+liboverflow_b200.  Calls are enqueued on torch's current stream.
+"""
+import ctypes
+
+import torch
+
+from . import _native
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _init_for(t: torch.Tensor):
+    if not t.is_cuda:
+        raise ValueError("expected a CUDA tensor (there is no CPU fallback)")
+    _native.init(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def synth_dem(rows, cols, *, row0=0, total_rows=None, seed=0, kind=0, relief=1000.0, holes_permille=0,
+              nodata=-9999.0, device="cuda"):
+    """Seeded synthetic float32 DEM generated on the device (kind 0 fractal, 1 terraces, 2 tilted plane).
+
+    Rows row0..row0+rows-1 of a raster with `total_rows` rows; rows outside [0,total_rows) are nodata
+    (that is what a strip's halo row is at the raster top / bottom).
+    """
+    total_rows = rows if total_rows is None else total_rows
+    dem = torch.empty((rows, cols), dtype=torch.float32, device=device)
+    _init_for(dem)
+    _native.check(
+        _native.lib().ofl_synth_dem_f32(
+            dem.data_ptr(), rows, cols, dem.stride(0), row0, total_rows, seed, kind, relief, holes_permille, nodata,
+            _stream(),
+        )
+    )
+    return dem
+
+
+def flow_direction(dem: torch.Tensor, nodata_value: float, *, mode="raster", out=None) -> torch.Tensor:
+    """uint8 D8 codes of a float32 CUDA raster.
+
+    mode "raster": whole raster, out-of-raster neighbours are nodata.
+    mode "tile":   flow_direction_for_tile semantics (dem carries its ring; ring of the result is 9).
+    mode "strip":  dem has 2 more rows than the result: halo rows above and below.
+    """
+    if dem.dtype != torch.float32 or dem.dim() != 2 or dem.stride(1) != 1:
+        raise ValueError("dem must be a 2-D float32 tensor with unit column stride")
+    _init_for(dem)
+    m = {"tile": _native.OFL_DIR_MODE_TILE, "raster": _native.OFL_DIR_MODE_RASTER, "strip": _native.OFL_DIR_MODE_STRIP}[mode]
+    rows, cols = dem.shape
+    if m == _native.OFL_DIR_MODE_STRIP:
+        rows -= 2
+    if out is None:
+        out = torch.empty((rows, cols), dtype=torch.uint8, device=dem.device)
+    elif out.dtype != torch.uint8 or tuple(out.shape) != (rows, cols) or out.stride(1) != 1:
+        raise ValueError("out must be a uint8 tensor of the result shape")
+    _native.check(
+        _native.lib().ofl_flow_direction_f32(
+            dem.data_ptr(), rows, cols, dem.stride(0), float(nodata_value), out.data_ptr(), out.stride(0), m,
+            _native.OFL_MEM_DEVICE, _stream(),
+        )
+    )
+    return out
+
+
+def accumulation_workspace(rows, cols, device="cuda") -> torch.Tensor:
+    n = int(_native.lib().ofl_accumulation_workspace_bytes(rows, cols))
+    return torch.empty((n,), dtype=torch.uint8, device=device)
+
+
+def flow_accumulation(fdr: torch.Tensor, *, out=None, workspace=None, with_links=False):
+    """int64 upstream-cell counts of a uint8 CUDA flow-direction raster.
+
+    Returns fac, or (fac, perim_links[n,2]) in perimeter_indices order when with_links.
+    Synchronises the stream (the perimeter-graph solve reports convergence to the host).
+    """
+    if fdr.dtype != torch.uint8 or fdr.dim() != 2 or fdr.stride(1) != 1:
+        raise ValueError("fdr must be a 2-D uint8 tensor with unit column stride")
+    _init_for(fdr)
+    rows, cols = fdr.shape
+    if out is None:
+        out = torch.empty((rows, cols), dtype=torch.int64, device=fdr.device)
+    if workspace is None:
+        workspace = accumulation_workspace(rows, cols, fdr.device)
+    links = None
+    if with_links:
+        n = int(_native.lib().ofl_perimeter_count(rows, cols))
+        links = torch.empty((n, 2), dtype=torch.int64, device=fdr.device)
+    _native.check(
+        _native.lib().ofl_flow_accumulation_u8(
+            fdr.data_ptr(), rows, cols, fdr.stride(0), out.data_ptr(), out.stride(0),
+            links.data_ptr() if with_links else None, workspace.data_ptr(), workspace.numel(),
+            _native.OFL_MEM_DEVICE, _stream(),
+        )
+    )
+    return (out, links) if with_links else out
+
+
+def check_accumulation(fdr: torch.Tensor, fac: torch.Tensor) -> int:
+    """Number of cells violating the accumulation recurrence (0 proves fac exact on an acyclic raster)."""
+    _init_for(fdr)
+    rows, cols = fdr.shape
+    n_bad = ctypes.c_int64(0)
+    _native.check(
+        _native.lib().ofl_check_accumulation_u8(
+            fdr.data_ptr(), rows, cols, fdr.stride(0), fac.data_ptr(), fac.stride(0), ctypes.byref(n_bad),
+            _native.OFL_MEM_DEVICE, _stream(),
+        )
+    )
+    return int(n_bad.value)

@@ -1,0 +1,105 @@
+"""D8 flow direction -- host-side mirror of the reference's src/overflow/flow_direction.py.
+
+`flow_direction_for_tile` (reference :14-69) and `flow_direction` (reference :99-124) keep
+their signatures; the stencil runs in liboverflow_b200 (csrc/direction.cu).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _native
+from .constants import FLOW_DIRECTION_NODATA
+
+# dtypes whose pairwise differences are exact in float32 (|a-b| < 2**24), so the float32
+# kernel reproduces the reference's integer subtraction bit for bit
+_EXACT_IN_F32 = (np.uint8, np.int8, np.uint16, np.int16)
+
+
+def _as_f32(dem: np.ndarray) -> np.ndarray:
+    if dem.dtype == np.float32:
+        return dem
+    if dem.dtype in [np.dtype(t) for t in _EXACT_IN_F32]:
+        return dem.astype(np.float32)
+    raise TypeError(
+        f"flow_direction_for_tile: dtype {dem.dtype} is not supported by the CUDA path "
+        "(float32, or 8/16-bit integers which convert exactly)"
+    )
+
+
+def _stream_ptr(stream):
+    return ctypes.c_void_p(int(stream)) if stream else None
+
+
+def flow_direction_for_tile(dem: np.ndarray, nodata_value: float) -> np.ndarray:
+    """D8 codes for the interior of a DEM chunk that carries a one-cell ring.
+
+    Same contract as the reference (flow_direction.py:14-69): returns uint8 of dem.shape;
+    interior cells hold E=0..SE=7, 8 (no downhill neighbour) or 9 (nodata).  The ring, which
+    the reference leaves uninitialised, is set to 9.
+    """
+    dem = np.asarray(dem)
+    if dem.ndim != 2:
+        raise ValueError("dem must be a 2-D array")
+    src = np.ascontiguousarray(_as_f32(dem))
+    rows, cols = src.shape
+    out = np.empty((rows, cols), dtype=np.uint8)
+    if rows == 0 or cols == 0:
+        return out
+    lib = _native.lib()
+    _native.check(
+        lib.ofl_flow_direction_f32(
+            src.ctypes.data, rows, cols, cols, float(nodata_value), out.ctypes.data, cols,
+            _native.OFL_DIR_MODE_TILE, _native.OFL_MEM_HOST, None,
+        )
+    )
+    return out
+
+
+def flow_direction_for_raster(dem: np.ndarray, nodata_value: float) -> np.ndarray:
+    """Whole-raster D8 codes: every cell computed, out-of-raster neighbours read as nodata.
+
+    Equals what `flow_direction()` writes for the file (the chunk loop pads the raster edge
+    with the band nodata value, util/raster.py:67); no ring is needed or returned.
+    """
+    dem = np.asarray(dem)
+    if dem.ndim != 2:
+        raise ValueError("dem must be a 2-D array")
+    src = np.ascontiguousarray(_as_f32(dem))
+    rows, cols = src.shape
+    out = np.empty((rows, cols), dtype=np.uint8)
+    if rows == 0 or cols == 0:
+        return out
+    lib = _native.lib()
+    _native.check(
+        lib.ofl_flow_direction_f32(
+            src.ctypes.data, rows, cols, cols, float(nodata_value), out.ctypes.data, cols,
+            _native.OFL_DIR_MODE_RASTER, _native.OFL_MEM_HOST, None,
+        )
+    )
+    return out
+
+
+def flow_direction(input_path, output_path, chunk_size=4000):
+    """Generate a flow-direction GeoTIFF from a DEM file (reference flow_direction.py:99-124).
+
+    Band 1 of `input_path` is read; the output is a 1-band Byte GeoTIFF with the same
+    projection / geotransform and nodata 9.  `chunk_size` keeps its meaning as the I/O
+    granularity (rows are streamed in bands of chunk_size); the result does not depend on it.
+    """
+    from .util import raster as _raster
+
+    src = _raster.open_raster(input_path)
+    band = src.GetRasterBand(1)
+    nodata_value = band.GetNoDataValue()
+    dst = _raster.create_raster(
+        output_path, src.RasterXSize, src.RasterYSize, "Byte",
+        projection=src.GetProjection(), geotransform=src.GetGeoTransform(),
+    )
+    out_band = dst.GetRasterBand(1)
+    out_band.SetNoDataValue(FLOW_DIRECTION_NODATA)
+    for chunk in _raster.raster_chunker(band, chunk_size=chunk_size, chunk_buffer_size=1):
+        result = flow_direction_for_tile(chunk.data, nodata_value)
+        chunk.from_numpy(result)
+        chunk.write(out_band)
+    dst.FlushCache()
+    dst = None
