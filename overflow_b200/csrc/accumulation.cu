@@ -36,9 +36,9 @@ namespace ofl {
 
 constexpr int AT = 64;                 // tile side (cells)
 constexpr int AT_SHIFT = 6;
-constexpr int ACS_W = 80;              // code tile pitch: columns x0-8 .. x0+71 (TMA box inner = 80 B)
+constexpr int ACS_W = 96;              // code tile pitch: columns x0-16 .. x0+79 (TMA box inner = 96 B, 16-B aligned start)
 constexpr int ACS_H = AT + 2;          // rows y0-1 .. y0+64
-constexpr int ACS_X0 = 8;
+constexpr int ACS_X0 = 16;
 constexpr int ACS_Y0 = 1;
 constexpr uint32_t ACS_BYTES = ACS_W * ACS_H;
 constexpr int SLOTS = 4 * AT;          // perimeter slots per tile (top, bottom, left, right)

@@ -13,6 +13,7 @@ namespace ofl {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 void count_launch(int n = 1);
+bool debug_sync();  // OFL_DEBUG_SYNC=1: synchronise after every launch so faults name their kernel
 
 #define OFL_CUDA(expr)                                                        \
   do {                                                                        \
@@ -24,6 +25,7 @@ void count_launch(int n = 1);
   do {                                                                        \
     ::ofl::count_launch();                                                    \
     cudaError_t _e = cudaGetLastError();                                      \
+    if (_e == cudaSuccess && ::ofl::debug_sync()) _e = cudaDeviceSynchronize(); \
     if (_e != cudaSuccess) return ::ofl::cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
   } while (0)
 

@@ -1,5 +1,6 @@
 // runtime.cu -- library state: error strings, device scratch, tensor-map encoding.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -24,6 +25,15 @@ const char* last_error() { return g_err; }
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
   return e == cudaErrorMemoryAllocation ? OFL_ERR_NOMEM : OFL_ERR_CUDA;
+}
+
+bool debug_sync() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OFL_DEBUG_SYNC");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
