@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- D8 flow direction + flow accumulation throughput on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--size S]
+
+One step = one pass of the hot path (flow direction, then flow accumulation) over one synthetic
+float32 DEM.  N=1: the S x S raster (default 65536, BASELINE.json configs[2]) is resident in HBM
+and processed by one GPU.  N>1 (launched by torchrun, one rank per GPU): the same raster split into
+N row strips (strong scaling), halo rows and the strip-boundary graph exchanged over NCCL.
+`--impl reference` times the CPU oracle port (oracle/d8_oracle.c, the reference's algorithm in C)
+on the host cores on a bounded sample of the same DEM.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NODATA = -9999.0
+METRIC = "d8_flowdir_flowacc_throughput"
+UNIT = "Gcells/s"
+DIR_BYTES_PER_CELL = 5.0   # 4 B float32 read + 1 B code write            
+ACC_BYTES_PER_CELL = 9.0   # 1 B code read + 8 B int64 count write         
+PHASE_BYTES = {"direction": 5.0, "acc_tile_a": 1.0, "acc_tile_b": 9.0}
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_pass(oracle, dem_pad):
+    """Reference algorithm on the host: direction on all threads (prange), accumulation serial."""
+    t0 = time.perf_counter()
+    fdr = oracle.flow_direction_for_tile(dem_pad, NODATA)[1:-1, 1:-1]
+    t1 = time.perf_counter()
+    fac = oracle.flow_accumulation(fdr)
+    t2 = time.perf_counter()
+    return fdr, fac, t1 - t0, t2 - t1
+
+
+def sample_dem_host(args, sample):
+    """`sample` x `sample` window of the benchmark DEM (+ nodata ring), generated on the GPU when there
+    is one (same generator, same seed as the native arm), else the numpy fractal."""
+    import numpy as np
+
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            from overflow_b200 import device as dev
+
+            d = dev.synth_dem(sample, sample, row0=0, total_rows=args.size, seed=args.seed, kind=args.kind,
+                              holes_permille=args.holes)
+            h = d.cpu().numpy()
+            del d
+            out = np.full((sample + 2, sample + 2), NODATA, dtype=np.float32)
+            out[1:-1, 1:-1] = h
+            return out, "device generator window"
+    except Exception:
+        pass
+    from oracle import synth
+
+    return synth.pad_nodata(synth.fractal(sample, sample, beta=2.0, seed=args.seed)), "numpy fractal (no GPU)"
+
+
+def run_reference(args):
+    """--impl reference: the CPU port of the reference's path on the box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+
+    oracle.build()
+    sample = min(args.size, args.cpu_sample)
+    dem_pad, how = sample_dem_host(args, sample)
+    cells = sample * sample
+    for _ in range(args.warmup):
+        cpu_pass(oracle, dem_pad)
+    t0 = time.perf_counter()
+    td = ta = 0.0
+    for _ in range(args.steps):
+        _, _, a, b = cpu_pass(oracle, dem_pad)
+        td += a
+        ta += b
+    el = time.perf_counter() - t0
+    value = cells * args.steps / el / 1e9
+    sample_txt = (f"{sample}x{sample} window of the {args.size}x{args.size} DEM ({how}); direction on "
+                  f"{oracle.num_threads()} threads {td / args.steps * 1e3:.0f} ms, accumulation serial "
+                  f"{ta / args.steps * 1e3:.0f} ms per step")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32->u8->int64", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "sample": sample_txt},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n):
+    kinds = {0: "fractal value-noise", 1: "terraced fractal", 2: "tilted plane"}
+    return {
+        "workload": f"flow_direction + flow_accumulation on synthetic {args.size}x{args.size} float32 DEM "
+                    f"({kinds[args.kind]}, {args.holes} permille nodata holes, seed {args.seed})",
+        "rows": args.size, "cols": args.size, "partition": f"{n} row strip(s)",
+        "cache": "inputs (4 B/cell DEM) far exceed the 126 MB L2, no flush needed",
+    }
+
+
+def run_native(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from overflow_b200 import _native, device as dev
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torchrun (one rank per GPU)")
+    torch.cuda.set_device(local)
+    _native.init(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    S = args.size
+    peak, peak_src = measured_hbm_peak()
+
+    if world > 1:
+        from overflow_b200 import strips
+
+        runner = strips.StripPipeline(S, S, rank, world, nodata=NODATA, seed=args.seed, kind=args.kind,
+                                      holes_permille=args.holes)
+        step = runner.step
+        cells_total = S * S
+    else:
+        dem = dev.synth_dem(S, S, seed=args.seed, kind=args.kind, holes_permille=args.holes, nodata=NODATA)
+        fdr = torch.empty((S, S), dtype=torch.uint8, device="cuda")
+        fac = torch.empty((S, S), dtype=torch.int64, device="cuda")
+        ws = dev.accumulation_workspace(S, S)
+
+        def step():
+            dev.flow_direction(dem, NODATA, out=fdr)
+            dev.flow_accumulation(fdr, out=fac, workspace=ws)
+
+        cells_total = S * S
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    _native.phase_timing_read(reset=True)
+    _native.phase_timing_enable(True)
+    _native.launch_count_reset()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            step()
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _native.launch_count()
+    _native.phase_timing_enable(False)
+    phases = _native.phase_timing_read(reset=True)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    ms_per_step = ms / args.steps
+    value = cells_total / (ms_per_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (live CUDA-event times from the timed region, this rank)
+    cells_rank = cells_total // world
+    per_phase = {k: (v[0] / max(v[1], 1), v[1]) for k, v in phases.items()}
+    dom = max(PHASE_BYTES, key=lambda k: per_phase[k][0])
+    dom_ms = per_phase[dom][0]
+    achieved = cells_rank * PHASE_BYTES[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("rows") == S and tj.get("cols") == S and world == 1:
+            traffic = tj.get(dom)
+    except Exception:
+        pass
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": traffic, "peak_source": peak_src, "bytes_per_cell": PHASE_BYTES[dom],
+        "avg_launch_ms": dom_ms,
+        "phases_ms_per_launch": {k: round(v[0], 4) for k, v in per_phase.items()},
+        "phase_gbs": {k: (cells_rank * PHASE_BYTES[k] / (per_phase[k][0] * 1e-3) / 1e9 if per_phase[k][0] > 0 else None)
+                      for k in PHASE_BYTES},
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32->u8->int64", "data": "synthetic", "config": workload_config(args, world),
+        "clocks": clocks.summary(), "gpu_launches": launches, "roofline": roofline,
+    }
+
+    # ---- parity on the benchmarked result (outside the timed region)
+    if world == 1 and not args.no_check:
+        import oracle
+
+        bad = dev.check_accumulation(fdr, fac)
+        rng = np.random.default_rng(0)
+        wsz = min(512, S - 2)
+        dir_ok = True
+        for _ in range(4):
+            r, c = int(rng.integers(1, S - wsz - 1)), int(rng.integers(1, S - wsz - 1))
+            win = dem[r - 1 : r + wsz + 1, c - 1 : c + wsz + 1].cpu().numpy()
+            want = oracle.flow_direction_for_tile(win, NODATA)[1:-1, 1:-1]
+            dir_ok &= bool(np.array_equal(fdr[r : r + wsz, c : c + wsz].cpu().numpy(), want))
+        line["parity"] = {"accumulation_recurrence_violations": bad, "direction_windows_vs_oracle": dir_ok,
+                          "max_fac": int(fac.max().item())}
+
+    # ---- CPU baseline: the oracle port on a bounded sample of the same DEM (rank 0, N=1 only)
+    if world == 1 and not args.no_cpu:
+        import oracle
+
+        sample = min(S, args.cpu_sample)
+        dem_pad = np.full((sample + 2, sample + 2), NODATA, dtype=np.float32)
+        dem_pad[1:-1, 1:-1] = dem[:sample, :sample].cpu().numpy()
+        cpu_pass(oracle, dem_pad[:66, :66])  # warm-up (thread pool)
+        best = None
+        for _ in range(2):
+            _, _, td, ta = cpu_pass(oracle, dem_pad)
+            if best is None or td + ta < best[0] + best[1]:
+                best = (td, ta)
+        line["cpu_baseline"] = {
+            "value": sample * sample / (best[0] + best[1]) / 1e9, "unit": UNIT, "cores": oracle.num_threads(),
+            "kind": "port",
+            "sample": f"{sample}x{sample} window of the benchmark DEM; direction {best[0] * 1e3:.0f} ms on "
+                      f"{oracle.num_threads()} threads, accumulation {best[1] * 1e3:.0f} ms on 1 thread (serial algorithm)",
+        }
+
+    # ---- end to end through the public host API: pinned host buffers, H2D + D2H inside the timed region
+    if world == 1 and not args.no_e2e:
+        from overflow_b200.flow_accumulation import flow_accumulation_for_raster
+        from overflow_b200.flow_direction import flow_direction_for_raster
+
+        h_dem = torch.empty((S, S), dtype=torch.float32, pin_memory=True)
+        h_dem.copy_(dem)
+        del dem, fdr, fac, ws
+        torch.cuda.empty_cache()
+        h_fdr = torch.empty((S, S), dtype=torch.uint8, pin_memory=True)
+        h_fac = torch.empty((S, S), dtype=torch.int64, pin_memory=True)
+        n_dem, n_fdr, n_fac = h_dem.numpy(), h_fdr.numpy(), h_fac.numpy()
+
+        def e2e_step():
+            flow_direction_for_raster(n_dem, NODATA, out=n_fdr)
+            flow_accumulation_for_raster(n_fdr, out=n_fac)
+
+        e2e_step()  # warm-up: allocates the library's device staging
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        el = (time.perf_counter() - t0) / args.e2e_steps
+        line["e2e"] = {
+            "value": cells_total / el / 1e9, "unit": UNIT,
+            "h2d_bytes_per_step": int(cells_total * 4 + cells_total), "d2h_bytes_per_step": int(cells_total + cells_total * 8),
+            "ms_per_step": el * 1e3, "steps": args.e2e_steps,
+            "api": "flow_direction_for_raster + flow_accumulation_for_raster on pinned host arrays",
+        }
+    elif world > 1:
+        line["e2e"] = runner.e2e(args.e2e_steps) if hasattr(runner, "e2e") else None
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--size", type=int, default=65536)
+    ap.add_argument("--kind", type=int, default=0)
+    ap.add_argument("--holes", type=int, default=5, help="nodata holes, permille of the raster")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=8192)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -93,6 +93,17 @@ int64_t ofl_launch_count(void);
 void ofl_launch_count_reset(void);
 
 /*
+ * Per-phase device timing (benchmarks).  When enabled, each phase is bracketed by CUDA events on the
+ * launching stream.  ofl_phase_timing_read waits for the recorded events, adds them to per-phase
+ * totals and copies up to n totals (milliseconds) and launch counts out; returns the number of phases:
+ *   0 direction kernel   1 accumulation tile pass A   2 perimeter-graph solve
+ *   3 accumulation tile pass B   4 perimeter links
+ */
+#define OFL_PHASE_COUNT 5
+void ofl_phase_timing_enable(int on);
+int ofl_phase_timing_read(double* ms, int64_t* counts, int n, int reset);
+
+/*
  * D8 steepest-descent flow direction.
  *   dem      float32, `rows` x `cols` (STRIP mode: rows+2 x cols), leading dimension ld_dem
  *   nodata   the band nodata value as a double; a cell is nodata iff (double)cell == nodata

@@ -37,6 +37,8 @@ SIGNATURES = {
     "ofl_shutdown": (_int, []),
     "ofl_launch_count": (_i64, []),
     "ofl_launch_count_reset": (None, []),
+    "ofl_phase_timing_enable": (None, [_int]),
+    "ofl_phase_timing_read": (_int, [ctypes.POINTER(_f64), ctypes.POINTER(_i64), _int, _int]),
     "ofl_flow_direction_f32": (_int, [_vp, _i64, _i64, _i64, _f64, _vp, _i64, _int, _int, _vp]),
     "ofl_perimeter_count": (_i64, [_i64, _i64]),
     "ofl_accumulation_workspace_bytes": (_sz, [_i64, _i64]),
@@ -84,3 +86,19 @@ def launch_count():
 
 def launch_count_reset():
     lib().ofl_launch_count_reset()
+
+
+PHASES = ("direction", "acc_tile_a", "acc_solve", "acc_tile_b", "acc_links")
+
+
+def phase_timing_enable(on=True):
+    lib().ofl_phase_timing_enable(1 if on else 0)
+
+
+def phase_timing_read(reset=True):
+    """{phase: (total_ms, launches)} measured with CUDA events on the launching stream."""
+    n = len(PHASES)
+    ms = (_f64 * n)()
+    cnt = (_i64 * n)()
+    lib().ofl_phase_timing_read(ms, cnt, n, 1 if reset else 0)
+    return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(PHASES)}

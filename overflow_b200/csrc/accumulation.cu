@@ -496,12 +496,16 @@ int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t 
   OFL_CUDA(cudaMemsetAsync(ws + L.off_S, 0, L.off_link - L.off_S, st));
   OFL_CUDA(cudaMemsetAsync(flags, 0, 64 * sizeof(int), st));
 
-  acc_tile_kernel<false><<<(unsigned)ntiles, ACC_THREADS, 0, st>>>(tm, p);
+  {
+    PhaseScope ps(PHASE_ACC_TILE_A, st);
+    acc_tile_kernel<false><<<(unsigned)ntiles, ACC_THREADS, 0, st>>>(tm, p);
+  }
   OFL_CHECK_LAUNCH();
 
   // reduced-graph solve
   const int sms = sm_count();
   const int pj_blocks = (int)(((L.n_nodes + 255) / 256) < (int64_t)sms * 8 ? ((L.n_nodes + 255) / 256) : (int64_t)sms * 8);
+  PhaseScope* solve_scope = new PhaseScope(PHASE_ACC_SOLVE, st);
   int32_t* ptr_cur = ptr_b;
   int32_t* ptr_nxt = p.succ;  // succ is dead once pj_init has consumed it
   pj_init_kernel<<<pj_blocks, 256, 0, st>>>(p.succ, ptr_cur, L.n_nodes);
@@ -521,9 +525,13 @@ int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t 
     ptr_nxt = t;
   }
   pj_fold_kernel<<<pj_blocks, 256, 0, st>>>(p.S, d0, d1, L.n_nodes);
+  delete solve_scope;
   OFL_CHECK_LAUNCH();
 
-  acc_tile_kernel<true><<<(unsigned)ntiles, ACC_THREADS, 0, st>>>(tm, p);
+  {
+    PhaseScope ps(PHASE_ACC_TILE_B, st);
+    acc_tile_kernel<true><<<(unsigned)ntiles, ACC_THREADS, 0, st>>>(tm, p);
+  }
   OFL_CHECK_LAUNCH();
 
   // Rounds after convergence return early without writing ptr_out, so the converged pointers sit in
@@ -540,7 +548,10 @@ int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t 
     const int32_t* roots = (last_active < 0) ? ptr_b : ((last_active & 1) == 0 ? p.succ : ptr_b);
     const int64_t n = perimeter_count(rows, cols);
     const int blocks = (int)((n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048);
-    links_kernel<<<blocks, 256, 0, st>>>(fdr, ld_fdr, roots, p.link, p, perim_links_dev, n);
+    {
+      PhaseScope ps(PHASE_ACC_LINKS, st);
+      links_kernel<<<blocks, 256, 0, st>>>(fdr, ld_fdr, roots, p.link, p, perim_links_dev, n);
+    }
     OFL_CHECK_LAUNCH();
   }
   return OFL_OK;

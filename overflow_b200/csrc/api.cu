@@ -9,6 +9,8 @@ int ensure_init();
 int shutdown();
 int64_t launch_count();
 void launch_count_reset();
+void phase_timing_enable(int on);
+int phase_timing_read(double* ms, int64_t* counts, int n, int reset);
 
 int launch_direction(const float* dem, int64_t in_rows, int64_t cols, int64_t ld_dem, double nodata, uint8_t* fdr,
                      int64_t rows, int64_t ld_fdr, int y_off, cudaStream_t st);
@@ -35,6 +37,8 @@ int ofl_init(int device) { return init_device(device); }
 int ofl_shutdown(void) { return shutdown(); }
 int64_t ofl_launch_count(void) { return launch_count(); }
 void ofl_launch_count_reset(void) { launch_count_reset(); }
+void ofl_phase_timing_enable(int on) { phase_timing_enable(on); }
+int ofl_phase_timing_read(double* ms, int64_t* counts, int n, int reset) { return phase_timing_read(ms, counts, n, reset); }
 int64_t ofl_perimeter_count(int64_t rows, int64_t cols) { return perimeter_count(rows, cols); }
 size_t ofl_accumulation_workspace_bytes(int64_t rows, int64_t cols) { return accumulation_workspace_bytes(rows, cols); }
 

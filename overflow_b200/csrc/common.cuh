@@ -37,6 +37,18 @@ bool debug_sync();  // OFL_DEBUG_SYNC=1: synchronise after every launch so fault
     }                                 \
   } while (0)
 
+// ---------------------------------------------------------------- per-phase CUDA-event timing
+// When enabled (ofl_phase_timing_enable), every phase is bracketed by cudaEventRecord on the
+// launching stream; ofl_phase_timing_read drains the pairs into per-phase sums.
+enum Phase { PHASE_DIRECTION = 0, PHASE_ACC_TILE_A, PHASE_ACC_SOLVE, PHASE_ACC_TILE_B, PHASE_ACC_LINKS, PHASE_COUNT };
+struct PhaseScope {
+  int phase;
+  cudaStream_t st;
+  cudaEvent_t start;
+  PhaseScope(int phase, cudaStream_t st);
+  ~PhaseScope();
+};
+
 // ---------------------------------------------------------------- device properties / scratch
 int sm_count();
 

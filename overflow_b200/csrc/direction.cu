@@ -347,7 +347,10 @@ int launch_direction(const float* dem, int64_t in_rows, int64_t cols, int64_t ld
   int ctas = (int)((n_items + DIR_WARPS - 1) / DIR_WARPS);
   const int max_ctas = sms * 3;
   if (ctas > max_ctas) ctas = max_ctas;
-  direction_kernel<<<ctas, DIR_WARPS * 32, DIR_SMEM_BYTES, st>>>(tm, p);
+  {
+    PhaseScope ps(PHASE_DIRECTION, st);
+    direction_kernel<<<ctas, DIR_WARPS * 32, DIR_SMEM_BYTES, st>>>(tm, p);
+  }
   OFL_CHECK_LAUNCH();
   return OFL_OK;
 }

@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -39,6 +40,75 @@ bool debug_sync() {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int64_t launch_count() { return g_launches.load(); }
 void launch_count_reset() { g_launches.store(0); }
+
+// ---------------------------------------------------------------- phase timing
+struct PendingPhase {
+  int phase;
+  cudaEvent_t start, stop;
+};
+static bool g_timing = false;
+static std::vector<PendingPhase> g_pending;
+static std::vector<cudaEvent_t> g_event_pool;
+static double g_phase_ms[PHASE_COUNT] = {};
+static int64_t g_phase_n[PHASE_COUNT] = {};
+static std::mutex g_timing_mu;
+
+static cudaEvent_t event_get() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+PhaseScope::PhaseScope(int phase_, cudaStream_t st_) : phase(phase_), st(st_), start(nullptr) {
+  if (!g_timing) return;
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  start = event_get();
+  if (start) cudaEventRecord(start, st);
+}
+
+PhaseScope::~PhaseScope() {
+  if (!start) return;
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  cudaEvent_t stop = event_get();
+  if (stop) cudaEventRecord(stop, st);
+  g_pending.push_back({phase, start, stop});
+}
+
+void phase_timing_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  g_timing = on != 0;
+}
+
+int phase_timing_read(double* ms, int64_t* counts, int n, int reset) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  for (auto& pp : g_pending) {
+    if (pp.start && pp.stop) {
+      float t = 0.f;
+      if (cudaEventSynchronize(pp.stop) == cudaSuccess && cudaEventElapsedTime(&t, pp.start, pp.stop) == cudaSuccess) {
+        g_phase_ms[pp.phase] += t;
+        g_phase_n[pp.phase] += 1;
+      }
+    }
+    if (pp.start) g_event_pool.push_back(pp.start);
+    if (pp.stop) g_event_pool.push_back(pp.stop);
+  }
+  g_pending.clear();
+  for (int i = 0; i < n && i < PHASE_COUNT; ++i) {
+    if (ms) ms[i] = g_phase_ms[i];
+    if (counts) counts[i] = g_phase_n[i];
+  }
+  if (reset)
+    for (int i = 0; i < PHASE_COUNT; ++i) {
+      g_phase_ms[i] = 0;
+      g_phase_n[i] = 0;
+    }
+  return PHASE_COUNT;
+}
 
 // ---------------------------------------------------------------- device state
 struct State {

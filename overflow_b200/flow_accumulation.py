@@ -81,15 +81,21 @@ def _as_codes(flow_direction: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(fdr)
 
 
-def flow_accumulation_for_raster(flow_direction: np.ndarray, with_links: bool = False):
+def flow_accumulation_for_raster(flow_direction: np.ndarray, with_links: bool = False, out: np.ndarray = None):
     """int64 upstream-cell counts for a whole flow-direction raster (+ perimeter links).
 
     Returns fac, or (fac, perim_links[n,2]) with the links in perimeter_indices order.
-    NODATA cells hold -9998 exactly as the reference leaves them.
+    NODATA cells hold -9998 exactly as the reference leaves them.  `out` may be a preallocated
+    C-contiguous int64 array (e.g. pinned memory) of the raster's shape.
     """
     fdr = _as_codes(flow_direction)
     rows, cols = fdr.shape
-    fac = np.empty((rows, cols), dtype=np.int64)
+    if out is None:
+        fac = np.empty((rows, cols), dtype=np.int64)
+    elif out.dtype != np.int64 or out.shape != (rows, cols) or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous int64 array of the raster's shape")
+    else:
+        fac = out
     lib = _native.lib()
     n_perim = int(lib.ofl_perimeter_count(rows, cols))
     perim = np.empty((n_perim, 2), dtype=np.int64) if with_links else None

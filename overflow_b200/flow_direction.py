@@ -55,18 +55,22 @@ def flow_direction_for_tile(dem: np.ndarray, nodata_value: float) -> np.ndarray:
     return out
 
 
-def flow_direction_for_raster(dem: np.ndarray, nodata_value: float) -> np.ndarray:
+def flow_direction_for_raster(dem: np.ndarray, nodata_value: float, out: np.ndarray = None) -> np.ndarray:
     """Whole-raster D8 codes: every cell computed, out-of-raster neighbours read as nodata.
 
     Equals what `flow_direction()` writes for the file (the chunk loop pads the raster edge
-    with the band nodata value, util/raster.py:67); no ring is needed or returned.
+    with the band nodata value, util/raster.py:67); no ring is needed or returned.  `out` may be
+    a preallocated C-contiguous uint8 array (e.g. pinned memory) of dem.shape.
     """
     dem = np.asarray(dem)
     if dem.ndim != 2:
         raise ValueError("dem must be a 2-D array")
     src = np.ascontiguousarray(_as_f32(dem))
     rows, cols = src.shape
-    out = np.empty((rows, cols), dtype=np.uint8)
+    if out is None:
+        out = np.empty((rows, cols), dtype=np.uint8)
+    elif out.dtype != np.uint8 or out.shape != (rows, cols) or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous uint8 array of dem.shape")
     if rows == 0 or cols == 0:
         return out
     lib = _native.lib()
