@@ -10,8 +10,9 @@
 // as the "tile":
 //
 //   pass A  (acc_tile_kernel<false>)  one CTA per 64x64 tile: TMA-load the codes plus a
-//           one-cell halo, accumulate every flow path that stays inside the tile (pull-based
-//           topological relaxation in shared memory, no atomics), follow each perimeter cell
+//           one-cell halo, accumulate every flow path that stays inside the tile (frontier
+//           propagation in shared memory: missing-upstream counts, one shared atomic per edge,
+//           warp-ballot compacted frontier queues), follow each perimeter cell
 //           to where its path leaves the tile (Alg. 2), and emit the reduced graph: for each
 //           of the tile's <=252 perimeter cells its successor perimeter cell in the next
 //           tile, plus the locally accumulated counts that cross the tile edge.
@@ -100,49 +101,56 @@ __device__ __forceinline__ int node_of_cell(int gy, int gx, const AccParams& p) 
   return (ty * p.ntx + tx) * SLOTS + slot_of(gy & (AT - 1), gx & (AT - 1), h, w);
 }
 
-template <typename V>
-struct Flag;
-template <>
-struct Flag<uint32_t> {
-  static constexpr uint32_t value = 0x80000000u;
-};
-template <>
-struct Flag<unsigned long long> {
-  static constexpr unsigned long long value = 0x8000000000000000ull;
+// ---------------------------------------------------------------- in-tile frontier propagation
+// Kahn's algorithm inside one 64x64 tile, frontier kept in per-warp queues in shared memory:
+//   * every cell carries the number of in-tile upstream neighbours still missing;
+//   * a finished cell hands its count to its downstream cell with ONE shared-memory atomic that
+//     also decrements the downstream's missing-count; the thread that brings it to zero appends the
+//     downstream cell to its warp's queue (ballot + popc compaction, no queue atomics);
+//   * each warp pops 32 cells per trip until its own queue is dry.  A warp's queue only grows while
+//     it scans its 512 source candidates, so 512 entries always suffice.
+// Pass A packs [missing:4 | count:28] in one 32-bit word, so the hand-off atomic carries the value.
+// Pass B needs 64-bit counts (seeds from outside the tile): missing-counts are packed four per
+// 32-bit word, values live in a 64-bit array and are pulled from the upstream neighbours when a cell
+// is popped (its missing-count reaching zero orders those stores before the pull).
+constexpr int QCAP = 512;
+
+struct TileLut {
+  int off[8];  // cell-index offset of the downstream neighbour per direction code
 };
 
-// One attempt to finish `cell`: consume every upstream neighbour whose count is final.
-// acc[cell] carries the partial sum with the top bit set until the cell is final.
-template <typename V>
-__device__ __forceinline__ bool visit_cell(volatile V* acc, volatile uint8_t* rem, int cell) {
-  constexpr V FLAG = Flag<V>::value;
-  uint32_t r = rem[cell];
-  V s = acc[cell] & ~FLAG;
-  while (r) {
-    const int i = __ffs(r) - 1;
-    const V v = acc[cell + dir_dy(i) * AT + dir_dx(i)];
-    if (v & FLAG) break;
-    s += v;
-    r &= r - 1;
-  }
-  if (r == 0) {
-    acc[cell] = s + 1;
-    return true;
-  }
-  rem[cell] = (uint8_t)r;
-  acc[cell] = s | FLAG;
-  return false;
+__device__ __forceinline__ void tile_lut_init(int* off_s) {
+  if (threadIdx.x < 8) off_s[threadIdx.x] = dir_dy(threadIdx.x) * AT + dir_dx(threadIdx.x);
 }
+
+template <bool FINAL>
+struct TileSmem {
+  static constexpr int CS = 0;
+  static constexpr int VAL = 6400;  // ACS_BYTES rounded up to 128
+  static constexpr int WORD = VAL + (FINAL ? AT * AT * 8 : 0);
+  static constexpr int DN = WORD + (FINAL ? AT * AT : AT * AT * 4);
+  static constexpr int UPM = DN + AT * AT;
+  static constexpr int Q = UPM + (FINAL ? AT * AT : 0);
+  static constexpr int OFF = Q + (ACC_THREADS / 32) * QCAP * 2;
+  static constexpr int BAR = OFF + 32;
+  static constexpr int BYTES = BAR + 16;
+};
+static_assert(ACS_BYTES <= 6400, "code tile does not fit its shared-memory slot");
 
 template <bool FINAL>
 __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_constant__ CUtensorMap tm,
                                                                 const AccParams p) {
-  using V = typename std::conditional<FINAL, unsigned long long, uint32_t>::type;
-  constexpr V FLAG = Flag<V>::value;
-  __shared__ __align__(128) uint8_t cs[ACS_BYTES];
-  __shared__ __align__(16) V acc[AT * AT];
-  __shared__ uint8_t rem[AT * AT];
-  __shared__ __align__(8) uint64_t bar;
+  // dynamic shared memory, carved by TileSmem<FINAL>
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  using SM = TileSmem<FINAL>;
+  uint8_t* cs = smem_raw + SM::CS;                                                  // codes + halo (TMA destination)
+  unsigned long long* val64 = reinterpret_cast<unsigned long long*>(smem_raw + SM::VAL);  // pass B: 64-bit counts
+  uint32_t* word = reinterpret_cast<uint32_t*>(smem_raw + SM::WORD);  // A: [missing:4|count:28]; B: 4 counts/word
+  uint8_t* dn = smem_raw + SM::DN;                                                  // in-tile downstream direction, 8 = none
+  uint8_t* upm = smem_raw + SM::UPM;                                                // pass B: upstream-neighbour mask
+  uint16_t(*q)[QCAP] = reinterpret_cast<uint16_t(*)[QCAP]>(smem_raw + SM::Q);
+  int* off_s = reinterpret_cast<int*>(smem_raw + SM::OFF);
+  uint64_t& bar = *reinterpret_cast<uint64_t*>(smem_raw + SM::BAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x;
@@ -156,6 +164,7 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     mbar_arrive_expect_tx(&bar, ACS_BYTES);
     tma_load_2d(cs, &tm, x0 - ACS_X0, y0 - ACS_Y0, &bar);
   }
+  tile_lut_init(off_s);
   __syncthreads();
   mbar_wait(&bar, 0);
 
@@ -170,8 +179,12 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     __syncthreads();
   }
 
-  // ---- init: upstream masks, seeds, sources.  Thread owns rows 8*warp..+7 of columns lane, lane+32.
-  uint32_t pend = 0;
+  // pass B keeps four 8-bit missing-counts per word; cell c -> word c>>2, byte c&3
+  uint32_t* cnt4 = word;
+
+  // ---- phase 1: missing-counts, downstream direction, seeds.  Thread owns rows 8*warp..+7 of
+  //      columns lane and lane+32 (lanes touch consecutive shared-memory words).
+  uint32_t srcmask = 0;
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int x = lane + 32 * half;
@@ -180,8 +193,8 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
       const int y = 8 * warp + k;
       const int cell = y * AT + x;
       const uint8_t* c = cs + (y + ACS_Y0) * ACS_W + (x + ACS_X0);
-      const uint8_t own = c[0];
-      uint32_t up = 0;
+      const uint32_t own = c[0];
+      uint32_t up = 0, dnb = 8;
       if (own != OFL_DIR_NODATA && own != CODE_OUTSIDE) {
         // neighbour in direction i flows into this cell iff its code is the opposite direction
         up |= (x + 1 < w && c[1] == 4) ? 1u : 0u;
@@ -192,42 +205,91 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
         up |= (y + 1 < h && x > 0 && c[ACS_W - 1] == 1) ? 32u : 0u;
         up |= (y + 1 < h && c[ACS_W] == 2) ? 64u : 0u;
         up |= (y + 1 < h && x + 1 < w && c[ACS_W + 1] == 3) ? 128u : 0u;
+        if (own < 8) {
+          const int ny = y + dir_dy(own), nx = x + dir_dx(own);
+          if (ny >= 0 && ny < h && nx >= 0 && nx < w && c[dir_dy(own) * ACS_W + dir_dx(own)] != OFL_DIR_NODATA)
+            dnb = own;
+        }
       }
-      V seed = 0;
-      if (FINAL && own != CODE_OUTSIDE) {
-        const int s = slot_of(y, x, h, w);
-        if (s >= 0) seed = (V)p.S[(size_t)tile * SLOTS + s];
-      }
-      rem[cell] = (uint8_t)up;
-      if (up) {
-        acc[cell] = seed | FLAG;
-        pend |= 1u << (k + 8 * half);
+      const uint32_t missing = __popc(up);
+      dn[cell] = (uint8_t)dnb;
+      if (FINAL) {
+        unsigned long long seed = 0;
+        if (own != CODE_OUTSIDE) {
+          const int s = slot_of(y, x, h, w);
+          if (s >= 0) seed = p.S[(size_t)tile * SLOTS + s];
+        }
+        val64[cell] = seed;
+        upm[cell] = (uint8_t)up;
+        // four consecutive cells of a row belong to four consecutive lanes: assemble the count word
+        uint32_t packed = missing << (8 * (x & 3));
+        packed |= __shfl_xor_sync(0xffffffffu, packed, 1);
+        packed |= __shfl_xor_sync(0xffffffffu, packed, 2);
+        if ((x & 3) == 0) cnt4[cell >> 2] = packed;
       } else {
-        acc[cell] = seed + 1;
+        word[cell] = missing << 28;
       }
+      if (missing == 0) srcmask |= 1u << (k + 8 * half);
     }
   }
   __syncthreads();
 
-  // ---- relaxation: each warp polls until its own cells are final (other warps publish through smem)
-  {
-    volatile V* vacc = acc;
-    volatile uint8_t* vrem = rem;
-    int iter = 0;
-    while (__any_sync(0xffffffffu, pend != 0)) {
-      uint32_t m = pend;
-      const bool up_order = (iter & 1) == 0;
-      while (m) {
-        const int j = up_order ? (__ffs(m) - 1) : (31 - __clz(m));
-        m &= ~(1u << j);
-        const int cell = (8 * warp + (j & 7)) * AT + lane + 32 * (j >> 3);
-        if (visit_cell<V>(vacc, vrem, cell)) pend &= ~(1u << j);
-      }
-      if (++iter > (1 << 20)) {  // only a cyclic raster can get here
-        if (lane == 0) atomicExch(p.err, 1);
-        break;
+  // ---- phase 2 + 3: sources first (one per lane per step), then drain this warp's queue
+  uint16_t* myq = q[warp];
+  uint32_t head = 0, tail = 0;
+  auto process = [&](int cell, bool active) {
+    // finish `cell`, hand its count downstream, return the downstream cell if this made it ready
+    bool ready = false;
+    int nxt = 0;
+    if (active) {
+      const uint32_t d = dn[cell];
+      if (FINAL) {
+        unsigned long long v = val64[cell] + 1;
+        uint32_t um = upm[cell];
+        while (um) {
+          const int i = __ffs(um) - 1;
+          um &= um - 1;
+          v += val64[cell + off_s[i]];
+        }
+        val64[cell] = v;
+        if (d < 8) {
+          nxt = cell + off_s[d];
+          __threadfence_block();  // publish val64[cell] before the count that releases the downstream cell
+          const uint32_t sh = 8 * (nxt & 3);
+          const uint32_t old = atomicSub(&cnt4[nxt >> 2], 1u << sh);
+          ready = ((old >> sh) & 0xFF) == 1;
+          if (ready) __threadfence_block();
+        }
+      } else {
+        const uint32_t v = (word[cell] & 0x0FFFFFFFu) + 1;
+        word[cell] = v;
+        if (d < 8) {
+          nxt = cell + off_s[d];
+          const uint32_t old = atomicAdd(&word[nxt], v - (1u << 28));
+          ready = (old >> 28) == 1;
+        }
       }
     }
+    const uint32_t bal = __ballot_sync(0xffffffffu, ready);
+    if (ready) myq[(tail + __popc(bal & ((1u << lane) - 1))) & (QCAP - 1)] = (uint16_t)nxt;
+    tail += __popc(bal);
+  };
+
+#pragma unroll 1
+  for (int j = 0; j < 16; ++j) {
+    const int cell = (8 * warp + (j & 7)) * AT + lane + 32 * (j >> 3);
+    process(cell, (srcmask >> j) & 1);
+  }
+  __syncwarp();
+  while (head != tail) {
+    const uint32_t n = tail - head;
+    const uint32_t take = n < 32 ? n : 32;
+    const bool active = lane < take;
+    const int cell = active ? myq[(head + lane) & (QCAP - 1)] : 0;
+    head += take;
+    __syncwarp();
+    process(cell, active);
+    __syncwarp();
   }
   __syncthreads();
 
@@ -238,45 +300,49 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     int32_t succ = -1;
     uint16_t lk = KIND_TERM << 8;
     if (cell_of_slot(s, h, w, y, x) && cs[(y + ACS_Y0) * ACS_W + x + ACS_X0] != CODE_OUTSIDE) {
-      int cy = y, cx = x;
-      uint16_t kind = KIND_TERM;
+      int cur = y * AT + x;
       for (int steps = 0;; ++steps) {
-        const int code = cs[(cy + ACS_Y0) * ACS_W + cx + ACS_X0];
-        if (code >= 8) break;  // pit / flat / nodata: no downstream cell
-        const int ny = cy + dir_dy(code), nx = cx + dir_dx(code);
-        const int dcode = cs[(ny + ACS_Y0) * ACS_W + nx + ACS_X0];
-        if (dcode == CODE_OUTSIDE) {
-          kind = KIND_RASTER_EXIT;
-          break;
-        }
-        if (dcode == OFL_DIR_NODATA) break;
-        if (ny < 0 || ny >= h || nx < 0 || nx >= w) {
-          kind = KIND_TILE_EXIT;
-          succ = node_of_cell(y0 + ny, x0 + nx, p);
-          break;
-        }
-        cy = ny;
-        cx = nx;
+        const uint32_t d = dn[cur];
+        if (d >= 8) break;
+        cur += off_s[d];
         if (steps > AT * AT) {
           atomicExch(p.err, 1);
           break;
         }
       }
+      // classify the end of the in-tile path
+      const int cy = cur >> AT_SHIFT, cx = cur & (AT - 1);
+      uint16_t kind = KIND_TERM;
+      const int code = cs[(cy + ACS_Y0) * ACS_W + cx + ACS_X0];
+      if (code < 8) {
+        const int ny = cy + dir_dy(code), nx = cx + dir_dx(code);
+        const int dcode = cs[(ny + ACS_Y0) * ACS_W + nx + ACS_X0];
+        if (dcode == CODE_OUTSIDE) {
+          kind = KIND_RASTER_EXIT;
+        } else if (dcode != OFL_DIR_NODATA) {
+          kind = KIND_TILE_EXIT;  // dn == 8 with a live downstream cell: it lies in the next tile
+          succ = node_of_cell(y0 + ny, x0 + nx, p);
+        }
+      }
       const int ls = slot_of(cy, cx, h, w);
       lk = (uint16_t)((ls < 0 ? 0 : ls) | (kind << 8));
       // this cell's own edge across the tile boundary carries its local count to the next tile
-      const int code = cs[(y + ACS_Y0) * ACS_W + x + ACS_X0];
-      if (code < 8) {
-        const int ny = y + dir_dy(code), nx = x + dir_dx(code);
+      const int own = cs[(y + ACS_Y0) * ACS_W + x + ACS_X0];
+      if (own < 8 && dn[y * AT + x] >= 8) {
+        const int ny = y + dir_dy(own), nx = x + dir_dx(own);
         const int dcode = cs[(ny + ACS_Y0) * ACS_W + nx + ACS_X0];
-        if ((ny < 0 || ny >= h || nx < 0 || nx >= w) && dcode != CODE_OUTSIDE && dcode != OFL_DIR_NODATA)
-          atomicAdd(&p.S[node_of_cell(y0 + ny, x0 + nx, p)], (unsigned long long)acc[y * AT + x]);
+        if (dcode != CODE_OUTSIDE && dcode != OFL_DIR_NODATA) {
+          const uint32_t wv = word[y * AT + x];
+          if (wv >> 28) atomicExch(p.err, 1);  // never finished: the tile holds a cycle
+          atomicAdd(&p.S[node_of_cell(y0 + ny, x0 + nx, p)], (unsigned long long)(wv & 0x0FFFFFFFu));
+        }
       }
     }
     p.succ[(size_t)tile * SLOTS + s] = succ;
     p.link[(size_t)tile * SLOTS + s] = lk;
   } else {
     // ---- final counts: lane-contiguous int64 stores (256 B per half row); NODATA cells get -9998
+    bool stuck = false;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int x = lane + 32 * half;
@@ -284,12 +350,15 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
       for (int k = 0; k < 8; ++k) {
         const int y = 8 * warp + k;
         if (y < h && x < w) {
+          const int cell = y * AT + x;
           const uint8_t own = cs[(y + ACS_Y0) * ACS_W + x + ACS_X0];
-          const long long v = (own == OFL_DIR_NODATA) ? (long long)OFL_FAC_NODATA_EMITTED : (long long)acc[y * AT + x];
+          stuck |= ((cnt4[cell >> 2] >> (8 * (cell & 3))) & 0xFF) != 0;
+          const long long v = (own == OFL_DIR_NODATA) ? (long long)OFL_FAC_NODATA_EMITTED : (long long)val64[cell];
           p.fac[(int64_t)(y0 + y) * p.ld_fac + (x0 + x)] = v;
         }
       }
     }
+    if (stuck) atomicExch(p.err, 1);  // a missing-count never reached zero: cycle
   }
 }
 
@@ -492,13 +561,22 @@ int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t 
   int rc = make_tensor_map_2d(&tm, fdr, 1, (uint64_t)cols, (uint64_t)rows, (uint64_t)ld_fdr, ACS_W, ACS_H);
   if (rc != OFL_OK) return rc;
 
+  static bool attr_set = false;
+  if (!attr_set) {
+    OFL_CUDA(cudaFuncSetAttribute(acc_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TileSmem<false>::BYTES));
+    OFL_CUDA(cudaFuncSetAttribute(acc_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TileSmem<true>::BYTES));
+    attr_set = true;
+  }
+
   // S, d0, d1 are contiguous: one memset; flags: active-before-round-0 = 1, the rest 0
   OFL_CUDA(cudaMemsetAsync(ws + L.off_S, 0, L.off_link - L.off_S, st));
   OFL_CUDA(cudaMemsetAsync(flags, 0, 64 * sizeof(int), st));
 
   {
     PhaseScope ps(PHASE_ACC_TILE_A, st);
-    acc_tile_kernel<false><<<(unsigned)ntiles, ACC_THREADS, 0, st>>>(tm, p);
+    acc_tile_kernel<false><<<(unsigned)ntiles, ACC_THREADS, TileSmem<false>::BYTES, st>>>(tm, p);
   }
   OFL_CHECK_LAUNCH();
 
@@ -530,7 +608,7 @@ int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t 
 
   {
     PhaseScope ps(PHASE_ACC_TILE_B, st);
-    acc_tile_kernel<true><<<(unsigned)ntiles, ACC_THREADS, 0, st>>>(tm, p);
+    acc_tile_kernel<true><<<(unsigned)ntiles, ACC_THREADS, TileSmem<true>::BYTES, st>>>(tm, p);
   }
   OFL_CHECK_LAUNCH();
 
