@@ -44,7 +44,8 @@ constexpr int ACS_Y0 = 1;
 constexpr uint32_t ACS_BYTES = ACS_W * ACS_H;
 constexpr int SLOTS = 4 * AT;          // perimeter slots per tile (top, bottom, left, right)
 constexpr int ACC_THREADS = 256;
-constexpr uint8_t CODE_OUTSIDE = 0xFF; // halo / partial-tile positions outside the raster
+constexpr uint8_t CODE_OUTSIDE = 15;   // positions outside the raster (halo or partial tile)
+constexpr uint8_t CODE_HALO_LIVE = 14; // halo cell that is a live (non-NODATA) cell of the next tile
 
 // node kinds, stored in link[] bits 8..9
 constexpr uint16_t KIND_TERM = 0;        // path ends inside the raster (pit, or downstream is NODATA)
@@ -102,55 +103,58 @@ __device__ __forceinline__ int node_of_cell(int gy, int gx, const AccParams& p) 
 }
 
 // ---------------------------------------------------------------- in-tile frontier propagation
-// Kahn's algorithm inside one 64x64 tile, frontier kept in per-warp queues in shared memory:
-//   * every cell carries the number of in-tile upstream neighbours still missing;
-//   * a finished cell hands its count to its downstream cell with ONE shared-memory atomic that
-//     also decrements the downstream's missing-count; the thread that brings it to zero appends the
-//     downstream cell to its warp's queue (ballot + popc compaction, no queue atomics);
-//   * each warp pops 32 cells per trip until its own queue is dry.  A warp's queue only grows while
-//     it scans its 512 source candidates, so 512 entries always suffice.
-// Pass A packs [missing:4 | count:28] in one 32-bit word, so the hand-off atomic carries the value.
-// Pass B needs 64-bit counts (seeds from outside the tile): missing-counts are packed four per
-// 32-bit word, values live in a 64-bit array and are pulled from the upstream neighbours when a cell
-// is popped (its missing-count reaching zero orders those stores before the pull).
-constexpr int QCAP = 512;
-
-struct TileLut {
-  int off[8];  // cell-index offset of the downstream neighbour per direction code
-};
-
-__device__ __forceinline__ void tile_lut_init(int* off_s) {
-  if (threadIdx.x < 8) off_s[threadIdx.x] = dir_dy(threadIdx.x) * AT + dir_dx(threadIdx.x);
-}
+// Kahn's algorithm inside one 64x64 tile, level-synchronous, frontier in a shared-memory queue:
+//   * every cell carries the number of in-tile upstream neighbours still missing, packed with its
+//     running count in one 32-bit word [missing:4 | count:28];
+//   * a finished cell hands its count to its downstream cell with ONE shared-memory atomicAdd of
+//     (count - 1<<28): it adds the count and decrements the missing field at once, so the thread that
+//     sees the field drop to zero knows the sum is complete and appends the cell to the frontier
+//     (warp ballot + popc compaction, one queue atomic per warp);
+//   * the word array has a one-cell halo and no edge is ever skipped: hand-offs into the halo, into
+//     NODATA cells or out of the raster land in words nobody reads;
+//   * frontier levels are consecutive segments of one 4096-entry queue (a cell is appended once);
+//     a level never grows, so once it fits one warp, warp 0 finishes the tail alone.
+// Pass B carries 64-bit counts as (hi32 << 24) + lo24: the low 24 bits ride in the packed word (nine
+// 24-bit terms fit the 28-bit field), the high part goes through a second atomic only when non-zero.
+constexpr int WP = 68;                 // word-array pitch: cells x = -1..64 in columns 0..65
+constexpr int WORDS = (AT + 2) * WP;   // rows y = -1..64
+constexpr int QMAX = AT * AT;
 
 template <bool FINAL>
 struct TileSmem {
   static constexpr int CS = 0;
-  static constexpr int VAL = 6400;  // ACS_BYTES rounded up to 128
-  static constexpr int WORD = VAL + (FINAL ? AT * AT * 8 : 0);
-  static constexpr int DN = WORD + (FINAL ? AT * AT : AT * AT * 4);
-  static constexpr int UPM = DN + AT * AT;
-  static constexpr int Q = UPM + (FINAL ? AT * AT : 0);
-  static constexpr int OFF = Q + (ACC_THREADS / 32) * QCAP * 2;
-  static constexpr int BAR = OFF + 32;
-  static constexpr int BYTES = BAR + 16;
+  static constexpr int WORD = 6400;  // ACS_BYTES rounded up to 128
+  static constexpr int HI = WORD + WORDS * 4;
+  static constexpr int Q = HI + (FINAL ? WORDS * 4 : 0);
+  static constexpr int MISC = Q + QMAX * 2;
+  static constexpr int BYTES = MISC + 128;
 };
 static_assert(ACS_BYTES <= 6400, "code tile does not fit its shared-memory slot");
+static_assert((WORDS * 4) % 16 == 0, "word array must be a whole number of uint4");
+
+__device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, int bits) {
+  return __funnelshift_r(lo, hi, bits);
+}
+
+// per byte (all bytes < 16): 1 where the byte of `nb` differs from the code replicated in `pat`
+__device__ __forceinline__ uint32_t bytes_differ(uint32_t nb, uint32_t pat) {
+  return (((nb ^ pat) + 0x7F7F7F7Fu) >> 7) & 0x01010101u;
+}
 
 template <bool FINAL>
 __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_constant__ CUtensorMap tm,
                                                                 const AccParams p) {
-  // dynamic shared memory, carved by TileSmem<FINAL>
   extern __shared__ __align__(128) uint8_t smem_raw[];
   using SM = TileSmem<FINAL>;
-  uint8_t* cs = smem_raw + SM::CS;                                                  // codes + halo (TMA destination)
-  unsigned long long* val64 = reinterpret_cast<unsigned long long*>(smem_raw + SM::VAL);  // pass B: 64-bit counts
-  uint32_t* word = reinterpret_cast<uint32_t*>(smem_raw + SM::WORD);  // A: [missing:4|count:28]; B: 4 counts/word
-  uint8_t* dn = smem_raw + SM::DN;                                                  // in-tile downstream direction, 8 = none
-  uint8_t* upm = smem_raw + SM::UPM;                                                // pass B: upstream-neighbour mask
-  uint16_t(*q)[QCAP] = reinterpret_cast<uint16_t(*)[QCAP]>(smem_raw + SM::Q);
-  int* off_s = reinterpret_cast<int*>(smem_raw + SM::OFF);
-  uint64_t& bar = *reinterpret_cast<uint64_t*>(smem_raw + SM::BAR);
+  uint8_t* cs = smem_raw + SM::CS;                                   // codes + halo (TMA destination)
+  uint32_t* csw = reinterpret_cast<uint32_t*>(cs);
+  uint32_t* word = reinterpret_cast<uint32_t*>(smem_raw + SM::WORD);  // [missing:4 | count:28], halo-padded
+  uint32_t* hiw = reinterpret_cast<uint32_t*>(smem_raw + SM::HI);     // pass B: count >> 24
+  uint16_t* q = reinterpret_cast<uint16_t*>(smem_raw + SM::Q);        // frontier queue of cell ids (y*64+x)
+  int* off_idx = reinterpret_cast<int*>(smem_raw + SM::MISC);         // downstream offset in cell ids, per code
+  int* off_wi = off_idx + 8;                                           // same in word-array indices
+  uint32_t* tail = reinterpret_cast<uint32_t*>(off_idx + 16);
+  uint64_t& bar = *reinterpret_cast<uint64_t*>(smem_raw + SM::MISC + 96);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x;
@@ -163,12 +167,61 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     mbar_fence_init();
     mbar_arrive_expect_tx(&bar, ACS_BYTES);
     tma_load_2d(cs, &tm, x0 - ACS_X0, y0 - ACS_Y0, &bar);
+    *tail = 0;
   }
-  tile_lut_init(off_s);
+  if (tid < 8) {
+    off_idx[tid] = dir_dy(tid) * AT + dir_dx(tid);
+    off_wi[tid] = dir_dy(tid) * WP + dir_dx(tid);
+  }
+  {
+    uint4* z = reinterpret_cast<uint4*>(word);
+    constexpr int NZ = (FINAL ? 2 : 1) * WORDS / 4;  // word[] and hiw[] are adjacent
+    for (int i = tid; i < NZ; i += ACC_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+  }
   __syncthreads();
   mbar_wait(&bar, 0);
 
-  // positions outside the raster were zero-filled by TMA (code 0 = east): mark them
+  // ---- phase 0: invalid codes (>= 10) -> 8; halo ring -> {9 nodata, 14 live} so it can never look like
+  //      an in-tile upstream; then positions outside the raster (TMA zero fill) -> CODE_OUTSIDE
+  const int qx = lane & 15, rp = lane >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int y = 8 * warp + 2 * i + rp;
+    const int cw = (y + ACS_Y0) * (ACS_W / 4) + ACS_X0 / 4 + qx;
+    const uint32_t v = csw[cw];
+    if ((v + 0x06060606u) & 0xF0F0F0F0u) {  // some byte >= 10: invalid input, behaves like "no downstream"
+      uint32_t f = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        uint32_t c = (v >> (8 * b)) & 0xFF;
+        if (c >= 10) c = OFL_DIR_UNDEFINED;
+        f |= c << (8 * b);
+      }
+      csw[cw] = f;
+    }
+  }
+  for (int t = tid; t < 4 * AT + 4; t += ACC_THREADS) {
+    int hy, hx;  // halo position in tile coordinates (-1..64)
+    if (t < AT) {
+      hy = -1;
+      hx = t;
+    } else if (t < 2 * AT) {
+      hy = AT;
+      hx = t - AT;
+    } else if (t < 3 * AT) {
+      hy = t - 2 * AT;
+      hx = -1;
+    } else if (t < 4 * AT) {
+      hy = t - 3 * AT;
+      hx = AT;
+    } else {
+      hy = (t & 1) ? AT : -1;
+      hx = (t & 2) ? AT : -1;
+    }
+    uint8_t* hp = cs + (hy + ACS_Y0) * ACS_W + hx + ACS_X0;
+    *hp = (*hp == OFL_DIR_NODATA) ? (uint8_t)OFL_DIR_NODATA : CODE_HALO_LIVE;
+  }
+  __syncthreads();
   const bool edge_tile = (y0 == 0) || (x0 == 0) || (y0 + AT + 1 > p.rows) || (x0 + AT + 1 > p.cols);
   if (edge_tile) {
     for (int idx = tid; idx < (int)ACS_BYTES; idx += ACC_THREADS) {
@@ -179,117 +232,120 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     __syncthreads();
   }
 
-  // pass B keeps four 8-bit missing-counts per word; cell c -> word c>>2, byte c&3
-  uint32_t* cnt4 = word;
+  auto push = [&](bool ready, uint32_t idx) {
+    const uint32_t bal = __ballot_sync(0xffffffffu, ready);
+    if (bal) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(tail, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (ready) q[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)idx;
+    }
+  };
 
-  // ---- phase 1: missing-counts, downstream direction, seeds.  Thread owns rows 8*warp..+7 of
-  //      columns lane and lane+32 (lanes touch consecutive shared-memory words).
-  uint32_t srcmask = 0;
+  // ---- phase 1: missing-counts for four cells at a time (byte-parallel), sources into the queue.
+  //      Lane owns the quad of columns 4*qx..4*qx+3 in rows 8*warp + 2*i + rp.
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int x = lane + 32 * half;
+  for (int i = 0; i < 4; ++i) {
+    const int y = 8 * warp + 2 * i + rp;
+    const int cw = (y + ACS_Y0) * (ACS_W / 4) + ACS_X0 / 4 + qx;
+    constexpr int RW = ACS_W / 4;
+    const uint32_t L0 = csw[cw - RW - 1], C0 = csw[cw - RW], R0 = csw[cw - RW + 1];
+    const uint32_t L1 = csw[cw - 1], C1 = csw[cw], R1 = csw[cw + 1];
+    const uint32_t L2 = csw[cw + RW - 1], C2 = csw[cw + RW], R2 = csw[cw + RW + 1];
+    // a neighbour flows into the cell iff its code is the direction pointing back at it
+    uint32_t nm = bytes_differ(funnel_r(C1, R1, 8), 0x04040404u);   // E neighbour flowing W
+    nm += bytes_differ(funnel_r(C0, R0, 8), 0x05050505u);           // NE neighbour flowing SW
+    nm += bytes_differ(C0, 0x06060606u);                            // N neighbour flowing S
+    nm += bytes_differ(funnel_r(L0, C0, 24), 0x07070707u);          // NW neighbour flowing SE
+    nm += bytes_differ(funnel_r(L1, C1, 24), 0x00000000u);          // W neighbour flowing E
+    nm += bytes_differ(funnel_r(L2, C2, 24), 0x01010101u);          // SW neighbour flowing NE
+    nm += bytes_differ(C2, 0x02020202u);                            // S neighbour flowing N
+    nm += bytes_differ(funnel_r(C2, R2, 8), 0x03030303u);           // SE neighbour flowing NW
+    const uint32_t cnt4 = 0x08080808u - nm;                         // missing upstream neighbours per cell
+    // not a source: missing != 0, or the cell is NODATA / outside (own code >= 9)
+    const uint32_t notsrc = ((cnt4 + 0x7F7F7F7Fu) | (C1 + 0x77777777u)) & 0x80808080u;
+    const int idx0 = y * AT + 4 * qx;
+    const int wi0 = (y + 1) * WP + 4 * qx + 1;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int y = 8 * warp + k;
-      const int cell = y * AT + x;
-      const uint8_t* c = cs + (y + ACS_Y0) * ACS_W + (x + ACS_X0);
-      const uint32_t own = c[0];
-      uint32_t up = 0, dnb = 8;
-      if (own != OFL_DIR_NODATA && own != CODE_OUTSIDE) {
-        // neighbour in direction i flows into this cell iff its code is the opposite direction
-        up |= (x + 1 < w && c[1] == 4) ? 1u : 0u;
-        up |= (y > 0 && x + 1 < w && c[-ACS_W + 1] == 5) ? 2u : 0u;
-        up |= (y > 0 && c[-ACS_W] == 6) ? 4u : 0u;
-        up |= (y > 0 && x > 0 && c[-ACS_W - 1] == 7) ? 8u : 0u;
-        up |= (x > 0 && c[-1] == 0) ? 16u : 0u;
-        up |= (y + 1 < h && x > 0 && c[ACS_W - 1] == 1) ? 32u : 0u;
-        up |= (y + 1 < h && c[ACS_W] == 2) ? 64u : 0u;
-        up |= (y + 1 < h && x + 1 < w && c[ACS_W + 1] == 3) ? 128u : 0u;
-        if (own < 8) {
-          const int ny = y + dir_dy(own), nx = x + dir_dx(own);
-          if (ny >= 0 && ny < h && nx >= 0 && nx < w && c[dir_dy(own) * ACS_W + dir_dx(own)] != OFL_DIR_NODATA)
-            dnb = own;
-        }
-      }
-      const uint32_t missing = __popc(up);
-      dn[cell] = (uint8_t)dnb;
-      if (FINAL) {
-        unsigned long long seed = 0;
-        if (own != CODE_OUTSIDE) {
-          const int s = slot_of(y, x, h, w);
-          if (s >= 0) seed = p.S[(size_t)tile * SLOTS + s];
-        }
-        val64[cell] = seed;
-        upm[cell] = (uint8_t)up;
-        // four consecutive cells of a row belong to four consecutive lanes: assemble the count word
-        uint32_t packed = missing << (8 * (x & 3));
-        packed |= __shfl_xor_sync(0xffffffffu, packed, 1);
-        packed |= __shfl_xor_sync(0xffffffffu, packed, 2);
-        if ((x & 3) == 0) cnt4[cell >> 2] = packed;
-      } else {
-        word[cell] = missing << 28;
-      }
-      if (missing == 0) srcmask |= 1u << (k + 8 * half);
+    for (int b = 0; b < 4; ++b) {
+      word[wi0 + b] = ((cnt4 >> (8 * b)) & 0xFu) << 28;
+      push(!((notsrc >> (8 * b)) & 0x80u), idx0 + b);
     }
   }
   __syncthreads();
-
-  // ---- phase 2 + 3: sources first (one per lane per step), then drain this warp's queue
-  uint16_t* myq = q[warp];
-  uint32_t head = 0, tail = 0;
-  auto process = [&](int cell, bool active) {
-    // finish `cell`, hand its count downstream, return the downstream cell if this made it ready
-    bool ready = false;
-    int nxt = 0;
-    if (active) {
-      const uint32_t d = dn[cell];
-      if (FINAL) {
-        unsigned long long v = val64[cell] + 1;
-        uint32_t um = upm[cell];
-        while (um) {
-          const int i = __ffs(um) - 1;
-          um &= um - 1;
-          v += val64[cell + off_s[i]];
-        }
-        val64[cell] = v;
-        if (d < 8) {
-          nxt = cell + off_s[d];
-          __threadfence_block();  // publish val64[cell] before the count that releases the downstream cell
-          const uint32_t sh = 8 * (nxt & 3);
-          const uint32_t old = atomicSub(&cnt4[nxt >> 2], 1u << sh);
-          ready = ((old >> sh) & 0xFF) == 1;
-          if (ready) __threadfence_block();
-        }
-      } else {
-        const uint32_t v = (word[cell] & 0x0FFFFFFFu) + 1;
-        word[cell] = v;
-        if (d < 8) {
-          nxt = cell + off_s[d];
-          const uint32_t old = atomicAdd(&word[nxt], v - (1u << 28));
-          ready = (old >> 28) == 1;
-        }
+  if (FINAL) {
+    // seeds: inflow from outside the tile into each perimeter cell (from the reduced-graph solve)
+    int y, x;
+    if (cell_of_slot(tid, h, w, y, x)) {
+      const unsigned long long seed = p.S[(size_t)tile * SLOTS + tid];
+      if (seed) {
+        const int wi = (y + 1) * WP + x + 1;
+        word[wi] += (uint32_t)(seed & 0xFFFFFFu);
+        hiw[wi] = (uint32_t)(seed >> 24);
       }
     }
-    const uint32_t bal = __ballot_sync(0xffffffffu, ready);
-    if (ready) myq[(tail + __popc(bal & ((1u << lane) - 1))) & (QCAP - 1)] = (uint16_t)nxt;
-    tail += __popc(bal);
+    __syncthreads();
+  }
+
+  // finish cell `idx`, hand its count downstream; append the downstream cell if that completed it
+  auto process = [&](uint32_t idx, bool active) {
+    bool ready = false;
+    uint32_t nidx = 0;
+    if (active) {
+      const uint32_t yy = idx >> AT_SHIFT;
+      const uint32_t wi = idx + 4 * yy + (WP + 1);
+      const uint32_t code = cs[idx + (ACS_W - AT) * yy + (ACS_W * ACS_Y0 + ACS_X0)];
+      const uint32_t s = word[wi] & 0x0FFFFFFFu;
+      uint32_t lo, hn = 0;
+      if (FINAL) {
+        const unsigned long long v = ((unsigned long long)hiw[wi] << 24) + s + 1;
+        lo = (uint32_t)v & 0xFFFFFFu;
+        hn = (uint32_t)(v >> 24);
+        hiw[wi] = hn;
+      } else {
+        lo = s + 1;
+      }
+      word[wi] = lo;
+      if (code < 8) {
+        const uint32_t nwi = wi + off_wi[code];
+        nidx = idx + off_idx[code];
+        if (FINAL && hn) {
+          atomicAdd(&hiw[nwi], hn);
+          __threadfence_block();  // the high part must be in place before the count can reach zero
+        }
+        const uint32_t old = atomicAdd(&word[nwi], lo - (1u << 28));
+        ready = (old >> 28) == 1;
+      }
+    }
+    push(ready, nidx);
   };
 
-#pragma unroll 1
-  for (int j = 0; j < 16; ++j) {
-    const int cell = (8 * warp + (j & 7)) * AT + lane + 32 * (j >> 3);
-    process(cell, (srcmask >> j) & 1);
+  // ---- level-synchronous sweep: level k is q[lo, hi); processing it appends level k+1 after it
+  uint32_t lo = 0, hi = *tail;
+  __syncthreads();
+  while (hi - lo > 32) {
+    for (uint32_t base = lo + 32 * warp; base < hi; base += ACC_THREADS) {
+      const uint32_t i = base + lane;
+      const bool active = i < hi;
+      process(active ? q[i] : 0u, active);
+    }
+    __syncthreads();
+    const uint32_t nh = *tail;
+    __syncthreads();  // nobody appends to the next level before everyone has read where this one ends
+    lo = hi;
+    hi = nh;
   }
-  __syncwarp();
-  while (head != tail) {
-    const uint32_t n = tail - head;
-    const uint32_t take = n < 32 ? n : 32;
-    const bool active = lane < take;
-    const int cell = active ? myq[(head + lane) & (QCAP - 1)] : 0;
-    head += take;
-    __syncwarp();
-    process(cell, active);
-    __syncwarp();
+  if (warp == 0) {
+    volatile uint32_t* vtail = tail;
+    while (lo < hi) {
+      const uint32_t i = lo + lane;
+      const bool active = i < hi;
+      process(active ? q[i] : 0u, active);
+      __syncwarp();
+      lo = hi;
+      hi = *vtail;
+      __syncwarp();
+    }
   }
   __syncthreads();
 
@@ -299,42 +355,44 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     int y, x;
     int32_t succ = -1;
     uint16_t lk = KIND_TERM << 8;
-    if (cell_of_slot(s, h, w, y, x) && cs[(y + ACS_Y0) * ACS_W + x + ACS_X0] != CODE_OUTSIDE) {
-      int cur = y * AT + x;
-      for (int steps = 0;; ++steps) {
-        const uint32_t d = dn[cur];
-        if (d >= 8) break;
-        cur += off_s[d];
-        if (steps > AT * AT) {
-          atomicExch(p.err, 1);
-          break;
-        }
-      }
-      // classify the end of the in-tile path
-      const int cy = cur >> AT_SHIFT, cx = cur & (AT - 1);
+    if (cell_of_slot(s, h, w, y, x)) {
+      int cy = y, cx = x;
       uint16_t kind = KIND_TERM;
-      const int code = cs[(cy + ACS_Y0) * ACS_W + cx + ACS_X0];
-      if (code < 8) {
+      for (int steps = 0;; ++steps) {
+        const int code = cs[(cy + ACS_Y0) * ACS_W + cx + ACS_X0];
+        if (code >= 8) break;  // pit / flat / nodata: the path ends here
         const int ny = cy + dir_dy(code), nx = cx + dir_dx(code);
         const int dcode = cs[(ny + ACS_Y0) * ACS_W + nx + ACS_X0];
         if (dcode == CODE_OUTSIDE) {
           kind = KIND_RASTER_EXIT;
-        } else if (dcode != OFL_DIR_NODATA) {
-          kind = KIND_TILE_EXIT;  // dn == 8 with a live downstream cell: it lies in the next tile
+          break;
+        }
+        if (dcode == OFL_DIR_NODATA) break;
+        if (ny < 0 || ny >= AT || nx < 0 || nx >= AT) {
+          kind = KIND_TILE_EXIT;
           succ = node_of_cell(y0 + ny, x0 + nx, p);
+          break;
+        }
+        cy = ny;
+        cx = nx;
+        if (steps > AT * AT) {
+          atomicExch(p.err, 1);
+          break;
         }
       }
       const int ls = slot_of(cy, cx, h, w);
       lk = (uint16_t)((ls < 0 ? 0 : ls) | (kind << 8));
       // this cell's own edge across the tile boundary carries its local count to the next tile
       const int own = cs[(y + ACS_Y0) * ACS_W + x + ACS_X0];
-      if (own < 8 && dn[y * AT + x] >= 8) {
+      if (own < 8) {
         const int ny = y + dir_dy(own), nx = x + dir_dx(own);
-        const int dcode = cs[(ny + ACS_Y0) * ACS_W + nx + ACS_X0];
-        if (dcode != CODE_OUTSIDE && dcode != OFL_DIR_NODATA) {
-          const uint32_t wv = word[y * AT + x];
-          if (wv >> 28) atomicExch(p.err, 1);  // never finished: the tile holds a cycle
-          atomicAdd(&p.S[node_of_cell(y0 + ny, x0 + nx, p)], (unsigned long long)(wv & 0x0FFFFFFFu));
+        if (ny < 0 || ny >= AT || nx < 0 || nx >= AT) {
+          const int dcode = cs[(ny + ACS_Y0) * ACS_W + nx + ACS_X0];
+          if (dcode == CODE_HALO_LIVE) {
+            const uint32_t wv = word[(y + 1) * WP + x + 1];
+            if (wv >> 28) atomicExch(p.err, 1);  // never finished: the tile holds a cycle
+            atomicAdd(&p.S[node_of_cell(y0 + ny, x0 + nx, p)], (unsigned long long)(wv & 0x0FFFFFFFu));
+          }
         }
       }
     }
@@ -350,10 +408,12 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
       for (int k = 0; k < 8; ++k) {
         const int y = 8 * warp + k;
         if (y < h && x < w) {
-          const int cell = y * AT + x;
+          const int wi = (y + 1) * WP + x + 1;
           const uint8_t own = cs[(y + ACS_Y0) * ACS_W + x + ACS_X0];
-          stuck |= ((cnt4[cell >> 2] >> (8 * (cell & 3))) & 0xFF) != 0;
-          const long long v = (own == OFL_DIR_NODATA) ? (long long)OFL_FAC_NODATA_EMITTED : (long long)val64[cell];
+          const uint32_t wv = word[wi];
+          long long v = (long long)(((unsigned long long)hiw[wi] << 24) | (wv & 0xFFFFFFu));
+          if (own == OFL_DIR_NODATA) v = OFL_FAC_NODATA_EMITTED;
+          else stuck |= (wv >> 28) != 0;
           p.fac[(int64_t)(y0 + y) * p.ld_fac + (x0 + x)] = v;
         }
       }
