@@ -106,7 +106,7 @@ __device__ __forceinline__ int node_of_cell(int gy, int gx, const AccParams& p) 
 // Kahn's algorithm inside one 64x64 tile, level-synchronous, frontier in a shared-memory queue:
 //   * every cell carries the number of in-tile upstream neighbours still missing, packed with its
 //     running count in one 32-bit word [missing:4 | count:28];
-//   * a finished cell hands its count to its downstream cell with ONE shared-memory atomicAdd of
+//   * a finished cell hands its count to its downstream cell with ONE shared-memory atomic add of
 //     (count - 1<<28): it adds the count and decrements the missing field at once, so the thread that
 //     sees the field drop to zero knows the sum is complete and appends the cell to the frontier
 //     (warp ballot + popc compaction, one queue atomic per warp);
@@ -116,6 +116,8 @@ __device__ __forceinline__ int node_of_cell(int gy, int gx, const AccParams& p) 
 //     a level never grows, so once it fits one warp, warp 0 finishes the tail alone.
 // Pass B carries 64-bit counts as (hi32 << 24) + lo24: the low 24 bits ride in the packed word (nine
 // 24-bit terms fit the 28-bit field), the high part goes through a second atomic only when non-zero.
+// Shared memory is addressed through explicit 32-bit shared-space addresses (ld/st/atom.shared):
+// the hot loop is ~40 instructions per 32 cells.
 constexpr int WP = 68;                 // word-array pitch: cells x = -1..64 in columns 0..65
 constexpr int WORDS = (AT + 2) * WP;   // rows y = -1..64
 constexpr int QMAX = AT * AT;
@@ -126,14 +128,52 @@ struct TileSmem {
   static constexpr int WORD = 6400;  // ACS_BYTES rounded up to 128
   static constexpr int HI = WORD + WORDS * 4;
   static constexpr int Q = HI + (FINAL ? WORDS * 4 : 0);
-  static constexpr int MISC = Q + QMAX * 2;
-  static constexpr int BYTES = MISC + 128;
+  static constexpr int TAB = Q + QMAX * 2;  // int2 per direction code: {word-array byte offset, cell-id offset}
+  static constexpr int TAIL = TAB + 64;
+  static constexpr int BAR = TAIL + 16;
+  static constexpr int BYTES = BAR + 16;
 };
 static_assert(ACS_BYTES <= 6400, "code tile does not fit its shared-memory slot");
 static_assert((WORDS * 4) % 16 == 0, "word array must be a whole number of uint4");
 
-__device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, int bits) {
-  return __funnelshift_r(lo, hi, bits);
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+  uint32_t v;
+  asm volatile("{.reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t;}" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
+  asm volatile("{.reg .u16 t; cvt.u16.u32 t, %1; st.shared.u16 [%0], t;}" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v) {
+  uint32_t o;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory");
+  return o;
+}
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
 }
 
 // per byte (all bytes < 16): 1 where the byte of `nb` differs from the code replicated in `pat`
@@ -146,15 +186,14 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
                                                                 const AccParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   using SM = TileSmem<FINAL>;
-  uint8_t* cs = smem_raw + SM::CS;                                   // codes + halo (TMA destination)
-  uint32_t* csw = reinterpret_cast<uint32_t*>(cs);
-  uint32_t* word = reinterpret_cast<uint32_t*>(smem_raw + SM::WORD);  // [missing:4 | count:28], halo-padded
-  uint32_t* hiw = reinterpret_cast<uint32_t*>(smem_raw + SM::HI);     // pass B: count >> 24
-  uint16_t* q = reinterpret_cast<uint16_t*>(smem_raw + SM::Q);        // frontier queue of cell ids (y*64+x)
-  int* off_idx = reinterpret_cast<int*>(smem_raw + SM::MISC);         // downstream offset in cell ids, per code
-  int* off_wi = off_idx + 8;                                           // same in word-array indices
-  uint32_t* tail = reinterpret_cast<uint32_t*>(off_idx + 16);
-  uint64_t& bar = *reinterpret_cast<uint64_t*>(smem_raw + SM::MISC + 96);
+  const uint32_t sb = smem_u32(smem_raw);
+  const uint32_t a_cs = sb + SM::CS;      // codes + halo (TMA destination), pitch ACS_W bytes
+  const uint32_t a_word = sb + SM::WORD;  // [missing:4 | count:28], halo-padded, pitch WP words
+  const uint32_t a_hi = sb + SM::HI;      // pass B: count >> 24, same layout
+  const uint32_t a_q = sb + SM::Q;        // frontier queue of cell ids (y*64+x), u16
+  const uint32_t a_tab = sb + SM::TAB;
+  const uint32_t a_tail = sb + SM::TAIL;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + SM::BAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x;
@@ -163,32 +202,33 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
   const int h = min(AT, p.rows - y0), w = min(AT, p.cols - x0);
 
   if (tid == 0) {
-    mbar_init(&bar, 1);
+    mbar_init(bar, 1);
     mbar_fence_init();
-    mbar_arrive_expect_tx(&bar, ACS_BYTES);
-    tma_load_2d(cs, &tm, x0 - ACS_X0, y0 - ACS_Y0, &bar);
-    *tail = 0;
+    mbar_arrive_expect_tx(bar, ACS_BYTES);
+    tma_load_2d(smem_raw + SM::CS, &tm, x0 - ACS_X0, y0 - ACS_Y0, bar);
+    sts32(a_tail, 0);
   }
   if (tid < 8) {
-    off_idx[tid] = dir_dy(tid) * AT + dir_dx(tid);
-    off_wi[tid] = dir_dy(tid) * WP + dir_dx(tid);
+    sts32(a_tab + 8 * tid, (uint32_t)((dir_dy(tid) * WP + dir_dx(tid)) * 4));
+    sts32(a_tab + 8 * tid + 4, (uint32_t)(dir_dy(tid) * AT + dir_dx(tid)));
   }
   {
-    uint4* z = reinterpret_cast<uint4*>(word);
-    constexpr int NZ = (FINAL ? 2 : 1) * WORDS / 4;  // word[] and hiw[] are adjacent
+    uint4* z = reinterpret_cast<uint4*>(smem_raw + SM::WORD);
+    constexpr int NZ = (FINAL ? 2 : 1) * WORDS / 4;  // word[] and hi[] are adjacent
     for (int i = tid; i < NZ; i += ACC_THREADS) z[i] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
-  mbar_wait(&bar, 0);
+  mbar_wait(bar, 0);
 
   // ---- phase 0: invalid codes (>= 10) -> 8; halo ring -> {9 nodata, 14 live} so it can never look like
   //      an in-tile upstream; then positions outside the raster (TMA zero fill) -> CODE_OUTSIDE
   const int qx = lane & 15, rp = lane >> 4;
+  constexpr int RWB = ACS_W;  // code row pitch in bytes
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int y = 8 * warp + 2 * i + rp;
-    const int cw = (y + ACS_Y0) * (ACS_W / 4) + ACS_X0 / 4 + qx;
-    const uint32_t v = csw[cw];
+    const uint32_t a = a_cs + (y + ACS_Y0) * RWB + ACS_X0 + 4 * qx;
+    const uint32_t v = lds32(a);
     if ((v + 0x06060606u) & 0xF0F0F0F0u) {  // some byte >= 10: invalid input, behaves like "no downstream"
       uint32_t f = 0;
 #pragma unroll
@@ -197,7 +237,7 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
         if (c >= 10) c = OFL_DIR_UNDEFINED;
         f |= c << (8 * b);
       }
-      csw[cw] = f;
+      sts32(a, f);
     }
   }
   for (int t = tid; t < 4 * AT + 4; t += ACC_THREADS) {
@@ -218,8 +258,8 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
       hy = (t & 1) ? AT : -1;
       hx = (t & 2) ? AT : -1;
     }
-    uint8_t* hp = cs + (hy + ACS_Y0) * ACS_W + hx + ACS_X0;
-    *hp = (*hp == OFL_DIR_NODATA) ? (uint8_t)OFL_DIR_NODATA : CODE_HALO_LIVE;
+    const uint32_t a = a_cs + (hy + ACS_Y0) * RWB + hx + ACS_X0;
+    sts8(a, lds8(a) == OFL_DIR_NODATA ? (uint32_t)OFL_DIR_NODATA : (uint32_t)CODE_HALO_LIVE);
   }
   __syncthreads();
   const bool edge_tile = (y0 == 0) || (x0 == 0) || (y0 + AT + 1 > p.rows) || (x0 + AT + 1 > p.cols);
@@ -227,49 +267,56 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     for (int idx = tid; idx < (int)ACS_BYTES; idx += ACC_THREADS) {
       const int yy = idx / ACS_W, xx = idx - yy * ACS_W;
       const int gy = y0 - ACS_Y0 + yy, gx = x0 - ACS_X0 + xx;
-      if (gy < 0 || gy >= p.rows || gx < 0 || gx >= p.cols) cs[idx] = CODE_OUTSIDE;
+      if (gy < 0 || gy >= p.rows || gx < 0 || gx >= p.cols) sts8(a_cs + idx, CODE_OUTSIDE);
     }
     __syncthreads();
   }
 
-  auto push = [&](bool ready, uint32_t idx) {
-    const uint32_t bal = __ballot_sync(0xffffffffu, ready);
-    if (bal) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(tail, __popc(bal));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (ready) q[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)idx;
-    }
-  };
+  const uint32_t lt_mask = lanemask_lt();
 
   // ---- phase 1: missing-counts for four cells at a time (byte-parallel), sources into the queue.
   //      Lane owns the quad of columns 4*qx..4*qx+3 in rows 8*warp + 2*i + rp.
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int y = 8 * warp + 2 * i + rp;
-    const int cw = (y + ACS_Y0) * (ACS_W / 4) + ACS_X0 / 4 + qx;
-    constexpr int RW = ACS_W / 4;
-    const uint32_t L0 = csw[cw - RW - 1], C0 = csw[cw - RW], R0 = csw[cw - RW + 1];
-    const uint32_t L1 = csw[cw - 1], C1 = csw[cw], R1 = csw[cw + 1];
-    const uint32_t L2 = csw[cw + RW - 1], C2 = csw[cw + RW], R2 = csw[cw + RW + 1];
+    const uint32_t a = a_cs + (y + ACS_Y0) * RWB + ACS_X0 + 4 * qx;
+    const uint32_t L0 = lds32(a - RWB - 4), C0 = lds32(a - RWB), R0 = lds32(a - RWB + 4);
+    const uint32_t L1 = lds32(a - 4), C1 = lds32(a), R1 = lds32(a + 4);
+    const uint32_t L2 = lds32(a + RWB - 4), C2 = lds32(a + RWB), R2 = lds32(a + RWB + 4);
     // a neighbour flows into the cell iff its code is the direction pointing back at it
-    uint32_t nm = bytes_differ(funnel_r(C1, R1, 8), 0x04040404u);   // E neighbour flowing W
-    nm += bytes_differ(funnel_r(C0, R0, 8), 0x05050505u);           // NE neighbour flowing SW
-    nm += bytes_differ(C0, 0x06060606u);                            // N neighbour flowing S
-    nm += bytes_differ(funnel_r(L0, C0, 24), 0x07070707u);          // NW neighbour flowing SE
-    nm += bytes_differ(funnel_r(L1, C1, 24), 0x00000000u);          // W neighbour flowing E
-    nm += bytes_differ(funnel_r(L2, C2, 24), 0x01010101u);          // SW neighbour flowing NE
-    nm += bytes_differ(C2, 0x02020202u);                            // S neighbour flowing N
-    nm += bytes_differ(funnel_r(C2, R2, 8), 0x03030303u);           // SE neighbour flowing NW
-    const uint32_t cnt4 = 0x08080808u - nm;                         // missing upstream neighbours per cell
-    // not a source: missing != 0, or the cell is NODATA / outside (own code >= 9)
-    const uint32_t notsrc = ((cnt4 + 0x7F7F7F7Fu) | (C1 + 0x77777777u)) & 0x80808080u;
-    const int idx0 = y * AT + 4 * qx;
-    const int wi0 = (y + 1) * WP + 4 * qx + 1;
+    uint32_t nm = bytes_differ(__funnelshift_r(C1, R1, 8), 0x04040404u);  // E neighbour flowing W
+    nm += bytes_differ(__funnelshift_r(C0, R0, 8), 0x05050505u);          // NE neighbour flowing SW
+    nm += bytes_differ(C0, 0x06060606u);                                  // N neighbour flowing S
+    nm += bytes_differ(__funnelshift_r(L0, C0, 24), 0x07070707u);         // NW neighbour flowing SE
+    nm += bytes_differ(__funnelshift_r(L1, C1, 24), 0x00000000u);         // W neighbour flowing E
+    nm += bytes_differ(__funnelshift_r(L2, C2, 24), 0x01010101u);         // SW neighbour flowing NE
+    nm += bytes_differ(C2, 0x02020202u);                                  // S neighbour flowing N
+    nm += bytes_differ(__funnelshift_r(C2, R2, 8), 0x03030303u);          // SE neighbour flowing NW
+    const uint32_t cnt4 = 0x08080808u - nm;  // missing upstream neighbours per cell
+    // source: missing == 0 and the cell is a data cell (own code <= 8)
+    const uint32_t src = ~((cnt4 + 0x7F7F7F7Fu) | (C1 + 0x77777777u)) & 0x80808080u;
+    const uint32_t idx0 = y * AT + 4 * qx;
+    const uint32_t aw = a_word + ((y + 1) * WP + 4 * qx + 1) * 4;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) sts32(aw + 4 * b, ((cnt4 >> (8 * b)) & 0xFu) << 28);
+    // append this warp's sources: exclusive scan of per-lane source counts, one queue atomic per warp
+    const uint32_t mine = __popc(src);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    uint32_t base = 0;
+    if (lane == 31) base = atoms_add(a_tail, incl);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    uint32_t aq = a_q + 2 * (base + incl - mine);
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      word[wi0 + b] = ((cnt4 >> (8 * b)) & 0xFu) << 28;
-      push(!((notsrc >> (8 * b)) & 0x80u), idx0 + b);
+      if (src & (0x80u << (8 * b))) {
+        sts16(aq, idx0 + b);
+        aq += 2;
+      }
     }
   }
   __syncthreads();
@@ -279,71 +326,79 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     if (cell_of_slot(tid, h, w, y, x)) {
       const unsigned long long seed = p.S[(size_t)tile * SLOTS + tid];
       if (seed) {
-        const int wi = (y + 1) * WP + x + 1;
-        word[wi] += (uint32_t)(seed & 0xFFFFFFu);
-        hiw[wi] = (uint32_t)(seed >> 24);
+        const uint32_t o = ((y + 1) * WP + x + 1) * 4;
+        sts32(a_word + o, lds32(a_word + o) + (uint32_t)(seed & 0xFFFFFFu));
+        sts32(a_hi + o, (uint32_t)(seed >> 24));
       }
     }
     __syncthreads();
   }
 
   // finish cell `idx`, hand its count downstream; append the downstream cell if that completed it
+  const uint32_t a_word0 = a_word + (WP + 1) * 4;                    // word of cell (0,0)
+  const uint32_t a_hi0 = a_hi + (WP + 1) * 4;
+  const uint32_t a_cs0 = a_cs + ACS_W * ACS_Y0 + ACS_X0;             // code of cell (0,0)
   auto process = [&](uint32_t idx, bool active) {
     bool ready = false;
     uint32_t nidx = 0;
     if (active) {
       const uint32_t yy = idx >> AT_SHIFT;
-      const uint32_t wi = idx + 4 * yy + (WP + 1);
-      const uint32_t code = cs[idx + (ACS_W - AT) * yy + (ACS_W * ACS_Y0 + ACS_X0)];
-      const uint32_t s = word[wi] & 0x0FFFFFFFu;
+      const uint32_t ow = idx * 4 + yy * 16;  // ((y+1)*WP + x+1)*4 relative to cell (0,0)
+      const uint32_t code = lds8(a_cs0 + idx + (ACS_W - AT) * yy);
+      const uint32_t s = lds32(a_word0 + ow) & 0x0FFFFFFFu;
       uint32_t lo, hn = 0;
       if (FINAL) {
-        const unsigned long long v = ((unsigned long long)hiw[wi] << 24) + s + 1;
+        const unsigned long long v = ((unsigned long long)lds32(a_hi0 + ow) << 24) + s + 1;
         lo = (uint32_t)v & 0xFFFFFFu;
         hn = (uint32_t)(v >> 24);
-        hiw[wi] = hn;
+        sts32(a_hi0 + ow, hn);
       } else {
         lo = s + 1;
       }
-      word[wi] = lo;
+      sts32(a_word0 + ow, lo);
       if (code < 8) {
-        const uint32_t nwi = wi + off_wi[code];
-        nidx = idx + off_idx[code];
+        const uint2 t = lds64(a_tab + 8 * code);
+        nidx = idx + t.y;
         if (FINAL && hn) {
-          atomicAdd(&hiw[nwi], hn);
+          atoms_add(a_hi0 + ow + t.x, hn);
           __threadfence_block();  // the high part must be in place before the count can reach zero
         }
-        const uint32_t old = atomicAdd(&word[nwi], lo - (1u << 28));
+        const uint32_t old = atoms_add(a_word0 + ow + t.x, lo - (1u << 28));
         ready = (old >> 28) == 1;
       }
     }
-    push(ready, nidx);
+    const uint32_t bal = __ballot_sync(0xffffffffu, ready);
+    if (bal) {
+      uint32_t base = 0;
+      if (lane == 0) base = atoms_add(a_tail, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (ready) sts16(a_q + 2 * (base + __popc(bal & lt_mask)), nidx);
+    }
   };
 
   // ---- level-synchronous sweep: level k is q[lo, hi); processing it appends level k+1 after it
-  uint32_t lo = 0, hi = *tail;
+  uint32_t lo = 0, hi = lds32(a_tail);
   __syncthreads();
   while (hi - lo > 32) {
     for (uint32_t base = lo + 32 * warp; base < hi; base += ACC_THREADS) {
       const uint32_t i = base + lane;
       const bool active = i < hi;
-      process(active ? q[i] : 0u, active);
+      process(active ? lds16(a_q + 2 * i) : 0u, active);
     }
     __syncthreads();
-    const uint32_t nh = *tail;
+    const uint32_t nh = lds32(a_tail);
     __syncthreads();  // nobody appends to the next level before everyone has read where this one ends
     lo = hi;
     hi = nh;
   }
   if (warp == 0) {
-    volatile uint32_t* vtail = tail;
     while (lo < hi) {
       const uint32_t i = lo + lane;
       const bool active = i < hi;
-      process(active ? q[i] : 0u, active);
+      process(active ? lds16(a_q + 2 * i) : 0u, active);
       __syncwarp();
       lo = hi;
-      hi = *vtail;
+      hi = lds32(a_tail);
       __syncwarp();
     }
   }
@@ -356,40 +411,41 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     int32_t succ = -1;
     uint16_t lk = KIND_TERM << 8;
     if (cell_of_slot(s, h, w, y, x)) {
-      int cy = y, cx = x;
+      // walk while the downstream cell is a live in-tile cell (codes 9 nodata, 14 live halo, 15 outside stop it)
+      uint32_t idx = y * AT + x;
+      uint32_t code = lds8(a_cs0 + idx + (ACS_W - AT) * y), dcode = 0;
+      int dy = 0, dx = 0;
+      for (int steps = 0; code < 8; ++steps) {
+        dy = dir_dy(code);
+        dx = dir_dx(code);
+        const uint32_t nidx = idx + dy * AT + dx;
+        dcode = lds8(a_cs0 + idx + (ACS_W - AT) * (idx >> AT_SHIFT) + dy * ACS_W + dx);
+        if (dcode > 8 || steps > AT * AT) break;
+        idx = nidx;
+        code = dcode;
+        if (code == 8) break;
+      }
+      const int cy = idx >> AT_SHIFT, cx = idx & (AT - 1);
       uint16_t kind = KIND_TERM;
-      for (int steps = 0;; ++steps) {
-        const int code = cs[(cy + ACS_Y0) * ACS_W + cx + ACS_X0];
-        if (code >= 8) break;  // pit / flat / nodata: the path ends here
-        const int ny = cy + dir_dy(code), nx = cx + dir_dx(code);
-        const int dcode = cs[(ny + ACS_Y0) * ACS_W + nx + ACS_X0];
+      if (code < 8) {
         if (dcode == CODE_OUTSIDE) {
           kind = KIND_RASTER_EXIT;
-          break;
-        }
-        if (dcode == OFL_DIR_NODATA) break;
-        if (ny < 0 || ny >= AT || nx < 0 || nx >= AT) {
+        } else if (dcode == CODE_HALO_LIVE) {
           kind = KIND_TILE_EXIT;
-          succ = node_of_cell(y0 + ny, x0 + nx, p);
-          break;
-        }
-        cy = ny;
-        cx = nx;
-        if (steps > AT * AT) {
-          atomicExch(p.err, 1);
-          break;
+          succ = node_of_cell(y0 + cy + dy, x0 + cx + dx, p);
+        } else if (dcode != OFL_DIR_NODATA) {
+          atomicExch(p.err, 1);  // ran out of steps: cycle inside the tile
         }
       }
       const int ls = slot_of(cy, cx, h, w);
       lk = (uint16_t)((ls < 0 ? 0 : ls) | (kind << 8));
       // this cell's own edge across the tile boundary carries its local count to the next tile
-      const int own = cs[(y + ACS_Y0) * ACS_W + x + ACS_X0];
+      const uint32_t own = lds8(a_cs0 + y * ACS_W + x);
       if (own < 8) {
         const int ny = y + dir_dy(own), nx = x + dir_dx(own);
         if (ny < 0 || ny >= AT || nx < 0 || nx >= AT) {
-          const int dcode = cs[(ny + ACS_Y0) * ACS_W + nx + ACS_X0];
-          if (dcode == CODE_HALO_LIVE) {
-            const uint32_t wv = word[(y + 1) * WP + x + 1];
+          if (lds8(a_cs0 + ny * ACS_W + nx) == CODE_HALO_LIVE) {
+            const uint32_t wv = lds32(a_word0 + (y * WP + x) * 4);
             if (wv >> 28) atomicExch(p.err, 1);  // never finished: the tile holds a cycle
             atomicAdd(&p.S[node_of_cell(y0 + ny, x0 + nx, p)], (unsigned long long)(wv & 0x0FFFFFFFu));
           }
@@ -408,10 +464,10 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
       for (int k = 0; k < 8; ++k) {
         const int y = 8 * warp + k;
         if (y < h && x < w) {
-          const int wi = (y + 1) * WP + x + 1;
-          const uint8_t own = cs[(y + ACS_Y0) * ACS_W + x + ACS_X0];
-          const uint32_t wv = word[wi];
-          long long v = (long long)(((unsigned long long)hiw[wi] << 24) | (wv & 0xFFFFFFu));
+          const uint32_t o = (y * WP + x) * 4;
+          const uint32_t own = lds8(a_cs0 + y * ACS_W + x);
+          const uint32_t wv = lds32(a_word0 + o);
+          long long v = (long long)(((unsigned long long)lds32(a_hi0 + o) << 24) | (wv & 0xFFFFFFu));
           if (own == OFL_DIR_NODATA) v = OFL_FAC_NODATA_EMITTED;
           else stuck |= (wv >> 28) != 0;
           p.fac[(int64_t)(y0 + y) * p.ld_fac + (x0 + x)] = v;
