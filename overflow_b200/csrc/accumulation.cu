@@ -113,7 +113,8 @@ __device__ __forceinline__ int node_of_cell(int gy, int gx, const AccParams& p) 
 //   * the word array has a one-cell halo and no edge is ever skipped: hand-offs into the halo, into
 //     NODATA cells or out of the raster land in words nobody reads;
 //   * frontier levels are consecutive segments of one 4096-entry queue (a cell is appended once);
-//     a level never grows, so once it fits one warp, warp 0 finishes the tail alone.
+//     a level never grows, so once it fits one cell per thread each thread simply follows its chain
+//     (it continues exactly when its hand-off completed the next cell): no queue, no barriers.
 // Pass B carries 64-bit counts as (hi32 << 24) + lo24: the low 24 bits ride in the packed word (nine
 // 24-bit terms fit the 28-bit field), the high part goes through a second atomic only when non-zero.
 // Shared memory is addressed through explicit 32-bit shared-space addresses (ld/st/atom.shared):
@@ -334,56 +335,52 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     __syncthreads();
   }
 
-  // finish cell `idx`, hand its count downstream; append the downstream cell if that completed it
-  const uint32_t a_word0 = a_word + (WP + 1) * 4;                    // word of cell (0,0)
+  // finish cell `idx` and hand its count downstream; returns true (and the downstream cell id in
+  // `nidx`) when that hand-off was the last one the downstream cell was waiting for
+  const uint32_t a_word0 = a_word + (WP + 1) * 4;         // word of cell (0,0)
   const uint32_t a_hi0 = a_hi + (WP + 1) * 4;
-  const uint32_t a_cs0 = a_cs + ACS_W * ACS_Y0 + ACS_X0;             // code of cell (0,0)
-  auto process = [&](uint32_t idx, bool active) {
-    bool ready = false;
-    uint32_t nidx = 0;
-    if (active) {
-      const uint32_t yy = idx >> AT_SHIFT;
-      const uint32_t ow = idx * 4 + yy * 16;  // ((y+1)*WP + x+1)*4 relative to cell (0,0)
-      const uint32_t code = lds8(a_cs0 + idx + (ACS_W - AT) * yy);
-      const uint32_t s = lds32(a_word0 + ow) & 0x0FFFFFFFu;
-      uint32_t lo, hn = 0;
-      if (FINAL) {
-        const unsigned long long v = ((unsigned long long)lds32(a_hi0 + ow) << 24) + s + 1;
-        lo = (uint32_t)v & 0xFFFFFFu;
-        hn = (uint32_t)(v >> 24);
-        sts32(a_hi0 + ow, hn);
-      } else {
-        lo = s + 1;
-      }
-      sts32(a_word0 + ow, lo);
-      if (code < 8) {
-        const uint2 t = lds64(a_tab + 8 * code);
-        nidx = idx + t.y;
-        if (FINAL && hn) {
-          atoms_add(a_hi0 + ow + t.x, hn);
-          __threadfence_block();  // the high part must be in place before the count can reach zero
-        }
-        const uint32_t old = atoms_add(a_word0 + ow + t.x, lo - (1u << 28));
-        ready = (old >> 28) == 1;
-      }
+  const uint32_t a_cs0 = a_cs + ACS_W * ACS_Y0 + ACS_X0;  // code of cell (0,0)
+  auto finish = [&](uint32_t idx, uint32_t& nidx) -> bool {
+    const uint32_t yy = idx >> AT_SHIFT;
+    const uint32_t ow = idx * 4 + yy * 16;  // ((y+1)*WP + x+1)*4 relative to cell (0,0)
+    const uint32_t code = lds8(a_cs0 + idx + (ACS_W - AT) * yy);
+    const uint32_t s = lds32(a_word0 + ow) & 0x0FFFFFFFu;
+    uint32_t lo, hn = 0;
+    if (FINAL) {
+      const unsigned long long v = ((unsigned long long)lds32(a_hi0 + ow) << 24) + s + 1;
+      lo = (uint32_t)v & 0xFFFFFFu;
+      hn = (uint32_t)(v >> 24);
+      sts32(a_hi0 + ow, hn);
+    } else {
+      lo = s + 1;
     }
-    const uint32_t bal = __ballot_sync(0xffffffffu, ready);
-    if (bal) {
-      uint32_t base = 0;
-      if (lane == 0) base = atoms_add(a_tail, __popc(bal));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (ready) sts16(a_q + 2 * (base + __popc(bal & lt_mask)), nidx);
+    sts32(a_word0 + ow, lo);
+    if (code >= 8) return false;
+    const uint2 t = lds64(a_tab + 8 * code);
+    nidx = idx + t.y;
+    if (FINAL && hn) {
+      atoms_add(a_hi0 + ow + t.x, hn);
+      __threadfence_block();  // the high part must be in place before the count can reach zero
     }
+    const uint32_t old = atoms_add(a_word0 + ow + t.x, lo - (1u << 28));
+    return (old >> 28) == 1;
   };
 
-  // ---- level-synchronous sweep: level k is q[lo, hi); processing it appends level k+1 after it
+  // ---- wide levels: level k is q[lo, hi); processing it appends level k+1 right after it
   uint32_t lo = 0, hi = lds32(a_tail);
   __syncthreads();
-  while (hi - lo > 32) {
+  while (hi - lo > ACC_THREADS) {
     for (uint32_t base = lo + 32 * warp; base < hi; base += ACC_THREADS) {
       const uint32_t i = base + lane;
-      const bool active = i < hi;
-      process(active ? lds16(a_q + 2 * i) : 0u, active);
+      uint32_t nidx = 0;
+      const bool ready = (i < hi) && finish(lds16(a_q + 2 * i), nidx);
+      const uint32_t bal = __ballot_sync(0xffffffffu, ready);
+      if (bal) {
+        uint32_t qb = 0;
+        if (lane == 0) qb = atoms_add(a_tail, __popc(bal));
+        qb = __shfl_sync(0xffffffffu, qb, 0);
+        if (ready) sts16(a_q + 2 * (qb + __popc(bal & lt_mask)), nidx);
+      }
     }
     __syncthreads();
     const uint32_t nh = lds32(a_tail);
@@ -391,16 +388,11 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     lo = hi;
     hi = nh;
   }
-  if (warp == 0) {
-    while (lo < hi) {
-      const uint32_t i = lo + lane;
-      const bool active = i < hi;
-      process(active ? lds16(a_q + 2 * i) : 0u, active);
-      __syncwarp();
-      lo = hi;
-      hi = lds32(a_tail);
-      __syncwarp();
-    }
+  // ---- narrow tail (a level never grows): one thread per frontier cell follows its chain for as
+  //      long as its hand-off is the one that completes the next cell; no queue, no barriers
+  if (lo + tid < hi) {
+    uint32_t idx = lds16(a_q + 2 * (lo + tid)), nidx = 0;
+    while (finish(idx, nidx)) idx = nidx;
   }
   __syncthreads();
 
