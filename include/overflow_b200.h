@@ -146,6 +146,35 @@ int ofl_check_accumulation_u8(const uint8_t* fdr, int64_t rows, int64_t cols, in
 int ofl_fill_border_u8(uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, int value, void* stream);
 
 /*
+ * Row strips (one per GPU).  A strip is `rows` consecutive raster rows, all columns; strips that have a
+ * strip below them must have a multiple of 64 rows.  `fdr_halo` is the strip's code raster with ONE halo
+ * row above and below: (rows+2) x cols, row 0 = last row of the strip above, row rows+1 = first row of
+ * the strip below (contents ignored where has_above / has_below is 0: that side is the raster edge).
+ * All pointers are DEVICE pointers; fdr_halo 16-byte aligned with ld_fdr % 16 == 0.
+ *
+ *   1. ofl_strip_accum_local     strip-local solve; writes the boundary records of the strip's first
+ *                                (t=0) and last (t=1) row, each [2][cols]: slink (int32: (exit row selector
+ *                                << 30) | exit column of the cell where the path leaves the strip, or -1),
+ *                                floc (int64 strip-local count), bcode (uint8 direction code).
+ *                                `fac` (rows x cols) is used as scratch for the boundary rows.
+ *   2. all-gather the three records over the strips in order (caller; NCCL)  -> [n_strips][2][cols]
+ *   3. ofl_strip_boundary_solve  same on every GPU: inflow from other strips into every boundary cell,
+ *                                J_all [n_strips][2][cols] int64
+ *   4. ofl_strip_accum_final     J_mine = J_all[this strip]; writes the final counts of the strip to `fac`
+ * The strip workspace must be the same buffer in steps 1 and 4.  All four calls synchronise the stream.
+ */
+size_t ofl_strip_workspace_bytes(int64_t rows, int64_t cols);
+size_t ofl_strip_boundary_workspace_bytes(int n_strips, int64_t cols);
+int ofl_strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above,
+                          int has_below, int64_t* fac, int64_t ld_fac, void* workspace, size_t workspace_bytes,
+                          int32_t* slink, int64_t* floc, uint8_t* bcode, void* stream);
+int ofl_strip_boundary_solve(const int32_t* slink_all, const int64_t* floc_all, const uint8_t* bcode_all, int n_strips,
+                             int64_t cols, int64_t* J_all, void* workspace, size_t workspace_bytes, void* stream);
+int ofl_strip_accum_final(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above,
+                          int has_below, const int64_t* J_mine, void* workspace, size_t workspace_bytes, int64_t* fac,
+                          int64_t ld_fac, void* stream);
+
+/*
  * Seeded synthetic DEM written straight into device memory (benchmarks / large parity runs).
  * Cell (row0 + r, c) depends only on its global coordinates and the seed, so every rank of a
  * row-strip run can synthesise its own strip and halo rows.

@@ -45,6 +45,11 @@ SIGNATURES = {
     "ofl_flow_accumulation_u8": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _sz, _int, _vp]),
     "ofl_check_accumulation_u8": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, ctypes.POINTER(_i64), _int, _vp]),
     "ofl_fill_border_u8": (_int, [_vp, _i64, _i64, _i64, _int, _vp]),
+    "ofl_strip_workspace_bytes": (_sz, [_i64, _i64]),
+    "ofl_strip_boundary_workspace_bytes": (_sz, [_int, _i64]),
+    "ofl_strip_accum_local": (_int, [_vp, _i64, _i64, _i64, _int, _int, _vp, _i64, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "ofl_strip_boundary_solve": (_int, [_vp, _vp, _vp, _int, _i64, _vp, _vp, _sz, _vp]),
+    "ofl_strip_accum_final": (_int, [_vp, _i64, _i64, _i64, _int, _int, _vp, _vp, _sz, _vp, _i64, _vp]),
     "ofl_synth_dem_f32": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, ctypes.c_uint64, _int, ctypes.c_float, _int,
                                  ctypes.c_float, _vp]),
 }

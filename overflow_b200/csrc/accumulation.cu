@@ -46,11 +46,13 @@ constexpr int SLOTS = 4 * AT;          // perimeter slots per tile (top, bottom,
 constexpr int ACC_THREADS = 256;
 constexpr uint8_t CODE_OUTSIDE = 15;   // positions outside the raster (halo or partial tile)
 constexpr uint8_t CODE_HALO_LIVE = 14; // halo cell that is a live (non-NODATA) cell of the next tile
+constexpr uint8_t CODE_HALO_STRIP = 13; // halo cell that is a live cell of the neighbouring row strip (another GPU)
 
 // node kinds, stored in link[] bits 8..9
 constexpr uint16_t KIND_TERM = 0;        // path ends inside the raster (pit, or downstream is NODATA)
 constexpr uint16_t KIND_TILE_EXIT = 1;   // path continues in the next tile (succ >= 0)
 constexpr uint16_t KIND_RASTER_EXIT = 2; // path leaves the raster at the link cell
+constexpr uint16_t KIND_STRIP_EXIT = 3;  // path continues in the neighbouring row strip (resolved by the strip exchange)
 
 __device__ __forceinline__ int dir_dy(int code) { return ((0xA901 >> (2 * code)) & 3) - 1; }  // dy+1 = 1,0,0,0,1,2,2,2
 __device__ __forceinline__ int dir_dx(int code) { return ((0x901A >> (2 * code)) & 3) - 1; }  // dx+1 = 2,2,1,0,0,0,1,2
@@ -94,6 +96,10 @@ struct AccParams {
   long long* fac;
   int64_t ld_fac;
   int* err;  // device flag: set to 1 when a cycle is detected
+  // row-strip mode: the code raster has y_off halo rows above row 0 (and as many below the last row)
+  // holding the neighbouring strips' rows; strip_above / strip_below say whether a strip exists there
+  int y_off, strip_above, strip_below;
+  int tile_base;  // first tile handled by this launch (blockIdx.x + tile_base)
 };
 
 __device__ __forceinline__ int node_of_cell(int gy, int gx, const AccParams& p) {
@@ -122,6 +128,10 @@ __device__ __forceinline__ int node_of_cell(int gy, int gx, const AccParams& p) 
 constexpr int WP = 68;                 // word-array pitch: cells x = -1..64 in columns 0..65
 constexpr int WORDS = (AT + 2) * WP;   // rows y = -1..64
 constexpr int QMAX = AT * AT;
+#ifndef OFL_WALK_PER_THREAD
+#define OFL_WALK_PER_THREAD 1
+#endif
+constexpr int WALK_PER_THREAD = OFL_WALK_PER_THREAD;  // switch to chain walking once a level has <= this many cells per thread
 
 template <bool FINAL>
 struct TileSmem {
@@ -197,7 +207,7 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + SM::BAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x;
+  const int tile = blockIdx.x + p.tile_base;
   const int ty = tile / p.ntx, tx = tile - ty * p.ntx;
   const int y0 = ty << AT_SHIFT, x0 = tx << AT_SHIFT;
   const int h = min(AT, p.rows - y0), w = min(AT, p.cols - x0);
@@ -206,7 +216,7 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     mbar_init(bar, 1);
     mbar_fence_init();
     mbar_arrive_expect_tx(bar, ACS_BYTES);
-    tma_load_2d(smem_raw + SM::CS, &tm, x0 - ACS_X0, y0 - ACS_Y0, bar);
+    tma_load_2d(smem_raw + SM::CS, &tm, x0 - ACS_X0, y0 - ACS_Y0 + p.y_off, bar);
     sts32(a_tail, 0);
   }
   if (tid < 8) {
@@ -260,18 +270,29 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
       hx = (t & 2) ? AT : -1;
     }
     const uint32_t a = a_cs + (hy + ACS_Y0) * RWB + hx + ACS_X0;
-    sts8(a, lds8(a) == OFL_DIR_NODATA ? (uint32_t)OFL_DIR_NODATA : (uint32_t)CODE_HALO_LIVE);
+    const int gy = y0 + hy, gx = x0 + hx;
+    const bool nodata = lds8(a) == OFL_DIR_NODATA;
+    uint32_t c;
+    if (gx < 0 || gx >= p.cols) {
+      c = CODE_OUTSIDE;
+    } else if (gy < 0) {
+      c = p.strip_above ? (nodata ? (uint32_t)OFL_DIR_NODATA : (uint32_t)CODE_HALO_STRIP) : (uint32_t)CODE_OUTSIDE;
+    } else if (gy >= p.rows) {
+      c = p.strip_below ? (nodata ? (uint32_t)OFL_DIR_NODATA : (uint32_t)CODE_HALO_STRIP) : (uint32_t)CODE_OUTSIDE;
+    } else {
+      c = nodata ? (uint32_t)OFL_DIR_NODATA : (uint32_t)CODE_HALO_LIVE;
+    }
+    sts8(a, c);
+  }
+  if (h < AT || w < AT) {
+    // partial tile at the raster's bottom / right edge: in-tile positions beyond the raster
+    __syncthreads();  // the word-wise sanitise above must not race with these byte stores
+    for (int idx = tid; idx < AT * AT; idx += ACC_THREADS) {
+      const int yy = idx >> AT_SHIFT, xx = idx & (AT - 1);
+      if (yy >= h || xx >= w) sts8(a_cs + (yy + ACS_Y0) * RWB + xx + ACS_X0, CODE_OUTSIDE);
+    }
   }
   __syncthreads();
-  const bool edge_tile = (y0 == 0) || (x0 == 0) || (y0 + AT + 1 > p.rows) || (x0 + AT + 1 > p.cols);
-  if (edge_tile) {
-    for (int idx = tid; idx < (int)ACS_BYTES; idx += ACC_THREADS) {
-      const int yy = idx / ACS_W, xx = idx - yy * ACS_W;
-      const int gy = y0 - ACS_Y0 + yy, gx = x0 - ACS_X0 + xx;
-      if (gy < 0 || gy >= p.rows || gx < 0 || gx >= p.cols) sts8(a_cs + idx, CODE_OUTSIDE);
-    }
-    __syncthreads();
-  }
 
   const uint32_t lt_mask = lanemask_lt();
 
@@ -369,7 +390,7 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
   // ---- wide levels: level k is q[lo, hi); processing it appends level k+1 right after it
   uint32_t lo = 0, hi = lds32(a_tail);
   __syncthreads();
-  while (hi - lo > ACC_THREADS) {
+  while (hi - lo > WALK_PER_THREAD * ACC_THREADS) {
     for (uint32_t base = lo + 32 * warp; base < hi; base += ACC_THREADS) {
       const uint32_t i = base + lane;
       uint32_t nidx = 0;
@@ -390,8 +411,8 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
   }
   // ---- narrow tail (a level never grows): one thread per frontier cell follows its chain for as
   //      long as its hand-off is the one that completes the next cell; no queue, no barriers
-  if (lo + tid < hi) {
-    uint32_t idx = lds16(a_q + 2 * (lo + tid)), nidx = 0;
+  for (uint32_t i = lo + tid; i < hi; i += ACC_THREADS) {
+    uint32_t idx = lds16(a_q + 2 * i), nidx = 0;
     while (finish(idx, nidx)) idx = nidx;
   }
   __syncthreads();
@@ -425,6 +446,8 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
         } else if (dcode == CODE_HALO_LIVE) {
           kind = KIND_TILE_EXIT;
           succ = node_of_cell(y0 + cy + dy, x0 + cx + dx, p);
+        } else if (dcode == CODE_HALO_STRIP) {
+          kind = KIND_STRIP_EXIT;
         } else if (dcode != OFL_DIR_NODATA) {
           atomicExch(p.err, 1);  // ran out of steps: cycle inside the tile
         }
@@ -633,6 +656,75 @@ size_t accumulation_workspace_bytes(int64_t rows, int64_t cols) {
 
 constexpr int PJ_MAX_ROUNDS = 40;  // flags[0..40]: active-before-round j; flags[48]: cycle error
 
+static int ensure_tile_attrs() {
+  static bool attr_set = false;
+  if (!attr_set) {
+    OFL_CUDA(cudaFuncSetAttribute(acc_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TileSmem<false>::BYTES));
+    OFL_CUDA(cudaFuncSetAttribute(acc_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TileSmem<true>::BYTES));
+    attr_set = true;
+  }
+  return OFL_OK;
+}
+
+static inline int grid_for(int64_t n, int per_sm) {
+  const int64_t want = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * per_sm;
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+// Subtree sums over the forest `succ` (succ[u] = parent node or -1): on return S[u] holds the sum of
+// the initial S over u's subtree and *roots_out points at the buffer holding ~root(u) for every node.
+// ptr_a / ptr_b are ping-pong buffers (ptr_b may alias succ when succ need not survive); d0 / d1 must
+// be zero on entry.  Synchronises the stream (convergence is read back from the device flags).
+static int pj_solve(const int32_t* succ, int32_t* ptr_a, int32_t* ptr_b, unsigned long long* S,
+                    unsigned long long* d0, unsigned long long* d1, int* flags, int64_t n, cudaStream_t st,
+                    const int32_t** roots_out) {
+  const int blocks = grid_for(n, 8);
+  OFL_CUDA(cudaMemsetAsync(flags, 0, 48 * sizeof(int), st));
+  pj_init_kernel<<<blocks, 256, 0, st>>>(succ, ptr_a, n);
+  OFL_CHECK_LAUNCH();
+  {
+    const int one = 1;
+    OFL_CUDA(cudaMemcpyAsync(flags, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  int max_rounds = 2;
+  while ((1ll << (max_rounds - 1)) < n && max_rounds < PJ_MAX_ROUNDS) ++max_rounds;
+  int32_t* cur = ptr_a;
+  int32_t* nxt = ptr_b;
+  for (int j = 0; j < max_rounds; ++j) {
+    pj_round_kernel<<<blocks, 256, 0, st>>>(cur, nxt, S, (j & 1) ? d1 : d0, (j & 1) ? d0 : d1, flags + j,
+                                            flags + j + 1, n);
+    OFL_CHECK_LAUNCH();
+    int32_t* t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+  pj_fold_kernel<<<blocks, 256, 0, st>>>(S, d0, d1, n);
+  OFL_CHECK_LAUNCH();
+  // Rounds after convergence return early without writing ptr_out, so the converged pointers sit in
+  // whichever buffer the last ACTIVE round wrote: round j writes (j even ? ptr_b : ptr_a).
+  int h_flags[48];
+  OFL_CUDA(cudaMemcpyAsync(h_flags, flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+  OFL_CUDA(cudaStreamSynchronize(st));
+  OFL_REQUIRE(h_flags[max_rounds] == 0, OFL_ERR_CYCLE, "flow-direction raster contains a cycle (perimeter graph)");
+  int last_active = 0;
+  for (int j = 0; j < max_rounds; ++j)
+    if (h_flags[j]) last_active = j;
+  if (roots_out) *roots_out = (last_active & 1) == 0 ? ptr_b : ptr_a;
+  // d0 / d1 are zero again except for what the fold consumed: clear for the next solve
+  return OFL_OK;
+}
+
+static int check_cycle_flag(const int* err_flag, cudaStream_t st) {
+  int h = 0;
+  OFL_CUDA(cudaMemcpyAsync(&h, err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  OFL_CUDA(cudaStreamSynchronize(st));
+  OFL_REQUIRE(h == 0, OFL_ERR_CYCLE, "flow-direction raster contains a cycle");
+  return OFL_OK;
+}
+
 int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, long long* fac,
                         int64_t ld_fac, long long* perim_links_dev, void* workspace, size_t workspace_bytes,
                         cudaStream_t st) {
@@ -662,85 +754,337 @@ int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t 
   p.fac = fac;
   p.ld_fac = ld_fac;
   p.err = flags + 48;
+  p.y_off = 0;
+  p.strip_above = p.strip_below = 0;
+  p.tile_base = 0;
   const int64_t ntiles = (int64_t)p.nty * p.ntx;
   OFL_REQUIRE(ntiles < (1ll << 31), OFL_ERR_INVALID, "too many tiles");
 
   CUtensorMap tm;
   int rc = make_tensor_map_2d(&tm, fdr, 1, (uint64_t)cols, (uint64_t)rows, (uint64_t)ld_fdr, ACS_W, ACS_H);
   if (rc != OFL_OK) return rc;
+  rc = ensure_tile_attrs();
+  if (rc != OFL_OK) return rc;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    OFL_CUDA(cudaFuncSetAttribute(acc_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  TileSmem<false>::BYTES));
-    OFL_CUDA(cudaFuncSetAttribute(acc_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  TileSmem<true>::BYTES));
-    attr_set = true;
-  }
-
-  // S, d0, d1 are contiguous: one memset; flags: active-before-round-0 = 1, the rest 0
+  // S, d0, d1 are contiguous: one memset
   OFL_CUDA(cudaMemsetAsync(ws + L.off_S, 0, L.off_link - L.off_S, st));
   OFL_CUDA(cudaMemsetAsync(flags, 0, 64 * sizeof(int), st));
-
   {
     PhaseScope ps(PHASE_ACC_TILE_A, st);
     acc_tile_kernel<false><<<(unsigned)ntiles, ACC_THREADS, TileSmem<false>::BYTES, st>>>(tm, p);
   }
   OFL_CHECK_LAUNCH();
 
-  // reduced-graph solve
-  const int sms = sm_count();
-  const int pj_blocks = (int)(((L.n_nodes + 255) / 256) < (int64_t)sms * 8 ? ((L.n_nodes + 255) / 256) : (int64_t)sms * 8);
-  PhaseScope* solve_scope = new PhaseScope(PHASE_ACC_SOLVE, st);
-  int32_t* ptr_cur = ptr_b;
-  int32_t* ptr_nxt = p.succ;  // succ is dead once pj_init has consumed it
-  pj_init_kernel<<<pj_blocks, 256, 0, st>>>(p.succ, ptr_cur, L.n_nodes);
-  OFL_CHECK_LAUNCH();
+  // reduced-graph solve; succ is dead once pj_init has consumed it, so it doubles as a ping-pong buffer
+  const int32_t* roots = nullptr;
   {
-    const int one = 1;
-    OFL_CUDA(cudaMemcpyAsync(flags, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+    PhaseScope ps(PHASE_ACC_SOLVE, st);
+    rc = pj_solve(p.succ, ptr_b, p.succ, p.S, d0, d1, flags, L.n_nodes, st, &roots);
   }
-  int max_rounds = 2;
-  while ((1ll << (max_rounds - 1)) < L.n_nodes && max_rounds < PJ_MAX_ROUNDS) ++max_rounds;
-  for (int j = 0; j < max_rounds; ++j) {
-    pj_round_kernel<<<pj_blocks, 256, 0, st>>>(ptr_cur, ptr_nxt, p.S, (j & 1) ? d1 : d0, (j & 1) ? d0 : d1,
-                                               flags + j, flags + j + 1, L.n_nodes);
-    OFL_CHECK_LAUNCH();
-    int32_t* t = ptr_cur;
-    ptr_cur = ptr_nxt;
-    ptr_nxt = t;
-  }
-  pj_fold_kernel<<<pj_blocks, 256, 0, st>>>(p.S, d0, d1, L.n_nodes);
-  delete solve_scope;
-  OFL_CHECK_LAUNCH();
-
+  if (rc != OFL_OK) return rc;
   {
     PhaseScope ps(PHASE_ACC_TILE_B, st);
     acc_tile_kernel<true><<<(unsigned)ntiles, ACC_THREADS, TileSmem<true>::BYTES, st>>>(tm, p);
   }
   OFL_CHECK_LAUNCH();
-
-  // Rounds after convergence return early without writing ptr_out, so the converged pointers sit in
-  // whichever buffer the last ACTIVE round wrote: round j writes buffer (j even ? succ : ptr_b).
-  int h_flags[64];
-  OFL_CUDA(cudaMemcpyAsync(h_flags, flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
-  OFL_CUDA(cudaStreamSynchronize(st));
-  OFL_REQUIRE(h_flags[48] == 0, OFL_ERR_CYCLE, "flow-direction raster contains a cycle");
-  int last_active = -1;
-  for (int j = 0; j < max_rounds; ++j)
-    if (h_flags[j]) last_active = j;
-  OFL_REQUIRE(h_flags[max_rounds] == 0, OFL_ERR_CYCLE, "flow-direction raster contains a cycle (perimeter graph)");
+  rc = check_cycle_flag(p.err, st);
+  if (rc != OFL_OK) return rc;
   if (perim_links_dev) {
-    const int32_t* roots = (last_active < 0) ? ptr_b : ((last_active & 1) == 0 ? p.succ : ptr_b);
     const int64_t n = perimeter_count(rows, cols);
-    const int blocks = (int)((n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048);
     {
       PhaseScope ps(PHASE_ACC_LINKS, st);
-      links_kernel<<<blocks, 256, 0, st>>>(fdr, ld_fdr, roots, p.link, p, perim_links_dev, n);
+      links_kernel<<<grid_for(n, 16), 256, 0, st>>>(fdr, ld_fdr, roots, p.link, p, perim_links_dev, n);
     }
     OFL_CHECK_LAUNCH();
   }
   return OFL_OK;
+}
+
+// ================================================================ row strips (multi-GPU)
+// Barnes 2016 at the strip level.  Each GPU owns a row strip [r0, r1) whose boundaries are multiples of
+// the tile side, and holds the codes of the neighbouring strips' adjacent rows as halo rows.
+//   local     pass A + solve with cross-strip edges as roots; pass B on the first and last tile row only
+//             gives the strip-local counts of the boundary rows; emit for every boundary-row cell its
+//             local count, its code and the boundary cell where its in-strip path leaves the strip
+//   exchange  all-gather of those 13 B/cell boundary records (done by the caller, NCCL)
+//   solve     the same pointer-doubling solve on the boundary forest (2 rows x cols x strips nodes),
+//             replicated on every GPU: inflow from other strips into every boundary cell
+//   final     push the strip's inflows down its own perimeter graph (second solve on seeds only, by
+//             linearity), then pass B over all tiles
+struct StripLayout {
+  int64_t n_nodes;
+  size_t off_succ, off_pa, off_pb, off_S, off_S2, off_d0, off_d1, off_link, off_flags, total;
+};
+
+static StripLayout strip_layout(int64_t rows, int64_t cols) {
+  StripLayout L;
+  const int64_t nty = (rows + AT - 1) / AT, ntx = (cols + AT - 1) / AT;
+  L.n_nodes = nty * ntx * SLOTS;
+  size_t o = 0;
+  L.off_succ = o;
+  o = align_up(o + (size_t)L.n_nodes * 4, 256);
+  L.off_pa = o;
+  o = align_up(o + (size_t)L.n_nodes * 4, 256);
+  L.off_pb = o;
+  o = align_up(o + (size_t)L.n_nodes * 4, 256);
+  L.off_S = o;
+  o = align_up(o + (size_t)L.n_nodes * 8, 256);
+  L.off_S2 = o;
+  o = align_up(o + (size_t)L.n_nodes * 8, 256);
+  L.off_d0 = o;
+  o = align_up(o + (size_t)L.n_nodes * 8, 256);
+  L.off_d1 = o;
+  o = align_up(o + (size_t)L.n_nodes * 8, 256);
+  L.off_link = o;
+  o = align_up(o + (size_t)L.n_nodes * 2, 256);
+  L.off_flags = o;
+  o = align_up(o + 64 * sizeof(int), 256);
+  L.total = o;
+  return L;
+}
+
+size_t strip_workspace_bytes(int64_t rows, int64_t cols) {
+  if (rows <= 0 || cols <= 0) return 256;
+  return strip_layout(rows, cols).total;
+}
+
+// boundary record of cell (t ? last row : first row, c): strip-local count, code, and where its in-strip
+// path leaves the strip: (exit row selector << 30) | exit column, or -1 when it does not leave
+__global__ void strip_boundary_extract_kernel(const uint8_t* __restrict__ fdr, int64_t ld_fdr,
+                                              const long long* __restrict__ fac, int64_t ld_fac,
+                                              const int32_t* __restrict__ root_ptr, const uint16_t* __restrict__ link,
+                                              AccParams p, int32_t* __restrict__ slink, long long* __restrict__ floc,
+                                              uint8_t* __restrict__ bcode) {
+  const int64_t n = 2 * (int64_t)p.cols;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(k / p.cols), c = (int)(k - (int64_t)t * p.cols);
+    const int r = t ? p.rows - 1 : 0;
+    const uint8_t code = fdr[(int64_t)(r + p.y_off) * ld_fdr + c];
+    bcode[k] = code;
+    floc[k] = fac[(int64_t)r * ld_fac + c];
+    int32_t sl = -1;
+    if (code < 8) {
+      const int u = node_of_cell(r, c, p);
+      const int32_t pr = root_ptr[u];
+      const int root = pr < 0 ? ~pr : u;
+      const uint16_t lk = link[root];
+      if ((lk >> 8) == KIND_STRIP_EXIT) {
+        const int tile = root / SLOTS;
+        const int ty = tile / p.ntx, tx = tile - ty * p.ntx;
+        const int h = min(AT, p.rows - (ty << AT_SHIFT)), w = min(AT, p.cols - (tx << AT_SHIFT));
+        int y, x;
+        cell_of_slot(lk & 0xFF, h, w, y, x);
+        const int er = (ty << AT_SHIFT) + y, ec = (tx << AT_SHIFT) + x;
+        sl = ((er == 0 ? 0 : 1) << 30) | ec;
+      }
+    }
+    slink[k] = sl;
+  }
+}
+
+// node id of boundary cell (strip s, row selector t, column c)
+__device__ __forceinline__ int64_t bnode(int s, int t, int64_t c, int64_t cols) { return ((int64_t)s * 2 + t) * cols + c; }
+
+// where does boundary cell (s, t, c) with code `code` send its water?  -1 when not across a strip boundary
+__device__ __forceinline__ int64_t bnode_target(int s, int t, int64_t c, int code, int n_strips, int64_t cols,
+                                                const uint8_t* __restrict__ code_all) {
+  if (code >= 8) return -1;
+  const int dy = dir_dy(code);
+  if ((t == 0 && dy != -1) || (t == 1 && dy != 1)) return -1;
+  const int s2 = s + dy;
+  const int64_t c2 = c + dir_dx(code);
+  if (s2 < 0 || s2 >= n_strips || c2 < 0 || c2 >= cols) return -1;
+  const int64_t d = bnode(s2, dy < 0 ? 1 : 0, c2, cols);
+  return code_all[d] == OFL_DIR_NODATA ? -1 : d;
+}
+
+__global__ void strip_graph_build_kernel(const int32_t* __restrict__ slink_all, const long long* __restrict__ floc_all,
+                                         const uint8_t* __restrict__ code_all, int n_strips, int64_t cols,
+                                         int32_t* __restrict__ succ, unsigned long long* __restrict__ base) {
+  const int64_t n = (int64_t)n_strips * 2 * cols;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(k / (2 * cols));
+    const int t = (int)((k - (int64_t)s * 2 * cols) / cols);
+    const int64_t c = k - ((int64_t)s * 2 + t) * cols;
+    // this cell's own edge across the boundary carries its strip-local count into the next strip
+    const int64_t d = bnode_target(s, t, c, code_all[k], n_strips, cols, code_all);
+    if (d >= 0) atomicAdd(&base[d], (unsigned long long)floc_all[k]);
+    // parent in the boundary forest: the entry cell fed by the cell where this cell's path leaves the strip
+    int32_t parent = -1;
+    const int32_t sl = slink_all[k];
+    if (sl >= 0) {
+      const int te = sl >> 30;
+      const int64_t ce = sl & ((1 << 30) - 1);
+      const int64_t x = bnode(s, te, ce, cols);
+      const int64_t dd = bnode_target(s, te, ce, code_all[x], n_strips, cols, code_all);
+      if (dd >= 0) parent = (int32_t)dd;
+    }
+    succ[k] = parent;
+  }
+}
+
+__global__ void strip_seed_kernel(const long long* __restrict__ J, AccParams p, unsigned long long* __restrict__ S2) {
+  const int64_t n = 2 * (int64_t)p.cols;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(k / p.cols), c = (int)(k - (int64_t)t * p.cols);
+    const long long j = J[k];
+    if (j != 0) S2[node_of_cell(t ? p.rows - 1 : 0, c, p)] = (unsigned long long)j;
+  }
+}
+
+struct StripCtx {
+  AccParams p;
+  CUtensorMap tm;
+  StripLayout L;
+  uint8_t* ws;
+  int64_t ntiles;
+};
+
+static int strip_setup(StripCtx& C, const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above,
+                       int has_below, long long* fac, int64_t ld_fac, void* workspace, size_t workspace_bytes) {
+  OFL_REQUIRE(rows >= 2 && cols >= 1 && rows < (1ll << 30) && cols < (1ll << 30), OFL_ERR_INVALID,
+              "strip needs at least 2 rows");
+  OFL_REQUIRE(!has_below || rows % AT == 0, OFL_ERR_INVALID,
+              "a strip with a strip below it must have a multiple of %d rows (got %lld)", AT, (long long)rows);
+  OFL_REQUIRE((reinterpret_cast<uintptr_t>(fdr_halo) & 15) == 0 && (ld_fdr % 16) == 0 && ld_fdr >= cols,
+              OFL_ERR_ALIGNMENT, "fdr must be 16-byte aligned with ld_fdr %% 16 == 0");
+  OFL_REQUIRE((reinterpret_cast<uintptr_t>(fac) & 7) == 0 && ld_fac >= cols, OFL_ERR_ALIGNMENT, "fac must be 8-byte aligned");
+  C.L = strip_layout(rows, cols);
+  OFL_REQUIRE(C.L.n_nodes < (1ll << 31), OFL_ERR_INVALID, "strip too large for 32-bit perimeter node ids");
+  OFL_REQUIRE(workspace != nullptr && workspace_bytes >= C.L.total, OFL_ERR_WORKSPACE,
+              "strip workspace too small: need %zu bytes, have %zu", C.L.total, workspace_bytes);
+  C.ws = static_cast<uint8_t*>(workspace);
+  AccParams& p = C.p;
+  p.rows = (int)rows;
+  p.cols = (int)cols;
+  p.nty = (int)((rows + AT - 1) / AT);
+  p.ntx = (int)((cols + AT - 1) / AT);
+  p.succ = reinterpret_cast<int32_t*>(C.ws + C.L.off_succ);
+  p.link = reinterpret_cast<uint16_t*>(C.ws + C.L.off_link);
+  p.S = reinterpret_cast<unsigned long long*>(C.ws + C.L.off_S);
+  p.fac = fac;
+  p.ld_fac = ld_fac;
+  p.err = reinterpret_cast<int*>(C.ws + C.L.off_flags) + 48;
+  p.y_off = 1;
+  p.strip_above = has_above ? 1 : 0;
+  p.strip_below = has_below ? 1 : 0;
+  p.tile_base = 0;
+  C.ntiles = (int64_t)p.nty * p.ntx;
+  int rc = make_tensor_map_2d(&C.tm, fdr_halo, 1, (uint64_t)cols, (uint64_t)rows + 2, (uint64_t)ld_fdr, ACS_W, ACS_H);
+  if (rc != OFL_OK) return rc;
+  return ensure_tile_attrs();
+}
+
+int strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above, int has_below,
+                      long long* fac, int64_t ld_fac, void* workspace, size_t workspace_bytes, int32_t* slink,
+                      long long* floc, uint8_t* bcode, cudaStream_t st) {
+  StripCtx C;
+  int rc = strip_setup(C, fdr_halo, rows, cols, ld_fdr, has_above, has_below, fac, ld_fac, workspace, workspace_bytes);
+  if (rc != OFL_OK) return rc;
+  const StripLayout& L = C.L;
+  int* flags = reinterpret_cast<int*>(C.ws + L.off_flags);
+  OFL_CUDA(cudaMemsetAsync(C.ws + L.off_S, 0, L.off_link - L.off_S, st));  // S, S2, d0, d1
+  OFL_CUDA(cudaMemsetAsync(flags, 0, 64 * sizeof(int), st));
+  {
+    PhaseScope ps(PHASE_ACC_TILE_A, st);
+    acc_tile_kernel<false><<<(unsigned)C.ntiles, ACC_THREADS, TileSmem<false>::BYTES, st>>>(C.tm, C.p);
+  }
+  OFL_CHECK_LAUNCH();
+  const int32_t* roots = nullptr;
+  {
+    PhaseScope ps(PHASE_ACC_SOLVE, st);
+    rc = pj_solve(C.p.succ, reinterpret_cast<int32_t*>(C.ws + L.off_pa), reinterpret_cast<int32_t*>(C.ws + L.off_pb),
+                  C.p.S, reinterpret_cast<unsigned long long*>(C.ws + L.off_d0),
+                  reinterpret_cast<unsigned long long*>(C.ws + L.off_d1), flags, L.n_nodes, st, &roots);
+  }
+  if (rc != OFL_OK) return rc;
+  // strip-local counts of the first and last tile row (their cells include both boundary rows)
+  {
+    PhaseScope ps(PHASE_ACC_TILE_B, st);
+    AccParams pb = C.p;
+    pb.tile_base = 0;
+    acc_tile_kernel<true><<<(unsigned)pb.ntx, ACC_THREADS, TileSmem<true>::BYTES, st>>>(C.tm, pb);
+    if (pb.nty > 1) {
+      pb.tile_base = (pb.nty - 1) * pb.ntx;
+      acc_tile_kernel<true><<<(unsigned)pb.ntx, ACC_THREADS, TileSmem<true>::BYTES, st>>>(C.tm, pb);
+      count_launch();
+    }
+  }
+  OFL_CHECK_LAUNCH();
+  strip_boundary_extract_kernel<<<grid_for(2 * cols, 8), 256, 0, st>>>(fdr_halo, ld_fdr, fac, ld_fac, roots, C.p.link,
+                                                                       C.p, slink, floc, bcode);
+  OFL_CHECK_LAUNCH();
+  return check_cycle_flag(C.p.err, st);
+}
+
+size_t strip_boundary_workspace_bytes(int n_strips, int64_t cols) {
+  const size_t n = (size_t)n_strips * 2 * (size_t)cols;
+  return align_up(n * 4, 256) * 3 + align_up(n * 8, 256) * 3 + 512;
+}
+
+int strip_boundary_solve(const int32_t* slink_all, const long long* floc_all, const uint8_t* code_all, int n_strips,
+                         int64_t cols, long long* J_all, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  OFL_REQUIRE(n_strips >= 1 && cols >= 1, OFL_ERR_INVALID, "bad boundary graph size");
+  const int64_t n = (int64_t)n_strips * 2 * cols;
+  OFL_REQUIRE(n < (1ll << 31), OFL_ERR_INVALID, "boundary graph too large");
+  OFL_REQUIRE(workspace != nullptr && workspace_bytes >= strip_boundary_workspace_bytes(n_strips, cols),
+              OFL_ERR_WORKSPACE, "boundary workspace too small");
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const size_t a4 = align_up((size_t)n * 4, 256), a8 = align_up((size_t)n * 8, 256);
+  int32_t* succ = reinterpret_cast<int32_t*>(ws);
+  int32_t* pa = reinterpret_cast<int32_t*>(ws + a4);
+  int32_t* pb = reinterpret_cast<int32_t*>(ws + 2 * a4);
+  unsigned long long* S = reinterpret_cast<unsigned long long*>(ws + 3 * a4);
+  unsigned long long* d0 = reinterpret_cast<unsigned long long*>(ws + 3 * a4 + a8);
+  unsigned long long* d1 = reinterpret_cast<unsigned long long*>(ws + 3 * a4 + 2 * a8);
+  int* flags = reinterpret_cast<int*>(ws + 3 * a4 + 3 * a8);
+  OFL_CUDA(cudaMemsetAsync(S, 0, 3 * a8, st));
+  strip_graph_build_kernel<<<grid_for(n, 8), 256, 0, st>>>(slink_all, floc_all, code_all, n_strips, cols, succ, S);
+  OFL_CHECK_LAUNCH();
+  int rc;
+  {
+    PhaseScope ps(PHASE_ACC_SOLVE, st);
+    rc = pj_solve(succ, pa, pb, S, d0, d1, flags, n, st, nullptr);
+  }
+  if (rc != OFL_OK) return rc;
+  OFL_CUDA(cudaMemcpyAsync(J_all, S, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+  return OFL_OK;
+}
+
+int strip_accum_final(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above, int has_below,
+                      const long long* J_mine, void* workspace, size_t workspace_bytes, long long* fac, int64_t ld_fac,
+                      cudaStream_t st) {
+  StripCtx C;
+  int rc = strip_setup(C, fdr_halo, rows, cols, ld_fdr, has_above, has_below, fac, ld_fac, workspace, workspace_bytes);
+  if (rc != OFL_OK) return rc;
+  const StripLayout& L = C.L;
+  int* flags = reinterpret_cast<int*>(C.ws + L.off_flags);
+  unsigned long long* S2 = reinterpret_cast<unsigned long long*>(C.ws + L.off_S2);
+  unsigned long long* d0 = reinterpret_cast<unsigned long long*>(C.ws + L.off_d0);
+  unsigned long long* d1 = reinterpret_cast<unsigned long long*>(C.ws + L.off_d1);
+  // inflow from other strips enters at the boundary rows; by linearity its effect on every perimeter
+  // node is the subtree sum of those seeds over the strip's (preserved) perimeter forest
+  OFL_CUDA(cudaMemsetAsync(S2, 0, L.off_link - L.off_S2, st));  // S2, d0, d1
+  strip_seed_kernel<<<grid_for(2 * cols, 8), 256, 0, st>>>(J_mine, C.p, S2);
+  OFL_CHECK_LAUNCH();
+  {
+    PhaseScope ps(PHASE_ACC_SOLVE, st);
+    rc = pj_solve(C.p.succ, reinterpret_cast<int32_t*>(C.ws + L.off_pa), reinterpret_cast<int32_t*>(C.ws + L.off_pb), S2,
+                  d0, d1, flags, L.n_nodes, st, nullptr);
+    if (rc == OFL_OK) {
+      // S += S2 (d1 is zero again after the solve's own fold only if it was untouched: use a zeroed d0)
+      OFL_CUDA(cudaMemsetAsync(d0, 0, (size_t)L.n_nodes * 8, st));
+      pj_fold_kernel<<<grid_for(L.n_nodes, 8), 256, 0, st>>>(C.p.S, S2, d0, L.n_nodes);
+    }
+  }
+  if (rc != OFL_OK) return rc;
+  OFL_CHECK_LAUNCH();
+  {
+    PhaseScope ps(PHASE_ACC_TILE_B, st);
+    acc_tile_kernel<true><<<(unsigned)C.ntiles, ACC_THREADS, TileSmem<true>::BYTES, st>>>(C.tm, C.p);
+  }
+  OFL_CHECK_LAUNCH();
+  return check_cycle_flag(C.p.err, st);
 }
 
 int launch_check(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, const long long* fac, int64_t ld_fac,

@@ -19,6 +19,16 @@ int64_t perimeter_count(int64_t rows, int64_t cols);
 size_t accumulation_workspace_bytes(int64_t rows, int64_t cols);
 int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, long long* fac, int64_t ld_fac,
                         long long* perim_links_dev, void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t strip_workspace_bytes(int64_t rows, int64_t cols);
+size_t strip_boundary_workspace_bytes(int n_strips, int64_t cols);
+int strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above, int has_below,
+                      long long* fac, int64_t ld_fac, void* workspace, size_t workspace_bytes, int32_t* slink,
+                      long long* floc, uint8_t* bcode, cudaStream_t st);
+int strip_boundary_solve(const int32_t* slink_all, const long long* floc_all, const uint8_t* code_all, int n_strips,
+                         int64_t cols, long long* J_all, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int strip_accum_final(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above, int has_below,
+                      const long long* J_mine, void* workspace, size_t workspace_bytes, long long* fac, int64_t ld_fac,
+                      cudaStream_t st);
 int launch_check(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, const long long* fac, int64_t ld_fac,
                  unsigned long long* n_bad_dev, cudaStream_t st);
 int launch_synth(float* dem, int64_t rows, int64_t cols, int64_t ld, int64_t row0, int64_t total_rows, uint64_t seed,
@@ -173,6 +183,43 @@ int ofl_check_accumulation_u8(const uint8_t* fdr, int64_t rows, int64_t cols, in
   OFL_CUDA(cudaStreamSynchronize(st));
   *n_bad = (int64_t)h;
   return OFL_OK;
+}
+
+size_t ofl_strip_workspace_bytes(int64_t rows, int64_t cols) { return strip_workspace_bytes(rows, cols); }
+size_t ofl_strip_boundary_workspace_bytes(int n_strips, int64_t cols) {
+  return strip_boundary_workspace_bytes(n_strips, cols);
+}
+
+int ofl_strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above,
+                          int has_below, int64_t* fac, int64_t ld_fac, void* workspace, size_t workspace_bytes,
+                          int32_t* slink, int64_t* floc, uint8_t* bcode, void* stream) {
+  OFL_REQUIRE(fdr_halo && fac && workspace && slink && floc && bcode, OFL_ERR_INVALID, "null pointer");
+  int rc = ensure_init();
+  if (rc != OFL_OK) return rc;
+  return strip_accum_local(fdr_halo, rows, cols, ld_fdr, has_above, has_below, reinterpret_cast<long long*>(fac), ld_fac,
+                           workspace, workspace_bytes, slink, reinterpret_cast<long long*>(floc), bcode,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int ofl_strip_boundary_solve(const int32_t* slink_all, const int64_t* floc_all, const uint8_t* bcode_all, int n_strips,
+                             int64_t cols, int64_t* J_all, void* workspace, size_t workspace_bytes, void* stream) {
+  OFL_REQUIRE(slink_all && floc_all && bcode_all && J_all && workspace, OFL_ERR_INVALID, "null pointer");
+  int rc = ensure_init();
+  if (rc != OFL_OK) return rc;
+  return strip_boundary_solve(slink_all, reinterpret_cast<const long long*>(floc_all), bcode_all, n_strips, cols,
+                              reinterpret_cast<long long*>(J_all), workspace, workspace_bytes,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int ofl_strip_accum_final(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above,
+                          int has_below, const int64_t* J_mine, void* workspace, size_t workspace_bytes, int64_t* fac,
+                          int64_t ld_fac, void* stream) {
+  OFL_REQUIRE(fdr_halo && fac && workspace && J_mine, OFL_ERR_INVALID, "null pointer");
+  int rc = ensure_init();
+  if (rc != OFL_OK) return rc;
+  return strip_accum_final(fdr_halo, rows, cols, ld_fdr, has_above, has_below, reinterpret_cast<const long long*>(J_mine),
+                           workspace, workspace_bytes, reinterpret_cast<long long*>(fac), ld_fac,
+                           static_cast<cudaStream_t>(stream));
 }
 
 int ofl_synth_dem_f32(float* dem, int64_t rows, int64_t cols, int64_t ld_dem, int64_t row0, int64_t total_rows,

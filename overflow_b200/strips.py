@@ -1,0 +1,236 @@
+"""Row-strip (multi-GPU) flow direction + flow accumulation.
+
+The raster is split into contiguous row strips, one per GPU (one process per GPU, torch.distributed).
+Per step:
+  1. DEM halo exchange   each strip sends its first / last row to the neighbour above / below
+                         (NCCL send/recv over NVLink); the raster's top and bottom get nodata rows
+  2. direction           strip-mode stencil on the strip + halo rows
+  3. code halo exchange  same pattern with the uint8 direction codes
+  4. local accumulation  ofl_strip_accum_local: strip-local solve, boundary records of the strip's
+                         first and last row (13 B per boundary cell)
+  5. all-gather          the boundary records of all strips (NCCL all_gather, a few MB)
+  6. boundary solve      ofl_strip_boundary_solve, replicated on every GPU
+  7. final accumulation  ofl_strip_accum_final: push the inflow from other strips down the strip and
+                         write the strip's final int64 counts
+This mirrors the tile structure of Barnes 2016 (the paper cited by the reference at
+src/overflow/flow_accumulation.py:61,100) one level up: strips play the role of tiles.
+
+The compute lives behind a small engine interface so the host-side exchange logic can be tested on
+CPU (gloo) with a stand-in engine; the shipped engine (CudaStripEngine) is the C ABI and has no
+CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native
+
+TILE = 64  # strips must start on multiples of the accumulation tile side
+
+
+def partition_rows(rows, world, tile=TILE):
+    """[(r0, r1)] per rank: contiguous strips whose boundaries are multiples of `tile`.
+
+    Whole tile rows are dealt out as evenly as possible; a ragged remainder (rows % tile) stays with the
+    last strip, so every strip has at least `tile` rows.
+    """
+    n_full = rows // tile
+    if n_full < world:
+        raise ValueError(f"{rows} rows hold {n_full} full tile rows of {tile}, fewer than {world} strips")
+    base, rem = divmod(n_full, world)
+    out, t0 = [], 0
+    for i in range(world):
+        t1 = t0 + base + (1 if i < rem else 0)
+        out.append((t0 * tile, rows if i == world - 1 else t1 * tile))
+        t0 = t1
+    return out
+
+
+def _round_up(v, a):
+    return (v + a - 1) // a * a
+
+
+class CudaStripEngine:
+    """The product engine: every method is a liboverflow_b200 call on torch CUDA tensors."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("CudaStripEngine needs a CUDA device (there is no CPU fallback)")
+        _native.init(self.device.index if self.device.index is not None else torch.cuda.current_device())
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def strip_workspace(self, rows, cols):
+        return self.empty((int(_native.lib().ofl_strip_workspace_bytes(rows, cols)),), torch.uint8)
+
+    def boundary_workspace(self, n_strips, cols):
+        return self.empty((int(_native.lib().ofl_strip_boundary_workspace_bytes(n_strips, cols)),), torch.uint8)
+
+    def synth_dem(self, out, row0, total_rows, seed, kind, holes_permille, nodata):
+        rows, cols = out.shape
+        _native.check(_native.lib().ofl_synth_dem_f32(out.data_ptr(), rows, cols, out.stride(0), row0, total_rows, seed,
+                                                      kind, 1000.0, holes_permille, nodata, self._stream()))
+
+    def direction(self, dem_halo, nodata, fdr_out):
+        rows, cols = fdr_out.shape
+        _native.check(_native.lib().ofl_flow_direction_f32(
+            dem_halo.data_ptr(), rows, cols, dem_halo.stride(0), float(nodata), fdr_out.data_ptr(), fdr_out.stride(0),
+            _native.OFL_DIR_MODE_STRIP, _native.OFL_MEM_DEVICE, self._stream()))
+
+    def accum_local(self, fdr_halo, has_above, has_below, fac, ws, slink, floc, bcode):
+        rows, cols = fac.shape
+        _native.check(_native.lib().ofl_strip_accum_local(
+            fdr_halo.data_ptr(), rows, cols, fdr_halo.stride(0), int(has_above), int(has_below), fac.data_ptr(),
+            fac.stride(0), ws.data_ptr(), ws.numel(), slink.data_ptr(), floc.data_ptr(), bcode.data_ptr(), self._stream()))
+
+    def boundary_solve(self, slink_all, floc_all, bcode_all, J_all, ws):
+        n_strips, _, cols = slink_all.shape
+        _native.check(_native.lib().ofl_strip_boundary_solve(
+            slink_all.data_ptr(), floc_all.data_ptr(), bcode_all.data_ptr(), n_strips, cols, J_all.data_ptr(),
+            ws.data_ptr(), ws.numel(), self._stream()))
+
+    def accum_final(self, fdr_halo, has_above, has_below, J_mine, ws, fac):
+        rows, cols = fac.shape
+        _native.check(_native.lib().ofl_strip_accum_final(
+            fdr_halo.data_ptr(), rows, cols, fdr_halo.stride(0), int(has_above), int(has_below), J_mine.data_ptr(),
+            ws.data_ptr(), ws.numel(), fac.data_ptr(), fac.stride(0), self._stream()))
+
+
+class StripPipeline:
+    """One rank's strip: buffers, the per-phase compute, and the distributed step."""
+
+    def __init__(self, rows, cols, rank, world, nodata=-9999.0, engine=None, device=None):
+        self.rows, self.cols, self.rank, self.world, self.nodata = rows, cols, rank, world, float(nodata)
+        self.r0, self.r1 = partition_rows(rows, world)[rank]
+        self.h = self.r1 - self.r0
+        self.has_above, self.has_below = rank > 0, rank < world - 1
+        if engine is None:
+            engine = CudaStripEngine(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+        self.engine = e = engine
+        h, c = self.h, cols
+        # pitched so every row start satisfies the library's alignment contract
+        self.dem_halo = e.empty((h + 2, _round_up(c, 4)), torch.float32)[:, :c]
+        self.fdr_halo = e.empty((h + 2, _round_up(c, 16)), torch.uint8)[:, :c]
+        self.fac = e.empty((h, c), torch.int64)
+        self.ws = e.strip_workspace(h, c)
+        self.bws = e.boundary_workspace(world, c)
+        self.slink = e.empty((2, c), torch.int32)
+        self.floc = e.empty((2, c), torch.int64)
+        self.bcode = e.empty((2, c), torch.uint8)
+        self.slink_all = e.empty((world, 2, c), torch.int32)
+        self.floc_all = e.empty((world, 2, c), torch.int64)
+        self.bcode_all = e.empty((world, 2, c), torch.uint8)
+        self.J_all = e.empty((world, 2, c), torch.int64)
+        self.fdr_halo.zero_()
+
+    # ---- data
+    @property
+    def dem(self):
+        return self.dem_halo[1:-1]
+
+    @property
+    def fdr(self):
+        return self.fdr_halo[1:-1]
+
+    def load_synthetic(self, seed=0, kind=0, holes_permille=0):
+        self.engine.synth_dem(self.dem, self.r0, self.rows, seed, kind, holes_permille, self.nodata)
+
+    def load_dem(self, dem_strip):
+        self.dem.copy_(torch.as_tensor(dem_strip))
+
+    # ---- phases (compute only)
+    def fill_edge_halos(self):
+        # util/raster.py:67 pads the raster edge with the band nodata cast to the band dtype
+        if not self.has_above:
+            self.dem_halo[0].fill_(np.float32(self.nodata).item())
+        if not self.has_below:
+            self.dem_halo[-1].fill_(np.float32(self.nodata).item())
+
+    def direction(self):
+        self.engine.direction(self.dem_halo, self.nodata, self.fdr)
+
+    def accum_local(self):
+        self.engine.accum_local(self.fdr_halo, self.has_above, self.has_below, self.fac, self.ws, self.slink, self.floc,
+                                self.bcode)
+
+    def boundary_solve(self):
+        self.engine.boundary_solve(self.slink_all, self.floc_all, self.bcode_all, self.J_all, self.bws)
+
+    def accum_final(self):
+        self.engine.accum_final(self.fdr_halo, self.has_above, self.has_below, self.J_all[self.rank], self.ws, self.fac)
+
+    # ---- distributed step (one process per strip)
+    def _exchange(self, buf):
+        """Send my first / last row to the strip above / below; receive theirs into my halo rows."""
+        import torch.distributed as dist
+
+        ops = []
+        if self.has_above:
+            ops.append(dist.P2POp(dist.isend, buf[1], self.rank - 1))
+            ops.append(dist.P2POp(dist.irecv, buf[0], self.rank - 1))
+        if self.has_below:
+            ops.append(dist.P2POp(dist.isend, buf[-2], self.rank + 1))
+            ops.append(dist.P2POp(dist.irecv, buf[-1], self.rank + 1))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def step(self):
+        """flow direction + flow accumulation of the whole raster; this rank's strip ends up in self.fdr / self.fac."""
+        import torch.distributed as dist
+
+        self.fill_edge_halos()
+        if self.world > 1:
+            self._exchange(self.dem_halo)
+        self.direction()
+        if self.world > 1:
+            self._exchange(self.fdr_halo)
+        self.accum_local()
+        if self.world > 1:
+            for out, inp in ((self.slink_all, self.slink), (self.floc_all, self.floc), (self.bcode_all, self.bcode)):
+                if dist.get_backend() == "gloo":  # CPU tests
+                    dist.all_gather(list(out.unbind(0)), inp)
+                else:
+                    dist.all_gather_into_tensor(out, inp)
+        else:
+            self.slink_all[0].copy_(self.slink)
+            self.floc_all[0].copy_(self.floc)
+            self.bcode_all[0].copy_(self.bcode)
+        self.boundary_solve()
+        self.accum_final()
+
+
+def step_in_process(pipes):
+    """Run all strips of one raster inside ONE process (loop-back exchange): single-GPU emulation of
+    the multi-GPU path for tests, and the way to check N-strip == 1-strip results."""
+    world = len(pipes)
+
+    def exchange(get):
+        for i, p in enumerate(pipes):
+            if i > 0:
+                get(p)[0].copy_(get(pipes[i - 1])[-2])
+            if i < world - 1:
+                get(p)[-1].copy_(get(pipes[i + 1])[1])
+
+    for p in pipes:
+        p.fill_edge_halos()
+    exchange(lambda p: p.dem_halo)
+    for p in pipes:
+        p.direction()
+    exchange(lambda p: p.fdr_halo)
+    for p in pipes:
+        p.accum_local()
+    for p in pipes:
+        for i, q in enumerate(pipes):
+            p.slink_all[i].copy_(q.slink)
+            p.floc_all[i].copy_(q.floc)
+            p.bcode_all[i].copy_(q.bcode)
+    for p in pipes:
+        p.boundary_solve()
+        p.accum_final()
