@@ -193,8 +193,8 @@ def run_native(args):
     if world > 1:
         from overflow_b200 import strips
 
-        runner = strips.StripPipeline(S, S, rank, world, nodata=NODATA, seed=args.seed, kind=args.kind,
-                                      holes_permille=args.holes)
+        runner = strips.StripPipeline(S, S, rank, world, nodata=NODATA, device=torch.device("cuda", local))
+        runner.load_synthetic(seed=args.seed, kind=args.kind, holes_permille=args.holes)
         step = runner.step
         cells_total = S * S
     else:
@@ -338,8 +338,35 @@ def run_native(args):
             "ms_per_step": el * 1e3, "steps": args.e2e_steps,
             "api": "flow_direction_for_raster + flow_accumulation_for_raster on pinned host arrays",
         }
-    elif world > 1:
-        line["e2e"] = runner.e2e(args.e2e_steps) if hasattr(runner, "e2e") else None
+    elif world > 1 and not args.no_e2e:
+        # every rank streams its strip from / to pinned host memory around the distributed step
+        h_dem = torch.empty(tuple(runner.dem.shape), dtype=torch.float32, pin_memory=True)
+        h_dem.copy_(runner.dem)
+        h_fdr = torch.empty(tuple(runner.fdr.shape), dtype=torch.uint8, pin_memory=True)
+        h_fac = torch.empty(tuple(runner.fac.shape), dtype=torch.int64, pin_memory=True)
+
+        def e2e_step():
+            runner.load_dem(h_dem)
+            runner.step()
+            h_fdr.copy_(runner.fdr, non_blocking=True)
+            h_fac.copy_(runner.fac, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        el = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        el = float(el.item())
+        line["e2e"] = {
+            "value": cells_total / el / 1e9, "unit": UNIT,
+            "h2d_bytes_per_step": int(cells_total * 4), "d2h_bytes_per_step": int(cells_total * 9),
+            "ms_per_step": el * 1e3, "steps": args.e2e_steps,
+            "api": "StripPipeline.load_dem(pinned host strip) + step() + copy of fdr/fac strips to pinned host memory, per rank",
+        }
 
     if rank == 0:
         print(json.dumps(line), flush=True)

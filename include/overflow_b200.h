@@ -97,9 +97,9 @@ void ofl_launch_count_reset(void);
  * launching stream.  ofl_phase_timing_read waits for the recorded events, adds them to per-phase
  * totals and copies up to n totals (milliseconds) and launch counts out; returns the number of phases:
  *   0 direction kernel   1 accumulation tile pass A   2 perimeter-graph solve
- *   3 accumulation tile pass B   4 perimeter links
+ *   3 accumulation tile pass B   4 perimeter links   5 strip mode: pass B on the strip's first/last tile row
  */
-#define OFL_PHASE_COUNT 5
+#define OFL_PHASE_COUNT 6
 void ofl_phase_timing_enable(int on);
 int ofl_phase_timing_read(double* ms, int64_t* counts, int n, int reset);
 

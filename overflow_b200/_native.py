@@ -93,7 +93,7 @@ def launch_count_reset():
     lib().ofl_launch_count_reset()
 
 
-PHASES = ("direction", "acc_tile_a", "acc_solve", "acc_tile_b", "acc_links")
+PHASES = ("direction", "acc_tile_a", "acc_solve", "acc_tile_b", "acc_links", "strip_edge")
 
 
 def phase_timing_enable(on=True):

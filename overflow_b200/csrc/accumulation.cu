@@ -1000,7 +1000,7 @@ int strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
   if (rc != OFL_OK) return rc;
   // strip-local counts of the first and last tile row (their cells include both boundary rows)
   {
-    PhaseScope ps(PHASE_ACC_TILE_B, st);
+    PhaseScope ps(PHASE_STRIP_EDGE, st);
     AccParams pb = C.p;
     pb.tile_base = 0;
     acc_tile_kernel<true><<<(unsigned)pb.ntx, ACC_THREADS, TileSmem<true>::BYTES, st>>>(C.tm, pb);
