@@ -1,0 +1,46 @@
+"""Command line interface -- mirror of the reference's src/overflow_cli.py for the D8 path.
+
+`flow-direction` keeps the reference's options, messages and exit codes (overflow_cli.py:54-84);
+`flow-accumulation` is added with the same conventions (the reference snapshot has no such command).
+"""
+import click
+
+from .constants import DEFAULT_CHUNK_SIZE
+from .flow_accumulation import flow_accumulation
+from .flow_direction import flow_direction
+
+
+@click.group()
+def main():
+    """The main entry point for the command line interface."""
+
+
+@main.command(name="flow-direction")
+@click.option("--input_file", help="path to the DEM file")
+@click.option("--output_file", help="path to the output file")
+@click.option("--chunk_size", help="chunk size", default=DEFAULT_CHUNK_SIZE)
+def flow_direction_cli(input_file: str, output_file: str, chunk_size: int):
+    """Generate a D8 flow direction raster from a DEM."""
+    try:
+        flow_direction(input_file, output_file, chunk_size)
+    except Exception as exc:
+        print(f"flow_direction failed with the following exception: {str(exc)}")
+        # non-zero exit code on failure, like the reference
+        raise click.Abort()
+
+
+@main.command(name="flow-accumulation")
+@click.option("--input_file", help="path to the flow direction raster")
+@click.option("--output_file", help="path to the output file")
+@click.option("--chunk_size", help="chunk size", default=DEFAULT_CHUNK_SIZE)
+def flow_accumulation_cli(input_file: str, output_file: str, chunk_size: int):
+    """Generate a flow accumulation raster from a D8 flow direction raster."""
+    try:
+        flow_accumulation(input_file, output_file, chunk_size)
+    except Exception as exc:
+        print(f"flow_accumulation failed with the following exception: {str(exc)}")
+        raise click.Abort()
+
+
+if __name__ == "__main__":
+    main()  # pylint: disable=no-value-for-parameter

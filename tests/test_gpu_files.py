@@ -1,0 +1,74 @@
+"""GPU: the file-level API and the CLI -- the reference's tests/test_flow_direction.py:121-160 with the
+built-in GeoTIFF I/O standing in for GDAL's /vsimem, plus the added flow-accumulation driver."""
+import click.testing
+import numpy as np
+import pytest
+
+import oracle
+from oracle import synth
+from conftest import load_golden
+from overflow.constants import FLOW_DIRECTION_NODATA, FLOW_ACCUMULATION_NODATA
+from overflow.flow_accumulation import flow_accumulation
+from overflow.flow_direction import flow_direction
+from overflow_b200.util.raster import create_raster, open_raster
+from overflow_cli import flow_accumulation_cli, flow_direction_cli
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def raster_file_path(tmp_path):
+    """5x5 DEM of the reference's fixture (tests/test_flow_direction.py:21-50), nodata 0."""
+    path = str(tmp_path / "test_raster_FDIR.tif")
+    ds = create_raster(path, 5, 5, "Float32")
+    band = ds.GetRasterBand(1)
+    band.WriteArray(load_golden("kat.npz")["dir_dem"][1:-1, 1:-1])
+    band.SetNoDataValue(0)
+    ds.FlushCache()
+    return path
+
+
+def test_flow_direction_from_file(raster_file_path, tmp_path):
+    out = str(tmp_path / "fdr.tif")
+    flow_direction(raster_file_path, out, chunk_size=5)
+    band = open_raster(out).GetRasterBand(1)
+    assert band.GetNoDataValue() == FLOW_DIRECTION_NODATA
+    assert np.array_equal(band.ReadAsArray(), load_golden("kat.npz")["dir_expected"])
+
+
+def test_flow_direction_cli(raster_file_path, tmp_path):
+    out = str(tmp_path / "fdr_cli.tif")
+    result = click.testing.CliRunner().invoke(
+        flow_direction_cli, ["--input_file", raster_file_path, "--output_file", out, "--chunk_size", "5"])
+    assert result.exit_code == 0
+    assert np.array_equal(open_raster(out).GetRasterBand(1).ReadAsArray(), load_golden("kat.npz")["dir_expected"])
+
+
+def test_cli_failure_exits_non_zero(tmp_path):
+    result = click.testing.CliRunner().invoke(
+        flow_direction_cli, ["--input_file", str(tmp_path / "missing.tif"), "--output_file", str(tmp_path / "o.tif")])
+    assert result.exit_code == 1
+    assert "flow_direction failed with the following exception" in result.output
+
+
+@pytest.mark.parametrize("chunk_size", [16, 50, 64, 4000])
+def test_file_pipeline_is_chunk_size_invariant(tmp_path, chunk_size):
+    dem = synth.punch_holes(synth.fractal(137, 211, beta=2.0, seed=5), frac=0.03, seed=6)
+    src = str(tmp_path / "dem.tif")
+    ds = create_raster(src, dem.shape[1], dem.shape[0], "Float32", geotransform=(0.0, 30.0, 0.0, 0.0, 0.0, -30.0))
+    ds.GetRasterBand(1).WriteArray(dem)
+    ds.GetRasterBand(1).SetNoDataValue(synth.NODATA)
+    ds.FlushCache()
+    fdr_path, fac_path = str(tmp_path / "fdr.tif"), str(tmp_path / "fac.tif")
+    flow_direction(src, fdr_path, chunk_size=chunk_size)
+    want_fdr = oracle.flow_direction_for_tile(synth.pad_nodata(dem), synth.NODATA)[1:-1, 1:-1]
+    fdr = open_raster(fdr_path).GetRasterBand(1).ReadAsArray()
+    assert np.array_equal(fdr, want_fdr)
+    result = click.testing.CliRunner().invoke(
+        flow_accumulation_cli, ["--input_file", fdr_path, "--output_file", fac_path, "--chunk_size", str(chunk_size)])
+    assert result.exit_code == 0, result.output
+    out = open_raster(fac_path)
+    band = out.GetRasterBand(1)
+    assert band.GetNoDataValue() == FLOW_ACCUMULATION_NODATA
+    assert out.GetGeoTransform() == pytest.approx((0.0, 30.0, 0.0, 0.0, 0.0, -30.0))
+    assert np.array_equal(band.ReadAsArray(), oracle.flow_accumulation(want_fdr))
