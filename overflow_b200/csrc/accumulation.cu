@@ -140,7 +140,8 @@ struct TileSmem {
   static constexpr int HI = WORD + WORDS * 4;
   static constexpr int Q = HI + (FINAL ? WORDS * 4 : 0);
   static constexpr int TAB = Q + QMAX * 2;  // int2 per direction code: {word-array byte offset, cell-id offset}
-  static constexpr int TAIL = TAB + 64;
+  static constexpr int TAB2 = TAB + 64;  // int2 per direction code: {code-array byte offset, cell-id offset}
+  static constexpr int TAIL = TAB2 + 64;
   static constexpr int BAR = TAIL + 16;
   static constexpr int BYTES = BAR + 16;
 };
@@ -222,6 +223,8 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
   if (tid < 8) {
     sts32(a_tab + 8 * tid, (uint32_t)((dir_dy(tid) * WP + dir_dx(tid)) * 4));
     sts32(a_tab + 8 * tid + 4, (uint32_t)(dir_dy(tid) * AT + dir_dx(tid)));
+    sts32(sb + SM::TAB2 + 8 * tid, (uint32_t)(dir_dy(tid) * ACS_W + dir_dx(tid)));
+    sts32(sb + SM::TAB2 + 8 * tid + 4, (uint32_t)(dir_dy(tid) * AT + dir_dx(tid)));
   }
   {
     uint4* z = reinterpret_cast<uint4*>(smem_raw + SM::WORD);
@@ -424,19 +427,22 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     int32_t succ = -1;
     uint16_t lk = KIND_TERM << 8;
     if (cell_of_slot(s, h, w, y, x)) {
-      // walk while the downstream cell is a live in-tile cell (codes 9 nodata, 14 live halo, 15 outside stop it)
+      // walk while the downstream cell is a live in-tile cell (codes 9 nodata, 13/14 live halo, 15 outside stop it)
       uint32_t idx = y * AT + x;
-      uint32_t code = lds8(a_cs0 + idx + (ACS_W - AT) * y), dcode = 0;
+      uint32_t ca = a_cs0 + y * ACS_W + x;  // shared address of the current cell's code
+      uint32_t code = lds8(ca), dcode = 0;
       int dy = 0, dx = 0;
       for (int steps = 0; code < 8; ++steps) {
+        const uint2 t = lds64(sb + SM::TAB2 + 8 * code);
+        dcode = lds8(ca + t.x);
+        if (dcode > 8 || steps > AT * AT) break;
+        ca += t.x;
+        idx += t.y;
+        code = dcode;
+      }
+      if (code < 8) {
         dy = dir_dy(code);
         dx = dir_dx(code);
-        const uint32_t nidx = idx + dy * AT + dx;
-        dcode = lds8(a_cs0 + idx + (ACS_W - AT) * (idx >> AT_SHIFT) + dy * ACS_W + dx);
-        if (dcode > 8 || steps > AT * AT) break;
-        idx = nidx;
-        code = dcode;
-        if (code == 8) break;
       }
       const int cy = idx >> AT_SHIFT, cx = idx & (AT - 1);
       uint16_t kind = KIND_TERM;
@@ -494,40 +500,114 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
 }
 
 // ---------------------------------------------------------------- reduced-graph solve
-// ptr[u] >= 0: u's 2^j-th ancestor.  ptr[u] < 0: ~root(u), the chain is exhausted.
-__global__ void pj_init_kernel(const int32_t* __restrict__ succ, int32_t* __restrict__ ptr, int64_t n) {
-  for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < n; u += (int64_t)gridDim.x * blockDim.x) {
-    const int32_t s = succ[u];
-    ptr[u] = s >= 0 ? s : ~(int32_t)u;
+// Subtree sums over the perimeter forest by pointer doubling, restricted to the nodes that still have
+// an ancestor to jump to.  ptr[u] >= 0: u's 2^j-th ancestor.  ptr[u] < 0: ~root(u), chain exhausted.
+// Round j, for every ACTIVE node w: S_j[w] is added to its 2^j-th ancestor a (delta buffers d0/d1
+// alternate so a node only ever forwards sums that were complete before the round), then w jumps to
+// a's pointer.  A node whose jump finds an exhausted chain retires: it is dropped from the active list
+// and, one round later, its root is copied into the other ping-pong buffer so both stay readable.
+// The node array is cut into one segment per CTA; each CTA keeps the active nodes of its segment
+// compacted at the front of the segment (retirees at the back) of a ping-pong list, so compaction needs
+// only shared-memory atomics and the work per round is proportional to the active nodes, which shrink
+// geometrically on real terrain.
+struct PjSeg {
+  int64_t n;        // nodes
+  int64_t seg;      // nodes per CTA segment (multiple of 32)
+  int blocks;       // CTAs == segments
+};
+
+__device__ __forceinline__ void block_append(int32_t* seg_list, int* s_counter, bool pred, int32_t value, bool from_back,
+                                             int64_t seg_len) {
+  const uint32_t bal = __ballot_sync(0xffffffffu, pred);
+  if (!bal) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(s_counter, __popc(bal));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (pred) {
+    const int64_t pos = base + __popc(bal & ((1u << lane) - 1));
+    seg_list[from_back ? seg_len - 1 - pos : pos] = value;
   }
 }
 
-// Round j: S_{j+1}[v] = S_j[v] + sum of S_j[w] over nodes w whose 2^j-th ancestor is v.
-// Deltas land in d_next and are folded into S by their owner at the start of the next round.
-__global__ void pj_round_kernel(const int32_t* __restrict__ ptr_in, int32_t* __restrict__ ptr_out,
-                                unsigned long long* __restrict__ S, unsigned long long* __restrict__ d_prev,
-                                unsigned long long* __restrict__ d_next, const int* __restrict__ active_in,
-                                int* __restrict__ active_out, int64_t n) {
-  if (*active_in == 0) return;  // converged in an earlier round
-  bool any = false;
-  for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < n; u += (int64_t)gridDim.x * blockDim.x) {
-    unsigned long long s = S[u];
-    const unsigned long long dp = d_prev[u];
-    if (dp) {
-      s += dp;
-      S[u] = s;
-      d_prev[u] = 0;
+// counts layout: [round][2][blocks] ints; round r's input counts are written by round r-1 (r = 0: init)
+__global__ void pj_init_kernel(const int32_t* __restrict__ succ, int32_t* __restrict__ ptr_a, int32_t* __restrict__ ptr_b,
+                               int32_t* __restrict__ list0, int* __restrict__ counts0, PjSeg g) {
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * g.seg;
+  const int64_t len = min(g.seg, g.n - base);
+  for (int64_t i = threadIdx.x; i < g.seg; i += blockDim.x) {  // whole warps stay together for the ballots
+    bool active = false;
+    const int64_t u = base + i;
+    if (i < len) {
+      const int32_t sc = succ[u];
+      active = sc >= 0;
+      if (active) {
+        ptr_a[u] = sc;
+      } else {
+        ptr_a[u] = ~(int32_t)u;
+        ptr_b[u] = ~(int32_t)u;
+      }
     }
-    const int32_t a = ptr_in[u];
-    int32_t q = a;
-    if (a >= 0) {
-      if (s) atomicAdd(&d_next[a], s);
-      q = ptr_in[a];
-      any |= (q >= 0);
-    }
-    ptr_out[u] = q;
+    block_append(list0 + base, &s_cnt, active, (int32_t)u, false, g.seg);
   }
-  if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) *active_out = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    counts0[blockIdx.x] = s_cnt;
+    counts0[g.blocks + blockIdx.x] = 0;
+  }
+}
+
+__global__ void pj_round_kernel(const int32_t* __restrict__ list_in, int32_t* __restrict__ list_out,
+                                const int* __restrict__ cnt_in, int* __restrict__ cnt_out,
+                                const int32_t* __restrict__ ptr_in, int32_t* __restrict__ ptr_out,
+                                unsigned long long* __restrict__ S, unsigned long long* __restrict__ d_prev,
+                                unsigned long long* __restrict__ d_next, PjSeg g) {
+  __shared__ int s_keep, s_ret;
+  const int n_active = cnt_in[blockIdx.x], n_retired = cnt_in[g.blocks + blockIdx.x];
+  if (threadIdx.x == 0) {
+    s_keep = 0;
+    s_ret = 0;
+  }
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * g.seg;
+  const int32_t* in = list_in + base;
+  int32_t* out = list_out + base;
+  // nodes retired by the previous round: make their root visible in this round's output buffer too
+  for (int i = threadIdx.x; i < n_retired; i += blockDim.x) {
+    const int32_t w = in[g.seg - 1 - i];
+    ptr_out[w] = ptr_in[w];
+  }
+  const int n_up = (n_active + 31) / 32 * 32;
+  for (int i = threadIdx.x; i < n_up; i += blockDim.x) {
+    bool keep = false, retire = false;
+    int32_t w = 0;
+    if (i < n_active) {
+      w = in[i];
+      unsigned long long s = S[w];
+      const unsigned long long dp = d_prev[w];
+      if (dp) {
+        s += dp;
+        S[w] = s;
+        d_prev[w] = 0;
+      }
+      const int32_t a = ptr_in[w];
+      if (s) atomicAdd(&d_next[a], s);
+      const int32_t q = ptr_in[a];
+      ptr_out[w] = q;
+      keep = q >= 0;
+      retire = !keep;
+    }
+    block_append(out, &s_keep, keep, w, false, g.seg);
+    block_append(out, &s_ret, retire, w, true, g.seg);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cnt_out[blockIdx.x] = s_keep;
+    cnt_out[g.blocks + blockIdx.x] = s_ret;
+  }
 }
 
 __global__ void pj_fold_kernel(unsigned long long* __restrict__ S, const unsigned long long* __restrict__ d0,
@@ -536,6 +616,13 @@ __global__ void pj_fold_kernel(unsigned long long* __restrict__ S, const unsigne
     const unsigned long long d = d0[u] + d1[u];
     if (d) S[u] += d;
   }
+}
+
+// after the last round: any segment with active nodes left means the forest has a cycle
+__global__ void pj_leftover_kernel(const int* __restrict__ cnt, int blocks, int* __restrict__ leftover) {
+  int any = 0;
+  for (int i = threadIdx.x; i < blocks; i += blockDim.x) any |= cnt[i] != 0;
+  if (__syncthreads_or(any) && threadIdx.x == 0) *leftover = 1;
 }
 
 // ---------------------------------------------------------------- links for the raster perimeter
@@ -621,40 +708,7 @@ int64_t perimeter_count(int64_t rows, int64_t cols) {
   return 2 * rows + 2 * inner;
 }
 
-struct AccLayout {
-  int64_t n_nodes;
-  size_t off_succ, off_ptr, off_S, off_d0, off_d1, off_link, off_flags, total;
-};
-
-static AccLayout acc_layout(int64_t rows, int64_t cols) {
-  AccLayout L;
-  const int64_t nty = (rows + AT - 1) / AT, ntx = (cols + AT - 1) / AT;
-  L.n_nodes = nty * ntx * SLOTS;
-  size_t o = 0;
-  L.off_succ = o;
-  o = align_up(o + (size_t)L.n_nodes * 4, 256);
-  L.off_ptr = o;
-  o = align_up(o + (size_t)L.n_nodes * 4, 256);
-  L.off_S = o;
-  o = align_up(o + (size_t)L.n_nodes * 8, 256);
-  L.off_d0 = o;
-  o = align_up(o + (size_t)L.n_nodes * 8, 256);
-  L.off_d1 = o;
-  o = align_up(o + (size_t)L.n_nodes * 8, 256);
-  L.off_link = o;
-  o = align_up(o + (size_t)L.n_nodes * 2, 256);
-  L.off_flags = o;
-  o = align_up(o + 64 * sizeof(int), 256);
-  L.total = o;
-  return L;
-}
-
-size_t accumulation_workspace_bytes(int64_t rows, int64_t cols) {
-  if (rows <= 0 || cols <= 0) return 256;
-  return acc_layout(rows, cols).total;
-}
-
-constexpr int PJ_MAX_ROUNDS = 40;  // flags[0..40]: active-before-round j; flags[48]: cycle error
+constexpr int PJ_MAX_ROUNDS = 40;
 
 static int ensure_tile_attrs() {
   static bool attr_set = false;
@@ -674,130 +728,197 @@ static inline int grid_for(int64_t n, int per_sm) {
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
-// Subtree sums over the forest `succ` (succ[u] = parent node or -1): on return S[u] holds the sum of
-// the initial S over u's subtree and *roots_out points at the buffer holding ~root(u) for every node.
-// ptr_a / ptr_b are ping-pong buffers (ptr_b may alias succ when succ need not survive); d0 / d1 must
-// be zero on entry.  Synchronises the stream (convergence is read back from the device flags).
-static int pj_solve(const int32_t* succ, int32_t* ptr_a, int32_t* ptr_b, unsigned long long* S,
-                    unsigned long long* d0, unsigned long long* d1, int* flags, int64_t n, cudaStream_t st,
-                    const int32_t** roots_out) {
-  const int blocks = grid_for(n, 8);
-  OFL_CUDA(cudaMemsetAsync(flags, 0, 48 * sizeof(int), st));
-  pj_init_kernel<<<blocks, 256, 0, st>>>(succ, ptr_a, n);
+static int pj_rounds_for(int64_t n) {
+  int r = 2;
+  while ((1ll << (r - 1)) < n && r < PJ_MAX_ROUNDS) ++r;
+  return r + 1;  // one more round copies the last retirees' roots into both pointer buffers
+}
+
+static PjSeg pj_segments(int64_t n) {
+  PjSeg g;
+  g.n = n;
+  int64_t blocks = (n + 2047) / 2048;  // at least 2048 nodes per segment
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  g.seg = ((n + blocks - 1) / blocks + 31) / 32 * 32;
+  g.blocks = (int)((n + g.seg - 1) / g.seg);
+  return g;
+}
+constexpr int PJ_MAX_BLOCKS = 148 * 8 * 2;  // counts are sized for this many segments
+
+// Subtree sums over the forest `succ` (succ[u] = parent node or -1): on return (stream order) S[u] holds
+// the sum of the initial S over u's subtree and ptr_a holds ~root(u) for every node.  succ is preserved.
+// lists: 2 * (blocks * seg) int32; counts: (PJ_MAX_ROUNDS + 2) * 2 * blocks ints; d0/d1 zero on entry.
+// Does not synchronise: *leftover is set when the forest did not converge (a cycle).
+static int pj_solve(const int32_t* succ, int32_t* ptr_a, int32_t* ptr_b, int32_t* lists, int* counts, int* leftover,
+                    unsigned long long* S, unsigned long long* d0, unsigned long long* d1, int64_t n, cudaStream_t st) {
+  const PjSeg g = pj_segments(n);
+  OFL_REQUIRE(g.blocks <= PJ_MAX_BLOCKS, OFL_ERR_INVALID, "device has too many SMs for the solve's counter table");
+  const int rounds = pj_rounds_for(n);
+  int32_t* list[2] = {lists, lists + (int64_t)g.blocks * g.seg};
+  const int cstride = 2 * g.blocks;
+  pj_init_kernel<<<g.blocks, 256, 0, st>>>(succ, ptr_a, ptr_b, list[0], counts, g);
   OFL_CHECK_LAUNCH();
-  {
-    const int one = 1;
-    OFL_CUDA(cudaMemcpyAsync(flags, &one, sizeof(int), cudaMemcpyHostToDevice, st));
-  }
-  int max_rounds = 2;
-  while ((1ll << (max_rounds - 1)) < n && max_rounds < PJ_MAX_ROUNDS) ++max_rounds;
   int32_t* cur = ptr_a;
   int32_t* nxt = ptr_b;
-  for (int j = 0; j < max_rounds; ++j) {
-    pj_round_kernel<<<blocks, 256, 0, st>>>(cur, nxt, S, (j & 1) ? d1 : d0, (j & 1) ? d0 : d1, flags + j,
-                                            flags + j + 1, n);
+  for (int j = 0; j < rounds; ++j) {
+    pj_round_kernel<<<g.blocks, 256, 0, st>>>(list[j & 1], list[(j + 1) & 1], counts + (int64_t)j * cstride,
+                                              counts + (int64_t)(j + 1) * cstride, cur, nxt, S, (j & 1) ? d1 : d0,
+                                              (j & 1) ? d0 : d1, g);
     OFL_CHECK_LAUNCH();
     int32_t* t = cur;
     cur = nxt;
     nxt = t;
   }
-  pj_fold_kernel<<<blocks, 256, 0, st>>>(S, d0, d1, n);
+  pj_leftover_kernel<<<1, 256, 0, st>>>(counts + (int64_t)rounds * cstride, g.blocks, leftover);
   OFL_CHECK_LAUNCH();
-  // Rounds after convergence return early without writing ptr_out, so the converged pointers sit in
-  // whichever buffer the last ACTIVE round wrote: round j writes (j even ? ptr_b : ptr_a).
-  int h_flags[48];
-  OFL_CUDA(cudaMemcpyAsync(h_flags, flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
-  OFL_CUDA(cudaStreamSynchronize(st));
-  OFL_REQUIRE(h_flags[max_rounds] == 0, OFL_ERR_CYCLE, "flow-direction raster contains a cycle (perimeter graph)");
-  int last_active = 0;
-  for (int j = 0; j < max_rounds; ++j)
-    if (h_flags[j]) last_active = j;
-  if (roots_out) *roots_out = (last_active & 1) == 0 ? ptr_b : ptr_a;
-  // d0 / d1 are zero again except for what the fold consumed: clear for the next solve
+  pj_fold_kernel<<<grid_for(n, 8), 256, 0, st>>>(S, d0, d1, n);
+  OFL_CHECK_LAUNCH();
   return OFL_OK;
 }
 
-static int check_cycle_flag(const int* err_flag, cudaStream_t st) {
-  int h = 0;
-  OFL_CUDA(cudaMemcpyAsync(&h, err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+// One synchronisation at the end of a call: err[0] = cycle seen by a tile kernel, err[1] = a solve did
+// not converge.
+static int check_flags(const int* err_flags, cudaStream_t st) {
+  int h[2] = {0, 0};
+  OFL_CUDA(cudaMemcpyAsync(h, err_flags, sizeof(h), cudaMemcpyDeviceToHost, st));
   OFL_CUDA(cudaStreamSynchronize(st));
-  OFL_REQUIRE(h == 0, OFL_ERR_CYCLE, "flow-direction raster contains a cycle");
+  OFL_REQUIRE(h[0] == 0, OFL_ERR_CYCLE, "flow-direction raster contains a cycle");
+  OFL_REQUIRE(h[1] == 0, OFL_ERR_CYCLE, "flow-direction raster contains a cycle (perimeter graph)");
   return OFL_OK;
+}
+
+// Workspace of one perimeter graph with n nodes.  `keep_succ`: strips solve the same forest twice.
+struct GraphLayout {
+  int64_t n;
+  size_t off_succ, off_pa, off_pb, off_lists, off_S, off_S2, off_d0, off_d1, off_link, off_counts, off_err, total;
+};
+
+static GraphLayout graph_layout(int64_t n, bool strip) {
+  GraphLayout L;
+  L.n = n;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    const size_t at = o;
+    o = align_up(o + bytes, 256);
+    return at;
+  };
+  L.off_succ = take((size_t)n * 4);
+  L.off_pa = take((size_t)n * 4);
+  L.off_pb = take((size_t)n * 4);
+  L.off_lists = take(((size_t)n + 64 * (size_t)PJ_MAX_BLOCKS) * 8);  // 2 ping-pong lists of blocks*seg >= n entries
+  L.off_S = take((size_t)n * 8);
+  L.off_S2 = strip ? take((size_t)n * 8) : L.off_S;
+  L.off_d0 = take((size_t)n * 8);
+  L.off_d1 = take((size_t)n * 8);
+  L.off_link = take((size_t)n * 2);
+  L.off_counts = take((size_t)(PJ_MAX_ROUNDS + 2) * 2 * PJ_MAX_BLOCKS * sizeof(int));
+  L.off_err = take(64);
+  L.total = o;
+  return L;
+}
+
+static inline int64_t node_count(int64_t rows, int64_t cols) {
+  return ((rows + AT - 1) / AT) * ((cols + AT - 1) / AT) * SLOTS;
+}
+
+size_t accumulation_workspace_bytes(int64_t rows, int64_t cols) {
+  if (rows <= 0 || cols <= 0) return 256;
+  return graph_layout(node_count(rows, cols), false).total;
+}
+
+size_t strip_workspace_bytes(int64_t rows, int64_t cols) {
+  if (rows <= 0 || cols <= 0) return 256;
+  return graph_layout(node_count(rows, cols), true).total;
+}
+
+// Everything one raster (or strip) needs to launch its kernels.
+struct AccCtx {
+  AccParams p;
+  CUtensorMap tm;
+  GraphLayout L;
+  uint8_t* ws;
+  int64_t ntiles;
+  int32_t *pa, *pb, *lists;
+  unsigned long long *S2, *d0, *d1;
+  int* counts;
+};
+
+static int acc_setup(AccCtx& C, const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, int y_off, int has_above,
+                     int has_below, long long* fac, int64_t ld_fac, void* workspace, size_t workspace_bytes, bool strip) {
+  OFL_REQUIRE(rows >= 1 && cols >= 1 && rows < (1ll << 30) && cols < (1ll << 30), OFL_ERR_INVALID, "bad raster size");
+  OFL_REQUIRE((reinterpret_cast<uintptr_t>(fdr) & 15) == 0 && (ld_fdr % 16) == 0 && ld_fdr >= cols, OFL_ERR_ALIGNMENT,
+              "fdr must be 16-byte aligned with ld_fdr %% 16 == 0 (ld_fdr=%lld)", (long long)ld_fdr);
+  OFL_REQUIRE((reinterpret_cast<uintptr_t>(fac) & 7) == 0 && ld_fac >= cols, OFL_ERR_ALIGNMENT, "fac must be 8-byte aligned");
+  const int64_t n = node_count(rows, cols);
+  OFL_REQUIRE(n < (1ll << 31), OFL_ERR_INVALID, "raster too large for 32-bit perimeter node ids");
+  C.L = graph_layout(n, strip);
+  OFL_REQUIRE(workspace != nullptr && workspace_bytes >= C.L.total, OFL_ERR_WORKSPACE,
+              "accumulation workspace too small: need %zu bytes, have %zu", C.L.total, workspace_bytes);
+  C.ws = static_cast<uint8_t*>(workspace);
+  AccParams& p = C.p;
+  p.rows = (int)rows;
+  p.cols = (int)cols;
+  p.nty = (int)((rows + AT - 1) / AT);
+  p.ntx = (int)((cols + AT - 1) / AT);
+  p.succ = reinterpret_cast<int32_t*>(C.ws + C.L.off_succ);
+  p.link = reinterpret_cast<uint16_t*>(C.ws + C.L.off_link);
+  p.S = reinterpret_cast<unsigned long long*>(C.ws + C.L.off_S);
+  p.fac = fac;
+  p.ld_fac = ld_fac;
+  p.err = reinterpret_cast<int*>(C.ws + C.L.off_err);
+  p.y_off = y_off;
+  p.strip_above = has_above ? 1 : 0;
+  p.strip_below = has_below ? 1 : 0;
+  p.tile_base = 0;
+  C.pa = reinterpret_cast<int32_t*>(C.ws + C.L.off_pa);
+  C.pb = reinterpret_cast<int32_t*>(C.ws + C.L.off_pb);
+  C.lists = reinterpret_cast<int32_t*>(C.ws + C.L.off_lists);
+  C.S2 = reinterpret_cast<unsigned long long*>(C.ws + C.L.off_S2);
+  C.d0 = reinterpret_cast<unsigned long long*>(C.ws + C.L.off_d0);
+  C.d1 = reinterpret_cast<unsigned long long*>(C.ws + C.L.off_d1);
+  C.counts = reinterpret_cast<int*>(C.ws + C.L.off_counts);
+  C.ntiles = (int64_t)p.nty * p.ntx;
+  int rc = make_tensor_map_2d(&C.tm, fdr, 1, (uint64_t)cols, (uint64_t)(rows + 2 * y_off), (uint64_t)ld_fdr, ACS_W, ACS_H);
+  if (rc != OFL_OK) return rc;
+  return ensure_tile_attrs();
 }
 
 int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, long long* fac,
                         int64_t ld_fac, long long* perim_links_dev, void* workspace, size_t workspace_bytes,
                         cudaStream_t st) {
   if (rows <= 0 || cols <= 0) return OFL_OK;
-  OFL_REQUIRE(rows < (1ll << 30) && cols < (1ll << 30), OFL_ERR_INVALID, "raster dimension too large");
-  OFL_REQUIRE((reinterpret_cast<uintptr_t>(fdr) & 15) == 0 && (ld_fdr % 16) == 0 && ld_fdr >= cols, OFL_ERR_ALIGNMENT,
-              "fdr must be 16-byte aligned with ld_fdr %% 16 == 0 (ld_fdr=%lld)", (long long)ld_fdr);
-  OFL_REQUIRE((reinterpret_cast<uintptr_t>(fac) & 7) == 0 && ld_fac >= cols, OFL_ERR_ALIGNMENT,
-              "fac must be 8-byte aligned");
-  const AccLayout L = acc_layout(rows, cols);
-  OFL_REQUIRE(L.n_nodes < (1ll << 31), OFL_ERR_INVALID, "raster too large for 32-bit perimeter node ids");
-  OFL_REQUIRE(workspace != nullptr && workspace_bytes >= L.total, OFL_ERR_WORKSPACE,
-              "accumulation workspace too small: need %zu bytes, have %zu", L.total, workspace_bytes);
-  uint8_t* ws = static_cast<uint8_t*>(workspace);
-  AccParams p;
-  p.rows = (int)rows;
-  p.cols = (int)cols;
-  p.nty = (int)((rows + AT - 1) / AT);
-  p.ntx = (int)((cols + AT - 1) / AT);
-  p.succ = reinterpret_cast<int32_t*>(ws + L.off_succ);
-  int32_t* ptr_b = reinterpret_cast<int32_t*>(ws + L.off_ptr);
-  p.link = reinterpret_cast<uint16_t*>(ws + L.off_link);
-  p.S = reinterpret_cast<unsigned long long*>(ws + L.off_S);
-  unsigned long long* d0 = reinterpret_cast<unsigned long long*>(ws + L.off_d0);
-  unsigned long long* d1 = reinterpret_cast<unsigned long long*>(ws + L.off_d1);
-  int* flags = reinterpret_cast<int*>(ws + L.off_flags);
-  p.fac = fac;
-  p.ld_fac = ld_fac;
-  p.err = flags + 48;
-  p.y_off = 0;
-  p.strip_above = p.strip_below = 0;
-  p.tile_base = 0;
-  const int64_t ntiles = (int64_t)p.nty * p.ntx;
-  OFL_REQUIRE(ntiles < (1ll << 31), OFL_ERR_INVALID, "too many tiles");
-
-  CUtensorMap tm;
-  int rc = make_tensor_map_2d(&tm, fdr, 1, (uint64_t)cols, (uint64_t)rows, (uint64_t)ld_fdr, ACS_W, ACS_H);
+  AccCtx C;
+  int rc = acc_setup(C, fdr, rows, cols, ld_fdr, 0, 0, 0, fac, ld_fac, workspace, workspace_bytes, false);
   if (rc != OFL_OK) return rc;
-  rc = ensure_tile_attrs();
-  if (rc != OFL_OK) return rc;
-
-  // S, d0, d1 are contiguous: one memset
-  OFL_CUDA(cudaMemsetAsync(ws + L.off_S, 0, L.off_link - L.off_S, st));
-  OFL_CUDA(cudaMemsetAsync(flags, 0, 64 * sizeof(int), st));
+  const GraphLayout& L = C.L;
+  OFL_CUDA(cudaMemsetAsync(C.ws + L.off_S, 0, L.off_link - L.off_S, st));  // S, d0, d1
+  OFL_CUDA(cudaMemsetAsync(C.p.err, 0, 64, st));
   {
     PhaseScope ps(PHASE_ACC_TILE_A, st);
-    acc_tile_kernel<false><<<(unsigned)ntiles, ACC_THREADS, TileSmem<false>::BYTES, st>>>(tm, p);
+    acc_tile_kernel<false><<<(unsigned)C.ntiles, ACC_THREADS, TileSmem<false>::BYTES, st>>>(C.tm, C.p);
   }
   OFL_CHECK_LAUNCH();
-
-  // reduced-graph solve; succ is dead once pj_init has consumed it, so it doubles as a ping-pong buffer
-  const int32_t* roots = nullptr;
   {
     PhaseScope ps(PHASE_ACC_SOLVE, st);
-    rc = pj_solve(p.succ, ptr_b, p.succ, p.S, d0, d1, flags, L.n_nodes, st, &roots);
+    rc = pj_solve(C.p.succ, C.pa, C.pb, C.lists, C.counts, C.p.err + 1, C.p.S, C.d0, C.d1, L.n, st);
   }
   if (rc != OFL_OK) return rc;
   {
     PhaseScope ps(PHASE_ACC_TILE_B, st);
-    acc_tile_kernel<true><<<(unsigned)ntiles, ACC_THREADS, TileSmem<true>::BYTES, st>>>(tm, p);
+    acc_tile_kernel<true><<<(unsigned)C.ntiles, ACC_THREADS, TileSmem<true>::BYTES, st>>>(C.tm, C.p);
   }
   OFL_CHECK_LAUNCH();
-  rc = check_cycle_flag(p.err, st);
-  if (rc != OFL_OK) return rc;
   if (perim_links_dev) {
     const int64_t n = perimeter_count(rows, cols);
     {
       PhaseScope ps(PHASE_ACC_LINKS, st);
-      links_kernel<<<grid_for(n, 16), 256, 0, st>>>(fdr, ld_fdr, roots, p.link, p, perim_links_dev, n);
+      links_kernel<<<grid_for(n, 16), 256, 0, st>>>(fdr, ld_fdr, C.pa, C.p.link, C.p, perim_links_dev, n);
     }
     OFL_CHECK_LAUNCH();
   }
-  return OFL_OK;
+  return check_flags(C.p.err, st);
 }
 
 // ================================================================ row strips (multi-GPU)
@@ -811,43 +932,6 @@ int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t 
 //             replicated on every GPU: inflow from other strips into every boundary cell
 //   final     push the strip's inflows down its own perimeter graph (second solve on seeds only, by
 //             linearity), then pass B over all tiles
-struct StripLayout {
-  int64_t n_nodes;
-  size_t off_succ, off_pa, off_pb, off_S, off_S2, off_d0, off_d1, off_link, off_flags, total;
-};
-
-static StripLayout strip_layout(int64_t rows, int64_t cols) {
-  StripLayout L;
-  const int64_t nty = (rows + AT - 1) / AT, ntx = (cols + AT - 1) / AT;
-  L.n_nodes = nty * ntx * SLOTS;
-  size_t o = 0;
-  L.off_succ = o;
-  o = align_up(o + (size_t)L.n_nodes * 4, 256);
-  L.off_pa = o;
-  o = align_up(o + (size_t)L.n_nodes * 4, 256);
-  L.off_pb = o;
-  o = align_up(o + (size_t)L.n_nodes * 4, 256);
-  L.off_S = o;
-  o = align_up(o + (size_t)L.n_nodes * 8, 256);
-  L.off_S2 = o;
-  o = align_up(o + (size_t)L.n_nodes * 8, 256);
-  L.off_d0 = o;
-  o = align_up(o + (size_t)L.n_nodes * 8, 256);
-  L.off_d1 = o;
-  o = align_up(o + (size_t)L.n_nodes * 8, 256);
-  L.off_link = o;
-  o = align_up(o + (size_t)L.n_nodes * 2, 256);
-  L.off_flags = o;
-  o = align_up(o + 64 * sizeof(int), 256);
-  L.total = o;
-  return L;
-}
-
-size_t strip_workspace_bytes(int64_t rows, int64_t cols) {
-  if (rows <= 0 || cols <= 0) return 256;
-  return strip_layout(rows, cols).total;
-}
-
 // boundary record of cell (t ? last row : first row, c): strip-local count, code, and where its in-strip
 // path leaves the strip: (exit row selector << 30) | exit column, or -1 when it does not leave
 __global__ void strip_boundary_extract_kernel(const uint8_t* __restrict__ fdr, int64_t ld_fdr,
@@ -932,77 +1016,37 @@ __global__ void strip_seed_kernel(const long long* __restrict__ J, AccParams p, 
   }
 }
 
-struct StripCtx {
-  AccParams p;
-  CUtensorMap tm;
-  StripLayout L;
-  uint8_t* ws;
-  int64_t ntiles;
-};
-
-static int strip_setup(StripCtx& C, const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above,
+static int strip_setup(AccCtx& C, const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above,
                        int has_below, long long* fac, int64_t ld_fac, void* workspace, size_t workspace_bytes) {
-  OFL_REQUIRE(rows >= 2 && cols >= 1 && rows < (1ll << 30) && cols < (1ll << 30), OFL_ERR_INVALID,
-              "strip needs at least 2 rows");
+  OFL_REQUIRE(rows >= 2, OFL_ERR_INVALID, "a strip needs at least 2 rows");
   OFL_REQUIRE(!has_below || rows % AT == 0, OFL_ERR_INVALID,
               "a strip with a strip below it must have a multiple of %d rows (got %lld)", AT, (long long)rows);
-  OFL_REQUIRE((reinterpret_cast<uintptr_t>(fdr_halo) & 15) == 0 && (ld_fdr % 16) == 0 && ld_fdr >= cols,
-              OFL_ERR_ALIGNMENT, "fdr must be 16-byte aligned with ld_fdr %% 16 == 0");
-  OFL_REQUIRE((reinterpret_cast<uintptr_t>(fac) & 7) == 0 && ld_fac >= cols, OFL_ERR_ALIGNMENT, "fac must be 8-byte aligned");
-  C.L = strip_layout(rows, cols);
-  OFL_REQUIRE(C.L.n_nodes < (1ll << 31), OFL_ERR_INVALID, "strip too large for 32-bit perimeter node ids");
-  OFL_REQUIRE(workspace != nullptr && workspace_bytes >= C.L.total, OFL_ERR_WORKSPACE,
-              "strip workspace too small: need %zu bytes, have %zu", C.L.total, workspace_bytes);
-  C.ws = static_cast<uint8_t*>(workspace);
-  AccParams& p = C.p;
-  p.rows = (int)rows;
-  p.cols = (int)cols;
-  p.nty = (int)((rows + AT - 1) / AT);
-  p.ntx = (int)((cols + AT - 1) / AT);
-  p.succ = reinterpret_cast<int32_t*>(C.ws + C.L.off_succ);
-  p.link = reinterpret_cast<uint16_t*>(C.ws + C.L.off_link);
-  p.S = reinterpret_cast<unsigned long long*>(C.ws + C.L.off_S);
-  p.fac = fac;
-  p.ld_fac = ld_fac;
-  p.err = reinterpret_cast<int*>(C.ws + C.L.off_flags) + 48;
-  p.y_off = 1;
-  p.strip_above = has_above ? 1 : 0;
-  p.strip_below = has_below ? 1 : 0;
-  p.tile_base = 0;
-  C.ntiles = (int64_t)p.nty * p.ntx;
-  int rc = make_tensor_map_2d(&C.tm, fdr_halo, 1, (uint64_t)cols, (uint64_t)rows + 2, (uint64_t)ld_fdr, ACS_W, ACS_H);
-  if (rc != OFL_OK) return rc;
-  return ensure_tile_attrs();
+  return acc_setup(C, fdr_halo, rows, cols, ld_fdr, 1, has_above, has_below, fac, ld_fac, workspace, workspace_bytes, true);
 }
 
 int strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above, int has_below,
                       long long* fac, int64_t ld_fac, void* workspace, size_t workspace_bytes, int32_t* slink,
                       long long* floc, uint8_t* bcode, cudaStream_t st) {
-  StripCtx C;
+  AccCtx C;
   int rc = strip_setup(C, fdr_halo, rows, cols, ld_fdr, has_above, has_below, fac, ld_fac, workspace, workspace_bytes);
   if (rc != OFL_OK) return rc;
-  const StripLayout& L = C.L;
-  int* flags = reinterpret_cast<int*>(C.ws + L.off_flags);
+  const GraphLayout& L = C.L;
   OFL_CUDA(cudaMemsetAsync(C.ws + L.off_S, 0, L.off_link - L.off_S, st));  // S, S2, d0, d1
-  OFL_CUDA(cudaMemsetAsync(flags, 0, 64 * sizeof(int), st));
+  OFL_CUDA(cudaMemsetAsync(C.p.err, 0, 64, st));
   {
     PhaseScope ps(PHASE_ACC_TILE_A, st);
     acc_tile_kernel<false><<<(unsigned)C.ntiles, ACC_THREADS, TileSmem<false>::BYTES, st>>>(C.tm, C.p);
   }
   OFL_CHECK_LAUNCH();
-  const int32_t* roots = nullptr;
   {
     PhaseScope ps(PHASE_ACC_SOLVE, st);
-    rc = pj_solve(C.p.succ, reinterpret_cast<int32_t*>(C.ws + L.off_pa), reinterpret_cast<int32_t*>(C.ws + L.off_pb),
-                  C.p.S, reinterpret_cast<unsigned long long*>(C.ws + L.off_d0),
-                  reinterpret_cast<unsigned long long*>(C.ws + L.off_d1), flags, L.n_nodes, st, &roots);
+    rc = pj_solve(C.p.succ, C.pa, C.pb, C.lists, C.counts, C.p.err + 1, C.p.S, C.d0, C.d1, L.n, st);
   }
   if (rc != OFL_OK) return rc;
   // strip-local counts of the first and last tile row (their cells include both boundary rows)
   {
     PhaseScope ps(PHASE_STRIP_EDGE, st);
     AccParams pb = C.p;
-    pb.tile_base = 0;
     acc_tile_kernel<true><<<(unsigned)pb.ntx, ACC_THREADS, TileSmem<true>::BYTES, st>>>(C.tm, pb);
     if (pb.nty > 1) {
       pb.tile_base = (pb.nty - 1) * pb.ntx;
@@ -1011,15 +1055,14 @@ int strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
     }
   }
   OFL_CHECK_LAUNCH();
-  strip_boundary_extract_kernel<<<grid_for(2 * cols, 8), 256, 0, st>>>(fdr_halo, ld_fdr, fac, ld_fac, roots, C.p.link,
-                                                                       C.p, slink, floc, bcode);
+  strip_boundary_extract_kernel<<<grid_for(2 * cols, 8), 256, 0, st>>>(fdr_halo, ld_fdr, fac, ld_fac, C.pa, C.p.link, C.p,
+                                                                       slink, floc, bcode);
   OFL_CHECK_LAUNCH();
-  return check_cycle_flag(C.p.err, st);
+  return check_flags(C.p.err, st);
 }
 
 size_t strip_boundary_workspace_bytes(int n_strips, int64_t cols) {
-  const size_t n = (size_t)n_strips * 2 * (size_t)cols;
-  return align_up(n * 4, 256) * 3 + align_up(n * 8, 256) * 3 + 512;
+  return graph_layout((int64_t)n_strips * 2 * cols, false).total;
 }
 
 int strip_boundary_solve(const int32_t* slink_all, const long long* floc_all, const uint8_t* code_all, int n_strips,
@@ -1027,54 +1070,49 @@ int strip_boundary_solve(const int32_t* slink_all, const long long* floc_all, co
   OFL_REQUIRE(n_strips >= 1 && cols >= 1, OFL_ERR_INVALID, "bad boundary graph size");
   const int64_t n = (int64_t)n_strips * 2 * cols;
   OFL_REQUIRE(n < (1ll << 31), OFL_ERR_INVALID, "boundary graph too large");
-  OFL_REQUIRE(workspace != nullptr && workspace_bytes >= strip_boundary_workspace_bytes(n_strips, cols),
-              OFL_ERR_WORKSPACE, "boundary workspace too small");
+  const GraphLayout L = graph_layout(n, false);
+  OFL_REQUIRE(workspace != nullptr && workspace_bytes >= L.total, OFL_ERR_WORKSPACE, "boundary workspace too small");
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  const size_t a4 = align_up((size_t)n * 4, 256), a8 = align_up((size_t)n * 8, 256);
-  int32_t* succ = reinterpret_cast<int32_t*>(ws);
-  int32_t* pa = reinterpret_cast<int32_t*>(ws + a4);
-  int32_t* pb = reinterpret_cast<int32_t*>(ws + 2 * a4);
-  unsigned long long* S = reinterpret_cast<unsigned long long*>(ws + 3 * a4);
-  unsigned long long* d0 = reinterpret_cast<unsigned long long*>(ws + 3 * a4 + a8);
-  unsigned long long* d1 = reinterpret_cast<unsigned long long*>(ws + 3 * a4 + 2 * a8);
-  int* flags = reinterpret_cast<int*>(ws + 3 * a4 + 3 * a8);
-  OFL_CUDA(cudaMemsetAsync(S, 0, 3 * a8, st));
+  int32_t* succ = reinterpret_cast<int32_t*>(ws + L.off_succ);
+  unsigned long long* S = reinterpret_cast<unsigned long long*>(ws + L.off_S);
+  int* counts = reinterpret_cast<int*>(ws + L.off_counts);
+  int* err = reinterpret_cast<int*>(ws + L.off_err);
+  OFL_CUDA(cudaMemsetAsync(ws + L.off_S, 0, L.off_link - L.off_S, st));
+  OFL_CUDA(cudaMemsetAsync(err, 0, 64, st));
   strip_graph_build_kernel<<<grid_for(n, 8), 256, 0, st>>>(slink_all, floc_all, code_all, n_strips, cols, succ, S);
   OFL_CHECK_LAUNCH();
   int rc;
   {
     PhaseScope ps(PHASE_ACC_SOLVE, st);
-    rc = pj_solve(succ, pa, pb, S, d0, d1, flags, n, st, nullptr);
+    rc = pj_solve(succ, reinterpret_cast<int32_t*>(ws + L.off_pa), reinterpret_cast<int32_t*>(ws + L.off_pb),
+                  reinterpret_cast<int32_t*>(ws + L.off_lists), counts, err + 1, S,
+                  reinterpret_cast<unsigned long long*>(ws + L.off_d0), reinterpret_cast<unsigned long long*>(ws + L.off_d1), n,
+                  st);
   }
   if (rc != OFL_OK) return rc;
   OFL_CUDA(cudaMemcpyAsync(J_all, S, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
-  return OFL_OK;
+  return check_flags(err, st);
 }
 
 int strip_accum_final(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above, int has_below,
                       const long long* J_mine, void* workspace, size_t workspace_bytes, long long* fac, int64_t ld_fac,
                       cudaStream_t st) {
-  StripCtx C;
+  AccCtx C;
   int rc = strip_setup(C, fdr_halo, rows, cols, ld_fdr, has_above, has_below, fac, ld_fac, workspace, workspace_bytes);
   if (rc != OFL_OK) return rc;
-  const StripLayout& L = C.L;
-  int* flags = reinterpret_cast<int*>(C.ws + L.off_flags);
-  unsigned long long* S2 = reinterpret_cast<unsigned long long*>(C.ws + L.off_S2);
-  unsigned long long* d0 = reinterpret_cast<unsigned long long*>(C.ws + L.off_d0);
-  unsigned long long* d1 = reinterpret_cast<unsigned long long*>(C.ws + L.off_d1);
+  const GraphLayout& L = C.L;
   // inflow from other strips enters at the boundary rows; by linearity its effect on every perimeter
   // node is the subtree sum of those seeds over the strip's (preserved) perimeter forest
-  OFL_CUDA(cudaMemsetAsync(S2, 0, L.off_link - L.off_S2, st));  // S2, d0, d1
-  strip_seed_kernel<<<grid_for(2 * cols, 8), 256, 0, st>>>(J_mine, C.p, S2);
+  OFL_CUDA(cudaMemsetAsync(C.ws + L.off_S2, 0, L.off_link - L.off_S2, st));  // S2, d0, d1
+  OFL_CUDA(cudaMemsetAsync(C.p.err, 0, 64, st));
+  strip_seed_kernel<<<grid_for(2 * cols, 8), 256, 0, st>>>(J_mine, C.p, C.S2);
   OFL_CHECK_LAUNCH();
   {
     PhaseScope ps(PHASE_ACC_SOLVE, st);
-    rc = pj_solve(C.p.succ, reinterpret_cast<int32_t*>(C.ws + L.off_pa), reinterpret_cast<int32_t*>(C.ws + L.off_pb), S2,
-                  d0, d1, flags, L.n_nodes, st, nullptr);
+    rc = pj_solve(C.p.succ, C.pa, C.pb, C.lists, C.counts, C.p.err + 1, C.S2, C.d0, C.d1, L.n, st);
     if (rc == OFL_OK) {
-      // S += S2 (d1 is zero again after the solve's own fold only if it was untouched: use a zeroed d0)
-      OFL_CUDA(cudaMemsetAsync(d0, 0, (size_t)L.n_nodes * 8, st));
-      pj_fold_kernel<<<grid_for(L.n_nodes, 8), 256, 0, st>>>(C.p.S, S2, d0, L.n_nodes);
+      OFL_CUDA(cudaMemsetAsync(C.d0, 0, (size_t)L.n * 8, st));
+      pj_fold_kernel<<<grid_for(L.n, 8), 256, 0, st>>>(C.p.S, C.S2, C.d0, L.n);  // S += S2
     }
   }
   if (rc != OFL_OK) return rc;
@@ -1084,7 +1122,7 @@ int strip_accum_final(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
     acc_tile_kernel<true><<<(unsigned)C.ntiles, ACC_THREADS, TileSmem<true>::BYTES, st>>>(C.tm, C.p);
   }
   OFL_CHECK_LAUNCH();
-  return check_cycle_flag(C.p.err, st);
+  return check_flags(C.p.err, st);
 }
 
 int launch_check(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, const long long* fac, int64_t ld_fac,
