@@ -25,7 +25,8 @@ METRIC = "d8_flowdir_flowacc_throughput"
 UNIT = "Gcells/s"
 DIR_BYTES_PER_CELL = 5.0   # 4 B float32 read + 1 B code write            
 ACC_BYTES_PER_CELL = 9.0   # 1 B code read + 8 B int64 count write         
-PHASE_BYTES = {"direction": 5.0, "acc_tile_a": 1.0, "acc_tile_b": 9.0}
+# accumulation: 9 B/cell = 1 B code read (pass A) + 8 B count write (final pass)
+PHASE_BYTES = {"direction": 5.0, "acc_tile_a": 1.0, "acc_tile_b": 8.0}
 
 
 def measured_hbm_peak():

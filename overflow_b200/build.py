@@ -44,7 +44,8 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + srcs
+    extra = os.environ.get("OFL_NVCC_EXTRA", "").split()  # e.g. -DOFL_DIR_RB=4 for tuning sweeps
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + srcs
     env = dict(os.environ)
     env.pop("CC", None)  # the image exports a gcc wrapper that nvcc should not pick up
     env.pop("CXX", None)

@@ -92,7 +92,8 @@ struct AccParams {
   int ntx, nty;    // tiles per row / column
   int32_t* succ;   // [ntiles*SLOTS] successor node or -1
   uint16_t* link;  // [ntiles*SLOTS] exit slot | kind << 8
-  unsigned long long* S;  // [ntiles*SLOTS] pass A: base inflow; pass B: total inflow from outside the tile
+  unsigned long long* S;  // [ntiles*SLOTS] pass A: base inflow; final pass: total inflow from outside the tile
+  uint16_t* L;            // [ntiles][64*64] tile-local counts written by pass A, read by the final pass
   long long* fac;
   int64_t ld_fac;
   int* err;  // device flag: set to 1 when a cycle is detected
@@ -475,6 +476,21 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     }
     p.succ[(size_t)tile * SLOTS + s] = succ;
     p.link[(size_t)tile * SLOTS + s] = lk;
+    // tile-local counts (<= 4096, fit 16 bits) for the final pass: tile-major, 16-byte vector stores
+    uint4* Lt = reinterpret_cast<uint4*>(p.L + (size_t)tile * (AT * AT));
+#pragma unroll
+    for (int g = tid; g < AT * AT / 8; g += ACC_THREADS) {
+      const uint32_t a = a_word0 + ((g >> 3) * WP + (g & 7) * 8) * 4;
+      uint32_t v[8], missing = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        v[k] = lds32(a + 4 * k);
+        missing |= v[k];
+        v[k] &= 0xFFFFu;
+      }
+      if (missing >> 28) atomicExch(p.err, 1);  // a cell never completed: the raster holds a cycle
+      Lt[g] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+    }
   } else {
     // ---- final counts: lane-contiguous int64 stores (256 B per half row); NODATA cells get -9998
     bool stuck = false;
@@ -496,6 +512,107 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
       }
     }
     if (stuck) atomicExch(p.err, 1);  // a missing-count never reached zero: cycle
+  }
+}
+
+// ---------------------------------------------------------------- final pass
+// fac(v) = L(v) + sum of the inflows I(e) of the perimeter cells e whose in-tile path runs through v.
+// Pass A left L (tile-local counts) in HBM and the solve left I(e) in S, so the final pass only has to
+// add every non-zero inflow along its path: one thread per perimeter cell walks downstream adding its
+// 64-bit inflow to each cell with a 32-bit shared atomic (+ a carry atomic when the low word wraps),
+// then the tile is written out as int64.  ~11 B/cell of HBM traffic and a few hundred instructions per
+// warp: this kernel runs close to the HBM roofline instead of re-doing the whole propagation.
+struct FinalSmem {
+  static constexpr int CS = 0;
+  static constexpr int LO = 6400;
+  static constexpr int HI = LO + AT * AT * 4;
+  static constexpr int TAB = HI + AT * AT * 4;  // int4 per direction code: {code-array byte offset, dy, dx, 0}
+  static constexpr int BAR = TAB + 128;
+  static constexpr int BYTES = BAR + 16;
+};
+
+__global__ void __launch_bounds__(ACC_THREADS) acc_final_kernel(const __grid_constant__ CUtensorMap tm, const AccParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const uint32_t sb = smem_u32(smem_raw);
+  const uint32_t a_cs0 = sb + FinalSmem::CS + ACS_W * ACS_Y0 + ACS_X0;  // code of cell (0,0)
+  const uint32_t a_lo = sb + FinalSmem::LO, a_hi = sb + FinalSmem::HI, a_tab = sb + FinalSmem::TAB;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + FinalSmem::BAR);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x + p.tile_base;
+  const int ty = tile / p.ntx, tx = tile - ty * p.ntx;
+  const int y0 = ty << AT_SHIFT, x0 = tx << AT_SHIFT;
+  const int h = min(AT, p.rows - y0), w = min(AT, p.cols - x0);
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(bar, ACS_BYTES);
+    tma_load_2d(smem_raw + FinalSmem::CS, &tm, x0 - ACS_X0, y0 - ACS_Y0 + p.y_off, bar);
+  }
+  if (tid < 8) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_tab + 16 * tid),
+                 "r"((uint32_t)(dir_dy(tid) * ACS_W + dir_dx(tid))), "r"((uint32_t)dir_dy(tid)), "r"((uint32_t)dir_dx(tid)),
+                 "r"(0u)
+                 : "memory");
+  }
+  // tile-local counts -> low words; high words start at zero
+  const uint4* Lt = reinterpret_cast<const uint4*>(p.L + (size_t)tile * (AT * AT));
+#pragma unroll
+  for (int g = tid; g < AT * AT / 8; g += ACC_THREADS) {
+    const uint4 q = Lt[g];
+    const uint32_t a = a_lo + g * 32;
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(q.x & 0xFFFFu), "r"(q.x >> 16),
+                 "r"(q.y & 0xFFFFu), "r"(q.y >> 16)
+                 : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16), "r"(q.z & 0xFFFFu), "r"(q.z >> 16),
+                 "r"(q.w & 0xFFFFu), "r"(q.w >> 16)
+                 : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a_hi + g * 32), "r"(0u) : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a_hi + g * 32 + 16), "r"(0u) : "memory");
+  }
+  // inflow of this thread's perimeter cell (global load overlaps the TMA wait)
+  int y = 0, x = 0;
+  unsigned long long seed = 0;
+  if (cell_of_slot(tid, h, w, y, x)) seed = p.S[(size_t)tile * SLOTS + tid];
+  __syncthreads();
+  mbar_wait(bar, 0);
+
+  if (seed) {
+    const uint32_t slo = (uint32_t)seed, shi = (uint32_t)(seed >> 32);
+    uint32_t ca = a_cs0 + y * ACS_W + x;
+    for (int steps = 0; steps <= AT * AT; ++steps) {
+      const uint32_t o = (y * AT + x) * 4;
+      const uint32_t old = atoms_add(a_lo + o, slo);
+      const uint32_t hadd = shi + ((old + slo) < old ? 1u : 0u);
+      if (hadd) atoms_add(a_hi + o, hadd);
+      const uint32_t code = lds8(ca);
+      if (code >= 8) break;  // pit / flat / nodata / invalid: no downstream cell
+      uint32_t t0, t1, t2, t3;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3) : "r"(a_tab + 16 * code) : "memory");
+      y += (int)t1;
+      x += (int)t2;
+      if (y < 0 || y >= h || x < 0 || x >= w) break;  // leaves the tile (or the raster)
+      ca += t0;
+      if (lds8(ca) == OFL_DIR_NODATA) break;  // no edge into a NODATA cell
+      (void)t3;
+    }
+  }
+  __syncthreads();
+
+  // final counts: lane-contiguous int64 stores (256 B per half row); NODATA cells get -9998
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int xx = lane + 32 * half;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int yy = 8 * warp + k;
+      if (yy < h && xx < w) {
+        const uint32_t o = (yy * AT + xx) * 4;
+        long long v = (long long)(((unsigned long long)lds32(a_hi + o) << 32) | lds32(a_lo + o));
+        if (lds8(a_cs0 + yy * ACS_W + xx) == OFL_DIR_NODATA) v = OFL_FAC_NODATA_EMITTED;
+        p.fac[(int64_t)(y0 + yy) * p.ld_fac + (x0 + xx)] = v;
+      }
+    }
   }
 }
 
@@ -715,8 +832,7 @@ static int ensure_tile_attrs() {
   if (!attr_set) {
     OFL_CUDA(cudaFuncSetAttribute(acc_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   TileSmem<false>::BYTES));
-    OFL_CUDA(cudaFuncSetAttribute(acc_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  TileSmem<true>::BYTES));
+    OFL_CUDA(cudaFuncSetAttribute(acc_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FinalSmem::BYTES));
     attr_set = true;
   }
   return OFL_OK;
@@ -792,10 +908,10 @@ static int check_flags(const int* err_flags, cudaStream_t st) {
 // Workspace of one perimeter graph with n nodes.  `keep_succ`: strips solve the same forest twice.
 struct GraphLayout {
   int64_t n;
-  size_t off_succ, off_pa, off_pb, off_lists, off_S, off_S2, off_d0, off_d1, off_link, off_counts, off_err, total;
+  size_t off_succ, off_pa, off_pb, off_lists, off_S, off_S2, off_d0, off_d1, off_link, off_counts, off_err, off_L, total;
 };
 
-static GraphLayout graph_layout(int64_t n, bool strip) {
+static GraphLayout graph_layout(int64_t n, bool strip, bool with_tiles = true) {
   GraphLayout L;
   L.n = n;
   size_t o = 0;
@@ -815,6 +931,7 @@ static GraphLayout graph_layout(int64_t n, bool strip) {
   L.off_link = take((size_t)n * 2);
   L.off_counts = take((size_t)(PJ_MAX_ROUNDS + 2) * 2 * PJ_MAX_BLOCKS * sizeof(int));
   L.off_err = take(64);
+  L.off_L = with_tiles ? take((size_t)(n / SLOTS) * AT * AT * sizeof(uint16_t)) : o;
   L.total = o;
   return L;
 }
@@ -868,6 +985,7 @@ static int acc_setup(AccCtx& C, const uint8_t* fdr, int64_t rows, int64_t cols, 
   p.fac = fac;
   p.ld_fac = ld_fac;
   p.err = reinterpret_cast<int*>(C.ws + C.L.off_err);
+  p.L = reinterpret_cast<uint16_t*>(C.ws + C.L.off_L);
   p.y_off = y_off;
   p.strip_above = has_above ? 1 : 0;
   p.strip_below = has_below ? 1 : 0;
@@ -907,7 +1025,7 @@ int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t 
   if (rc != OFL_OK) return rc;
   {
     PhaseScope ps(PHASE_ACC_TILE_B, st);
-    acc_tile_kernel<true><<<(unsigned)C.ntiles, ACC_THREADS, TileSmem<true>::BYTES, st>>>(C.tm, C.p);
+    acc_final_kernel<<<(unsigned)C.ntiles, ACC_THREADS, FinalSmem::BYTES, st>>>(C.tm, C.p);
   }
   OFL_CHECK_LAUNCH();
   if (perim_links_dev) {
@@ -1047,10 +1165,10 @@ int strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
   {
     PhaseScope ps(PHASE_STRIP_EDGE, st);
     AccParams pb = C.p;
-    acc_tile_kernel<true><<<(unsigned)pb.ntx, ACC_THREADS, TileSmem<true>::BYTES, st>>>(C.tm, pb);
+    acc_final_kernel<<<(unsigned)pb.ntx, ACC_THREADS, FinalSmem::BYTES, st>>>(C.tm, pb);
     if (pb.nty > 1) {
       pb.tile_base = (pb.nty - 1) * pb.ntx;
-      acc_tile_kernel<true><<<(unsigned)pb.ntx, ACC_THREADS, TileSmem<true>::BYTES, st>>>(C.tm, pb);
+      acc_final_kernel<<<(unsigned)pb.ntx, ACC_THREADS, FinalSmem::BYTES, st>>>(C.tm, pb);
       count_launch();
     }
   }
@@ -1062,7 +1180,7 @@ int strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
 }
 
 size_t strip_boundary_workspace_bytes(int n_strips, int64_t cols) {
-  return graph_layout((int64_t)n_strips * 2 * cols, false).total;
+  return graph_layout((int64_t)n_strips * 2 * cols, false, false).total;
 }
 
 int strip_boundary_solve(const int32_t* slink_all, const long long* floc_all, const uint8_t* code_all, int n_strips,
@@ -1070,7 +1188,7 @@ int strip_boundary_solve(const int32_t* slink_all, const long long* floc_all, co
   OFL_REQUIRE(n_strips >= 1 && cols >= 1, OFL_ERR_INVALID, "bad boundary graph size");
   const int64_t n = (int64_t)n_strips * 2 * cols;
   OFL_REQUIRE(n < (1ll << 31), OFL_ERR_INVALID, "boundary graph too large");
-  const GraphLayout L = graph_layout(n, false);
+  const GraphLayout L = graph_layout(n, false, false);
   OFL_REQUIRE(workspace != nullptr && workspace_bytes >= L.total, OFL_ERR_WORKSPACE, "boundary workspace too small");
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   int32_t* succ = reinterpret_cast<int32_t*>(ws + L.off_succ);
@@ -1119,7 +1237,7 @@ int strip_accum_final(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
   OFL_CHECK_LAUNCH();
   {
     PhaseScope ps(PHASE_ACC_TILE_B, st);
-    acc_tile_kernel<true><<<(unsigned)C.ntiles, ACC_THREADS, TileSmem<true>::BYTES, st>>>(C.tm, C.p);
+    acc_final_kernel<<<(unsigned)C.ntiles, ACC_THREADS, FinalSmem::BYTES, st>>>(C.tm, C.p);
   }
   OFL_CHECK_LAUNCH();
   return check_flags(C.p.err, st);

@@ -39,11 +39,23 @@
 
 namespace ofl {
 
-constexpr int DIR_RB = 8;        // rows per TMA box / pipeline stage
-constexpr int DIR_STAGES = 4;    // stages per warp
+#ifndef OFL_DIR_RB
+#define OFL_DIR_RB 4
+#endif
+#ifndef OFL_DIR_STAGES
+#define OFL_DIR_STAGES 4
+#endif
+#ifndef OFL_DIR_WARPS
+#define OFL_DIR_WARPS 4
+#endif
+#ifndef OFL_DIR_CTAS_PER_SM
+#define OFL_DIR_CTAS_PER_SM 5
+#endif
+constexpr int DIR_RB = OFL_DIR_RB;          // rows per TMA box / pipeline stage
+constexpr int DIR_STAGES = OFL_DIR_STAGES;  // stages per warp
 constexpr int DIR_BOXW = 136;    // 4 apron + 128 band + 4 apron floats
 constexpr int DIR_BAND = 128;    // columns per warp band
-constexpr int DIR_WARPS = 4;     // warps per CTA
+constexpr int DIR_WARPS = OFL_DIR_WARPS;    // warps per CTA
 constexpr int DIR_STAGE_FLOATS = DIR_RB * DIR_BOXW;
 constexpr uint32_t DIR_STAGE_BYTES = DIR_STAGE_FLOATS * 4;
 constexpr size_t DIR_SMEM_BYTES = size_t(DIR_WARPS) * DIR_STAGES * DIR_STAGE_BYTES + DIR_WARPS * DIR_STAGES * 8;
@@ -106,6 +118,15 @@ __device__ __forceinline__ uint32_t d8_fast(float dE, float dNE, float dN, float
   return code;
 }
 
+// One input row as a lane sees it: its 4 cells plus one cell either side (nodata already -inf), and the
+// float32 differences between the row above and this row, formed when this row arrived.
+struct DirRow {
+  float v[6];     // columns xl-1 .. xl+4
+  float uS[4];    // above[j+1] - v[j+1]   (cell j of the row above -> its S neighbour)
+  float uSE[5];   // above[j]   - v[j+1]   (cell j-1 of the row above -> its SE neighbour)
+  float uSW[5];   // above[j+1] - v[j]     (cell j of the row above -> its SW neighbour)
+};
+
 __global__ void __launch_bounds__(DIR_WARPS * 32) direction_kernel(const __grid_constant__ CUtensorMap tm,
                                                                     const DirParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -159,113 +180,115 @@ __global__ void __launch_bounds__(DIR_WARPS * 32) direction_kernel(const __grid_
       return tiles[s * DIR_STAGE_FLOATS + (rel % DIR_RB) * DIR_BOXW + (cx - x0 + 4)];
     };
 
-    // rolling state: centre row b (cols -1..4) and the differences carried from the row above
-    float b[6];
-    float nS[4], nSE[5], nSW[5];  // carried: (row above) - (centre row) pairs
-#pragma unroll
-    for (int j = 0; j < 6; ++j) b[j] = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) nS[j] = 0.f;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) nSE[j] = nSW[j] = 0.f;
-
-    for (int k = 0; k < nblk; ++k) {
+    // load input row i (relative) into r.v: patch cells outside the array, nodata -> -inf
+    auto load_row = [&](int i, DirRow& r) {
+      const int k = i / DIR_RB, rr = i - k * DIR_RB;
       const uint32_t s = (g0 + k) % DIR_STAGES;
-      mbar_wait(&bars[s], ((g0 + k) / DIR_STAGES) & 1);
-      const float* t = tiles + s * DIR_STAGE_FLOATS + 4 * lane;
+      if (rr == 0) mbar_wait(&bars[s], ((g0 + k) / DIR_STAGES) & 1);
+      const float* t = tiles + s * DIR_STAGE_FLOATS + rr * DIR_BOXW + 4 * lane;
+      const float4 q = *reinterpret_cast<const float4*>(t + 4);
+      r.v[0] = t[3];
+      r.v[1] = q.x;
+      r.v[2] = q.y;
+      r.v[3] = q.z;
+      r.v[4] = q.w;
+      r.v[5] = t[8];
+      const int iy = iy0 + i;
+      if (iy < 0 || iy >= p.in_rows) {
 #pragma unroll
-      for (int rr = 0; rr < DIR_RB; ++rr) {
-        const int i = k * DIR_RB + rr;
-        if (i >= n_in) break;
-        const int iy = iy0 + i;
-        // ---- load the new row (cols -1..4 of this lane), patch out-of-array cells, nodata -> -inf
-        float c[6];
-        {
-          const float4 v = *reinterpret_cast<const float4*>(t + rr * DIR_BOXW + 4);
-          c[0] = t[rr * DIR_BOXW + 3];
-          c[1] = v.x;
-          c[2] = v.y;
-          c[3] = v.z;
-          c[4] = v.w;
-          c[5] = t[rr * DIR_BOXW + 8];
+        for (int j = 0; j < 6; ++j) r.v[j] = p.fillv;
+      } else if (edge_band) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const int cx = xl - 1 + j;
+          if (cx < 0 || cx >= p.W) r.v[j] = p.fillv;
         }
-        if (iy < 0 || iy >= p.in_rows) {
+      }
 #pragma unroll
-          for (int j = 0; j < 6; ++j) c[j] = p.fillv;
-        } else if (edge_band) {
-#pragma unroll
-          for (int j = 0; j < 6; ++j) {
-            const int cx = xl - 1 + j;
-            if (cx < 0 || cx >= p.W) c[j] = p.fillv;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 6; ++j) c[j] = (c[j] == nd) ? NINF : c[j];
+      for (int j = 0; j < 6; ++j) r.v[j] = (r.v[j] == nd) ? NINF : r.v[j];
+    };
 
-        if (i >= 1) {
-          // ---- differences between centre row b and the new row c (shared by both rows)
-          float vS[4], pSE[5], pSW[5];
+    // after the last row of box k has been consumed, box k-1 is no longer needed by the exact path:
+    // its stage takes box k+STAGES-1
+    auto end_of_row = [&](int i) {
+      const int k = i / DIR_RB;
+      if (i - k * DIR_RB == DIR_RB - 1 || i == n_in - 1) {
+        __syncwarp();
+        if (lane == 0 && (k + DIR_STAGES - 1) < nblk) {
+          const int kn = k + DIR_STAGES - 1;
+          const uint32_t sn = (g0 + kn) % DIR_STAGES;
+          mbar_arrive_expect_tx(&bars[sn], DIR_STAGE_BYTES);
+          tma_load_2d(tiles + sn * DIR_STAGE_FLOATS, &tm, x0 - 4, iy0 + kn * DIR_RB, &bars[sn]);
+        }
+      }
+    };
+
+    // input row i arrives in `c`; `b` is the row above it.  Forms the differences between the two rows
+    // and, when b is an output row (i >= 2), emits b's codes.
+    auto step = [&](int i, const DirRow& b, DirRow& c) {
+      load_row(i, c);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) vS[j] = __fsub_rn(b[j + 1], c[j + 1]);  // cell j -> S
+      for (int j = 0; j < 4; ++j) c.uS[j] = __fsub_rn(b.v[j + 1], c.v[j + 1]);
 #pragma unroll
-          for (int j = 0; j < 5; ++j) pSE[j] = __fsub_rn(b[j], c[j + 1]);  // cell j-1 -> SE
+      for (int j = 0; j < 5; ++j) c.uSE[j] = __fsub_rn(b.v[j], c.v[j + 1]);
 #pragma unroll
-          for (int j = 0; j < 5; ++j) pSW[j] = __fsub_rn(b[j + 1], c[j]);  // cell j -> SW
-          if (i >= 2) {
-            const int y = y0 + i - 2;
-            float hE[5];
+      for (int j = 0; j < 5; ++j) c.uSW[j] = __fsub_rn(b.v[j + 1], c.v[j]);
+      if (i >= 2) {
+        float hE[5];
 #pragma unroll
-            for (int j = 0; j < 5; ++j) hE[j] = __fsub_rn(b[j], b[j + 1]);  // cell j-1 -> E
-            uint32_t packed = 0;
+        for (int j = 0; j < 5; ++j) hE[j] = __fsub_rn(b.v[j], b.v[j + 1]);  // cell j-1 -> E
+        uint32_t packed = 0;
+        bool any_special = false;
+        uint32_t special_mask = 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              bool special;
-              uint32_t code = d8_fast(/*E*/ hE[j + 1], /*NE*/ -nSW[j + 1], /*N*/ -nS[j], /*NW*/ -nSE[j],
-                                      /*W*/ -hE[j], /*SW*/ pSW[j], /*S*/ vS[j], /*SE*/ pSE[j + 1], special);
-              if (special) {
-                const int cx = xl + j;
-                float n[8];
-                n[0] = raw_at(i - 1, cx + 1);
-                n[1] = raw_at(i - 2, cx + 1);
-                n[2] = raw_at(i - 2, cx);
-                n[3] = raw_at(i - 2, cx - 1);
-                n[4] = raw_at(i - 1, cx - 1);
-                n[5] = raw_at(i, cx - 1);
-                n[6] = raw_at(i, cx);
-                n[7] = raw_at(i, cx + 1);
-                code = d8_exact(raw_at(i - 1, cx), n, nd);
-              }
-              packed |= code << (8 * j);
-            }
-            uint8_t* orow = p.out + (int64_t)y * p.ld_out + xl;
-            if (xl + 3 < p.W) {
-              *reinterpret_cast<uint32_t*>(orow) = packed;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (xl + j < p.W) orow[j] = (uint8_t)(packed >> (8 * j));
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) nS[j] = vS[j];
-#pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            nSE[j] = pSE[j];
-            nSW[j] = pSW[j];
+        for (int j = 0; j < 4; ++j) {
+          bool special;
+          const uint32_t code = d8_fast(/*E*/ hE[j + 1], /*NE*/ -b.uSW[j + 1], /*N*/ -b.uS[j], /*NW*/ -b.uSE[j],
+                                        /*W*/ -hE[j], /*SW*/ c.uSW[j], /*S*/ c.uS[j], /*SE*/ c.uSE[j + 1], special);
+          packed |= code << (8 * j);
+          any_special |= special;
+          special_mask |= special ? (1u << j) : 0u;
+        }
+        if (any_special) {
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            if (!((special_mask >> j) & 1)) continue;
+            const int cx = xl + j;
+            float n[8];
+            n[0] = raw_at(i - 1, cx + 1);
+            n[1] = raw_at(i - 2, cx + 1);
+            n[2] = raw_at(i - 2, cx);
+            n[3] = raw_at(i - 2, cx - 1);
+            n[4] = raw_at(i - 1, cx - 1);
+            n[5] = raw_at(i, cx - 1);
+            n[6] = raw_at(i, cx);
+            n[7] = raw_at(i, cx + 1);
+            const uint32_t code = d8_exact(raw_at(i - 1, cx), n, nd);
+            packed = (packed & ~(0xFFu << (8 * j))) | (code << (8 * j));
           }
         }
+        uint8_t* orow = p.out + (int64_t)(y0 + i - 2) * p.ld_out + xl;
+        if (xl + 3 < p.W) {
+          *reinterpret_cast<uint32_t*>(orow) = packed;
+        } else {
 #pragma unroll
-        for (int j = 0; j < 6; ++j) b[j] = c[j];
+          for (int j = 0; j < 4; ++j)
+            if (xl + j < p.W) orow[j] = (uint8_t)(packed >> (8 * j));
+        }
       }
-      __syncwarp();
-      // box k-1 is no longer needed by the exact path: its stage takes box k+STAGES-1
-      if (lane == 0 && (k + DIR_STAGES - 1) < nblk) {
-        const int kn = k + DIR_STAGES - 1;
-        const uint32_t sn = (g0 + kn) % DIR_STAGES;
-        mbar_arrive_expect_tx(&bars[sn], DIR_STAGE_BYTES);
-        tma_load_2d(tiles + sn * DIR_STAGE_FLOATS, &tm, x0 - 4, iy0 + kn * DIR_RB, &bars[sn]);
-      }
+      end_of_row(i);
+    };
+
+    DirRow A, B;
+    load_row(0, A);
+    end_of_row(0);
+    int i = 1;
+#pragma unroll 1
+    for (; i + 1 < n_in; i += 2) {  // two rows per trip: the row structs swap roles without register moves
+      step(i, A, B);
+      step(i + 1, B, A);
     }
+    if (i < n_in) step(i, A, B);
     g0 += nblk;
     __syncwarp();
   }
@@ -332,7 +355,7 @@ int launch_direction(const float* dem, int64_t in_rows, int64_t cols, int64_t ld
   // rows per work item: long enough to amortise the 2-row prologue, short enough to balance the grid
   const int sms = sm_count();
   int chunk_rows = 512;
-  while (chunk_rows > 32 && (int64_t)p.n_bands * ((rows + chunk_rows - 1) / chunk_rows) < (int64_t)sms * 3 * DIR_WARPS * 4)
+  while (chunk_rows > 32 && (int64_t)p.n_bands * ((rows + chunk_rows - 1) / chunk_rows) < (int64_t)sms * OFL_DIR_CTAS_PER_SM * DIR_WARPS * 4)
     chunk_rows >>= 1;
   p.chunk_rows = chunk_rows;
   p.n_chunks = (int)((rows + chunk_rows - 1) / chunk_rows);
@@ -345,7 +368,7 @@ int launch_direction(const float* dem, int64_t in_rows, int64_t cols, int64_t ld
     attr_set = true;
   }
   int ctas = (int)((n_items + DIR_WARPS - 1) / DIR_WARPS);
-  const int max_ctas = sms * 3;
+  const int max_ctas = sms * OFL_DIR_CTAS_PER_SM;
   if (ctas > max_ctas) ctas = max_ctas;
   {
     PhaseScope ps(PHASE_DIRECTION, st);
