@@ -81,8 +81,16 @@ def check(status):
         raise OverflowB200Error(status, msg.decode("utf-8", "replace") if msg else "unknown error")
 
 
+_current_device = None
+
+
 def init(device=0):
-    check(lib().ofl_init(int(device)))
+    """Select the CUDA device for subsequent calls (cheap when it is already selected)."""
+    global _current_device
+    device = int(device)
+    if _current_device != device:
+        check(lib().ofl_init(device))
+        _current_device = device
 
 
 def launch_count():

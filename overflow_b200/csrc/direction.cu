@@ -49,7 +49,7 @@ namespace ofl {
 #define OFL_DIR_WARPS 4
 #endif
 #ifndef OFL_DIR_CTAS_PER_SM
-#define OFL_DIR_CTAS_PER_SM 5
+#define OFL_DIR_CTAS_PER_SM 3
 #endif
 constexpr int DIR_RB = OFL_DIR_RB;          // rows per TMA box / pipeline stage
 constexpr int DIR_STAGES = OFL_DIR_STAGES;  // stages per warp
@@ -75,7 +75,6 @@ struct DirParams {
 // The reference algorithm, literally, on one 3x3 window (flow_direction.py:49-67, :91-96).
 // n[] is in scan order E,NE,N,NW,W,SW,S,SE.
 __device__ __noinline__ uint32_t d8_exact(float z, const float* n, float nd) {
-  if (z == nd) return OFL_DIR_NODATA;
   float d[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) d[i] = (n[i] == nd) ? INFINITY : __fsub_rn(z, n[i]);
@@ -98,23 +97,43 @@ __device__ __noinline__ uint32_t d8_exact(float z, const float* n, float nd) {
   return any_pos ? (uint32_t)bi : (uint32_t)OFL_DIR_UNDEFINED;
 }
 
-// Fast path for one cell.  Differences are (centre - neighbour) in float32.
-// Returns the code; sets `special` when the exact path must decide instead.
-__device__ __forceinline__ uint32_t d8_fast(float dE, float dNE, float dN, float dNW, float dW, float dSW,
-                                            float dS, float dSE, bool& special) {
+// 1.0f / 0.0f comparison results (SASS FSET.BF): they feed FMA-pipe arithmetic, which keeps the
+// index selection off the half-rate ALU pipe that the compares and max operations already saturate.
+__device__ __forceinline__ float f_ne(float a, float b) {  // a != b or unordered
+  float r;
+  asm("set.neu.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float f_gt(float a, float b) {
+  float r;
+  asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float f_leu(float a, float b) {  // !(a > b): a <= b or unordered
+  float r;
+  asm("set.leu.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+
+// Fast path for one cell.  Differences are (centre - neighbour) in float32.  Returns the code as a small
+// float (0..8); `special` accumulates a non-zero value when the exact path must decide instead.
+__device__ __forceinline__ float d8_fast(float dE, float dNE, float dN, float dNW, float dW, float dSW, float dS,
+                                         float dSE, float& special) {
   // fmaxf ignores NaN operands, like the reference's `slope > max_slope` scan
   const float c = fmaxf(fmaxf(dE, dN), fmaxf(dW, dS));
   const float d = fmaxf(fmaxf(dNE, dNW), fmaxf(dSW, dSE));
-  const int ic = (dE == c) ? 0 : (dN == c) ? 2 : (dW == c) ? 4 : 6;
-  const int id = (dNE == d) ? 1 : (dNW == d) ? 3 : (dSW == d) ? 5 : 7;
+  // first index attaining the class maximum: E,N,W,S -> 0,2,4,6 and NE,NW,SW,SE -> 1,3,5,7
+  const float ic = f_ne(dE, c) * __fmaf_rn(f_ne(dN, c), __fmaf_rn(f_ne(dW, c), 2.f, 2.f), 2.f);
+  const float id = __fmaf_rn(f_ne(dNE, d), __fmaf_rn(f_ne(dNW, d), __fmaf_rn(f_ne(dSW, d), 2.f, 2.f), 2.f), 1.f);
   const float m = fmaxf(c, d);
-  const float u = __fmaf_rn(d, 0.70710678118654752f, -c);
-  const float thr = fabsf(d) * 4.76837158203125e-07f;  // 2^-21
-  const bool decided = fabsf(u) > thr;
-  const bool pos = m > 0.0f;
-  uint32_t code = (u > 0.0f) ? id : ic;
-  code = pos ? code : (uint32_t)OFL_DIR_UNDEFINED;
-  special = !(fabsf(m) < INFINITY) || (pos && !decided);
+  const float u = __fmaf_rn(d, 0.70710678118654752f, -c);               // > 0: the diagonal is steeper
+  const float thr = __fmul_rn(__fadd_rn(fabsf(c), fabsf(d)), 4.76837158203125e-07f);  // guard band, >= 2^-21 |d|
+  const float pos = f_gt(m, 0.f);
+  float code = __fmaf_rn(f_gt(u, 0.f), __fsub_rn(id, ic), ic);
+  code = __fmaf_rn(pos, __fsub_rn(code, 8.f), 8.f);
+  // exact path: sign of u not certain (includes every inf / NaN case with a positive maximum), or the
+  // maximum is -inf / NaN (non-finite or NODATA centre)
+  special = __fadd_rn(special, __fmaf_rn(pos, f_leu(fabsf(u), thr), f_leu(m, -INFINITY)));
   return code;
 }
 
@@ -127,170 +146,197 @@ struct DirRow {
   float uSW[5];   // above[j+1] - v[j]     (cell j of the row above -> its SW neighbour)
 };
 
-__global__ void __launch_bounds__(DIR_WARPS * 32) direction_kernel(const __grid_constant__ CUtensorMap tm,
+struct DirWarp {
+  float* tiles;     // this warp's ring of stages
+  uint64_t* bars;   // one mbarrier per stage
+  uint32_t g0;      // boxes consumed so far: stage = g % STAGES, parity = (g / STAGES) & 1
+  int lane;
+};
+
+// One (band, chunk) work item of one warp.  EDGE: the band touches the raster's left or right edge, so
+// columns outside the raster must be patched; interior bands skip those checks entirely.
+template <bool EDGE>
+__device__ __forceinline__ void direction_item(const CUtensorMap* tm, const DirParams& p, DirWarp& wp, int x0, int y0,
+                                               int y1) {
+  static_assert(DIR_RB % 2 == 0, "rows alternate between two register sets per box");
+  const int lane = wp.lane;
+  const float nd = p.nd;
+  const int iy0 = y0 + p.y_off - 1;  // first input row this item reads
+  const int n_in = (y1 - y0) + 2;
+  const int nblk = (n_in + DIR_RB - 1) / DIR_RB;
+  const int xl = x0 + 4 * lane;  // first of this lane's 4 columns
+  float* const tiles = wp.tiles;
+  uint64_t* const bars = wp.bars;
+  const uint32_t g0 = wp.g0;
+
+  auto issue = [&](int k) {
+    const uint32_t s = (g0 + k) % DIR_STAGES;
+    mbar_arrive_expect_tx(&bars[s], DIR_STAGE_BYTES);
+    tma_load_2d(tiles + s * DIR_STAGE_FLOATS, tm, x0 - 4, iy0 + k * DIR_RB, &bars[s]);
+  };
+  // A box may be refilled only after the NEXT box has been consumed (the exact path re-reads up to two
+  // rows back), so STAGES-1 boxes are in flight.
+  if (lane == 0) {
+    const int pre = min(DIR_STAGES - 1, nblk);
+    for (int k = 0; k < pre; ++k) issue(k);
+  }
+
+  // raw window read for the exact path: rel = row relative to iy0, cx = absolute column
+  auto raw_at = [&](int rel, int cx) -> float {
+    const int iy = iy0 + rel;
+    if (iy < 0 || iy >= p.in_rows || cx < 0 || cx >= p.W) return p.fill_raw;
+    const uint32_t s = (g0 + rel / DIR_RB) % DIR_STAGES;
+    return tiles[s * DIR_STAGE_FLOATS + (rel % DIR_RB) * DIR_BOXW + (cx - x0 + 4)];
+  };
+
+  // row rr of the box at `t` into r.v; GUARD adds the out-of-array row check (first / last box only)
+  auto load_row = [&](const float* t, int rr, int i, DirRow& r, bool guard) {
+    const float* q = t + rr * DIR_BOXW;
+    const float4 m = *reinterpret_cast<const float4*>(q + 4);
+    r.v[0] = q[3];
+    r.v[1] = m.x;
+    r.v[2] = m.y;
+    r.v[3] = m.z;
+    r.v[4] = m.w;
+    r.v[5] = q[8];
+    if (guard && (iy0 + i < 0 || iy0 + i >= p.in_rows)) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) r.v[j] = p.fillv;
+    } else if (EDGE) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int cx = xl - 1 + j;
+        if (cx < 0 || cx >= p.W) r.v[j] = p.fillv;
+      }
+    }
+    bool any_nd = false;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) any_nd |= (r.v[j] == nd);
+    if (any_nd) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) r.v[j] = (r.v[j] == nd) ? -INFINITY : r.v[j];
+    }
+  };
+
+  uint8_t* orow = p.out + (int64_t)y0 * p.ld_out + xl;  // next output row of this lane
+  const bool full_store = xl + 3 < p.W;
+
+  // differences between row b (above) and the new row c; emits b's codes when b is an output row
+  auto diffs_and_emit = [&](int i, const DirRow& b, DirRow& c, bool emit) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c.uS[j] = __fsub_rn(b.v[j + 1], c.v[j + 1]);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) c.uSE[j] = __fsub_rn(b.v[j], c.v[j + 1]);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) c.uSW[j] = __fsub_rn(b.v[j + 1], c.v[j]);
+    if (!emit) return;
+    float hE[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) hE[j] = __fsub_rn(b.v[j], b.v[j + 1]);  // cell j-1 -> E
+    float special = 0.f, code[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      code[j] = d8_fast(/*E*/ hE[j + 1], /*NE*/ -b.uSW[j + 1], /*N*/ -b.uS[j], /*NW*/ -b.uSE[j], /*W*/ -hE[j],
+                        /*SW*/ c.uSW[j], /*S*/ c.uS[j], /*SE*/ c.uSE[j + 1], special);
+    // codes are 0..8: pack pairs exactly in float, then take the low 16 bits of (value + 2^23)
+    const uint32_t lo = __float_as_uint(__fadd_rn(__fmaf_rn(code[1], 256.f, code[0]), 8388608.f));
+    const uint32_t hi = __float_as_uint(__fadd_rn(__fmaf_rn(code[3], 256.f, code[2]), 8388608.f));
+    uint32_t packed = __byte_perm(lo, hi, 0x5410);
+    if (special != 0.f) {
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        const int cx = xl + j;
+        const float z = raw_at(i - 1, cx);
+        uint32_t ex;
+        if (z == nd) {
+          ex = OFL_DIR_NODATA;
+        } else {
+          float n[8];
+          n[0] = raw_at(i - 1, cx + 1);
+          n[1] = raw_at(i - 2, cx + 1);
+          n[2] = raw_at(i - 2, cx);
+          n[3] = raw_at(i - 2, cx - 1);
+          n[4] = raw_at(i - 1, cx - 1);
+          n[5] = raw_at(i, cx - 1);
+          n[6] = raw_at(i, cx);
+          n[7] = raw_at(i, cx + 1);
+          ex = d8_exact(z, n, nd);
+        }
+        packed = (packed & ~(0xFFu << (8 * j))) | (ex << (8 * j));
+      }
+    }
+    if (!EDGE || full_store) {
+      *reinterpret_cast<uint32_t*>(orow) = packed;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (xl + j < p.W) orow[j] = (uint8_t)(packed >> (8 * j));
+    }
+    orow += p.ld_out;
+  };
+
+  DirRow X[2];  // row i lives in X[i & 1]; indices are compile-time inside the unrolled box loop
+#pragma unroll 1
+  for (int k = 0; k < nblk; ++k) {
+    const uint32_t s = (g0 + k) % DIR_STAGES;
+    mbar_wait(&bars[s], ((g0 + k) / DIR_STAGES) & 1);
+    const float* t = tiles + s * DIR_STAGE_FLOATS + 4 * lane;
+    const int ib = k * DIR_RB;
+    if (k > 0 && ib + DIR_RB <= n_in - 1) {
+      // interior box: every row is inside the array and has a row above it that is an output row
+#pragma unroll
+      for (int rr = 0; rr < DIR_RB; ++rr) {
+        load_row(t, rr, ib + rr, X[rr & 1], false);
+        diffs_and_emit(ib + rr, X[(rr + 1) & 1], X[rr & 1], true);
+      }
+    } else {
+#pragma unroll
+      for (int rr = 0; rr < DIR_RB; ++rr) {
+        const int i = ib + rr;
+        if (i < n_in) {
+          load_row(t, rr, i, X[rr & 1], true);
+          if (i >= 1) diffs_and_emit(i, X[(rr + 1) & 1], X[rr & 1], i >= 2);
+        }
+      }
+    }
+    __syncwarp();
+    // box k-1 is no longer needed by the exact path: its stage takes box k+STAGES-1
+    if (lane == 0 && (k + DIR_STAGES - 1) < nblk) issue(k + DIR_STAGES - 1);
+  }
+  wp.g0 = g0 + nblk;
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(DIR_WARPS * 32, 3) direction_kernel(const __grid_constant__ CUtensorMap tm,
                                                                     const DirParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* tiles = reinterpret_cast<float*>(smem_raw) + warp * (DIR_STAGES * DIR_STAGE_FLOATS);
-  uint64_t* bars =
-      reinterpret_cast<uint64_t*>(smem_raw + size_t(DIR_WARPS) * DIR_STAGES * DIR_STAGE_BYTES) + warp * DIR_STAGES;
-  if (lane == 0) {
+  const int warp = threadIdx.x >> 5;
+  DirWarp wp;
+  wp.lane = threadIdx.x & 31;
+  wp.tiles = reinterpret_cast<float*>(smem_raw) + warp * (DIR_STAGES * DIR_STAGE_FLOATS);
+  wp.bars = reinterpret_cast<uint64_t*>(smem_raw + size_t(DIR_WARPS) * DIR_STAGES * DIR_STAGE_BYTES) + warp * DIR_STAGES;
+  wp.g0 = 0;
+  if (wp.lane == 0) {
     tma_prefetch_desc(&tm);
 #pragma unroll
-    for (int s = 0; s < DIR_STAGES; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < DIR_STAGES; ++s) mbar_init(&wp.bars[s], 1);
     mbar_fence_init();
   }
   __syncwarp();
 
-  const float nd = p.nd;
-  const float NINF = -INFINITY;
   const int gwarp = blockIdx.x * DIR_WARPS + warp;
   const int nwarps = gridDim.x * DIR_WARPS;
   const int n_items = p.n_bands * p.n_chunks;
-  uint32_t g0 = 0;  // boxes this warp has consumed so far (stage = g % STAGES, parity = (g / STAGES) & 1)
-
   for (int item = gwarp; item < n_items; item += nwarps) {
     const int chunk = item / p.n_bands;
     const int band = item - chunk * p.n_bands;
     const int x0 = band * DIR_BAND;
     const int y0 = chunk * p.chunk_rows;
     const int y1 = min(y0 + p.chunk_rows, p.H);
-    const int iy0 = y0 + p.y_off - 1;  // first input row this item reads
-    const int n_in = (y1 - y0) + 2;
-    const int nblk = (n_in + DIR_RB - 1) / DIR_RB;
-    const int xl = x0 + 4 * lane;  // first of this lane's 4 columns
-    const bool edge_band = (x0 == 0) || (x0 + DIR_BAND + 1 > p.W);
-
-    // A box may be refilled only after the NEXT box has been consumed (the exact path re-reads up to
-    // two rows back), so STAGES-1 boxes are in flight.
-    if (lane == 0) {
-      const int pre = min(DIR_STAGES - 1, nblk);
-      for (int k = 0; k < pre; ++k) {
-        const uint32_t s = (g0 + k) % DIR_STAGES;
-        mbar_arrive_expect_tx(&bars[s], DIR_STAGE_BYTES);
-        tma_load_2d(tiles + s * DIR_STAGE_FLOATS, &tm, x0 - 4, iy0 + k * DIR_RB, &bars[s]);
-      }
-    }
-
-    // raw window read for the exact path: rel = row relative to iy0, cx = absolute column
-    auto raw_at = [&](int rel, int cx) -> float {
-      const int iy = iy0 + rel;
-      if (iy < 0 || iy >= p.in_rows || cx < 0 || cx >= p.W) return p.fill_raw;
-      const uint32_t s = (g0 + rel / DIR_RB) % DIR_STAGES;
-      return tiles[s * DIR_STAGE_FLOATS + (rel % DIR_RB) * DIR_BOXW + (cx - x0 + 4)];
-    };
-
-    // load input row i (relative) into r.v: patch cells outside the array, nodata -> -inf
-    auto load_row = [&](int i, DirRow& r) {
-      const int k = i / DIR_RB, rr = i - k * DIR_RB;
-      const uint32_t s = (g0 + k) % DIR_STAGES;
-      if (rr == 0) mbar_wait(&bars[s], ((g0 + k) / DIR_STAGES) & 1);
-      const float* t = tiles + s * DIR_STAGE_FLOATS + rr * DIR_BOXW + 4 * lane;
-      const float4 q = *reinterpret_cast<const float4*>(t + 4);
-      r.v[0] = t[3];
-      r.v[1] = q.x;
-      r.v[2] = q.y;
-      r.v[3] = q.z;
-      r.v[4] = q.w;
-      r.v[5] = t[8];
-      const int iy = iy0 + i;
-      if (iy < 0 || iy >= p.in_rows) {
-#pragma unroll
-        for (int j = 0; j < 6; ++j) r.v[j] = p.fillv;
-      } else if (edge_band) {
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          const int cx = xl - 1 + j;
-          if (cx < 0 || cx >= p.W) r.v[j] = p.fillv;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 6; ++j) r.v[j] = (r.v[j] == nd) ? NINF : r.v[j];
-    };
-
-    // after the last row of box k has been consumed, box k-1 is no longer needed by the exact path:
-    // its stage takes box k+STAGES-1
-    auto end_of_row = [&](int i) {
-      const int k = i / DIR_RB;
-      if (i - k * DIR_RB == DIR_RB - 1 || i == n_in - 1) {
-        __syncwarp();
-        if (lane == 0 && (k + DIR_STAGES - 1) < nblk) {
-          const int kn = k + DIR_STAGES - 1;
-          const uint32_t sn = (g0 + kn) % DIR_STAGES;
-          mbar_arrive_expect_tx(&bars[sn], DIR_STAGE_BYTES);
-          tma_load_2d(tiles + sn * DIR_STAGE_FLOATS, &tm, x0 - 4, iy0 + kn * DIR_RB, &bars[sn]);
-        }
-      }
-    };
-
-    // input row i arrives in `c`; `b` is the row above it.  Forms the differences between the two rows
-    // and, when b is an output row (i >= 2), emits b's codes.
-    auto step = [&](int i, const DirRow& b, DirRow& c) {
-      load_row(i, c);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) c.uS[j] = __fsub_rn(b.v[j + 1], c.v[j + 1]);
-#pragma unroll
-      for (int j = 0; j < 5; ++j) c.uSE[j] = __fsub_rn(b.v[j], c.v[j + 1]);
-#pragma unroll
-      for (int j = 0; j < 5; ++j) c.uSW[j] = __fsub_rn(b.v[j + 1], c.v[j]);
-      if (i >= 2) {
-        float hE[5];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) hE[j] = __fsub_rn(b.v[j], b.v[j + 1]);  // cell j-1 -> E
-        uint32_t packed = 0;
-        bool any_special = false;
-        uint32_t special_mask = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          bool special;
-          const uint32_t code = d8_fast(/*E*/ hE[j + 1], /*NE*/ -b.uSW[j + 1], /*N*/ -b.uS[j], /*NW*/ -b.uSE[j],
-                                        /*W*/ -hE[j], /*SW*/ c.uSW[j], /*S*/ c.uS[j], /*SE*/ c.uSE[j + 1], special);
-          packed |= code << (8 * j);
-          any_special |= special;
-          special_mask |= special ? (1u << j) : 0u;
-        }
-        if (any_special) {
-#pragma unroll 1
-          for (int j = 0; j < 4; ++j) {
-            if (!((special_mask >> j) & 1)) continue;
-            const int cx = xl + j;
-            float n[8];
-            n[0] = raw_at(i - 1, cx + 1);
-            n[1] = raw_at(i - 2, cx + 1);
-            n[2] = raw_at(i - 2, cx);
-            n[3] = raw_at(i - 2, cx - 1);
-            n[4] = raw_at(i - 1, cx - 1);
-            n[5] = raw_at(i, cx - 1);
-            n[6] = raw_at(i, cx);
-            n[7] = raw_at(i, cx + 1);
-            const uint32_t code = d8_exact(raw_at(i - 1, cx), n, nd);
-            packed = (packed & ~(0xFFu << (8 * j))) | (code << (8 * j));
-          }
-        }
-        uint8_t* orow = p.out + (int64_t)(y0 + i - 2) * p.ld_out + xl;
-        if (xl + 3 < p.W) {
-          *reinterpret_cast<uint32_t*>(orow) = packed;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (xl + j < p.W) orow[j] = (uint8_t)(packed >> (8 * j));
-        }
-      }
-      end_of_row(i);
-    };
-
-    DirRow A, B;
-    load_row(0, A);
-    end_of_row(0);
-    int i = 1;
-#pragma unroll 1
-    for (; i + 1 < n_in; i += 2) {  // two rows per trip: the row structs swap roles without register moves
-      step(i, A, B);
-      step(i + 1, B, A);
-    }
-    if (i < n_in) step(i, A, B);
-    g0 += nblk;
-    __syncwarp();
+    if ((x0 == 0) || (x0 + DIR_BAND + 1 > p.W))
+      direction_item<true>(&tm, p, wp, x0, y0, y1);
+    else
+      direction_item<false>(&tm, p, wp, x0, y0, y1);
   }
 }
 

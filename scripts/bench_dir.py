@@ -11,9 +11,10 @@ for _ in range(3): dev.flow_direction(dem, -9999.0, out=out)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-for _ in range(10): dev.flow_direction(dem, -9999.0, out=out)
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+for _ in range(N): dev.flow_direction(dem, -9999.0, out=out)
 e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / 10
+ms = e0.elapsed_time(e1) / N
 ok = True
 for r, c in ((1, 1), (S // 2, S // 3), (S - 402, S - 402)):
     win = dem[r - 1:r + 401, c - 1:c + 401].cpu().numpy()
