@@ -9,7 +9,7 @@
 // sweep is organised the way the cited paper organises its tiles, with a CTA's shared memory
 // as the "tile":
 //
-//   pass A  (acc_tile_kernel<false>)  one CTA per 64x64 tile: TMA-load the codes plus a
+//   pass A  (acc_tile_kernel)  one CTA per 64x64 tile: TMA-load the codes plus a
 //           one-cell halo, accumulate every flow path that stays inside the tile (frontier
 //           propagation in shared memory: missing-upstream counts, one shared atomic per edge,
 //           warp-ballot compacted frontier queues), follow each perimeter cell
@@ -19,12 +19,13 @@
 //   solve   (pj_round_kernel)         the reduced graph is a forest over ~6% of the cells;
 //           subtree sums over it by pointer doubling: O(log depth) rounds of
 //           "add my sum to my 2^j-th ancestor, then jump", integer atomics, exact.
-//   pass B  (acc_tile_kernel<true>)   re-run the tile relaxation seeded with each perimeter
-//           cell's inflow from outside the tile and write the final int64 counts.
+//   final   (acc_final_kernel)        per tile: tile-local counts (stored by pass A, 2 B/cell) plus
+//           every perimeter cell's inflow from outside the tile added along its in-tile path;
+//           writes the final int64 counts.
 //
-// HBM traffic per cell: 1 B (codes) in pass A, 1 B + 8 B in pass B, plus ~1.5 B of reduced
-// graph -- against 9 B/cell compulsory.  Long drainage chains cost O(log) rounds on the
-// reduced graph instead of O(length) sweeps.
+// HBM traffic per cell: 1 B (codes) + 2 B (local counts) in pass A, 1 + 2 + 8 B in the final pass,
+// plus ~2 B of reduced graph -- against 9 B/cell compulsory.  Long drainage chains cost O(log)
+// rounds on the reduced graph instead of O(length) sweeps.
 //
 // Edge rule (flow_accumulation.py:116-124): u -> c is an edge iff code(u) in 0..7, c lies
 // inside the raster and code(c) != 9.  Codes >= 8 have no downstream cell (the reference's
@@ -122,8 +123,7 @@ __device__ __forceinline__ int node_of_cell(int gy, int gx, const AccParams& p) 
 //   * frontier levels are consecutive segments of one 4096-entry queue (a cell is appended once);
 //     a level never grows, so once it fits one cell per thread each thread simply follows its chain
 //     (it continues exactly when its hand-off completed the next cell): no queue, no barriers.
-// Pass B carries 64-bit counts as (hi32 << 24) + lo24: the low 24 bits ride in the packed word (nine
-// 24-bit terms fit the 28-bit field), the high part goes through a second atomic only when non-zero.
+// Tile-local counts are at most 4096, so the 28-bit count field never overflows.
 // Shared memory is addressed through explicit 32-bit shared-space addresses (ld/st/atom.shared):
 // the hot loop is ~40 instructions per 32 cells.
 constexpr int WP = 68;                 // word-array pitch: cells x = -1..64 in columns 0..65
@@ -134,12 +134,10 @@ constexpr int QMAX = AT * AT;
 #endif
 constexpr int WALK_PER_THREAD = OFL_WALK_PER_THREAD;  // switch to chain walking once a level has <= this many cells per thread
 
-template <bool FINAL>
 struct TileSmem {
   static constexpr int CS = 0;
   static constexpr int WORD = 6400;  // ACS_BYTES rounded up to 128
-  static constexpr int HI = WORD + WORDS * 4;
-  static constexpr int Q = HI + (FINAL ? WORDS * 4 : 0);
+  static constexpr int Q = WORD + WORDS * 4;
   static constexpr int TAB = Q + QMAX * 2;  // int2 per direction code: {word-array byte offset, cell-id offset}
   static constexpr int TAB2 = TAB + 64;  // int2 per direction code: {code-array byte offset, cell-id offset}
   static constexpr int TAIL = TAB2 + 64;
@@ -194,15 +192,13 @@ __device__ __forceinline__ uint32_t bytes_differ(uint32_t nb, uint32_t pat) {
   return (((nb ^ pat) + 0x7F7F7F7Fu) >> 7) & 0x01010101u;
 }
 
-template <bool FINAL>
 __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_constant__ CUtensorMap tm,
                                                                 const AccParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  using SM = TileSmem<FINAL>;
+  using SM = TileSmem;
   const uint32_t sb = smem_u32(smem_raw);
   const uint32_t a_cs = sb + SM::CS;      // codes + halo (TMA destination), pitch ACS_W bytes
   const uint32_t a_word = sb + SM::WORD;  // [missing:4 | count:28], halo-padded, pitch WP words
-  const uint32_t a_hi = sb + SM::HI;      // pass B: count >> 24, same layout
   const uint32_t a_q = sb + SM::Q;        // frontier queue of cell ids (y*64+x), u16
   const uint32_t a_tab = sb + SM::TAB;
   const uint32_t a_tail = sb + SM::TAIL;
@@ -229,7 +225,7 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
   }
   {
     uint4* z = reinterpret_cast<uint4*>(smem_raw + SM::WORD);
-    constexpr int NZ = (FINAL ? 2 : 1) * WORDS / 4;  // word[] and hi[] are adjacent
+    constexpr int NZ = WORDS / 4;
     for (int i = tid; i < NZ; i += ACC_THREADS) z[i] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
@@ -346,47 +342,20 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     }
   }
   __syncthreads();
-  if (FINAL) {
-    // seeds: inflow from outside the tile into each perimeter cell (from the reduced-graph solve)
-    int y, x;
-    if (cell_of_slot(tid, h, w, y, x)) {
-      const unsigned long long seed = p.S[(size_t)tile * SLOTS + tid];
-      if (seed) {
-        const uint32_t o = ((y + 1) * WP + x + 1) * 4;
-        sts32(a_word + o, lds32(a_word + o) + (uint32_t)(seed & 0xFFFFFFu));
-        sts32(a_hi + o, (uint32_t)(seed >> 24));
-      }
-    }
-    __syncthreads();
-  }
-
   // finish cell `idx` and hand its count downstream; returns true (and the downstream cell id in
   // `nidx`) when that hand-off was the last one the downstream cell was waiting for
   const uint32_t a_word0 = a_word + (WP + 1) * 4;         // word of cell (0,0)
-  const uint32_t a_hi0 = a_hi + (WP + 1) * 4;
   const uint32_t a_cs0 = a_cs + ACS_W * ACS_Y0 + ACS_X0;  // code of cell (0,0)
   auto finish = [&](uint32_t idx, uint32_t& nidx) -> bool {
     const uint32_t yy = idx >> AT_SHIFT;
     const uint32_t ow = idx * 4 + yy * 16;  // ((y+1)*WP + x+1)*4 relative to cell (0,0)
     const uint32_t code = lds8(a_cs0 + idx + (ACS_W - AT) * yy);
     const uint32_t s = lds32(a_word0 + ow) & 0x0FFFFFFFu;
-    uint32_t lo, hn = 0;
-    if (FINAL) {
-      const unsigned long long v = ((unsigned long long)lds32(a_hi0 + ow) << 24) + s + 1;
-      lo = (uint32_t)v & 0xFFFFFFu;
-      hn = (uint32_t)(v >> 24);
-      sts32(a_hi0 + ow, hn);
-    } else {
-      lo = s + 1;
-    }
+    const uint32_t lo = s + 1;
     sts32(a_word0 + ow, lo);
     if (code >= 8) return false;
     const uint2 t = lds64(a_tab + 8 * code);
     nidx = idx + t.y;
-    if (FINAL && hn) {
-      atoms_add(a_hi0 + ow + t.x, hn);
-      __threadfence_block();  // the high part must be in place before the count can reach zero
-    }
     const uint32_t old = atoms_add(a_word0 + ow + t.x, lo - (1u << 28));
     return (old >> 28) == 1;
   };
@@ -421,7 +390,7 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
   }
   __syncthreads();
 
-  if (!FINAL) {
+  {
     // ---- Alg. 2: follow every perimeter cell to where its path leaves the tile; emit the reduced graph
     const int s = tid;  // SLOTS == ACC_THREADS
     int y, x;
@@ -491,27 +460,6 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
       if (missing >> 28) atomicExch(p.err, 1);  // a cell never completed: the raster holds a cycle
       Lt[g] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
     }
-  } else {
-    // ---- final counts: lane-contiguous int64 stores (256 B per half row); NODATA cells get -9998
-    bool stuck = false;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int x = lane + 32 * half;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int y = 8 * warp + k;
-        if (y < h && x < w) {
-          const uint32_t o = (y * WP + x) * 4;
-          const uint32_t own = lds8(a_cs0 + y * ACS_W + x);
-          const uint32_t wv = lds32(a_word0 + o);
-          long long v = (long long)(((unsigned long long)lds32(a_hi0 + o) << 24) | (wv & 0xFFFFFFu));
-          if (own == OFL_DIR_NODATA) v = OFL_FAC_NODATA_EMITTED;
-          else stuck |= (wv >> 28) != 0;
-          p.fac[(int64_t)(y0 + y) * p.ld_fac + (x0 + x)] = v;
-        }
-      }
-    }
-    if (stuck) atomicExch(p.err, 1);  // a missing-count never reached zero: cycle
   }
 }
 
@@ -830,8 +778,8 @@ constexpr int PJ_MAX_ROUNDS = 40;
 static int ensure_tile_attrs() {
   static bool attr_set = false;
   if (!attr_set) {
-    OFL_CUDA(cudaFuncSetAttribute(acc_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  TileSmem<false>::BYTES));
+    OFL_CUDA(cudaFuncSetAttribute(acc_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TileSmem::BYTES));
     OFL_CUDA(cudaFuncSetAttribute(acc_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FinalSmem::BYTES));
     attr_set = true;
   }
@@ -1015,7 +963,7 @@ int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t 
   OFL_CUDA(cudaMemsetAsync(C.p.err, 0, 64, st));
   {
     PhaseScope ps(PHASE_ACC_TILE_A, st);
-    acc_tile_kernel<false><<<(unsigned)C.ntiles, ACC_THREADS, TileSmem<false>::BYTES, st>>>(C.tm, C.p);
+    acc_tile_kernel<<<(unsigned)C.ntiles, ACC_THREADS, TileSmem::BYTES, st>>>(C.tm, C.p);
   }
   OFL_CHECK_LAUNCH();
   {
@@ -1153,7 +1101,7 @@ int strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
   OFL_CUDA(cudaMemsetAsync(C.p.err, 0, 64, st));
   {
     PhaseScope ps(PHASE_ACC_TILE_A, st);
-    acc_tile_kernel<false><<<(unsigned)C.ntiles, ACC_THREADS, TileSmem<false>::BYTES, st>>>(C.tm, C.p);
+    acc_tile_kernel<<<(unsigned)C.ntiles, ACC_THREADS, TileSmem::BYTES, st>>>(C.tm, C.p);
   }
   OFL_CHECK_LAUNCH();
   {
