@@ -140,7 +140,8 @@ struct TileSmem {
   static constexpr int Q = WORD + WORDS * 4;
   static constexpr int TAB = Q + QMAX * 2;  // int2 per direction code: {word-array byte offset, cell-id offset}
   static constexpr int TAB2 = TAB + 64;  // int2 per direction code: {code-array byte offset, cell-id offset}
-  static constexpr int TAIL = TAB2 + 64;
+  static constexpr int TAB3 = TAB2 + 64;  // int2 per direction code: {word-array byte offset, code-array byte offset}
+  static constexpr int TAIL = TAB3 + 64;
   static constexpr int BAR = TAIL + 16;
   static constexpr int BYTES = BAR + 16;
 };
@@ -222,6 +223,8 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     sts32(a_tab + 8 * tid + 4, (uint32_t)(dir_dy(tid) * AT + dir_dx(tid)));
     sts32(sb + SM::TAB2 + 8 * tid, (uint32_t)(dir_dy(tid) * ACS_W + dir_dx(tid)));
     sts32(sb + SM::TAB2 + 8 * tid + 4, (uint32_t)(dir_dy(tid) * AT + dir_dx(tid)));
+    sts32(sb + SM::TAB3 + 8 * tid, (uint32_t)((dir_dy(tid) * WP + dir_dx(tid)) * 4));
+    sts32(sb + SM::TAB3 + 8 * tid + 4, (uint32_t)(dir_dy(tid) * ACS_W + dir_dx(tid)));
   }
   {
     uint4* z = reinterpret_cast<uint4*>(smem_raw + SM::WORD);
@@ -383,10 +386,27 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     hi = nh;
   }
   // ---- narrow tail (a level never grows): one thread per frontier cell follows its chain for as
-  //      long as its hand-off is the one that completes the next cell; no queue, no barriers
+  //      long as its hand-off is the one that completes the next cell; no queue, no barriers.  The
+  //      atomic's return value already holds the next cell's running sum, so a step is one code load,
+  //      one table load, one store and one atomic.
   for (uint32_t i = lo + tid; i < hi; i += ACC_THREADS) {
-    uint32_t idx = lds16(a_q + 2 * i), nidx = 0;
-    while (finish(idx, nidx)) idx = nidx;
+    const uint32_t idx = lds16(a_q + 2 * i);
+    const uint32_t yy = idx >> AT_SHIFT;
+    uint32_t aw = a_word0 + idx * 4 + yy * 16;        // shared address of the cell's word
+    uint32_t ac = a_cs0 + idx + (ACS_W - AT) * yy;    // ... and of its code
+    uint32_t sum = lds32(aw) & 0x0FFFFFFFu;
+    for (;;) {
+      const uint32_t code = lds8(ac);
+      const uint32_t cnt = sum + 1;
+      sts32(aw, cnt);
+      if (code >= 8) break;
+      const uint2 t = lds64(sb + SM::TAB3 + 8 * code);  // {word byte offset, code byte offset}
+      aw += t.x;
+      ac += t.y;
+      const uint32_t old = atoms_add(aw, cnt - (1u << 28));
+      if ((old >> 28) != 1) break;
+      sum = (old & 0x0FFFFFFFu) + cnt;
+    }
   }
   __syncthreads();
 
