@@ -102,6 +102,7 @@ struct AccParams {
   // holding the neighbouring strips' rows; strip_above / strip_below say whether a strip exists there
   int y_off, strip_above, strip_below;
   int tile_base;  // first tile handled by this launch (blockIdx.x + tile_base)
+  int vec_store;  // fac rows are 16-byte aligned: the final pass may use 16-byte stores
 };
 
 __device__ __forceinline__ int node_of_cell(int gy, int gx, const AccParams& p) {
@@ -494,7 +495,7 @@ struct FinalSmem {
   static constexpr int CS = 0;
   static constexpr int LO = 6400;
   static constexpr int HI = LO + AT * AT * 4;
-  static constexpr int TAB = HI + AT * AT * 4;  // int4 per direction code: {code-array byte offset, dy, dx, 0}
+  static constexpr int TAB = HI + AT * AT * 4;  // int4 per direction code: {code-array byte offset, dy, dx, lo/hi byte offset}
   static constexpr int BAR = TAB + 128;
   static constexpr int BYTES = BAR + 16;
 };
@@ -520,7 +521,7 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_final_kernel(const __grid_con
   if (tid < 8) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_tab + 16 * tid),
                  "r"((uint32_t)(dir_dy(tid) * ACS_W + dir_dx(tid))), "r"((uint32_t)dir_dy(tid)), "r"((uint32_t)dir_dx(tid)),
-                 "r"(0u)
+                 "r"((uint32_t)((dir_dy(tid) * AT + dir_dx(tid)) * 4))
                  : "memory");
   }
   // tile-local counts -> low words; high words start at zero
@@ -547,9 +548,9 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_final_kernel(const __grid_con
 
   if (seed) {
     const uint32_t slo = (uint32_t)seed, shi = (uint32_t)(seed >> 32);
-    uint32_t ca = a_cs0 + y * ACS_W + x;
+    uint32_t ca = a_cs0 + y * ACS_W + x;     // shared address of the current cell's code
+    uint32_t o = (y * AT + x) * 4;           // byte offset of the current cell in lo[] / hi[]
     for (int steps = 0; steps <= AT * AT; ++steps) {
-      const uint32_t o = (y * AT + x) * 4;
       const uint32_t old = atoms_add(a_lo + o, slo);
       const uint32_t hadd = shi + ((old + slo) < old ? 1u : 0u);
       if (hadd) atoms_add(a_hi + o, hadd);
@@ -559,28 +560,37 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_final_kernel(const __grid_con
       asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3) : "r"(a_tab + 16 * code) : "memory");
       y += (int)t1;
       x += (int)t2;
-      if (y < 0 || y >= h || x < 0 || x >= w) break;  // leaves the tile (or the raster)
+      if ((uint32_t)y >= (uint32_t)h || (uint32_t)x >= (uint32_t)w) break;  // leaves the tile (or the raster)
       ca += t0;
+      o += t3;
       if (lds8(ca) == OFL_DIR_NODATA) break;  // no edge into a NODATA cell
-      (void)t3;
     }
   }
   __syncthreads();
 
-  // final counts: lane-contiguous int64 stores (256 B per half row); NODATA cells get -9998
+  // final counts: each lane writes two adjacent cells as one 16-byte store, a warp one 512-byte row per
+  // instruction; NODATA cells get -9998
+  const uint32_t xx = 2 * lane;
+  long long* orow = p.fac + (int64_t)(y0 + 8 * warp) * p.ld_fac + x0 + xx;
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int xx = lane + 32 * half;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int yy = 8 * warp + k;
-      if (yy < h && xx < w) {
-        const uint32_t o = (yy * AT + xx) * 4;
-        long long v = (long long)(((unsigned long long)lds32(a_hi + o) << 32) | lds32(a_lo + o));
-        if (lds8(a_cs0 + yy * ACS_W + xx) == OFL_DIR_NODATA) v = OFL_FAC_NODATA_EMITTED;
-        p.fac[(int64_t)(y0 + yy) * p.ld_fac + (x0 + xx)] = v;
+  for (int k = 0; k < 8; ++k) {
+    const int yy = 8 * warp + k;
+    if (yy < h && (int)xx < w) {
+      const uint32_t oo = (yy * AT + xx) * 4;
+      const uint2 lo2 = lds64(a_lo + oo), hi2 = lds64(a_hi + oo);
+      const uint32_t c2 = lds16(a_cs0 + yy * ACS_W + xx);
+      long long v0 = (long long)(((unsigned long long)hi2.x << 32) | lo2.x);
+      long long v1 = (long long)(((unsigned long long)hi2.y << 32) | lo2.y);
+      if ((c2 & 0xFF) == OFL_DIR_NODATA) v0 = OFL_FAC_NODATA_EMITTED;
+      if ((c2 >> 8) == OFL_DIR_NODATA) v1 = OFL_FAC_NODATA_EMITTED;
+      if ((int)xx + 1 < w && p.vec_store) {
+        *reinterpret_cast<longlong2*>(orow) = make_longlong2(v0, v1);
+      } else {
+        orow[0] = v0;
+        if ((int)xx + 1 < w) orow[1] = v1;
       }
     }
+    orow += p.ld_fac;
   }
 }
 
@@ -958,6 +968,7 @@ static int acc_setup(AccCtx& C, const uint8_t* fdr, int64_t rows, int64_t cols, 
   p.strip_above = has_above ? 1 : 0;
   p.strip_below = has_below ? 1 : 0;
   p.tile_base = 0;
+  p.vec_store = ((reinterpret_cast<uintptr_t>(fac) & 15) == 0 && (ld_fac % 2) == 0) ? 1 : 0;
   C.pa = reinterpret_cast<int32_t*>(C.ws + C.L.off_pa);
   C.pb = reinterpret_cast<int32_t*>(C.ws + C.L.off_pb);
   C.lists = reinterpret_cast<int32_t*>(C.ws + C.L.off_lists);
