@@ -245,9 +245,10 @@ def run_native(args):
 
     # ---- roofline of the dominant kernel (live CUDA-event times from the timed region, this rank)
     cells_rank = cells_total // world
-    per_phase = {k: (v[0] / max(v[1], 1), v[1]) for k, v in phases.items()}
-    dom = max(PHASE_BYTES, key=lambda k: per_phase[k][0])
-    dom_ms = per_phase[dom][0]
+    per_step = {k: v[0] / args.steps for k, v in phases.items()}          # ms per step, all launches of the phase
+    per_launch = {k: v[0] / max(v[1], 1) for k, v in phases.items()}
+    dom = max(PHASE_BYTES, key=lambda k: per_step[k])
+    dom_ms = per_step[dom] if world > 1 else per_launch[dom]              # strips: the tile passes run once per step
     achieved = cells_rank * PHASE_BYTES[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     traffic = None
     try:
@@ -257,13 +258,22 @@ def run_native(args):
             traffic = tj.get(dom)
     except Exception:
         pass
+    acc_ms = per_step["acc_tile_a"] + per_step["acc_solve"] + per_step["acc_tile_b"] + per_step["strip_edge"]
+
+    def gbs(bytes_per_cell, ms_):
+        return cells_rank * bytes_per_cell / (ms_ * 1e-3) / 1e9 if ms_ > 0 else None
+
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "peak_source": peak_src, "bytes_per_cell": PHASE_BYTES[dom],
-        "avg_launch_ms": dom_ms,
-        "phases_ms_per_launch": {k: round(v[0], 4) for k, v in per_phase.items()},
-        "phase_gbs": {k: (cells_rank * PHASE_BYTES[k] / (per_phase[k][0] * 1e-3) / 1e9 if per_phase[k][0] > 0 else None)
-                      for k in PHASE_BYTES},
+        "traffic": traffic, "peak_source": peak_src, "bytes_per_cell": PHASE_BYTES[dom], "avg_launch_ms": dom_ms,
+        "phases_ms_per_step": {k: round(v, 4) for k, v in per_step.items()},
+        "phase_gbs": {k: gbs(PHASE_BYTES[k], per_step[k]) for k in PHASE_BYTES},
+        "phase_frac": {k: (gbs(PHASE_BYTES[k], per_step[k]) or 0.0) / peak for k in PHASE_BYTES},
+        # the same algorithmic bytes over larger pieces of the step
+        "accumulation_9B_per_cell": {"ms": acc_ms, "gbs": gbs(ACC_BYTES_PER_CELL, acc_ms),
+                                     "frac": (gbs(ACC_BYTES_PER_CELL, acc_ms) or 0.0) / peak},
+        "whole_step_13B_per_cell": {"ms": ms_per_step, "gbs": gbs(13.0, ms_per_step),
+                                    "frac": (gbs(13.0, ms_per_step) or 0.0) / peak},
     }
 
     line = {

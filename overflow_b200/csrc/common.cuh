@@ -61,7 +61,7 @@ int pinned_get(size_t bytes, void** out);
 // ---------------------------------------------------------------- TMA tensor maps (host)
 // 2-D row-major tensor, element size `esz`, `cols` x `rows`, row pitch in bytes, box_w x box_h tile.
 int make_tensor_map_2d(CUtensorMap* tm, const void* base, int esz, uint64_t cols, uint64_t rows,
-                       uint64_t pitch_bytes, uint32_t box_w, uint32_t box_h);
+                       uint64_t pitch_bytes, uint32_t box_w, uint32_t box_h, int l2_promotion_bytes = 128);
 
 // ---------------------------------------------------------------- device-side PTX wrappers
 #ifdef __CUDACC__

@@ -39,6 +39,9 @@
 
 namespace ofl {
 
+#ifndef OFL_DIR_L2PROMO
+#define OFL_DIR_L2PROMO 0
+#endif
 #ifndef OFL_DIR_RB
 #define OFL_DIR_RB 4
 #endif
@@ -382,7 +385,7 @@ int launch_direction(const float* dem, int64_t in_rows, int64_t cols, int64_t ld
   OFL_REQUIRE((reinterpret_cast<uintptr_t>(fdr) & 3) == 0 && (ld_fdr % 4) == 0 && ld_fdr >= cols, OFL_ERR_ALIGNMENT,
               "fdr must be 4-byte aligned with ld_fdr %% 4 == 0 (ld_fdr=%lld)", (long long)ld_fdr);
   CUtensorMap tm;
-  int rc = make_tensor_map_2d(&tm, dem, 4, (uint64_t)cols, (uint64_t)in_rows, (uint64_t)ld_dem * 4, DIR_BOXW, DIR_RB);
+  int rc = make_tensor_map_2d(&tm, dem, 4, (uint64_t)cols, (uint64_t)in_rows, (uint64_t)ld_dem * 4, DIR_BOXW, DIR_RB, OFL_DIR_L2PROMO);
   if (rc != OFL_OK) return rc;
 
   DirParams p;

@@ -221,7 +221,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int make_tensor_map_2d(CUtensorMap* tm, const void* base, int esz, uint64_t cols, uint64_t rows, uint64_t pitch_bytes,
-                       uint32_t box_w, uint32_t box_h) {
+                       uint32_t box_w, uint32_t box_h, int l2_promotion_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   OFL_REQUIRE(fn != nullptr, OFL_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   CUtensorMapDataType dt;
@@ -231,12 +231,18 @@ int make_tensor_map_2d(CUtensorMap* tm, const void* base, int esz, uint64_t cols
     case 8: dt = CU_TENSOR_MAP_DATA_TYPE_UINT64; break;
     default: set_error("unsupported tensor-map element size %d", esz); return OFL_ERR_INVALID;
   }
+  // L2 promotion widens every fetch to that granularity: boxes whose rows are far apart in memory (wide
+  // rasters) and not aligned to it would drag in neighbouring bytes they never use
+  const CUtensorMapL2promotion promo = l2_promotion_bytes >= 256   ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                       : l2_promotion_bytes >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                       : l2_promotion_bytes >= 64  ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                                                   : CU_TENSOR_MAP_L2_PROMOTION_NONE;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {pitch_bytes};
   cuuint32_t box[2] = {box_w, box_h};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   OFL_REQUIRE(r == CUDA_SUCCESS, OFL_ERR_CUDA,
               "cuTensorMapEncodeTiled failed (%d) for %llux%llu esz=%d pitch=%llu box=%ux%u", (int)r,
               (unsigned long long)cols, (unsigned long long)rows, esz, (unsigned long long)pitch_bytes, box_w, box_h);

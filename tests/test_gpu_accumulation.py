@@ -138,3 +138,31 @@ def test_large_device_adversarial(kind):
     fac = dev.flow_accumulation(fdr)
     assert dev.check_accumulation(fdr, fac) == 0
     assert np.array_equal(fac.cpu().numpy(), oracle.flow_accumulation(fdr.cpu().numpy()))
+
+
+def test_config1_1024_reference_golden():
+    """configs[0] against the REFERENCE's own output (fixture made by oracle/gen_golden.py --big)."""
+    import os
+
+    from conftest import GOLDEN
+
+    if not os.path.exists(os.path.join(GOLDEN, "config1_1024.npz")):
+        pytest.skip("big anchor not generated")
+    g = load_golden("config1_1024.npz")
+    fac, links = stfa(g["fdr"])
+    assert np.array_equal(fac, g["fac"].astype(np.int64))
+    rc = g["perim_rc"].astype(np.int64)
+    assert np.array_equal(links[rc[:, 0], rc[:, 1]], g["perim_links"].astype(np.int64))
+
+
+def test_perimeter_links_device_large():
+    """links of a 2048 x 3072 device raster vs the oracle (paths crossing many tiles)."""
+    from overflow_b200 import device as dev
+
+    dem = dev.synth_dem(2048, 3072, seed=21, kind=0, holes_permille=3)
+    fdr = dev.flow_direction(dem, synth.NODATA)
+    fac, links = dev.flow_accumulation(fdr, with_links=True)
+    h = fdr.cpu().numpy()
+    _, want = oracle.links_perimeter(h)
+    assert np.array_equal(links.cpu().numpy(), want)
+    assert np.array_equal(fac.cpu().numpy(), oracle.flow_accumulation(h))
