@@ -597,10 +597,11 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_final_kernel(const __grid_con
 // ---------------------------------------------------------------- reduced-graph solve
 // Subtree sums over the perimeter forest by pointer doubling, restricted to the nodes that still have
 // an ancestor to jump to.  ptr[u] >= 0: u's 2^j-th ancestor.  ptr[u] < 0: ~root(u), chain exhausted.
-// Round j, for every ACTIVE node w: S_j[w] is added to its 2^j-th ancestor a (delta buffers d0/d1
-// alternate so a node only ever forwards sums that were complete before the round), then w jumps to
-// a's pointer.  A node whose jump finds an exhausted chain retires: it is dropped from the active list
-// and, one round later, its root is copied into the other ping-pong buffer so both stay readable.
+// Round j, for every ACTIVE node w: S_j[w] is added to its 2^j-th ancestor a (through alternating delta
+// buffers d0/d1 while a is itself still jumping, so a node only ever forwards sums that were complete
+// before the round; directly into S[a] once a's chain is exhausted), then w jumps to a's pointer.  A
+// node whose jump finds an exhausted chain retires: it is dropped from the active list and, one round
+// later, its root is copied into the other ping-pong buffer and its last deltas are flushed into S.
 // The node array is cut into one segment per CTA; each CTA keeps the active nodes of its segment
 // compacted at the front of the segment (retirees at the back) of a ping-pong list, so compaction needs
 // only shared-memory atomics and the work per round is proportional to the active nodes, which shrink
@@ -674,6 +675,11 @@ __global__ void pj_round_kernel(const int32_t* __restrict__ list_in, int32_t* __
   for (int i = threadIdx.x; i < n_retired; i += blockDim.x) {
     const int32_t w = in[g.seg - 1 - i];
     ptr_out[w] = ptr_in[w];
+    const unsigned long long dp = d_prev[w];  // what it received during the round it retired in
+    if (dp) {
+      atomicAdd(&S[w], dp);
+      d_prev[w] = 0;
+    }
   }
   const int n_up = (n_active + 31) / 32 * 32;
   for (int i = threadIdx.x; i < n_up; i += blockDim.x) {
@@ -689,8 +695,10 @@ __global__ void pj_round_kernel(const int32_t* __restrict__ list_in, int32_t* __
         d_prev[w] = 0;
       }
       const int32_t a = ptr_in[w];
-      if (s) atomicAdd(&d_next[a], s);
       const int32_t q = ptr_in[a];
+      // an ancestor that still jumps forwards what it receives next round (delta buffer); one whose
+      // chain is exhausted never forwards again, so its sum takes the contribution directly
+      if (s) atomicAdd(q >= 0 ? &d_next[a] : &S[a], s);
       ptr_out[w] = q;
       keep = q >= 0;
       retire = !keep;
@@ -867,9 +875,7 @@ static int pj_solve(const int32_t* succ, int32_t* ptr_a, int32_t* ptr_b, int32_t
   }
   pj_leftover_kernel<<<1, 256, 0, st>>>(counts + (int64_t)rounds * cstride, g.blocks, leftover);
   OFL_CHECK_LAUNCH();
-  pj_fold_kernel<<<grid_for(n, 8), 256, 0, st>>>(S, d0, d1, n);
-  OFL_CHECK_LAUNCH();
-  return OFL_OK;
+  return OFL_OK;  // every delta has been flushed into S: d0 / d1 are all zero again
 }
 
 // One synchronisation at the end of a call: err[0] = cycle seen by a tile kernel, err[1] = a solve did
