@@ -404,7 +404,7 @@ int launch_direction(const float* dem, int64_t in_rows, int64_t cols, int64_t ld
   // rows per work item: long enough to amortise the 2-row prologue, short enough to balance the grid
   const int sms = sm_count();
   int chunk_rows = 512;
-  while (chunk_rows > 32 && (int64_t)p.n_bands * ((rows + chunk_rows - 1) / chunk_rows) < (int64_t)sms * OFL_DIR_CTAS_PER_SM * DIR_WARPS * 4)
+  while (chunk_rows > 32 && (int64_t)p.n_bands * ((rows + chunk_rows - 1) / chunk_rows) < (int64_t)sms * OFL_DIR_CTAS_PER_SM * DIR_WARPS * 16)
     chunk_rows >>= 1;
   p.chunk_rows = chunk_rows;
   p.n_chunks = (int)((rows + chunk_rows - 1) / chunk_rows);
