@@ -492,8 +492,8 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
 // then the tile is written out as int64.  ~11 B/cell of HBM traffic and a few hundred instructions per
 // warp: this kernel runs close to the HBM roofline instead of re-doing the whole propagation.
 struct FinalSmem {
-  static constexpr int CS = 0;
-  static constexpr int LO = 6400;
+  static constexpr int CS = 0;       // 64 x 64 codes, no halo (TMA box starts on the tile, 16-byte aligned)
+  static constexpr int LO = AT * AT;
   static constexpr int HI = LO + AT * AT * 4;
   static constexpr int TAB = HI + AT * AT * 4;  // int4 per direction code: {code-array byte offset, dy, dx, lo/hi byte offset}
   static constexpr int BAR = TAB + 128;
@@ -503,7 +503,7 @@ struct FinalSmem {
 __global__ void __launch_bounds__(ACC_THREADS) acc_final_kernel(const __grid_constant__ CUtensorMap tm, const AccParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t sb = smem_u32(smem_raw);
-  const uint32_t a_cs0 = sb + FinalSmem::CS + ACS_W * ACS_Y0 + ACS_X0;  // code of cell (0,0)
+  const uint32_t a_cs0 = sb + FinalSmem::CS;  // code of cell (0,0), pitch AT
   const uint32_t a_lo = sb + FinalSmem::LO, a_hi = sb + FinalSmem::HI, a_tab = sb + FinalSmem::TAB;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + FinalSmem::BAR);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -515,12 +515,12 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_final_kernel(const __grid_con
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
-    mbar_arrive_expect_tx(bar, ACS_BYTES);
-    tma_load_2d(smem_raw + FinalSmem::CS, &tm, x0 - ACS_X0, y0 - ACS_Y0 + p.y_off, bar);
+    mbar_arrive_expect_tx(bar, AT * AT);
+    tma_load_2d(smem_raw + FinalSmem::CS, &tm, x0, y0 + p.y_off, bar);
   }
   if (tid < 8) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_tab + 16 * tid),
-                 "r"((uint32_t)(dir_dy(tid) * ACS_W + dir_dx(tid))), "r"((uint32_t)dir_dy(tid)), "r"((uint32_t)dir_dx(tid)),
+                 "r"((uint32_t)(dir_dy(tid) * AT + dir_dx(tid))), "r"((uint32_t)dir_dy(tid)), "r"((uint32_t)dir_dx(tid)),
                  "r"((uint32_t)((dir_dy(tid) * AT + dir_dx(tid)) * 4))
                  : "memory");
   }
@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_final_kernel(const __grid_con
 
   if (seed) {
     const uint32_t slo = (uint32_t)seed, shi = (uint32_t)(seed >> 32);
-    uint32_t ca = a_cs0 + y * ACS_W + x;     // shared address of the current cell's code
+    uint32_t ca = a_cs0 + y * AT + x;        // shared address of the current cell's code
     uint32_t o = (y * AT + x) * 4;           // byte offset of the current cell in lo[] / hi[]
     for (int steps = 0; steps <= AT * AT; ++steps) {
       const uint32_t old = atoms_add(a_lo + o, slo);
@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_final_kernel(const __grid_con
     if (yy < h && (int)xx < w) {
       const uint32_t oo = (yy * AT + xx) * 4;
       const uint2 lo2 = lds64(a_lo + oo), hi2 = lds64(a_hi + oo);
-      const uint32_t c2 = lds16(a_cs0 + yy * ACS_W + xx);
+      const uint32_t c2 = lds16(a_cs0 + yy * AT + xx);
       long long v0 = (long long)(((unsigned long long)hi2.x << 32) | lo2.x);
       long long v1 = (long long)(((unsigned long long)hi2.y << 32) | lo2.y);
       if ((c2 & 0xFF) == OFL_DIR_NODATA) v0 = OFL_FAC_NODATA_EMITTED;
@@ -937,7 +937,8 @@ size_t strip_workspace_bytes(int64_t rows, int64_t cols) {
 // Everything one raster (or strip) needs to launch its kernels.
 struct AccCtx {
   AccParams p;
-  CUtensorMap tm;
+  CUtensorMap tm;        // codes + halo box for pass A
+  CUtensorMap tm_tile;   // exact 64 x 64 box for the final pass
   GraphLayout L;
   uint8_t* ws;
   int64_t ntiles;
@@ -985,6 +986,8 @@ static int acc_setup(AccCtx& C, const uint8_t* fdr, int64_t rows, int64_t cols, 
   C.ntiles = (int64_t)p.nty * p.ntx;
   int rc = make_tensor_map_2d(&C.tm, fdr, 1, (uint64_t)cols, (uint64_t)(rows + 2 * y_off), (uint64_t)ld_fdr, ACS_W, ACS_H);
   if (rc != OFL_OK) return rc;
+  rc = make_tensor_map_2d(&C.tm_tile, fdr, 1, (uint64_t)cols, (uint64_t)(rows + 2 * y_off), (uint64_t)ld_fdr, AT, AT);
+  if (rc != OFL_OK) return rc;
   return ensure_tile_attrs();
 }
 
@@ -1010,7 +1013,7 @@ int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t 
   if (rc != OFL_OK) return rc;
   {
     PhaseScope ps(PHASE_ACC_TILE_B, st);
-    acc_final_kernel<<<(unsigned)C.ntiles, ACC_THREADS, FinalSmem::BYTES, st>>>(C.tm, C.p);
+    acc_final_kernel<<<(unsigned)C.ntiles, ACC_THREADS, FinalSmem::BYTES, st>>>(C.tm_tile, C.p);
   }
   OFL_CHECK_LAUNCH();
   if (perim_links_dev) {
@@ -1150,10 +1153,10 @@ int strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
   {
     PhaseScope ps(PHASE_STRIP_EDGE, st);
     AccParams pb = C.p;
-    acc_final_kernel<<<(unsigned)pb.ntx, ACC_THREADS, FinalSmem::BYTES, st>>>(C.tm, pb);
+    acc_final_kernel<<<(unsigned)pb.ntx, ACC_THREADS, FinalSmem::BYTES, st>>>(C.tm_tile, pb);
     if (pb.nty > 1) {
       pb.tile_base = (pb.nty - 1) * pb.ntx;
-      acc_final_kernel<<<(unsigned)pb.ntx, ACC_THREADS, FinalSmem::BYTES, st>>>(C.tm, pb);
+      acc_final_kernel<<<(unsigned)pb.ntx, ACC_THREADS, FinalSmem::BYTES, st>>>(C.tm_tile, pb);
       count_launch();
     }
   }
@@ -1222,7 +1225,7 @@ int strip_accum_final(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
   OFL_CHECK_LAUNCH();
   {
     PhaseScope ps(PHASE_ACC_TILE_B, st);
-    acc_final_kernel<<<(unsigned)C.ntiles, ACC_THREADS, FinalSmem::BYTES, st>>>(C.tm, C.p);
+    acc_final_kernel<<<(unsigned)C.ntiles, ACC_THREADS, FinalSmem::BYTES, st>>>(C.tm_tile, C.p);
   }
   OFL_CHECK_LAUNCH();
   return check_flags(C.p.err, st);
