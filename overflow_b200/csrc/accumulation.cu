@@ -183,6 +183,13 @@ __device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v) {
   asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory");
   return o;
 }
+// Shared-window base as an opaque value: the compiler keeps it in a register instead of re-deriving it
+// (S2R SR_CgaCtaId + LEA) in front of every shared-memory access of the hot loops.
+__device__ __forceinline__ uint32_t smem_base_opaque(const void* p) {
+  uint32_t a;
+  asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(a) : "l"(p));
+  return a;
+}
 __device__ __forceinline__ uint32_t lanemask_lt() {
   uint32_t m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -198,7 +205,7 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
                                                                 const AccParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   using SM = TileSmem;
-  const uint32_t sb = smem_u32(smem_raw);
+  const uint32_t sb = smem_base_opaque(smem_raw);
   const uint32_t a_cs = sb + SM::CS;      // codes + halo (TMA destination), pitch ACS_W bytes
   const uint32_t a_word = sb + SM::WORD;  // [missing:4 | count:28], halo-padded, pitch WP words
   const uint32_t a_q = sb + SM::Q;        // frontier queue of cell ids (y*64+x), u16
@@ -372,13 +379,8 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
       const uint32_t i = base + lane;
       uint32_t nidx = 0;
       const bool ready = (i < hi) && finish(lds16(a_q + 2 * i), nidx);
-      const uint32_t bal = __ballot_sync(0xffffffffu, ready);
-      if (bal) {
-        uint32_t qb = 0;
-        if (lane == 0) qb = atoms_add(a_tail, __popc(bal));
-        qb = __shfl_sync(0xffffffffu, qb, 0);
-        if (ready) sts16(a_q + 2 * (qb + __popc(bal & lt_mask)), nidx);
-      }
+      // one slot per completed cell; ptxas turns these same-address atomics into one per warp
+      if (ready) sts16(a_q + 2 * atoms_add(a_tail, 1u), nidx);
     }
     __syncthreads();
     const uint32_t nh = lds32(a_tail);
@@ -502,7 +504,7 @@ struct FinalSmem {
 
 __global__ void __launch_bounds__(ACC_THREADS) acc_final_kernel(const __grid_constant__ CUtensorMap tm, const AccParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  const uint32_t sb = smem_u32(smem_raw);
+  const uint32_t sb = smem_base_opaque(smem_raw);
   const uint32_t a_cs0 = sb + FinalSmem::CS;  // code of cell (0,0), pitch AT
   const uint32_t a_lo = sb + FinalSmem::LO, a_hi = sb + FinalSmem::HI, a_tab = sb + FinalSmem::TAB;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + FinalSmem::BAR);
