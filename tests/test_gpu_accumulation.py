@@ -166,3 +166,29 @@ def test_perimeter_links_device_large():
     _, want = oracle.links_perimeter(h)
     assert np.array_equal(links.cpu().numpy(), want)
     assert np.array_equal(fac.cpu().numpy(), oracle.flow_accumulation(h))
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 300), (300, 1), (63, 65), (64, 64), (129, 64), (2, 5000)])
+def test_degenerate_and_tile_aligned_shapes(shape):
+    dem = synth.fractal(shape[0], shape[1], beta=2.0, seed=shape[0] * 7 + shape[1])
+    fdr = oracle.flow_direction_for_tile(synth.pad_nodata(dem), synth.NODATA)[1:-1, 1:-1].copy()
+    fac, links = stfa(fdr)
+    assert np.array_equal(fac, oracle.flow_accumulation(fdr))
+    rc, want_links = oracle.links_perimeter(fdr)
+    assert np.array_equal(links[rc[:, 0], rc[:, 1]], want_links)
+
+
+def test_all_cells_one_chain_counts_exceed_32_bits_path():
+    """A long single channel: the 64-bit path of the final pass (low word + carry) stays exact."""
+    from overflow_b200 import device as dev
+    import torch
+
+    # serpentine on the device path; counts reach rows*cols-ish in the channel
+    dem = synth.serpentine(513, 517)
+    fdr = oracle.flow_direction_for_tile(synth.pad_nodata(dem), synth.NODATA)[1:-1, 1:-1].copy()
+    want = oracle.flow_accumulation(fdr)
+    pitched = torch.zeros((513, 528), dtype=torch.uint8, device="cuda")[:, :517]
+    pitched.copy_(torch.from_numpy(fdr))
+    fac = dev.flow_accumulation(pitched)
+    assert np.array_equal(fac.cpu().numpy(), want)
+    assert want.max() > 100000

@@ -72,3 +72,19 @@ def test_long_chain_across_all_strips():
     assert np.array_equal(fac, oracle.flow_accumulation(want_fdr))
     assert fac.max() >= rows - 1
     del strips
+
+
+@pytest.mark.parametrize("shape,world", [((257, 65), 3), ((200, 1000), 2), ((1000, 37), 5), ((449, 129), 7)])
+def test_ragged_shapes_with_nodata_on_strip_boundaries(shape, world):
+    """nodata rows / blobs exactly on strip boundaries, widths that are not multiples of the tile or band."""
+    from overflow_b200 import strips
+
+    rows, cols = shape
+    dem = synth.punch_holes(synth.fractal(rows, cols, beta=2.5, seed=rows + cols), frac=0.03, seed=7)
+    for r0, _ in strips.partition_rows(rows, world)[1:]:
+        dem[r0 - 1 : r0 + 1, cols // 4 : cols // 2] = synth.NODATA  # nodata straddling the boundary
+    want_fdr = oracle.flow_direction_for_tile(synth.pad_nodata(dem), synth.NODATA)[1:-1, 1:-1]
+    want_fac = oracle.flow_accumulation(want_fdr)
+    fdr, fac = run_strips(dem, world)
+    assert np.array_equal(fdr, want_fdr)
+    assert np.array_equal(fac, want_fac)
