@@ -310,7 +310,7 @@ __device__ __forceinline__ void direction_item(const CUtensorMap* tm, const DirP
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(DIR_WARPS * 32, 3) direction_kernel(const __grid_constant__ CUtensorMap tm,
+__global__ void __launch_bounds__(DIR_WARPS * 32, OFL_DIR_CTAS_PER_SM) direction_kernel(const __grid_constant__ CUtensorMap tm,
                                                                     const DirParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5;
