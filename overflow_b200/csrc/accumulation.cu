@@ -112,24 +112,42 @@ __device__ __forceinline__ int node_of_cell(int gy, int gx, const AccParams& p) 
 }
 
 // ---------------------------------------------------------------- in-tile frontier propagation
-// Kahn's algorithm inside one 64x64 tile, level-synchronous, frontier in a shared-memory queue:
-//   * every cell carries the number of in-tile upstream neighbours still missing, packed with its
-//     running count in one 32-bit word [missing:4 | count:28];
-//   * a finished cell hands its count to its downstream cell with ONE shared-memory atomic add of
-//     (count - 1<<28): it adds the count and decrements the missing field at once, so the thread that
-//     sees the field drop to zero knows the sum is complete and appends the cell to the frontier
-//     (warp ballot + popc compaction, one queue atomic per warp);
-//   * the word array has a one-cell halo and no edge is ever skipped: hand-offs into the halo, into
-//     NODATA cells or out of the raster land in words nobody reads;
-//   * frontier levels are consecutive segments of one 4096-entry queue (a cell is appended once);
-//     a level never grows, so once it fits one cell per thread each thread simply follows its chain
-//     (it continues exactly when its hand-off completed the next cell): no queue, no barriers.
-// Tile-local counts are at most 4096, so the 28-bit count field never overflows.
-// Shared memory is addressed through explicit 32-bit shared-space addresses (ld/st/atom.shared):
-// the hot loop is ~40 instructions per 32 cells.
-constexpr int WP = 68;                 // word-array pitch: cells x = -1..64 in columns 0..65
+// Kahn's algorithm inside one 64x64 tile.  Every cell (plus a one-cell halo ring) owns one 32-bit word
+//
+//     [31 visited | 30..27 missing | 26 live | 25..8 count | 7..0 downstream offset]
+//
+//   * offset   signed distance, in words, to the downstream cell's word (0: no downstream cell) -- a
+//              step along a flow path is one sign-extension and one scaled add, no table, no code load;
+//   * live     the cell is a data cell of this tile (code <= 8, inside the raster); halo and NODATA words
+//              have it clear, so they absorb hand-offs but are never scheduled;
+//   * missing  in-tile upstream neighbours that have not handed their count down yet;
+//   * count    running sum of the upstream counts (tile-local counts are <= 4096);
+//   * visited  set together with "missing = 15" when the cell is finished.
+// A finished cell hands its count to its downstream cell with ONE shared-memory atomic add of
+// (count << 8) - (1 << 27): it adds the count and decrements the missing field at once, and the value the
+// atomic returns tells the thread whether it was the last hand-off the downstream cell waited for -- and
+// already holds that cell's offset and running sum.  No edge is ever skipped: hand-offs into the halo,
+// into NODATA cells or out of the raster land in words nobody schedules.
+// Frontier levels are consecutive segments of one 4096-entry queue of word addresses (a cell is appended
+// once).  A level never grows, so once it fits one cell per thread each thread simply follows its chain
+// (it continues exactly when its hand-off completed the next cell): no queue, no barriers.
+constexpr int WP = 72;                 // word-array pitch; cell x sits in column x + 4, so quads are 16-byte aligned
+constexpr int WX0 = 4;
 constexpr int WORDS = (AT + 2) * WP;   // rows y = -1..64
 constexpr int QMAX = AT * AT;
+constexpr uint32_t W_CNT_ONE = 1u << 8;
+constexpr uint32_t W_LIVE = 1u << 26;
+constexpr uint32_t W_MISS_ONE = 1u << 27;
+constexpr uint32_t W_VISITED = 1u << 31;
+constexpr uint32_t W_FINISH = 0xF8000000u + W_CNT_ONE;       // ready word -> finished word (counts the cell itself)
+constexpr uint32_t W_HANDOFF_MASK = ~(W_LIVE | 0xFFu);               // finished word -> what its hand-off adds downstream
+constexpr uint32_t W_READY_MASK = (0xFu << 27) | W_LIVE;     // hand-off result: the downstream cell is a live cell ...
+constexpr uint32_t W_READY_VAL = W_MISS_ONE | W_LIVE;        // ... and this was the hand-off it was waiting for
+// downstream word offsets per direction code E, NE, N, NW | W, SW, S, SE as signed bytes (PRMT lookup tables)
+constexpr uint32_t W_TAB_LO = (uint32_t)(uint8_t)(1) | ((uint32_t)(uint8_t)(1 - WP) << 8) |
+                              ((uint32_t)(uint8_t)(-WP) << 16) | ((uint32_t)(uint8_t)(-WP - 1) << 24);
+constexpr uint32_t W_TAB_HI = (uint32_t)(uint8_t)(-1) | ((uint32_t)(uint8_t)(WP - 1) << 8) |
+                              ((uint32_t)(uint8_t)(WP) << 16) | ((uint32_t)(uint8_t)(WP + 1) << 24);
 #ifndef OFL_WALK_PER_THREAD
 #define OFL_WALK_PER_THREAD 1
 #endif
@@ -139,15 +157,13 @@ struct TileSmem {
   static constexpr int CS = 0;
   static constexpr int WORD = 6400;  // ACS_BYTES rounded up to 128
   static constexpr int Q = WORD + WORDS * 4;
-  static constexpr int TAB = Q + QMAX * 2;  // int2 per direction code: {word-array byte offset, cell-id offset}
-  static constexpr int TAB2 = TAB + 64;  // int2 per direction code: {code-array byte offset, cell-id offset}
-  static constexpr int TAB3 = TAB2 + 64;  // int2 per direction code: {word-array byte offset, code-array byte offset}
-  static constexpr int TAIL = TAB3 + 64;
+  static constexpr int TAIL = Q + QMAX * 2;
   static constexpr int BAR = TAIL + 16;
   static constexpr int BYTES = BAR + 16;
 };
 static_assert(ACS_BYTES <= 6400, "code tile does not fit its shared-memory slot");
-static_assert((WORDS * 4) % 16 == 0, "word array must be a whole number of uint4");
+static_assert((WORDS * 4) % 16 == 0 && (WP * 4) % 16 == 0, "word rows must be whole uint4s");
+static_assert(WORDS * 4 < 65536, "queue entries are 16-bit byte offsets into the word array");
 
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
   uint32_t v;
@@ -157,6 +173,11 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a) {
 __device__ __forceinline__ uint2 lds64(uint32_t a) {
   uint2 v;
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
   return v;
 }
 __device__ __forceinline__ uint32_t lds16(uint32_t a) {
@@ -172,6 +193,9 @@ __device__ __forceinline__ uint32_t lds8(uint32_t a) {
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+}
 __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
   asm volatile("{.reg .u16 t; cvt.u16.u32 t, %1; st.shared.u16 [%0], t;}" ::"r"(a), "r"(v) : "memory");
 }
@@ -182,6 +206,11 @@ __device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v) {
   uint32_t o;
   asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory");
   return o;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
 }
 // Shared-window base as an opaque value: the compiler keeps it in a register instead of re-deriving it
 // (S2R SR_CgaCtaId + LEA) in front of every shared-memory access of the hot loops.
@@ -201,15 +230,19 @@ __device__ __forceinline__ uint32_t bytes_differ(uint32_t nb, uint32_t pat) {
   return (((nb ^ pat) + 0x7F7F7F7Fu) >> 7) & 0x01010101u;
 }
 
+// shared address of the word the flow path steps to from the word `w` at address `aw` (w's offset byte != 0)
+__device__ __forceinline__ uint32_t word_next(uint32_t aw, uint32_t w) {
+  return aw + (uint32_t)((int32_t)(int8_t)(w & 0xFFu) * 4);
+}
+
 __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_constant__ CUtensorMap tm,
                                                                 const AccParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   using SM = TileSmem;
   const uint32_t sb = smem_base_opaque(smem_raw);
   const uint32_t a_cs = sb + SM::CS;      // codes + halo (TMA destination), pitch ACS_W bytes
-  const uint32_t a_word = sb + SM::WORD;  // [missing:4 | count:28], halo-padded, pitch WP words
-  const uint32_t a_q = sb + SM::Q;        // frontier queue of cell ids (y*64+x), u16
-  const uint32_t a_tab = sb + SM::TAB;
+  const uint32_t a_word = sb + SM::WORD;  // per-cell words, halo-padded, pitch WP words
+  const uint32_t a_q = sb + SM::Q;        // frontier queue: byte offsets of words from a_word, u16
   const uint32_t a_tail = sb + SM::TAIL;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + SM::BAR);
 
@@ -226,18 +259,13 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     tma_load_2d(smem_raw + SM::CS, &tm, x0 - ACS_X0, y0 - ACS_Y0 + p.y_off, bar);
     sts32(a_tail, 0);
   }
-  if (tid < 8) {
-    sts32(a_tab + 8 * tid, (uint32_t)((dir_dy(tid) * WP + dir_dx(tid)) * 4));
-    sts32(a_tab + 8 * tid + 4, (uint32_t)(dir_dy(tid) * AT + dir_dx(tid)));
-    sts32(sb + SM::TAB2 + 8 * tid, (uint32_t)(dir_dy(tid) * ACS_W + dir_dx(tid)));
-    sts32(sb + SM::TAB2 + 8 * tid + 4, (uint32_t)(dir_dy(tid) * AT + dir_dx(tid)));
-    sts32(sb + SM::TAB3 + 8 * tid, (uint32_t)((dir_dy(tid) * WP + dir_dx(tid)) * 4));
-    sts32(sb + SM::TAB3 + 8 * tid + 4, (uint32_t)(dir_dy(tid) * ACS_W + dir_dx(tid)));
-  }
-  {
-    uint4* z = reinterpret_cast<uint4*>(smem_raw + SM::WORD);
-    constexpr int NZ = WORDS / 4;
-    for (int i = tid; i < NZ; i += ACC_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+  // halo ring of the word array: zero (not live, so never scheduled); in-tile words are written in phase 1
+  if (tid < 2 * (WP / 4)) {
+    const int r = tid < WP / 4 ? 0 : AT + 1, c4 = tid < WP / 4 ? tid : tid - WP / 4;
+    sts128(a_word + (r * WP + 4 * c4) * 4, 0, 0, 0, 0);
+  } else if (tid < 2 * (WP / 4) + 2 * AT) {
+    const int k = tid - 2 * (WP / 4);
+    sts128(a_word + (((k >> 1) + 1) * WP + ((k & 1) ? WX0 + AT : 0)) * 4, 0, 0, 0, 0);
   }
   __syncthreads();
   mbar_wait(bar, 0);
@@ -306,9 +334,14 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
   __syncthreads();
 
   const uint32_t lt_mask = lanemask_lt();
+  // the queue tail's address through a lane-dependent zero: ptxas then leaves the hand-aggregated queue
+  // atomics alone instead of wrapping each in its own warp-aggregation sequence
+  const uint32_t a_tail_v = a_tail + (lt_mask >> 31);
+  const uint32_t a_word0 = a_word + (WP + WX0) * 4;       // word of cell (0,0)
+  const uint32_t a_cs0 = a_cs + ACS_W * ACS_Y0 + ACS_X0;  // code of cell (0,0)
 
-  // ---- phase 1: missing-counts for four cells at a time (byte-parallel), sources into the queue.
-  //      Lane owns the quad of columns 4*qx..4*qx+3 in rows 8*warp + 2*i + rp.
+  // ---- phase 1: missing-counts for four cells at a time (byte-parallel), the four words, sources into
+  //      the queue.  Lane owns the quad of columns 4*qx..4*qx+3 in rows 8*warp + 2*i + rp.
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int y = 8 * warp + 2 * i + rp;
@@ -326,12 +359,17 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     nm += bytes_differ(C2, 0x02020202u);                                  // S neighbour flowing N
     nm += bytes_differ(__funnelshift_r(C2, R2, 8), 0x03030303u);          // SE neighbour flowing NW
     const uint32_t cnt4 = 0x08080808u - nm;  // missing upstream neighbours per cell
+    const uint32_t dead = C1 + 0x77777777u;  // bit 7 of a byte set: code >= 9, not a data cell
     // source: missing == 0 and the cell is a data cell (own code <= 8)
-    const uint32_t src = ~((cnt4 + 0x7F7F7F7Fu) | (C1 + 0x77777777u)) & 0x80808080u;
-    const uint32_t idx0 = y * AT + 4 * qx;
-    const uint32_t aw = a_word + ((y + 1) * WP + 4 * qx + 1) * 4;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) sts32(aw + 4 * b, ((cnt4 >> (8 * b)) & 0xFu) << 28);
+    const uint32_t src = ~((cnt4 + 0x7F7F7F7Fu) | dead) & 0x80808080u;
+    // the four words: offsets by a byte-wise table lookup on the codes (codes >= 8 select in PRMT's
+    // sign-replicate mode: code 8 -> sign of +1 -> 0 = no downstream; code >= 9 -> garbage in a word that
+    // is never scheduled), top bytes [missing << 3 | live << 2]; one PRMT assembles each word
+    const uint32_t nib = C1 | (C1 >> 4);
+    const uint32_t off4 = prmt(W_TAB_LO, W_TAB_HI, prmt(nib, 0u, 0x4420u));
+    const uint32_t hi4 = (cnt4 << 3) | ((~dead >> 5) & 0x04040404u);
+    const uint32_t aw = a_word0 + (y * WP + 4 * qx) * 4;
+    sts128(aw, prmt(off4, hi4, 0x4CC0u), prmt(off4, hi4, 0x5DD1u), prmt(off4, hi4, 0x6EE2u), prmt(off4, hi4, 0x7FF3u));
     // append this warp's sources: exclusive scan of per-lane source counts, one queue atomic per warp
     const uint32_t mine = __popc(src);
     uint32_t incl = mine;
@@ -341,35 +379,19 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
       if (lane >= o) incl += t;
     }
     uint32_t base = 0;
-    if (lane == 31) base = atoms_add(a_tail, incl);
+    if (lane == 31) base = atoms_add(a_tail_v, incl);
     base = __shfl_sync(0xffffffffu, base, 31);
     uint32_t aq = a_q + 2 * (base + incl - mine);
+    const uint32_t qv = aw - a_word;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       if (src & (0x80u << (8 * b))) {
-        sts16(aq, idx0 + b);
+        sts16(aq, qv + 4 * b);
         aq += 2;
       }
     }
   }
   __syncthreads();
-  // finish cell `idx` and hand its count downstream; returns true (and the downstream cell id in
-  // `nidx`) when that hand-off was the last one the downstream cell was waiting for
-  const uint32_t a_word0 = a_word + (WP + 1) * 4;         // word of cell (0,0)
-  const uint32_t a_cs0 = a_cs + ACS_W * ACS_Y0 + ACS_X0;  // code of cell (0,0)
-  auto finish = [&](uint32_t idx, uint32_t& nidx) -> bool {
-    const uint32_t yy = idx >> AT_SHIFT;
-    const uint32_t ow = idx * 4 + yy * 16;  // ((y+1)*WP + x+1)*4 relative to cell (0,0)
-    const uint32_t code = lds8(a_cs0 + idx + (ACS_W - AT) * yy);
-    const uint32_t s = lds32(a_word0 + ow) & 0x0FFFFFFFu;
-    const uint32_t lo = s + 1;
-    sts32(a_word0 + ow, lo);
-    if (code >= 8) return false;
-    const uint2 t = lds64(a_tab + 8 * code);
-    nidx = idx + t.y;
-    const uint32_t old = atoms_add(a_word0 + ow + t.x, lo - (1u << 28));
-    return (old >> 28) == 1;
-  };
 
   // ---- wide levels: level k is q[lo, hi); processing it appends level k+1 right after it
   uint32_t lo = 0, hi = lds32(a_tail);
@@ -377,10 +399,25 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
   while (hi - lo > WALK_PER_THREAD * ACC_THREADS) {
     for (uint32_t base = lo + 32 * warp; base < hi; base += ACC_THREADS) {
       const uint32_t i = base + lane;
-      uint32_t nidx = 0;
-      const bool ready = (i < hi) && finish(lds16(a_q + 2 * i), nidx);
-      // one slot per completed cell; ptxas turns these same-address atomics into one per warp
-      if (ready) sts16(a_q + 2 * atoms_add(a_tail, 1u), nidx);
+      uint32_t old = 0, an = 0;  // old == 0 reads as "nothing completed"
+      if (i < hi) {
+        const uint32_t aw = a_word + lds16(a_q + 2 * i);
+        const uint32_t wv = lds32(aw);
+        const uint32_t own = wv + W_FINISH;
+        sts32(aw, own);
+        if (wv & 0xFFu) {
+          an = word_next(aw, wv);
+          old = atoms_add(an, own & W_HANDOFF_MASK);
+        }
+      }
+      const bool ready = (old & W_READY_MASK) == W_READY_VAL;
+      const uint32_t bal = __ballot_sync(0xffffffffu, ready);
+      if (bal) {
+        uint32_t qb = 0;
+        if (lane == 0) qb = atoms_add(a_tail_v, __popc(bal));
+        qb = __shfl_sync(0xffffffffu, qb, 0);
+        if (ready) sts16(a_q + 2 * (qb + __popc(bal & lt_mask)), an - a_word);
+      }
     }
     __syncthreads();
     const uint32_t nh = lds32(a_tail);
@@ -388,102 +425,95 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     lo = hi;
     hi = nh;
   }
-  // ---- narrow tail (a level never grows): one thread per frontier cell follows its chain for as
-  //      long as its hand-off is the one that completes the next cell; no queue, no barriers.  The
-  //      atomic's return value already holds the next cell's running sum, so a step is one code load,
-  //      one table load, one store and one atomic.
+  // ---- narrow tail (a level never grows): one thread per frontier cell follows its chain for as long
+  //      as its hand-off is the one that completes the next cell; no queue, no barriers.  The atomic's
+  //      return value already is the next cell's word, so a step is one store and one atomic.
   for (uint32_t i = lo + tid; i < hi; i += ACC_THREADS) {
-    const uint32_t idx = lds16(a_q + 2 * i);
-    const uint32_t yy = idx >> AT_SHIFT;
-    uint32_t aw = a_word0 + idx * 4 + yy * 16;        // shared address of the cell's word
-    uint32_t ac = a_cs0 + idx + (ACS_W - AT) * yy;    // ... and of its code
-    uint32_t sum = lds32(aw) & 0x0FFFFFFFu;
+    uint32_t aw = a_word + lds16(a_q + 2 * i);
+    uint32_t wv = lds32(aw);
     for (;;) {
-      const uint32_t code = lds8(ac);
-      const uint32_t cnt = sum + 1;
-      sts32(aw, cnt);
-      if (code >= 8) break;
-      const uint2 t = lds64(sb + SM::TAB3 + 8 * code);  // {word byte offset, code byte offset}
-      aw += t.x;
-      ac += t.y;
-      const uint32_t old = atoms_add(aw, cnt - (1u << 28));
-      if ((old >> 28) != 1) break;
-      sum = (old & 0x0FFFFFFFu) + cnt;
+      const uint32_t own = wv + W_FINISH;
+      sts32(aw, own);
+      if (!(wv & 0xFFu)) break;
+      aw = word_next(aw, wv);
+      const uint32_t add = own & W_HANDOFF_MASK;
+      const uint32_t old = atoms_add(aw, add);
+      if ((old & W_READY_MASK) != W_READY_VAL) break;
+      wv = old + add;
     }
   }
-  __syncthreads();
 
+  // ---- Alg. 2: follow every perimeter cell to where its path leaves the tile.  Only the offset bytes and
+  //      live bits are read, which never change, so this runs while other warps still finish their chains.
+  const int s = tid;  // SLOTS == ACC_THREADS
+  int32_t succ = -1, own_target = -1;
+  uint16_t lk = KIND_TERM << 8;
+  uint32_t a_own = 0;
   {
-    // ---- Alg. 2: follow every perimeter cell to where its path leaves the tile; emit the reduced graph
-    const int s = tid;  // SLOTS == ACC_THREADS
     int y, x;
-    int32_t succ = -1;
-    uint16_t lk = KIND_TERM << 8;
     if (cell_of_slot(s, h, w, y, x)) {
-      // walk while the downstream cell is a live in-tile cell (codes 9 nodata, 13/14 live halo, 15 outside stop it)
-      uint32_t idx = y * AT + x;
-      uint32_t ca = a_cs0 + y * ACS_W + x;  // shared address of the current cell's code
-      uint32_t code = lds8(ca), dcode = 0;
-      int dy = 0, dx = 0;
-      for (int steps = 0; code < 8; ++steps) {
-        const uint2 t = lds64(sb + SM::TAB2 + 8 * code);
-        dcode = lds8(ca + t.x);
-        if (dcode > 8 || steps > AT * AT) break;
-        ca += t.x;
-        idx += t.y;
-        code = dcode;
+      uint32_t aw = a_word0 + (y * WP + x) * 4, an = 0;
+      a_own = aw;
+      uint32_t wv = lds32(aw);
+      bool exited = false;
+      int steps = 0;
+      if (wv & W_LIVE) {
+        while (wv & 0xFFu) {
+          an = word_next(aw, wv);
+          const uint32_t wn = lds32(an);
+          if (!(wn & W_LIVE)) {
+            exited = true;
+            break;
+          }
+          if (++steps > AT * AT) {
+            atomicExch(p.err, 2);  // ran out of steps: cycle inside the tile
+            break;
+          }
+          aw = an;
+          wv = wn;
+        }
       }
-      if (code < 8) {
-        dy = dir_dy(code);
-        dx = dir_dx(code);
-      }
-      const int cy = idx >> AT_SHIFT, cx = idx & (AT - 1);
+      // aw: the last live in-tile cell of the path; an: the word it steps to when the path leaves
+      const int j = (int)(aw - a_word) >> 2;
+      const int cy = j / WP - 1, cx = j - (cy + 1) * WP - WX0;
       uint16_t kind = KIND_TERM;
-      if (code < 8) {
+      if (exited) {
+        const int jn = (int)(an - a_word) >> 2;
+        const int ny = jn / WP - 1, nx = jn - (ny + 1) * WP - WX0;
+        const uint32_t dcode = lds8(a_cs0 + ny * ACS_W + nx);
         if (dcode == CODE_OUTSIDE) {
           kind = KIND_RASTER_EXIT;
         } else if (dcode == CODE_HALO_LIVE) {
           kind = KIND_TILE_EXIT;
-          succ = node_of_cell(y0 + cy + dy, x0 + cx + dx, p);
+          succ = node_of_cell(y0 + ny, x0 + nx, p);
+          // the perimeter cell's own edge across the tile boundary carries its local count to the next tile
+          if (steps == 0) own_target = succ;
         } else if (dcode == CODE_HALO_STRIP) {
           kind = KIND_STRIP_EXIT;
-        } else if (dcode != OFL_DIR_NODATA) {
-          atomicExch(p.err, 1);  // ran out of steps: cycle inside the tile
-        }
+        }  // else NODATA: the path ends in front of it
       }
       const int ls = slot_of(cy, cx, h, w);
       lk = (uint16_t)((ls < 0 ? 0 : ls) | (kind << 8));
-      // this cell's own edge across the tile boundary carries its local count to the next tile
-      const uint32_t own = lds8(a_cs0 + y * ACS_W + x);
-      if (own < 8) {
-        const int ny = y + dir_dy(own), nx = x + dir_dx(own);
-        if (ny < 0 || ny >= AT || nx < 0 || nx >= AT) {
-          if (lds8(a_cs0 + ny * ACS_W + nx) == CODE_HALO_LIVE) {
-            const uint32_t wv = lds32(a_word0 + (y * WP + x) * 4);
-            if (wv >> 28) atomicExch(p.err, 1);  // never finished: the tile holds a cycle
-            atomicAdd(&p.S[node_of_cell(y0 + ny, x0 + nx, p)], (unsigned long long)(wv & 0x0FFFFFFFu));
-          }
-        }
-      }
-    }
-    p.succ[(size_t)tile * SLOTS + s] = succ;
-    p.link[(size_t)tile * SLOTS + s] = lk;
-    // tile-local counts (<= 4096, fit 16 bits) for the final pass: tile-major, 16-byte vector stores
-    uint4* Lt = reinterpret_cast<uint4*>(p.L + (size_t)tile * (AT * AT));
-#pragma unroll
-    for (int g = tid; g < AT * AT / 8; g += ACC_THREADS) {
-      const uint32_t a = a_word0 + ((g >> 3) * WP + (g & 7) * 8) * 4;
-      uint32_t v[8], missing = 0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        v[k] = lds32(a + 4 * k);
-        missing |= v[k];
-        v[k] &= 0xFFFFu;
-      }
-      if (missing >> 28) atomicExch(p.err, 1);  // a cell never completed: the raster holds a cycle
-      Lt[g] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
     }
   }
+  __syncthreads();  // all chains are finished: counts are final
+
+  if (own_target >= 0) atomicAdd(&p.S[own_target], (unsigned long long)((lds32(a_own) >> 8) & 0x3FFFFu));
+  p.succ[(size_t)tile * SLOTS + s] = succ;
+  p.link[(size_t)tile * SLOTS + s] = lk;
+  // tile-local counts (<= 4096, fit 16 bits) for the final pass: tile-major, a warp stores 256 contiguous bytes
+  uint2* Lt = reinterpret_cast<uint2*>(p.L + (size_t)tile * (AT * AT));
+  uint32_t unfinished = 0;
+#pragma unroll
+  for (int g = tid; g < AT * AT / 4; g += ACC_THREADS) {
+    const uint4 v = lds128(a_word0 + ((g >> 4) * WP + (g & 15) * 4) * 4);
+    unfinished |= (~v.x >> 5) & v.x;  // bit 26: live and not visited
+    unfinished |= (~v.y >> 5) & v.y;
+    unfinished |= (~v.z >> 5) & v.z;
+    unfinished |= (~v.w >> 5) & v.w;
+    Lt[g] = make_uint2(prmt(v.x, v.y, 0x6521u), prmt(v.z, v.w, 0x6521u));
+  }
+  if (unfinished & W_LIVE) atomicExch(p.err, 1);  // a cell never completed: the raster holds a cycle
 }
 
 // ---------------------------------------------------------------- final pass
@@ -886,7 +916,7 @@ static int check_flags(const int* err_flags, cudaStream_t st) {
   int h[2] = {0, 0};
   OFL_CUDA(cudaMemcpyAsync(h, err_flags, sizeof(h), cudaMemcpyDeviceToHost, st));
   OFL_CUDA(cudaStreamSynchronize(st));
-  OFL_REQUIRE(h[0] == 0, OFL_ERR_CYCLE, "flow-direction raster contains a cycle");
+  OFL_REQUIRE(h[0] == 0, OFL_ERR_CYCLE, "flow-direction raster contains a cycle (tile flag %d)", h[0]);
   OFL_REQUIRE(h[1] == 0, OFL_ERR_CYCLE, "flow-direction raster contains a cycle (perimeter graph)");
   return OFL_OK;
 }
@@ -934,6 +964,13 @@ size_t accumulation_workspace_bytes(int64_t rows, int64_t cols) {
 size_t strip_workspace_bytes(int64_t rows, int64_t cols) {
   if (rows <= 0 || cols <= 0) return 256;
   return graph_layout(node_count(rows, cols), true).total;
+}
+
+// Zero [from_off, off_link) of the workspace (sums and delta buffers) and the error flags.
+static int ws_begin(uint8_t* ws, const GraphLayout& L, size_t from_off, cudaStream_t st) {
+  OFL_CUDA(cudaMemsetAsync(ws + from_off, 0, L.off_link - from_off, st));
+  OFL_CUDA(cudaMemsetAsync(ws + L.off_err, 0, 64, st));
+  return OFL_OK;
 }
 
 // Everything one raster (or strip) needs to launch its kernels.
@@ -1001,8 +1038,8 @@ int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t 
   int rc = acc_setup(C, fdr, rows, cols, ld_fdr, 0, 0, 0, fac, ld_fac, workspace, workspace_bytes, false);
   if (rc != OFL_OK) return rc;
   const GraphLayout& L = C.L;
-  OFL_CUDA(cudaMemsetAsync(C.ws + L.off_S, 0, L.off_link - L.off_S, st));  // S, d0, d1
-  OFL_CUDA(cudaMemsetAsync(C.p.err, 0, 64, st));
+  rc = ws_begin(C.ws, L, L.off_S, st);  // S, d0, d1
+  if (rc != OFL_OK) return rc;
   {
     PhaseScope ps(PHASE_ACC_TILE_A, st);
     acc_tile_kernel<<<(unsigned)C.ntiles, ACC_THREADS, TileSmem::BYTES, st>>>(C.tm, C.p);
@@ -1139,8 +1176,8 @@ int strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
   int rc = strip_setup(C, fdr_halo, rows, cols, ld_fdr, has_above, has_below, fac, ld_fac, workspace, workspace_bytes);
   if (rc != OFL_OK) return rc;
   const GraphLayout& L = C.L;
-  OFL_CUDA(cudaMemsetAsync(C.ws + L.off_S, 0, L.off_link - L.off_S, st));  // S, S2, d0, d1
-  OFL_CUDA(cudaMemsetAsync(C.p.err, 0, 64, st));
+  rc = ws_begin(C.ws, L, L.off_S, st);  // S, S2, d0, d1
+  if (rc != OFL_OK) return rc;
   {
     PhaseScope ps(PHASE_ACC_TILE_A, st);
     acc_tile_kernel<<<(unsigned)C.ntiles, ACC_THREADS, TileSmem::BYTES, st>>>(C.tm, C.p);
@@ -1211,8 +1248,8 @@ int strip_accum_final(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
   const GraphLayout& L = C.L;
   // inflow from other strips enters at the boundary rows; by linearity its effect on every perimeter
   // node is the subtree sum of those seeds over the strip's (preserved) perimeter forest
-  OFL_CUDA(cudaMemsetAsync(C.ws + L.off_S2, 0, L.off_link - L.off_S2, st));  // S2, d0, d1
-  OFL_CUDA(cudaMemsetAsync(C.p.err, 0, 64, st));
+  rc = ws_begin(C.ws, L, L.off_S2, st);  // S2, d0, d1
+  if (rc != OFL_OK) return rc;
   strip_seed_kernel<<<grid_for(2 * cols, 8), 256, 0, st>>>(J_mine, C.p, C.S2);
   OFL_CHECK_LAUNCH();
   {
