@@ -30,6 +30,7 @@
 // Edge rule (flow_accumulation.py:116-124): u -> c is an edge iff code(u) in 0..7, c lies
 // inside the raster and code(c) != 9.  Codes >= 8 have no downstream cell (the reference's
 // out-of-bounds NEIGHBOR_OFFSETS read); NODATA cells end at -9998 (:119-121,129-137).
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -129,7 +130,7 @@ __device__ __forceinline__ int node_of_cell(int gy, int gx, const AccParams& p) 
 // already holds that cell's offset and running sum.  No edge is ever skipped: hand-offs into the halo,
 // into NODATA cells or out of the raster land in words nobody schedules.
 // Frontier levels are consecutive segments of one 4096-entry queue of word addresses (a cell is appended
-// once).  A level never grows, so once it fits one cell per thread each thread simply follows its chain
+// once).  Halo words carry, in their offset byte, how a path that steps onto them continues (KIND_*).  A level never grows, so once it fits one cell per thread each thread simply follows its chain
 // (it continues exactly when its hand-off completed the next cell): no queue, no barriers.
 constexpr int WP = 72;                 // word-array pitch; cell x sits in column x + 4, so quads are 16-byte aligned
 constexpr int WX0 = 4;
@@ -153,15 +154,17 @@ constexpr uint32_t W_TAB_HI = (uint32_t)(uint8_t)(-1) | ((uint32_t)(uint8_t)(WP 
 #endif
 constexpr int WALK_PER_THREAD = OFL_WALK_PER_THREAD;  // switch to chain walking once a level has <= this many cells per thread
 
+// Shared memory (27.2 KB, eight CTAs per SM): the code tile is only read until the words are built, so the
+// frontier queue takes over its bytes afterwards.
 struct TileSmem {
-  static constexpr int CS = 0;
-  static constexpr int WORD = 6400;  // ACS_BYTES rounded up to 128
-  static constexpr int Q = WORD + WORDS * 4;
-  static constexpr int TAIL = Q + QMAX * 2;
+  static constexpr int CS = 0;                 // codes + halo (TMA destination) ...
+  static constexpr int Q = 0;                  // ... then the frontier queue
+  static constexpr int WORD = QMAX * 2;        // 8192
+  static constexpr int TAIL = WORD + WORDS * 4;  // [0] number of sources, [1] cells appended by the level loop
   static constexpr int BAR = TAIL + 16;
   static constexpr int BYTES = BAR + 16;
 };
-static_assert(ACS_BYTES <= 6400, "code tile does not fit its shared-memory slot");
+static_assert(ACS_BYTES <= QMAX * 2, "code tile does not fit the slot it shares with the queue");
 static_assert((WORDS * 4) % 16 == 0 && (WP * 4) % 16 == 0, "word rows must be whole uint4s");
 static_assert(WORDS * 4 < 65536, "queue entries are 16-bit byte offsets into the word array");
 
@@ -257,21 +260,14 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     mbar_fence_init();
     mbar_arrive_expect_tx(bar, ACS_BYTES);
     tma_load_2d(smem_raw + SM::CS, &tm, x0 - ACS_X0, y0 - ACS_Y0 + p.y_off, bar);
-    sts32(a_tail, 0);
-  }
-  // halo ring of the word array: zero (not live, so never scheduled); in-tile words are written in phase 1
-  if (tid < 2 * (WP / 4)) {
-    const int r = tid < WP / 4 ? 0 : AT + 1, c4 = tid < WP / 4 ? tid : tid - WP / 4;
-    sts128(a_word + (r * WP + 4 * c4) * 4, 0, 0, 0, 0);
-  } else if (tid < 2 * (WP / 4) + 2 * AT) {
-    const int k = tid - 2 * (WP / 4);
-    sts128(a_word + (((k >> 1) + 1) * WP + ((k & 1) ? WX0 + AT : 0)) * 4, 0, 0, 0, 0);
+    asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(a_tail), "r"(0u) : "memory");
   }
   __syncthreads();
   mbar_wait(bar, 0);
 
-  // ---- phase 0: invalid codes (>= 10) -> 8; halo ring -> {9 nodata, 14 live} so it can never look like
-  //      an in-tile upstream; then positions outside the raster (TMA zero fill) -> CODE_OUTSIDE
+  // ---- phase 0: invalid codes (>= 10) -> 8; halo ring: codes -> {9 nodata, 14 live} so it can never look
+  //      like an in-tile upstream, words -> how a path stepping there continues; then in-tile positions
+  //      outside the raster (TMA zero fill) -> CODE_OUTSIDE
   const int qx = lane & 15, rp = lane >> 4;
   constexpr int RWB = ACS_W;  // code row pitch in bytes
 #pragma unroll
@@ -290,38 +286,39 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
       sts32(a, f);
     }
   }
-  for (int t = tid; t < 4 * AT + 4; t += ACC_THREADS) {
-    int hy, hx;  // halo position in tile coordinates (-1..64)
-    if (t < AT) {
-      hy = -1;
-      hx = t;
-    } else if (t < 2 * AT) {
-      hy = AT;
-      hx = t - AT;
-    } else if (t < 3 * AT) {
-      hy = t - 2 * AT;
-      hx = -1;
-    } else if (t < 4 * AT) {
-      hy = t - 3 * AT;
-      hx = AT;
-    } else {
-      hy = (t & 1) ? AT : -1;
-      hx = (t & 2) ? AT : -1;
+  {
+    // thread t < 256: side t >> 6 (top, bottom, left, right), position t & 63; the four threads with
+    // position 0 also take one corner each
+    const int side = tid >> AT_SHIFT, k = tid & (AT - 1);
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      int hy, hx;  // halo position in tile coordinates (-1..64)
+      if (pass == 0) {
+        hy = side == 0 ? -1 : side == 1 ? AT : k;
+        hx = side == 2 ? -1 : side == 3 ? AT : k;
+      } else {
+        if (k != 0) break;
+        hy = (side & 1) ? AT : -1;
+        hx = (side & 2) ? AT : -1;
+      }
+      const uint32_t a = a_cs + (hy + ACS_Y0) * RWB + hx + ACS_X0;
+      const int gy = y0 + hy, gx = x0 + hx;
+      const bool nodata = lds8(a) == OFL_DIR_NODATA;
+      uint32_t c, kind;
+      if (gx < 0 || gx >= p.cols) {
+        c = CODE_OUTSIDE;
+        kind = KIND_RASTER_EXIT;
+      } else if (gy < 0 || gy >= p.rows) {
+        const bool strip = gy < 0 ? p.strip_above : p.strip_below;
+        c = strip ? (nodata ? (uint32_t)OFL_DIR_NODATA : (uint32_t)CODE_HALO_STRIP) : (uint32_t)CODE_OUTSIDE;
+        kind = strip ? (nodata ? KIND_TERM : KIND_STRIP_EXIT) : KIND_RASTER_EXIT;
+      } else {
+        c = nodata ? (uint32_t)OFL_DIR_NODATA : (uint32_t)CODE_HALO_LIVE;
+        kind = nodata ? KIND_TERM : KIND_TILE_EXIT;
+      }
+      sts8(a, c);
+      sts32(a_word + ((hy + 1) * WP + hx + WX0) * 4, kind);  // not live: absorbs hand-offs, never scheduled
     }
-    const uint32_t a = a_cs + (hy + ACS_Y0) * RWB + hx + ACS_X0;
-    const int gy = y0 + hy, gx = x0 + hx;
-    const bool nodata = lds8(a) == OFL_DIR_NODATA;
-    uint32_t c;
-    if (gx < 0 || gx >= p.cols) {
-      c = CODE_OUTSIDE;
-    } else if (gy < 0) {
-      c = p.strip_above ? (nodata ? (uint32_t)OFL_DIR_NODATA : (uint32_t)CODE_HALO_STRIP) : (uint32_t)CODE_OUTSIDE;
-    } else if (gy >= p.rows) {
-      c = p.strip_below ? (nodata ? (uint32_t)OFL_DIR_NODATA : (uint32_t)CODE_HALO_STRIP) : (uint32_t)CODE_OUTSIDE;
-    } else {
-      c = nodata ? (uint32_t)OFL_DIR_NODATA : (uint32_t)CODE_HALO_LIVE;
-    }
-    sts8(a, c);
   }
   if (h < AT || w < AT) {
     // partial tile at the raster's bottom / right edge: in-tile positions beyond the raster
@@ -338,10 +335,11 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
   // atomics alone instead of wrapping each in its own warp-aggregation sequence
   const uint32_t a_tail_v = a_tail + (lt_mask >> 31);
   const uint32_t a_word0 = a_word + (WP + WX0) * 4;       // word of cell (0,0)
-  const uint32_t a_cs0 = a_cs + ACS_W * ACS_Y0 + ACS_X0;  // code of cell (0,0)
 
-  // ---- phase 1: missing-counts for four cells at a time (byte-parallel), the four words, sources into
-  //      the queue.  Lane owns the quad of columns 4*qx..4*qx+3 in rows 8*warp + 2*i + rp.
+  // ---- phase 1: missing-counts for four cells at a time (byte-parallel) and the four words.
+  //      Lane owns the quad of columns 4*qx..4*qx+3 in rows 8*warp + 2*i + rp.
+  uint32_t srcs[4];
+  const uint32_t aw_lane = a_word0 + ((8 * warp + rp) * WP + 4 * qx) * 4;  // first quad; the next ones are 2 rows apart
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int y = 8 * warp + 2 * i + rp;
@@ -361,17 +359,21 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     const uint32_t cnt4 = 0x08080808u - nm;  // missing upstream neighbours per cell
     const uint32_t dead = C1 + 0x77777777u;  // bit 7 of a byte set: code >= 9, not a data cell
     // source: missing == 0 and the cell is a data cell (own code <= 8)
-    const uint32_t src = ~((cnt4 + 0x7F7F7F7Fu) | dead) & 0x80808080u;
+    srcs[i] = ~((cnt4 + 0x7F7F7F7Fu) | dead) & 0x80808080u;
     // the four words: offsets by a byte-wise table lookup on the codes (codes >= 8 select in PRMT's
     // sign-replicate mode: code 8 -> sign of +1 -> 0 = no downstream; code >= 9 -> garbage in a word that
     // is never scheduled), top bytes [missing << 3 | live << 2]; one PRMT assembles each word
     const uint32_t nib = C1 | (C1 >> 4);
     const uint32_t off4 = prmt(W_TAB_LO, W_TAB_HI, prmt(nib, 0u, 0x4420u));
     const uint32_t hi4 = (cnt4 << 3) | ((~dead >> 5) & 0x04040404u);
-    const uint32_t aw = a_word0 + (y * WP + 4 * qx) * 4;
-    sts128(aw, prmt(off4, hi4, 0x4CC0u), prmt(off4, hi4, 0x5DD1u), prmt(off4, hi4, 0x6EE2u), prmt(off4, hi4, 0x7FF3u));
-    // append this warp's sources: exclusive scan of per-lane source counts, one queue atomic per warp
-    const uint32_t mine = __popc(src);
+    sts128(aw_lane + i * (2 * WP * 4), prmt(off4, hi4, 0x4CC0u), prmt(off4, hi4, 0x5DD1u), prmt(off4, hi4, 0x6EE2u),
+           prmt(off4, hi4, 0x7FF3u));
+  }
+  __syncthreads();  // every word is built; the code tile is dead from here and the queue takes its place
+
+  // ---- sources into the queue: one exclusive scan of the per-lane source counts, one queue atomic per warp
+  {
+    const uint32_t mine = __popc(srcs[0]) + __popc(srcs[1]) + __popc(srcs[2]) + __popc(srcs[3]);
     uint32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -382,45 +384,54 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     if (lane == 31) base = atoms_add(a_tail_v, incl);
     base = __shfl_sync(0xffffffffu, base, 31);
     uint32_t aq = a_q + 2 * (base + incl - mine);
-    const uint32_t qv = aw - a_word;
+    const uint32_t qv = aw_lane - a_word;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      if (src & (0x80u << (8 * b))) {
-        sts16(aq, qv + 4 * b);
-        aq += 2;
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (srcs[i] & (0x80u << (8 * b))) {
+          sts16(aq, qv + i * (2 * WP * 4) + 4 * b);
+          aq += 2;
+        }
       }
     }
   }
   __syncthreads();
 
-  // ---- wide levels: level k is q[lo, hi); processing it appends level k+1 right after it
-  uint32_t lo = 0, hi = lds32(a_tail);
-  __syncthreads();
+  // ---- wide levels: level k is q[lo, hi); processing it appends level k+1 right after it.  A warp takes
+  //      64 entries per turn, two per lane, and reserves queue slots for both with one atomic.
+  const uint32_t n_src = lds32(a_tail);  // final: the level loop appends through the second counter
+  uint32_t lo = 0, hi = n_src;
   while (hi - lo > WALK_PER_THREAD * ACC_THREADS) {
-    for (uint32_t base = lo + 32 * warp; base < hi; base += ACC_THREADS) {
-      const uint32_t i = base + lane;
-      uint32_t old = 0, an = 0;  // old == 0 reads as "nothing completed"
-      if (i < hi) {
-        const uint32_t aw = a_word + lds16(a_q + 2 * i);
-        const uint32_t wv = lds32(aw);
-        const uint32_t own = wv + W_FINISH;
-        sts32(aw, own);
-        if (wv & 0xFFu) {
-          an = word_next(aw, wv);
-          old = atoms_add(an, own & W_HANDOFF_MASK);
+    for (uint32_t base = lo + 64 * warp; base < hi; base += 2 * ACC_THREADS) {
+      uint32_t old[2] = {0, 0}, an[2] = {0, 0};  // old == 0 reads as "nothing completed"
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const uint32_t i = base + 32 * e + lane;
+        if (i < hi) {
+          const uint32_t aw = a_word + lds16(a_q + 2 * i);
+          const uint32_t wv = lds32(aw);
+          const uint32_t own = wv + W_FINISH;
+          sts32(aw, own);
+          if (wv & 0xFFu) {
+            an[e] = word_next(aw, wv);
+            old[e] = atoms_add(an[e], own & W_HANDOFF_MASK);
+          }
         }
       }
-      const bool ready = (old & W_READY_MASK) == W_READY_VAL;
-      const uint32_t bal = __ballot_sync(0xffffffffu, ready);
-      if (bal) {
+      const bool r0 = (old[0] & W_READY_MASK) == W_READY_VAL, r1 = (old[1] & W_READY_MASK) == W_READY_VAL;
+      const uint32_t b0 = __ballot_sync(0xffffffffu, r0), b1 = __ballot_sync(0xffffffffu, r1);
+      if (b0 | b1) {
+        const uint32_t n0 = __popc(b0);
         uint32_t qb = 0;
-        if (lane == 0) qb = atoms_add(a_tail_v, __popc(bal));
-        qb = __shfl_sync(0xffffffffu, qb, 0);
-        if (ready) sts16(a_q + 2 * (qb + __popc(bal & lt_mask)), an - a_word);
+        if (lane == 0) qb = atoms_add(a_tail_v + 4, n0 + __popc(b1));
+        qb = n_src + __shfl_sync(0xffffffffu, qb, 0);
+        if (r0) sts16(a_q + 2 * (qb + __popc(b0 & lt_mask)), an[0] - a_word);
+        if (r1) sts16(a_q + 2 * (qb + n0 + __popc(b1 & lt_mask)), an[1] - a_word);
       }
     }
     __syncthreads();
-    const uint32_t nh = lds32(a_tail);
+    const uint32_t nh = n_src + lds32(a_tail + 4);
     __syncthreads();  // nobody appends to the next level before everyone has read where this one ends
     lo = hi;
     hi = nh;
@@ -454,13 +465,13 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     if (cell_of_slot(s, h, w, y, x)) {
       uint32_t aw = a_word0 + (y * WP + x) * 4, an = 0;
       a_own = aw;
-      uint32_t wv = lds32(aw);
+      uint32_t wv = lds32(aw), wn = 0;
       bool exited = false;
       int steps = 0;
       if (wv & W_LIVE) {
         while (wv & 0xFFu) {
           an = word_next(aw, wv);
-          const uint32_t wn = lds32(an);
+          wn = lds32(an);
           if (!(wn & W_LIVE)) {
             exited = true;
             break;
@@ -473,24 +484,24 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
           wv = wn;
         }
       }
-      // aw: the last live in-tile cell of the path; an: the word it steps to when the path leaves
+      // aw: the last live in-tile cell of the path; an / wn: the word it steps to when the path leaves
       const int j = (int)(aw - a_word) >> 2;
       const int cy = j / WP - 1, cx = j - (cy + 1) * WP - WX0;
-      uint16_t kind = KIND_TERM;
+      uint32_t kind = KIND_TERM;
       if (exited) {
         const int jn = (int)(an - a_word) >> 2;
         const int ny = jn / WP - 1, nx = jn - (ny + 1) * WP - WX0;
-        const uint32_t dcode = lds8(a_cs0 + ny * ACS_W + nx);
-        if (dcode == CODE_OUTSIDE) {
-          kind = KIND_RASTER_EXIT;
-        } else if (dcode == CODE_HALO_LIVE) {
-          kind = KIND_TILE_EXIT;
-          succ = node_of_cell(y0 + ny, x0 + nx, p);
-          // the perimeter cell's own edge across the tile boundary carries its local count to the next tile
-          if (steps == 0) own_target = succ;
-        } else if (dcode == CODE_HALO_STRIP) {
-          kind = KIND_STRIP_EXIT;
-        }  // else NODATA: the path ends in front of it
+        if ((uint32_t)ny < (uint32_t)AT && (uint32_t)nx < (uint32_t)AT) {
+          // a dead in-tile cell: NODATA (the path ends in front of it) or beyond the raster's edge
+          kind = (ny < h && nx < w) ? KIND_TERM : KIND_RASTER_EXIT;
+        } else {
+          kind = wn & 0xFFu;  // the halo word says how the path continues
+          if (kind == KIND_TILE_EXIT) {
+            succ = node_of_cell(y0 + ny, x0 + nx, p);
+            // the perimeter cell's own edge across the tile boundary carries its local count to the next tile
+            if (steps == 0) own_target = succ;
+          }
+        }
       }
       const int ls = slot_of(cy, cx, h, w);
       lk = (uint16_t)((ls < 0 ? 0 : ls) | (kind << 8));
@@ -845,11 +856,19 @@ int64_t perimeter_count(int64_t rows, int64_t cols) {
 
 constexpr int PJ_MAX_ROUNDS = 40;
 
+static int tile_extra_smem() {
+  static int extra = -1;
+  if (extra < 0) {
+    const char* e = getenv("OFL_ACC_EXTRA_SMEM");
+    extra = e ? atoi(e) : 0;
+  }
+  return extra;
+}
 static int ensure_tile_attrs() {
   static bool attr_set = false;
   if (!attr_set) {
     OFL_CUDA(cudaFuncSetAttribute(acc_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  TileSmem::BYTES));
+                                  TileSmem::BYTES + tile_extra_smem()));
     OFL_CUDA(cudaFuncSetAttribute(acc_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FinalSmem::BYTES));
     attr_set = true;
   }
@@ -1042,7 +1061,7 @@ int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t 
   if (rc != OFL_OK) return rc;
   {
     PhaseScope ps(PHASE_ACC_TILE_A, st);
-    acc_tile_kernel<<<(unsigned)C.ntiles, ACC_THREADS, TileSmem::BYTES, st>>>(C.tm, C.p);
+    acc_tile_kernel<<<(unsigned)C.ntiles, ACC_THREADS, TileSmem::BYTES + tile_extra_smem(), st>>>(C.tm, C.p);
   }
   OFL_CHECK_LAUNCH();
   {
@@ -1180,7 +1199,7 @@ int strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
   if (rc != OFL_OK) return rc;
   {
     PhaseScope ps(PHASE_ACC_TILE_A, st);
-    acc_tile_kernel<<<(unsigned)C.ntiles, ACC_THREADS, TileSmem::BYTES, st>>>(C.tm, C.p);
+    acc_tile_kernel<<<(unsigned)C.ntiles, ACC_THREADS, TileSmem::BYTES + tile_extra_smem(), st>>>(C.tm, C.p);
   }
   OFL_CHECK_LAUNCH();
   {
