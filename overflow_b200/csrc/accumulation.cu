@@ -160,9 +160,10 @@ struct TileSmem {
   static constexpr int CS = 0;                 // codes + halo (TMA destination) ...
   static constexpr int Q = 0;                  // ... then the frontier queue
   static constexpr int WORD = QMAX * 2;        // 8192
-  static constexpr int TAIL = WORD + WORDS * 4;  // [0] number of sources, [1] cells appended by the level loop
+  static constexpr int TAIL = WORD + WORDS * 4;  // [0] number of sources, [1] cells appended by the level loop, [2] paths to follow
   static constexpr int BAR = TAIL + 16;
-  static constexpr int BYTES = BAR + 16;
+  static constexpr int LIST = BAR + 16;        // perimeter slots whose path has to be followed (u8 each)
+  static constexpr int BYTES = LIST + SLOTS;
 };
 static_assert(ACS_BYTES <= QMAX * 2, "code tile does not fit the slot it shares with the queue");
 static_assert((WORDS * 4) % 16 == 0 && (WP * 4) % 16 == 0, "word rows must be whole uint4s");
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     mbar_fence_init();
     mbar_arrive_expect_tx(bar, ACS_BYTES);
     tma_load_2d(smem_raw + SM::CS, &tm, x0 - ACS_X0, y0 - ACS_Y0 + p.y_off, bar);
-    asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(a_tail), "r"(0u) : "memory");
+    sts128(a_tail, 0, 0, 0, 0);
   }
   __syncthreads();
   mbar_wait(bar, 0);
@@ -316,8 +317,12 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
         c = nodata ? (uint32_t)OFL_DIR_NODATA : (uint32_t)CODE_HALO_LIVE;
         kind = nodata ? KIND_TERM : KIND_TILE_EXIT;
       }
+      // the halo word (not live: absorbs hand-offs, never scheduled) keeps, in its offset byte, how a path
+      // stepping onto it continues and which way the cell there flows (8: nowhere / not a cell)
+      const uint32_t raw = lds8(a);
+      const uint32_t hcode = (kind == KIND_RASTER_EXIT || raw > 8) ? 8u : raw;
       sts8(a, c);
-      sts32(a_word + ((hy + 1) * WP + hx + WX0) * 4, kind);  // not live: absorbs hand-offs, never scheduled
+      sts32(a_word + ((hy + 1) * WP + hx + WX0) * 4, kind | (hcode << 2));
     }
   }
   if (h < AT || w < AT) {
@@ -396,6 +401,56 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
       }
     }
   }
+  // ---- Alg. 2, part 1 (words are static from here on in everything it reads).  Thread = perimeter slot.
+  //      A perimeter cell's path only has to be followed when something can arrive at the cell from outside
+  //      the tile -- a neighbouring tile's (or strip's) cell flows into it -- or when the cell lies on the
+  //      raster's (strip's) edge, whose links the callers ask for.  Those slots are compacted into a list;
+  //      every other slot gets its final "no successor" entry right away.
+  int32_t own_target = -1;
+  uint32_t a_own;
+  {
+    const int side = tid >> AT_SHIFT, k = tid & (AT - 1);
+    const int py = side == 0 ? 0 : side == 1 ? h - 1 : k;
+    const int px = side == 2 ? 0 : side == 3 ? w - 1 : k;
+    const bool valid = side < 2 ? (k < w && (side == 0 || h > 1)) : (k > 0 && k < h - 1 && (side == 2 || w > 1));
+    a_own = a_word0 + (py * WP + px) * 4;
+    const uint32_t w_own = lds32(a_own);
+    const bool live = valid && (w_own & W_LIVE);
+    // does the cell at (py, px) + direction d lie outside the tile box and flow back into this cell?
+    auto inflow = [&](int d) -> bool {
+      const int ny = py + dir_dy(d), nx = px + dir_dx(d);
+      if ((uint32_t)ny < (uint32_t)AT && (uint32_t)nx < (uint32_t)AT) return false;
+      return (lds8(a_word + ((ny + 1) * WP + nx + WX0) * 4) >> 2) == (uint32_t)((d + 4) & 7);
+    };
+    const int d0 = (0x7351 >> (4 * side)) & 7;  // the three directions pointing out of this side: from NE, SW, NW, SE on
+    bool target = inflow(d0) | inflow((d0 + 1) & 7) | inflow((d0 + 2) & 7);
+    if (side < 2 && (k == 0 || k == w - 1)) {  // corner: the two directions of the adjoining side
+      const int e = k == 0 ? 4 : 0;
+      target |= inflow(e) | inflow(k == 0 ? (side == 0 ? 5 : 3) : (side == 0 ? 7 : 1));
+    }
+    const int gy = y0 + py, gx = x0 + px;
+    const bool edge = gy == 0 || gy == p.rows - 1 || gx == 0 || gx == p.cols - 1;
+    // the cell's own edge across the tile boundary carries its local count to the next tile
+    if (live && (w_own & 0xFFu)) {
+      const uint32_t an = word_next(a_own, w_own);
+      const uint32_t wn = lds32(an);
+      const int jn = (int)(an - a_word) >> 2;
+      const int ny = jn / WP - 1, nx = jn - (ny + 1) * WP - WX0;
+      if (!((uint32_t)ny < (uint32_t)AT && (uint32_t)nx < (uint32_t)AT) && (wn & 3u) == KIND_TILE_EXIT)
+        own_target = node_of_cell(y0 + ny, x0 + nx, p);
+    }
+    const bool follow = live && (target || edge);
+    const uint32_t bal = __ballot_sync(0xffffffffu, follow);
+    uint32_t lb = 0;
+    if (lane == 0 && bal) lb = atoms_add(a_tail_v + 8, __popc(bal));
+    lb = __shfl_sync(0xffffffffu, lb, 0);
+    if (follow) {
+      sts8(sb + SM::LIST + lb + __popc(bal & lt_mask), tid);
+    } else {
+      p.succ[(size_t)tile * SLOTS + tid] = -1;
+      p.link[(size_t)tile * SLOTS + tid] = (uint16_t)((valid ? tid : 0) | (KIND_TERM << 8));
+    }
+  }
   __syncthreads();
 
   // ---- wide levels: level k is q[lo, hi); processing it appends level k+1 right after it.  A warp takes
@@ -454,40 +509,44 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     }
   }
 
-  // ---- Alg. 2: follow every perimeter cell to where its path leaves the tile.  Only the offset bytes and
+  // ---- Alg. 2, part 2: follow the listed paths to where they leave the tile, one thread per path, taken
+  //      from the high thread ids (the chain walking above keeps the low ones busy).  Only offset bytes and
   //      live bits are read, which never change, so this runs while other warps still finish their chains.
-  const int s = tid;  // SLOTS == ACC_THREADS
-  int32_t succ = -1, own_target = -1;
-  uint16_t lk = KIND_TERM << 8;
-  uint32_t a_own = 0;
   {
-    int y, x;
-    if (cell_of_slot(s, h, w, y, x)) {
-      uint32_t aw = a_word0 + (y * WP + x) * 4, an = 0;
-      a_own = aw;
-      uint32_t wv = lds32(aw), wn = 0;
-      bool exited = false;
-      int steps = 0;
-      if (wv & W_LIVE) {
-        while (wv & 0xFFu) {
-          an = word_next(aw, wv);
-          wn = lds32(an);
-          if (!(wn & W_LIVE)) {
-            exited = true;
-            break;
-          }
-          if (++steps > AT * AT) {
-            atomicExch(p.err, 2);  // ran out of steps: cycle inside the tile
-            break;
-          }
-          aw = an;
-          wv = wn;
+    const uint32_t t = ACC_THREADS - 1 - tid;
+    const bool walker = t < lds32(a_tail + 8);
+    uint32_t slot = 0, aw = 0, an = 0, wn = 0;
+    bool exited = false;
+    int steps = 0;
+    if (walker) {
+      slot = lds8(sb + SM::LIST + t);
+      const int side = slot >> AT_SHIFT, k = slot & (AT - 1);
+      const int py = side == 0 ? 0 : side == 1 ? h - 1 : k;
+      const int px = side == 2 ? 0 : side == 3 ? w - 1 : k;
+      aw = a_word0 + (py * WP + px) * 4;
+      uint32_t wv = lds32(aw);
+      while (wv & 0xFFu) {
+        an = word_next(aw, wv);
+        wn = lds32(an);
+        if (!(wn & W_LIVE)) {
+          exited = true;
+          break;
         }
+        if (++steps > AT * AT) {
+          atomicExch(p.err, 2);  // ran out of steps: cycle inside the tile
+          break;
+        }
+        aw = an;
+        wv = wn;
       }
+    }
+    __syncwarp();  // classify once per warp, not once per exit path
+    if (walker) {
       // aw: the last live in-tile cell of the path; an / wn: the word it steps to when the path leaves
       const int j = (int)(aw - a_word) >> 2;
       const int cy = j / WP - 1, cx = j - (cy + 1) * WP - WX0;
       uint32_t kind = KIND_TERM;
+      int32_t succ = -1;
       if (exited) {
         const int jn = (int)(an - a_word) >> 2;
         const int ny = jn / WP - 1, nx = jn - (ny + 1) * WP - WX0;
@@ -495,23 +554,18 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
           // a dead in-tile cell: NODATA (the path ends in front of it) or beyond the raster's edge
           kind = (ny < h && nx < w) ? KIND_TERM : KIND_RASTER_EXIT;
         } else {
-          kind = wn & 0xFFu;  // the halo word says how the path continues
-          if (kind == KIND_TILE_EXIT) {
-            succ = node_of_cell(y0 + ny, x0 + nx, p);
-            // the perimeter cell's own edge across the tile boundary carries its local count to the next tile
-            if (steps == 0) own_target = succ;
-          }
+          kind = wn & 3u;  // the halo word says how the path continues
+          if (kind == KIND_TILE_EXIT) succ = node_of_cell(y0 + ny, x0 + nx, p);
         }
       }
       const int ls = slot_of(cy, cx, h, w);
-      lk = (uint16_t)((ls < 0 ? 0 : ls) | (kind << 8));
+      p.succ[(size_t)tile * SLOTS + slot] = succ;
+      p.link[(size_t)tile * SLOTS + slot] = (uint16_t)((ls < 0 ? 0 : ls) | (kind << 8));
     }
   }
   __syncthreads();  // all chains are finished: counts are final
 
   if (own_target >= 0) atomicAdd(&p.S[own_target], (unsigned long long)((lds32(a_own) >> 8) & 0x3FFFFu));
-  p.succ[(size_t)tile * SLOTS + s] = succ;
-  p.link[(size_t)tile * SLOTS + s] = lk;
   // tile-local counts (<= 4096, fit 16 bits) for the final pass: tile-major, a warp stores 256 contiguous bytes
   uint2* Lt = reinterpret_cast<uint2*>(p.L + (size_t)tile * (AT * AT));
   uint32_t unfinished = 0;
