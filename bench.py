@@ -321,8 +321,7 @@ def run_native(args):
 
     # ---- end to end through the public host API: pinned host buffers, H2D + D2H inside the timed region
     if world == 1 and not args.no_e2e:
-        from overflow_b200.flow_accumulation import flow_accumulation_for_raster
-        from overflow_b200.flow_direction import flow_direction_for_raster
+        from overflow_b200.flow_routing import flow_routing_for_raster
 
         h_dem = torch.empty((S, S), dtype=torch.float32, pin_memory=True)
         h_dem.copy_(dem)
@@ -333,8 +332,7 @@ def run_native(args):
         n_dem, n_fdr, n_fac = h_dem.numpy(), h_fdr.numpy(), h_fac.numpy()
 
         def e2e_step():
-            flow_direction_for_raster(n_dem, NODATA, out=n_fdr)
-            flow_accumulation_for_raster(n_fdr, out=n_fac)
+            flow_routing_for_raster(n_dem, NODATA, out_fdr=n_fdr, out_fac=n_fac)
 
         e2e_step()  # warm-up: allocates the library's device staging
         torch.cuda.synchronize()
@@ -345,9 +343,10 @@ def run_native(args):
         el = (time.perf_counter() - t0) / args.e2e_steps
         line["e2e"] = {
             "value": cells_total / el / 1e9, "unit": UNIT,
-            "h2d_bytes_per_step": int(cells_total * 4 + cells_total), "d2h_bytes_per_step": int(cells_total + cells_total * 8),
+            "h2d_bytes_per_step": int(cells_total * 4), "d2h_bytes_per_step": int(cells_total + cells_total * 8),
             "ms_per_step": el * 1e3, "steps": args.e2e_steps,
-            "api": "flow_direction_for_raster + flow_accumulation_for_raster on pinned host arrays",
+            "api": "overflow_b200.flow_routing.flow_routing_for_raster (C ABI ofl_flow_routing_f32, OFL_MEM_HOST) on pinned "
+                   "host arrays: DEM in, codes and counts out",
         }
     elif world > 1 and not args.no_e2e:
         # every rank streams its strip from / to pinned host memory around the distributed step

@@ -136,6 +136,18 @@ int ofl_flow_accumulation_u8(const uint8_t* fdr, int64_t rows, int64_t cols, int
                              int mem_kind, void* stream);
 
 /*
+ * Both steps in one call: flow direction of a whole DEM (RASTER semantics: every cell computed,
+ * out-of-raster neighbours read as nodata -- what flow_direction() writes for the file,
+ * flow_direction.py:99-124 with util/raster.py:67) followed by flow accumulation of those codes.
+ * Host rasters are uploaded in row bands that overlap the stencil and the download of the codes, and
+ * the codes never make the round trip through the host that two separate calls need.
+ *   fdr   uint8 out, nullable for host callers that only want the counts
+ * Alignment contracts as for the two functions above.  Synchronous with respect to the host.
+ */
+int ofl_flow_routing_f32(const float* dem, int64_t rows, int64_t cols, int64_t ld_dem, double nodata, uint8_t* fdr,
+                         int64_t ld_fdr, int64_t* fac, int64_t ld_fac, int64_t* perim_links, int mem_kind, void* stream);
+
+/*
  * Exactness check: counts cells where fac != 1 + sum(fac of upstream neighbours) (data cells) or
  * fac != -9998 (NODATA cells).  On an acyclic raster zero violations prove fac is THE answer.
  */

@@ -1,5 +1,7 @@
 // api.cu -- the extern "C" surface declared in include/overflow_b200.h.
 // Host-pointer calls stage through library-owned device buffers; device-pointer calls launch directly.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ofl {
@@ -38,6 +40,75 @@ int launch_synth(float* dem, int64_t rows, int64_t cols, int64_t ld, int64_t row
 using namespace ofl;
 
 static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------- host rasters: banded pipeline
+// A host DEM goes to the device in row bands on its own stream; the stencil of band b runs as soon as
+// the first row of band b+1 has arrived, and its codes return to the host on a third stream, so the
+// upload, the kernel and the download overlap (PCIe is full duplex).  The staging buffers hold the whole
+// raster: accumulation needs every code before it can finish a single count.
+namespace {
+struct HostPipe {
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+};
+HostPipe g_pipe;
+
+int pipe_streams() {
+  if (!g_pipe.h2d) OFL_CUDA(cudaStreamCreateWithFlags(&g_pipe.h2d, cudaStreamNonBlocking));
+  if (!g_pipe.d2h) OFL_CUDA(cudaStreamCreateWithFlags(&g_pipe.d2h, cudaStreamNonBlocking));
+  return OFL_OK;
+}
+
+constexpr int64_t PIPE_BAND_BYTES = 512ll << 20;  // ~0.5 GiB of DEM per band
+constexpr int PIPE_MAX_BANDS = 256;
+
+// dem: host, in_rows x cols.  d_dem / d_fdr: device staging (pitches ldd / ldo).  fdr_host may be null.
+// Output row y reads input rows y + y_off - 1 .. y + y_off + 1.  On return every stream is idle.
+int direction_from_host(const float* dem, int64_t in_rows, int64_t rows, int64_t cols, int64_t ld_dem, double nodata,
+                        int y_off, float* d_dem, int64_t ldd, uint8_t* d_fdr, int64_t ldo, uint8_t* fdr_host,
+                        int64_t ld_fdr, cudaStream_t st, bool sync_downloads) {
+  int rc = pipe_streams();
+  if (rc != OFL_OK) return rc;
+  int64_t band_bytes = PIPE_BAND_BYTES;
+  if (const char* e = getenv("OFL_PIPE_BAND_BYTES")) band_bytes = atoll(e) > 0 ? atoll(e) : band_bytes;  // tests: many small bands
+  int64_t band = band_bytes / (cols * (int64_t)sizeof(float));
+  band = band < 64 ? 64 : band / 64 * 64;
+  if ((in_rows + band - 1) / band > PIPE_MAX_BANDS) band = ((in_rows + PIPE_MAX_BANDS - 1) / PIPE_MAX_BANDS + 63) / 64 * 64;
+  const int n_in = (int)((in_rows + band - 1) / band), n_out = (int)((rows + band - 1) / band);
+  cudaEvent_t ev_up[PIPE_MAX_BANDS], ev_dir[PIPE_MAX_BANDS];
+  for (int b = 0; b < n_in; ++b) OFL_CUDA(cudaEventCreateWithFlags(&ev_up[b], cudaEventDisableTiming));
+  for (int b = 0; b < n_out; ++b) OFL_CUDA(cudaEventCreateWithFlags(&ev_dir[b], cudaEventDisableTiming));
+  for (int b = 0; b < n_in; ++b) {
+    const int64_t r0 = b * band, r1 = (r0 + band < in_rows) ? r0 + band : in_rows;
+    OFL_CUDA(cudaMemcpy2DAsync(d_dem + r0 * ldd, ldd * sizeof(float), dem + r0 * ld_dem, ld_dem * sizeof(float),
+                               cols * sizeof(float), r1 - r0, cudaMemcpyHostToDevice, g_pipe.h2d));
+    OFL_CUDA(cudaEventRecord(ev_up[b], g_pipe.h2d));
+  }
+  for (int b = 0; b < n_out && rc == OFL_OK; ++b) {
+    const int64_t r0 = b * band, r1 = (r0 + band < rows) ? r0 + band : rows;
+    int64_t in_lo = r0 + y_off - 1, in_hi = r1 + y_off + 1;  // input rows [in_lo, in_hi)
+    if (in_lo < 0) in_lo = 0;
+    if (in_hi > in_rows) in_hi = in_rows;
+    OFL_CUDA(cudaStreamWaitEvent(st, ev_up[(in_hi - 1) / band], 0));  // uploads complete in order
+    rc = launch_direction(d_dem + in_lo * ldd, in_hi - in_lo, cols, ldd, nodata, d_fdr + r0 * ldo, r1 - r0, ldo,
+                          (int)(r0 + y_off - in_lo), st);
+    if (rc != OFL_OK) break;
+    if (fdr_host) {
+      OFL_CUDA(cudaEventRecord(ev_dir[b], st));
+      OFL_CUDA(cudaStreamWaitEvent(g_pipe.d2h, ev_dir[b], 0));
+      OFL_CUDA(cudaMemcpy2DAsync(fdr_host + r0 * ld_fdr, ld_fdr, d_fdr + r0 * ldo, ldo, cols, r1 - r0,
+                                 cudaMemcpyDeviceToHost, g_pipe.d2h));
+    }
+  }
+  if (rc != OFL_OK || sync_downloads) {
+    cudaStreamSynchronize(g_pipe.h2d);
+    cudaStreamSynchronize(st);
+    cudaStreamSynchronize(g_pipe.d2h);
+  }
+  for (int b = 0; b < n_in; ++b) cudaEventDestroy(ev_up[b]);
+  for (int b = 0; b < n_out; ++b) cudaEventDestroy(ev_dir[b]);
+  return rc;
+}
+}  // namespace
 
 extern "C" {
 
@@ -81,6 +152,9 @@ int ofl_flow_direction_f32(const float* dem, int64_t rows, int64_t cols, int64_t
   if (rc != OFL_OK) return rc;
   rc = scratch_get(SCRATCH_FDR, (size_t)rows * ldo, &d_fdr);
   if (rc != OFL_OK) return rc;
+  if (mode != OFL_DIR_MODE_TILE)  // the ring fill of TILE mode follows the kernel: tiles take the plain path below
+    return direction_from_host(dem, in_rows, rows, cols, ld_dem, nodata, y_off, static_cast<float*>(d_dem), ldd,
+                               static_cast<uint8_t*>(d_fdr), ldo, fdr, ld_fdr, st, true);
   OFL_CUDA(cudaMemcpy2DAsync(d_dem, ldd * sizeof(float), dem, ld_dem * sizeof(float), cols * sizeof(float), in_rows,
                              cudaMemcpyHostToDevice, st));
   rc = launch_direction(static_cast<const float*>(d_dem), in_rows, cols, ldd, nodata, static_cast<uint8_t*>(d_fdr),
@@ -144,6 +218,59 @@ int ofl_flow_accumulation_u8(const uint8_t* fdr, int64_t rows, int64_t cols, int
     OFL_CUDA(cudaMemcpyAsync(perim_links, d_links, (size_t)n_perim * 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   OFL_CUDA(cudaStreamSynchronize(st));
   return OFL_OK;
+}
+
+int ofl_flow_routing_f32(const float* dem, int64_t rows, int64_t cols, int64_t ld_dem, double nodata, uint8_t* fdr,
+                         int64_t ld_fdr, int64_t* fac, int64_t ld_fac, int64_t* perim_links, int mem_kind, void* stream) {
+  OFL_REQUIRE(rows >= 0 && cols >= 0, OFL_ERR_INVALID, "negative raster size");
+  OFL_REQUIRE(mem_kind == OFL_MEM_HOST || mem_kind == OFL_MEM_DEVICE, OFL_ERR_INVALID, "unknown mem_kind %d", mem_kind);
+  if (rows == 0 || cols == 0) return OFL_OK;
+  OFL_REQUIRE(dem != nullptr && fac != nullptr, OFL_ERR_INVALID, "null raster pointer");
+  OFL_REQUIRE(ld_dem >= cols && ld_fac >= cols && (fdr == nullptr || ld_fdr >= cols), OFL_ERR_INVALID,
+              "leading dimension smaller than cols");
+  int rc = ensure_init();
+  if (rc != OFL_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void* work = nullptr;
+  const size_t need = accumulation_workspace_bytes(rows, cols);
+  rc = scratch_get(SCRATCH_WORK, need, &work);
+  if (rc != OFL_OK) return rc;
+  if (mem_kind == OFL_MEM_DEVICE) {
+    OFL_REQUIRE(fdr != nullptr, OFL_ERR_INVALID, "device callers provide the code raster");
+    rc = launch_direction(dem, rows, cols, ld_dem, nodata, fdr, rows, ld_fdr, 0, st);
+    if (rc != OFL_OK) return rc;
+    return launch_accumulation(fdr, rows, cols, ld_fdr, reinterpret_cast<long long*>(fac), ld_fac,
+                               reinterpret_cast<long long*>(perim_links), work, need, st);
+  }
+  const int64_t ldd = round_up(cols, 4), ldi = round_up(cols, 16), ldo = round_up(cols, 2);
+  void *d_dem = nullptr, *d_fdr = nullptr, *d_fac = nullptr, *d_links = nullptr;
+  rc = scratch_get(SCRATCH_DEM, (size_t)rows * ldd * sizeof(float), &d_dem);
+  if (rc != OFL_OK) return rc;
+  rc = scratch_get(SCRATCH_FDR, (size_t)rows * ldi, &d_fdr);
+  if (rc != OFL_OK) return rc;
+  rc = scratch_get(SCRATCH_FAC, (size_t)rows * ldo * sizeof(int64_t), &d_fac);
+  if (rc != OFL_OK) return rc;
+  const int64_t n_perim = perimeter_count(rows, cols);
+  if (perim_links) {
+    rc = scratch_get(SCRATCH_LINKS, (size_t)n_perim * 2 * sizeof(int64_t), &d_links);
+    if (rc != OFL_OK) return rc;
+  }
+  // codes stream back to the host while later bands are still uploading; the counts follow the accumulation
+  rc = direction_from_host(dem, rows, rows, cols, ld_dem, nodata, 0, static_cast<float*>(d_dem), ldd,
+                           static_cast<uint8_t*>(d_fdr), ldi, fdr, ld_fdr, st, false);
+  if (rc != OFL_OK) return rc;
+  rc = launch_accumulation(static_cast<const uint8_t*>(d_fdr), rows, cols, ldi, static_cast<long long*>(d_fac), ldo,
+                           static_cast<long long*>(d_links), work, need, st);
+  if (rc == OFL_OK) {
+    cudaError_t e = cudaMemcpy2DAsync(fac, ld_fac * sizeof(int64_t), d_fac, ldo * sizeof(int64_t), cols * sizeof(int64_t),
+                                      rows, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && perim_links)
+      e = cudaMemcpyAsync(perim_links, d_links, (size_t)n_perim * 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync(fac)", __FILE__, __LINE__);
+  }
+  cudaStreamSynchronize(st);
+  cudaStreamSynchronize(g_pipe.d2h);
+  return rc;
 }
 
 int ofl_check_accumulation_u8(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, const int64_t* fac,

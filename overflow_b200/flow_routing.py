@@ -1,0 +1,48 @@
+"""Flow direction followed by flow accumulation in one call.
+
+The reference runs the two steps as separate file-level passes (flow_direction.py:99-124 writes the
+codes, a later pass reads them back).  On the GPU the codes can stay in HBM between the two kernels, and
+for host rasters the upload of the DEM, the stencil and the download of the codes overlap in row bands
+(`ofl_flow_routing_f32`, csrc/api.cu).  Results are identical to `flow_direction_for_raster` followed by
+`flow_accumulation_for_raster`.
+"""
+import numpy as np
+
+from . import _native
+from .flow_direction import _as_f32
+
+
+def flow_routing_for_raster(dem: np.ndarray, nodata_value: float, out_fdr: np.ndarray = None,
+                            out_fac: np.ndarray = None, with_links: bool = False, want_fdr: bool = True):
+    """(fdr uint8, fac int64[, perim_links]) of a whole DEM held in host memory.
+
+    `out_fdr` / `out_fac` may be preallocated C-contiguous arrays (e.g. pinned memory) of dem.shape.
+    With `want_fdr=False` the codes are not copied back and None is returned in their place.
+    """
+    dem = np.asarray(dem)
+    if dem.ndim != 2:
+        raise ValueError("dem must be a 2-D array")
+    src = np.ascontiguousarray(_as_f32(dem))
+    rows, cols = src.shape
+    if want_fdr:
+        if out_fdr is None:
+            out_fdr = np.empty((rows, cols), dtype=np.uint8)
+        elif out_fdr.dtype != np.uint8 or out_fdr.shape != (rows, cols) or not out_fdr.flags.c_contiguous:
+            raise ValueError("out_fdr must be a C-contiguous uint8 array of dem.shape")
+    else:
+        out_fdr = None
+    if out_fac is None:
+        out_fac = np.empty((rows, cols), dtype=np.int64)
+    elif out_fac.dtype != np.int64 or out_fac.shape != (rows, cols) or not out_fac.flags.c_contiguous:
+        raise ValueError("out_fac must be a C-contiguous int64 array of dem.shape")
+    lib = _native.lib()
+    perim = np.empty((int(lib.ofl_perimeter_count(rows, cols)), 2), dtype=np.int64) if with_links else None
+    if rows and cols:
+        _native.check(
+            lib.ofl_flow_routing_f32(
+                src.ctypes.data, rows, cols, cols, float(nodata_value),
+                out_fdr.ctypes.data if want_fdr else None, cols, out_fac.ctypes.data, cols,
+                perim.ctypes.data if with_links else None, _native.OFL_MEM_HOST, None,
+            )
+        )
+    return (out_fdr, out_fac, perim) if with_links else (out_fdr, out_fac)
