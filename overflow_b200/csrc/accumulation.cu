@@ -104,6 +104,8 @@ struct AccParams {
   int y_off, strip_above, strip_below;
   int tile_base;  // first tile handled by this launch (blockIdx.x + tile_base)
   int vec_store;  // fac rows are 16-byte aligned: the final pass may use 16-byte stores
+  int* wide_list;  // [0]: number of tiles the 32-bit final pass left to the 64-bit variant, [1..]: their ids
+  int force_wide;  // test hook: send every tile with an inflow through the 64-bit variant
 };
 
 __device__ __forceinline__ int node_of_cell(int gy, int gx, const AccParams& p) {
@@ -140,7 +142,7 @@ constexpr uint32_t W_CNT_ONE = 1u << 8;
 constexpr uint32_t W_LIVE = 1u << 26;
 constexpr uint32_t W_MISS_ONE = 1u << 27;
 constexpr uint32_t W_VISITED = 1u << 31;
-constexpr uint32_t W_FINISH = 0xF8000000u + W_CNT_ONE;       // ready word -> finished word (counts the cell itself)
+constexpr uint32_t W_FINISH = (W_VISITED | (0xFu << 27)) + W_CNT_ONE;       // ready word -> finished word (counts the cell itself)
 constexpr uint32_t W_HANDOFF_MASK = ~(W_LIVE | 0xFFu);               // finished word -> what its hand-off adds downstream
 constexpr uint32_t W_READY_MASK = (0xFu << 27) | W_LIVE;     // hand-off result: the downstream cell is a live cell ...
 constexpr uint32_t W_READY_VAL = W_MISS_ONE | W_LIVE;        // ... and this was the hand-off it was waiting for
@@ -584,98 +586,155 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
 // ---------------------------------------------------------------- final pass
 // fac(v) = L(v) + sum of the inflows I(e) of the perimeter cells e whose in-tile path runs through v.
 // Pass A left L (tile-local counts) in HBM and the solve left I(e) in S, so the final pass only has to
-// add every non-zero inflow along its path: one thread per perimeter cell walks downstream adding its
-// 64-bit inflow to each cell with a 32-bit shared atomic (+ a carry atomic when the low word wraps),
-// then the tile is written out as int64.  ~11 B/cell of HBM traffic and a few hundred instructions per
-// warp: this kernel runs close to the HBM roofline instead of re-doing the whole propagation.
+// add every non-zero inflow along its path and write the tile out as int64 (~11 B/cell of HBM traffic).
+//   * the perimeter slots with a non-zero inflow are compacted onto whole warps; a step of a path is one
+//     shared atomic on the cell's count, one byte load of the next cell's code and two PRMT table lookups;
+//   * the code tile carries a one-cell halo marked NODATA, so leaving the tile, leaving the raster and
+//     running into a NODATA cell are the same test;
+//   * counts are accumulated in 32 bits (22 KB of shared memory, eight CTAs per SM).  A tile in which an
+//     inflow or a sum does not fit 32 bits -- possible only on rasters of more than 2^32 cells' worth of
+//     drainage -- is put on a list instead of being written, and redone by the WIDE variant (64-bit).
 struct FinalSmem {
-  static constexpr int CS = 0;       // 64 x 64 codes, no halo (TMA box starts on the tile, 16-byte aligned)
-  static constexpr int LO = AT * AT;
-  static constexpr int HI = LO + AT * AT * 4;
-  static constexpr int TAB = HI + AT * AT * 4;  // int4 per direction code: {code-array byte offset, dy, dx, lo/hi byte offset}
-  static constexpr int BAR = TAB + 128;
-  static constexpr int BYTES = BAR + 16;
+  static constexpr int CS = 0;                       // codes + halo (TMA destination), pitch ACS_W
+  static constexpr int LO = 6400;                    // low words of the counts, pitch AT, no halo
+  static constexpr int SEED = LO + AT * AT * 4;      // 64-bit inflow of every listed path
+  static constexpr int LIST = SEED + SLOTS * 8;      // slots of the listed paths (u8)
+  static constexpr int CNT = LIST + SLOTS;           // number of listed paths
+  static constexpr int BAR = CNT + 16;
+  static constexpr int HI = BAR + 16;                // high words (WIDE only)
+  static constexpr int BYTES_FAST = HI;
+  static constexpr int BYTES_WIDE = HI + AT * AT * 4;
 };
+// per direction code E, NE, N, NW | W, SW, S, SE: code-array byte offset and count-array word offset
+constexpr uint32_t F_TABC_LO = (uint32_t)(uint8_t)(1) | ((uint32_t)(uint8_t)(1 - ACS_W) << 8) |
+                               ((uint32_t)(uint8_t)(-ACS_W) << 16) | ((uint32_t)(uint8_t)(-ACS_W - 1) << 24);
+constexpr uint32_t F_TABC_HI = (uint32_t)(uint8_t)(-1) | ((uint32_t)(uint8_t)(ACS_W - 1) << 8) |
+                               ((uint32_t)(uint8_t)(ACS_W) << 16) | ((uint32_t)(uint8_t)(ACS_W + 1) << 24);
+constexpr uint32_t F_TABL_LO = (uint32_t)(uint8_t)(1) | ((uint32_t)(uint8_t)(1 - AT) << 8) |
+                               ((uint32_t)(uint8_t)(-AT) << 16) | ((uint32_t)(uint8_t)(-AT - 1) << 24);
+constexpr uint32_t F_TABL_HI = (uint32_t)(uint8_t)(-1) | ((uint32_t)(uint8_t)(AT - 1) << 8) |
+                               ((uint32_t)(uint8_t)(AT) << 16) | ((uint32_t)(uint8_t)(AT + 1) << 24);
 
-__global__ void __launch_bounds__(ACC_THREADS) acc_final_kernel(const __grid_constant__ CUtensorMap tm, const AccParams p) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  const uint32_t sb = smem_base_opaque(smem_raw);
-  const uint32_t a_cs0 = sb + FinalSmem::CS;  // code of cell (0,0), pitch AT
-  const uint32_t a_lo = sb + FinalSmem::LO, a_hi = sb + FinalSmem::HI, a_tab = sb + FinalSmem::TAB;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + FinalSmem::BAR);
+// One tile.  Returns true (fast variant only) when the tile needs the 64-bit variant; nothing has been
+// written to fac in that case.  `parity`: phase of the tile's TMA barrier.
+template <bool WIDE>
+__device__ __forceinline__ bool final_tile(const CUtensorMap& tm, const AccParams& p, int tile, uint8_t* smem_raw,
+                                           uint32_t sb, uint32_t parity) {
+  using SM = FinalSmem;
+  const uint32_t a_cs = sb + SM::CS, a_lo = sb + SM::LO, a_hi = sb + SM::HI;
+  const uint32_t a_cs0 = a_cs + ACS_W * ACS_Y0 + ACS_X0;  // code of cell (0,0)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + SM::BAR);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x + p.tile_base;
   const int ty = tile / p.ntx, tx = tile - ty * p.ntx;
   const int y0 = ty << AT_SHIFT, x0 = tx << AT_SHIFT;
   const int h = min(AT, p.rows - y0), w = min(AT, p.cols - x0);
 
   if (tid == 0) {
-    mbar_init(bar, 1);
-    mbar_fence_init();
-    mbar_arrive_expect_tx(bar, AT * AT);
-    tma_load_2d(smem_raw + FinalSmem::CS, &tm, x0, y0 + p.y_off, bar);
+    mbar_arrive_expect_tx(bar, ACS_BYTES);
+    tma_load_2d(smem_raw + SM::CS, &tm, x0 - ACS_X0, y0 - ACS_Y0 + p.y_off, bar);
+    sts32(sb + SM::CNT, 0);
   }
-  if (tid < 8) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_tab + 16 * tid),
-                 "r"((uint32_t)(dir_dy(tid) * AT + dir_dx(tid))), "r"((uint32_t)dir_dy(tid)), "r"((uint32_t)dir_dx(tid)),
-                 "r"((uint32_t)((dir_dy(tid) * AT + dir_dx(tid)) * 4))
-                 : "memory");
-  }
-  // tile-local counts -> low words; high words start at zero
+  // global loads first (they overlap the TMA): tile-local counts and this thread's perimeter inflow
   const uint4* Lt = reinterpret_cast<const uint4*>(p.L + (size_t)tile * (AT * AT));
-#pragma unroll
-  for (int g = tid; g < AT * AT / 8; g += ACC_THREADS) {
-    const uint4 q = Lt[g];
-    const uint32_t a = a_lo + g * 32;
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(q.x & 0xFFFFu), "r"(q.x >> 16),
-                 "r"(q.y & 0xFFFFu), "r"(q.y >> 16)
-                 : "memory");
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16), "r"(q.z & 0xFFFFu), "r"(q.z >> 16),
-                 "r"(q.w & 0xFFFFu), "r"(q.w >> 16)
-                 : "memory");
-    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a_hi + g * 32), "r"(0u) : "memory");
-    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a_hi + g * 32 + 16), "r"(0u) : "memory");
-  }
-  // inflow of this thread's perimeter cell (global load overlaps the TMA wait)
-  int y = 0, x = 0;
+  const uint4 q0 = Lt[tid], q1 = Lt[tid + ACC_THREADS];
+  const int side = tid >> AT_SHIFT, k = tid & (AT - 1);
+  const bool valid = side < 2 ? (k < w && (side == 0 || h > 1)) : (k > 0 && k < h - 1 && (side == 2 || w > 1));
   unsigned long long seed = 0;
-  if (cell_of_slot(tid, h, w, y, x)) seed = p.S[(size_t)tile * SLOTS + tid];
+  if (valid) seed = p.S[(size_t)tile * SLOTS + tid];
   __syncthreads();
-  mbar_wait(bar, 0);
 
-  if (seed) {
-    const uint32_t slo = (uint32_t)seed, shi = (uint32_t)(seed >> 32);
-    uint32_t ca = a_cs0 + y * AT + x;        // shared address of the current cell's code
-    uint32_t o = (y * AT + x) * 4;           // byte offset of the current cell in lo[] / hi[]
-    for (int steps = 0; steps <= AT * AT; ++steps) {
-      const uint32_t old = atoms_add(a_lo + o, slo);
-      const uint32_t hadd = shi + ((old + slo) < old ? 1u : 0u);
-      if (hadd) atoms_add(a_hi + o, hadd);
-      const uint32_t code = lds8(ca);
-      if (code >= 8) break;  // pit / flat / nodata / invalid: no downstream cell
-      uint32_t t0, t1, t2, t3;
-      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3) : "r"(a_tab + 16 * code) : "memory");
-      y += (int)t1;
-      x += (int)t2;
-      if ((uint32_t)y >= (uint32_t)h || (uint32_t)x >= (uint32_t)w) break;  // leaves the tile (or the raster)
-      ca += t0;
-      o += t3;
-      if (lds8(ca) == OFL_DIR_NODATA) break;  // no edge into a NODATA cell
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const uint4 q = r ? q1 : q0;
+    const uint32_t o = (tid + r * ACC_THREADS) * 32;
+    sts128(a_lo + o, q.x & 0xFFFFu, q.x >> 16, q.y & 0xFFFFu, q.y >> 16);
+    sts128(a_lo + o + 16, q.z & 0xFFFFu, q.z >> 16, q.w & 0xFFFFu, q.w >> 16);
+    if (WIDE) {
+      sts128(a_hi + o, 0, 0, 0, 0);
+      sts128(a_hi + o + 16, 0, 0, 0, 0);
+    }
+  }
+  bool wide_needed = false;
+  {
+    // compact the slots with a non-zero inflow
+    const bool has = seed != 0;
+    const uint32_t bal = __ballot_sync(0xffffffffu, has);
+    uint32_t lb = 0;
+    if (lane == 0 && bal) lb = atoms_add(sb + SM::CNT + (lanemask_lt() >> 31), __popc(bal));
+    lb = __shfl_sync(0xffffffffu, lb, 0);
+    if (has) {
+      const uint32_t pos = lb + __popc(bal & lanemask_lt());
+      sts8(sb + SM::LIST + pos, tid);
+      asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sb + SM::SEED + 8 * pos), "r"((uint32_t)seed),
+                   "r"((uint32_t)(seed >> 32))
+                   : "memory");
+      if (!WIDE && ((seed >> 32) || p.force_wide)) wide_needed = true;
+    }
+  }
+  mbar_wait(bar, parity);
+  // halo ring -> NODATA: a path stops in front of it exactly as in front of a NODATA cell
+  {
+    int hy = side == 0 ? -1 : side == 1 ? AT : k;
+    int hx = side == 2 ? -1 : side == 3 ? AT : k;
+    sts8(a_cs0 + hy * ACS_W + hx, OFL_DIR_NODATA);
+    if (k == 0) sts8(a_cs0 + ((side & 1) ? AT : -1) * ACS_W + ((side & 2) ? AT : -1), OFL_DIR_NODATA);
+  }
+  if (h < AT || w < AT) {
+    // partial tile at the raster's bottom / right edge: in-tile positions beyond the raster stop a path too
+    for (int idx = tid; idx < AT * AT; idx += ACC_THREADS) {
+      const int yy = idx >> AT_SHIFT, xx = idx & (AT - 1);
+      if (yy >= h || xx >= w) sts8(a_cs0 + yy * ACS_W + xx, OFL_DIR_NODATA);
     }
   }
   __syncthreads();
+
+  {
+    // one thread per listed path, from the high thread ids down
+    const uint32_t t = ACC_THREADS - 1 - tid;
+    if (t < lds32(sb + SM::CNT)) {
+      const uint32_t slot = lds8(sb + SM::LIST + t);
+      const uint2 sd = lds64(sb + SM::SEED + 8 * t);
+      const int ss = slot >> AT_SHIFT, sk = slot & (AT - 1);
+      const int y = ss == 0 ? 0 : ss == 1 ? h - 1 : sk;
+      const int x = ss == 2 ? 0 : ss == 3 ? w - 1 : sk;
+      uint32_t ca = a_cs0 + y * ACS_W + x;      // shared address of the current cell's code
+      uint32_t o = a_lo + (y * AT + x) * 4;     // ... and of its count
+      uint32_t code = lds8(ca);
+      if (WIDE || (sd.y == 0 && !p.force_wide)) {
+        for (int steps = 0; steps <= AT * AT; ++steps) {
+          const uint32_t old = atoms_add(o, sd.x);
+          const bool carry = (old + sd.x) < old;
+          if (WIDE) {
+            const uint32_t hadd = sd.y + (carry ? 1u : 0u);
+            if (hadd) atoms_add(o + (SM::HI - SM::LO), hadd);
+          } else {
+            wide_needed |= carry;
+          }
+          if (code >= 8) break;  // pit / flat / invalid: no downstream cell
+          const uint32_t sel = code * 0x1111u + 0x8880u;  // byte 0: table entry, bytes 1..3: its sign
+          ca += prmt(F_TABC_LO, F_TABC_HI, sel);
+          o += prmt(F_TABL_LO, F_TABL_HI, sel) << 2;
+          code = lds8(ca);
+          if (code == OFL_DIR_NODATA) break;  // NODATA cell, tile edge or raster edge: the path ends here
+        }
+      }
+    }
+  }
+  if (__syncthreads_or(wide_needed) && !WIDE) return true;
 
   // final counts: each lane writes two adjacent cells as one 16-byte store, a warp one 512-byte row per
   // instruction; NODATA cells get -9998
   const uint32_t xx = 2 * lane;
   long long* orow = p.fac + (int64_t)(y0 + 8 * warp) * p.ld_fac + x0 + xx;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int yy = 8 * warp + k;
+  for (int r = 0; r < 8; ++r) {
+    const int yy = 8 * warp + r;
     if (yy < h && (int)xx < w) {
       const uint32_t oo = (yy * AT + xx) * 4;
-      const uint2 lo2 = lds64(a_lo + oo), hi2 = lds64(a_hi + oo);
-      const uint32_t c2 = lds16(a_cs0 + yy * AT + xx);
+      const uint2 lo2 = lds64(a_lo + oo);
+      uint2 hi2 = make_uint2(0, 0);
+      if (WIDE) hi2 = lds64(a_hi + oo);
+      const uint32_t c2 = lds16(a_cs0 + yy * ACS_W + xx);
       long long v0 = (long long)(((unsigned long long)hi2.x << 32) | lo2.x);
       long long v1 = (long long)(((unsigned long long)hi2.y << 32) | lo2.y);
       if ((c2 & 0xFF) == OFL_DIR_NODATA) v0 = OFL_FAC_NODATA_EMITTED;
@@ -688,6 +747,36 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_final_kernel(const __grid_con
       }
     }
     orow += p.ld_fac;
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(ACC_THREADS) acc_final_kernel(const __grid_constant__ CUtensorMap tm, const AccParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const uint32_t sb = smem_base_opaque(smem_raw);
+  if (threadIdx.x == 0) {
+    mbar_init(reinterpret_cast<uint64_t*>(smem_raw + FinalSmem::BAR), 1);
+    mbar_fence_init();
+  }
+  const int tile = blockIdx.x + p.tile_base;
+  if (final_tile<false>(tm, p, tile, smem_raw, sb, 0) && threadIdx.x == 0)
+    p.wide_list[1 + atomicAdd(p.wide_list, 1)] = tile;
+}
+
+// The tiles the 32-bit variant gave up on (normally none): a small persistent grid walks the list.
+__global__ void __launch_bounds__(ACC_THREADS) acc_final_wide_kernel(const __grid_constant__ CUtensorMap tm, const AccParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const uint32_t sb = smem_base_opaque(smem_raw);
+  if (threadIdx.x == 0) {
+    mbar_init(reinterpret_cast<uint64_t*>(smem_raw + FinalSmem::BAR), 1);
+    mbar_fence_init();
+  }
+  const int n = p.wide_list[0];
+  uint32_t parity = 0;
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    final_tile<true>(tm, p, p.wide_list[1 + i], smem_raw, sb, parity);
+    parity ^= 1;
+    __syncthreads();  // the next tile's TMA overwrites the codes this tile's output rows still read
   }
 }
 
@@ -923,7 +1012,9 @@ static int ensure_tile_attrs() {
   if (!attr_set) {
     OFL_CUDA(cudaFuncSetAttribute(acc_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   TileSmem::BYTES + tile_extra_smem()));
-    OFL_CUDA(cudaFuncSetAttribute(acc_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FinalSmem::BYTES));
+    OFL_CUDA(cudaFuncSetAttribute(acc_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FinalSmem::BYTES_FAST));
+    OFL_CUDA(cudaFuncSetAttribute(acc_final_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  FinalSmem::BYTES_WIDE));
     attr_set = true;
   }
   return OFL_OK;
@@ -997,7 +1088,7 @@ static int check_flags(const int* err_flags, cudaStream_t st) {
 // Workspace of one perimeter graph with n nodes.  `keep_succ`: strips solve the same forest twice.
 struct GraphLayout {
   int64_t n;
-  size_t off_succ, off_pa, off_pb, off_lists, off_S, off_S2, off_d0, off_d1, off_link, off_counts, off_err, off_L, total;
+  size_t off_succ, off_pa, off_pb, off_lists, off_S, off_S2, off_d0, off_d1, off_link, off_counts, off_err, off_L, off_wide, total;
 };
 
 static GraphLayout graph_layout(int64_t n, bool strip, bool with_tiles = true) {
@@ -1021,6 +1112,7 @@ static GraphLayout graph_layout(int64_t n, bool strip, bool with_tiles = true) {
   L.off_counts = take((size_t)(PJ_MAX_ROUNDS + 2) * 2 * PJ_MAX_BLOCKS * sizeof(int));
   L.off_err = take(64);
   L.off_L = with_tiles ? take((size_t)(n / SLOTS) * AT * AT * sizeof(uint16_t)) : o;
+  L.off_wide = with_tiles ? take((size_t)(n / SLOTS + 1) * sizeof(int)) : o;
   L.total = o;
   return L;
 }
@@ -1049,8 +1141,7 @@ static int ws_begin(uint8_t* ws, const GraphLayout& L, size_t from_off, cudaStre
 // Everything one raster (or strip) needs to launch its kernels.
 struct AccCtx {
   AccParams p;
-  CUtensorMap tm;        // codes + halo box for pass A
-  CUtensorMap tm_tile;   // exact 64 x 64 box for the final pass
+  CUtensorMap tm;        // codes + halo box (both tile passes)
   GraphLayout L;
   uint8_t* ws;
   int64_t ntiles;
@@ -1083,6 +1174,8 @@ static int acc_setup(AccCtx& C, const uint8_t* fdr, int64_t rows, int64_t cols, 
   p.ld_fac = ld_fac;
   p.err = reinterpret_cast<int*>(C.ws + C.L.off_err);
   p.L = reinterpret_cast<uint16_t*>(C.ws + C.L.off_L);
+  p.wide_list = reinterpret_cast<int*>(C.ws + C.L.off_wide);
+  p.force_wide = getenv("OFL_FORCE_WIDE_FINAL") ? 1 : 0;
   p.y_off = y_off;
   p.strip_above = has_above ? 1 : 0;
   p.strip_below = has_below ? 1 : 0;
@@ -1098,9 +1191,19 @@ static int acc_setup(AccCtx& C, const uint8_t* fdr, int64_t rows, int64_t cols, 
   C.ntiles = (int64_t)p.nty * p.ntx;
   int rc = make_tensor_map_2d(&C.tm, fdr, 1, (uint64_t)cols, (uint64_t)(rows + 2 * y_off), (uint64_t)ld_fdr, ACS_W, ACS_H);
   if (rc != OFL_OK) return rc;
-  rc = make_tensor_map_2d(&C.tm_tile, fdr, 1, (uint64_t)cols, (uint64_t)(rows + 2 * y_off), (uint64_t)ld_fdr, AT, AT);
-  if (rc != OFL_OK) return rc;
   return ensure_tile_attrs();
+}
+
+
+// Final pass over `grid` tiles starting at p.tile_base: the 32-bit kernel, then the 64-bit one on whatever it listed.
+static int launch_final(const AccCtx& C, const AccParams& p, unsigned grid, cudaStream_t st) {
+  OFL_CUDA(cudaMemsetAsync(p.wide_list, 0, sizeof(int), st));
+  acc_final_kernel<<<grid, ACC_THREADS, FinalSmem::BYTES_FAST, st>>>(C.tm, p);
+  OFL_CHECK_LAUNCH();
+  const unsigned wide_grid = grid < (unsigned)sm_count() * 2 ? grid : (unsigned)sm_count() * 2;
+  acc_final_wide_kernel<<<wide_grid, ACC_THREADS, FinalSmem::BYTES_WIDE, st>>>(C.tm, p);
+  OFL_CHECK_LAUNCH();
+  return OFL_OK;
 }
 
 int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, long long* fac,
@@ -1125,9 +1228,9 @@ int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t 
   if (rc != OFL_OK) return rc;
   {
     PhaseScope ps(PHASE_ACC_TILE_B, st);
-    acc_final_kernel<<<(unsigned)C.ntiles, ACC_THREADS, FinalSmem::BYTES, st>>>(C.tm_tile, C.p);
+    rc = launch_final(C, C.p, (unsigned)C.ntiles, st);
   }
-  OFL_CHECK_LAUNCH();
+  if (rc != OFL_OK) return rc;
   if (perim_links_dev) {
     const int64_t n = perimeter_count(rows, cols);
     {
@@ -1265,14 +1368,13 @@ int strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
   {
     PhaseScope ps(PHASE_STRIP_EDGE, st);
     AccParams pb = C.p;
-    acc_final_kernel<<<(unsigned)pb.ntx, ACC_THREADS, FinalSmem::BYTES, st>>>(C.tm_tile, pb);
-    if (pb.nty > 1) {
+    rc = launch_final(C, pb, (unsigned)pb.ntx, st);
+    if (rc == OFL_OK && pb.nty > 1) {
       pb.tile_base = (pb.nty - 1) * pb.ntx;
-      acc_final_kernel<<<(unsigned)pb.ntx, ACC_THREADS, FinalSmem::BYTES, st>>>(C.tm_tile, pb);
-      count_launch();
+      rc = launch_final(C, pb, (unsigned)pb.ntx, st);
     }
   }
-  OFL_CHECK_LAUNCH();
+  if (rc != OFL_OK) return rc;
   strip_boundary_extract_kernel<<<grid_for(2 * cols, 8), 256, 0, st>>>(fdr_halo, ld_fdr, fac, ld_fac, C.pa, C.p.link, C.p,
                                                                        slink, floc, bcode);
   OFL_CHECK_LAUNCH();
@@ -1337,9 +1439,9 @@ int strip_accum_final(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
   OFL_CHECK_LAUNCH();
   {
     PhaseScope ps(PHASE_ACC_TILE_B, st);
-    acc_final_kernel<<<(unsigned)C.ntiles, ACC_THREADS, FinalSmem::BYTES, st>>>(C.tm_tile, C.p);
+    rc = launch_final(C, C.p, (unsigned)C.ntiles, st);
   }
-  OFL_CHECK_LAUNCH();
+  if (rc != OFL_OK) return rc;
   return check_flags(C.p.err, st);
 }
 

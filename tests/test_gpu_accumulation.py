@@ -192,3 +192,21 @@ def test_all_cells_one_chain_counts_exceed_32_bits_path():
     fac = dev.flow_accumulation(pitched)
     assert np.array_equal(fac.cpu().numpy(), want)
     assert want.max() > 100000
+
+
+def test_wide_final_pass_matches(monkeypatch):
+    """The 64-bit variant of the final pass (taken when a count does not fit 32 bits) gives the same
+    counts: force every tile with an inflow through it."""
+    fdr = oracle.flow_direction_for_tile(
+        synth.pad_nodata(synth.punch_holes(synth.fractal(300, 517, beta=2.5, seed=21), frac=0.02, seed=22)),
+        synth.NODATA)[1:-1, 1:-1]
+    from overflow_b200.flow_accumulation import single_tile_flow_accumulation
+
+    fdr = np.ascontiguousarray(fdr)
+    want = oracle.flow_accumulation(fdr)
+    monkeypatch.setenv("OFL_FORCE_WIDE_FINAL", "1")
+    fac, _ = single_tile_flow_accumulation(fdr)
+    assert np.array_equal(fac, want)
+    monkeypatch.delenv("OFL_FORCE_WIDE_FINAL")
+    fac, _ = single_tile_flow_accumulation(fdr)
+    assert np.array_equal(fac, want)
