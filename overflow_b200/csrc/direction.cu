@@ -224,15 +224,51 @@ __device__ __forceinline__ void direction_item(const CUtensorMap* tm, const DirP
   uint8_t* orow = p.out + (int64_t)y0 * p.ld_out + xl;  // next output row of this lane
   const bool full_store = xl + 3 < p.W;
 
-  // differences between row b (above) and the new row c; emits b's codes when b is an output row
-  auto diffs_and_emit = [&](int i, const DirRow& b, DirRow& c, bool emit) {
+  // exact codes of the lane's four cells of input row i - 1 (output row y0 + i - 2), stored over the fast ones
+  auto fixup = [&](int i) {
+    uint32_t packed = 0;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const int cx = xl + j;
+      const float z = raw_at(i - 1, cx);
+      uint32_t ex;
+      if (z == nd) {
+        ex = OFL_DIR_NODATA;
+      } else {
+        float n[8];
+        n[0] = raw_at(i - 1, cx + 1);
+        n[1] = raw_at(i - 2, cx + 1);
+        n[2] = raw_at(i - 2, cx);
+        n[3] = raw_at(i - 2, cx - 1);
+        n[4] = raw_at(i - 1, cx - 1);
+        n[5] = raw_at(i, cx - 1);
+        n[6] = raw_at(i, cx);
+        n[7] = raw_at(i, cx + 1);
+        ex = d8_exact(z, n, nd);
+      }
+      packed |= ex << (8 * j);
+    }
+    uint8_t* o = p.out + (int64_t)(y0 + i - 2) * p.ld_out + xl;
+    if (!EDGE || full_store) {
+      *reinterpret_cast<uint32_t*>(o) = packed;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (xl + j < p.W) o[j] = (uint8_t)(packed >> (8 * j));
+    }
+  };
+
+  // differences between row b (above) and the new row c; emits b's fast-path codes when b is an output row.
+  // Returns non-zero when some cell of the row needs the exact path: the caller looks at that once per box
+  // (fixup), so the rows of a box flow through without a branch on the end of each row's dependency chain.
+  auto diffs_and_emit = [&](const DirRow& b, DirRow& c, bool emit) -> float {
 #pragma unroll
     for (int j = 0; j < 4; ++j) c.uS[j] = __fsub_rn(b.v[j + 1], c.v[j + 1]);
 #pragma unroll
     for (int j = 0; j < 5; ++j) c.uSE[j] = __fsub_rn(b.v[j], c.v[j + 1]);
 #pragma unroll
     for (int j = 0; j < 5; ++j) c.uSW[j] = __fsub_rn(b.v[j + 1], c.v[j]);
-    if (!emit) return;
+    if (!emit) return 0.f;
     float hE[5];
 #pragma unroll
     for (int j = 0; j < 5; ++j) hE[j] = __fsub_rn(b.v[j], b.v[j + 1]);  // cell j-1 -> E
@@ -244,30 +280,7 @@ __device__ __forceinline__ void direction_item(const CUtensorMap* tm, const DirP
     // codes are 0..8: pack pairs exactly in float, then take the low 16 bits of (value + 2^23)
     const uint32_t lo = __float_as_uint(__fadd_rn(__fmaf_rn(code[1], 256.f, code[0]), 8388608.f));
     const uint32_t hi = __float_as_uint(__fadd_rn(__fmaf_rn(code[3], 256.f, code[2]), 8388608.f));
-    uint32_t packed = __byte_perm(lo, hi, 0x5410);
-    if (special != 0.f) {
-#pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        const int cx = xl + j;
-        const float z = raw_at(i - 1, cx);
-        uint32_t ex;
-        if (z == nd) {
-          ex = OFL_DIR_NODATA;
-        } else {
-          float n[8];
-          n[0] = raw_at(i - 1, cx + 1);
-          n[1] = raw_at(i - 2, cx + 1);
-          n[2] = raw_at(i - 2, cx);
-          n[3] = raw_at(i - 2, cx - 1);
-          n[4] = raw_at(i - 1, cx - 1);
-          n[5] = raw_at(i, cx - 1);
-          n[6] = raw_at(i, cx);
-          n[7] = raw_at(i, cx + 1);
-          ex = d8_exact(z, n, nd);
-        }
-        packed = (packed & ~(0xFFu << (8 * j))) | (ex << (8 * j));
-      }
-    }
+    const uint32_t packed = __byte_perm(lo, hi, 0x5410);
     if (!EDGE || full_store) {
       *reinterpret_cast<uint32_t*>(orow) = packed;
     } else {
@@ -276,6 +289,7 @@ __device__ __forceinline__ void direction_item(const CUtensorMap* tm, const DirP
         if (xl + j < p.W) orow[j] = (uint8_t)(packed >> (8 * j));
     }
     orow += p.ld_out;
+    return special;
   };
 
   DirRow X[2];  // row i lives in X[i & 1]; indices are compile-time inside the unrolled box loop
@@ -285,22 +299,35 @@ __device__ __forceinline__ void direction_item(const CUtensorMap* tm, const DirP
     mbar_wait(&bars[s], ((g0 + k) / DIR_STAGES) & 1);
     const float* t = tiles + s * DIR_STAGE_FLOATS + 4 * lane;
     const int ib = k * DIR_RB;
+    float sp[DIR_RB];
     if (k > 0 && ib + DIR_RB <= n_in - 1) {
       // interior box: every row is inside the array and has a row above it that is an output row
 #pragma unroll
       for (int rr = 0; rr < DIR_RB; ++rr) {
         load_row(t, rr, ib + rr, X[rr & 1], false);
-        diffs_and_emit(ib + rr, X[(rr + 1) & 1], X[rr & 1], true);
+        sp[rr] = diffs_and_emit(X[(rr + 1) & 1], X[rr & 1], true);
       }
     } else {
 #pragma unroll
       for (int rr = 0; rr < DIR_RB; ++rr) {
         const int i = ib + rr;
+        sp[rr] = 0.f;
         if (i < n_in) {
           load_row(t, rr, i, X[rr & 1], true);
-          if (i >= 1) diffs_and_emit(i, X[(rr + 1) & 1], X[rr & 1], i >= 2);
+          if (i >= 1) sp[rr] = diffs_and_emit(X[(rr + 1) & 1], X[rr & 1], i >= 2);
         }
       }
+    }
+    // special values are sums of non-negative terms: one test for the whole box, then row by row
+    float sp_any = sp[0];
+#pragma unroll
+    for (int rr = 1; rr < DIR_RB; ++rr) sp_any = __fadd_rn(sp_any, sp[rr]);
+    if (sp_any != 0.f) {
+      uint32_t rows_mask = 0;
+#pragma unroll
+      for (int rr = 0; rr < DIR_RB; ++rr) rows_mask |= (sp[rr] != 0.f ? 1u : 0u) << rr;
+#pragma unroll 1
+      for (; rows_mask; rows_mask &= rows_mask - 1) fixup(ib + __ffs(rows_mask) - 1);
     }
     __syncwarp();
     // box k-1 is no longer needed by the exact path: its stage takes box k+STAGES-1
