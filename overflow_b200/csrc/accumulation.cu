@@ -154,6 +154,10 @@ constexpr uint32_t W_TAB_HI = (uint32_t)(uint8_t)(-1) | ((uint32_t)(uint8_t)(WP 
 #ifndef OFL_WALK_PER_THREAD
 #define OFL_WALK_PER_THREAD 1
 #endif
+#ifndef OFL_WIDE_PER_LANE
+#define OFL_WIDE_PER_LANE 2
+#endif
+constexpr int WIDE_PER_LANE = OFL_WIDE_PER_LANE;      // queue entries a lane visits per turn of the level loop
 constexpr int WALK_PER_THREAD = OFL_WALK_PER_THREAD;  // switch to chain walking once a level has <= this many cells per thread
 
 // Shared memory (27.2 KB, eight CTAs per SM): the code tile is only read until the words are built, so the
@@ -456,15 +460,18 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
   __syncthreads();
 
   // ---- wide levels: level k is q[lo, hi); processing it appends level k+1 right after it.  A warp takes
-  //      64 entries per turn, two per lane, and reserves queue slots for both with one atomic.
+  //      WIDE_PER_LANE * 32 entries per turn and reserves queue slots for everything they complete with
+  //      one atomic.
   const uint32_t n_src = lds32(a_tail);  // final: the level loop appends through the second counter
   uint32_t lo = 0, hi = n_src;
   while (hi - lo > WALK_PER_THREAD * ACC_THREADS) {
-    for (uint32_t base = lo + 64 * warp; base < hi; base += 2 * ACC_THREADS) {
-      uint32_t old[2] = {0, 0}, an[2] = {0, 0};  // old == 0 reads as "nothing completed"
+    for (uint32_t base = lo + 32 * WIDE_PER_LANE * warp; base < hi; base += WIDE_PER_LANE * ACC_THREADS) {
+      uint32_t old[WIDE_PER_LANE], an[WIDE_PER_LANE];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
+      for (int e = 0; e < WIDE_PER_LANE; ++e) {
         const uint32_t i = base + 32 * e + lane;
+        old[e] = 0;  // reads as "nothing completed"
+        an[e] = 0;
         if (i < hi) {
           const uint32_t aw = a_word + lds16(a_q + 2 * i);
           const uint32_t wv = lds32(aw);
@@ -476,15 +483,21 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
           }
         }
       }
-      const bool r0 = (old[0] & W_READY_MASK) == W_READY_VAL, r1 = (old[1] & W_READY_MASK) == W_READY_VAL;
-      const uint32_t b0 = __ballot_sync(0xffffffffu, r0), b1 = __ballot_sync(0xffffffffu, r1);
-      if (b0 | b1) {
-        const uint32_t n0 = __popc(b0);
+      uint32_t bal[WIDE_PER_LANE], total = 0;
+#pragma unroll
+      for (int e = 0; e < WIDE_PER_LANE; ++e) {
+        bal[e] = __ballot_sync(0xffffffffu, (old[e] & W_READY_MASK) == W_READY_VAL);
+        total += __popc(bal[e]);
+      }
+      if (total) {
         uint32_t qb = 0;
-        if (lane == 0) qb = atoms_add(a_tail_v + 4, n0 + __popc(b1));
+        if (lane == 0) qb = atoms_add(a_tail_v + 4, total);
         qb = n_src + __shfl_sync(0xffffffffu, qb, 0);
-        if (r0) sts16(a_q + 2 * (qb + __popc(b0 & lt_mask)), an[0] - a_word);
-        if (r1) sts16(a_q + 2 * (qb + n0 + __popc(b1 & lt_mask)), an[1] - a_word);
+#pragma unroll
+        for (int e = 0; e < WIDE_PER_LANE; ++e) {
+          if (bal[e] & (1u << lane)) sts16(a_q + 2 * (qb + __popc(bal[e] & lt_mask)), an[e] - a_word);
+          qb += __popc(bal[e]);
+        }
       }
     }
     __syncthreads();
