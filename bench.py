@@ -243,35 +243,42 @@ def run_native(args):
     ms_per_step = ms / args.steps
     value = cells_total / (ms_per_step * 1e-3) / 1e9
 
-    # ---- roofline of the dominant kernel (live CUDA-event times from the timed region, this rank)
+    # ---- roofline (live CUDA-event times from the timed region, this rank).  SURVEY 8(d) states the algorithmic
+    #      bytes per stage: direction 5 B/cell, accumulation 9 B/cell (1 B code read + 8 B count write).  The
+    #      accumulation stage is three kernels -- tile pass A, the perimeter-graph solve, the final tile pass --
+    #      so its launch time is the sum of theirs; `kernels` also gives every kernel on its own share of those
+    #      bytes (pass A: the 1 B code read, final pass: the 8 B count write).
     cells_rank = cells_total // world
     per_step = {k: v[0] / args.steps for k, v in phases.items()}          # ms per step, all launches of the phase
-    per_launch = {k: v[0] / max(v[1], 1) for k, v in phases.items()}
-    dom = max(PHASE_BYTES, key=lambda k: per_step[k])
-    dom_ms = per_step[dom] if world > 1 else per_launch[dom]              # strips: the tile passes run once per step
-    achieved = cells_rank * PHASE_BYTES[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    acc_ms = per_step["acc_tile_a"] + per_step["acc_solve"] + per_step["acc_tile_b"] + per_step["strip_edge"]
+    stage_ms = {"flow_direction": per_step["direction"], "flow_accumulation": acc_ms}
+    stage_bytes = {"flow_direction": DIR_BYTES_PER_CELL, "flow_accumulation": ACC_BYTES_PER_CELL}
+    stage_kernels = {"flow_direction": "direction_kernel",
+                     "flow_accumulation": "acc_tile_kernel + pj_* (perimeter-graph solve) + acc_final_kernel"}
+
+    def gbs(bytes_per_cell, ms_):
+        return cells_rank * bytes_per_cell / (ms_ * 1e-3) / 1e9 if ms_ > 0 else None
+
+    dom = max(stage_ms, key=stage_ms.get)
+    achieved = gbs(stage_bytes[dom], stage_ms[dom]) or 0.0
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
         if tj.get("rows") == S and tj.get("cols") == S and world == 1:
-            traffic = tj.get(dom)
+            keys = ["direction"] if dom == "flow_direction" else ["acc_tile_a", "acc_solve", "acc_tile_b"]
+            traffic = float(sum(tj.get(k, 0.0) for k in keys))
     except Exception:
         pass
-    acc_ms = per_step["acc_tile_a"] + per_step["acc_solve"] + per_step["acc_tile_b"] + per_step["strip_edge"]
-
-    def gbs(bytes_per_cell, ms_):
-        return cells_rank * bytes_per_cell / (ms_ * 1e-3) / 1e9 if ms_ > 0 else None
-
     roofline = {
-        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "peak_source": peak_src, "bytes_per_cell": PHASE_BYTES[dom], "avg_launch_ms": dom_ms,
+        "bound": "hbm", "kernel": f"{dom}: {stage_kernels[dom]}", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "bytes_per_cell": stage_bytes[dom],
+        "avg_launch_ms": stage_ms[dom],
         "phases_ms_per_step": {k: round(v, 4) for k, v in per_step.items()},
-        "phase_gbs": {k: gbs(PHASE_BYTES[k], per_step[k]) for k in PHASE_BYTES},
-        "phase_frac": {k: (gbs(PHASE_BYTES[k], per_step[k]) or 0.0) / peak for k in PHASE_BYTES},
-        # the same algorithmic bytes over larger pieces of the step
-        "accumulation_9B_per_cell": {"ms": acc_ms, "gbs": gbs(ACC_BYTES_PER_CELL, acc_ms),
-                                     "frac": (gbs(ACC_BYTES_PER_CELL, acc_ms) or 0.0) / peak},
+        "stages": {k: {"ms": stage_ms[k], "bytes_per_cell": stage_bytes[k], "gbs": gbs(stage_bytes[k], stage_ms[k]),
+                       "frac": (gbs(stage_bytes[k], stage_ms[k]) or 0.0) / peak} for k in stage_ms},
+        "kernels": {k: {"ms": per_step[k], "bytes_per_cell": PHASE_BYTES[k], "gbs": gbs(PHASE_BYTES[k], per_step[k]),
+                        "frac": (gbs(PHASE_BYTES[k], per_step[k]) or 0.0) / peak} for k in PHASE_BYTES},
         "whole_step_13B_per_cell": {"ms": ms_per_step, "gbs": gbs(13.0, ms_per_step),
                                     "frac": (gbs(13.0, ms_per_step) or 0.0) / peak},
     }
