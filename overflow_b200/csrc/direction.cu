@@ -25,12 +25,12 @@
 //    monotone and injective on float32 inputs), so each class maximum and its
 //    first index come from float32 max / compares;
 //  * cardinal best c against diagonal best d: the float64 test d/sqrt(2) > c is
-//    decided by u = fma(d, 1/sqrt(2), -c) whenever |u| > 2^-21 |d| (the float32
-//    evaluation error is below 2^-23 |d|); an exact tie d/sqrt(2) == c cannot
+//    decided by u = fma(d, 1/sqrt(2), -c) whenever |u| > 2^-19 |c|, which implies
+//    |u| > 2^-21 |d| (the float32 evaluation error is below 2^-23 |d|); an exact tie d/sqrt(2) == c cannot
 //    happen for finite non-zero float32 inputs (sqrt(2) is irrational and the
 //    float64 constant is 2^-53-close to it);
-//  * everything else -- a +inf maximum (nodata neighbour), a non-finite centre,
-//    NaNs, or |u| inside the guard band -- takes d8_exact(), which re-reads the
+//  * everything else -- +inf in both classes or among the cardinals (nodata neighbours),
+//    a NODATA or non-finite centre, or |u| inside the guard band -- takes d8_exact(), which re-reads the
 //    3x3 window from shared memory and runs the reference algorithm literally in
 //    float64.
 #include <math.h>
@@ -130,13 +130,15 @@ __device__ __forceinline__ float d8_fast(float dE, float dNE, float dN, float dN
   const float id = __fmaf_rn(f_ne(dNE, d), __fmaf_rn(f_ne(dNW, d), __fmaf_rn(f_ne(dSW, d), 2.f, 2.f), 2.f), 1.f);
   const float m = fmaxf(c, d);
   const float u = __fmaf_rn(d, 0.70710678118654752f, -c);               // > 0: the diagonal is steeper
-  const float thr = __fmul_rn(__fadd_rn(fabsf(c), fabsf(d)), 4.76837158203125e-07f);  // guard band, >= 2^-21 |d|
+  // guard band: the sign of u is certain when |u| > 2^-19 |c|.  (|d| >= 4|c| makes |u| >= 0.45 |d|; otherwise
+  // 2^-19 |c| > 2^-21 |d|, eight times the evaluation error of u.)  An infinite c makes the band infinite.
+  const float thr = __fmul_rn(fabsf(c), 1.9073486328125e-06f);
   const float pos = f_gt(m, 0.f);
   float code = __fmaf_rn(f_gt(u, 0.f), __fsub_rn(id, ic), ic);
   code = __fmaf_rn(pos, __fsub_rn(code, 8.f), 8.f);
-  // exact path: sign of u not certain (includes every inf / NaN case with a positive maximum), or the
-  // maximum is -inf / NaN (non-finite or NODATA centre)
-  special = __fadd_rn(special, __fmaf_rn(pos, f_leu(fabsf(u), thr), f_leu(m, -INFINITY)));
+  // exact path: a positive maximum whose class is not certain (this includes a NaN u: +inf in both classes,
+  // or a +inf centre).  A NODATA / -inf centre is caught per row by the caller.
+  special = __fmaf_rn(pos, f_leu(fabsf(u), thr), special);
   return code;
 }
 
@@ -277,6 +279,8 @@ __device__ __forceinline__ void direction_item(const CUtensorMap* tm, const DirP
     for (int j = 0; j < 4; ++j)
       code[j] = d8_fast(/*E*/ hE[j + 1], /*NE*/ -b.uSW[j + 1], /*N*/ -b.uS[j], /*NW*/ -b.uSE[j], /*W*/ -hE[j],
                         /*SW*/ c.uSW[j], /*S*/ c.uS[j], /*SE*/ c.uSE[j + 1], special);
+    // a centre that is NODATA (-inf by now) or not finite: one test for the lane's four cells
+    special = __fadd_rn(special, f_leu(INFINITY, fabsf(__fadd_rn(__fadd_rn(b.v[1], b.v[2]), __fadd_rn(b.v[3], b.v[4])))));
     // codes are 0..8: pack pairs exactly in float, then take the low 16 bits of (value + 2^23)
     const uint32_t lo = __float_as_uint(__fadd_rn(__fmaf_rn(code[1], 256.f, code[0]), 8388608.f));
     const uint32_t hi = __float_as_uint(__fadd_rn(__fmaf_rn(code[3], 256.f, code[2]), 8388608.f));
