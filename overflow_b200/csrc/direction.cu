@@ -75,22 +75,17 @@ struct DirParams {
   int n_bands, n_chunks, chunk_rows;
 };
 
-// The reference algorithm, literally, on one 3x3 window (flow_direction.py:49-67, :91-96).
-// n[] is in scan order E,NE,N,NW,W,SW,S,SE.
-__device__ __noinline__ uint32_t d8_exact(float z, const float* n, float nd) {
-  float d[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) d[i] = (n[i] == nd) ? INFINITY : __fsub_rn(z, n[i]);
-  // a +inf slope is maximal and the first one in scan order wins; division keeps +inf
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (d[i] == INFINITY) return i;
+// The reference's scan, literally, over the eight float32 differences (centre - neighbour) of one cell in
+// scan order E,NE,N,NW,W,SW,S,SE, none of them +inf (flow_direction.py:49-67, :94-96): diagonals divided by
+// sqrt(2) in float64, first strict maximum wins, no positive slope -> undefined.
+__device__ __noinline__ uint32_t d8_slopes(float d0, float d1, float d2, float d3, float d4, float d5, float d6, float d7) {
+  const float d[8] = {d0, d1, d2, d3, d4, d5, d6, d7};
   double best = -INFINITY;
   int bi = -1;
   bool any_pos = false;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    double s = (i & 1) ? __ddiv_rn((double)d[i], 1.4142135623730951) : (double)d[i];
+    const double s = (i & 1) ? __ddiv_rn((double)d[i], 1.4142135623730951) : (double)d[i];
     if (s > best) {
       best = s;
       bi = i;
@@ -98,6 +93,22 @@ __device__ __noinline__ uint32_t d8_exact(float z, const float* n, float nd) {
     if (s > 0.0) any_pos = true;
   }
   return any_pos ? (uint32_t)bi : (uint32_t)OFL_DIR_UNDEFINED;
+}
+
+// One cell by the reference's rules: a NODATA neighbour is slope +inf, and the first +inf in scan order wins
+// (it is the first strict maximum); only a cell without one needs the float64 scan.
+__device__ __forceinline__ uint32_t d8_exact(float z, float nE, float nNE, float nN, float nNW, float nW, float nSW,
+                                             float nS, float nSE, float nd) {
+  if (z == nd) return OFL_DIR_NODATA;
+  const float n[8] = {nE, nNE, nN, nNW, nW, nSW, nS, nSE};
+  float d[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d[i] = (n[i] == nd) ? INFINITY : __fsub_rn(z, n[i]);
+  uint32_t first = 8;
+#pragma unroll
+  for (int i = 7; i >= 0; --i) first = (d[i] == INFINITY) ? (uint32_t)i : first;
+  if (first < 8) return first;
+  return d8_slopes(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
 }
 
 // 1.0f / 0.0f comparison results (SASS FSET.BF): they feed FMA-pipe arithmetic, which keeps the
@@ -186,12 +197,25 @@ __device__ __forceinline__ void direction_item(const CUtensorMap* tm, const DirP
     for (int k = 0; k < pre; ++k) issue(k);
   }
 
-  // raw window read for the exact path: rel = row relative to iy0, cx = absolute column
-  auto raw_at = [&](int rel, int cx) -> float {
+  // raw row for the exact path (no NODATA transform): columns xl-1 .. xl+4 of the row `rel` rows below iy0,
+  // still in its pipeline stage; positions outside the input array read as the fill value
+  auto raw_row = [&](int rel, float* v) {
     const int iy = iy0 + rel;
-    if (iy < 0 || iy >= p.in_rows || cx < 0 || cx >= p.W) return p.fill_raw;
     const uint32_t s = (g0 + rel / DIR_RB) % DIR_STAGES;
-    return tiles[s * DIR_STAGE_FLOATS + (rel % DIR_RB) * DIR_BOXW + (cx - x0 + 4)];
+    const float* q = tiles + s * DIR_STAGE_FLOATS + (rel % DIR_RB) * DIR_BOXW + 4 * lane;
+    const float4 m = *reinterpret_cast<const float4*>(q + 4);
+    v[0] = q[3];
+    v[1] = m.x;
+    v[2] = m.y;
+    v[3] = m.z;
+    v[4] = m.w;
+    v[5] = q[8];
+    const bool row_out = iy < 0 || iy >= p.in_rows;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int cx = xl - 1 + j;
+      if (row_out || (EDGE && (cx < 0 || cx >= p.W))) v[j] = p.fill_raw;
+    }
   };
 
   // row rr of the box at `t` into r.v; GUARD adds the out-of-array row check (first / last box only)
@@ -228,28 +252,16 @@ __device__ __forceinline__ void direction_item(const CUtensorMap* tm, const DirP
 
   // exact codes of the lane's four cells of input row i - 1 (output row y0 + i - 2), stored over the fast ones
   auto fixup = [&](int i) {
+    float r0[6], r1[6], r2[6];
+    raw_row(i - 2, r0);
+    raw_row(i - 1, r1);
+    raw_row(i, r2);
     uint32_t packed = 0;
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-      const int cx = xl + j;
-      const float z = raw_at(i - 1, cx);
-      uint32_t ex;
-      if (z == nd) {
-        ex = OFL_DIR_NODATA;
-      } else {
-        float n[8];
-        n[0] = raw_at(i - 1, cx + 1);
-        n[1] = raw_at(i - 2, cx + 1);
-        n[2] = raw_at(i - 2, cx);
-        n[3] = raw_at(i - 2, cx - 1);
-        n[4] = raw_at(i - 1, cx - 1);
-        n[5] = raw_at(i, cx - 1);
-        n[6] = raw_at(i, cx);
-        n[7] = raw_at(i, cx + 1);
-        ex = d8_exact(z, n, nd);
-      }
-      packed |= ex << (8 * j);
-    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      packed |= d8_exact(r1[j + 1], /*E*/ r1[j + 2], /*NE*/ r0[j + 2], /*N*/ r0[j + 1], /*NW*/ r0[j], /*W*/ r1[j],
+                         /*SW*/ r2[j], /*S*/ r2[j + 1], /*SE*/ r2[j + 2], nd)
+                << (8 * j);
     uint8_t* o = p.out + (int64_t)(y0 + i - 2) * p.ld_out + xl;
     if (!EDGE || full_store) {
       *reinterpret_cast<uint32_t*>(o) = packed;
