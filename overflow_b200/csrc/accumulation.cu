@@ -422,15 +422,23 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     a_own = a_word0 + (py * WP + px) * 4;
     const uint32_t w_own = lds32(a_own);
     const bool live = valid && (w_own & W_LIVE);
-    // does the cell at (py, px) + direction d lie outside the tile box and flow back into this cell?
-    auto inflow = [&](int d) -> bool {
-      const int ny = py + dir_dy(d), nx = px + dir_dx(d);
-      if ((uint32_t)ny < (uint32_t)AT && (uint32_t)nx < (uint32_t)AT) return false;
-      return (lds8(a_word + ((ny + 1) * WP + nx + WX0) * 4) >> 2) == (uint32_t)((d + 4) & 7);
-    };
-    const int d0 = (0x7351 >> (4 * side)) & 7;  // the three directions pointing out of this side: from NE, SW, NW, SE on
-    bool target = inflow(d0) | inflow((d0 + 1) & 7) | inflow((d0 + 2) & 7);
+    // Does a cell outside the tile flow into this one?  The three candidates of a side sit next to each
+    // other on the halo row / column facing it: word hb + {+1, 0, -1} * step, and the codes that point back
+    // at this cell are three consecutive ones.  (On the cut sides of a partial tile this looks at halo
+    // words beyond the raster, which flow nowhere; those cells are raster-edge cells anyway.)
+    const int hb = side == 0 ? WX0 + k : side == 1 ? (AT + 1) * WP + WX0 + k : (k + 1) * WP + (side == 2 ? WX0 - 1 : WX0 + AT);
+    const int step = ((side == 0 || side == 3) ? 1 : -1) * (side < 2 ? 1 : WP);
+    const uint32_t back0 = (0x3715u >> (4 * side)) & 7u;  // sides top, bottom, left, right: SW, NE, SE, NW first
+    const uint32_t ah = a_word + hb * 4;
+    bool target = (lds8(ah + step * 4) >> 2) == back0;
+    target |= (lds8(ah) >> 2) == ((back0 + 1) & 7u);
+    target |= (lds8(ah - step * 4) >> 2) == ((back0 + 2) & 7u);
     if (side < 2 && (k == 0 || k == w - 1)) {  // corner: the two directions of the adjoining side
+      auto inflow = [&](int d) -> bool {
+        const int ny = py + dir_dy(d), nx = px + dir_dx(d);
+        if ((uint32_t)ny < (uint32_t)AT && (uint32_t)nx < (uint32_t)AT) return false;
+        return (lds8(a_word + ((ny + 1) * WP + nx + WX0) * 4) >> 2) == (uint32_t)((d + 4) & 7);
+      };
       const int e = k == 0 ? 4 : 0;
       target |= inflow(e) | inflow(k == 0 ? (side == 0 ? 5 : 3) : (side == 0 ? 7 : 1));
     }
@@ -826,8 +834,11 @@ __device__ __forceinline__ void block_append(int32_t* seg_list, int* s_counter, 
 }
 
 // counts layout: [round][2][blocks] ints; round r's input counts are written by round r-1 (r = 0: init)
+// Also zeroes the delta-buffer entries of the active nodes: deltas are only ever written for a node that
+// still has a pointer to jump along, i.e. one that starts out active, so the rest need no clearing.
 __global__ void pj_init_kernel(const int32_t* __restrict__ succ, int32_t* __restrict__ ptr_a, int32_t* __restrict__ ptr_b,
-                               int32_t* __restrict__ list0, int* __restrict__ counts0, PjSeg g) {
+                               int32_t* __restrict__ list0, int* __restrict__ counts0, unsigned long long* __restrict__ d0,
+                               unsigned long long* __restrict__ d1, PjSeg g) {
   __shared__ int s_cnt;
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
@@ -841,6 +852,8 @@ __global__ void pj_init_kernel(const int32_t* __restrict__ succ, int32_t* __rest
       active = sc >= 0;
       if (active) {
         ptr_a[u] = sc;
+        d0[u] = 0;
+        d1[u] = 0;
       } else {
         ptr_a[u] = ~(int32_t)u;
         ptr_b[u] = ~(int32_t)u;
@@ -912,10 +925,9 @@ __global__ void pj_round_kernel(const int32_t* __restrict__ list_in, int32_t* __
   }
 }
 
-__global__ void pj_fold_kernel(unsigned long long* __restrict__ S, const unsigned long long* __restrict__ d0,
-                               const unsigned long long* __restrict__ d1, int64_t n) {
+__global__ void pj_add_kernel(unsigned long long* __restrict__ S, const unsigned long long* __restrict__ S2, int64_t n) {
   for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < n; u += (int64_t)gridDim.x * blockDim.x) {
-    const unsigned long long d = d0[u] + d1[u];
+    const unsigned long long d = S2[u];
     if (d) S[u] += d;
   }
 }
@@ -1060,7 +1072,7 @@ constexpr int PJ_MAX_BLOCKS = 148 * 8 * 2;  // counts are sized for this many se
 
 // Subtree sums over the forest `succ` (succ[u] = parent node or -1): on return (stream order) S[u] holds
 // the sum of the initial S over u's subtree and ptr_a holds ~root(u) for every node.  succ is preserved.
-// lists: 2 * (blocks * seg) int32; counts: (PJ_MAX_ROUNDS + 2) * 2 * blocks ints; d0/d1 zero on entry.
+// lists: 2 * (blocks * seg) int32; counts: (PJ_MAX_ROUNDS + 2) * 2 * blocks ints; d0/d1 need no initialisation.
 // Does not synchronise: *leftover is set when the forest did not converge (a cycle).
 static int pj_solve(const int32_t* succ, int32_t* ptr_a, int32_t* ptr_b, int32_t* lists, int* counts, int* leftover,
                     unsigned long long* S, unsigned long long* d0, unsigned long long* d1, int64_t n, cudaStream_t st) {
@@ -1069,7 +1081,7 @@ static int pj_solve(const int32_t* succ, int32_t* ptr_a, int32_t* ptr_b, int32_t
   const int rounds = pj_rounds_for(n);
   int32_t* list[2] = {lists, lists + (int64_t)g.blocks * g.seg};
   const int cstride = 2 * g.blocks;
-  pj_init_kernel<<<g.blocks, 256, 0, st>>>(succ, ptr_a, ptr_b, list[0], counts, g);
+  pj_init_kernel<<<g.blocks, 256, 0, st>>>(succ, ptr_a, ptr_b, list[0], counts, d0, d1, g);
   OFL_CHECK_LAUNCH();
   int32_t* cur = ptr_a;
   int32_t* nxt = ptr_b;
@@ -1084,7 +1096,7 @@ static int pj_solve(const int32_t* succ, int32_t* ptr_a, int32_t* ptr_b, int32_t
   }
   pj_leftover_kernel<<<1, 256, 0, st>>>(counts + (int64_t)rounds * cstride, g.blocks, leftover);
   OFL_CHECK_LAUNCH();
-  return OFL_OK;  // every delta has been flushed into S: d0 / d1 are all zero again
+  return OFL_OK;
 }
 
 // One synchronisation at the end of a call: err[0] = cycle seen by a tile kernel, err[1] = a solve did
@@ -1144,9 +1156,10 @@ size_t strip_workspace_bytes(int64_t rows, int64_t cols) {
   return graph_layout(node_count(rows, cols), true).total;
 }
 
-// Zero [from_off, off_link) of the workspace (sums and delta buffers) and the error flags.
+// Zero the sums [from_off, off_d0) of the workspace (the solve clears what it uses of the delta buffers
+// itself) and the error flags.
 static int ws_begin(uint8_t* ws, const GraphLayout& L, size_t from_off, cudaStream_t st) {
-  OFL_CUDA(cudaMemsetAsync(ws + from_off, 0, L.off_link - from_off, st));
+  OFL_CUDA(cudaMemsetAsync(ws + from_off, 0, L.off_d0 - from_off, st));
   OFL_CUDA(cudaMemsetAsync(ws + L.off_err, 0, 64, st));
   return OFL_OK;
 }
@@ -1227,7 +1240,7 @@ int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t 
   int rc = acc_setup(C, fdr, rows, cols, ld_fdr, 0, 0, 0, fac, ld_fac, workspace, workspace_bytes, false);
   if (rc != OFL_OK) return rc;
   const GraphLayout& L = C.L;
-  rc = ws_begin(C.ws, L, L.off_S, st);  // S, d0, d1
+  rc = ws_begin(C.ws, L, L.off_S, st);  // S
   if (rc != OFL_OK) return rc;
   {
     PhaseScope ps(PHASE_ACC_TILE_A, st);
@@ -1365,7 +1378,7 @@ int strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
   int rc = strip_setup(C, fdr_halo, rows, cols, ld_fdr, has_above, has_below, fac, ld_fac, workspace, workspace_bytes);
   if (rc != OFL_OK) return rc;
   const GraphLayout& L = C.L;
-  rc = ws_begin(C.ws, L, L.off_S, st);  // S, S2, d0, d1
+  rc = ws_begin(C.ws, L, L.off_S, st);  // S, S2
   if (rc != OFL_OK) return rc;
   {
     PhaseScope ps(PHASE_ACC_TILE_A, st);
@@ -1436,17 +1449,14 @@ int strip_accum_final(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
   const GraphLayout& L = C.L;
   // inflow from other strips enters at the boundary rows; by linearity its effect on every perimeter
   // node is the subtree sum of those seeds over the strip's (preserved) perimeter forest
-  rc = ws_begin(C.ws, L, L.off_S2, st);  // S2, d0, d1
+  rc = ws_begin(C.ws, L, L.off_S2, st);  // S2
   if (rc != OFL_OK) return rc;
   strip_seed_kernel<<<grid_for(2 * cols, 8), 256, 0, st>>>(J_mine, C.p, C.S2);
   OFL_CHECK_LAUNCH();
   {
     PhaseScope ps(PHASE_ACC_SOLVE, st);
     rc = pj_solve(C.p.succ, C.pa, C.pb, C.lists, C.counts, C.p.err + 1, C.S2, C.d0, C.d1, L.n, st);
-    if (rc == OFL_OK) {
-      OFL_CUDA(cudaMemsetAsync(C.d0, 0, (size_t)L.n * 8, st));
-      pj_fold_kernel<<<grid_for(L.n, 8), 256, 0, st>>>(C.p.S, C.S2, C.d0, L.n);  // S += S2
-    }
+    if (rc == OFL_OK) pj_add_kernel<<<grid_for(L.n, 8), 256, 0, st>>>(C.p.S, C.S2, L.n);  // S += S2
   }
   if (rc != OFL_OK) return rc;
   OFL_CHECK_LAUNCH();
