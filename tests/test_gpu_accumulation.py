@@ -210,3 +210,29 @@ def test_wide_final_pass_matches(monkeypatch):
     monkeypatch.delenv("OFL_FORCE_WIDE_FINAL")
     fac, _ = single_tile_flow_accumulation(fdr)
     assert np.array_equal(fac, want)
+
+
+def test_random_shapes_counts_and_links():
+    """Seeded sweep over ragged shapes around the 64-cell tile size (partial tiles, one-cell-wide
+    tiles, nodata on tile corners): counts and perimeter links against the oracle."""
+    rng = np.random.default_rng(2024)
+    sides = [1, 2, 3, 63, 64, 65, 66, 127, 128, 129, 130, 191, 193, 257]
+    for trial in range(40):
+        rows, cols = int(rng.choice(sides)), int(rng.choice(sides))
+        beta = float(rng.choice([2.0, 3.0, 4.0]))
+        dem = synth.fractal(max(rows, 2), max(cols, 2), beta=beta, seed=100 + trial)[:rows, :cols]
+        if trial % 3 == 0:
+            dem = np.floor(dem / 25.0).astype(np.float32)  # terraces: plateaus of undefined cells
+        dem = np.ascontiguousarray(dem)
+        if rows * cols > 16 and trial % 2 == 0:
+            dem = synth.punch_holes(dem, frac=0.05, seed=trial)
+        for y in range(63, rows, 64):  # nodata straddling tile corners
+            for x in range(63, cols, 64):
+                if (y + x + trial) % 3 == 0:
+                    dem[y : y + 2, x : x + 2] = synth.NODATA
+        fdr = np.ascontiguousarray(
+            oracle.flow_direction_for_tile(synth.pad_nodata(dem), synth.NODATA)[1:-1, 1:-1])
+        fac, links = stfa(fdr)
+        want_fac, want_links = oracle.single_tile_flow_accumulation(fdr)
+        assert np.array_equal(fac, want_fac), (trial, rows, cols)
+        assert np.array_equal(links, want_links), (trial, rows, cols)
