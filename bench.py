@@ -186,7 +186,19 @@ def run_native(args):
     torch.cuda.set_device(local)
     _native.init(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL announces its version on stdout when the first communicator comes up; stdout carries exactly
+        # one JSON line, so that goes to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     S = args.size
     peak, peak_src = measured_hbm_peak()
