@@ -31,7 +31,9 @@
 // inside the raster and code(c) != 9.  Codes >= 8 have no downstream cell (the reference's
 // out-of-bounds NEIGHBOR_OFFSETS read); NODATA cells end at -9998 (:119-121,129-137).
 #include <cstdlib>
+#include <mutex>
 #include <type_traits>
+#include <vector>
 
 #include "common.cuh"
 
@@ -1074,28 +1076,92 @@ constexpr int PJ_MAX_BLOCKS = 148 * 8 * 2;  // counts are sized for this many se
 // the sum of the initial S over u's subtree and ptr_a holds ~root(u) for every node.  succ is preserved.
 // lists: 2 * (blocks * seg) int32; counts: (PJ_MAX_ROUNDS + 2) * 2 * blocks ints; d0/d1 need no initialisation.
 // Does not synchronise: *leftover is set when the forest did not converge (a cycle).
-static int pj_solve(const int32_t* succ, int32_t* ptr_a, int32_t* ptr_b, int32_t* lists, int* counts, int* leftover,
-                    unsigned long long* S, unsigned long long* d0, unsigned long long* d1, int64_t n, cudaStream_t st) {
+static int pj_solve_launch(const int32_t* succ, int32_t* ptr_a, int32_t* ptr_b, int32_t* lists, int* counts,
+                           int* leftover, unsigned long long* S, unsigned long long* d0, unsigned long long* d1, int64_t n,
+                           cudaStream_t st, int* n_kernels) {
   const PjSeg g = pj_segments(n);
   OFL_REQUIRE(g.blocks <= PJ_MAX_BLOCKS, OFL_ERR_INVALID, "device has too many SMs for the solve's counter table");
   const int rounds = pj_rounds_for(n);
   int32_t* list[2] = {lists, lists + (int64_t)g.blocks * g.seg};
   const int cstride = 2 * g.blocks;
   pj_init_kernel<<<g.blocks, 256, 0, st>>>(succ, ptr_a, ptr_b, list[0], counts, d0, d1, g);
-  OFL_CHECK_LAUNCH();
+  OFL_CUDA(cudaGetLastError());
   int32_t* cur = ptr_a;
   int32_t* nxt = ptr_b;
   for (int j = 0; j < rounds; ++j) {
     pj_round_kernel<<<g.blocks, 256, 0, st>>>(list[j & 1], list[(j + 1) & 1], counts + (int64_t)j * cstride,
                                               counts + (int64_t)(j + 1) * cstride, cur, nxt, S, (j & 1) ? d1 : d0,
                                               (j & 1) ? d0 : d1, g);
-    OFL_CHECK_LAUNCH();
+    OFL_CUDA(cudaGetLastError());
     int32_t* t = cur;
     cur = nxt;
     nxt = t;
   }
   pj_leftover_kernel<<<1, 256, 0, st>>>(counts + (int64_t)rounds * cstride, g.blocks, leftover);
-  OFL_CHECK_LAUNCH();
+  OFL_CUDA(cudaGetLastError());
+  *n_kernels = rounds + 2;
+  return OFL_OK;
+}
+
+// The solve is a fixed sequence of ~30 small kernels whose arguments depend only on the workspace
+// addresses and the node count, and on a strip of an 8-GPU run they finish faster than the host can
+// launch them.  It is therefore captured once per (addresses, n) into a CUDA graph and replayed.
+struct PjGraphKey {
+  const void *succ, *pa, *pb, *lists, *counts, *leftover, *S, *d0, *d1;
+  int64_t n;
+  int device;
+  bool operator==(const PjGraphKey& o) const {
+    return succ == o.succ && pa == o.pa && pb == o.pb && lists == o.lists && counts == o.counts && leftover == o.leftover &&
+           S == o.S && d0 == o.d0 && d1 == o.d1 && n == o.n && device == o.device;
+  }
+};
+struct PjGraphEntry {
+  PjGraphKey key;
+  cudaGraphExec_t exec;
+  int n_kernels;
+};
+static std::mutex g_pj_mu;
+static std::vector<PjGraphEntry> g_pj_graphs;
+static cudaStream_t g_pj_capture_stream = nullptr;  // capture is not allowed on the legacy default stream
+
+static int pj_solve(const int32_t* succ, int32_t* ptr_a, int32_t* ptr_b, int32_t* lists, int* counts, int* leftover,
+                    unsigned long long* S, unsigned long long* d0, unsigned long long* d1, int64_t n, cudaStream_t st) {
+  int n_kernels = 0;
+  if (getenv("OFL_NO_GRAPHS")) {
+    const int rc = pj_solve_launch(succ, ptr_a, ptr_b, lists, counts, leftover, S, d0, d1, n, st, &n_kernels);
+    if (rc == OFL_OK) count_launch(n_kernels);
+    return rc;
+  }
+  PjGraphKey key{succ, ptr_a, ptr_b, lists, counts, leftover, S, d0, d1, n, 0};
+  OFL_CUDA(cudaGetDevice(&key.device));
+  std::lock_guard<std::mutex> lk(g_pj_mu);
+  PjGraphEntry* hit = nullptr;
+  for (auto& e : g_pj_graphs)
+    if (e.key == key) hit = &e;
+  if (!hit) {
+    if (g_pj_graphs.size() >= 32) {  // workspaces come and go: start over rather than grow without bound
+      for (auto& e : g_pj_graphs) cudaGraphExecDestroy(e.exec);
+      g_pj_graphs.clear();
+    }
+    if (!g_pj_capture_stream) OFL_CUDA(cudaStreamCreateWithFlags(&g_pj_capture_stream, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    OFL_CUDA(cudaStreamBeginCapture(g_pj_capture_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = pj_solve_launch(succ, ptr_a, ptr_b, lists, counts, leftover, S, d0, d1, n, g_pj_capture_stream, &n_kernels);
+    const cudaError_t ce = cudaStreamEndCapture(g_pj_capture_stream, &graph);
+    if (rc != OFL_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    OFL_CUDA(ce);
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    OFL_CUDA(ie);
+    g_pj_graphs.push_back(PjGraphEntry{key, exec, n_kernels});
+    hit = &g_pj_graphs.back();
+  }
+  OFL_CUDA(cudaGraphLaunch(hit->exec, st));
+  count_launch(hit->n_kernels);
   return OFL_OK;
 }
 
