@@ -108,7 +108,42 @@ struct AccParams {
   int vec_store;  // fac rows are 16-byte aligned: the final pass may use 16-byte stores
   int* wide_list;  // [0]: number of tiles the 32-bit final pass left to the 64-bit variant, [1..]: their ids
   int force_wide;  // test hook: send every tile with an inflow through the 64-bit variant
+  // whole-raster calls: pass A publishes its slots straight into the solve's initial state (pointer
+  // buffers, cleared delta entries, per-segment active lists) instead of `succ` + a separate init kernel
+  int fuse_init;
+  int32_t *ptr_a, *ptr_b, *list0;
+  unsigned long long *d0, *d1;
+  int* counts0;
+  int tiles_per_seg;
+  long long seg;
 };
+
+// Result of Alg. 2 for one perimeter slot (all 32 lanes call; `mine`: this lane has a slot to publish).
+__device__ __forceinline__ void publish_slot(const AccParams& p, int tile, bool mine, uint32_t slot, int32_t succ,
+                                             uint32_t lt_mask, int lane) {
+  const size_t u = (size_t)tile * SLOTS + slot;
+  if (!p.fuse_init) {
+    if (mine) p.succ[u] = succ;
+    return;
+  }
+  const bool active = mine && succ >= 0;
+  if (active) {
+    p.ptr_a[u] = succ;
+    p.d0[u] = 0;
+    p.d1[u] = 0;
+  } else if (mine) {
+    p.ptr_a[u] = ~(int32_t)u;
+    p.ptr_b[u] = ~(int32_t)u;
+  }
+  const uint32_t bal = __ballot_sync(0xffffffffu, active);
+  if (bal) {
+    const int sidx = tile / p.tiles_per_seg;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&p.counts0[sidx], __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (active) p.list0[(size_t)sidx * p.seg + base + __popc(bal & lt_mask)] = (int32_t)u;
+  }
+}
 
 __device__ __forceinline__ int node_of_cell(int gy, int gx, const AccParams& p) {
   const int ty = gy >> AT_SHIFT, tx = gx >> AT_SHIFT;
@@ -463,9 +498,9 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     if (follow) {
       sts8(sb + SM::LIST + lb + __popc(bal & lt_mask), tid);
     } else {
-      p.succ[(size_t)tile * SLOTS + tid] = -1;
       p.link[(size_t)tile * SLOTS + tid] = (uint16_t)((valid ? tid : 0) | (KIND_TERM << 8));
     }
+    publish_slot(p, tile, !follow, tid, -1, lt_mask, lane);
   }
   __syncthreads();
 
@@ -566,12 +601,12 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
       }
     }
     __syncwarp();  // classify once per warp, not once per exit path
+    int32_t succ = -1;
     if (walker) {
       // aw: the last live in-tile cell of the path; an / wn: the word it steps to when the path leaves
       const int j = (int)(aw - a_word) >> 2;
       const int cy = j / WP - 1, cx = j - (cy + 1) * WP - WX0;
       uint32_t kind = KIND_TERM;
-      int32_t succ = -1;
       if (exited) {
         const int jn = (int)(an - a_word) >> 2;
         const int ny = jn / WP - 1, nx = jn - (ny + 1) * WP - WX0;
@@ -584,9 +619,9 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
         }
       }
       const int ls = slot_of(cy, cx, h, w);
-      p.succ[(size_t)tile * SLOTS + slot] = succ;
       p.link[(size_t)tile * SLOTS + slot] = (uint16_t)((ls < 0 ? 0 : ls) | (kind << 8));
     }
+    publish_slot(p, tile, walker, slot, succ, lt_mask, lane);
   }
   __syncthreads();  // all chains are finished: counts are final
 
@@ -1066,7 +1101,7 @@ static PjSeg pj_segments(int64_t n) {
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  g.seg = ((n + blocks - 1) / blocks + 31) / 32 * 32;
+  g.seg = ((n + blocks - 1) / blocks + SLOTS - 1) / SLOTS * SLOTS;  // whole tiles (pass A appends to the lists per tile)
   g.blocks = (int)((n + g.seg - 1) / g.seg);
   return g;
 }
@@ -1078,14 +1113,16 @@ constexpr int PJ_MAX_BLOCKS = 148 * 8 * 2;  // counts are sized for this many se
 // Does not synchronise: *leftover is set when the forest did not converge (a cycle).
 static int pj_solve_launch(const int32_t* succ, int32_t* ptr_a, int32_t* ptr_b, int32_t* lists, int* counts,
                            int* leftover, unsigned long long* S, unsigned long long* d0, unsigned long long* d1, int64_t n,
-                           cudaStream_t st, int* n_kernels) {
+                           bool with_init, cudaStream_t st, int* n_kernels) {
   const PjSeg g = pj_segments(n);
   OFL_REQUIRE(g.blocks <= PJ_MAX_BLOCKS, OFL_ERR_INVALID, "device has too many SMs for the solve's counter table");
   const int rounds = pj_rounds_for(n);
   int32_t* list[2] = {lists, lists + (int64_t)g.blocks * g.seg};
   const int cstride = 2 * g.blocks;
-  pj_init_kernel<<<g.blocks, 256, 0, st>>>(succ, ptr_a, ptr_b, list[0], counts, d0, d1, g);
-  OFL_CUDA(cudaGetLastError());
+  if (with_init) {
+    pj_init_kernel<<<g.blocks, 256, 0, st>>>(succ, ptr_a, ptr_b, list[0], counts, d0, d1, g);
+    OFL_CUDA(cudaGetLastError());
+  }
   int32_t* cur = ptr_a;
   int32_t* nxt = ptr_b;
   for (int j = 0; j < rounds; ++j) {
@@ -1099,7 +1136,7 @@ static int pj_solve_launch(const int32_t* succ, int32_t* ptr_a, int32_t* ptr_b, 
   }
   pj_leftover_kernel<<<1, 256, 0, st>>>(counts + (int64_t)rounds * cstride, g.blocks, leftover);
   OFL_CUDA(cudaGetLastError());
-  *n_kernels = rounds + 2;
+  *n_kernels = rounds + 1 + (with_init ? 1 : 0);
   return OFL_OK;
 }
 
@@ -1110,8 +1147,9 @@ struct PjGraphKey {
   const void *succ, *pa, *pb, *lists, *counts, *leftover, *S, *d0, *d1;
   int64_t n;
   int device;
+  bool with_init;
   bool operator==(const PjGraphKey& o) const {
-    return succ == o.succ && pa == o.pa && pb == o.pb && lists == o.lists && counts == o.counts && leftover == o.leftover &&
+    return with_init == o.with_init && succ == o.succ && pa == o.pa && pb == o.pb && lists == o.lists && counts == o.counts && leftover == o.leftover &&
            S == o.S && d0 == o.d0 && d1 == o.d1 && n == o.n && device == o.device;
   }
 };
@@ -1124,15 +1162,17 @@ static std::mutex g_pj_mu;
 static std::vector<PjGraphEntry> g_pj_graphs;
 static cudaStream_t g_pj_capture_stream = nullptr;  // capture is not allowed on the legacy default stream
 
+// with_init = false: the caller (pass A) has already published pointers, delta entries, list 0 and counts 0.
 static int pj_solve(const int32_t* succ, int32_t* ptr_a, int32_t* ptr_b, int32_t* lists, int* counts, int* leftover,
-                    unsigned long long* S, unsigned long long* d0, unsigned long long* d1, int64_t n, cudaStream_t st) {
+                    unsigned long long* S, unsigned long long* d0, unsigned long long* d1, int64_t n, cudaStream_t st,
+                    bool with_init = true) {
   int n_kernels = 0;
   if (getenv("OFL_NO_GRAPHS")) {
-    const int rc = pj_solve_launch(succ, ptr_a, ptr_b, lists, counts, leftover, S, d0, d1, n, st, &n_kernels);
+    const int rc = pj_solve_launch(succ, ptr_a, ptr_b, lists, counts, leftover, S, d0, d1, n, with_init, st, &n_kernels);
     if (rc == OFL_OK) count_launch(n_kernels);
     return rc;
   }
-  PjGraphKey key{succ, ptr_a, ptr_b, lists, counts, leftover, S, d0, d1, n, 0};
+  PjGraphKey key{succ, ptr_a, ptr_b, lists, counts, leftover, S, d0, d1, n, 0, with_init};
   OFL_CUDA(cudaGetDevice(&key.device));
   std::lock_guard<std::mutex> lk(g_pj_mu);
   PjGraphEntry* hit = nullptr;
@@ -1146,7 +1186,8 @@ static int pj_solve(const int32_t* succ, int32_t* ptr_a, int32_t* ptr_b, int32_t
     if (!g_pj_capture_stream) OFL_CUDA(cudaStreamCreateWithFlags(&g_pj_capture_stream, cudaStreamNonBlocking));
     cudaGraph_t graph = nullptr;
     OFL_CUDA(cudaStreamBeginCapture(g_pj_capture_stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = pj_solve_launch(succ, ptr_a, ptr_b, lists, counts, leftover, S, d0, d1, n, g_pj_capture_stream, &n_kernels);
+    const int rc = pj_solve_launch(succ, ptr_a, ptr_b, lists, counts, leftover, S, d0, d1, n, with_init, g_pj_capture_stream,
+                                   &n_kernels);
     const cudaError_t ce = cudaStreamEndCapture(g_pj_capture_stream, &graph);
     if (rc != OFL_OK) {
       if (graph) cudaGraphDestroy(graph);
@@ -1268,6 +1309,18 @@ static int acc_setup(AccCtx& C, const uint8_t* fdr, int64_t rows, int64_t cols, 
   p.L = reinterpret_cast<uint16_t*>(C.ws + C.L.off_L);
   p.wide_list = reinterpret_cast<int*>(C.ws + C.L.off_wide);
   p.force_wide = getenv("OFL_FORCE_WIDE_FINAL") ? 1 : 0;
+  {
+    const PjSeg g = pj_segments(n);
+    p.fuse_init = (!strip && !getenv("OFL_NO_FUSED_INIT")) ? 1 : 0;
+    p.ptr_a = reinterpret_cast<int32_t*>(C.ws + C.L.off_pa);
+    p.ptr_b = reinterpret_cast<int32_t*>(C.ws + C.L.off_pb);
+    p.list0 = reinterpret_cast<int32_t*>(C.ws + C.L.off_lists);
+    p.d0 = reinterpret_cast<unsigned long long*>(C.ws + C.L.off_d0);
+    p.d1 = reinterpret_cast<unsigned long long*>(C.ws + C.L.off_d1);
+    p.counts0 = reinterpret_cast<int*>(C.ws + C.L.off_counts);
+    p.tiles_per_seg = (int)(g.seg / SLOTS);
+    p.seg = g.seg;
+  }
   p.y_off = y_off;
   p.strip_above = has_above ? 1 : 0;
   p.strip_below = has_below ? 1 : 0;
@@ -1308,6 +1361,8 @@ int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t 
   const GraphLayout& L = C.L;
   rc = ws_begin(C.ws, L, L.off_S, st);  // S
   if (rc != OFL_OK) return rc;
+  if (C.p.fuse_init)  // round 0's active / retired counts: pass A adds to the first, nothing retires before round 0
+    OFL_CUDA(cudaMemsetAsync(C.counts, 0, 2 * (size_t)PJ_MAX_BLOCKS * sizeof(int), st));
   {
     PhaseScope ps(PHASE_ACC_TILE_A, st);
     acc_tile_kernel<<<(unsigned)C.ntiles, ACC_THREADS, TileSmem::BYTES + tile_extra_smem(), st>>>(C.tm, C.p);
@@ -1315,7 +1370,7 @@ int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t 
   OFL_CHECK_LAUNCH();
   {
     PhaseScope ps(PHASE_ACC_SOLVE, st);
-    rc = pj_solve(C.p.succ, C.pa, C.pb, C.lists, C.counts, C.p.err + 1, C.p.S, C.d0, C.d1, L.n, st);
+    rc = pj_solve(C.p.succ, C.pa, C.pb, C.lists, C.counts, C.p.err + 1, C.p.S, C.d0, C.d1, L.n, st, !C.p.fuse_init);
   }
   if (rc != OFL_OK) return rc;
   {
