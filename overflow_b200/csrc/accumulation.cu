@@ -1061,19 +1061,11 @@ int64_t perimeter_count(int64_t rows, int64_t cols) {
 
 constexpr int PJ_MAX_ROUNDS = 40;
 
-static int tile_extra_smem() {
-  static int extra = -1;
-  if (extra < 0) {
-    const char* e = getenv("OFL_ACC_EXTRA_SMEM");
-    extra = e ? atoi(e) : 0;
-  }
-  return extra;
-}
 static int ensure_tile_attrs() {
   static bool attr_set = false;
   if (!attr_set) {
     OFL_CUDA(cudaFuncSetAttribute(acc_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  TileSmem::BYTES + tile_extra_smem()));
+                                  TileSmem::BYTES));
     OFL_CUDA(cudaFuncSetAttribute(acc_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FinalSmem::BYTES_FAST));
     OFL_CUDA(cudaFuncSetAttribute(acc_final_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   FinalSmem::BYTES_WIDE));
@@ -1365,7 +1357,7 @@ int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t 
     OFL_CUDA(cudaMemsetAsync(C.counts, 0, 2 * (size_t)PJ_MAX_BLOCKS * sizeof(int), st));
   {
     PhaseScope ps(PHASE_ACC_TILE_A, st);
-    acc_tile_kernel<<<(unsigned)C.ntiles, ACC_THREADS, TileSmem::BYTES + tile_extra_smem(), st>>>(C.tm, C.p);
+    acc_tile_kernel<<<(unsigned)C.ntiles, ACC_THREADS, TileSmem::BYTES, st>>>(C.tm, C.p);
   }
   OFL_CHECK_LAUNCH();
   {
@@ -1503,7 +1495,7 @@ int strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
   if (rc != OFL_OK) return rc;
   {
     PhaseScope ps(PHASE_ACC_TILE_A, st);
-    acc_tile_kernel<<<(unsigned)C.ntiles, ACC_THREADS, TileSmem::BYTES + tile_extra_smem(), st>>>(C.tm, C.p);
+    acc_tile_kernel<<<(unsigned)C.ntiles, ACC_THREADS, TileSmem::BYTES, st>>>(C.tm, C.p);
   }
   OFL_CHECK_LAUNCH();
   {
