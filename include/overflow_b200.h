@@ -114,6 +114,17 @@ int ofl_phase_timing_read(double* ms, int64_t* counts, int n, int reset);
 int ofl_flow_direction_f32(const float* dem, int64_t rows, int64_t cols, int64_t ld_dem, double nodata,
                            uint8_t* fdr, int64_t ld_fdr, int mode, int mem_kind, void* stream);
 
+/*
+ * The same stencil for DEMs that are not float32.  The reference's arithmetic follows the array's dtype
+ * (flow_direction.py:94-96 under numba): float64 differences for float64, int64 for the signed integer
+ * types, and uint64 -- with wrap-around for uphill neighbours -- for the unsigned ones; callers widen their
+ * elements to one of these three 8-byte kinds (exact for every integer type).  Arguments as for
+ * ofl_flow_direction_f32; device pointers need 8-byte alignment for dem, 4-byte for fdr.
+ */
+typedef enum ofl_elem_kind { OFL_ELEM_F64 = 0, OFL_ELEM_I64 = 1, OFL_ELEM_U64 = 2 } ofl_elem_kind;
+int ofl_flow_direction_x64(const void* dem, int elem_kind, int64_t rows, int64_t cols, int64_t ld_dem, double nodata,
+                           uint8_t* fdr, int64_t ld_fdr, int mode, int mem_kind, void* stream);
+
 /* Perimeter entries of `links` in perimeter_indices order (flow_accumulation.py:40-51). */
 int64_t ofl_perimeter_count(int64_t rows, int64_t cols);
 

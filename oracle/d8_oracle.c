@@ -115,8 +115,26 @@ static inline double orc_slope_f64(double z, double n, int diagonal, double noda
     }                                                                                 \
   }
 
+/* Integer DEMs: numba takes the difference in int64 for signed element types and in uint64 for
+ * unsigned ones -- an uphill neighbour wraps around to ~2^64 -- and widens it to float64 for the
+ * division (flow_direction.py:94-96; typing probed with numba 0.65).  The nodata test compares the
+ * element widened to float64 (:91). */
+static inline double orc_slope_i64(int64_t z, int64_t n, int diagonal, double nodata) {
+  if ((double)n == nodata) return INFINITY;
+  int64_t diff = (int64_t)((uint64_t)z - (uint64_t)n); /* two's-complement wrap, like int64 */
+  return (double)diff / (diagonal ? sqrt(2.0) : 1.0);
+}
+
+static inline double orc_slope_u64(uint64_t z, uint64_t n, int diagonal, double nodata) {
+  if ((double)n == nodata) return INFINITY;
+  uint64_t diff = z - n; /* modulo 2^64 */
+  return (double)diff / (diagonal ? sqrt(2.0) : 1.0);
+}
+
 ORC_DEFINE_DIRECTION(orc_flow_direction_f32, float, orc_slope_f32)
 ORC_DEFINE_DIRECTION(orc_flow_direction_f64, double, orc_slope_f64)
+ORC_DEFINE_DIRECTION(orc_flow_direction_i64, int64_t, orc_slope_i64)
+ORC_DEFINE_DIRECTION(orc_flow_direction_u64, uint64_t, orc_slope_u64)
 
 /* ---------------------------------------------------------------------------
  * get_next_cell -- src/overflow/flow_accumulation.py:13-37

@@ -33,7 +33,7 @@ def _load():
     build()
     lib = ctypes.CDLL(_SO)
     i64, f64, vp = ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
-    for name in ("orc_flow_direction_f32", "orc_flow_direction_f64"):
+    for name in ("orc_flow_direction_f32", "orc_flow_direction_f64", "orc_flow_direction_i64", "orc_flow_direction_u64"):
         fn = getattr(lib, name)
         fn.argtypes = [vp, i64, i64, i64, f64, vp, i64, ctypes.c_int]
         fn.restype = None
@@ -72,8 +72,14 @@ def flow_direction_for_tile(dem, nodata_value, border=9):
         fn = _load().orc_flow_direction_f32
     elif dem.dtype == np.float64:
         fn = _load().orc_flow_direction_f64
+    elif np.issubdtype(dem.dtype, np.signedinteger):
+        fn = _load().orc_flow_direction_i64
+        dem = dem.astype(np.int64)
+    elif np.issubdtype(dem.dtype, np.unsignedinteger):
+        fn = _load().orc_flow_direction_u64
+        dem = dem.astype(np.uint64)
     else:
-        raise TypeError(f"oracle supports float32/float64 DEMs, got {dem.dtype}")
+        raise TypeError(f"oracle supports float32/float64/integer DEMs, got {dem.dtype}")
     dem = np.ascontiguousarray(dem)
     rows, cols = dem.shape
     out = np.empty((rows, cols), dtype=np.uint8)

@@ -15,6 +15,10 @@ OFL_DIR_MODE_TILE = 0
 OFL_DIR_MODE_RASTER = 1
 OFL_DIR_MODE_STRIP = 2
 
+OFL_ELEM_F64 = 0
+OFL_ELEM_I64 = 1
+OFL_ELEM_U64 = 2
+
 OFL_ERR_CYCLE = -5
 
 
@@ -40,6 +44,7 @@ SIGNATURES = {
     "ofl_phase_timing_enable": (None, [_int]),
     "ofl_phase_timing_read": (_int, [ctypes.POINTER(_f64), ctypes.POINTER(_i64), _int, _int]),
     "ofl_flow_direction_f32": (_int, [_vp, _i64, _i64, _i64, _f64, _vp, _i64, _int, _int, _vp]),
+    "ofl_flow_direction_x64": (_int, [_vp, _int, _i64, _i64, _i64, _f64, _vp, _i64, _int, _int, _vp]),
     "ofl_perimeter_count": (_i64, [_i64, _i64]),
     "ofl_accumulation_workspace_bytes": (_sz, [_i64, _i64]),
     "ofl_flow_accumulation_u8": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _sz, _int, _vp]),

@@ -16,6 +16,8 @@ int phase_timing_read(double* ms, int64_t* counts, int n, int reset);
 
 int launch_direction(const float* dem, int64_t in_rows, int64_t cols, int64_t ld_dem, double nodata, uint8_t* fdr,
                      int64_t rows, int64_t ld_fdr, int y_off, cudaStream_t st);
+int launch_direction_generic(const void* dem, int kind, int64_t in_rows, int64_t cols, int64_t ld_dem, double nodata,
+                             uint8_t* fdr, int64_t rows, int64_t ld_fdr, int y_off, cudaStream_t st);
 int launch_fill_border(uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld, int value, cudaStream_t st);
 int64_t perimeter_count(int64_t rows, int64_t cols);
 size_t accumulation_workspace_bytes(int64_t rows, int64_t cols);
@@ -166,6 +168,50 @@ int ofl_flow_direction_f32(const float* dem, int64_t rows, int64_t cols, int64_t
   }
   OFL_CUDA(cudaMemcpy2DAsync(fdr, ld_fdr, d_fdr, ldo, cols, rows, cudaMemcpyDeviceToHost, st));
   OFL_CUDA(cudaStreamSynchronize(st));
+  return OFL_OK;
+}
+
+int ofl_flow_direction_x64(const void* dem, int elem_kind, int64_t rows, int64_t cols, int64_t ld_dem, double nodata,
+                           uint8_t* fdr, int64_t ld_fdr, int mode, int mem_kind, void* stream) {
+  OFL_REQUIRE(rows >= 0 && cols >= 0, OFL_ERR_INVALID, "negative raster size");
+  OFL_REQUIRE(elem_kind == OFL_ELEM_F64 || elem_kind == OFL_ELEM_I64 || elem_kind == OFL_ELEM_U64, OFL_ERR_INVALID,
+              "unknown element kind %d", elem_kind);
+  OFL_REQUIRE(mode == OFL_DIR_MODE_TILE || mode == OFL_DIR_MODE_RASTER || mode == OFL_DIR_MODE_STRIP, OFL_ERR_INVALID,
+              "unknown direction mode %d", mode);
+  OFL_REQUIRE(mem_kind == OFL_MEM_HOST || mem_kind == OFL_MEM_DEVICE, OFL_ERR_INVALID, "unknown mem_kind %d", mem_kind);
+  if (rows == 0 || cols == 0) return OFL_OK;
+  OFL_REQUIRE(dem != nullptr && fdr != nullptr, OFL_ERR_INVALID, "null raster pointer");
+  OFL_REQUIRE(ld_dem >= cols && ld_fdr >= cols, OFL_ERR_INVALID, "leading dimension smaller than cols");
+  int rc = ensure_init();
+  if (rc != OFL_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int y_off = (mode == OFL_DIR_MODE_STRIP) ? 1 : 0;
+  const int64_t in_rows = rows + 2 * y_off;
+  const void* d_in = dem;
+  uint8_t* d_out = fdr;
+  int64_t ldd = ld_dem, ldo = ld_fdr;
+  if (mem_kind == OFL_MEM_HOST) {
+    void *b0 = nullptr, *b1 = nullptr;
+    ldd = cols;
+    ldo = round_up(cols, 16);
+    rc = scratch_get(SCRATCH_DEM, (size_t)in_rows * ldd * 8, &b0);
+    if (rc != OFL_OK) return rc;
+    rc = scratch_get(SCRATCH_FDR, (size_t)rows * ldo, &b1);
+    if (rc != OFL_OK) return rc;
+    OFL_CUDA(cudaMemcpy2DAsync(b0, ldd * 8, dem, ld_dem * 8, cols * 8, in_rows, cudaMemcpyHostToDevice, st));
+    d_in = b0;
+    d_out = static_cast<uint8_t*>(b1);
+  }
+  rc = launch_direction_generic(d_in, elem_kind, in_rows, cols, ldd, nodata, d_out, rows, ldo, y_off, st);
+  if (rc != OFL_OK) return rc;
+  if (mode == OFL_DIR_MODE_TILE) {
+    rc = launch_fill_border(d_out, rows, cols, ldo, OFL_DIR_NODATA, st);
+    if (rc != OFL_OK) return rc;
+  }
+  if (mem_kind == OFL_MEM_HOST) {
+    OFL_CUDA(cudaMemcpy2DAsync(fdr, ld_fdr, d_out, ldo, cols, rows, cudaMemcpyDeviceToHost, st));
+    OFL_CUDA(cudaStreamSynchronize(st));
+  }
   return OFL_OK;
 }
 

@@ -10,20 +10,45 @@ import numpy as np
 from . import _native
 from .constants import FLOW_DIRECTION_NODATA
 
-# dtypes whose pairwise differences are exact in float32 (|a-b| < 2**24), so the float32
-# kernel reproduces the reference's integer subtraction bit for bit
-_EXACT_IN_F32 = (np.uint8, np.int8, np.uint16, np.int16)
+def _classify(dem: np.ndarray):
+    """(kind, array) for the C ABI.  kind None: the float32 TMA kernel; otherwise an ofl_elem_kind for
+    ofl_flow_direction_x64.  The reference's arithmetic follows the array dtype under numba
+    (flow_direction.py:94-96): float32 differences for float32, float64 for float64, int64 for signed
+    integers and uint64 -- wrapping for uphill neighbours -- for unsigned ones.  int8/int16 differences
+    are exact in float32, so those share the float32 kernel."""
+    dt = dem.dtype
+    if dt == np.float32:
+        return None, dem
+    if dt in (np.dtype(np.int8), np.dtype(np.int16)):
+        return None, dem.astype(np.float32)
+    if dt == np.float64:
+        return _native.OFL_ELEM_F64, dem
+    if np.issubdtype(dt, np.signedinteger):
+        return _native.OFL_ELEM_I64, dem.astype(np.int64)
+    if np.issubdtype(dt, np.unsignedinteger):
+        return _native.OFL_ELEM_U64, dem.astype(np.uint64)
+    raise TypeError(f"flow direction: DEM dtype {dt} is not supported (float32, float64 or an integer type)")
 
 
 def _as_f32(dem: np.ndarray) -> np.ndarray:
-    if dem.dtype == np.float32:
-        return dem
-    if dem.dtype in [np.dtype(t) for t in _EXACT_IN_F32]:
-        return dem.astype(np.float32)
-    raise TypeError(
-        f"flow_direction_for_tile: dtype {dem.dtype} is not supported by the CUDA path "
-        "(float32, or 8/16-bit integers which convert exactly)"
-    )
+    """float32 view of a DEM that the float32 kernel reproduces exactly, else TypeError."""
+    kind, arr = _classify(dem)
+    if kind is not None:
+        raise TypeError(f"DEM dtype {dem.dtype} does not take the float32 path")
+    return arr
+
+
+def _run_direction(dem, nodata_value, out, mode):
+    kind, src = _classify(dem)
+    src = np.ascontiguousarray(src)
+    rows, cols = src.shape
+    lib = _native.lib()
+    if kind is None:
+        _native.check(lib.ofl_flow_direction_f32(src.ctypes.data, rows, cols, cols, float(nodata_value), out.ctypes.data,
+                                                 cols, mode, _native.OFL_MEM_HOST, None))
+    else:
+        _native.check(lib.ofl_flow_direction_x64(src.ctypes.data, kind, rows, cols, cols, float(nodata_value),
+                                                 out.ctypes.data, cols, mode, _native.OFL_MEM_HOST, None))
 
 
 def _stream_ptr(stream):
@@ -40,18 +65,12 @@ def flow_direction_for_tile(dem: np.ndarray, nodata_value: float) -> np.ndarray:
     dem = np.asarray(dem)
     if dem.ndim != 2:
         raise ValueError("dem must be a 2-D array")
-    src = np.ascontiguousarray(_as_f32(dem))
-    rows, cols = src.shape
+    _classify(dem)  # unsupported dtypes raise before anything is allocated
+    rows, cols = dem.shape
     out = np.empty((rows, cols), dtype=np.uint8)
     if rows == 0 or cols == 0:
         return out
-    lib = _native.lib()
-    _native.check(
-        lib.ofl_flow_direction_f32(
-            src.ctypes.data, rows, cols, cols, float(nodata_value), out.ctypes.data, cols,
-            _native.OFL_DIR_MODE_TILE, _native.OFL_MEM_HOST, None,
-        )
-    )
+    _run_direction(dem, nodata_value, out, _native.OFL_DIR_MODE_TILE)
     return out
 
 
@@ -65,21 +84,15 @@ def flow_direction_for_raster(dem: np.ndarray, nodata_value: float, out: np.ndar
     dem = np.asarray(dem)
     if dem.ndim != 2:
         raise ValueError("dem must be a 2-D array")
-    src = np.ascontiguousarray(_as_f32(dem))
-    rows, cols = src.shape
+    _classify(dem)
+    rows, cols = dem.shape
     if out is None:
         out = np.empty((rows, cols), dtype=np.uint8)
     elif out.dtype != np.uint8 or out.shape != (rows, cols) or not out.flags.c_contiguous:
         raise ValueError("out must be a C-contiguous uint8 array of dem.shape")
     if rows == 0 or cols == 0:
         return out
-    lib = _native.lib()
-    _native.check(
-        lib.ofl_flow_direction_f32(
-            src.ctypes.data, rows, cols, cols, float(nodata_value), out.ctypes.data, cols,
-            _native.OFL_DIR_MODE_RASTER, _native.OFL_MEM_HOST, None,
-        )
-    )
+    _run_direction(dem, nodata_value, out, _native.OFL_DIR_MODE_RASTER)
     return out
 
 

@@ -9,7 +9,7 @@ for host rasters the upload of the DEM, the stencil and the download of the code
 import numpy as np
 
 from . import _native
-from .flow_direction import _as_f32
+from .flow_direction import _classify, flow_direction_for_raster
 
 
 def flow_routing_for_raster(dem: np.ndarray, nodata_value: float, out_fdr: np.ndarray = None,
@@ -22,7 +22,16 @@ def flow_routing_for_raster(dem: np.ndarray, nodata_value: float, out_fdr: np.nd
     dem = np.asarray(dem)
     if dem.ndim != 2:
         raise ValueError("dem must be a 2-D array")
-    src = np.ascontiguousarray(_as_f32(dem))
+    kind, src = _classify(dem)
+    if kind is not None:
+        # float64 / integer DEMs: the generic stencil, then accumulation of its codes
+        from .flow_accumulation import flow_accumulation_for_raster
+
+        fdr = flow_direction_for_raster(dem, nodata_value, out=out_fdr)
+        res = flow_accumulation_for_raster(fdr, with_links=with_links, out=out_fac)
+        fdr = fdr if want_fdr else None
+        return (fdr, res[0], res[1]) if with_links else (fdr, res)
+    src = np.ascontiguousarray(src)
     rows, cols = src.shape
     if want_fdr:
         if out_fdr is None:

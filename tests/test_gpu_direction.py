@@ -90,8 +90,8 @@ def test_integer_dem_dtypes():
     dem = rng.integers(-300, 300, (40, 50)).astype(np.int16)
     want = oracle.flow_direction_for_tile(dem.astype(np.float64), -300)
     assert np.array_equal(fd_tile(dem, -300)[1:-1, 1:-1], want[1:-1, 1:-1])
-    with pytest.raises(TypeError):
-        fd_tile(dem.astype(np.float64), -300)
+    assert np.array_equal(fd_tile(dem.astype(np.float64), -300)[1:-1, 1:-1], want[1:-1, 1:-1])
+    assert np.array_equal(fd_tile(dem.astype(np.int64), -300)[1:-1, 1:-1], want[1:-1, 1:-1])
 
 
 def test_config1_1024_fractal():
@@ -148,3 +148,44 @@ def test_large_device_raster_windows_vs_oracle():
     top = dem[:3].cpu().numpy()
     want = oracle.flow_direction_for_tile(synth.pad_nodata(top), synth.NODATA)[1:2, 1:-1]
     assert np.array_equal(fdr[:1].cpu().numpy(), want)
+
+
+def _dtype_cases():
+    g = load_golden("direction_dtypes.npz")
+    return sorted({k.split("__")[0] for k in g.files})
+
+
+@pytest.mark.parametrize("name", _dtype_cases())
+def test_dtypes_match_reference(name):
+    """float64 / integer DEMs through ofl_flow_direction_x64 (and int8 / int16 through the float32 kernel)
+    against the reference's own outputs."""
+    from overflow_b200.flow_direction import flow_direction_for_tile
+
+    g = load_golden("direction_dtypes.npz")
+    dem, nodata = g[name + "__dem"], float(g[name + "__nodata"])
+    got = flow_direction_for_tile(dem, nodata)
+    assert got.dtype == np.uint8 and got.shape == dem.shape
+    assert np.array_equal(got[1:-1, 1:-1], g[name + "__fdr"])
+    assert (got[0] == 9).all() and (got[:, 0] == 9).all()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.int32, np.uint16])
+def test_dtypes_raster_mode_matches_oracle(dtype):
+    """Whole-raster mode (out-of-raster neighbours read as nodata cast to the dtype) for the generic kernel."""
+    from overflow_b200.flow_direction import flow_direction_for_raster
+
+    rng = np.random.default_rng(5)
+    dem = rng.integers(0, 500, size=(150, 203)).astype(dtype)
+    nodata = 65535 if dtype == np.uint16 else -9999
+    dem[40:50, 60:80] = nodata
+    pad = np.full((152, 205), nodata, dtype=dtype)
+    pad[1:-1, 1:-1] = dem
+    want = oracle.flow_direction_for_tile(pad, float(nodata))[1:-1, 1:-1]
+    assert np.array_equal(flow_direction_for_raster(dem, float(nodata)), want)
+
+
+def test_unsupported_dtype_raises():
+    from overflow_b200.flow_direction import flow_direction_for_tile
+
+    with pytest.raises(TypeError):
+        flow_direction_for_tile(np.zeros((5, 5), dtype=np.float16), -9999.0)

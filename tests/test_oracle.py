@@ -94,3 +94,18 @@ def test_config1_1024_anchor():
     rc, pl = oracle.links_perimeter(fdr)
     assert np.array_equal(rc, g["perim_rc"].astype(np.int64))
     assert np.array_equal(pl, g["perim_links"].astype(np.int64))
+
+
+def _dtype_cases():
+    g = load_golden("direction_dtypes.npz")
+    return sorted({k.split("__")[0] for k in g.files})
+
+
+@pytest.mark.parametrize("name", _dtype_cases())
+def test_direction_dtypes_match_reference(name):
+    """float64 and integer DEMs: the reference's arithmetic follows the array dtype (unsigned differences
+    wrap); fixtures produced by the reference (oracle/gen_golden_dtypes.py)."""
+    g = load_golden("direction_dtypes.npz")
+    dem, nodata = g[name + "__dem"], float(g[name + "__nodata"])
+    got = oracle.flow_direction_for_tile(dem, nodata)[1:-1, 1:-1]
+    assert np.array_equal(got, g[name + "__fdr"])
