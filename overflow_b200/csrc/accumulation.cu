@@ -110,7 +110,7 @@ struct AccParams {
   int force_wide;  // test hook: send every tile with an inflow through the 64-bit variant
   // whole-raster calls: pass A publishes its slots straight into the solve's initial state (pointer
   // buffers, cleared delta entries, per-segment active lists) instead of `succ` + a separate init kernel
-  int fuse_init;
+  int fuse_init, keep_succ;
   int32_t *ptr_a, *ptr_b, *list0;
   unsigned long long *d0, *d1;
   int* counts0;
@@ -122,10 +122,8 @@ struct AccParams {
 __device__ __forceinline__ void publish_slot(const AccParams& p, int tile, bool mine, uint32_t slot, int32_t succ,
                                              uint32_t lt_mask, int lane) {
   const size_t u = (size_t)tile * SLOTS + slot;
-  if (!p.fuse_init) {
-    if (mine) p.succ[u] = succ;
-    return;
-  }
+  if (mine && p.keep_succ) p.succ[u] = succ;  // strips solve the same forest a second time, from `succ`
+  if (!p.fuse_init) return;
   const bool active = mine && succ >= 0;
   if (active) {
     p.ptr_a[u] = succ;
@@ -1303,7 +1301,8 @@ static int acc_setup(AccCtx& C, const uint8_t* fdr, int64_t rows, int64_t cols, 
   p.force_wide = getenv("OFL_FORCE_WIDE_FINAL") ? 1 : 0;
   {
     const PjSeg g = pj_segments(n);
-    p.fuse_init = (!strip && !getenv("OFL_NO_FUSED_INIT")) ? 1 : 0;
+    p.fuse_init = getenv("OFL_NO_FUSED_INIT") ? 0 : 1;
+    p.keep_succ = (strip || !p.fuse_init) ? 1 : 0;
     p.ptr_a = reinterpret_cast<int32_t*>(C.ws + C.L.off_pa);
     p.ptr_b = reinterpret_cast<int32_t*>(C.ws + C.L.off_pb);
     p.list0 = reinterpret_cast<int32_t*>(C.ws + C.L.off_lists);
@@ -1493,6 +1492,7 @@ int strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
   const GraphLayout& L = C.L;
   rc = ws_begin(C.ws, L, L.off_S, st);  // S, S2
   if (rc != OFL_OK) return rc;
+  if (C.p.fuse_init) OFL_CUDA(cudaMemsetAsync(C.counts, 0, 2 * (size_t)PJ_MAX_BLOCKS * sizeof(int), st));
   {
     PhaseScope ps(PHASE_ACC_TILE_A, st);
     acc_tile_kernel<<<(unsigned)C.ntiles, ACC_THREADS, TileSmem::BYTES, st>>>(C.tm, C.p);
@@ -1500,7 +1500,7 @@ int strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
   OFL_CHECK_LAUNCH();
   {
     PhaseScope ps(PHASE_ACC_SOLVE, st);
-    rc = pj_solve(C.p.succ, C.pa, C.pb, C.lists, C.counts, C.p.err + 1, C.p.S, C.d0, C.d1, L.n, st);
+    rc = pj_solve(C.p.succ, C.pa, C.pb, C.lists, C.counts, C.p.err + 1, C.p.S, C.d0, C.d1, L.n, st, !C.p.fuse_init);
   }
   if (rc != OFL_OK) return rc;
   // strip-local counts of the first and last tile row (their cells include both boundary rows)
