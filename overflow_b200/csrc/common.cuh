@@ -53,7 +53,7 @@ struct PhaseScope {
 int sm_count();
 
 // Library-owned device scratch, grown on demand and kept until ofl_shutdown (slot-indexed).
-enum ScratchSlot { SCRATCH_DEM = 0, SCRATCH_FDR, SCRATCH_FAC, SCRATCH_WORK, SCRATCH_LINKS, SCRATCH_MISC, SCRATCH_SLOTS };
+enum ScratchSlot { SCRATCH_DEM = 0, SCRATCH_FDR, SCRATCH_FAC, SCRATCH_WORK, SCRATCH_LINKS, SCRATCH_MISC, SCRATCH_DIRCTR, SCRATCH_SLOTS };
 int scratch_get(int slot, size_t bytes, void** out);
 // Pinned host scratch (slot-indexed) for small read-backs.
 int pinned_get(size_t bytes, void** out);
