@@ -208,7 +208,7 @@ struct TileSmem {
 };
 static_assert(ACS_BYTES <= QMAX * 2, "code tile does not fit the slot it shares with the queue");
 static_assert((WORDS * 4) % 16 == 0 && (WP * 4) % 16 == 0, "word rows must be whole uint4s");
-static_assert(WORDS * 4 < 65536, "queue entries are 16-bit byte offsets into the word array");
+static_assert(WORDS * 4 < 65536, "queue entries are 16-bit shared addresses of words");
 
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
   uint32_t v;
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
   const uint32_t sb = smem_base_opaque(smem_raw);
   const uint32_t a_cs = sb + SM::CS;      // codes + halo (TMA destination), pitch ACS_W bytes
   const uint32_t a_word = sb + SM::WORD;  // per-cell words, halo-padded, pitch WP words
-  const uint32_t a_q = sb + SM::Q;        // frontier queue: byte offsets of words from a_word, u16
+  const uint32_t a_q = sb + SM::Q;        // frontier queue: shared addresses of words, u16
   const uint32_t a_tail = sb + SM::TAIL;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + SM::BAR);
 
@@ -297,6 +297,10 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
   const int y0 = ty << AT_SHIFT, x0 = tx << AT_SHIFT;
   const int h = min(AT, p.rows - y0), w = min(AT, p.cols - x0);
 
+  if (sb + SM::BYTES > 0x10000u) {  // the frontier queue holds shared addresses as 16-bit values
+    if (tid == 0) atomicExch(p.err, 3);
+    return;
+  }
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
@@ -430,7 +434,7 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     if (lane == 31) base = atoms_add(a_tail_v, incl);
     base = __shfl_sync(0xffffffffu, base, 31);
     uint32_t aq = a_q + 2 * (base + incl - mine);
-    const uint32_t qv = aw_lane - a_word;
+    const uint32_t qv = aw_lane;  // queue entries: 16-bit shared addresses (checked at kernel entry)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
 #pragma unroll
@@ -504,26 +508,35 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
 
   // ---- wide levels: level k is q[lo, hi); processing it appends level k+1 right after it.  A warp takes
   //      WIDE_PER_LANE * 32 entries per turn and reserves queue slots for everything they complete with
-  //      one atomic.
+  //      one atomic.  Queue entries are the 16-bit shared addresses of the words themselves.
   const uint32_t n_src = lds32(a_tail);  // final: the level loop appends through the second counter
   uint32_t lo = 0, hi = n_src;
+  // finish the cell whose word sits at `aw`; returns the hand-off's result (0: there was none) and the
+  // address of the downstream word
+  auto visit = [&](uint32_t aw, uint32_t& an) -> uint32_t {
+    const uint32_t wv = lds32(aw);
+    const uint32_t own = wv + W_FINISH;
+    sts32(aw, own);
+    if (!(wv & 0xFFu)) return 0;
+    an = word_next(aw, wv);
+    return atoms_add(an, own & W_HANDOFF_MASK);
+  };
   while (hi - lo > TAIL_MAX) {
     for (uint32_t base = lo + 32 * WIDE_PER_LANE * warp; base < hi; base += WIDE_PER_LANE * ACC_THREADS) {
       uint32_t old[WIDE_PER_LANE], an[WIDE_PER_LANE];
+      if (base + 32 * WIDE_PER_LANE <= hi) {  // a full turn: no per-entry bounds checks
 #pragma unroll
-      for (int e = 0; e < WIDE_PER_LANE; ++e) {
-        const uint32_t i = base + 32 * e + lane;
-        old[e] = 0;  // reads as "nothing completed"
-        an[e] = 0;
-        if (i < hi) {
-          const uint32_t aw = a_word + lds16(a_q + 2 * i);
-          const uint32_t wv = lds32(aw);
-          const uint32_t own = wv + W_FINISH;
-          sts32(aw, own);
-          if (wv & 0xFFu) {
-            an[e] = word_next(aw, wv);
-            old[e] = atoms_add(an[e], own & W_HANDOFF_MASK);
-          }
+        for (int e = 0; e < WIDE_PER_LANE; ++e) {
+          an[e] = 0;
+          old[e] = visit(lds16(a_q + 2 * (base + 32 * e + lane)), an[e]);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < WIDE_PER_LANE; ++e) {
+          const uint32_t i = base + 32 * e + lane;
+          old[e] = 0;  // reads as "nothing completed"
+          an[e] = 0;
+          if (i < hi) old[e] = visit(lds16(a_q + 2 * i), an[e]);
         }
       }
       uint32_t bal[WIDE_PER_LANE], total = 0;
@@ -538,7 +551,7 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
         qb = n_src + __shfl_sync(0xffffffffu, qb, 0);
 #pragma unroll
         for (int e = 0; e < WIDE_PER_LANE; ++e) {
-          if (bal[e] & (1u << lane)) sts16(a_q + 2 * (qb + __popc(bal[e] & lt_mask)), an[e] - a_word);
+          if (bal[e] & (1u << lane)) sts16(a_q + 2 * (qb + __popc(bal[e] & lt_mask)), an[e]);
           qb += __popc(bal[e]);
         }
       }
@@ -553,7 +566,7 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
   //      as its hand-off is the one that completes the next cell; no queue, no barriers.  The atomic's
   //      return value already is the next cell's word, so a step is one store and one atomic.
   for (uint32_t i = lo + tid; i < hi; i += ACC_THREADS) {
-    uint32_t aw = a_word + lds16(a_q + 2 * i);
+    uint32_t aw = lds16(a_q + 2 * i);
     uint32_t wv = lds32(aw);
     for (;;) {
       const uint32_t own = wv + W_FINISH;
@@ -1202,6 +1215,7 @@ static int check_flags(const int* err_flags, cudaStream_t st) {
   int h[2] = {0, 0};
   OFL_CUDA(cudaMemcpyAsync(h, err_flags, sizeof(h), cudaMemcpyDeviceToHost, st));
   OFL_CUDA(cudaStreamSynchronize(st));
+  OFL_REQUIRE(h[0] != 3, OFL_ERR_INVALID, "shared-memory window above 64 KB: the tile kernel's 16-bit queue does not apply");
   OFL_REQUIRE(h[0] == 0, OFL_ERR_CYCLE, "flow-direction raster contains a cycle (tile flag %d)", h[0]);
   OFL_REQUIRE(h[1] == 0, OFL_ERR_CYCLE, "flow-direction raster contains a cycle (perimeter graph)");
   return OFL_OK;
