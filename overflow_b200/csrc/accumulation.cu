@@ -658,14 +658,14 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
 // add every non-zero inflow along its path and write the tile out as int64 (~11 B/cell of HBM traffic).
 //   * the perimeter slots with a non-zero inflow are compacted onto whole warps; a step of a path is one
 //     shared atomic on the cell's count, one byte load of the next cell's code and two PRMT table lookups;
-//   * the code tile carries a one-cell halo marked NODATA, so leaving the tile, leaving the raster and
-//     running into a NODATA cell are the same test;
-//   * counts are accumulated in 32 bits (22 KB of shared memory, eight CTAs per SM).  A tile in which an
+//   * the code tile is the exact 64 x 64 box (4 KB); a step that would leave the tile (or the raster, on a
+//     partial tile) is caught by the column and the cell index going out of range;
+//   * counts are accumulated in 32 bits (23 KB of shared memory, eight CTAs per SM).  A tile in which an
 //     inflow or a sum does not fit 32 bits -- possible only on rasters of more than 2^32 cells' worth of
 //     drainage -- is put on a list instead of being written, and redone by the WIDE variant (64-bit).
 struct FinalSmem {
-  static constexpr int CS = 0;                       // codes + halo (TMA destination), pitch ACS_W
-  static constexpr int LO = 6400;                    // low words of the counts, pitch AT, no halo
+  static constexpr int CS = 0;                       // codes (TMA destination), pitch AT
+  static constexpr int LO = AT * AT;                 // low words of the counts, pitch AT
   static constexpr int SEED = LO + AT * AT * 4;      // 64-bit inflow of every listed path
   static constexpr int LIST = SEED + SLOTS * 8;      // slots of the listed paths (u8)
   static constexpr int CNT = LIST + SLOTS;           // number of listed paths
@@ -674,15 +674,13 @@ struct FinalSmem {
   static constexpr int BYTES_FAST = HI;
   static constexpr int BYTES_WIDE = HI + AT * AT * 4;
 };
-// per direction code E, NE, N, NW | W, SW, S, SE: code-array byte offset and count-array word offset
-constexpr uint32_t F_TABC_LO = (uint32_t)(uint8_t)(1) | ((uint32_t)(uint8_t)(1 - ACS_W) << 8) |
-                               ((uint32_t)(uint8_t)(-ACS_W) << 16) | ((uint32_t)(uint8_t)(-ACS_W - 1) << 24);
-constexpr uint32_t F_TABC_HI = (uint32_t)(uint8_t)(-1) | ((uint32_t)(uint8_t)(ACS_W - 1) << 8) |
-                               ((uint32_t)(uint8_t)(ACS_W) << 16) | ((uint32_t)(uint8_t)(ACS_W + 1) << 24);
-constexpr uint32_t F_TABL_LO = (uint32_t)(uint8_t)(1) | ((uint32_t)(uint8_t)(1 - AT) << 8) |
+// per direction code E, NE, N, NW | W, SW, S, SE: cell-index offset (dy * 64 + dx) and column offset
+constexpr uint32_t F_TABI_LO = (uint32_t)(uint8_t)(1) | ((uint32_t)(uint8_t)(1 - AT) << 8) |
                                ((uint32_t)(uint8_t)(-AT) << 16) | ((uint32_t)(uint8_t)(-AT - 1) << 24);
-constexpr uint32_t F_TABL_HI = (uint32_t)(uint8_t)(-1) | ((uint32_t)(uint8_t)(AT - 1) << 8) |
+constexpr uint32_t F_TABI_HI = (uint32_t)(uint8_t)(-1) | ((uint32_t)(uint8_t)(AT - 1) << 8) |
                                ((uint32_t)(uint8_t)(AT) << 16) | ((uint32_t)(uint8_t)(AT + 1) << 24);
+constexpr uint32_t F_TABX_LO = 0xFF000101u;  // dx of E, NE, N, NW = +1, +1, 0, -1
+constexpr uint32_t F_TABX_HI = 0x0100FFFFu;  // dx of W, SW, S, SE = -1, -1, 0, +1
 
 // One tile.  Returns true (fast variant only) when the tile needs the 64-bit variant; nothing has been
 // written to fac in that case.  `parity`: phase of the tile's TMA barrier.
@@ -690,8 +688,7 @@ template <bool WIDE>
 __device__ __forceinline__ bool final_tile(const CUtensorMap& tm, const AccParams& p, int tile, uint8_t* smem_raw,
                                            uint32_t sb, uint32_t parity) {
   using SM = FinalSmem;
-  const uint32_t a_cs = sb + SM::CS, a_lo = sb + SM::LO, a_hi = sb + SM::HI;
-  const uint32_t a_cs0 = a_cs + ACS_W * ACS_Y0 + ACS_X0;  // code of cell (0,0)
+  const uint32_t a_cs0 = sb + SM::CS, a_lo = sb + SM::LO, a_hi = sb + SM::HI;  // a_cs0: code of cell (0,0), pitch AT
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + SM::BAR);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ty = tile / p.ntx, tx = tile - ty * p.ntx;
@@ -699,8 +696,8 @@ __device__ __forceinline__ bool final_tile(const CUtensorMap& tm, const AccParam
   const int h = min(AT, p.rows - y0), w = min(AT, p.cols - x0);
 
   if (tid == 0) {
-    mbar_arrive_expect_tx(bar, ACS_BYTES);
-    tma_load_2d(smem_raw + SM::CS, &tm, x0 - ACS_X0, y0 - ACS_Y0 + p.y_off, bar);
+    mbar_arrive_expect_tx(bar, AT * AT);
+    tma_load_2d(smem_raw + SM::CS, &tm, x0, y0 + p.y_off, bar);
     sts32(sb + SM::CNT, 0);
   }
   // global loads first (they overlap the TMA): tile-local counts and this thread's perimeter inflow
@@ -741,20 +738,6 @@ __device__ __forceinline__ bool final_tile(const CUtensorMap& tm, const AccParam
     }
   }
   mbar_wait(bar, parity);
-  // halo ring -> NODATA: a path stops in front of it exactly as in front of a NODATA cell
-  {
-    int hy = side == 0 ? -1 : side == 1 ? AT : k;
-    int hx = side == 2 ? -1 : side == 3 ? AT : k;
-    sts8(a_cs0 + hy * ACS_W + hx, OFL_DIR_NODATA);
-    if (k == 0) sts8(a_cs0 + ((side & 1) ? AT : -1) * ACS_W + ((side & 2) ? AT : -1), OFL_DIR_NODATA);
-  }
-  if (h < AT || w < AT) {
-    // partial tile at the raster's bottom / right edge: in-tile positions beyond the raster stop a path too
-    for (int idx = tid; idx < AT * AT; idx += ACC_THREADS) {
-      const int yy = idx >> AT_SHIFT, xx = idx & (AT - 1);
-      if (yy >= h || xx >= w) sts8(a_cs0 + yy * ACS_W + xx, OFL_DIR_NODATA);
-    }
-  }
   __syncthreads();
 
   {
@@ -765,26 +748,26 @@ __device__ __forceinline__ bool final_tile(const CUtensorMap& tm, const AccParam
       const uint2 sd = lds64(sb + SM::SEED + 8 * t);
       const int ss = slot >> AT_SHIFT, sk = slot & (AT - 1);
       const int y = ss == 0 ? 0 : ss == 1 ? h - 1 : sk;
-      const int x = ss == 2 ? 0 : ss == 3 ? w - 1 : sk;
-      uint32_t ca = a_cs0 + y * ACS_W + x;      // shared address of the current cell's code
-      uint32_t o = a_lo + (y * AT + x) * 4;     // ... and of its count
-      uint32_t code = lds8(ca);
+      int x = ss == 2 ? 0 : ss == 3 ? w - 1 : sk;
+      uint32_t idx = y * AT + x;  // cell index: code at a_cs0 + idx, count at a_lo + 4 * idx
+      uint32_t code = lds8(a_cs0 + idx);
       if (WIDE || (sd.y == 0 && !p.force_wide)) {
         for (int steps = 0; steps <= AT * AT; ++steps) {
-          const uint32_t old = atoms_add(o, sd.x);
+          const uint32_t old = atoms_add(a_lo + 4 * idx, sd.x);
           const bool carry = (old + sd.x) < old;
           if (WIDE) {
             const uint32_t hadd = sd.y + (carry ? 1u : 0u);
-            if (hadd) atoms_add(o + (SM::HI - SM::LO), hadd);
+            if (hadd) atoms_add(a_hi + 4 * idx, hadd);
           } else {
             wide_needed |= carry;
           }
           if (code >= 8) break;  // pit / flat / invalid: no downstream cell
           const uint32_t sel = code * 0x1111u + 0x8880u;  // byte 0: table entry, bytes 1..3: its sign
-          ca += prmt(F_TABC_LO, F_TABC_HI, sel);
-          o += prmt(F_TABL_LO, F_TABL_HI, sel) << 2;
-          code = lds8(ca);
-          if (code == OFL_DIR_NODATA) break;  // NODATA cell, tile edge or raster edge: the path ends here
+          x += (int)prmt(F_TABX_LO, F_TABX_HI, sel);
+          idx += prmt(F_TABI_LO, F_TABI_HI, sel);
+          if ((uint32_t)x >= (uint32_t)w || idx >= (uint32_t)(h * AT)) break;  // leaves the tile (or the raster)
+          code = lds8(a_cs0 + idx);
+          if (code == OFL_DIR_NODATA) break;  // no edge into a NODATA cell
         }
       }
     }
@@ -803,7 +786,7 @@ __device__ __forceinline__ bool final_tile(const CUtensorMap& tm, const AccParam
       const uint2 lo2 = lds64(a_lo + oo);
       uint2 hi2 = make_uint2(0, 0);
       if (WIDE) hi2 = lds64(a_hi + oo);
-      const uint32_t c2 = lds16(a_cs0 + yy * ACS_W + xx);
+      const uint32_t c2 = lds16(a_cs0 + yy * AT + xx);
       long long v0 = (long long)(((unsigned long long)hi2.x << 32) | lo2.x);
       long long v1 = (long long)(((unsigned long long)hi2.y << 32) | lo2.y);
       if ((c2 & 0xFF) == OFL_DIR_NODATA) v0 = OFL_FAC_NODATA_EMITTED;
@@ -1278,7 +1261,8 @@ static int ws_begin(uint8_t* ws, const GraphLayout& L, size_t from_off, cudaStre
 // Everything one raster (or strip) needs to launch its kernels.
 struct AccCtx {
   AccParams p;
-  CUtensorMap tm;        // codes + halo box (both tile passes)
+  CUtensorMap tm;        // codes + halo box for pass A
+  CUtensorMap tm_tile;   // exact 64 x 64 box for the final pass
   GraphLayout L;
   uint8_t* ws;
   int64_t ntiles;
@@ -1341,6 +1325,8 @@ static int acc_setup(AccCtx& C, const uint8_t* fdr, int64_t rows, int64_t cols, 
   C.ntiles = (int64_t)p.nty * p.ntx;
   int rc = make_tensor_map_2d(&C.tm, fdr, 1, (uint64_t)cols, (uint64_t)(rows + 2 * y_off), (uint64_t)ld_fdr, ACS_W, ACS_H);
   if (rc != OFL_OK) return rc;
+  rc = make_tensor_map_2d(&C.tm_tile, fdr, 1, (uint64_t)cols, (uint64_t)(rows + 2 * y_off), (uint64_t)ld_fdr, AT, AT);
+  if (rc != OFL_OK) return rc;
   return ensure_tile_attrs();
 }
 
@@ -1348,10 +1334,10 @@ static int acc_setup(AccCtx& C, const uint8_t* fdr, int64_t rows, int64_t cols, 
 // Final pass over `grid` tiles starting at p.tile_base: the 32-bit kernel, then the 64-bit one on whatever it listed.
 static int launch_final(const AccCtx& C, const AccParams& p, unsigned grid, cudaStream_t st) {
   OFL_CUDA(cudaMemsetAsync(p.wide_list, 0, sizeof(int), st));
-  acc_final_kernel<<<grid, ACC_THREADS, FinalSmem::BYTES_FAST, st>>>(C.tm, p);
+  acc_final_kernel<<<grid, ACC_THREADS, FinalSmem::BYTES_FAST, st>>>(C.tm_tile, p);
   OFL_CHECK_LAUNCH();
   const unsigned wide_grid = grid < (unsigned)sm_count() * 2 ? grid : (unsigned)sm_count() * 2;
-  acc_final_wide_kernel<<<wide_grid, ACC_THREADS, FinalSmem::BYTES_WIDE, st>>>(C.tm, p);
+  acc_final_wide_kernel<<<wide_grid, ACC_THREADS, FinalSmem::BYTES_WIDE, st>>>(C.tm_tile, p);
   OFL_CHECK_LAUNCH();
   return OFL_OK;
 }
