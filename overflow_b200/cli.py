@@ -1,13 +1,15 @@
 """Command line interface -- mirror of the reference's src/overflow_cli.py for the D8 path.
 
 `flow-direction` keeps the reference's options, messages and exit codes (overflow_cli.py:54-84);
-`flow-accumulation` is added with the same conventions (the reference snapshot has no such command).
+`flow-accumulation` and `flow-routing` (both steps, one pass over the device) are added with the same
+conventions (the reference snapshot has no such commands).
 """
 import click
 
 from .constants import DEFAULT_CHUNK_SIZE
 from .flow_accumulation import flow_accumulation
 from .flow_direction import flow_direction
+from .flow_routing import flow_routing
 
 
 @click.group()
@@ -39,6 +41,20 @@ def flow_accumulation_cli(input_file: str, output_file: str, chunk_size: int):
         flow_accumulation(input_file, output_file, chunk_size)
     except Exception as exc:
         print(f"flow_accumulation failed with the following exception: {str(exc)}")
+        raise click.Abort()
+
+
+@main.command(name="flow-routing")
+@click.option("--input_file", help="path to the DEM file")
+@click.option("--flow_direction_file", help="path to the flow direction output file")
+@click.option("--flow_accumulation_file", help="path to the flow accumulation output file")
+@click.option("--chunk_size", help="chunk size", default=DEFAULT_CHUNK_SIZE)
+def flow_routing_cli(input_file: str, flow_direction_file: str, flow_accumulation_file: str, chunk_size: int):
+    """Generate D8 flow direction and flow accumulation rasters from a DEM in one pass."""
+    try:
+        flow_routing(input_file, flow_direction_file, flow_accumulation_file, chunk_size)
+    except Exception as exc:
+        print(f"flow_routing failed with the following exception: {str(exc)}")
         raise click.Abort()
 
 

@@ -55,3 +55,31 @@ def flow_routing_for_raster(dem: np.ndarray, nodata_value: float, out_fdr: np.nd
             )
         )
     return (out_fdr, out_fac, perim) if with_links else (out_fdr, out_fac)
+
+
+def flow_routing(input_path, flow_direction_path, flow_accumulation_path, chunk_size=2000):
+    """DEM file -> flow-direction GeoTIFF and flow-accumulation GeoTIFF in one pass over the device.
+
+    File-level counterpart of `flow_routing_for_raster`, in the pattern of the reference's
+    `flow_direction()` (flow_direction.py:99-124): band 1 in; a 1-band Byte raster (nodata 9) and a 1-band
+    Int64 raster (nodata FLOW_ACCUMULATION_NODATA) out, same projection / geotransform.  The outputs equal
+    what `flow_direction()` followed by `flow_accumulation()` write; `chunk_size` is the I/O granularity.
+    """
+    from .constants import FLOW_ACCUMULATION_NODATA, FLOW_DIRECTION_NODATA
+    from .util import raster as _raster
+
+    src = _raster.open_raster(input_path)
+    band = src.GetRasterBand(1)
+    nodata_value = band.GetNoDataValue()
+    assert nodata_value is not None, "the DEM band needs a nodata value (util/raster.py:59 in the reference)"
+    dem = _raster.read_band(band, chunk_size)
+    fdr, fac = flow_routing_for_raster(dem, nodata_value)
+    for path, name, nodata, arr in ((flow_direction_path, "Byte", FLOW_DIRECTION_NODATA, fdr),
+                                    (flow_accumulation_path, "Int64", FLOW_ACCUMULATION_NODATA, fac)):
+        dst = _raster.create_raster(path, src.RasterXSize, src.RasterYSize, name, projection=src.GetProjection(),
+                                    geotransform=src.GetGeoTransform())
+        out_band = dst.GetRasterBand(1)
+        out_band.SetNoDataValue(nodata)
+        _raster.write_band(out_band, arr, chunk_size)
+        dst.FlushCache()
+        dst = None

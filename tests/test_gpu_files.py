@@ -72,3 +72,30 @@ def test_file_pipeline_is_chunk_size_invariant(tmp_path, chunk_size):
     assert band.GetNoDataValue() == FLOW_ACCUMULATION_NODATA
     assert out.GetGeoTransform() == pytest.approx((0.0, 30.0, 0.0, 0.0, 0.0, -30.0))
     assert np.array_equal(band.ReadAsArray(), oracle.flow_accumulation(want_fdr))
+
+
+def test_flow_routing_files_equal_the_two_step_outputs(tmp_path):
+    """DEM file -> both rasters in one pass: same bytes as flow_direction() then flow_accumulation()."""
+    from overflow_cli import flow_routing_cli
+
+    dem = synth.punch_holes(synth.fractal(150, 97, beta=2.5, seed=8), frac=0.03, seed=9)
+    src = str(tmp_path / "dem.tif")
+    ds = create_raster(src, dem.shape[1], dem.shape[0], "Float32", geotransform=(10.0, 30.0, 0.0, 20.0, 0.0, -30.0))
+    ds.GetRasterBand(1).WriteArray(dem)
+    ds.GetRasterBand(1).SetNoDataValue(synth.NODATA)
+    ds.FlushCache()
+    a_fdr, a_fac = str(tmp_path / "a_fdr.tif"), str(tmp_path / "a_fac.tif")
+    b_fdr, b_fac = str(tmp_path / "b_fdr.tif"), str(tmp_path / "b_fac.tif")
+    flow_direction(src, a_fdr, chunk_size=40)
+    flow_accumulation(a_fdr, a_fac, chunk_size=40)
+    result = click.testing.CliRunner().invoke(
+        flow_routing_cli, ["--input_file", src, "--flow_direction_file", b_fdr, "--flow_accumulation_file", b_fac,
+                           "--chunk_size", "64"])
+    assert result.exit_code == 0, result.output
+    for a, b in ((a_fdr, b_fdr), (a_fac, b_fac)):
+        ra, rb = open_raster(a), open_raster(b)
+        assert np.array_equal(ra.GetRasterBand(1).ReadAsArray(), rb.GetRasterBand(1).ReadAsArray())
+        assert ra.GetRasterBand(1).GetNoDataValue() == rb.GetRasterBand(1).GetNoDataValue()
+        assert ra.GetGeoTransform() == pytest.approx(rb.GetGeoTransform())
+    want_fdr = oracle.flow_direction_for_tile(synth.pad_nodata(dem), synth.NODATA)[1:-1, 1:-1]
+    assert np.array_equal(open_raster(b_fac).GetRasterBand(1).ReadAsArray(), oracle.flow_accumulation(want_fdr))
