@@ -189,3 +189,52 @@ def test_unsupported_dtype_raises():
 
     with pytest.raises(TypeError):
         flow_direction_for_tile(np.zeros((5, 5), dtype=np.float16), -9999.0)
+
+
+def test_near_ties_between_cardinal_and_diagonal():
+    """Stress the guard band of the float32 class decision: windows whose best diagonal drop is within a
+    few ulps of sqrt(2) times the best cardinal drop, at many magnitudes, signs and with plateaus around
+    them; the exact path must take exactly the cases the fast path cannot decide."""
+    rng = np.random.default_rng(77)
+    rows, cols = 300, 512
+    dem = np.full((rows, cols), 1000.0, dtype=np.float32)
+    for r in range(1, rows - 1, 3):
+        for c in range(1, cols - 1, 3):
+            z = np.float32(rng.choice([1.0, 37.5, 1e3, 1e6, 1e-3, 3e-30]) * rng.uniform(0.5, 2.0))
+            drop_c = np.float32(abs(z) * rng.choice([1e-6, 1e-3, 0.25, 0.9]))
+            ulps = int(rng.integers(-6, 7))
+            drop_d = np.float32(np.float64(drop_c) * np.sqrt(2.0))
+            for _ in range(abs(ulps)):
+                drop_d = np.nextafter(drop_d, np.float32(np.inf if ulps > 0 else -np.inf), dtype=np.float32)
+            win = np.full((3, 3), z, dtype=np.float32)
+            win[1, 1] = z
+            ci = [(1, 2), (0, 1), (1, 0), (2, 1)][int(rng.integers(0, 4))]
+            di = [(0, 2), (0, 0), (2, 0), (2, 2)][int(rng.integers(0, 4))]
+            win[ci] = z - drop_c
+            win[di] = z - drop_d
+            dem[r - 1 : r + 2, c - 1 : c + 2] = win
+    want = oracle.flow_direction_for_tile(dem, synth.NODATA)
+    got = fd_tile(dem, synth.NODATA)
+    assert np.array_equal(got[1:-1, 1:-1], want[1:-1, 1:-1])
+
+
+def test_heavy_nodata_and_non_finite_values():
+    """A quarter of the cells NODATA in blobs and singles, plus NaN / +-inf / denormal data cells: every
+    combination of +inf slopes in the two neighbour classes, through the fast path and the fix-up."""
+    rng = np.random.default_rng(78)
+    dem = synth.fractal(700, 900, beta=2.0, seed=12)
+    mask = rng.random(dem.shape)
+    dem[mask < 0.15] = synth.NODATA
+    for _ in range(300):
+        r, c = int(rng.integers(0, 690)), int(rng.integers(0, 890))
+        dem[r : r + int(rng.integers(1, 9)), c : c + int(rng.integers(1, 9))] = synth.NODATA
+    special = rng.random(dem.shape)
+    dem[special < 0.002] = np.nan
+    dem[(special >= 0.002) & (special < 0.004)] = np.inf
+    dem[(special >= 0.004) & (special < 0.006)] = -np.inf
+    dem[(special >= 0.006) & (special < 0.008)] = np.float32(1e-42)
+    want = oracle.flow_direction_for_tile(dem, synth.NODATA)
+    got = fd_tile(dem, synth.NODATA)
+    assert np.array_equal(got[1:-1, 1:-1], want[1:-1, 1:-1])
+    pad = synth.pad_nodata(dem)
+    assert np.array_equal(fd_raster(dem, synth.NODATA), oracle.flow_direction_for_tile(pad, synth.NODATA)[1:-1, 1:-1])
