@@ -52,3 +52,24 @@ def test_no_cpu_fallback(lib):
 
     with pytest.raises(_native.OverflowB200Error):
         flow_direction_for_tile(np.zeros((5, 5), dtype=np.float32), -9999.0)
+
+
+def test_dem_dtype_dispatch():
+    """Host logic only: which kernel family a DEM dtype takes and how it is widened (no compute call)."""
+    from overflow_b200 import _native
+    from overflow_b200.flow_direction import _classify
+
+    for dt in (np.float32, np.int8, np.int16):
+        kind, arr = _classify(np.zeros((3, 3), dtype=dt))
+        assert kind is None and arr.dtype == np.float32
+    kind, arr = _classify(np.zeros((3, 3), dtype=np.float64))
+    assert kind == _native.OFL_ELEM_F64 and arr.dtype == np.float64
+    for dt in (np.int32, np.int64):
+        kind, arr = _classify(np.full((3, 3), -7, dtype=dt))
+        assert kind == _native.OFL_ELEM_I64 and arr.dtype == np.int64 and arr[0, 0] == -7
+    for dt in (np.uint8, np.uint16, np.uint32, np.uint64):
+        kind, arr = _classify(np.full((3, 3), 200, dtype=dt))
+        assert kind == _native.OFL_ELEM_U64 and arr.dtype == np.uint64 and arr[0, 0] == 200
+    for dt in (np.float16, np.complex64, np.bool_):
+        with pytest.raises(TypeError):
+            _classify(np.zeros((3, 3), dtype=dt))
