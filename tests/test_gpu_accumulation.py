@@ -212,6 +212,18 @@ def test_wide_final_pass_matches(monkeypatch):
     assert np.array_equal(fac, want)
 
 
+def test_wide_final_pass_many_tiles_per_cta(monkeypatch):
+    """More listed tiles than the 64-bit kernel has CTAs (2 per SM): every CTA loops over several tiles,
+    re-arming its TMA barrier each time."""
+    from overflow_b200.flow_accumulation import flow_accumulation_for_raster
+
+    dem = synth.punch_holes(synth.fractal(1500, 1700, beta=2.0, seed=31), frac=0.01, seed=32)
+    fdr = np.ascontiguousarray(oracle.flow_direction_for_tile(synth.pad_nodata(dem), synth.NODATA)[1:-1, 1:-1])
+    want = oracle.flow_accumulation(fdr)
+    monkeypatch.setenv("OFL_FORCE_WIDE_FINAL", "1")
+    assert np.array_equal(flow_accumulation_for_raster(fdr), want)
+
+
 def test_random_shapes_counts_and_links():
     """Seeded sweep over ragged shapes around the 64-cell tile size (partial tiles, one-cell-wide
     tiles, nodata on tile corners): counts and perimeter links against the oracle."""

@@ -58,3 +58,27 @@ def test_many_bands_equal_separate_calls(monkeypatch):
     # oracle on a window that spans several band boundaries
     want = oracle.flow_direction_for_tile(np.ascontiguousarray(synth.pad_nodata(dem)[0:402, 0:502]), synth.NODATA)
     assert np.array_equal(fdr[1:399, 1:499], want[2:-2, 2:-2])
+
+
+def test_fused_call_on_device_buffers():
+    """ofl_flow_routing_f32 with OFL_MEM_DEVICE: the codes and counts of a device-resident DEM."""
+    import torch
+
+    from overflow_b200 import _native, device as dev
+
+    rows, cols = 777, 1040
+    dem = synth.punch_holes(synth.fractal(rows, cols, beta=2.0, seed=41), frac=0.01, seed=42)
+    want_fdr, want_fac = _oracle(dem)
+    d_dem = torch.from_numpy(dem).cuda()
+    d_fdr = torch.empty((rows, cols), dtype=torch.uint8, device="cuda")
+    d_fac = torch.empty((rows, cols), dtype=torch.int64, device="cuda")
+    assert d_dem.stride(0) % 4 == 0 and d_fdr.stride(0) % 16 == 0
+    _native.init(0)
+    _native.check(_native.lib().ofl_flow_routing_f32(
+        d_dem.data_ptr(), rows, cols, d_dem.stride(0), float(synth.NODATA), d_fdr.data_ptr(), d_fdr.stride(0),
+        d_fac.data_ptr(), d_fac.stride(0), None, _native.OFL_MEM_DEVICE,
+        torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(d_fdr.cpu().numpy(), want_fdr)
+    assert np.array_equal(d_fac.cpu().numpy(), want_fac)
+    assert dev.check_accumulation(d_fdr, d_fac) == 0
