@@ -214,11 +214,9 @@ def run_native(args):
         dem = dev.synth_dem(S, S, seed=args.seed, kind=args.kind, holes_permille=args.holes, nodata=NODATA)
         fdr = torch.empty((S, S), dtype=torch.uint8, device="cuda")
         fac = torch.empty((S, S), dtype=torch.int64, device="cuda")
-        ws = dev.accumulation_workspace(S, S)
 
         def step():
-            dev.flow_direction(dem, NODATA, out=fdr)
-            dev.flow_accumulation(fdr, out=fac, workspace=ws)
+            dev.flow_routing(dem, NODATA, out_fdr=fdr, out_fac=fac)  # one C-ABI call: direction, then accumulation
 
         cells_total = S * S
 
@@ -344,7 +342,7 @@ def run_native(args):
 
         h_dem = torch.empty((S, S), dtype=torch.float32, pin_memory=True)
         h_dem.copy_(dem)
-        del dem, fdr, fac, ws
+        del dem, fdr, fac
         torch.cuda.empty_cache()
         h_fdr = torch.empty((S, S), dtype=torch.uint8, pin_memory=True)
         h_fac = torch.empty((S, S), dtype=torch.int64, pin_memory=True)

@@ -1343,18 +1343,35 @@ static int launch_final(const AccCtx& C, const AccParams& p, unsigned grid, cuda
   return OFL_OK;
 }
 
+// The part of a whole-raster accumulation that does not depend on the codes: clearing the sums, the error
+// flags and round 0's counters.  A caller that produces the codes on the same device (ofl_flow_routing_f32)
+// runs it on a second stream next to the direction kernel and passes prepared = true below.
+int accumulation_prepare(int64_t rows, int64_t cols, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return OFL_OK;
+  const int64_t n = node_count(rows, cols);
+  const GraphLayout L = graph_layout(n, false);
+  OFL_REQUIRE(workspace != nullptr && workspace_bytes >= L.total, OFL_ERR_WORKSPACE,
+              "accumulation workspace too small: need %zu bytes, have %zu", L.total, workspace_bytes);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  int rc = ws_begin(ws, L, L.off_S, st);  // S
+  if (rc != OFL_OK) return rc;
+  // round 0's active / retired counts: pass A adds to the first, nothing retires before round 0
+  OFL_CUDA(cudaMemsetAsync(ws + L.off_counts, 0, 2 * (size_t)PJ_MAX_BLOCKS * sizeof(int), st));
+  return OFL_OK;
+}
+
 int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, long long* fac,
                         int64_t ld_fac, long long* perim_links_dev, void* workspace, size_t workspace_bytes,
-                        cudaStream_t st) {
+                        cudaStream_t st, bool prepared) {
   if (rows <= 0 || cols <= 0) return OFL_OK;
   AccCtx C;
   int rc = acc_setup(C, fdr, rows, cols, ld_fdr, 0, 0, 0, fac, ld_fac, workspace, workspace_bytes, false);
   if (rc != OFL_OK) return rc;
   const GraphLayout& L = C.L;
-  rc = ws_begin(C.ws, L, L.off_S, st);  // S
-  if (rc != OFL_OK) return rc;
-  if (C.p.fuse_init)  // round 0's active / retired counts: pass A adds to the first, nothing retires before round 0
-    OFL_CUDA(cudaMemsetAsync(C.counts, 0, 2 * (size_t)PJ_MAX_BLOCKS * sizeof(int), st));
+  if (!prepared) {
+    rc = accumulation_prepare(rows, cols, workspace, workspace_bytes, st);
+    if (rc != OFL_OK) return rc;
+  }
   {
     PhaseScope ps(PHASE_ACC_TILE_A, st);
     acc_tile_kernel<<<(unsigned)C.ntiles, ACC_THREADS, TileSmem::BYTES, st>>>(C.tm, C.p);

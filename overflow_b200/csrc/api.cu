@@ -22,7 +22,9 @@ int launch_fill_border(uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld, int
 int64_t perimeter_count(int64_t rows, int64_t cols);
 size_t accumulation_workspace_bytes(int64_t rows, int64_t cols);
 int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, long long* fac, int64_t ld_fac,
-                        long long* perim_links_dev, void* workspace, size_t workspace_bytes, cudaStream_t st);
+                        long long* perim_links_dev, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                        bool prepared = false);
+int accumulation_prepare(int64_t rows, int64_t cols, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t strip_workspace_bytes(int64_t rows, int64_t cols);
 size_t strip_boundary_workspace_bytes(int n_strips, int64_t cols);
 int strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above, int has_below,
@@ -283,10 +285,22 @@ int ofl_flow_routing_f32(const float* dem, int64_t rows, int64_t cols, int64_t l
   if (rc != OFL_OK) return rc;
   if (mem_kind == OFL_MEM_DEVICE) {
     OFL_REQUIRE(fdr != nullptr, OFL_ERR_INVALID, "device callers provide the code raster");
+    // the workspace is cleared on a second stream while the stencil runs
+    static cudaEvent_t ev_in = nullptr, ev_prep = nullptr;
+    rc = pipe_streams();
+    if (rc != OFL_OK) return rc;
+    if (!ev_in) OFL_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+    if (!ev_prep) OFL_CUDA(cudaEventCreateWithFlags(&ev_prep, cudaEventDisableTiming));
+    OFL_CUDA(cudaEventRecord(ev_in, st));
+    OFL_CUDA(cudaStreamWaitEvent(g_pipe.h2d, ev_in, 0));
+    rc = accumulation_prepare(rows, cols, work, need, g_pipe.h2d);
+    if (rc != OFL_OK) return rc;
+    OFL_CUDA(cudaEventRecord(ev_prep, g_pipe.h2d));
     rc = launch_direction(dem, rows, cols, ld_dem, nodata, fdr, rows, ld_fdr, 0, st);
     if (rc != OFL_OK) return rc;
+    OFL_CUDA(cudaStreamWaitEvent(st, ev_prep, 0));
     return launch_accumulation(fdr, rows, cols, ld_fdr, reinterpret_cast<long long*>(fac), ld_fac,
-                               reinterpret_cast<long long*>(perim_links), work, need, st);
+                               reinterpret_cast<long long*>(perim_links), work, need, st, true);
   }
   const int64_t ldd = round_up(cols, 4), ldi = round_up(cols, 16), ldo = round_up(cols, 2);
   void *d_dem = nullptr, *d_fdr = nullptr, *d_fac = nullptr, *d_links = nullptr;

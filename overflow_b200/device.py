@@ -99,6 +99,26 @@ def flow_accumulation(fdr: torch.Tensor, *, out=None, workspace=None, with_links
     return (out, links) if with_links else out
 
 
+def flow_routing(dem: torch.Tensor, nodata_value: float, *, out_fdr=None, out_fac=None):
+    """(fdr uint8, fac int64) of a float32 CUDA DEM in one library call (ofl_flow_routing_f32): the
+    accumulation workspace is library-owned and cleared next to the stencil.  Synchronises the stream."""
+    if dem.dtype != torch.float32 or dem.dim() != 2 or dem.stride(1) != 1:
+        raise ValueError("dem must be a 2-D float32 tensor with unit column stride")
+    _init_for(dem)
+    rows, cols = dem.shape
+    if out_fdr is None:
+        out_fdr = torch.empty((rows, (cols + 15) // 16 * 16), dtype=torch.uint8, device=dem.device)[:, :cols]
+    if out_fac is None:
+        out_fac = torch.empty((rows, cols), dtype=torch.int64, device=dem.device)
+    _native.check(
+        _native.lib().ofl_flow_routing_f32(
+            dem.data_ptr(), rows, cols, dem.stride(0), float(nodata_value), out_fdr.data_ptr(), out_fdr.stride(0),
+            out_fac.data_ptr(), out_fac.stride(0), None, _native.OFL_MEM_DEVICE, _stream(),
+        )
+    )
+    return out_fdr, out_fac
+
+
 def check_accumulation(fdr: torch.Tensor, fac: torch.Tensor) -> int:
     """Number of cells violating the accumulation recurrence (0 proves fac exact on an acyclic raster)."""
     _init_for(fdr)
