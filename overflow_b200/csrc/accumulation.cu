@@ -112,6 +112,7 @@ struct AccParams {
   // whole-raster calls: pass A publishes its slots straight into the solve's initial state (pointer
   // buffers, cleared delta entries, per-segment active lists) instead of `succ` + a separate init kernel
   int fuse_init, keep_succ;
+  int trusted_codes;  // the codes come straight from direction_kernel (0..9 only): pass A skips its sanitising sweep
   int32_t *ptr_a, *ptr_b, *list0;
   unsigned long long *d0, *d1;
   int* counts0;
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
   const int qx = lane & 15, rp = lane >> 4;
   constexpr int RWB = ACS_W;  // code row pitch in bytes
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 4 && !p.trusted_codes; ++i) {
     const int y = 8 * warp + 2 * i + rp;
     const uint32_t a = a_cs + (y + ACS_Y0) * RWB + ACS_X0 + 4 * qx;
     const uint32_t v = lds32(a);
@@ -1298,6 +1299,7 @@ static int acc_setup(AccCtx& C, const uint8_t* fdr, int64_t rows, int64_t cols, 
   p.L = reinterpret_cast<uint16_t*>(C.ws + C.L.off_L);
   p.wide_list = reinterpret_cast<int*>(C.ws + C.L.off_wide);
   p.force_wide = getenv("OFL_FORCE_WIDE_FINAL") ? 1 : 0;
+  p.trusted_codes = 0;
   {
     const PjSeg g = pj_segments(n);
     p.fuse_init = getenv("OFL_NO_FUSED_INIT") ? 0 : 1;
@@ -1362,11 +1364,12 @@ int accumulation_prepare(int64_t rows, int64_t cols, void* workspace, size_t wor
 
 int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, long long* fac,
                         int64_t ld_fac, long long* perim_links_dev, void* workspace, size_t workspace_bytes,
-                        cudaStream_t st, bool prepared) {
+                        cudaStream_t st, bool prepared, bool trusted_codes) {
   if (rows <= 0 || cols <= 0) return OFL_OK;
   AccCtx C;
   int rc = acc_setup(C, fdr, rows, cols, ld_fdr, 0, 0, 0, fac, ld_fac, workspace, workspace_bytes, false);
   if (rc != OFL_OK) return rc;
+  C.p.trusted_codes = trusted_codes ? 1 : 0;
   const GraphLayout& L = C.L;
   if (!prepared) {
     rc = accumulation_prepare(rows, cols, workspace, workspace_bytes, st);

@@ -23,7 +23,7 @@ int64_t perimeter_count(int64_t rows, int64_t cols);
 size_t accumulation_workspace_bytes(int64_t rows, int64_t cols);
 int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, long long* fac, int64_t ld_fac,
                         long long* perim_links_dev, void* workspace, size_t workspace_bytes, cudaStream_t st,
-                        bool prepared = false);
+                        bool prepared = false, bool trusted_codes = false);
 int accumulation_prepare(int64_t rows, int64_t cols, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t strip_workspace_bytes(int64_t rows, int64_t cols);
 size_t strip_boundary_workspace_bytes(int n_strips, int64_t cols);
@@ -300,7 +300,7 @@ int ofl_flow_routing_f32(const float* dem, int64_t rows, int64_t cols, int64_t l
     if (rc != OFL_OK) return rc;
     OFL_CUDA(cudaStreamWaitEvent(st, ev_prep, 0));
     return launch_accumulation(fdr, rows, cols, ld_fdr, reinterpret_cast<long long*>(fac), ld_fac,
-                               reinterpret_cast<long long*>(perim_links), work, need, st, true);
+                               reinterpret_cast<long long*>(perim_links), work, need, st, true, true);
   }
   const int64_t ldd = round_up(cols, 4), ldi = round_up(cols, 16), ldo = round_up(cols, 2);
   void *d_dem = nullptr, *d_fdr = nullptr, *d_fac = nullptr, *d_links = nullptr;
@@ -320,7 +320,7 @@ int ofl_flow_routing_f32(const float* dem, int64_t rows, int64_t cols, int64_t l
                            static_cast<uint8_t*>(d_fdr), ldi, fdr, ld_fdr, st, false);
   if (rc != OFL_OK) return rc;
   rc = launch_accumulation(static_cast<const uint8_t*>(d_fdr), rows, cols, ldi, static_cast<long long*>(d_fac), ldo,
-                           static_cast<long long*>(d_links), work, need, st);
+                           static_cast<long long*>(d_links), work, need, st, false, true);
   if (rc == OFL_OK) {
     cudaError_t e = cudaMemcpy2DAsync(fac, ld_fac * sizeof(int64_t), d_fac, ldo * sizeof(int64_t), cols * sizeof(int64_t),
                                       rows, cudaMemcpyDeviceToHost, st);
