@@ -100,7 +100,9 @@ __device__ __noinline__ uint32_t d8_slopes(float d0, float d1, float d2, float d
 }
 
 // One cell by the reference's rules: a NODATA neighbour is slope +inf, and the first +inf in scan order wins
-// (it is the first strict maximum); only a cell without one needs the float64 scan.
+// (it is the first strict maximum).  A cell without one whose differences are all finite is decided in
+// float32 whenever the fast path's own argument applies (class maxima, then the sign of u outside the
+// guard band); only what is left -- non-finite data, or u inside the band -- needs the float64 scan.
 __device__ __forceinline__ uint32_t d8_exact(float z, float nE, float nNE, float nN, float nNW, float nW, float nSW,
                                              float nS, float nSE, float nd) {
   if (z == nd) return OFL_DIR_NODATA;
@@ -112,6 +114,19 @@ __device__ __forceinline__ uint32_t d8_exact(float z, float nE, float nNE, float
 #pragma unroll
   for (int i = 7; i >= 0; --i) first = (d[i] == INFINITY) ? (uint32_t)i : first;
   if (first < 8) return first;
+  float finite = 0.f;  // stays 0 iff every difference is finite
+#pragma unroll
+  for (int i = 0; i < 8; ++i) finite = __fmaf_rn(d[i], 0.f, finite);
+  if (finite == 0.f) {
+    const float c = fmaxf(fmaxf(d[0], d[2]), fmaxf(d[4], d[6]));
+    const float dg = fmaxf(fmaxf(d[1], d[3]), fmaxf(d[5], d[7]));
+    if (!(fmaxf(c, dg) > 0.f)) return OFL_DIR_UNDEFINED;
+    const float u = __fmaf_rn(dg, 0.70710678118654752f, -c);
+    if (fabsf(u) > __fmul_rn(fabsf(c), 1.9073486328125e-06f)) {
+      if (u > 0.f) return d[1] == dg ? 1u : d[3] == dg ? 3u : d[5] == dg ? 5u : 7u;
+      return d[0] == c ? 0u : d[2] == c ? 2u : d[4] == c ? 4u : 6u;
+    }
+  }
   return d8_slopes(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
 }
 
