@@ -1,0 +1,47 @@
+"""bench.py prints ONE JSON line with the keys the driver reads (reference arm on CPU, native arm on a GPU)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+COMMON = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+          "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"}
+
+
+def _run(args):
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True,
+                         timeout=900, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, f"stdout must be one JSON line, got {len(lines)}"
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-sample", "256"])
+    assert d["impl"] == "reference"
+    assert COMMON <= set(d)
+    assert d["unit"] == "Gcells/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["config"]["workload"].startswith("flow_direction + flow_accumulation")
+    cb = d["cpu_baseline"]
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(cb) and cb["kind"] == "port" and cb["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["e2e"]["value"] == d["value"]
+
+
+@pytest.mark.gpu
+def test_native_arm_line():
+    d = _run(["--size", "2048", "--steps", "2", "--warmup", "3", "--cpu-sample", "512"])
+    assert COMMON | {"clocks", "gpu_launches", "roofline", "parity"} <= set(d)
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["gpu_launches"] > 0
+    r = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "hbm"
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert d["parity"]["accumulation_recurrence_violations"] == 0 and d["parity"]["direction_windows_vs_oracle"]
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 2048 * 2048 * 4 and e["d2h_bytes_per_step"] == 2048 * 2048 * 9 and e["value"] > 0
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
