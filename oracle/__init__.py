@@ -15,4 +15,7 @@ from .oracle import (  # noqa: F401
     check_accumulation,
     num_threads,
     set_num_threads,
+    flat_edges,
+    resolve_flats,
+    d8_masked_flow_dirs,
 )

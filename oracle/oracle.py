@@ -20,8 +20,8 @@ FLOW_TERMINATES = (-1, -1)
 
 def build(force=False):
     """Compile d8_oracle.c with the committed Makefile (gcc, OpenMP)."""
-    src = os.path.join(_HERE, "d8_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("d8_oracle.c", "flats_oracle.c", "Makefile")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
     return _SO
 
@@ -46,6 +46,12 @@ def _load():
     lib.orc_check_accumulation.argtypes = [vp, i64, i64, i64, vp, i64]
     lib.orc_check_accumulation.restype = i64
     lib.orc_num_threads.restype = ctypes.c_int
+    lib.orc_flat_edges_f32.argtypes = [vp, vp, i64, i64, vp, ctypes.POINTER(i64)]
+    lib.orc_flat_edges_f32.restype = i64
+    lib.orc_resolve_flats_f32.argtypes = [vp, vp, i64, i64, vp, vp]
+    lib.orc_resolve_flats_f32.restype = i64
+    lib.orc_d8_masked_flow_dirs.argtypes = [vp, vp, vp, i64, i64]
+    lib.orc_d8_masked_flow_dirs.restype = None
     lib.orc_set_num_threads.argtypes = [ctypes.c_int]
     _lib = lib
     return lib
@@ -143,3 +149,47 @@ def check_accumulation(fdr, fac):
     fac = np.ascontiguousarray(fac, dtype=np.int64)
     rows, cols = fdr.shape
     return int(_load().orc_check_accumulation(fdr.ctypes.data, rows, cols, cols, fac.ctypes.data, cols))
+
+
+# ---------------------------------------------------------------- flat resolution (flats_oracle.c)
+def _dem_f32(dem):
+    dem = np.asarray(dem)
+    if dem.ndim != 2:
+        raise ValueError("dem must be 2-D")
+    return np.ascontiguousarray(dem, dtype=np.float32)
+
+
+def flat_edges(dem, fdr):
+    """Restates flat_edges (reference fix_flats.py:13-62): (high_edges, low_edges) as lists of
+    (row, col) in the reference's row-major order."""
+    dem, fdr = _dem_f32(dem), _as_codes(fdr)
+    rows, cols = fdr.shape
+    edges = np.zeros((rows, cols), dtype=np.uint8)
+    n_high = ctypes.c_int64(0)
+    _load().orc_flat_edges_f32(dem.ctypes.data, fdr.ctypes.data, rows, cols, edges.ctypes.data, ctypes.byref(n_high))
+    high = [(int(r), int(c)) for r, c in zip(*np.nonzero(edges & 2))]
+    low = [(int(r), int(c)) for r, c in zip(*np.nonzero(edges & 1))]
+    return high, low
+
+
+def resolve_flats(dem, fdr):
+    """Restates resolve_flats (fix_flats.py:227-288): (flat_mask int32, labels int32)."""
+    dem, fdr = _dem_f32(dem), _as_codes(fdr)
+    rows, cols = fdr.shape
+    flat_mask = np.zeros((rows, cols), dtype=np.int32)
+    labels = np.zeros((rows, cols), dtype=np.int32)
+    rc = _load().orc_resolve_flats_f32(dem.ctypes.data, fdr.ctypes.data, rows, cols, flat_mask.ctypes.data,
+                                       labels.ctypes.data)
+    if rc < 0:
+        raise MemoryError("oracle queue allocation failed")
+    return flat_mask, labels
+
+
+def d8_masked_flow_dirs(flat_mask, fdr, labels):
+    """Restates d8_masked_flow_dirs (fix_flats.py:291-339); returns the rewritten codes (copy)."""
+    out = _as_codes(fdr).copy()
+    fm = np.ascontiguousarray(flat_mask, dtype=np.int32)
+    lb = np.ascontiguousarray(labels, dtype=np.int32)
+    rows, cols = out.shape
+    _load().orc_d8_masked_flow_dirs(fm.ctypes.data, out.ctypes.data, lb.ctypes.data, rows, cols)
+    return out
