@@ -14,6 +14,12 @@
  *   ofl_strip_*                   no reference counterpart: row-strip (multi-GPU) decomposition in the
  *                                 structure of Barnes 2016 (arXiv 1608.04431), the paper cited at
  *                                 src/overflow/flow_accumulation.py:61,100
+ *   ofl_flat_edges_f32            src/overflow/fix_flats.py:13-62    flat_edges
+ *   ofl_resolve_flats_f32         src/overflow/fix_flats.py:227-288  resolve_flats (label_flats :65-108,
+ *                                 away_from_higher :111-161, towards_lower :164-224)
+ *   ofl_flat_gradient_i32         src/overflow/fix_flats.py:111-224  away_from_higher / towards_lower on their own
+ *   ofl_d8_masked_flow_dirs_i32   src/overflow/fix_flats.py:291-339  d8_masked_flow_dirs
+ *   ofl_fix_flats_f32             resolve_flats followed by d8_masked_flow_dirs, codes rewritten in place
  *   ofl_synth_dem_f32             no reference counterpart: seeded synthetic DEM for benchmarks
  *
  * Conventions
@@ -98,8 +104,9 @@ void ofl_launch_count_reset(void);
  * totals and copies up to n totals (milliseconds) and launch counts out; returns the number of phases:
  *   0 direction kernel   1 accumulation tile pass A   2 perimeter-graph solve
  *   3 accumulation tile pass B   4 perimeter links   5 strip mode: pass B on the strip's first/last tile row
+ *   6 flat resolution (ofl_flat_edges_f32 ... ofl_fix_flats_f32)
  */
-#define OFL_PHASE_COUNT 6
+#define OFL_PHASE_COUNT 7
 void ofl_phase_timing_enable(int on);
 int ofl_phase_timing_read(double* ms, int64_t* counts, int n, int reset);
 
@@ -196,6 +203,36 @@ int ofl_strip_boundary_solve(const int32_t* slink_all, const int64_t* floc_all, 
 int ofl_strip_accum_final(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above,
                           int has_below, const int64_t* J_mine, void* workspace, size_t workspace_bytes, int64_t* fac,
                           int64_t ld_fac, void* stream);
+
+/*
+ * Flat resolution (Barnes, Lehman & Mulla 2014; the reference's src/overflow/fix_flats.py).  One tile of fewer
+ * than 2^31 cells; every raster is DENSE row-major (leading dimension == cols).  Host-pointer calls stage through
+ * library buffers; device-pointer calls take CUDA pointers.  All of these synchronise the stream before they
+ * return (the level loops of the two sweeps read a frontier count back).
+ *   dem        float32 elevations (compared with == and <, as the reference does on the array's own dtype)
+ *   fdr        uint8 direction codes; 8 = no direction (the flats), 9 = NODATA
+ *   edges      uint8 out: bit 0 = low edge, bit 1 = high edge (the reference returns two lists, row-major)
+ *   flat_mask  int32 out: increments per cell      labels  int32 out: flat labels, numbered in the order the
+ *              row-major low-edge list first meets each flat (1-based; 0 = not in a drainable flat)
+ *   info       nullable int64[5] out: low edges, high edges, labels, levels of the away / towards sweeps
+ *   workspace  device scratch of ofl_flats_workspace_bytes (NULL: library-owned, cached)
+ * ofl_flat_gradient_i32 runs one sweep from a list of seed cell indices (row * cols + col): towards == 0 is
+ * away_from_higher, towards == 1 is towards_lower (which negates flat_mask first and reads flat_height).
+ * ofl_fix_flats_f32 rewrites the code-8 cells of fdr in place; for host callers flat_mask / labels may be NULL.
+ */
+size_t ofl_flats_workspace_bytes(int64_t rows, int64_t cols);
+int ofl_flat_edges_f32(const float* dem, const uint8_t* fdr, int64_t rows, int64_t cols, uint8_t* edges, int64_t* n_low,
+                       int64_t* n_high, int mem_kind, void* stream);
+int ofl_resolve_flats_f32(const float* dem, const uint8_t* fdr, int64_t rows, int64_t cols, int32_t* flat_mask,
+                          int32_t* labels, int64_t* info, void* workspace, size_t workspace_bytes, int mem_kind,
+                          void* stream);
+int ofl_flat_gradient_i32(const int32_t* labels, const uint8_t* fdr, int64_t rows, int64_t cols, const int32_t* seeds,
+                          int64_t n_seeds, int towards, int32_t* flat_mask, int32_t* flat_height, int64_t n_heights,
+                          void* workspace, size_t workspace_bytes, int mem_kind, void* stream);
+int ofl_d8_masked_flow_dirs_i32(const int32_t* flat_mask, const int32_t* labels, uint8_t* fdr, int64_t rows, int64_t cols,
+                                int mem_kind, void* stream);
+int ofl_fix_flats_f32(const float* dem, uint8_t* fdr, int64_t rows, int64_t cols, int32_t* flat_mask, int32_t* labels,
+                      int64_t* info, void* workspace, size_t workspace_bytes, int mem_kind, void* stream);
 
 /*
  * Seeded synthetic DEM written straight into device memory (benchmarks / large parity runs).

@@ -56,6 +56,12 @@ SIGNATURES = {
     "ofl_strip_accum_local": (_int, [_vp, _i64, _i64, _i64, _int, _int, _vp, _i64, _vp, _sz, _vp, _vp, _vp, _vp]),
     "ofl_strip_boundary_solve": (_int, [_vp, _vp, _vp, _int, _i64, _vp, _vp, _sz, _vp]),
     "ofl_strip_accum_final": (_int, [_vp, _i64, _i64, _i64, _int, _int, _vp, _vp, _sz, _vp, _i64, _vp]),
+    "ofl_flats_workspace_bytes": (_sz, [_i64, _i64]),
+    "ofl_flat_edges_f32": (_int, [_vp, _vp, _i64, _i64, _vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64), _int, _vp]),
+    "ofl_resolve_flats_f32": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, ctypes.POINTER(_i64), _vp, _sz, _int, _vp]),
+    "ofl_flat_gradient_i32": (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _int, _vp, _vp, _i64, _vp, _sz, _int, _vp]),
+    "ofl_d8_masked_flow_dirs_i32": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _vp]),
+    "ofl_fix_flats_f32": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, ctypes.POINTER(_i64), _vp, _sz, _int, _vp]),
     "ofl_synth_dem_f32": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, ctypes.c_uint64, _int, ctypes.c_float, _int,
                                  ctypes.c_float, _vp]),
 }
@@ -107,7 +113,7 @@ def launch_count_reset():
     lib().ofl_launch_count_reset()
 
 
-PHASES = ("direction", "acc_tile_a", "acc_solve", "acc_tile_b", "acc_links", "strip_edge")
+PHASES = ("direction", "acc_tile_a", "acc_solve", "acc_tile_b", "acc_links", "strip_edge", "fix_flats")
 
 
 def phase_timing_enable(on=True):

@@ -37,6 +37,16 @@ int strip_accum_final(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
                       cudaStream_t st);
 int launch_check(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, const long long* fac, int64_t ld_fac,
                  unsigned long long* n_bad_dev, cudaStream_t st);
+size_t flats_workspace_bytes(int64_t rows, int64_t cols);
+int launch_flat_edges(const float* dem, const uint8_t* fdr, int64_t rows, int64_t cols, uint8_t* edges, int64_t* n_low,
+                      int64_t* n_high, unsigned* cnt_dev, cudaStream_t st);
+int launch_resolve_flats(const float* dem, const uint8_t* fdr, int64_t rows, int64_t cols, int* flat_mask, int* labels,
+                         int64_t* info, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int launch_flat_gradient(const int* labels, const uint8_t* fdr, int64_t rows, int64_t cols, const int* seeds,
+                         int64_t n_seeds, int towards, int* flat_mask, int* flat_height, int64_t n_heights,
+                         void* workspace, size_t workspace_bytes, cudaStream_t st);
+int launch_masked_flow_dirs(const int* flat_mask, const int* labels, uint8_t* fdr, int64_t rows, int64_t cols,
+                            cudaStream_t st);
 int launch_synth(float* dem, int64_t rows, int64_t cols, int64_t ld, int64_t row0, int64_t total_rows, uint64_t seed,
                  int kind, float relief, int holes_permille, float nodata, cudaStream_t st);
 }  // namespace ofl
@@ -369,6 +379,154 @@ int ofl_check_accumulation_u8(const uint8_t* fdr, int64_t rows, int64_t cols, in
   OFL_CUDA(cudaMemcpyAsync(&h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, st));
   OFL_CUDA(cudaStreamSynchronize(st));
   *n_bad = (int64_t)h;
+  return OFL_OK;
+}
+
+// ---------------------------------------------------------------- flat resolution (csrc/flats.cu)
+size_t ofl_flats_workspace_bytes(int64_t rows, int64_t cols) {
+  return (rows > 0 && cols > 0) ? flats_workspace_bytes(rows, cols) : 0;
+}
+
+#define OFL_FLATS_COMMON(...)                                                                                        \
+  OFL_REQUIRE(rows >= 0 && cols >= 0, OFL_ERR_INVALID, "negative raster size");                                       \
+  OFL_REQUIRE(mem_kind == OFL_MEM_HOST || mem_kind == OFL_MEM_DEVICE, OFL_ERR_INVALID, "unknown mem_kind %d", mem_kind); \
+  if (rows == 0 || cols == 0) return OFL_OK;                                                                           \
+  OFL_REQUIRE(__VA_ARGS__, OFL_ERR_INVALID, "null raster pointer");                                                    \
+  int rc = ensure_init();                                                                                              \
+  if (rc != OFL_OK) return rc;                                                                                         \
+  cudaStream_t st = static_cast<cudaStream_t>(stream);                                                                 \
+  const size_t n = (size_t)rows * (size_t)cols
+
+int ofl_flat_edges_f32(const float* dem, const uint8_t* fdr, int64_t rows, int64_t cols, uint8_t* edges, int64_t* n_low,
+                       int64_t* n_high, int mem_kind, void* stream) {
+  if (n_low) *n_low = 0;
+  if (n_high) *n_high = 0;
+  OFL_FLATS_COMMON(dem && fdr && edges);
+  void* d_cnt = nullptr;
+  rc = scratch_get(SCRATCH_MISC, 256, &d_cnt);
+  if (rc != OFL_OK) return rc;
+  if (mem_kind == OFL_MEM_DEVICE)
+    return launch_flat_edges(dem, fdr, rows, cols, edges, n_low, n_high, static_cast<unsigned*>(d_cnt), st);
+  void *d_dem = nullptr, *d_fdr = nullptr, *d_edges = nullptr;
+  if ((rc = scratch_get(SCRATCH_DEM, n * sizeof(float), &d_dem)) != OFL_OK) return rc;
+  if ((rc = scratch_get(SCRATCH_FDR, n, &d_fdr)) != OFL_OK) return rc;
+  if ((rc = scratch_get(SCRATCH_LINKS, n, &d_edges)) != OFL_OK) return rc;
+  OFL_CUDA(cudaMemcpyAsync(d_dem, dem, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  OFL_CUDA(cudaMemcpyAsync(d_fdr, fdr, n, cudaMemcpyHostToDevice, st));
+  rc = launch_flat_edges(static_cast<float*>(d_dem), static_cast<uint8_t*>(d_fdr), rows, cols,
+                         static_cast<uint8_t*>(d_edges), n_low, n_high, static_cast<unsigned*>(d_cnt), st);
+  if (rc != OFL_OK) return rc;
+  OFL_CUDA(cudaMemcpyAsync(edges, d_edges, n, cudaMemcpyDeviceToHost, st));
+  OFL_CUDA(cudaStreamSynchronize(st));
+  return OFL_OK;
+}
+
+// resolve (+ optionally rewrite the codes): shared by ofl_resolve_flats_f32 and ofl_fix_flats_f32
+static int flats_run(const float* dem, const uint8_t* fdr_in, uint8_t* fdr_out, int64_t rows, int64_t cols,
+                     int32_t* flat_mask, int32_t* labels, int64_t* info, void* workspace, size_t workspace_bytes,
+                     int mem_kind, cudaStream_t st) {
+  const size_t n = (size_t)rows * (size_t)cols;
+  int rc;
+  if (!workspace) {
+    workspace_bytes = flats_workspace_bytes(rows, cols);
+    if ((rc = scratch_get(SCRATCH_WORK, workspace_bytes, &workspace)) != OFL_OK) return rc;
+  }
+  if (mem_kind == OFL_MEM_DEVICE) {
+    OFL_REQUIRE(flat_mask && labels, OFL_ERR_INVALID, "device callers provide flat_mask and labels");
+    rc = launch_resolve_flats(dem, fdr_in, rows, cols, flat_mask, labels, info, workspace, workspace_bytes, st);
+    if (rc == OFL_OK && fdr_out) rc = launch_masked_flow_dirs(flat_mask, labels, fdr_out, rows, cols, st);
+    return rc;
+  }
+  void *d_dem = nullptr, *d_fdr = nullptr, *d_out = nullptr;
+  if ((rc = scratch_get(SCRATCH_DEM, n * sizeof(float), &d_dem)) != OFL_OK) return rc;
+  if ((rc = scratch_get(SCRATCH_FDR, n, &d_fdr)) != OFL_OK) return rc;
+  if ((rc = scratch_get(SCRATCH_FAC, 2 * n * sizeof(int32_t), &d_out)) != OFL_OK) return rc;
+  int32_t* d_mask = static_cast<int32_t*>(d_out);
+  int32_t* d_labels = d_mask + n;
+  OFL_CUDA(cudaMemcpyAsync(d_dem, dem, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  OFL_CUDA(cudaMemcpyAsync(d_fdr, fdr_in, n, cudaMemcpyHostToDevice, st));
+  rc = launch_resolve_flats(static_cast<float*>(d_dem), static_cast<uint8_t*>(d_fdr), rows, cols, d_mask, d_labels, info,
+                            workspace, workspace_bytes, st);
+  if (rc != OFL_OK) return rc;
+  if (fdr_out) {
+    rc = launch_masked_flow_dirs(d_mask, d_labels, static_cast<uint8_t*>(d_fdr), rows, cols, st);
+    if (rc != OFL_OK) return rc;
+    OFL_CUDA(cudaMemcpyAsync(fdr_out, d_fdr, n, cudaMemcpyDeviceToHost, st));
+  }
+  if (flat_mask) OFL_CUDA(cudaMemcpyAsync(flat_mask, d_mask, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (labels) OFL_CUDA(cudaMemcpyAsync(labels, d_labels, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  OFL_CUDA(cudaStreamSynchronize(st));
+  return OFL_OK;
+}
+
+int ofl_resolve_flats_f32(const float* dem, const uint8_t* fdr, int64_t rows, int64_t cols, int32_t* flat_mask,
+                          int32_t* labels, int64_t* info, void* workspace, size_t workspace_bytes, int mem_kind,
+                          void* stream) {
+  if (info) for (int k = 0; k < 5; ++k) info[k] = 0;
+  OFL_FLATS_COMMON(dem && fdr && flat_mask && labels);
+  (void)n;
+  return flats_run(dem, fdr, nullptr, rows, cols, flat_mask, labels, info, workspace, workspace_bytes, mem_kind, st);
+}
+
+int ofl_fix_flats_f32(const float* dem, uint8_t* fdr, int64_t rows, int64_t cols, int32_t* flat_mask, int32_t* labels,
+                      int64_t* info, void* workspace, size_t workspace_bytes, int mem_kind, void* stream) {
+  if (info) for (int k = 0; k < 5; ++k) info[k] = 0;
+  OFL_FLATS_COMMON(dem && fdr);
+  (void)n;
+  return flats_run(dem, fdr, fdr, rows, cols, flat_mask, labels, info, workspace, workspace_bytes, mem_kind, st);
+}
+
+int ofl_d8_masked_flow_dirs_i32(const int32_t* flat_mask, const int32_t* labels, uint8_t* fdr, int64_t rows, int64_t cols,
+                                int mem_kind, void* stream) {
+  OFL_FLATS_COMMON(flat_mask && labels && fdr);
+  if (mem_kind == OFL_MEM_DEVICE) return launch_masked_flow_dirs(flat_mask, labels, fdr, rows, cols, st);
+  void *d_fdr = nullptr, *d_in = nullptr;
+  if ((rc = scratch_get(SCRATCH_FDR, n, &d_fdr)) != OFL_OK) return rc;
+  if ((rc = scratch_get(SCRATCH_FAC, 2 * n * sizeof(int32_t), &d_in)) != OFL_OK) return rc;
+  int32_t* d_mask = static_cast<int32_t*>(d_in);
+  int32_t* d_labels = d_mask + n;
+  OFL_CUDA(cudaMemcpyAsync(d_mask, flat_mask, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  OFL_CUDA(cudaMemcpyAsync(d_labels, labels, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  OFL_CUDA(cudaMemcpyAsync(d_fdr, fdr, n, cudaMemcpyHostToDevice, st));
+  rc = launch_masked_flow_dirs(d_mask, d_labels, static_cast<uint8_t*>(d_fdr), rows, cols, st);
+  if (rc != OFL_OK) return rc;
+  OFL_CUDA(cudaMemcpyAsync(fdr, d_fdr, n, cudaMemcpyDeviceToHost, st));
+  OFL_CUDA(cudaStreamSynchronize(st));
+  return OFL_OK;
+}
+
+int ofl_flat_gradient_i32(const int32_t* labels, const uint8_t* fdr, int64_t rows, int64_t cols, const int32_t* seeds,
+                          int64_t n_seeds, int towards, int32_t* flat_mask, int32_t* flat_height, int64_t n_heights,
+                          void* workspace, size_t workspace_bytes, int mem_kind, void* stream) {
+  OFL_FLATS_COMMON(labels && fdr && flat_mask && (seeds || n_seeds == 0) && (flat_height || n_heights == 0));
+  OFL_REQUIRE(n_seeds >= 0 && n_heights >= 0 && (size_t)n_seeds <= n && (size_t)n_heights <= n, OFL_ERR_INVALID,
+              "seed / flat_height count out of range");
+  if (!workspace) {
+    workspace_bytes = flats_workspace_bytes(rows, cols);
+    if ((rc = scratch_get(SCRATCH_WORK, workspace_bytes, &workspace)) != OFL_OK) return rc;
+  }
+  if (mem_kind == OFL_MEM_DEVICE)
+    return launch_flat_gradient(labels, fdr, rows, cols, seeds, n_seeds, towards, flat_mask, flat_height, n_heights,
+                                workspace, workspace_bytes, st);
+  void *d_fdr = nullptr, *d_io = nullptr, *d_small = nullptr;
+  if ((rc = scratch_get(SCRATCH_FDR, n, &d_fdr)) != OFL_OK) return rc;
+  if ((rc = scratch_get(SCRATCH_FAC, 2 * n * sizeof(int32_t), &d_io)) != OFL_OK) return rc;
+  if ((rc = scratch_get(SCRATCH_LINKS, (size_t)(n_seeds + n_heights + 2) * sizeof(int32_t), &d_small)) != OFL_OK) return rc;
+  int32_t* d_mask = static_cast<int32_t*>(d_io);
+  int32_t* d_labels = d_mask + n;
+  int32_t* d_seeds = static_cast<int32_t*>(d_small);
+  int32_t* d_fh = d_seeds + n_seeds;
+  OFL_CUDA(cudaMemcpyAsync(d_mask, flat_mask, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  OFL_CUDA(cudaMemcpyAsync(d_labels, labels, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  OFL_CUDA(cudaMemcpyAsync(d_fdr, fdr, n, cudaMemcpyHostToDevice, st));
+  if (n_seeds) OFL_CUDA(cudaMemcpyAsync(d_seeds, seeds, (size_t)n_seeds * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (n_heights) OFL_CUDA(cudaMemcpyAsync(d_fh, flat_height, (size_t)n_heights * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  rc = launch_flat_gradient(d_labels, static_cast<uint8_t*>(d_fdr), rows, cols, d_seeds, n_seeds, towards, d_mask, d_fh,
+                            n_heights, workspace, workspace_bytes, st);
+  if (rc != OFL_OK) return rc;
+  OFL_CUDA(cudaMemcpyAsync(flat_mask, d_mask, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (n_heights) OFL_CUDA(cudaMemcpyAsync(flat_height, d_fh, (size_t)n_heights * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  OFL_CUDA(cudaStreamSynchronize(st));
   return OFL_OK;
 }
 

@@ -1,0 +1,557 @@
+// flats.cu -- flat resolution (Barnes, Lehman & Mulla 2014) on the device: the reference's
+// src/overflow/fix_flats.py (flat_edges :13-62, label_flats :65-108, away_from_higher :111-161,
+// towards_lower :164-224, resolve_flats :227-288, d8_masked_flow_dirs :291-339).
+//
+// The reference is a chain of sequential scans and FIFO sweeps.  What it computes is order-free, and that is
+// what runs here:
+//   * flat_edges is a 3x3 stencil (a cell is a low edge iff it has a direction and an equally high
+//     neighbour without one; a high edge iff it has none and a higher neighbour that is not NODATA).
+//   * label_flats floods cells of equal elevation, 8-connected, whatever their direction code; labels are
+//     handed out in the order the row-major low-edge list meets unlabelled cells.  Here: union-find over
+//     "equal elevation" links (atomicMin hooking, path halving), the smallest low-edge index of every
+//     component by atomicMin, and label = 1 + rank of that index among all components' smallest low edges
+//     (a prefix sum over the raster).  Components without a low edge keep label 0.
+//   * away_from_higher / towards_lower are breadth-first sweeps with a level marker: a cell's value is its
+//     BFS level from the seed edges through same-label cells without a direction.  Here: level-synchronous
+//     frontier queues (ballot-compacted appends, one claim per cell by compare-and-swap), the level loop
+//     batched on the host with a count read back per batch; flat_height[label] = max level by atomicMax
+//     (the reference's "last write" is the largest level because levels only grow).
+//   * d8_masked_flow_dirs is a 3x3 stencil over flat_mask and labels, slopes in float64 as in the reference.
+// Everything is integer work except the two float compares (==, <) on elevations and the float64 slope
+// division, so results are compared bit for bit with the reference's.
+#include <limits.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace ofl {
+
+namespace {
+
+constexpr int FL_UNDEF = OFL_DIR_UNDEFINED, FL_NODATA = OFL_DIR_NODATA;
+constexpr int FL_BIG = INT_MAX;
+constexpr int FL_THREADS = 256;
+constexpr int FL_SCAN_THREADS = 1024;
+
+// counters (uint32) kept in device memory
+enum { CNT_LOW = 0, CNT_HIGH, CNT_LABELS, CNT_SEEDS, CNT_FRONT0, CNT_FRONT1, CNT_FRONT2, CNT_SLOTS = 16 };
+
+__constant__ int c_dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};  // E NE N NW W SW S SE: constants.py:29-40
+__constant__ int c_dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+
+// ---------------------------------------------------------------- flat_edges (fix_flats.py:13-62)
+// also initialises the union-find forest (parent = self) and the per-component "smallest low edge" slot
+__global__ void __launch_bounds__(FL_THREADS)
+flat_edges_kernel(const float* __restrict__ dem, const uint8_t* __restrict__ fdr, int rows, int cols, uint8_t* edges,
+                  int* parent, int* minlow, unsigned* cnt) {
+  const int64_t n = (int64_t)rows * cols;
+  const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
+  int flag = 0;
+  if (i < n) {
+    const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+    const int cur = fdr[i];
+    const float z = dem[i];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int nr = r + c_dy[k], nc = c + c_dx[k];
+      if (nr < 0 || nr >= rows || nc < 0 || nc >= cols) continue;
+      const int64_t j = (int64_t)nr * cols + nc;
+      const int fn = fdr[j];
+      if (fn == FL_NODATA) continue;
+      const float zn = dem[j];
+      if (cur != FL_UNDEF && fn == FL_UNDEF && z == zn) {
+        flag = 1;
+        break;
+      }
+      if (cur == FL_UNDEF && z < zn) {
+        flag = 2;
+        break;
+      }
+    }
+    edges[i] = (uint8_t)flag;
+    if (parent) {
+      parent[i] = (int)i;
+      minlow[i] = FL_BIG;
+    }
+  }
+  const unsigned lo = __ballot_sync(0xffffffffu, flag == 1), hi = __ballot_sync(0xffffffffu, flag == 2);
+  if ((threadIdx.x & 31) == 0) {
+    if (lo) atomicAdd(&cnt[CNT_LOW], __popc(lo));
+    if (hi) atomicAdd(&cnt[CNT_HIGH], __popc(hi));
+  }
+}
+
+// ---------------------------------------------------------------- equal-elevation components
+__device__ __forceinline__ int uf_find(int* p, int i) {
+  int cur = __ldcg(p + i);
+  while (cur != i) {
+    const int nxt = __ldcg(p + cur);
+    if (nxt != cur) p[i] = nxt;  // path halving; any ancestor is a valid parent
+    i = cur;
+    cur = nxt;
+  }
+  return i;
+}
+
+// read-only walk to the root (used once the forest is final: concurrent halving could overwrite a flattened entry)
+__device__ __forceinline__ int uf_find_ro(const int* p, int i) {
+  int cur = __ldcg(p + i);
+  while (cur != i) {
+    i = cur;
+    cur = __ldcg(p + cur);
+  }
+  return i;
+}
+
+__device__ __forceinline__ void uf_unite(int* p, int a, int b) {
+  for (;;) {
+    a = uf_find(p, a);
+    b = uf_find(p, b);
+    if (a == b) return;
+    if (a < b) {
+      const int t = a;
+      a = b;
+      b = t;
+    }
+    const int old = atomicMin(p + a, b);  // hook the larger root under the smaller one
+    if (old == a) return;
+    a = old;  // a was no longer a root: carry on from what it pointed to
+  }
+}
+
+__global__ void __launch_bounds__(FL_THREADS)
+flat_merge_kernel(const float* __restrict__ dem, int rows, int cols, int* parent) {
+  const int64_t n = (int64_t)rows * cols;
+  const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+  const float z = dem[i];
+  // the four forward neighbours cover every 8-connected pair once
+  if (c + 1 < cols && dem[i + 1] == z) uf_unite(parent, (int)i, (int)i + 1);
+  if (r + 1 < rows) {
+    const int64_t j = i + cols;
+    if (c > 0 && dem[j - 1] == z) uf_unite(parent, (int)i, (int)(j - 1));
+    if (dem[j] == z) uf_unite(parent, (int)i, (int)j);
+    if (c + 1 < cols && dem[j + 1] == z) uf_unite(parent, (int)i, (int)(j + 1));
+  }
+}
+
+// parent[i] = root; low edges post their index to the root's slot
+__global__ void __launch_bounds__(FL_THREADS)
+flat_flatten_kernel(int64_t n, int* parent, const uint8_t* __restrict__ edges, int* minlow) {
+  const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const int root = uf_find_ro(parent, (int)i);
+  parent[i] = root;  // the only kind of write in this kernel: every entry a reader meets is an ancestor or the root
+  if (edges[i] & 1) atomicMin(minlow + root, (int)i);
+}
+
+// a seed is the first low edge (row-major) of its component
+__device__ __forceinline__ bool is_seed(int64_t i, int64_t n, const int* parent, const uint8_t* edges, const int* minlow) {
+  return i < n && (edges[i] & 1) && minlow[parent[i]] == (int)i;
+}
+
+__global__ void __launch_bounds__(FL_SCAN_THREADS)
+flat_seed_count_kernel(int64_t n, const int* __restrict__ parent, const uint8_t* __restrict__ edges,
+                       const int* __restrict__ minlow, int* blockcnt) {
+  const int64_t i = (int64_t)blockIdx.x * FL_SCAN_THREADS + threadIdx.x;
+  const int total = __syncthreads_count(is_seed(i, n, parent, edges, minlow));
+  if (threadIdx.x == 0) blockcnt[blockIdx.x] = total;
+}
+
+// exclusive scan of blockcnt[nb] in place (one CTA; nb <= 2^21), total -> cnt[CNT_LABELS]
+__global__ void __launch_bounds__(FL_SCAN_THREADS) flat_seed_scan_kernel(int nb, int* blockcnt, unsigned* cnt) {
+  __shared__ int part[FL_SCAN_THREADS];
+  const int t = threadIdx.x;
+  const int per = (nb + FL_SCAN_THREADS - 1) / FL_SCAN_THREADS;
+  const int lo = t * per, hi = min(nb, lo + per);
+  int s = 0;
+  for (int k = lo; k < hi; ++k) s += blockcnt[k];
+  part[t] = s;
+  __syncthreads();
+  for (int off = 1; off < FL_SCAN_THREADS; off <<= 1) {  // Hillis-Steele inclusive scan
+    const int v = t >= off ? part[t - off] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int run = part[t] - s;
+  for (int k = lo; k < hi; ++k) {
+    const int v = blockcnt[k];
+    blockcnt[k] = run;
+    run += v;
+  }
+  if (t == FL_SCAN_THREADS - 1) cnt[CNT_LABELS] = (unsigned)part[t];
+}
+
+// seedlabel[i] = 1 + rank of seed i
+__global__ void __launch_bounds__(FL_SCAN_THREADS)
+flat_seed_rank_kernel(int64_t n, const int* __restrict__ parent, const uint8_t* __restrict__ edges,
+                      const int* __restrict__ minlow, const int* __restrict__ blockoff, int* seedlabel) {
+  __shared__ int warp_tot[FL_SCAN_THREADS / 32];
+  const int64_t i = (int64_t)blockIdx.x * FL_SCAN_THREADS + threadIdx.x;
+  const bool seed = is_seed(i, n, parent, edges, minlow);
+  const unsigned m = __ballot_sync(0xffffffffu, seed);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) warp_tot[w] = __popc(m);
+  __syncthreads();
+  if (seed) {
+    int before = __popc(m & ((1u << lane) - 1u));
+    for (int k = 0; k < w; ++k) before += warp_tot[k];
+    seedlabel[i] = blockoff[blockIdx.x] + before + 1;
+  }
+}
+
+// roots: slot (smallest low edge, or BIG) -> the component's label
+__global__ void __launch_bounds__(FL_THREADS)
+flat_root_label_kernel(int64_t n, const int* __restrict__ parent, int* labels, const int* __restrict__ seedlabel) {
+  const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
+  if (i >= n || parent[i] != (int)i) return;
+  const int m = labels[i];
+  labels[i] = (m == FL_BIG) ? 0 : seedlabel[m];
+}
+
+// everyone else copies the root's label; the scratch use of flat_mask and parent ends here
+__global__ void __launch_bounds__(FL_THREADS)
+flat_spread_label_kernel(int64_t n, int* parent, int* labels, int* flat_mask) {
+  const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const int root = parent[i];
+  if (root != (int)i) labels[i] = labels[root];
+  flat_mask[i] = 0;
+}
+
+// ---------------------------------------------------------------- gradients (away_from_higher / towards_lower)
+// edge cells -> seed list, in no particular order (the sweeps are order-free)
+__global__ void __launch_bounds__(FL_THREADS)
+flat_collect_kernel(int64_t n, const uint8_t* __restrict__ edges, int bit, const int* __restrict__ labels, int* seeds,
+                    unsigned* cnt) {
+  const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
+  const bool take = i < n && (edges[i] & bit) && labels[i] != 0;  // fix_flats.py:273-274 (low edges always carry a label)
+  const unsigned m = __ballot_sync(0xffffffffu, take);
+  if (m == 0) return;
+  const int lane = threadIdx.x & 31;
+  unsigned base = 0;
+  if (lane == 0) base = atomicAdd(&cnt[CNT_SEEDS], __popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (take) seeds[base + __popc(m & ((1u << lane) - 1u))] = (int)i;
+}
+
+__global__ void __launch_bounds__(FL_THREADS) flat_negate_kernel(int64_t n, int* flat_mask) {  // fix_flats.py:200
+  const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
+  if (i < n) flat_mask[i] = -flat_mask[i];
+}
+
+// One try to give cell p its value at `level`; true iff this thread won the cell.
+__device__ __forceinline__ bool flat_claim(int p, int level, int towards, int lab, int* flat_mask, const int* fh_read,
+                                           int* fh_acc) {
+  const int fm = __ldcg(flat_mask + p);
+  if (fm > 0) return false;  // :149 / :207
+  int nv;
+  if (!towards)
+    nv = level;  // :153
+  else
+    nv = ((fm < 0 && lab > 0) ? fm + fh_read[lab - 1] : 0) + 2 * level;  // :209-214
+  if (atomicCAS(flat_mask + p, fm, nv) != fm) return false;
+  if (!towards && lab > 0) atomicMax(fh_acc + lab - 1, level);  // :154
+  return true;
+}
+
+__device__ __forceinline__ void flat_append(bool won, int p, int* qout, unsigned* cnt_out) {
+  const unsigned m = __ballot_sync(0xffffffffu, won);
+  if (m == 0) return;
+  const int lane = threadIdx.x & 31;
+  unsigned base = 0;
+  if (lane == __ffs(m) - 1) base = atomicAdd(cnt_out, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (won) qout[base + __popc(m & ((1u << lane) - 1u))] = p;
+}
+
+// level 1: the seed edges themselves (duplicates and already positive cells drop out)
+__global__ void __launch_bounds__(FL_THREADS)
+flat_seed_level_kernel(const int* __restrict__ seeds, const int* __restrict__ labels, int towards, int* flat_mask,
+                       const int* fh_read, int* fh_acc, int* qout, unsigned* cnt) {
+  const unsigned n_seed = cnt[CNT_SEEDS];
+  if (blockIdx.x == 0 && threadIdx.x == 0) cnt[CNT_FRONT0 + 2] = 0;
+  const unsigned stride = gridDim.x * FL_THREADS;
+  for (unsigned base = blockIdx.x * FL_THREADS; base < n_seed; base += stride) {
+    const unsigned idx = base + threadIdx.x;
+    bool won = false;
+    int p = 0;
+    if (idx < n_seed) {
+      p = seeds[idx];
+      won = flat_claim(p, 1, towards, labels[p], flat_mask, fh_read, fh_acc);
+    }
+    flat_append(won, p, qout, &cnt[CNT_FRONT0 + 1]);
+  }
+}
+
+// level L -> L+1: neighbours with the same label and no direction (:155-161 / :215-224)
+__global__ void __launch_bounds__(FL_THREADS)
+flat_level_kernel(int level, const int* __restrict__ qin, int* qout, const int* __restrict__ labels,
+                  const uint8_t* __restrict__ fdr, int rows, int cols, int towards, int* flat_mask, const int* fh_read,
+                  int* fh_acc, unsigned* cnt) {
+  const unsigned n_in = cnt[CNT_FRONT0 + level % 3];
+  unsigned* cnt_out = &cnt[CNT_FRONT0 + (level + 1) % 3];
+  if (blockIdx.x == 0 && threadIdx.x == 0) cnt[CNT_FRONT0 + (level + 2) % 3] = 0;
+  const unsigned stride = gridDim.x * FL_THREADS;
+  for (unsigned base = blockIdx.x * FL_THREADS; base < n_in; base += stride) {
+    const unsigned idx = base + threadIdx.x;
+    const bool live = idx < n_in;
+    int p = 0, lab = 0, r = 0, c = 0;
+    if (live) {
+      p = qin[idx];
+      lab = labels[p];
+      r = p / cols;
+      c = p - r * cols;
+    }
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+      bool won = false;
+      int q = 0;
+      if (live) {
+        const int nr = r + c_dy[k], nc = c + c_dx[k];
+        if (nr >= 0 && nr < rows && nc >= 0 && nc < cols) {
+          q = nr * cols + nc;
+          if (labels[q] == lab && fdr[q] == FL_UNDEF) won = flat_claim(q, level + 1, towards, lab, flat_mask, fh_read, fh_acc);
+        }
+      }
+      flat_append(won, q, qout, cnt_out);
+    }
+  }
+}
+
+// flat_height[k] takes the sweep's value where the sweep reached label k+1 (standalone away_from_higher)
+__global__ void __launch_bounds__(FL_THREADS) flat_height_merge_kernel(int n, const int* __restrict__ acc, int* fh) {
+  const int i = blockIdx.x * FL_THREADS + threadIdx.x;
+  if (i < n && acc[i] > 0) fh[i] = acc[i];
+}
+
+// ---------------------------------------------------------------- d8_masked_flow_dirs (fix_flats.py:291-339)
+__global__ void __launch_bounds__(FL_THREADS)
+flat_masked_dirs_kernel(const int* __restrict__ flat_mask, const int* __restrict__ labels, uint8_t* fdr, int rows,
+                        int cols) {
+  const int64_t n = (int64_t)rows * cols;
+  const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
+  if (i >= n || fdr[i] != FL_UNDEF) return;
+  const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+  const int lab = labels[i];
+  const double fm = (double)flat_mask[i];
+  int nmin = FL_UNDEF;
+  double min_slope = CUDART_INF;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int nr = r + c_dy[k], nc = c + c_dx[k];
+    if (nr < 0 || nr >= rows || nc < 0 || nc >= cols) continue;
+    const int64_t j = (int64_t)nr * cols + nc;
+    if (labels[j] != lab) continue;
+    const double dz = (double)flat_mask[j] - fm;
+    const double slope = (k & 1) ? __ddiv_rn(dz, 1.4142135623730951) : dz;  // odd codes are the diagonals
+    if (slope < min_slope) {
+      min_slope = slope;
+      nmin = k;
+    }
+  }
+  fdr[i] = (uint8_t)nmin;
+}
+
+inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+struct FlatsWork {
+  int* parent;  // union-find forest, later flat_height
+  int* q0;      // frontier queue / block counts of the label scan
+  int* q1;      // seed list / frontier queue
+  uint8_t* edges;
+  unsigned* cnt;
+};
+
+size_t flats_align(size_t v) { return (v + 255) / 256 * 256; }
+
+int carve(void* workspace, size_t workspace_bytes, int64_t n, FlatsWork* w) {
+  const size_t a = flats_align((size_t)n * sizeof(int)), e = flats_align((size_t)n), c = flats_align(CNT_SLOTS * sizeof(unsigned));
+  OFL_REQUIRE(workspace_bytes >= 3 * a + e + c, OFL_ERR_WORKSPACE, "flats workspace too small: %zu < %zu", workspace_bytes,
+              3 * a + e + c);
+  char* p = static_cast<char*>(workspace);
+  w->parent = reinterpret_cast<int*>(p);
+  w->q0 = reinterpret_cast<int*>(p + a);
+  w->q1 = reinterpret_cast<int*>(p + 2 * a);
+  w->edges = reinterpret_cast<uint8_t*>(p + 3 * a);
+  w->cnt = reinterpret_cast<unsigned*>(p + 3 * a + e);
+  return OFL_OK;
+}
+
+// One sweep from the seed list in w.q1 (count in cnt[CNT_SEEDS]).  Host-synchronous: the level loop reads the
+// next frontier's size back once per batch of launches.
+int run_gradient(int rows, int cols, const int* labels, const uint8_t* fdr, int towards, int* flat_mask,
+                 const int* fh_read, int* fh_acc, const FlatsWork& w, int64_t* levels_out, cudaStream_t st) {
+  const int64_t n = (int64_t)rows * cols;
+  OFL_CUDA(cudaMemsetAsync(w.cnt + CNT_FRONT0, 0, 3 * sizeof(unsigned), st));
+  if (towards) {
+    flat_negate_kernel<<<blocks_for(n, FL_THREADS), FL_THREADS, 0, st>>>(n, flat_mask);
+    OFL_CHECK_LAUNCH();
+  }
+  const unsigned grid = (unsigned)(sm_count() * 4);
+  flat_seed_level_kernel<<<grid, FL_THREADS, 0, st>>>(w.q1, labels, towards, flat_mask, fh_read, fh_acc, w.q0, w.cnt);
+  OFL_CHECK_LAUNCH();
+  unsigned* h_cnt = nullptr;
+  int rc = pinned_get(64, reinterpret_cast<void**>(&h_cnt));
+  if (rc != OFL_OK) return rc;
+  int level = 1;  // the frontier in `qin` holds the cells of this level
+  int* qin = w.q0;
+  int* qout = w.q1;
+  int batch = 8;
+  for (;;) {
+    for (int b = 0; b < batch; ++b) {
+      flat_level_kernel<<<grid, FL_THREADS, 0, st>>>(level, qin, qout, labels, fdr, rows, cols, towards, flat_mask,
+                                                      fh_read, fh_acc, w.cnt);
+      OFL_CHECK_LAUNCH();
+      ++level;
+      int* t = qin;
+      qin = qout;
+      qout = t;
+    }
+    OFL_CUDA(cudaMemcpyAsync(h_cnt, w.cnt + CNT_FRONT0 + level % 3, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    OFL_CUDA(cudaStreamSynchronize(st));
+    if (*h_cnt == 0) break;
+    OFL_REQUIRE(level < INT_MAX / 4, OFL_ERR_INVALID, "flat gradient did not terminate");
+    if (batch < 64) batch *= 2;
+  }
+  if (levels_out) *levels_out = level;
+  return OFL_OK;
+}
+
+}  // namespace
+
+size_t flats_workspace_bytes(int64_t rows, int64_t cols) {
+  const int64_t n = rows * cols;
+  return 3 * flats_align((size_t)n * sizeof(int)) + flats_align((size_t)n) + flats_align(CNT_SLOTS * sizeof(unsigned));
+}
+
+static int check_shape(int64_t rows, int64_t cols) {
+  OFL_REQUIRE(rows > 0 && cols > 0 && rows * cols < (int64_t)INT_MAX, OFL_ERR_INVALID,
+              "flat resolution works on one tile of fewer than 2^31 cells (got %lld x %lld)", (long long)rows,
+              (long long)cols);
+  return OFL_OK;
+}
+
+// edges[i]: bit 0 low edge, bit 1 high edge; counts -> host.  Dense rasters (ld == cols), device pointers.
+int launch_flat_edges(const float* dem, const uint8_t* fdr, int64_t rows, int64_t cols, uint8_t* edges, int64_t* n_low,
+                      int64_t* n_high, unsigned* cnt_dev, cudaStream_t st) {
+  int rc = check_shape(rows, cols);
+  if (rc != OFL_OK) return rc;
+  const int64_t n = rows * cols;
+  PhaseScope ps(PHASE_FLATS, st);
+  OFL_CUDA(cudaMemsetAsync(cnt_dev, 0, CNT_SLOTS * sizeof(unsigned), st));
+  flat_edges_kernel<<<blocks_for(n, FL_THREADS), FL_THREADS, 0, st>>>(dem, fdr, (int)rows, (int)cols, edges, nullptr,
+                                                                      nullptr, cnt_dev);
+  OFL_CHECK_LAUNCH();
+  unsigned* h = nullptr;
+  rc = pinned_get(64, reinterpret_cast<void**>(&h));
+  if (rc != OFL_OK) return rc;
+  OFL_CUDA(cudaMemcpyAsync(h, cnt_dev, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  OFL_CUDA(cudaStreamSynchronize(st));
+  if (n_low) *n_low = h[CNT_LOW];
+  if (n_high) *n_high = h[CNT_HIGH];
+  return OFL_OK;
+}
+
+// resolve_flats (fix_flats.py:227-288).  All pointers device, dense.  info (host, nullable) receives
+// {low edges, high edges, labels, levels of the away sweep, levels of the towards sweep}.
+int launch_resolve_flats(const float* dem, const uint8_t* fdr, int64_t rows, int64_t cols, int* flat_mask, int* labels,
+                         int64_t* info, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  int rc = check_shape(rows, cols);
+  if (rc != OFL_OK) return rc;
+  const int64_t n = rows * cols;
+  FlatsWork w;
+  rc = carve(workspace, workspace_bytes, n, &w);
+  if (rc != OFL_OK) return rc;
+  PhaseScope ps(PHASE_FLATS, st);
+  const unsigned nb = blocks_for(n, FL_THREADS), nbs = blocks_for(n, FL_SCAN_THREADS);
+  OFL_CUDA(cudaMemsetAsync(w.cnt, 0, CNT_SLOTS * sizeof(unsigned), st));
+  // `labels` holds the per-component smallest-low-edge slots until the labels are known
+  flat_edges_kernel<<<nb, FL_THREADS, 0, st>>>(dem, fdr, (int)rows, (int)cols, w.edges, w.parent, labels, w.cnt);
+  OFL_CHECK_LAUNCH();
+  flat_merge_kernel<<<nb, FL_THREADS, 0, st>>>(dem, (int)rows, (int)cols, w.parent);
+  OFL_CHECK_LAUNCH();
+  flat_flatten_kernel<<<nb, FL_THREADS, 0, st>>>(n, w.parent, w.edges, labels);
+  OFL_CHECK_LAUNCH();
+  flat_seed_count_kernel<<<nbs, FL_SCAN_THREADS, 0, st>>>(n, w.parent, w.edges, labels, w.q0);
+  OFL_CHECK_LAUNCH();
+  flat_seed_scan_kernel<<<1, FL_SCAN_THREADS, 0, st>>>((int)nbs, w.q0, w.cnt);
+  OFL_CHECK_LAUNCH();
+  flat_seed_rank_kernel<<<nbs, FL_SCAN_THREADS, 0, st>>>(n, w.parent, w.edges, labels, w.q0, flat_mask);
+  OFL_CHECK_LAUNCH();
+  flat_root_label_kernel<<<nb, FL_THREADS, 0, st>>>(n, w.parent, labels, flat_mask);
+  OFL_CHECK_LAUNCH();
+  flat_spread_label_kernel<<<nb, FL_THREADS, 0, st>>>(n, w.parent, labels, flat_mask);
+  OFL_CHECK_LAUNCH();
+  // flat_height lives where the forest was (label count <= cell count)
+  int* flat_height = w.parent;
+  OFL_CUDA(cudaMemsetAsync(flat_height, 0, (size_t)n * sizeof(int), st));
+  int64_t lv_away = 0, lv_low = 0;
+  flat_collect_kernel<<<nb, FL_THREADS, 0, st>>>(n, w.edges, 2, labels, w.q1, w.cnt);
+  OFL_CHECK_LAUNCH();
+  rc = run_gradient((int)rows, (int)cols, labels, fdr, 0, flat_mask, flat_height, flat_height, w, &lv_away, st);
+  if (rc != OFL_OK) return rc;
+  OFL_CUDA(cudaMemsetAsync(w.cnt + CNT_SEEDS, 0, sizeof(unsigned), st));
+  flat_collect_kernel<<<nb, FL_THREADS, 0, st>>>(n, w.edges, 1, labels, w.q1, w.cnt);
+  OFL_CHECK_LAUNCH();
+  rc = run_gradient((int)rows, (int)cols, labels, fdr, 1, flat_mask, flat_height, flat_height, w, &lv_low, st);
+  if (rc != OFL_OK) return rc;
+  if (info) {
+    unsigned* h = nullptr;
+    rc = pinned_get(64, reinterpret_cast<void**>(&h));
+    if (rc != OFL_OK) return rc;
+    OFL_CUDA(cudaMemcpyAsync(h, w.cnt, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    OFL_CUDA(cudaStreamSynchronize(st));
+    info[0] = h[CNT_LOW];
+    info[1] = h[CNT_HIGH];
+    info[2] = h[CNT_LABELS];
+    info[3] = lv_away;
+    info[4] = lv_low;
+  }
+  return OFL_OK;
+}
+
+// Standalone away_from_higher (towards == 0) / towards_lower (towards == 1) from a caller-supplied seed list
+// (cell indices, device).  flat_height has n_heights entries (device).
+int launch_flat_gradient(const int* labels, const uint8_t* fdr, int64_t rows, int64_t cols, const int* seeds,
+                         int64_t n_seeds, int towards, int* flat_mask, int* flat_height, int64_t n_heights,
+                         void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  int rc = check_shape(rows, cols);
+  if (rc != OFL_OK) return rc;
+  const int64_t n = rows * cols;
+  OFL_REQUIRE(n_seeds >= 0 && n_seeds <= n && n_heights >= 0 && n_heights <= n, OFL_ERR_INVALID,
+              "seed / flat_height count out of range");
+  FlatsWork w;
+  rc = carve(workspace, workspace_bytes, n, &w);
+  if (rc != OFL_OK) return rc;
+  PhaseScope ps(PHASE_FLATS, st);
+  OFL_CUDA(cudaMemsetAsync(w.cnt, 0, CNT_SLOTS * sizeof(unsigned), st));
+  const unsigned ns = (unsigned)n_seeds;
+  OFL_CUDA(cudaMemcpyAsync(w.cnt + CNT_SEEDS, &ns, sizeof(unsigned), cudaMemcpyHostToDevice, st));
+  OFL_CUDA(cudaStreamSynchronize(st));  // `ns` is a stack variable
+  if (n_seeds) OFL_CUDA(cudaMemcpyAsync(w.q1, seeds, (size_t)n_seeds * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  int* acc = w.parent;  // the sweep's own maxima; merged below so untouched labels keep the caller's value
+  OFL_CUDA(cudaMemsetAsync(acc, 0, (size_t)n * sizeof(int), st));
+  rc = run_gradient((int)rows, (int)cols, labels, fdr, towards, flat_mask, flat_height, acc, w, nullptr, st);
+  if (rc != OFL_OK) return rc;
+  if (!towards && n_heights) {
+    flat_height_merge_kernel<<<blocks_for(n_heights, FL_THREADS), FL_THREADS, 0, st>>>((int)n_heights, acc, flat_height);
+    OFL_CHECK_LAUNCH();
+  }
+  return OFL_OK;
+}
+
+int launch_masked_flow_dirs(const int* flat_mask, const int* labels, uint8_t* fdr, int64_t rows, int64_t cols,
+                            cudaStream_t st) {
+  int rc = check_shape(rows, cols);
+  if (rc != OFL_OK) return rc;
+  PhaseScope ps(PHASE_FLATS, st);
+  flat_masked_dirs_kernel<<<blocks_for(rows * cols, FL_THREADS), FL_THREADS, 0, st>>>(flat_mask, labels, fdr, (int)rows,
+                                                                                        (int)cols);
+  OFL_CHECK_LAUNCH();
+  return OFL_OK;
+}
+
+}  // namespace ofl

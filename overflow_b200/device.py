@@ -131,3 +131,56 @@ def check_accumulation(fdr: torch.Tensor, fac: torch.Tensor) -> int:
         )
     )
     return int(n_bad.value)
+
+
+def flats_workspace(rows, cols, device="cuda") -> torch.Tensor:
+    n = int(_native.lib().ofl_flats_workspace_bytes(rows, cols))
+    return torch.empty((max(n, 256),), dtype=torch.uint8, device=device)
+
+
+def _flats_args(dem, fdr):
+    if dem.dtype != torch.float32 or dem.dim() != 2 or not dem.is_contiguous():
+        raise ValueError("dem must be a contiguous 2-D float32 tensor")
+    if fdr.dtype != torch.uint8 or fdr.shape != dem.shape or not fdr.is_contiguous():
+        raise ValueError("fdr must be a contiguous uint8 tensor of the DEM's shape")
+    _init_for(dem)
+
+
+def resolve_flats(dem: torch.Tensor, fdr: torch.Tensor, *, workspace=None):
+    """(flat_mask int32, labels int32, info) of a float32 CUDA DEM and its uint8 codes (ofl_resolve_flats_f32).
+    info = [low edges, high edges, labels, away levels, towards levels].  Synchronises the stream."""
+    _flats_args(dem, fdr)
+    rows, cols = dem.shape
+    flat_mask = torch.empty((rows, cols), dtype=torch.int32, device=dem.device)
+    labels = torch.empty((rows, cols), dtype=torch.int32, device=dem.device)
+    if workspace is None:
+        workspace = flats_workspace(rows, cols, dem.device)
+    info = (ctypes.c_int64 * 5)()
+    _native.check(
+        _native.lib().ofl_resolve_flats_f32(
+            dem.data_ptr(), fdr.data_ptr(), rows, cols, flat_mask.data_ptr(), labels.data_ptr(), info,
+            workspace.data_ptr(), workspace.numel(), _native.OFL_MEM_DEVICE, _stream(),
+        )
+    )
+    return flat_mask, labels, [int(v) for v in info]
+
+
+def fix_flats(dem: torch.Tensor, fdr: torch.Tensor, *, workspace=None, flat_mask=None, labels=None):
+    """Rewrite the code-8 cells of `fdr` in place (resolve_flats + d8_masked_flow_dirs, ofl_fix_flats_f32).
+    Returns (fdr, info).  Synchronises the stream."""
+    _flats_args(dem, fdr)
+    rows, cols = dem.shape
+    if flat_mask is None:
+        flat_mask = torch.empty((rows, cols), dtype=torch.int32, device=dem.device)
+    if labels is None:
+        labels = torch.empty((rows, cols), dtype=torch.int32, device=dem.device)
+    if workspace is None:
+        workspace = flats_workspace(rows, cols, dem.device)
+    info = (ctypes.c_int64 * 5)()
+    _native.check(
+        _native.lib().ofl_fix_flats_f32(
+            dem.data_ptr(), fdr.data_ptr(), rows, cols, flat_mask.data_ptr(), labels.data_ptr(), info,
+            workspace.data_ptr(), workspace.numel(), _native.OFL_MEM_DEVICE, _stream(),
+        )
+    )
+    return fdr, [int(v) for v in info]

@@ -1,0 +1,89 @@
+"""Time flat resolution (ofl_fix_flats_f32, device buffers) on synthetic DEMs and compare a window with the oracle.
+
+    python scripts/bench_flats.py [--size 8192] [--kind 1] [--relief 200] [--steps 3] [--oracle-window 1024]
+
+kind 0 fractal (few, small flats), kind 1 terraces (flat-heavy), kind 2 tilted plane (none).
+Prints one JSON line per run: ms per call (CUDA events on the launching stream), Gcells/s, the algorithmic
+GB/s at 14 B/cell (DEM 4 + codes 1 read; codes 1 + flat_mask 4 + labels 4 written) against the measured HBM
+peak, the sweep depths, and the CPU oracle's time on a window of the same DEM.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from overflow_b200 import _native, device as dev  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--size", type=int, default=8192)
+    ap.add_argument("--kind", type=int, default=1)
+    ap.add_argument("--relief", type=float, default=200.0)
+    ap.add_argument("--holes", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--oracle-window", type=int, default=1024)
+    a = ap.parse_args()
+    n = a.size
+    peak = 6551.4
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    _native.init(0)
+    dem = dev.synth_dem(n, n, seed=3, kind=a.kind, relief=a.relief, holes_permille=a.holes)
+    fdr0 = dev.flow_direction(dem, -9999.0).contiguous()
+    work = dev.flats_workspace(n, n)
+    flat_mask = torch.empty((n, n), dtype=torch.int32, device="cuda")
+    labels = torch.empty((n, n), dtype=torch.int32, device="cuda")
+    fdr = fdr0.clone()
+    times = []
+    info = None
+    _native.phase_timing_enable(True)
+    for it in range(a.steps + 1):
+        fdr.copy_(fdr0)
+        torch.cuda.synchronize()
+        _native.launch_count_reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _, info = dev.fix_flats(dem, fdr, workspace=work, flat_mask=flat_mask, labels=labels)
+        e1.record()
+        torch.cuda.synchronize()
+        if it:
+            times.append(e0.elapsed_time(e1))
+    launches = _native.launch_count()
+    ms = float(np.median(times))
+    cells = n * n
+    out = {
+        "what": "ofl_fix_flats_f32 (resolve_flats + d8_masked_flow_dirs), device buffers",
+        "size": n, "kind": a.kind, "relief": a.relief, "ms": ms, "gcells_s": cells / ms / 1e6,
+        "algorithmic_gbs_14B": cells * 14 / ms / 1e6, "frac_of_hbm_peak": cells * 14 / ms / 1e6 / peak, "peak_gbs": peak,
+        "undefined_before": int((fdr0 == 8).sum()), "undefined_after": int((fdr == 8).sum()),
+        "low_edges": info[0], "high_edges": info[1], "labels": info[2], "away_levels": info[3],
+        "towards_levels": info[4], "launches_per_call": launches,
+    }
+    w = min(a.oracle_window, n)
+    if w:
+        import oracle
+
+        hd, hf = dem[:w, :w].contiguous().cpu().numpy(), fdr0[:w, :w].contiguous().cpu().numpy()
+        t0 = time.perf_counter()
+        m, l = oracle.resolve_flats(hd, hf)
+        want = oracle.d8_masked_flow_dirs(m, hf, l)
+        t1 = time.perf_counter()
+        got = dev.fix_flats(torch.from_numpy(hd).cuda(), torch.from_numpy(hf).cuda())[0].cpu().numpy()
+        out["oracle_window"] = w
+        out["oracle_window_match"] = bool(np.array_equal(got, want))
+        out["cpu_oracle_gcells_s"] = w * w / (t1 - t0) / 1e9
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

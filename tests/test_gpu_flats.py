@@ -1,0 +1,212 @@
+"""GPU parity: flat resolution (csrc/flats.cu) through the C ABI vs fixtures produced by the reference's
+fix_flats.py and vs the C oracle.  The first block reads like the reference's tests/test_fix_flats.py."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import synth
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+Z = load_golden("fix_flats.npz")
+NAMES = sorted({k.split("__")[0] for k in Z.files})
+U = 8
+
+
+def ff():
+    from overflow import fix_flats
+
+    return fix_flats
+
+
+def edges_of(shape, high, low):
+    e = np.zeros(shape, dtype=np.uint8)
+    for r, c in low:
+        e[r, c] |= 1
+    for r, c in high:
+        e[r, c] |= 2
+    return e
+
+
+# ---- the reference's own tests (tests/test_fix_flats.py:195-372), same calls, same expectations
+EXPECTED_HIGH = [(1, 1), (1, 2), (1, 3), (1, 4), (1, 5), (2, 1), (3, 1), (4, 1), (2, 5), (3, 5), (4, 5), (5, 5), (5, 4)]
+EXPECTED_LOW = [(5, 1), (5, 2), (5, 3)]
+AWAY_MASK = np.array(
+    [
+        [0, 0, 0, 0, 0, 0, 0],
+        [0, 1, 1, 1, 1, 1, 0],
+        [0, 1, 2, 2, 2, 1, 0],
+        [0, 1, 2, 3, 2, 1, 0],
+        [0, 1, 2, 2, 2, 1, 0],
+        [0, 0, 0, 0, 1, 1, 0],
+        [0, 0, 0, 0, 0, 0, 0],
+    ],
+    np.int32,
+)
+
+
+def test_ref_flat_edges():
+    high, low = ff().flat_edges(Z["kat__dem"], Z["kat__fdr"])
+    assert sorted(high) == sorted(EXPECTED_HIGH)
+    assert sorted(low) == sorted(EXPECTED_LOW)
+
+
+def test_ref_label_flats():
+    labels = np.zeros((7, 7), dtype=np.uint32)
+    ff().label_flats(Z["kat__dem"], labels, 1, 2, 2)
+    assert np.array_equal(labels, Z["kat__labels"].astype(np.uint32))
+
+
+def test_ref_away_from_higher():
+    flat_mask = np.zeros((7, 7), dtype=np.int32)
+    flat_height = np.zeros((1), dtype=np.int32)
+    ff().away_from_higher(Z["kat__labels"].astype(np.uint32), flat_mask, Z["kat__fdr"], list(EXPECTED_HIGH), flat_height)
+    assert flat_height[0] == 3
+    assert np.array_equal(flat_mask, AWAY_MASK)
+
+
+def test_ref_towards_lower():
+    flat_mask = AWAY_MASK.copy()
+    flat_height = np.array([3], dtype=np.int32)
+    ff().towards_lower(Z["kat__labels"].astype(np.uint32), flat_mask, Z["kat__fdr"], list(EXPECTED_LOW), flat_height)
+    assert np.array_equal(flat_mask, Z["kat__flat_mask"])
+
+
+def test_ref_resolve_flats():
+    flat_mask, labels = ff().resolve_flats(Z["kat__dem"], Z["kat__fdr"])
+    assert flat_mask.dtype == np.int32 and labels.dtype == np.int32
+    assert np.array_equal(flat_mask, Z["kat__flat_mask"])
+    assert np.array_equal(labels, Z["kat__labels"])
+
+
+def test_ref_d8_masked_flow_dirs():
+    test_fdr = Z["kat__fdr"].copy()
+    ff().d8_masked_flow_dirs(Z["kat__flat_mask"].astype(np.uint32), test_fdr, Z["kat__labels"].astype(np.uint32))
+    assert np.array_equal(test_fdr, Z["kat__fdr_fixed"])
+
+
+# ---- every fixture the reference produced
+@pytest.mark.parametrize("name", NAMES)
+def test_golden_flat_edges(name):
+    high, low = ff().flat_edges(Z[f"{name}__dem"], Z[f"{name}__fdr"])
+    assert np.array_equal(edges_of(Z[f"{name}__dem"].shape, high, low), Z[f"{name}__edges"])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_golden_resolve_flats(name):
+    flat_mask, labels = ff().resolve_flats(Z[f"{name}__dem"], Z[f"{name}__fdr"])
+    assert np.array_equal(labels, Z[f"{name}__labels"])
+    assert np.array_equal(flat_mask, Z[f"{name}__flat_mask"])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_golden_masked_dirs(name):
+    fdr = Z[f"{name}__fdr"].copy()
+    ff().d8_masked_flow_dirs(Z[f"{name}__flat_mask"], fdr, Z[f"{name}__labels"])
+    assert np.array_equal(fdr, Z[f"{name}__fdr_fixed"])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_golden_fix_flats_one_call(name):
+    fixed, flat_mask, labels = ff().fix_flats_for_tile(Z[f"{name}__dem"], Z[f"{name}__fdr"], return_mask=True)
+    assert np.array_equal(fixed, Z[f"{name}__fdr_fixed"])
+    assert np.array_equal(flat_mask, Z[f"{name}__flat_mask"]) and np.array_equal(labels, Z[f"{name}__labels"])
+
+
+@pytest.mark.parametrize("name", ["terraced_0", "blocks", "inconsistent_2", "special"])
+def test_golden_sweeps_on_their_own(name):
+    """away_from_higher / towards_lower from the reference's edge lists reproduce the reference's mask."""
+    dem, fdr, labels = Z[f"{name}__dem"], Z[f"{name}__fdr"], Z[f"{name}__labels"]
+    e = Z[f"{name}__edges"]
+    high = [(int(r), int(c)) for r, c in zip(*np.nonzero(e & 2)) if labels[r, c] != 0]
+    low = [(int(r), int(c)) for r, c in zip(*np.nonzero(e & 1))]
+    flat_mask = np.zeros(dem.shape, dtype=np.int32)
+    flat_height = np.zeros(int(labels.max()) + 1, dtype=np.int32)
+    ff().away_from_higher(labels, flat_mask, fdr, high, flat_height)
+    ff().towards_lower(labels, flat_mask, fdr, low, flat_height)
+    assert np.array_equal(flat_mask, Z[f"{name}__flat_mask"])
+
+
+# ---- larger rasters against the C oracle
+def _cases():
+    yield "terraced_600x800", synth.terraced(600, 800, seed=4, relief=25.0)
+    yield "terraced_coarse", synth.terraced(1100, 700, seed=9, step=4.0, relief=40.0, nodata_frac=0.02)
+    rng = np.random.default_rng(3)
+    yield "ints", rng.integers(0, 4, size=(513, 771)).astype(np.float32)
+    yield "blocks", np.kron(rng.integers(0, 5, size=(40, 50)), np.ones((16, 13))).astype(np.float32)
+    yield "fractal", synth.punch_holes(synth.fractal(900, 900, beta=2.0, seed=0), frac=0.01, seed=1)
+    wide = np.zeros((300, 2500), dtype=np.float32)  # one flat 2500 cells long: deep sweeps, long union-find chains
+    wide[:, 0] = -1.0
+    wide[0, :] = 5.0
+    yield "one_long_flat", wide
+    yield "thin", np.round(synth.fractal(2, 3000, beta=2.0, seed=7) / 100.0).astype(np.float32)
+
+
+@pytest.mark.parametrize("name,dem", list(_cases()), ids=[n for n, _ in _cases()])
+def test_vs_oracle(name, dem):
+    fdr = oracle.flow_direction_for_tile(synth.pad_nodata(dem), synth.NODATA)[1:-1, 1:-1].copy()
+    want_mask, want_labels = oracle.resolve_flats(dem, fdr)
+    want_fixed = oracle.d8_masked_flow_dirs(want_mask, fdr, want_labels)
+    flat_mask, labels, info = ff().resolve_flats(dem, fdr, return_info=True)
+    assert np.array_equal(labels, want_labels)
+    assert np.array_equal(flat_mask, want_mask)
+    assert info["labels"] == int(want_labels.max())
+    fixed = ff().fix_flats_for_tile(dem, fdr)
+    assert np.array_equal(fixed, want_fixed)
+    high, low = ff().flat_edges(dem, fdr)
+    assert (high, low) == oracle.flat_edges(dem, fdr)
+
+
+def test_device_tensors():
+    """Device-resident chain: direction -> fix_flats, checked against the oracle chain."""
+    import torch
+    from overflow_b200 import device as dev
+
+    dem = synth.terraced(1024, 1536, seed=12, relief=30.0)
+    d_dem = torch.from_numpy(dem).cuda()
+    d_fdr = dev.flow_direction(d_dem, synth.NODATA).contiguous()
+    before = d_fdr.cpu().numpy()
+    want_fdr = oracle.flow_direction_for_tile(synth.pad_nodata(dem), synth.NODATA)[1:-1, 1:-1]
+    assert np.array_equal(before, want_fdr)
+    d_fdr, info = dev.fix_flats(d_dem, d_fdr)
+    want_mask, want_labels = oracle.resolve_flats(dem, before)
+    want_fixed = oracle.d8_masked_flow_dirs(want_mask, before, want_labels)
+    fixed = d_fdr.cpu().numpy()
+    assert np.array_equal(fixed, want_fixed)
+    assert info[2] == int(want_labels.max()) and (fixed == U).sum() < (before == U).sum()
+
+
+def test_routing_through_resolved_flats():
+    """direction -> fix_flats -> accumulation on the device.  A stepped plane has only drainable flats, so the
+    rewritten codes are acyclic and the counts must satisfy the accumulation recurrence exactly.  (On DEMs with
+    pits the reference's d8_masked_flow_dirs points a pit at its first label-0 neighbour, which can close a
+    2-cycle; the reference breaches pits before this step.)"""
+    import torch
+    from overflow_b200 import device as dev
+
+    rows, cols = 768, 1280
+    r = np.arange(rows, dtype=np.float64)[:, None]
+    c = np.arange(cols, dtype=np.float64)[None, :]
+    dem = np.floor((rows - 1 - r) * 0.07 + c * 0.03).astype(np.float32)
+    d_dem = torch.from_numpy(dem).cuda()
+    d_fdr = dev.flow_direction(d_dem, synth.NODATA).contiguous()
+    before = d_fdr.cpu().numpy()
+    assert (before == U).sum() > rows * cols // 2
+    d_fdr, info = dev.fix_flats(d_dem, d_fdr)
+    fixed = d_fdr.cpu().numpy()
+    want_mask, want_labels = oracle.resolve_flats(dem, before)
+    assert np.array_equal(fixed, oracle.d8_masked_flow_dirs(want_mask, before, want_labels))
+    assert (fixed == U).sum() == 0
+    fac = dev.flow_accumulation(d_fdr)
+    assert dev.check_accumulation(d_fdr, fac) == 0
+    assert np.array_equal(fac.cpu().numpy(), oracle.flow_accumulation(fixed))
+
+
+def test_rejects_inexact_dtypes_and_sizes():
+    with pytest.raises(TypeError):
+        ff().resolve_flats(np.array([[1e-50, 2.0]], dtype=np.float64), np.array([[8, 8]], dtype=np.uint8))
+    fm, lb = ff().resolve_flats(np.array([[1, 1], [1, 0]], dtype=np.int16), np.array([[8, 8], [8, 7]], dtype=np.uint8))
+    assert fm.shape == (2, 2) and lb.dtype == np.int32
+    fm, lb = ff().resolve_flats(np.zeros((0, 5), dtype=np.float32), np.zeros((0, 5), dtype=np.uint8))
+    assert fm.shape == (0, 5)
