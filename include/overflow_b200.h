@@ -104,9 +104,10 @@ void ofl_launch_count_reset(void);
  * totals and copies up to n totals (milliseconds) and launch counts out; returns the number of phases:
  *   0 direction kernel   1 accumulation tile pass A   2 perimeter-graph solve
  *   3 accumulation tile pass B   4 perimeter links   5 strip mode: pass B on the strip's first/last tile row
- *   6 flat resolution (ofl_flat_edges_f32 ... ofl_fix_flats_f32)
+ *   6 flat resolution: the edge / masked-direction stencils   7 flat labelling (edges, components, label order)
+ *   8 the two gradient sweeps of flat resolution
  */
-#define OFL_PHASE_COUNT 7
+#define OFL_PHASE_COUNT 9
 void ofl_phase_timing_enable(int on);
 int ofl_phase_timing_read(double* ms, int64_t* counts, int n, int reset);
 

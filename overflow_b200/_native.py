@@ -113,7 +113,7 @@ def launch_count_reset():
     lib().ofl_launch_count_reset()
 
 
-PHASES = ("direction", "acc_tile_a", "acc_solve", "acc_tile_b", "acc_links", "strip_edge", "fix_flats")
+PHASES = ("direction", "acc_tile_a", "acc_solve", "acc_tile_b", "acc_links", "strip_edge", "flats_stencils", "flats_label", "flats_sweeps")
 
 
 def phase_timing_enable(on=True):

@@ -286,7 +286,9 @@ flat_seed_level_kernel(const int* __restrict__ seeds, const int* __restrict__ la
   }
 }
 
-// level L -> L+1: neighbours with the same label and no direction (:155-161 / :215-224)
+// level L -> L+1: neighbours with the same label and no direction (:155-161 / :215-224).  Eight lanes share a
+// frontier cell, one neighbour each: a level is one load-compare-claim deep instead of eight (small frontiers
+// are latency bound), and a warp's appends still cost one queue atomic.
 __global__ void __launch_bounds__(FL_THREADS)
 flat_level_kernel(int level, const int* __restrict__ qin, int* qout, const int* __restrict__ labels,
                   const uint8_t* __restrict__ fdr, int rows, int cols, int towards, int* flat_mask, const int* fh_read,
@@ -294,30 +296,28 @@ flat_level_kernel(int level, const int* __restrict__ qin, int* qout, const int* 
   const unsigned n_in = cnt[CNT_FRONT0 + level % 3];
   unsigned* cnt_out = &cnt[CNT_FRONT0 + (level + 1) % 3];
   if (blockIdx.x == 0 && threadIdx.x == 0) cnt[CNT_FRONT0 + (level + 2) % 3] = 0;
-  const unsigned stride = gridDim.x * FL_THREADS;
-  for (unsigned base = blockIdx.x * FL_THREADS; base < n_in; base += stride) {
-    const unsigned idx = base + threadIdx.x;
-    const bool live = idx < n_in;
-    int p = 0, lab = 0, r = 0, c = 0;
-    if (live) {
-      p = qin[idx];
-      lab = labels[p];
-      r = p / cols;
-      c = p - r * cols;
-    }
-#pragma unroll 1
-    for (int k = 0; k < 8; ++k) {
-      bool won = false;
-      int q = 0;
-      if (live) {
-        const int nr = r + c_dy[k], nc = c + c_dx[k];
-        if (nr >= 0 && nr < rows && nc >= 0 && nc < cols) {
-          q = nr * cols + nc;
-          if (labels[q] == lab && fdr[q] == FL_UNDEF) won = flat_claim(q, level + 1, towards, lab, flat_mask, fh_read, fh_acc);
+  constexpr unsigned CELLS = FL_THREADS / 8;
+  const unsigned stride = gridDim.x * CELLS;
+  const int k = threadIdx.x & 7;
+  const int dy = c_dy[k], dx = c_dx[k];
+  for (unsigned base = blockIdx.x * CELLS; base < n_in; base += stride) {
+    const unsigned idx = base + (threadIdx.x >> 3);
+    bool won = false;
+    int q = 0;
+    if (idx < n_in) {
+      const int p = qin[idx];
+      const int r = p / cols, c = p - r * cols;
+      const int nr = r + dy, nc = c + dx;
+      if (nr >= 0 && nr < rows && nc >= 0 && nc < cols) {
+        q = nr * cols + nc;
+        // cheapest rejection first: most neighbours already carry their value
+        if (__ldcg(flat_mask + q) <= 0 && fdr[q] == FL_UNDEF) {
+          const int lab = labels[p];
+          if (labels[q] == lab) won = flat_claim(q, level + 1, towards, lab, flat_mask, fh_read, fh_acc);
         }
       }
-      flat_append(won, q, qout, cnt_out);
     }
+    flat_append(won, q, qout, cnt_out);
   }
 }
 
@@ -465,9 +465,11 @@ int launch_resolve_flats(const float* dem, const uint8_t* fdr, int64_t rows, int
   FlatsWork w;
   rc = carve(workspace, workspace_bytes, n, &w);
   if (rc != OFL_OK) return rc;
-  PhaseScope ps(PHASE_FLATS, st);
   const unsigned nb = blocks_for(n, FL_THREADS), nbs = blocks_for(n, FL_SCAN_THREADS);
   OFL_CUDA(cudaMemsetAsync(w.cnt, 0, CNT_SLOTS * sizeof(unsigned), st));
+  int* flat_height = w.parent;  // lives where the forest was once the labels are known (label count <= cell count)
+  {
+  PhaseScope ps(PHASE_FLATS_LABEL, st);
   // `labels` holds the per-component smallest-low-edge slots until the labels are known
   flat_edges_kernel<<<nb, FL_THREADS, 0, st>>>(dem, fdr, (int)rows, (int)cols, w.edges, w.parent, labels, w.cnt);
   OFL_CHECK_LAUNCH();
@@ -485,9 +487,9 @@ int launch_resolve_flats(const float* dem, const uint8_t* fdr, int64_t rows, int
   OFL_CHECK_LAUNCH();
   flat_spread_label_kernel<<<nb, FL_THREADS, 0, st>>>(n, w.parent, labels, flat_mask);
   OFL_CHECK_LAUNCH();
-  // flat_height lives where the forest was (label count <= cell count)
-  int* flat_height = w.parent;
   OFL_CUDA(cudaMemsetAsync(flat_height, 0, (size_t)n * sizeof(int), st));
+  }
+  PhaseScope ps(PHASE_FLATS_SWEEP, st);
   int64_t lv_away = 0, lv_low = 0;
   flat_collect_kernel<<<nb, FL_THREADS, 0, st>>>(n, w.edges, 2, labels, w.q1, w.cnt);
   OFL_CHECK_LAUNCH();

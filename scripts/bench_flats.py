@@ -59,6 +59,7 @@ def main():
         if it:
             times.append(e0.elapsed_time(e1))
     launches = _native.launch_count()
+    phases = {k: v[0] / max(1, a.steps + 1) for k, v in _native.phase_timing_read().items() if k.startswith("flats")}
     ms = float(np.median(times))
     cells = n * n
     out = {
@@ -67,7 +68,7 @@ def main():
         "algorithmic_gbs_14B": cells * 14 / ms / 1e6, "frac_of_hbm_peak": cells * 14 / ms / 1e6 / peak, "peak_gbs": peak,
         "undefined_before": int((fdr0 == 8).sum()), "undefined_after": int((fdr == 8).sum()),
         "low_edges": info[0], "high_edges": info[1], "labels": info[2], "away_levels": info[3],
-        "towards_levels": info[4], "launches_per_call": launches,
+        "towards_levels": info[4], "launches_per_call": launches, "phases_ms": phases,
     }
     w = min(a.oracle_window, n)
     if w:
