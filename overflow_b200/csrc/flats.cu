@@ -40,22 +40,26 @@ __constant__ int c_dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};  // E NE N NW W SW S SE:
 __constant__ int c_dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
 
 // ---------------------------------------------------------------- flat_edges (fix_flats.py:13-62)
-// also initialises the union-find forest (parent = self) and the per-component "smallest low edge" slot
+// Also initialises the union-find forest and the per-component "smallest low edge" slot.  The forest starts with
+// every horizontal run of equal elevation already hanging off its first cell as far as one warp sees it (a ballot
+// and a count-leading-zeros, no atomics), which is most of the linking on a plateau.
 __global__ void __launch_bounds__(FL_THREADS)
 flat_edges_kernel(const float* __restrict__ dem, const uint8_t* __restrict__ fdr, int rows, int cols, uint8_t* edges,
                   int* parent, int* minlow, unsigned* cnt) {
-  const int64_t n = (int64_t)rows * cols;
-  const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
+  const unsigned n = (unsigned)rows * (unsigned)cols;
+  const unsigned i = blockIdx.x * FL_THREADS + threadIdx.x;
   int flag = 0;
+  bool left_eq = false;
   if (i < n) {
-    const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+    const int r = (int)(i / (unsigned)cols), c = (int)(i - (unsigned)r * (unsigned)cols);
     const int cur = fdr[i];
     const float z = dem[i];
+    left_eq = c > 0 && dem[i - 1] == z;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int nr = r + c_dy[k], nc = c + c_dx[k];
       if (nr < 0 || nr >= rows || nc < 0 || nc >= cols) continue;
-      const int64_t j = (int64_t)nr * cols + nc;
+      const unsigned j = (unsigned)nr * (unsigned)cols + (unsigned)nc;
       const int fn = fdr[j];
       if (fn == FL_NODATA) continue;
       const float zn = dem[j];
@@ -69,15 +73,20 @@ flat_edges_kernel(const float* __restrict__ dem, const uint8_t* __restrict__ fdr
       }
     }
     edges[i] = (uint8_t)flag;
-    if (parent) {
-      parent[i] = (int)i;
+  }
+  if (parent) {
+    const int lane = threadIdx.x & 31;
+    const unsigned em = __ballot_sync(0xffffffffu, left_eq);
+    const unsigned starts = (~em & ((2u << lane) - 1u)) | 1u;  // lanes <= mine that begin a run (lane 0 always does)
+    if (i < n) {
+      parent[i] = (int)(i - (unsigned)(lane - (31 - __clz(starts))));
       minlow[i] = FL_BIG;
     }
   }
-  const unsigned lo = __ballot_sync(0xffffffffu, flag == 1), hi = __ballot_sync(0xffffffffu, flag == 2);
-  if ((threadIdx.x & 31) == 0) {
-    if (lo) atomicAdd(&cnt[CNT_LOW], __popc(lo));
-    if (hi) atomicAdd(&cnt[CNT_HIGH], __popc(hi));
+  const int lo = __syncthreads_count(flag == 1), hi = __syncthreads_count(flag == 2);
+  if (threadIdx.x == 0) {
+    if (lo) atomicAdd(&cnt[CNT_LOW], (unsigned)lo);
+    if (hi) atomicAdd(&cnt[CNT_HIGH], (unsigned)hi);
   }
 }
 
@@ -119,20 +128,28 @@ __device__ __forceinline__ void uf_unite(int* p, int a, int b) {
   }
 }
 
+// Unions between runs.  Inside a row only the hand-over between warps is left (lane 31 -> lane 0).  Between rows a
+// vertical pair needs a union only where one of the two runs begins (further right the pair to the left is the same
+// two runs), and a diagonal pair only when neither the cell below nor the cell beside it continues a run that the
+// vertical rule already ties in.
 __global__ void __launch_bounds__(FL_THREADS)
 flat_merge_kernel(const float* __restrict__ dem, int rows, int cols, int* parent) {
-  const int64_t n = (int64_t)rows * cols;
-  const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
+  const unsigned n = (unsigned)rows * (unsigned)cols;
+  const unsigned i = blockIdx.x * FL_THREADS + threadIdx.x;
   if (i >= n) return;
-  const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+  const int r = (int)(i / (unsigned)cols), c = (int)(i - (unsigned)r * (unsigned)cols);
   const float z = dem[i];
-  // the four forward neighbours cover every 8-connected pair once
-  if (c + 1 < cols && dem[i + 1] == z) uf_unite(parent, (int)i, (int)i + 1);
+  const bool left_eq = c > 0 && dem[i - 1] == z;
+  const bool right_eq = c + 1 < cols && dem[i + 1] == z;
+  if (right_eq && (threadIdx.x & 31) == 31) uf_unite(parent, (int)i, (int)i + 1);
   if (r + 1 < rows) {
-    const int64_t j = i + cols;
-    if (c > 0 && dem[j - 1] == z) uf_unite(parent, (int)i, (int)(j - 1));
-    if (dem[j] == z) uf_unite(parent, (int)i, (int)j);
-    if (c + 1 < cols && dem[j + 1] == z) uf_unite(parent, (int)i, (int)(j + 1));
+    const unsigned j = i + (unsigned)cols;
+    if (dem[j] == z) {
+      if (!left_eq || !(dem[j - 1] == z)) uf_unite(parent, (int)i, (int)j);  // c == 0 implies !left_eq
+    } else {
+      if (c > 0 && !left_eq && dem[j - 1] == z) uf_unite(parent, (int)i, (int)(j - 1));
+      if (c + 1 < cols && !right_eq && dem[j + 1] == z) uf_unite(parent, (int)i, (int)(j + 1));
+    }
   }
 }
 
@@ -223,18 +240,30 @@ flat_spread_label_kernel(int64_t n, int* parent, int* labels, int* flat_mask) {
 
 // ---------------------------------------------------------------- gradients (away_from_higher / towards_lower)
 // edge cells -> seed list, in no particular order (the sweeps are order-free)
-__global__ void __launch_bounds__(FL_THREADS)
+__global__ void __launch_bounds__(FL_SCAN_THREADS)
 flat_collect_kernel(int64_t n, const uint8_t* __restrict__ edges, int bit, const int* __restrict__ labels, int* seeds,
                     unsigned* cnt) {
-  const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
+  __shared__ unsigned warp_off[FL_SCAN_THREADS / 32];
+  __shared__ unsigned block_base;
+  const int64_t i = (int64_t)blockIdx.x * FL_SCAN_THREADS + threadIdx.x;
   const bool take = i < n && (edges[i] & bit) && labels[i] != 0;  // fix_flats.py:273-274 (low edges always carry a label)
   const unsigned m = __ballot_sync(0xffffffffu, take);
-  if (m == 0) return;
-  const int lane = threadIdx.x & 31;
-  unsigned base = 0;
-  if (lane == 0) base = atomicAdd(&cnt[CNT_SEEDS], __popc(m));
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (take) seeds[base + __popc(m & ((1u << lane) - 1u))] = (int)i;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) warp_off[w] = __popc(m);
+  __syncthreads();
+  if (w == 0) {  // exclusive scan of the 32 warp totals, one queue atomic for the block
+    const unsigned v = warp_off[lane];
+    unsigned inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, inc, off);
+      if (lane >= off) inc += t;
+    }
+    warp_off[lane] = inc - v;
+    if (lane == 31 && inc) block_base = atomicAdd(&cnt[CNT_SEEDS], inc);
+  }
+  __syncthreads();
+  if (take) seeds[block_base + warp_off[w] + __popc(m & ((1u << lane) - 1u))] = (int)i;
 }
 
 __global__ void __launch_bounds__(FL_THREADS) flat_negate_kernel(int64_t n, int* flat_mask) {  // fix_flats.py:200
@@ -253,27 +282,67 @@ __device__ __forceinline__ bool flat_claim(int p, int level, int towards, int la
   else
     nv = ((fm < 0 && lab > 0) ? fm + fh_read[lab - 1] : 0) + 2 * level;  // :209-214
   if (atomicCAS(flat_mask + p, fm, nv) != fm) return false;
-  if (!towards && lab > 0) atomicMax(fh_acc + lab - 1, level);  // :154
+  // :154 -- every cell of a level carries the same value: one atomic per flat and level gets through
+  if (!towards && lab > 0 && __ldcg(fh_acc + lab - 1) < level) atomicMax(fh_acc + lab - 1, level);
   return true;
 }
 
-__device__ __forceinline__ void flat_append(bool won, int p, int* qout, unsigned* cnt_out) {
+// Frontier appends go through a per-CTA buffer: a warp reserves its slots with one shared-memory atomic, and the
+// CTA moves the buffer to the global queue with one global atomic when it fills up.  (One global atomic per warp
+// was the bottleneck of the sweeps: tens of millions of adds on a single counter.)
+constexpr int FL_QBUF = 2048;
+constexpr int FL_ROUNDS = 4;  // loop rounds between two looks at the fill level: at most FL_ROUNDS * FL_THREADS pushes
+static_assert(FL_QBUF >= 2 * FL_ROUNDS * FL_THREADS, "buffer must hold two batches of rounds");
+
+struct BlockQueue {
+  int buf[FL_QBUF];
+  unsigned n, base;
+};
+
+__device__ __forceinline__ void bq_push(BlockQueue& bq, bool won, int p) {
   const unsigned m = __ballot_sync(0xffffffffu, won);
   if (m == 0) return;
-  const int lane = threadIdx.x & 31;
-  unsigned base = 0;
-  if (lane == __ffs(m) - 1) base = atomicAdd(cnt_out, __popc(m));
-  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-  if (won) qout[base + __popc(m & ((1u << lane) - 1u))] = p;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  unsigned off = 0;
+  if (lane == leader) off = atomicAdd(&bq.n, (unsigned)__popc(m));
+  off = __shfl_sync(0xffffffffu, off, leader);
+  if (won) bq.buf[off + __popc(m & ((1u << lane) - 1u))] = p;
+}
+
+// all threads of the CTA; pushes must not overlap a flush
+__device__ __forceinline__ void bq_flush(BlockQueue& bq, int* qout, unsigned* cnt_out) {
+  __syncthreads();
+  const unsigned n = bq.n;
+  if (n == 0) return;  // uniform: read between two barriers with no push in flight
+  if (threadIdx.x == 0) bq.base = atomicAdd(cnt_out, n);
+  __syncthreads();
+  const unsigned base = bq.base;
+  for (unsigned k = threadIdx.x; k < n; k += FL_THREADS) qout[base + k] = bq.buf[k];
+  __syncthreads();
+  if (threadIdx.x == 0) bq.n = 0;
+  __syncthreads();
+}
+
+// after every FL_ROUNDS rounds: flush when another batch of rounds might not fit
+__device__ __forceinline__ void bq_maybe_flush(BlockQueue& bq, unsigned round, int* qout, unsigned* cnt_out) {
+  if (round % FL_ROUNDS) return;
+  __syncthreads();
+  const bool full = bq.n > FL_QBUF - FL_ROUNDS * FL_THREADS;
+  __syncthreads();
+  if (full) bq_flush(bq, qout, cnt_out);
 }
 
 // level 1: the seed edges themselves (duplicates and already positive cells drop out)
 __global__ void __launch_bounds__(FL_THREADS)
 flat_seed_level_kernel(const int* __restrict__ seeds, const int* __restrict__ labels, int towards, int* flat_mask,
                        const int* fh_read, int* fh_acc, int* qout, unsigned* cnt) {
+  __shared__ BlockQueue bq;
   const unsigned n_seed = cnt[CNT_SEEDS];
   if (blockIdx.x == 0 && threadIdx.x == 0) cnt[CNT_FRONT0 + 2] = 0;
+  if (threadIdx.x == 0) bq.n = 0;
+  __syncthreads();
   const unsigned stride = gridDim.x * FL_THREADS;
+  unsigned round = 0;
   for (unsigned base = blockIdx.x * FL_THREADS; base < n_seed; base += stride) {
     const unsigned idx = base + threadIdx.x;
     bool won = false;
@@ -282,24 +351,30 @@ flat_seed_level_kernel(const int* __restrict__ seeds, const int* __restrict__ la
       p = seeds[idx];
       won = flat_claim(p, 1, towards, labels[p], flat_mask, fh_read, fh_acc);
     }
-    flat_append(won, p, qout, &cnt[CNT_FRONT0 + 1]);
+    bq_push(bq, won, p);
+    bq_maybe_flush(bq, ++round, qout, &cnt[CNT_FRONT0 + 1]);
   }
+  bq_flush(bq, qout, &cnt[CNT_FRONT0 + 1]);
 }
 
 // level L -> L+1: neighbours with the same label and no direction (:155-161 / :215-224).  Eight lanes share a
 // frontier cell, one neighbour each: a level is one load-compare-claim deep instead of eight (small frontiers
-// are latency bound), and a warp's appends still cost one queue atomic.
+// are latency bound).
 __global__ void __launch_bounds__(FL_THREADS)
 flat_level_kernel(int level, const int* __restrict__ qin, int* qout, const int* __restrict__ labels,
                   const uint8_t* __restrict__ fdr, int rows, int cols, int towards, int* flat_mask, const int* fh_read,
                   int* fh_acc, unsigned* cnt) {
+  __shared__ BlockQueue bq;
   const unsigned n_in = cnt[CNT_FRONT0 + level % 3];
   unsigned* cnt_out = &cnt[CNT_FRONT0 + (level + 1) % 3];
   if (blockIdx.x == 0 && threadIdx.x == 0) cnt[CNT_FRONT0 + (level + 2) % 3] = 0;
+  if (threadIdx.x == 0) bq.n = 0;
+  __syncthreads();
   constexpr unsigned CELLS = FL_THREADS / 8;
   const unsigned stride = gridDim.x * CELLS;
   const int k = threadIdx.x & 7;
   const int dy = c_dy[k], dx = c_dx[k];
+  unsigned round = 0;
   for (unsigned base = blockIdx.x * CELLS; base < n_in; base += stride) {
     const unsigned idx = base + (threadIdx.x >> 3);
     bool won = false;
@@ -317,8 +392,10 @@ flat_level_kernel(int level, const int* __restrict__ qin, int* qout, const int* 
         }
       }
     }
-    flat_append(won, q, qout, cnt_out);
+    bq_push(bq, won, q);
+    bq_maybe_flush(bq, ++round, qout, cnt_out);
   }
+  bq_flush(bq, qout, cnt_out);
 }
 
 // flat_height[k] takes the sweep's value where the sweep reached label k+1 (standalone away_from_higher)
@@ -491,12 +568,12 @@ int launch_resolve_flats(const float* dem, const uint8_t* fdr, int64_t rows, int
   }
   PhaseScope ps(PHASE_FLATS_SWEEP, st);
   int64_t lv_away = 0, lv_low = 0;
-  flat_collect_kernel<<<nb, FL_THREADS, 0, st>>>(n, w.edges, 2, labels, w.q1, w.cnt);
+  flat_collect_kernel<<<nbs, FL_SCAN_THREADS, 0, st>>>(n, w.edges, 2, labels, w.q1, w.cnt);
   OFL_CHECK_LAUNCH();
   rc = run_gradient((int)rows, (int)cols, labels, fdr, 0, flat_mask, flat_height, flat_height, w, &lv_away, st);
   if (rc != OFL_OK) return rc;
   OFL_CUDA(cudaMemsetAsync(w.cnt + CNT_SEEDS, 0, sizeof(unsigned), st));
-  flat_collect_kernel<<<nb, FL_THREADS, 0, st>>>(n, w.edges, 1, labels, w.q1, w.cnt);
+  flat_collect_kernel<<<nbs, FL_SCAN_THREADS, 0, st>>>(n, w.edges, 1, labels, w.q1, w.cnt);
   OFL_CHECK_LAUNCH();
   rc = run_gradient((int)rows, (int)cols, labels, fdr, 1, flat_mask, flat_height, flat_height, w, &lv_low, st);
   if (rc != OFL_OK) return rc;
