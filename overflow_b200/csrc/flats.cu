@@ -228,14 +228,23 @@ flat_root_label_kernel(int64_t n, const int* __restrict__ parent, int* labels, c
   labels[i] = (m == FL_BIG) ? 0 : seedlabel[m];
 }
 
-// everyone else copies the root's label; the scratch use of flat_mask and parent ends here
+// everyone else copies the root's label; the scratch use of flat_mask and parent ends here.  open[i] is the sweeps'
+// one-word view of a cell: label + 1 while the cell is a candidate (no direction, no value yet), 0 when it can
+// never be one, -(label + 1) once a sweep has claimed it.
 __global__ void __launch_bounds__(FL_THREADS)
-flat_spread_label_kernel(int64_t n, int* parent, int* labels, int* flat_mask) {
+flat_spread_label_kernel(int64_t n, int* parent, int* labels, int* flat_mask, const uint8_t* __restrict__ fdr, int* open) {
   const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
   if (i >= n) return;
   const int root = parent[i];
-  if (root != (int)i) labels[i] = labels[root];
+  int lab;
+  if (root != (int)i) {
+    lab = labels[root];
+    labels[i] = lab;
+  } else {
+    lab = labels[i];
+  }
   flat_mask[i] = 0;
+  open[i] = (fdr[i] == FL_UNDEF) ? lab + 1 : 0;
 }
 
 // ---------------------------------------------------------------- gradients (away_from_higher / towards_lower)
@@ -266,33 +275,41 @@ flat_collect_kernel(int64_t n, const uint8_t* __restrict__ edges, int bit, const
   if (take) seeds[block_base + warp_off[w] + __popc(m & ((1u << lane) - 1u))] = (int)i;
 }
 
-__global__ void __launch_bounds__(FL_THREADS) flat_negate_kernel(int64_t n, int* flat_mask) {  // fix_flats.py:200
+// start of a sweep: towards_lower negates the mask (fix_flats.py:200); candidates are re-armed from the mask
+__global__ void __launch_bounds__(FL_THREADS)
+flat_prepare_kernel(int64_t n, int towards, int* flat_mask, const int* __restrict__ labels,
+                    const uint8_t* __restrict__ fdr, int* open) {
   const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
-  if (i < n) flat_mask[i] = -flat_mask[i];
+  if (i >= n) return;
+  int fm = flat_mask[i];
+  if (towards) {
+    fm = -fm;
+    flat_mask[i] = fm;
+  }
+  open[i] = (fdr[i] == FL_UNDEF && fm <= 0) ? labels[i] + 1 : 0;
 }
 
-// One try to give cell p its value at `level`; true iff this thread won the cell.
-__device__ __forceinline__ bool flat_claim(int p, int level, int towards, int lab, int* flat_mask, const int* fh_read,
-                                           int* fh_acc) {
-  const int fm = __ldcg(flat_mask + p);
-  if (fm > 0) return false;  // :149 / :207
-  int nv;
-  if (!towards)
-    nv = level;  // :153
-  else
-    nv = ((fm < 0 && lab > 0) ? fm + fh_read[lab - 1] : 0) + 2 * level;  // :209-214
-  if (atomicCAS(flat_mask + p, fm, nv) != fm) return false;
-  // :154 -- every cell of a level carries the same value: one atomic per flat and level gets through
-  if (!towards && lab > 0 && __ldcg(fh_acc + lab - 1) < level) atomicMax(fh_acc + lab - 1, level);
-  return true;
+// The value a cell gets when a sweep reaches it at `level` (:153-154 / :209-214); only the claiming thread calls this.
+__device__ __forceinline__ void flat_assign(int p, int level, int towards, int lab, int* flat_mask, const int* fh_read,
+                                            int* fh_acc) {
+  if (!towards) {
+    flat_mask[p] = level;
+    // every cell of a level carries the same value: one atomic per flat and level gets through
+    if (lab > 0 && __ldcg(fh_acc + lab - 1) < level) atomicMax(fh_acc + lab - 1, level);
+  } else {
+    const int fm = flat_mask[p];
+    flat_mask[p] = ((fm < 0 && lab > 0) ? fm + fh_read[lab - 1] : 0) + 2 * level;
+  }
 }
 
 // Frontier appends go through a per-CTA buffer: a warp reserves its slots with one shared-memory atomic, and the
 // CTA moves the buffer to the global queue with one global atomic when it fills up.  (One global atomic per warp
 // was the bottleneck of the sweeps: tens of millions of adds on a single counter.)
 constexpr int FL_QBUF = 2048;
-constexpr int FL_ROUNDS = 4;  // loop rounds between two looks at the fill level: at most FL_ROUNDS * FL_THREADS pushes
-static_assert(FL_QBUF >= 2 * FL_ROUNDS * FL_THREADS, "buffer must hold two batches of rounds");
+constexpr int FL_ILP = 2;     // pushes per thread and loop round
+constexpr int FL_ROUNDS = 2;  // loop rounds between two looks at the fill level
+constexpr int FL_BATCH = FL_ROUNDS * FL_ILP * FL_THREADS;  // most pushes between two looks
+static_assert(FL_QBUF >= 2 * FL_BATCH, "buffer must hold two batches of rounds");
 
 struct BlockQueue {
   int buf[FL_QBUF];
@@ -327,7 +344,7 @@ __device__ __forceinline__ void bq_flush(BlockQueue& bq, int* qout, unsigned* cn
 __device__ __forceinline__ void bq_maybe_flush(BlockQueue& bq, unsigned round, int* qout, unsigned* cnt_out) {
   if (round % FL_ROUNDS) return;
   __syncthreads();
-  const bool full = bq.n > FL_QBUF - FL_ROUNDS * FL_THREADS;
+  const bool full = bq.n > FL_QBUF - FL_BATCH;
   __syncthreads();
   if (full) bq_flush(bq, qout, cnt_out);
 }
@@ -335,7 +352,7 @@ __device__ __forceinline__ void bq_maybe_flush(BlockQueue& bq, unsigned round, i
 // level 1: the seed edges themselves (duplicates and already positive cells drop out)
 __global__ void __launch_bounds__(FL_THREADS)
 flat_seed_level_kernel(const int* __restrict__ seeds, const int* __restrict__ labels, int towards, int* flat_mask,
-                       const int* fh_read, int* fh_acc, int* qout, unsigned* cnt) {
+                       int* open, const int* fh_read, int* fh_acc, int* qout, unsigned* cnt) {
   __shared__ BlockQueue bq;
   const unsigned n_seed = cnt[CNT_SEEDS];
   if (blockIdx.x == 0 && threadIdx.x == 0) cnt[CNT_FRONT0 + 2] = 0;
@@ -349,7 +366,19 @@ flat_seed_level_kernel(const int* __restrict__ seeds, const int* __restrict__ la
     int p = 0;
     if (idx < n_seed) {
       p = seeds[idx];
-      won = flat_claim(p, 1, towards, labels[p], flat_mask, fh_read, fh_acc);
+      const int lab = labels[p];
+      const int o = __ldcg(open + p);
+      if (o > 0) {  // a candidate cell: claimed like any other
+        won = atomicCAS(open + p, o, -o) == o;
+        if (won) flat_assign(p, 1, towards, lab, flat_mask, fh_read, fh_acc);
+      } else if (o == 0) {  // a cell with a direction (low edges): never a candidate, the mask itself dedupes
+        const int fm = __ldcg(flat_mask + p);
+        if (fm <= 0) {
+          const int nv = towards ? ((fm < 0 && lab > 0) ? fm + fh_read[lab - 1] : 0) + 2 : 1;
+          won = atomicCAS(flat_mask + p, fm, nv) == fm;
+          if (won && !towards && lab > 0) atomicMax(fh_acc + lab - 1, 1);
+        }
+      }
     }
     bq_push(bq, won, p);
     bq_maybe_flush(bq, ++round, qout, &cnt[CNT_FRONT0 + 1]);
@@ -358,12 +387,11 @@ flat_seed_level_kernel(const int* __restrict__ seeds, const int* __restrict__ la
 }
 
 // level L -> L+1: neighbours with the same label and no direction (:155-161 / :215-224).  Eight lanes share a
-// frontier cell, one neighbour each: a level is one load-compare-claim deep instead of eight (small frontiers
-// are latency bound).
+// frontier cell, one neighbour each: a level is one load-compare-claim deep instead of eight (small frontiers are
+// latency bound), and a neighbour costs one scattered word (open[q]) instead of three (mask, code, label).
 __global__ void __launch_bounds__(FL_THREADS)
-flat_level_kernel(int level, const int* __restrict__ qin, int* qout, const int* __restrict__ labels,
-                  const uint8_t* __restrict__ fdr, int rows, int cols, int towards, int* flat_mask, const int* fh_read,
-                  int* fh_acc, unsigned* cnt) {
+flat_level_kernel(int level, const int* __restrict__ qin, int* qout, const int* __restrict__ labels, int rows, int cols,
+                  int towards, int* flat_mask, int* open, const int* fh_read, int* fh_acc, unsigned* cnt) {
   __shared__ BlockQueue bq;
   const unsigned n_in = cnt[CNT_FRONT0 + level % 3];
   unsigned* cnt_out = &cnt[CNT_FRONT0 + (level + 1) % 3];
@@ -371,28 +399,40 @@ flat_level_kernel(int level, const int* __restrict__ qin, int* qout, const int* 
   if (threadIdx.x == 0) bq.n = 0;
   __syncthreads();
   constexpr unsigned CELLS = FL_THREADS / 8;
-  const unsigned stride = gridDim.x * CELLS;
+  const unsigned stride = gridDim.x * CELLS * FL_ILP;
   const int k = threadIdx.x & 7;
   const int dy = c_dy[k], dx = c_dx[k];
   unsigned round = 0;
-  for (unsigned base = blockIdx.x * CELLS; base < n_in; base += stride) {
-    const unsigned idx = base + (threadIdx.x >> 3);
-    bool won = false;
-    int q = 0;
-    if (idx < n_in) {
-      const int p = qin[idx];
+  for (unsigned base = blockIdx.x * CELLS * FL_ILP; base < n_in; base += stride) {
+    // FL_ILP independent (cell, neighbour) pairs per thread: the three dependent loads of each overlap
+    int q[FL_ILP], want[FL_ILP], seen[FL_ILP];
+    bool ok[FL_ILP];
+#pragma unroll
+    for (int u = 0; u < FL_ILP; ++u) {
+      const unsigned idx = base + u * CELLS + (threadIdx.x >> 3);
+      ok[u] = idx < n_in;
+      q[u] = ok[u] ? qin[idx] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < FL_ILP; ++u) {
+      const int p = q[u];
+      want[u] = ok[u] ? labels[p] + 1 : 0;
       const int r = p / cols, c = p - r * cols;
       const int nr = r + dy, nc = c + dx;
-      if (nr >= 0 && nr < rows && nc >= 0 && nc < cols) {
-        q = nr * cols + nc;
-        // cheapest rejection first: most neighbours already carry their value
-        if (__ldcg(flat_mask + q) <= 0 && fdr[q] == FL_UNDEF) {
-          const int lab = labels[p];
-          if (labels[q] == lab) won = flat_claim(q, level + 1, towards, lab, flat_mask, fh_read, fh_acc);
-        }
-      }
+      ok[u] = ok[u] && nr >= 0 && nr < rows && nc >= 0 && nc < cols;
+      q[u] = ok[u] ? nr * cols + nc : 0;
     }
-    bq_push(bq, won, q);
+#pragma unroll
+    for (int u = 0; u < FL_ILP; ++u) seen[u] = ok[u] ? __ldcg(open + q[u]) : 0;
+#pragma unroll
+    for (int u = 0; u < FL_ILP; ++u) {
+      bool won = false;
+      if (ok[u] && seen[u] == want[u] && atomicCAS(open + q[u], want[u], -want[u]) == want[u]) {
+        won = true;
+        flat_assign(q[u], level + 1, towards, want[u] - 1, flat_mask, fh_read, fh_acc);
+      }
+      bq_push(bq, won, q[u]);
+    }
     bq_maybe_flush(bq, ++round, qout, cnt_out);
   }
   bq_flush(bq, qout, cnt_out);
@@ -438,6 +478,7 @@ struct FlatsWork {
   int* parent;  // union-find forest, later flat_height
   int* q0;      // frontier queue / block counts of the label scan
   int* q1;      // seed list / frontier queue
+  int* open;    // the sweeps' candidate words
   uint8_t* edges;
   unsigned* cnt;
 };
@@ -446,29 +487,32 @@ size_t flats_align(size_t v) { return (v + 255) / 256 * 256; }
 
 int carve(void* workspace, size_t workspace_bytes, int64_t n, FlatsWork* w) {
   const size_t a = flats_align((size_t)n * sizeof(int)), e = flats_align((size_t)n), c = flats_align(CNT_SLOTS * sizeof(unsigned));
-  OFL_REQUIRE(workspace_bytes >= 3 * a + e + c, OFL_ERR_WORKSPACE, "flats workspace too small: %zu < %zu", workspace_bytes,
-              3 * a + e + c);
+  OFL_REQUIRE(workspace_bytes >= 4 * a + e + c, OFL_ERR_WORKSPACE, "flats workspace too small: %zu < %zu", workspace_bytes,
+              4 * a + e + c);
   char* p = static_cast<char*>(workspace);
   w->parent = reinterpret_cast<int*>(p);
   w->q0 = reinterpret_cast<int*>(p + a);
   w->q1 = reinterpret_cast<int*>(p + 2 * a);
-  w->edges = reinterpret_cast<uint8_t*>(p + 3 * a);
-  w->cnt = reinterpret_cast<unsigned*>(p + 3 * a + e);
+  w->open = reinterpret_cast<int*>(p + 3 * a);
+  w->edges = reinterpret_cast<uint8_t*>(p + 4 * a);
+  w->cnt = reinterpret_cast<unsigned*>(p + 4 * a + e);
   return OFL_OK;
 }
 
 // One sweep from the seed list in w.q1 (count in cnt[CNT_SEEDS]).  Host-synchronous: the level loop reads the
 // next frontier's size back once per batch of launches.
-int run_gradient(int rows, int cols, const int* labels, const uint8_t* fdr, int towards, int* flat_mask,
+int run_gradient(int rows, int cols, const int* labels, const uint8_t* fdr, int towards, bool open_ready, int* flat_mask,
                  const int* fh_read, int* fh_acc, const FlatsWork& w, int64_t* levels_out, cudaStream_t st) {
+  // open_ready: w.open already describes the candidates (fresh from the labelling, mask all zero)
   const int64_t n = (int64_t)rows * cols;
   OFL_CUDA(cudaMemsetAsync(w.cnt + CNT_FRONT0, 0, 3 * sizeof(unsigned), st));
-  if (towards) {
-    flat_negate_kernel<<<blocks_for(n, FL_THREADS), FL_THREADS, 0, st>>>(n, flat_mask);
+  if (!open_ready) {
+    flat_prepare_kernel<<<blocks_for(n, FL_THREADS), FL_THREADS, 0, st>>>(n, towards, flat_mask, labels, fdr, w.open);
     OFL_CHECK_LAUNCH();
   }
-  const unsigned grid = (unsigned)(sm_count() * 4);
-  flat_seed_level_kernel<<<grid, FL_THREADS, 0, st>>>(w.q1, labels, towards, flat_mask, fh_read, fh_acc, w.q0, w.cnt);
+  const unsigned grid = (unsigned)(sm_count() * 8);  // 8 CTAs of 256 threads fill an SM
+  flat_seed_level_kernel<<<grid, FL_THREADS, 0, st>>>(w.q1, labels, towards, flat_mask, w.open, fh_read, fh_acc, w.q0,
+                                                       w.cnt);
   OFL_CHECK_LAUNCH();
   unsigned* h_cnt = nullptr;
   int rc = pinned_get(64, reinterpret_cast<void**>(&h_cnt));
@@ -479,7 +523,7 @@ int run_gradient(int rows, int cols, const int* labels, const uint8_t* fdr, int 
   int batch = 8;
   for (;;) {
     for (int b = 0; b < batch; ++b) {
-      flat_level_kernel<<<grid, FL_THREADS, 0, st>>>(level, qin, qout, labels, fdr, rows, cols, towards, flat_mask,
+      flat_level_kernel<<<grid, FL_THREADS, 0, st>>>(level, qin, qout, labels, rows, cols, towards, flat_mask, w.open,
                                                       fh_read, fh_acc, w.cnt);
       OFL_CHECK_LAUNCH();
       ++level;
@@ -501,7 +545,7 @@ int run_gradient(int rows, int cols, const int* labels, const uint8_t* fdr, int 
 
 size_t flats_workspace_bytes(int64_t rows, int64_t cols) {
   const int64_t n = rows * cols;
-  return 3 * flats_align((size_t)n * sizeof(int)) + flats_align((size_t)n) + flats_align(CNT_SLOTS * sizeof(unsigned));
+  return 4 * flats_align((size_t)n * sizeof(int)) + flats_align((size_t)n) + flats_align(CNT_SLOTS * sizeof(unsigned));
 }
 
 static int check_shape(int64_t rows, int64_t cols) {
@@ -562,7 +606,7 @@ int launch_resolve_flats(const float* dem, const uint8_t* fdr, int64_t rows, int
   OFL_CHECK_LAUNCH();
   flat_root_label_kernel<<<nb, FL_THREADS, 0, st>>>(n, w.parent, labels, flat_mask);
   OFL_CHECK_LAUNCH();
-  flat_spread_label_kernel<<<nb, FL_THREADS, 0, st>>>(n, w.parent, labels, flat_mask);
+  flat_spread_label_kernel<<<nb, FL_THREADS, 0, st>>>(n, w.parent, labels, flat_mask, fdr, w.open);
   OFL_CHECK_LAUNCH();
   OFL_CUDA(cudaMemsetAsync(flat_height, 0, (size_t)n * sizeof(int), st));
   }
@@ -570,12 +614,12 @@ int launch_resolve_flats(const float* dem, const uint8_t* fdr, int64_t rows, int
   int64_t lv_away = 0, lv_low = 0;
   flat_collect_kernel<<<nbs, FL_SCAN_THREADS, 0, st>>>(n, w.edges, 2, labels, w.q1, w.cnt);
   OFL_CHECK_LAUNCH();
-  rc = run_gradient((int)rows, (int)cols, labels, fdr, 0, flat_mask, flat_height, flat_height, w, &lv_away, st);
+  rc = run_gradient((int)rows, (int)cols, labels, fdr, 0, true, flat_mask, flat_height, flat_height, w, &lv_away, st);
   if (rc != OFL_OK) return rc;
   OFL_CUDA(cudaMemsetAsync(w.cnt + CNT_SEEDS, 0, sizeof(unsigned), st));
   flat_collect_kernel<<<nbs, FL_SCAN_THREADS, 0, st>>>(n, w.edges, 1, labels, w.q1, w.cnt);
   OFL_CHECK_LAUNCH();
-  rc = run_gradient((int)rows, (int)cols, labels, fdr, 1, flat_mask, flat_height, flat_height, w, &lv_low, st);
+  rc = run_gradient((int)rows, (int)cols, labels, fdr, 1, false, flat_mask, flat_height, flat_height, w, &lv_low, st);
   if (rc != OFL_OK) return rc;
   if (info) {
     unsigned* h = nullptr;
@@ -613,7 +657,7 @@ int launch_flat_gradient(const int* labels, const uint8_t* fdr, int64_t rows, in
   if (n_seeds) OFL_CUDA(cudaMemcpyAsync(w.q1, seeds, (size_t)n_seeds * sizeof(int), cudaMemcpyDeviceToDevice, st));
   int* acc = w.parent;  // the sweep's own maxima; merged below so untouched labels keep the caller's value
   OFL_CUDA(cudaMemsetAsync(acc, 0, (size_t)n * sizeof(int), st));
-  rc = run_gradient((int)rows, (int)cols, labels, fdr, towards, flat_mask, flat_height, acc, w, nullptr, st);
+  rc = run_gradient((int)rows, (int)cols, labels, fdr, towards, false, flat_mask, flat_height, acc, w, nullptr, st);
   if (rc != OFL_OK) return rc;
   if (!towards && n_heights) {
     flat_height_merge_kernel<<<blocks_for(n_heights, FL_THREADS), FL_THREADS, 0, st>>>((int)n_heights, acc, flat_height);
