@@ -45,3 +45,6 @@ def test_native_arm_line():
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] == 2048 * 2048 * 4 and e["d2h_bytes_per_step"] == 2048 * 2048 * 9 and e["value"] > 0
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    ff = d["next_rows"]["fix_flats"]
+    assert ff["parity"]["codes_equal_oracle"] and ff["value"] > 0 and ff["left_without_direction"] < ff["cells_without_direction"]
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(ff["cpu_baseline"])
