@@ -153,30 +153,83 @@ flat_merge_kernel(const float* __restrict__ dem, int rows, int cols, int* parent
   }
 }
 
-// parent[i] = root; low edges post their index to the root's slot
-__global__ void __launch_bounds__(FL_THREADS)
-flat_flatten_kernel(int64_t n, int* parent, const uint8_t* __restrict__ edges, int* minlow) {
-  const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
-  if (i >= n) return;
-  const int root = uf_find_ro(parent, (int)i);
-  parent[i] = root;  // the only kind of write in this kernel: every entry a reader meets is an ancestor or the root
-  if (edges[i] & 1) atomicMin(minlow + root, (int)i);
+// The passes below only care about the flagged few cells: a thread reads four flag bytes as one word and a
+// 1024-thread CTA covers 4096 cells (one thread per byte spent its time scheduling CTAs, not moving data).
+constexpr int FL_CELLS_PER_CTA = 4 * FL_SCAN_THREADS;
+
+__device__ __forceinline__ unsigned flag_word(const uint8_t* bytes, int64_t n, int64_t i0, bool aligned) {
+  if (i0 >= n) return 0u;
+  if (aligned && i0 + 4 <= n) return *reinterpret_cast<const unsigned*>(bytes + i0);
+  unsigned w = 0;
+  for (int k = 0; k < 4; ++k)
+    if (i0 + k < n) w |= (unsigned)bytes[i0 + k] << (8 * k);
+  return w;
 }
 
-// a seed is the first low edge (row-major) of its component
-__device__ __forceinline__ bool is_seed(int64_t i, int64_t n, const int* parent, const uint8_t* edges, const int* minlow) {
-  return i < n && (edges[i] & 1) && minlow[parent[i]] == (int)i;
+// exclusive prefix of a per-thread count over the CTA (1024 threads); returns the CTA total through *total
+__device__ __forceinline__ unsigned cta_exclusive(unsigned c, unsigned* total) {
+  __shared__ unsigned warp_sum[FL_SCAN_THREADS / 32];
+  __shared__ unsigned cta_total;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned inc = c;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, inc, off);
+    if (lane >= off) inc += t;
+  }
+  if (lane == 31) warp_sum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    const unsigned v = warp_sum[lane];
+    unsigned ws = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, ws, off);
+      if (lane >= off) ws += t;
+    }
+    warp_sum[lane] = ws - v;
+    if (lane == 31) cta_total = ws;
+  }
+  __syncthreads();
+  *total = cta_total;
+  return warp_sum[w] + inc - c;
+}
+
+// low edges look their root up (making their own pointer direct) and post their index to the root's slot
+__global__ void __launch_bounds__(FL_SCAN_THREADS)
+flat_lowroot_kernel(int64_t n, int* parent, const uint8_t* __restrict__ edges, int* minlow) {
+  const int64_t i0 = 4 * ((int64_t)blockIdx.x * FL_SCAN_THREADS + threadIdx.x);
+  const unsigned w = flag_word(edges, n, i0, true) & 0x01010101u;
+  if (w == 0) return;
+  for (int k = 0; k < 4; ++k)
+    if ((w >> (8 * k)) & 1u) {
+      const int i = (int)(i0 + k);
+      const int root = uf_find_ro(parent, i);
+      parent[i] = root;  // own entry only, and a root is a valid parent for any reader walking by
+      atomicMin(minlow + root, i);
+    }
+}
+
+// a seed is the first low edge (row-major) of its component; bit k of the result: cell i0 + k is one
+__device__ __forceinline__ unsigned seed_bits(int64_t n, int64_t i0, const int* parent, const uint8_t* edges,
+                                              const int* minlow) {
+  const unsigned w = flag_word(edges, n, i0, true) & 0x01010101u;
+  unsigned bits = 0;
+  if (w)
+    for (int k = 0; k < 4; ++k)
+      if (((w >> (8 * k)) & 1u) && minlow[parent[i0 + k]] == (int)(i0 + k)) bits |= 1u << k;
+  return bits;
 }
 
 __global__ void __launch_bounds__(FL_SCAN_THREADS)
-flat_seed_count_kernel(int64_t n, const int* __restrict__ parent, const uint8_t* __restrict__ edges,
-                       const int* __restrict__ minlow, int* blockcnt) {
-  const int64_t i = (int64_t)blockIdx.x * FL_SCAN_THREADS + threadIdx.x;
-  const int total = __syncthreads_count(is_seed(i, n, parent, edges, minlow));
-  if (threadIdx.x == 0) blockcnt[blockIdx.x] = total;
+flat_seed_count_kernel(int64_t n, const int* parent, const uint8_t* __restrict__ edges, const int* minlow, int* blockcnt) {
+  const int64_t i0 = 4 * ((int64_t)blockIdx.x * FL_SCAN_THREADS + threadIdx.x);
+  unsigned total;
+  cta_exclusive(__popc(seed_bits(n, i0, parent, edges, minlow)), &total);
+  if (threadIdx.x == 0) blockcnt[blockIdx.x] = (int)total;
 }
 
-// exclusive scan of blockcnt[nb] in place (one CTA; nb <= 2^21), total -> cnt[CNT_LABELS]
+// exclusive scan of blockcnt[nb] in place (one CTA), total -> cnt[CNT_LABELS]
 __global__ void __launch_bounds__(FL_SCAN_THREADS) flat_seed_scan_kernel(int nb, int* blockcnt, unsigned* cnt) {
   __shared__ int part[FL_SCAN_THREADS];
   const int t = threadIdx.x;
@@ -201,112 +254,109 @@ __global__ void __launch_bounds__(FL_SCAN_THREADS) flat_seed_scan_kernel(int nb,
   if (t == FL_SCAN_THREADS - 1) cnt[CNT_LABELS] = (unsigned)part[t];
 }
 
-// seedlabel[i] = 1 + rank of seed i
+// seedlabel[i] = 1 + rank of seed i (row-major)
 __global__ void __launch_bounds__(FL_SCAN_THREADS)
-flat_seed_rank_kernel(int64_t n, const int* __restrict__ parent, const uint8_t* __restrict__ edges,
-                      const int* __restrict__ minlow, const int* __restrict__ blockoff, int* seedlabel) {
-  __shared__ int warp_tot[FL_SCAN_THREADS / 32];
-  const int64_t i = (int64_t)blockIdx.x * FL_SCAN_THREADS + threadIdx.x;
-  const bool seed = is_seed(i, n, parent, edges, minlow);
-  const unsigned m = __ballot_sync(0xffffffffu, seed);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) warp_tot[w] = __popc(m);
-  __syncthreads();
-  if (seed) {
-    int before = __popc(m & ((1u << lane) - 1u));
-    for (int k = 0; k < w; ++k) before += warp_tot[k];
-    seedlabel[i] = blockoff[blockIdx.x] + before + 1;
-  }
+flat_seed_rank_kernel(int64_t n, const int* parent, const uint8_t* __restrict__ edges, const int* minlow,
+                      const int* __restrict__ blockoff, int* seedlabel) {
+  const int64_t i0 = 4 * ((int64_t)blockIdx.x * FL_SCAN_THREADS + threadIdx.x);
+  const unsigned bits = seed_bits(n, i0, parent, edges, minlow);
+  unsigned total;
+  unsigned before = cta_exclusive(__popc(bits), &total) + (unsigned)blockoff[blockIdx.x];
+  for (int k = 0; k < 4; ++k)
+    if ((bits >> k) & 1u) seedlabel[i0 + k] = (int)(++before);
 }
 
-// roots: slot (smallest low edge, or BIG) -> the component's label
-__global__ void __launch_bounds__(FL_THREADS)
-flat_root_label_kernel(int64_t n, const int* __restrict__ parent, int* labels, const int* __restrict__ seedlabel) {
-  const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
-  if (i >= n || parent[i] != (int)i) return;
-  const int m = labels[i];
-  labels[i] = (m == FL_BIG) ? 0 : seedlabel[m];
-}
+// Every cell takes the label of its component: root -> the component's smallest low edge -> that seed's label
+// (0 when the component has no low edge).  The walk to the root is read-only (low edges already point at it).
+// open[i] is the sweeps' one-word view of a cell: 0 = never a candidate (it has a direction), otherwise
+// (label + 1) << 2 | g with g = 0 untouched, 1 claimed by the away sweep, 2 claimed by the towards sweep.
+__device__ __forceinline__ unsigned flat_state(int lab) { return (unsigned)(lab + 1) << 2; }
 
-// everyone else copies the root's label; the scratch use of flat_mask and parent ends here.  open[i] is the sweeps'
-// one-word view of a cell: label + 1 while the cell is a candidate (no direction, no value yet), 0 when it can
-// never be one, -(label + 1) once a sweep has claimed it.
 __global__ void __launch_bounds__(FL_THREADS)
-flat_spread_label_kernel(int64_t n, int* parent, int* labels, int* flat_mask, const uint8_t* __restrict__ fdr, int* open) {
+flat_spread_label_kernel(int64_t n, const int* __restrict__ parent, const int* __restrict__ minlow,
+                         const int* __restrict__ seedlabel, int* labels, const uint8_t* __restrict__ fdr, unsigned* open) {
   const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
   if (i >= n) return;
-  const int root = parent[i];
-  int lab;
-  if (root != (int)i) {
-    lab = labels[root];
-    labels[i] = lab;
-  } else {
-    lab = labels[i];
-  }
-  flat_mask[i] = 0;
-  open[i] = (fdr[i] == FL_UNDEF) ? lab + 1 : 0;
+  const int m = minlow[uf_find_ro(parent, (int)i)];
+  const int lab = (m == FL_BIG) ? 0 : seedlabel[m];
+  labels[i] = lab;
+  open[i] = (fdr[i] == FL_UNDEF) ? flat_state(lab) : 0u;
 }
 
 // ---------------------------------------------------------------- gradients (away_from_higher / towards_lower)
-// edge cells -> seed list, in no particular order (the sweeps are order-free)
+// edge cells -> seed list, in no particular order (the sweeps are order-free); one queue atomic per CTA
 __global__ void __launch_bounds__(FL_SCAN_THREADS)
-flat_collect_kernel(int64_t n, const uint8_t* __restrict__ edges, int bit, const int* __restrict__ labels, int* seeds,
-                    unsigned* cnt) {
-  __shared__ unsigned warp_off[FL_SCAN_THREADS / 32];
-  __shared__ unsigned block_base;
-  const int64_t i = (int64_t)blockIdx.x * FL_SCAN_THREADS + threadIdx.x;
-  const bool take = i < n && (edges[i] & bit) && labels[i] != 0;  // fix_flats.py:273-274 (low edges always carry a label)
-  const unsigned m = __ballot_sync(0xffffffffu, take);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) warp_off[w] = __popc(m);
+flat_collect_kernel(int64_t n, const uint8_t* __restrict__ edges, unsigned bit, const int* __restrict__ labels,
+                    int* seeds, unsigned* cnt) {
+  __shared__ unsigned cta_base;
+  const int64_t i0 = 4 * ((int64_t)blockIdx.x * FL_SCAN_THREADS + threadIdx.x);
+  const unsigned w = flag_word(edges, n, i0, true) & (bit * 0x01010101u);
+  unsigned bits = 0;
+  if (w)
+    for (int k = 0; k < 4; ++k)  // fix_flats.py:273-274: high edges outside labelled flats drop out (low edges never do)
+      if ((w >> (8 * k)) & 0xffu && labels[i0 + k] != 0) bits |= 1u << k;
+  unsigned total;
+  unsigned at = cta_exclusive(__popc(bits), &total);
+  if (total == 0) return;
+  if (threadIdx.x == 0) cta_base = atomicAdd(&cnt[CNT_SEEDS], total);
   __syncthreads();
-  if (w == 0) {  // exclusive scan of the 32 warp totals, one queue atomic for the block
-    const unsigned v = warp_off[lane];
-    unsigned inc = v;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const unsigned t = __shfl_up_sync(0xffffffffu, inc, off);
-      if (lane >= off) inc += t;
-    }
-    warp_off[lane] = inc - v;
-    if (lane == 31 && inc) block_base = atomicAdd(&cnt[CNT_SEEDS], inc);
-  }
-  __syncthreads();
-  if (take) seeds[block_base + warp_off[w] + __popc(m & ((1u << lane) - 1u))] = (int)i;
+  at += cta_base;
+  for (int k = 0; k < 4; ++k)
+    if ((bits >> k) & 1u) seeds[at++] = (int)(i0 + k);
 }
 
-// start of a sweep: towards_lower negates the mask (fix_flats.py:200); candidates are re-armed from the mask
+// Sweep modes: 0 away_from_higher; 1 towards_lower on a mask that was negated first (the standalone entry point,
+// any caller-supplied mask); 2 towards_lower straight on the away sweep's mask (resolve_flats: every cell the away
+// sweep valued is reached again, so the reference's negation never shows in the result and is not materialised).
+enum { SWEEP_AWAY = 0, SWEEP_TOWARDS_NEGATED = 1, SWEEP_TOWARDS = 2 };
+
+// standalone sweeps: towards_lower negates the mask (fix_flats.py:200); candidates are armed from the mask
 __global__ void __launch_bounds__(FL_THREADS)
-flat_prepare_kernel(int64_t n, int towards, int* flat_mask, const int* __restrict__ labels,
-                    const uint8_t* __restrict__ fdr, int* open) {
+flat_prepare_kernel(int64_t n, int mode, int* flat_mask, const int* __restrict__ labels, const uint8_t* __restrict__ fdr,
+                    unsigned* open) {
   const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
   if (i >= n) return;
   int fm = flat_mask[i];
-  if (towards) {
+  if (mode != SWEEP_AWAY) {
     fm = -fm;
     flat_mask[i] = fm;
   }
-  open[i] = (fdr[i] == FL_UNDEF && fm <= 0) ? labels[i] + 1 : 0;
+  open[i] = (fdr[i] == FL_UNDEF && fm <= 0) ? flat_state(labels[i]) : 0u;
+}
+
+// One try to claim candidate word `s` of cell q for this sweep.
+__device__ __forceinline__ bool flat_claim(unsigned* open, int q, unsigned s, unsigned want, int mode) {
+  if ((s & ~3u) != want) return false;
+  if (mode == SWEEP_AWAY) return (s & 3u) == 0u && atomicCAS(open + q, s, s | 1u) == s;
+  return (s & 3u) != 2u && atomicCAS(open + q, s, (s & ~3u) | 2u) == s;
 }
 
 // The value a cell gets when a sweep reaches it at `level` (:153-154 / :209-214); only the claiming thread calls this.
-__device__ __forceinline__ void flat_assign(int p, int level, int towards, int lab, int* flat_mask, const int* fh_read,
+__device__ __forceinline__ void flat_assign(int p, int level, int mode, int lab, int* flat_mask, const int* fh_read,
                                             int* fh_acc) {
-  if (!towards) {
+  if (mode == SWEEP_AWAY) {
     flat_mask[p] = level;
     // every cell of a level carries the same value: one atomic per flat and level gets through
     if (lab > 0 && __ldcg(fh_acc + lab - 1) < level) atomicMax(fh_acc + lab - 1, level);
   } else {
     const int fm = flat_mask[p];
-    flat_mask[p] = ((fm < 0 && lab > 0) ? fm + fh_read[lab - 1] : 0) + 2 * level;
+    int away = 0;  // flat_height - (increments away from higher terrain), 0 where the away sweep never came
+    if (lab > 0) {
+      if (mode == SWEEP_TOWARDS_NEGATED && fm < 0) away = fm + fh_read[lab - 1];
+      if (mode == SWEEP_TOWARDS && fm > 0) away = fh_read[lab - 1] - fm;
+    }
+    flat_mask[p] = away + 2 * level;
   }
 }
 
 // Frontier appends go through a per-CTA buffer: a warp reserves its slots with one shared-memory atomic, and the
 // CTA moves the buffer to the global queue with one global atomic when it fills up.  (One global atomic per warp
 // was the bottleneck of the sweeps: tens of millions of adds on a single counter.)
-constexpr int FL_QBUF = 2048;
-constexpr int FL_ILP = 2;     // pushes per thread and loop round
+#ifndef OFL_FL_ILP
+#define OFL_FL_ILP 2
+#endif
+constexpr int FL_ILP = OFL_FL_ILP;  // pushes per thread and loop round (tuning: -DOFL_FL_ILP=4)
+constexpr int FL_QBUF = 1024 * FL_ILP;
 constexpr int FL_ROUNDS = 2;  // loop rounds between two looks at the fill level
 constexpr int FL_BATCH = FL_ROUNDS * FL_ILP * FL_THREADS;  // most pushes between two looks
 static_assert(FL_QBUF >= 2 * FL_BATCH, "buffer must hold two batches of rounds");
@@ -351,8 +401,8 @@ __device__ __forceinline__ void bq_maybe_flush(BlockQueue& bq, unsigned round, i
 
 // level 1: the seed edges themselves (duplicates and already positive cells drop out)
 __global__ void __launch_bounds__(FL_THREADS)
-flat_seed_level_kernel(const int* __restrict__ seeds, const int* __restrict__ labels, int towards, int* flat_mask,
-                       int* open, const int* fh_read, int* fh_acc, int* qout, unsigned* cnt) {
+flat_seed_level_kernel(const int* __restrict__ seeds, const int* __restrict__ labels, int mode, int* flat_mask,
+                       unsigned* open, const int* fh_read, int* fh_acc, int* qout, unsigned* cnt) {
   __shared__ BlockQueue bq;
   const unsigned n_seed = cnt[CNT_SEEDS];
   if (blockIdx.x == 0 && threadIdx.x == 0) cnt[CNT_FRONT0 + 2] = 0;
@@ -367,16 +417,16 @@ flat_seed_level_kernel(const int* __restrict__ seeds, const int* __restrict__ la
     if (idx < n_seed) {
       p = seeds[idx];
       const int lab = labels[p];
-      const int o = __ldcg(open + p);
-      if (o > 0) {  // a candidate cell: claimed like any other
-        won = atomicCAS(open + p, o, -o) == o;
-        if (won) flat_assign(p, 1, towards, lab, flat_mask, fh_read, fh_acc);
-      } else if (o == 0) {  // a cell with a direction (low edges): never a candidate, the mask itself dedupes
+      const unsigned o = __ldcg(open + p);
+      if (o != 0u) {  // a candidate cell: claimed like any other
+        won = flat_claim(open, p, o, flat_state(lab), mode);
+        if (won) flat_assign(p, 1, mode, lab, flat_mask, fh_read, fh_acc);
+      } else {  // a cell with a direction (low edges) or one that already has its value: the mask itself dedupes
         const int fm = __ldcg(flat_mask + p);
         if (fm <= 0) {
-          const int nv = towards ? ((fm < 0 && lab > 0) ? fm + fh_read[lab - 1] : 0) + 2 : 1;
+          const int nv = mode == SWEEP_AWAY ? 1 : ((fm < 0 && lab > 0) ? fm + fh_read[lab - 1] : 0) + 2;
           won = atomicCAS(flat_mask + p, fm, nv) == fm;
-          if (won && !towards && lab > 0) atomicMax(fh_acc + lab - 1, 1);
+          if (won && mode == SWEEP_AWAY && lab > 0) atomicMax(fh_acc + lab - 1, 1);
         }
       }
     }
@@ -391,7 +441,7 @@ flat_seed_level_kernel(const int* __restrict__ seeds, const int* __restrict__ la
 // latency bound), and a neighbour costs one scattered word (open[q]) instead of three (mask, code, label).
 __global__ void __launch_bounds__(FL_THREADS)
 flat_level_kernel(int level, const int* __restrict__ qin, int* qout, const int* __restrict__ labels, int rows, int cols,
-                  int towards, int* flat_mask, int* open, const int* fh_read, int* fh_acc, unsigned* cnt) {
+                  int mode, int* flat_mask, unsigned* open, const int* fh_read, int* fh_acc, unsigned* cnt) {
   __shared__ BlockQueue bq;
   const unsigned n_in = cnt[CNT_FRONT0 + level % 3];
   unsigned* cnt_out = &cnt[CNT_FRONT0 + (level + 1) % 3];
@@ -405,7 +455,8 @@ flat_level_kernel(int level, const int* __restrict__ qin, int* qout, const int* 
   unsigned round = 0;
   for (unsigned base = blockIdx.x * CELLS * FL_ILP; base < n_in; base += stride) {
     // FL_ILP independent (cell, neighbour) pairs per thread: the three dependent loads of each overlap
-    int q[FL_ILP], want[FL_ILP], seen[FL_ILP];
+    int q[FL_ILP];
+    unsigned want[FL_ILP], seen[FL_ILP];
     bool ok[FL_ILP];
 #pragma unroll
     for (int u = 0; u < FL_ILP; ++u) {
@@ -416,20 +467,20 @@ flat_level_kernel(int level, const int* __restrict__ qin, int* qout, const int* 
 #pragma unroll
     for (int u = 0; u < FL_ILP; ++u) {
       const int p = q[u];
-      want[u] = ok[u] ? labels[p] + 1 : 0;
+      want[u] = ok[u] ? flat_state(labels[p]) : 0u;
       const int r = p / cols, c = p - r * cols;
       const int nr = r + dy, nc = c + dx;
       ok[u] = ok[u] && nr >= 0 && nr < rows && nc >= 0 && nc < cols;
       q[u] = ok[u] ? nr * cols + nc : 0;
     }
 #pragma unroll
-    for (int u = 0; u < FL_ILP; ++u) seen[u] = ok[u] ? __ldcg(open + q[u]) : 0;
+    for (int u = 0; u < FL_ILP; ++u) seen[u] = ok[u] ? __ldcg(open + q[u]) : 0u;
 #pragma unroll
     for (int u = 0; u < FL_ILP; ++u) {
       bool won = false;
-      if (ok[u] && seen[u] == want[u] && atomicCAS(open + q[u], want[u], -want[u]) == want[u]) {
+      if (ok[u] && seen[u] != 0u && flat_claim(open, q[u], seen[u], want[u], mode)) {
         won = true;
-        flat_assign(q[u], level + 1, towards, want[u] - 1, flat_mask, fh_read, fh_acc);
+        flat_assign(q[u], level + 1, mode, (int)(want[u] >> 2) - 1, flat_mask, fh_read, fh_acc);
       }
       bq_push(bq, won, q[u]);
     }
@@ -445,12 +496,8 @@ __global__ void __launch_bounds__(FL_THREADS) flat_height_merge_kernel(int n, co
 }
 
 // ---------------------------------------------------------------- d8_masked_flow_dirs (fix_flats.py:291-339)
-__global__ void __launch_bounds__(FL_THREADS)
-flat_masked_dirs_kernel(const int* __restrict__ flat_mask, const int* __restrict__ labels, uint8_t* fdr, int rows,
-                        int cols) {
-  const int64_t n = (int64_t)rows * cols;
-  const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
-  if (i >= n || fdr[i] != FL_UNDEF) return;
+__device__ __forceinline__ int masked_dir_of(int64_t i, const int* __restrict__ flat_mask, const int* __restrict__ labels,
+                                             int rows, int cols) {
   const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
   const int lab = labels[i];
   const double fm = (double)flat_mask[i];
@@ -469,7 +516,19 @@ flat_masked_dirs_kernel(const int* __restrict__ flat_mask, const int* __restrict
       nmin = k;
     }
   }
-  fdr[i] = (uint8_t)nmin;
+  return nmin;
+}
+
+// a thread looks at four codes at once; only cells without a direction cost anything
+__global__ void __launch_bounds__(FL_THREADS)
+flat_masked_dirs_kernel(const int* __restrict__ flat_mask, const int* __restrict__ labels, uint8_t* fdr, int rows,
+                        int cols, int aligned) {
+  const int64_t n = (int64_t)rows * cols;
+  const int64_t i0 = 4 * ((int64_t)blockIdx.x * FL_THREADS + threadIdx.x);
+  const unsigned w = flag_word(fdr, n, i0, aligned != 0);
+  for (int k = 0; k < 4; ++k)
+    if (i0 + k < n && ((w >> (8 * k)) & 0xffu) == (unsigned)FL_UNDEF)
+      fdr[i0 + k] = (uint8_t)masked_dir_of(i0 + k, flat_mask, labels, rows, cols);
 }
 
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
@@ -478,7 +537,7 @@ struct FlatsWork {
   int* parent;  // union-find forest, later flat_height
   int* q0;      // frontier queue / block counts of the label scan
   int* q1;      // seed list / frontier queue
-  int* open;    // the sweeps' candidate words
+  unsigned* open;  // the sweeps' candidate words
   uint8_t* edges;
   unsigned* cnt;
 };
@@ -493,7 +552,7 @@ int carve(void* workspace, size_t workspace_bytes, int64_t n, FlatsWork* w) {
   w->parent = reinterpret_cast<int*>(p);
   w->q0 = reinterpret_cast<int*>(p + a);
   w->q1 = reinterpret_cast<int*>(p + 2 * a);
-  w->open = reinterpret_cast<int*>(p + 3 * a);
+  w->open = reinterpret_cast<unsigned*>(p + 3 * a);
   w->edges = reinterpret_cast<uint8_t*>(p + 4 * a);
   w->cnt = reinterpret_cast<unsigned*>(p + 4 * a + e);
   return OFL_OK;
@@ -501,18 +560,18 @@ int carve(void* workspace, size_t workspace_bytes, int64_t n, FlatsWork* w) {
 
 // One sweep from the seed list in w.q1 (count in cnt[CNT_SEEDS]).  Host-synchronous: the level loop reads the
 // next frontier's size back once per batch of launches.
-int run_gradient(int rows, int cols, const int* labels, const uint8_t* fdr, int towards, bool open_ready, int* flat_mask,
+int run_gradient(int rows, int cols, const int* labels, const uint8_t* fdr, int mode, bool open_ready, int* flat_mask,
                  const int* fh_read, int* fh_acc, const FlatsWork& w, int64_t* levels_out, cudaStream_t st) {
-  // open_ready: w.open already describes the candidates (fresh from the labelling, mask all zero)
+  // open_ready: w.open already describes the candidates (resolve_flats: armed by the labelling, re-used by the
+  // second sweep through the generation bits); otherwise they are armed from the mask, negated first for towards_lower
   const int64_t n = (int64_t)rows * cols;
   OFL_CUDA(cudaMemsetAsync(w.cnt + CNT_FRONT0, 0, 3 * sizeof(unsigned), st));
   if (!open_ready) {
-    flat_prepare_kernel<<<blocks_for(n, FL_THREADS), FL_THREADS, 0, st>>>(n, towards, flat_mask, labels, fdr, w.open);
+    flat_prepare_kernel<<<blocks_for(n, FL_THREADS), FL_THREADS, 0, st>>>(n, mode, flat_mask, labels, fdr, w.open);
     OFL_CHECK_LAUNCH();
   }
   const unsigned grid = (unsigned)(sm_count() * 8);  // 8 CTAs of 256 threads fill an SM
-  flat_seed_level_kernel<<<grid, FL_THREADS, 0, st>>>(w.q1, labels, towards, flat_mask, w.open, fh_read, fh_acc, w.q0,
-                                                       w.cnt);
+  flat_seed_level_kernel<<<grid, FL_THREADS, 0, st>>>(w.q1, labels, mode, flat_mask, w.open, fh_read, fh_acc, w.q0, w.cnt);
   OFL_CHECK_LAUNCH();
   unsigned* h_cnt = nullptr;
   int rc = pinned_get(64, reinterpret_cast<void**>(&h_cnt));
@@ -523,8 +582,8 @@ int run_gradient(int rows, int cols, const int* labels, const uint8_t* fdr, int 
   int batch = 8;
   for (;;) {
     for (int b = 0; b < batch; ++b) {
-      flat_level_kernel<<<grid, FL_THREADS, 0, st>>>(level, qin, qout, labels, rows, cols, towards, flat_mask, w.open,
-                                                      fh_read, fh_acc, w.cnt);
+      flat_level_kernel<<<grid, FL_THREADS, 0, st>>>(level, qin, qout, labels, rows, cols, mode, flat_mask, w.open, fh_read,
+                                                      fh_acc, w.cnt);
       OFL_CHECK_LAUNCH();
       ++level;
       int* t = qin;
@@ -586,50 +645,61 @@ int launch_resolve_flats(const float* dem, const uint8_t* fdr, int64_t rows, int
   FlatsWork w;
   rc = carve(workspace, workspace_bytes, n, &w);
   if (rc != OFL_OK) return rc;
-  const unsigned nb = blocks_for(n, FL_THREADS), nbs = blocks_for(n, FL_SCAN_THREADS);
+  const unsigned nb = blocks_for(n, FL_THREADS), nbc = blocks_for(n, FL_CELLS_PER_CTA);
   OFL_CUDA(cudaMemsetAsync(w.cnt, 0, CNT_SLOTS * sizeof(unsigned), st));
   int* flat_height = w.parent;  // lives where the forest was once the labels are known (label count <= cell count)
-  {
-  PhaseScope ps(PHASE_FLATS_LABEL, st);
-  // `labels` holds the per-component smallest-low-edge slots until the labels are known
-  flat_edges_kernel<<<nb, FL_THREADS, 0, st>>>(dem, fdr, (int)rows, (int)cols, w.edges, w.parent, labels, w.cnt);
-  OFL_CHECK_LAUNCH();
-  flat_merge_kernel<<<nb, FL_THREADS, 0, st>>>(dem, (int)rows, (int)cols, w.parent);
-  OFL_CHECK_LAUNCH();
-  flat_flatten_kernel<<<nb, FL_THREADS, 0, st>>>(n, w.parent, w.edges, labels);
-  OFL_CHECK_LAUNCH();
-  flat_seed_count_kernel<<<nbs, FL_SCAN_THREADS, 0, st>>>(n, w.parent, w.edges, labels, w.q0);
-  OFL_CHECK_LAUNCH();
-  flat_seed_scan_kernel<<<1, FL_SCAN_THREADS, 0, st>>>((int)nbs, w.q0, w.cnt);
-  OFL_CHECK_LAUNCH();
-  flat_seed_rank_kernel<<<nbs, FL_SCAN_THREADS, 0, st>>>(n, w.parent, w.edges, labels, w.q0, flat_mask);
-  OFL_CHECK_LAUNCH();
-  flat_root_label_kernel<<<nb, FL_THREADS, 0, st>>>(n, w.parent, labels, flat_mask);
-  OFL_CHECK_LAUNCH();
-  flat_spread_label_kernel<<<nb, FL_THREADS, 0, st>>>(n, w.parent, labels, flat_mask, fdr, w.open);
-  OFL_CHECK_LAUNCH();
-  OFL_CUDA(cudaMemsetAsync(flat_height, 0, (size_t)n * sizeof(int), st));
-  }
-  PhaseScope ps(PHASE_FLATS_SWEEP, st);
+  int* minlow = w.q1;           // per-component smallest low edge, until the labels are known
+  int* seedlabel = flat_mask;   // label of each component's first low edge, until the labels are known
+  unsigned* h = nullptr;
+  rc = pinned_get(64, reinterpret_cast<void**>(&h));
+  if (rc != OFL_OK) return rc;
   int64_t lv_away = 0, lv_low = 0;
-  flat_collect_kernel<<<nbs, FL_SCAN_THREADS, 0, st>>>(n, w.edges, 2, labels, w.q1, w.cnt);
-  OFL_CHECK_LAUNCH();
-  rc = run_gradient((int)rows, (int)cols, labels, fdr, 0, true, flat_mask, flat_height, flat_height, w, &lv_away, st);
-  if (rc != OFL_OK) return rc;
-  OFL_CUDA(cudaMemsetAsync(w.cnt + CNT_SEEDS, 0, sizeof(unsigned), st));
-  flat_collect_kernel<<<nbs, FL_SCAN_THREADS, 0, st>>>(n, w.edges, 1, labels, w.q1, w.cnt);
-  OFL_CHECK_LAUNCH();
-  rc = run_gradient((int)rows, (int)cols, labels, fdr, 1, false, flat_mask, flat_height, flat_height, w, &lv_low, st);
-  if (rc != OFL_OK) return rc;
-  if (info) {
-    unsigned* h = nullptr;
-    rc = pinned_get(64, reinterpret_cast<void**>(&h));
-    if (rc != OFL_OK) return rc;
+  {
+    PhaseScope ps(PHASE_FLATS_LABEL, st);
+    flat_edges_kernel<<<nb, FL_THREADS, 0, st>>>(dem, fdr, (int)rows, (int)cols, w.edges, w.parent, minlow, w.cnt);
+    OFL_CHECK_LAUNCH();
+    flat_merge_kernel<<<nb, FL_THREADS, 0, st>>>(dem, (int)rows, (int)cols, w.parent);
+    OFL_CHECK_LAUNCH();
+    flat_lowroot_kernel<<<nbc, FL_SCAN_THREADS, 0, st>>>(n, w.parent, w.edges, minlow);
+    OFL_CHECK_LAUNCH();
+    flat_seed_count_kernel<<<nbc, FL_SCAN_THREADS, 0, st>>>(n, w.parent, w.edges, minlow, w.q0);
+    OFL_CHECK_LAUNCH();
+    flat_seed_scan_kernel<<<1, FL_SCAN_THREADS, 0, st>>>((int)nbc, w.q0, w.cnt);
+    OFL_CHECK_LAUNCH();
+    flat_seed_rank_kernel<<<nbc, FL_SCAN_THREADS, 0, st>>>(n, w.parent, w.edges, minlow, w.q0, seedlabel);
+    OFL_CHECK_LAUNCH();
+    // one look at the counts: nothing to do without low edges (fix_flats.py:258-264), and flat_height needs
+    // only as many cleared entries as there are labels
     OFL_CUDA(cudaMemcpyAsync(h, w.cnt, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     OFL_CUDA(cudaStreamSynchronize(st));
-    info[0] = h[CNT_LOW];
-    info[1] = h[CNT_HIGH];
-    info[2] = h[CNT_LABELS];
+    const unsigned n_low = h[CNT_LOW], n_high = h[CNT_HIGH], n_labels = h[CNT_LABELS];
+    if (info) {
+      info[0] = n_low;
+      info[1] = n_high;
+      info[2] = n_labels;
+    }
+    OFL_REQUIRE(n_labels < (1u << 29), OFL_ERR_INVALID, "more than 2^29 flats in one tile");
+    if (n_labels == 0) {
+      OFL_CUDA(cudaMemsetAsync(labels, 0, (size_t)n * sizeof(int), st));
+      OFL_CUDA(cudaMemsetAsync(flat_mask, 0, (size_t)n * sizeof(int), st));
+      return OFL_OK;
+    }
+    flat_spread_label_kernel<<<nb, FL_THREADS, 0, st>>>(n, w.parent, minlow, seedlabel, labels, fdr, w.open);
+    OFL_CHECK_LAUNCH();
+    OFL_CUDA(cudaMemsetAsync(flat_mask, 0, (size_t)n * sizeof(int), st));
+    OFL_CUDA(cudaMemsetAsync(flat_height, 0, ((size_t)n_labels + 1) * sizeof(int), st));
+  }
+  PhaseScope ps(PHASE_FLATS_SWEEP, st);
+  flat_collect_kernel<<<nbc, FL_SCAN_THREADS, 0, st>>>(n, w.edges, 2u, labels, w.q1, w.cnt);
+  OFL_CHECK_LAUNCH();
+  rc = run_gradient((int)rows, (int)cols, labels, fdr, SWEEP_AWAY, true, flat_mask, flat_height, flat_height, w, &lv_away, st);
+  if (rc != OFL_OK) return rc;
+  OFL_CUDA(cudaMemsetAsync(w.cnt + CNT_SEEDS, 0, sizeof(unsigned), st));
+  flat_collect_kernel<<<nbc, FL_SCAN_THREADS, 0, st>>>(n, w.edges, 1u, labels, w.q1, w.cnt);
+  OFL_CHECK_LAUNCH();
+  rc = run_gradient((int)rows, (int)cols, labels, fdr, SWEEP_TOWARDS, true, flat_mask, flat_height, flat_height, w, &lv_low, st);
+  if (rc != OFL_OK) return rc;
+  if (info) {
     info[3] = lv_away;
     info[4] = lv_low;
   }
@@ -657,7 +727,8 @@ int launch_flat_gradient(const int* labels, const uint8_t* fdr, int64_t rows, in
   if (n_seeds) OFL_CUDA(cudaMemcpyAsync(w.q1, seeds, (size_t)n_seeds * sizeof(int), cudaMemcpyDeviceToDevice, st));
   int* acc = w.parent;  // the sweep's own maxima; merged below so untouched labels keep the caller's value
   OFL_CUDA(cudaMemsetAsync(acc, 0, (size_t)n * sizeof(int), st));
-  rc = run_gradient((int)rows, (int)cols, labels, fdr, towards, false, flat_mask, flat_height, acc, w, nullptr, st);
+  rc = run_gradient((int)rows, (int)cols, labels, fdr, towards ? SWEEP_TOWARDS_NEGATED : SWEEP_AWAY, false, flat_mask,
+                    flat_height, acc, w, nullptr, st);
   if (rc != OFL_OK) return rc;
   if (!towards && n_heights) {
     flat_height_merge_kernel<<<blocks_for(n_heights, FL_THREADS), FL_THREADS, 0, st>>>((int)n_heights, acc, flat_height);
@@ -671,8 +742,9 @@ int launch_masked_flow_dirs(const int* flat_mask, const int* labels, uint8_t* fd
   int rc = check_shape(rows, cols);
   if (rc != OFL_OK) return rc;
   PhaseScope ps(PHASE_FLATS, st);
-  flat_masked_dirs_kernel<<<blocks_for(rows * cols, FL_THREADS), FL_THREADS, 0, st>>>(flat_mask, labels, fdr, (int)rows,
-                                                                                        (int)cols);
+  const int aligned = (reinterpret_cast<uintptr_t>(fdr) & 3u) == 0;
+  flat_masked_dirs_kernel<<<blocks_for((rows * cols + 3) / 4, FL_THREADS), FL_THREADS, 0, st>>>(flat_mask, labels, fdr,
+                                                                                                  (int)rows, (int)cols, aligned);
   OFL_CHECK_LAUNCH();
   return OFL_OK;
 }
