@@ -496,6 +496,9 @@ __global__ void __launch_bounds__(FL_THREADS) flat_height_merge_kernel(int n, co
 }
 
 // ---------------------------------------------------------------- d8_masked_flow_dirs (fix_flats.py:291-339)
+// Slopes in float64 with the reference's division (:335-340).  (An exact integer comparison, b^2 against 2 a^2,
+// was measured: it needs all eight differences in registers at once and ran 18 % slower; the kernel waits on its
+// sixteen neighbour loads, not on the divisions.)
 __device__ __forceinline__ int masked_dir_of(int64_t i, const int* __restrict__ flat_mask, const int* __restrict__ labels,
                                              int rows, int cols) {
   const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);

@@ -203,6 +203,24 @@ def test_routing_through_resolved_flats():
     assert np.array_equal(fac.cpu().numpy(), oracle.flow_accumulation(fixed))
 
 
+@pytest.mark.parametrize("span", [3, 1000, 2**20 - 1, 2**20 + 5, 2**30])
+def test_masked_dirs_value_ranges(span):
+    """d8_masked_flow_dirs on arbitrary masks, from tiny to int32-wide differences, with near-ties between cardinal
+    and diagonal steps planted: the float64 slopes must give the reference's (= the oracle's) choice everywhere."""
+    rng = np.random.default_rng(span % 1000)
+    shape = (97, 131)
+    flat_mask = rng.integers(-span, span + 1, size=shape).astype(np.int32)
+    near = np.round(flat_mask[:, :-1].astype(np.float64) * np.sqrt(2.0))  # near-ties between cardinal and diagonal steps
+    flat_mask[:, 1:] = np.where(rng.random((97, 130)) < 0.3, np.clip(near, -2**31 + 1, 2**31 - 1).astype(np.int64),
+                                flat_mask[:, 1:]).astype(np.int32)
+    labels = rng.integers(0, 3, size=shape).astype(np.int32)
+    fdr = rng.choice(np.array([0, 3, 8, 8, 8, 9], dtype=np.uint8), size=shape)
+    want = oracle.d8_masked_flow_dirs(flat_mask, fdr, labels)
+    got = fdr.copy()
+    ff().d8_masked_flow_dirs(flat_mask, got, labels)
+    assert np.array_equal(got, want)
+
+
 def test_rejects_inexact_dtypes_and_sizes():
     with pytest.raises(TypeError):
         ff().resolve_flats(np.array([[1e-50, 2.0]], dtype=np.float64), np.array([[8, 8]], dtype=np.uint8))
