@@ -206,7 +206,7 @@ flat_lowroot_kernel(int64_t n, int* parent, const uint8_t* __restrict__ edges, i
       const int i = (int)(i0 + k);
       const int root = uf_find_ro(parent, i);
       parent[i] = root;  // own entry only, and a root is a valid parent for any reader walking by
-      atomicMin(minlow + root, i);
+      if (__ldcg(minlow + root) > i) atomicMin(minlow + root, i);  // a plain look first: most low edges lose to an earlier one
     }
 }
 
