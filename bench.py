@@ -409,6 +409,8 @@ def run_native(args):
 def flats_leg(torch, dev, peak, size=8192, window=1024):
     """ofl_fix_flats_f32 (resolve_flats + d8_masked_flow_dirs) on device buffers: terraced synthetic DEM, CUDA-event
     time of the call, a window checked against the CPU oracle, and the oracle timed on that window."""
+    import numpy as np
+
     import oracle
 
     dem = dev.synth_dem(size, size, seed=3, kind=1, relief=200.0, holes_permille=5)
