@@ -99,13 +99,26 @@ def flow_accumulation(fdr: torch.Tensor, *, out=None, workspace=None, with_links
     return (out, links) if with_links else out
 
 
-def flow_routing(dem: torch.Tensor, nodata_value: float, *, out_fdr=None, out_fac=None):
+def flow_routing(dem: torch.Tensor, nodata_value: float, *, out_fdr=None, out_fac=None, resolve_flats=False):
     """(fdr uint8, fac int64) of a float32 CUDA DEM in one library call (ofl_flow_routing_f32): the
-    accumulation workspace is library-owned and cleared next to the stencil.  Synchronises the stream."""
+    accumulation workspace is library-owned and cleared next to the stencil.  Synchronises the stream.
+
+    resolve_flats=True runs the three steps as the reference orders them -- flow direction, flat resolution
+    (fix_flats.py), accumulation -- with the codes resident on the device throughout.  The DEM must be free of
+    pits then (the reference breaches them first): its d8_masked_flow_dirs points a pit at a neighbour, which can
+    close a cycle, and a cyclic raster makes the accumulation raise OFL_ERR_CYCLE."""
     if dem.dtype != torch.float32 or dem.dim() != 2 or dem.stride(1) != 1:
         raise ValueError("dem must be a 2-D float32 tensor with unit column stride")
     _init_for(dem)
     rows, cols = dem.shape
+    if resolve_flats:
+        if not dem.is_contiguous():
+            raise ValueError("resolve_flats needs a contiguous DEM")
+        if cols % 16:
+            raise ValueError("resolve_flats needs a column count that is a multiple of 16 (dense codes, TMA pitch)")
+        fdr = flow_direction(dem, nodata_value, out=out_fdr)
+        fix_flats(dem, fdr)
+        return fdr, flow_accumulation(fdr, out=out_fac)
     if out_fdr is None:
         out_fdr = torch.empty((rows, (cols + 15) // 16 * 16), dtype=torch.uint8, device=dem.device)[:, :cols]
     if out_fac is None:

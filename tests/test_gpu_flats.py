@@ -201,6 +201,9 @@ def test_routing_through_resolved_flats():
     fac = dev.flow_accumulation(d_fdr)
     assert dev.check_accumulation(d_fdr, fac) == 0
     assert np.array_equal(fac.cpu().numpy(), oracle.flow_accumulation(fixed))
+    # the same chain as one device call
+    fdr2, fac2 = dev.flow_routing(d_dem, synth.NODATA, resolve_flats=True)
+    assert torch.equal(fdr2, d_fdr) and torch.equal(fac2, fac)
 
 
 @pytest.mark.parametrize("span", [3, 1000, 2**20 - 1, 2**20 + 5, 2**30])
