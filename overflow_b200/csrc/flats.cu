@@ -399,19 +399,6 @@ __device__ __forceinline__ void bq_maybe_flush(BlockQueue& bq, unsigned round, i
   if (full) bq_flush(bq, qout, cnt_out);
 }
 
-// small frontiers skip the buffer: one queue atomic per warp costs nothing there, and the flush's barriers and
-// extra round trip are most of such a level's time
-__device__ __forceinline__ void direct_push(bool won, int p, int* qout, unsigned* cnt_out) {
-  const unsigned m = __ballot_sync(0xffffffffu, won);
-  if (m == 0) return;
-  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-  unsigned base = 0;
-  if (lane == leader) base = atomicAdd(cnt_out, (unsigned)__popc(m));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (won) qout[base + __popc(m & ((1u << lane) - 1u))] = p;
-}
-constexpr unsigned FL_DIRECT_BELOW = 16384;  // frontier cells
-
 // level 1: the seed edges themselves (duplicates and already positive cells drop out)
 __global__ void __launch_bounds__(FL_THREADS)
 flat_seed_level_kernel(const int* __restrict__ seeds, const int* __restrict__ labels, int mode, int* flat_mask,
@@ -459,11 +446,8 @@ flat_level_kernel(int level, const int* __restrict__ qin, int* qout, const int* 
   const unsigned n_in = cnt[CNT_FRONT0 + level % 3];
   unsigned* cnt_out = &cnt[CNT_FRONT0 + (level + 1) % 3];
   if (blockIdx.x == 0 && threadIdx.x == 0) cnt[CNT_FRONT0 + (level + 2) % 3] = 0;
-  const bool direct = n_in < FL_DIRECT_BELOW;  // uniform over the grid
-  if (!direct) {
-    if (threadIdx.x == 0) bq.n = 0;
-    __syncthreads();
-  }
+  if (threadIdx.x == 0) bq.n = 0;
+  __syncthreads();
   constexpr unsigned CELLS = FL_THREADS / 8;
   const unsigned stride = gridDim.x * CELLS * FL_ILP;
   const int k = threadIdx.x & 7;
@@ -498,14 +482,11 @@ flat_level_kernel(int level, const int* __restrict__ qin, int* qout, const int* 
         won = true;
         flat_assign(q[u], level + 1, mode, (int)(want[u] >> 2) - 1, flat_mask, fh_read, fh_acc);
       }
-      if (direct)
-        direct_push(won, q[u], qout, cnt_out);
-      else
-        bq_push(bq, won, q[u]);
+      bq_push(bq, won, q[u]);
     }
-    if (!direct) bq_maybe_flush(bq, ++round, qout, cnt_out);
+    bq_maybe_flush(bq, ++round, qout, cnt_out);
   }
-  if (!direct) bq_flush(bq, qout, cnt_out);
+  bq_flush(bq, qout, cnt_out);
 }
 
 // flat_height[k] takes the sweep's value where the sweep reached label k+1 (standalone away_from_higher)
