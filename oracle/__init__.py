@@ -4,7 +4,8 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 ``--impl reference`` legs may import this package.  Nothing under ``overflow_b200/``
 imports it; the product path fails loudly when the CUDA library is missing.
 
-Parity status: pinned (see ``oracle/d8_oracle.c`` header and ``oracle/gen_golden.py``).
+Parity status: pinned (see ``oracle/d8_oracle.c`` header and ``oracle/gen_golden.py``; flat resolution:
+``oracle/flats_oracle.c`` and ``oracle/gen_golden_flats.py``).
 """
 from .oracle import (  # noqa: F401
     build,

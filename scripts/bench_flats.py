@@ -1,17 +1,17 @@
-"""Time flat resolution (ofl_fix_flats_f32, device buffers) on synthetic DEMs and compare a window with the oracle.
+"""Time flat resolution (ofl_fix_flats_f32, device buffers) on synthetic DEMs.
 
-    python scripts/bench_flats.py [--size 8192] [--kind 1] [--relief 200] [--steps 3] [--oracle-window 1024]
+    python scripts/bench_flats.py [--size 8192] [--kind 1] [--relief 200] [--steps 3]
 
 kind 0 fractal (few, small flats), kind 1 terraces (flat-heavy), kind 2 tilted plane (none).
 Prints one JSON line per run: ms per call (CUDA events on the launching stream), Gcells/s, the algorithmic
 GB/s at 14 B/cell (DEM 4 + codes 1 read; codes 1 + flat_mask 4 + labels 4 written) against the measured HBM
-peak, the sweep depths, and the CPU oracle's time on a window of the same DEM.
+peak, the sweep depths and the per-phase times.  (Parity against the oracle and the CPU baseline of this row are
+in tests/test_gpu_flats.py and bench.py's next_rows.fix_flats.)
 """
 import argparse
 import json
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -29,7 +29,7 @@ def main():
     ap.add_argument("--relief", type=float, default=200.0)
     ap.add_argument("--holes", type=int, default=5)
     ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--oracle-window", type=int, default=1024)
+    ap.add_argument("--oracle-window", type=int, default=0, help="ignored (parity and the CPU baseline live in tests/ and bench.py)")
     a = ap.parse_args()
     n = a.size
     peak = 6551.4
@@ -70,19 +70,6 @@ def main():
         "low_edges": info[0], "high_edges": info[1], "labels": info[2], "away_levels": info[3],
         "towards_levels": info[4], "launches_per_call": launches, "phases_ms": phases,
     }
-    w = min(a.oracle_window, n)
-    if w:
-        import oracle
-
-        hd, hf = dem[:w, :w].contiguous().cpu().numpy(), fdr0[:w, :w].contiguous().cpu().numpy()
-        t0 = time.perf_counter()
-        m, l = oracle.resolve_flats(hd, hf)
-        want = oracle.d8_masked_flow_dirs(m, hf, l)
-        t1 = time.perf_counter()
-        got = dev.fix_flats(torch.from_numpy(hd).cuda(), torch.from_numpy(hf).cuda())[0].cpu().numpy()
-        out["oracle_window"] = w
-        out["oracle_window_match"] = bool(np.array_equal(got, want))
-        out["cpu_oracle_gcells_s"] = w * w / (t1 - t0) / 1e9
     print(json.dumps(out))
 
 
