@@ -55,21 +55,25 @@ flat_edges_kernel(const float* __restrict__ dem, const uint8_t* __restrict__ fdr
     const int cur = fdr[i];
     const float z = dem[i];
     left_eq = c > 0 && dem[i - 1] == z;
+    // The two kinds exclude each other, so each cell runs one loop only, and the result does not depend on the
+    // order the neighbours are visited in.  A cell with a direction reads a neighbour's elevation only where
+    // that neighbour has none (rare outside flats); cells off the raster's ring skip the bounds checks.
+    const bool inner = r > 0 && r + 1 < rows && c > 0 && c + 1 < cols;
+    if (cur != FL_UNDEF) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int nr = r + c_dy[k], nc = c + c_dx[k];
-      if (nr < 0 || nr >= rows || nc < 0 || nc >= cols) continue;
-      const unsigned j = (unsigned)nr * (unsigned)cols + (unsigned)nc;
-      const int fn = fdr[j];
-      if (fn == FL_NODATA) continue;
-      const float zn = dem[j];
-      if (cur != FL_UNDEF && fn == FL_UNDEF && z == zn) {
-        flag = 1;
-        break;
+      for (int k = 0; k < 8; ++k) {
+        const int nr = r + c_dy[k], nc = c + c_dx[k];
+        if (!inner && (nr < 0 || nr >= rows || nc < 0 || nc >= cols)) continue;
+        const unsigned j = (unsigned)nr * (unsigned)cols + (unsigned)nc;
+        if (fdr[j] == FL_UNDEF && dem[j] == z) flag = 1;  // :45-53
       }
-      if (cur == FL_UNDEF && z < zn) {
-        flag = 2;
-        break;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int nr = r + c_dy[k], nc = c + c_dx[k];
+        if (!inner && (nr < 0 || nr >= rows || nc < 0 || nc >= cols)) continue;
+        const unsigned j = (unsigned)nr * (unsigned)cols + (unsigned)nc;
+        if (z < dem[j] && fdr[j] != FL_NODATA) flag = 2;  // :41-43, :54-60
       }
     }
     edges[i] = (uint8_t)flag;
@@ -506,10 +510,11 @@ __device__ __forceinline__ int masked_dir_of(int64_t i, const int* __restrict__ 
   const double fm = (double)flat_mask[i];
   int nmin = FL_UNDEF;
   double min_slope = CUDART_INF;
+  const bool inner = r > 0 && r + 1 < rows && c > 0 && c + 1 < cols;  // off the raster's ring: no bounds checks
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int nr = r + c_dy[k], nc = c + c_dx[k];
-    if (nr < 0 || nr >= rows || nc < 0 || nc >= cols) continue;
+    if (!inner && (nr < 0 || nr >= rows || nc < 0 || nc >= cols)) continue;
     const int64_t j = (int64_t)nr * cols + nc;
     if (labels[j] != lab) continue;
     const double dz = (double)flat_mask[j] - fm;
