@@ -19,4 +19,5 @@ from .oracle import (  # noqa: F401
     flat_edges,
     resolve_flats,
     d8_masked_flow_dirs,
+    breach_single_cell_pits_in_chunk,
 )

@@ -20,7 +20,7 @@ FLOW_TERMINATES = (-1, -1)
 
 def build(force=False):
     """Compile d8_oracle.c with the committed Makefile (gcc, OpenMP)."""
-    srcs = [os.path.join(_HERE, f) for f in ("d8_oracle.c", "flats_oracle.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("d8_oracle.c", "flats_oracle.c", "pits_oracle.c", "Makefile")]
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
     return _SO
@@ -46,6 +46,8 @@ def _load():
     lib.orc_check_accumulation.argtypes = [vp, i64, i64, i64, vp, i64]
     lib.orc_check_accumulation.restype = i64
     lib.orc_num_threads.restype = ctypes.c_int
+    lib.orc_breach_single_cell_pits_f32.argtypes = [vp, i64, i64, f64, vp]
+    lib.orc_breach_single_cell_pits_f32.restype = i64
     lib.orc_flat_edges_f32.argtypes = [vp, vp, i64, i64, vp, ctypes.POINTER(i64)]
     lib.orc_flat_edges_f32.restype = i64
     lib.orc_resolve_flats_f32.argtypes = [vp, vp, i64, i64, vp, vp]
@@ -193,3 +195,16 @@ def d8_masked_flow_dirs(flat_mask, fdr, labels):
     rows, cols = out.shape
     _load().orc_d8_masked_flow_dirs(fm.ctypes.data, out.ctypes.data, lb.ctypes.data, rows, cols)
     return out
+
+
+# ---------------------------------------------------------------- single-cell pit breaching (pits_oracle.c)
+def breach_single_cell_pits_in_chunk(chunk, nodata_value):
+    """Restates breach_single_cell_pits_in_chunk (reference breach_single_cell_pits.py:9-63) on a COPY:
+    returns (breached chunk float32, unsolved int8)."""
+    out = np.array(chunk, dtype=np.float32, order="C", copy=True)
+    if out.ndim != 2:
+        raise ValueError("chunk must be 2-D")
+    rows, cols = out.shape
+    unsolved = np.zeros((rows, cols), dtype=np.int8)
+    _load().orc_breach_single_cell_pits_f32(out.ctypes.data, rows, cols, float(nodata_value), unsolved.ctypes.data)
+    return out, unsolved
