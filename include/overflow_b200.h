@@ -20,6 +20,7 @@
  *   ofl_flat_gradient_i32         src/overflow/fix_flats.py:111-224  away_from_higher / towards_lower on their own
  *   ofl_d8_masked_flow_dirs_i32   src/overflow/fix_flats.py:291-339  d8_masked_flow_dirs
  *   ofl_fix_flats_f32             resolve_flats followed by d8_masked_flow_dirs, codes rewritten in place
+ *   ofl_breach_single_cell_pits_f32  src/overflow/breach_single_cell_pits.py:9-63  breach_single_cell_pits_in_chunk
  *   ofl_synth_dem_f32             no reference counterpart: seeded synthetic DEM for benchmarks
  *
  * Conventions
@@ -105,9 +106,9 @@ void ofl_launch_count_reset(void);
  *   0 direction kernel   1 accumulation tile pass A   2 perimeter-graph solve
  *   3 accumulation tile pass B   4 perimeter links   5 strip mode: pass B on the strip's first/last tile row
  *   6 flat resolution: the edge / masked-direction stencils   7 flat labelling (edges, components, label order)
- *   8 the two gradient sweeps of flat resolution
+ *   8 the two gradient sweeps of flat resolution   9 single-cell pit breaching
  */
-#define OFL_PHASE_COUNT 9
+#define OFL_PHASE_COUNT 10
 void ofl_phase_timing_enable(int on);
 int ofl_phase_timing_read(double* ms, int64_t* counts, int n, int reset);
 
@@ -234,6 +235,21 @@ int ofl_d8_masked_flow_dirs_i32(const int32_t* flat_mask, const int32_t* labels,
                                 int mem_kind, void* stream);
 int ofl_fix_flats_f32(const float* dem, uint8_t* fdr, int64_t rows, int64_t cols, int32_t* flat_mask, int32_t* labels,
                       int64_t* info, void* workspace, size_t workspace_bytes, int mem_kind, void* stream);
+
+/*
+ * Single-cell pit breaching (the reference's breach_single_cell_pits_in_chunk): `chunk` is breached IN PLACE, as in
+ * the reference; the two outermost rows and columns are the chunk's buffer and are only read.
+ *   chunk     float32, rows x cols, leading dimension ld_chunk (in and out)
+ *   nodata    the band nodata value as a double; a cell is nodata iff (double)cell == nodata
+ *   unsolved  int8 out, dense rows x cols: 1 where a single-cell pit could not be breached (the reference's result)
+ *   info      nullable int64[3] out: pits found, pits left unsolved, rounds of the dependency-ordered second pass
+ *   workspace device scratch of ofl_pits_workspace_bytes (NULL: library-owned, cached)
+ * One chunk of fewer than 2^31 cells.  Synchronises the stream.
+ */
+size_t ofl_pits_workspace_bytes(int64_t rows, int64_t cols);
+int ofl_breach_single_cell_pits_f32(float* chunk, int64_t rows, int64_t cols, int64_t ld_chunk, double nodata,
+                                    int8_t* unsolved, int64_t* info, void* workspace, size_t workspace_bytes, int mem_kind,
+                                    void* stream);
 
 /*
  * Seeded synthetic DEM written straight into device memory (benchmarks / large parity runs).

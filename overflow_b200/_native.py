@@ -62,6 +62,8 @@ SIGNATURES = {
     "ofl_flat_gradient_i32": (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _int, _vp, _vp, _i64, _vp, _sz, _int, _vp]),
     "ofl_d8_masked_flow_dirs_i32": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _vp]),
     "ofl_fix_flats_f32": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, ctypes.POINTER(_i64), _vp, _sz, _int, _vp]),
+    "ofl_pits_workspace_bytes": (_sz, [_i64, _i64]),
+    "ofl_breach_single_cell_pits_f32": (_int, [_vp, _i64, _i64, _i64, _f64, _vp, ctypes.POINTER(_i64), _vp, _sz, _int, _vp]),
     "ofl_synth_dem_f32": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, ctypes.c_uint64, _int, ctypes.c_float, _int,
                                  ctypes.c_float, _vp]),
 }
@@ -113,7 +115,7 @@ def launch_count_reset():
     lib().ofl_launch_count_reset()
 
 
-PHASES = ("direction", "acc_tile_a", "acc_solve", "acc_tile_b", "acc_links", "strip_edge", "flats_stencils", "flats_label", "flats_sweeps")
+PHASES = ("direction", "acc_tile_a", "acc_solve", "acc_tile_b", "acc_links", "strip_edge", "flats_stencils", "flats_label", "flats_sweeps", "breach_pits")
 
 
 def phase_timing_enable(on=True):

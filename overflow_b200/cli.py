@@ -1,11 +1,12 @@
 """Command line interface -- mirror of the reference's src/overflow_cli.py for the D8 path.
 
 `flow-direction` keeps the reference's options, messages and exit codes (overflow_cli.py:54-84);
-`flow-accumulation` and `flow-routing` (both steps, one pass over the device) are added with the same
-conventions (the reference snapshot has no such commands).
+`breach-single-cell-pits` likewise (overflow_cli.py:18-51); `flow-accumulation` and `flow-routing` (both steps, one
+pass over the device) are added with the same conventions (the reference snapshot has no such commands).
 """
 import click
 
+from .breach_single_cell_pits import breach_single_cell_pits
 from .constants import DEFAULT_CHUNK_SIZE
 from .flow_accumulation import flow_accumulation
 from .flow_direction import flow_direction
@@ -15,6 +16,19 @@ from .flow_routing import flow_routing
 @click.group()
 def main():
     """The main entry point for the command line interface."""
+
+
+@main.command(name="breach-single-cell-pits")
+@click.option("--input_file", help="path to the DEM file")
+@click.option("--output_file", help="path to the output file")
+@click.option("--chunk_size", help="chunk size", default=DEFAULT_CHUNK_SIZE)
+def breach_single_cell_pits_cli(input_file: str, output_file: str, chunk_size: int):
+    """Breach single cell pits in a DEM (reference overflow_cli.py:18-51)."""
+    try:
+        breach_single_cell_pits(input_file, output_file, chunk_size)
+    except Exception as exc:
+        print(f"breach_single_cell_pits failed with the following exception: {str(exc)}")
+        raise click.Abort()
 
 
 @main.command(name="flow-direction")

@@ -47,6 +47,9 @@ int launch_flat_gradient(const int* labels, const uint8_t* fdr, int64_t rows, in
                          void* workspace, size_t workspace_bytes, cudaStream_t st);
 int launch_masked_flow_dirs(const int* flat_mask, const int* labels, uint8_t* fdr, int64_t rows, int64_t cols,
                             cudaStream_t st);
+size_t pits_workspace_bytes(int64_t rows, int64_t cols);
+int launch_breach_pits(float* chunk, int64_t rows, int64_t cols, int64_t ld, double nodata, int8_t* unsolved,
+                       int64_t* info, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int launch_synth(float* dem, int64_t rows, int64_t cols, int64_t ld, int64_t row0, int64_t total_rows, uint64_t seed,
                  int kind, float relief, int holes_permille, float nodata, cudaStream_t st);
 }  // namespace ofl
@@ -526,6 +529,38 @@ int ofl_flat_gradient_i32(const int32_t* labels, const uint8_t* fdr, int64_t row
   if (rc != OFL_OK) return rc;
   OFL_CUDA(cudaMemcpyAsync(flat_mask, d_mask, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (n_heights) OFL_CUDA(cudaMemcpyAsync(flat_height, d_fh, (size_t)n_heights * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  OFL_CUDA(cudaStreamSynchronize(st));
+  return OFL_OK;
+}
+
+// ---------------------------------------------------------------- single-cell pit breaching (csrc/pits.cu)
+size_t ofl_pits_workspace_bytes(int64_t rows, int64_t cols) {
+  return (rows > 0 && cols > 0) ? pits_workspace_bytes(rows, cols) : 0;
+}
+
+int ofl_breach_single_cell_pits_f32(float* chunk, int64_t rows, int64_t cols, int64_t ld_chunk, double nodata,
+                                    int8_t* unsolved, int64_t* info, void* workspace, size_t workspace_bytes, int mem_kind,
+                                    void* stream) {
+  if (info) info[0] = info[1] = info[2] = 0;
+  OFL_FLATS_COMMON(chunk && unsolved);
+  OFL_REQUIRE(ld_chunk >= cols, OFL_ERR_INVALID, "leading dimension smaller than cols");
+  if (!workspace) {
+    workspace_bytes = pits_workspace_bytes(rows, cols);
+    if ((rc = scratch_get(SCRATCH_WORK, workspace_bytes, &workspace)) != OFL_OK) return rc;
+  }
+  if (mem_kind == OFL_MEM_DEVICE)
+    return launch_breach_pits(chunk, rows, cols, ld_chunk, nodata, unsolved, info, workspace, workspace_bytes, st);
+  void *d_chunk = nullptr, *d_uns = nullptr;
+  if ((rc = scratch_get(SCRATCH_DEM, n * sizeof(float), &d_chunk)) != OFL_OK) return rc;
+  if ((rc = scratch_get(SCRATCH_FDR, n, &d_uns)) != OFL_OK) return rc;
+  OFL_CUDA(cudaMemcpy2DAsync(d_chunk, cols * sizeof(float), chunk, ld_chunk * sizeof(float), cols * sizeof(float), rows,
+                             cudaMemcpyHostToDevice, st));
+  rc = launch_breach_pits(static_cast<float*>(d_chunk), rows, cols, cols, nodata, static_cast<int8_t*>(d_uns), info,
+                          workspace, workspace_bytes, st);
+  if (rc != OFL_OK) return rc;
+  OFL_CUDA(cudaMemcpy2DAsync(chunk, ld_chunk * sizeof(float), d_chunk, cols * sizeof(float), cols * sizeof(float), rows,
+                             cudaMemcpyDeviceToHost, st));
+  OFL_CUDA(cudaMemcpyAsync(unsolved, d_uns, n, cudaMemcpyDeviceToHost, st));
   OFL_CUDA(cudaStreamSynchronize(st));
   return OFL_OK;
 }

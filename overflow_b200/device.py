@@ -197,3 +197,25 @@ def fix_flats(dem: torch.Tensor, fdr: torch.Tensor, *, workspace=None, flat_mask
         )
     )
     return fdr, [int(v) for v in info]
+
+
+def breach_single_cell_pits(chunk: torch.Tensor, nodata_value: float, *, unsolved=None, workspace=None):
+    """Breach the single-cell pits of a float32 CUDA chunk in place (ofl_breach_single_cell_pits_f32).
+    Returns (unsolved int8 tensor, [pits found, pits left unsolved, rounds]).  Synchronises the stream."""
+    if chunk.dtype != torch.float32 or chunk.dim() != 2 or chunk.stride(1) != 1:
+        raise ValueError("chunk must be a 2-D float32 tensor with unit column stride")
+    _init_for(chunk)
+    rows, cols = chunk.shape
+    if unsolved is None:
+        unsolved = torch.empty((rows, cols), dtype=torch.int8, device=chunk.device)
+    if workspace is None:
+        nbytes = int(_native.lib().ofl_pits_workspace_bytes(rows, cols))
+        workspace = torch.empty((max(nbytes, 256),), dtype=torch.uint8, device=chunk.device)
+    info = (ctypes.c_int64 * 3)()
+    _native.check(
+        _native.lib().ofl_breach_single_cell_pits_f32(
+            chunk.data_ptr(), rows, cols, chunk.stride(0), float(nodata_value), unsolved.data_ptr(), info,
+            workspace.data_ptr(), workspace.numel(), _native.OFL_MEM_DEVICE, _stream(),
+        )
+    )
+    return unsolved, [int(v) for v in info]
