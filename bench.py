@@ -397,7 +397,7 @@ def run_native(args):
 
     # ---- SURVEY 8(f) row 2, reported next to the headline: flat resolution on a flat-heavy DEM (config 4 shape)
     if world == 1 and not args.no_flats:
-        line["next_rows"] = {"fix_flats": flats_leg(torch, dev, peak)}
+        line["next_rows"] = {"fix_flats": flats_leg(torch, dev, peak), "breach_single_cell_pits": pits_leg(torch, dev, peak)}
 
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -450,6 +450,49 @@ def flats_leg(torch, dev, peak, size=8192, window=1024):
         "parity": {"window": window, "codes_equal_oracle": bool(np.array_equal(got, want))},
         "cpu_baseline": {"value": window * window / cpu_s / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": f"{window}x{window} window of the same DEM (the reference algorithm is serial)"},
+    }
+
+
+def pits_leg(torch, dev, peak, size=16384, window=2048):
+    """ofl_breach_single_cell_pits_f32 on device buffers: fractal synthetic DEM, CUDA-event time of the call, a window
+    breached on its own and compared with the CPU oracle, and the oracle timed on that window."""
+    import numpy as np
+
+    import oracle
+
+    dem0 = dev.synth_dem(size, size, seed=3, kind=0, holes_permille=5)
+    dem = dem0.clone()
+    times, info = [], None
+    for it in range(4):
+        dem.copy_(dem0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _, info = dev.breach_single_cell_pits(dem, NODATA)
+        e1.record()
+        torch.cuda.synchronize()
+        if it:
+            times.append(e0.elapsed_time(e1))
+    ms = float(np.median(times))
+    cells = size * size
+    hw = dem0[:window, :window].contiguous().cpu().numpy()
+    t0 = time.perf_counter()
+    want, want_unsolved = oracle.breach_single_cell_pits_in_chunk(hw, NODATA)
+    cpu_s = time.perf_counter() - t0
+    d_w = torch.from_numpy(hw.copy()).cuda()
+    got_unsolved, _ = dev.breach_single_cell_pits(d_w, NODATA)
+    ok = bool(np.array_equal(d_w.cpu().numpy().view(np.uint32), want.view(np.uint32))
+              and np.array_equal(got_unsolved.cpu().numpy(), want_unsolved))
+    return {
+        "api": "ofl_breach_single_cell_pits_f32 on device buffers (reference breach_single_cell_pits_in_chunk)",
+        "workload": f"synthetic {size}x{size} float32 DEM (fractal value-noise, 5 permille nodata holes, seed 3)",
+        "ms": ms, "value": cells / ms / 1e6, "unit": UNIT, "pits": info[0], "unsolved": info[1], "rounds": info[2],
+        "roofline": {"bound": "hbm", "bytes_per_cell": 5.0, "achieved": cells * 5.0 / ms / 1e6, "peak": peak, "unit": "GB/s",
+                     "frac": cells * 5.0 / ms / 1e6 / peak,
+                     "note": "4 B DEM read + 1 B unsolved raster written per cell; breached cells (about 1 %) are rewritten in place"},
+        "parity": {"window": window, "bits_equal_oracle": ok},
+        "cpu_baseline": {"value": window * window / cpu_s / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{window}x{window} window of the same DEM (the reference's second pass is serial)"},
     }
 
 

@@ -48,3 +48,5 @@ def test_native_arm_line():
     ff = d["next_rows"]["fix_flats"]
     assert ff["parity"]["codes_equal_oracle"] and ff["value"] > 0 and ff["left_without_direction"] < ff["cells_without_direction"]
     assert {"value", "unit", "cores", "kind", "sample"} <= set(ff["cpu_baseline"])
+    bp = d["next_rows"]["breach_single_cell_pits"]
+    assert bp["parity"]["bits_equal_oracle"] and bp["value"] > 0 and bp["pits"] >= bp["unsolved"] >= 0
