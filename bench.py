@@ -133,6 +133,11 @@ def run_reference(args):
     import oracle
 
     oracle.build()
+    # every host thread this process may use, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for N > 1)
+    try:
+        oracle.set_num_threads(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        oracle.set_num_threads(os.cpu_count() or 1)
     sample = min(args.size, args.cpu_sample)
     dem_pad, how = sample_dem_host(args, sample)
     cells = sample * sample
