@@ -61,3 +61,27 @@ def test_label_flats_degenerate_starts():
     assert labels.tolist() == [[0, 0], [0, 7]]
     ff.label_flats(dem, labels, 9, 1, 1)  # already labelled: left alone
     assert labels[1, 1] == 7
+
+
+def test_pit_breaching_argument_checks():
+    """breach_single_cell_pits_in_chunk rejects what the device path does not implement before touching the library."""
+    from overflow.breach_single_cell_pits import breach_single_cell_pits, breach_single_cell_pits_in_chunk
+
+    assert callable(breach_single_cell_pits)
+    with pytest.raises(TypeError):
+        breach_single_cell_pits_in_chunk(np.zeros((8, 8), dtype=np.float64), -9999.0)
+    with pytest.raises(ValueError):
+        breach_single_cell_pits_in_chunk(np.zeros(8, dtype=np.float32), -9999.0)
+    with pytest.raises(ValueError):
+        breach_single_cell_pits_in_chunk([[1.0, 2.0]], -9999.0)
+    empty = np.zeros((0, 7), dtype=np.float32)  # nothing to do: no library call, an empty result
+    assert breach_single_cell_pits_in_chunk(empty, -9999.0).shape == (0, 7)
+
+
+def test_cli_exposes_the_reference_commands():
+    import overflow_cli
+
+    names = set(overflow_cli.main.commands)
+    assert {"breach-single-cell-pits", "flow-direction"} <= names  # reference overflow_cli.py:18, :54
+    opts = {p.name for p in overflow_cli.main.commands["breach-single-cell-pits"].params}
+    assert opts == {"input_file", "output_file", "chunk_size"}
