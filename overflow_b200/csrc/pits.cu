@@ -15,6 +15,8 @@
 //
 // Arithmetic as numba types it for a float32 chunk: float32 sum, float64 division by two, float32 store; the
 // NODATA test compares in float64.  Bit-exact against the reference (tests/golden/breach_pits.npz).
+#include <math_constants.h>
+
 #include "common.cuh"
 
 namespace ofl {
@@ -31,8 +33,8 @@ __constant__ int p_breach[16] = {0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 0}
 
 // pass 1 (:38-50): pits of the chunk as it came in -> unsolved = waiting = 1, index appended to the list
 __global__ void __launch_bounds__(PT)
-pits_detect_kernel(const float* __restrict__ chunk, int rows, int cols, int64_t ld, double nodata, int8_t* unsolved,
-                   uint8_t* waiting, int* list, unsigned* cnt) {
+pits_detect_kernel(const float* __restrict__ chunk, int rows, int cols, int64_t ld, float nd_f, bool nd_exact,
+                   int8_t* unsolved, uint8_t* waiting, int* list, unsigned* cnt) {
   __shared__ unsigned warp_off[PT / 32];
   __shared__ unsigned cta_base;
   const unsigned n = (unsigned)rows * (unsigned)cols;
@@ -43,14 +45,18 @@ pits_detect_kernel(const float* __restrict__ chunk, int rows, int cols, int64_t 
     if (r >= 2 && r < rows - 2 && c >= 2 && c < cols - 2) {
       const float* at = chunk + (int64_t)r * ld + c;
       const float z = *at;
-      if ((double)z != nodata) {
-        pit = true;
+      // Branch-free form of :40-50.  (double)x == nodata <=> x == (float)nodata when float32 holds nodata exactly,
+      // and never otherwise.  fminf skips NaN neighbours exactly as "zn <= z" is false for them; starting from NaN
+      // and testing "not (lowest <= z)" keeps the reference's answer when z or every neighbour is NaN.
+      float lowest = CUDART_NAN_F;
+      bool nodata_seen = false;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float zn = at[(int64_t)p_dy[k] * ld + p_dx[k]];
-          if (zn <= z || (double)zn == nodata) pit = false;
-        }
+      for (int k = 0; k < 8; ++k) {
+        const float zn = at[(int64_t)p_dy[k] * ld + p_dx[k]];
+        lowest = fminf(lowest, zn);
+        nodata_seen = nodata_seen || zn == nd_f;
       }
+      pit = !(nd_exact && (nodata_seen || z == nd_f)) && !(lowest <= z);
     }
     unsolved[i] = pit ? 1 : 0;
     waiting[i] = pit ? 1 : 0;
@@ -151,7 +157,9 @@ int launch_breach_pits(float* chunk, int64_t rows, int64_t cols, int64_t ld, dou
   PhaseScope ps(PHASE_PITS, st);
   OFL_CUDA(cudaMemsetAsync(cnt, 0, PC_SLOTS * sizeof(unsigned), st));
   const unsigned nb = (unsigned)((n + PT - 1) / PT);
-  pits_detect_kernel<<<nb, PT, 0, st>>>(chunk, (int)rows, (int)cols, ld, nodata, unsolved, waiting, list, cnt);
+  const float nd_f = (float)nodata;
+  const bool nd_exact = (double)nd_f == nodata;  // false for NaN and for values float32 cannot hold: nothing matches then
+  pits_detect_kernel<<<nb, PT, 0, st>>>(chunk, (int)rows, (int)cols, ld, nd_f, nd_exact, unsolved, waiting, list, cnt);
   OFL_CHECK_LAUNCH();
   pits_begin_kernel<<<1, 1, 0, st>>>(cnt);
   OFL_CHECK_LAUNCH();
