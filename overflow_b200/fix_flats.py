@@ -186,42 +186,25 @@ def label_flats(dem, labels, new_label, flat_row, flat_col) -> None:
     elev = dem[flat_row, flat_col]
     if not (elev == elev):
         return  # NaN never equals itself: the reference labels nothing
+    if labels[flat_row, flat_col] != 0:
+        return  # the reference pops the start cell, finds it labelled and stops
+    # the reference's flood does not pass through cells that already carry a label: they become NaN here, which
+    # equals nothing, so the device's equal-elevation components stop at them exactly like the flood does
+    taken = labels != 0
+    if bool(taken.any()):
+        dem = dem.copy()
+        dem[taken] = np.nan
     fdr = np.full(dem.shape, FLOW_DIRECTION_UNDEFINED, dtype=np.uint8)
     fdr[flat_row, flat_col] = 0
     r0, r1 = max(0, flat_row - 1), min(rows, flat_row + 2)
     c0, c1 = max(0, flat_col - 1), min(cols, flat_col + 2)
-    window = dem[r0:r1, c0:c1] == elev
-    if int(window.sum()) <= 1:
-        if labels[flat_row, flat_col] == 0:
-            labels[flat_row, flat_col] = new_label
+    if int((dem[r0:r1, c0:c1] == elev).sum()) <= 1:
+        labels[flat_row, flat_col] = new_label  # a flat of one cell: nothing to search
         return
     _, got = resolve_flats(dem, fdr)
-    member = got == got[flat_row, flat_col]
     if got[flat_row, flat_col] == 0:
         raise RuntimeError("label_flats: start cell was not labelled")
-    # the reference's flood stops at cells that already carry a label; cells behind them stay unreached
-    if bool(np.any(labels[member] != 0)):
-        member = _reachable(member & (labels == 0), flat_row, flat_col)
-    labels[member] = new_label
-
-
-def _reachable(mask, row, col):
-    """8-connected part of `mask` containing (row, col) -- only used when label_flats meets labelled cells."""
-    out = np.zeros_like(mask)
-    if not mask[row, col]:
-        return out
-    stack = [(row, col)]
-    out[row, col] = True
-    rows, cols = mask.shape
-    while stack:
-        r, c = stack.pop()
-        for dr in (-1, 0, 1):
-            for dc in (-1, 0, 1):
-                rr, cc = r + dr, c + dc
-                if 0 <= rr < rows and 0 <= cc < cols and mask[rr, cc] and not out[rr, cc]:
-                    out[rr, cc] = True
-                    stack.append((rr, cc))
-    return out
+    labels[got == got[flat_row, flat_col]] = new_label
 
 
 def fix_flats_for_tile(dem: np.ndarray, fdr: np.ndarray, return_mask: bool = False):

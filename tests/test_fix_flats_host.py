@@ -59,7 +59,7 @@ def test_label_flats_degenerate_starts():
     assert not labels.any()
     ff.label_flats(dem, labels, 7, 1, 1)  # a flat of one cell: no equal neighbour, no device work needed
     assert labels.tolist() == [[0, 0], [0, 7]]
-    ff.label_flats(dem, labels, 9, 1, 1)  # already labelled: left alone
+    ff.label_flats(dem, labels, 9, 1, 1)  # already labelled: the reference pops it and stops
     assert labels[1, 1] == 7
 
 

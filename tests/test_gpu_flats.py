@@ -58,6 +58,19 @@ def test_ref_label_flats():
     assert np.array_equal(labels, Z["kat__labels"].astype(np.uint32))
 
 
+def test_label_flats_stops_at_labelled_cells():
+    """The reference's flood (fix_flats.py:102-103) does not pass through cells that already carry a label."""
+    dem = np.zeros((6, 7), dtype=np.float32)
+    labels = np.zeros((6, 7), dtype=np.int32)
+    labels[:, 3] = 5  # a labelled column splits the one flat in two
+    ff().label_flats(dem, labels, 2, 2, 1)
+    assert (labels[:, :3] == 2).all() and (labels[:, 3] == 5).all() and (labels[:, 4:] == 0).all()
+    ff().label_flats(dem, labels, 9, 0, 3)  # start on a labelled cell: nothing happens
+    assert (labels[:, 3] == 5).all() and (labels[:, 4:] == 0).all()
+    ff().label_flats(dem, labels, 3, 5, 6)
+    assert (labels[:, 4:] == 3).all() and (labels[:, :3] == 2).all()
+
+
 def test_ref_away_from_higher():
     flat_mask = np.zeros((7, 7), dtype=np.int32)
     flat_height = np.zeros((1), dtype=np.int32)
