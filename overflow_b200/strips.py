@@ -234,3 +234,90 @@ def step_in_process(pipes):
     for p in pipes:
         p.boundary_solve()
         p.accum_final()
+
+
+# ---------------------------------------------------------------- out of core: strips through ONE device
+def strip_bounds(rows, strip_rows, tile=TILE):
+    """[(r0, r1)]: consecutive strips of `strip_rows` rows (a multiple of the tile side); the last takes the rest."""
+    strip_rows = int(strip_rows)
+    if strip_rows < tile or strip_rows % tile:
+        raise ValueError(f"strip_rows must be a positive multiple of {tile}, got {strip_rows}")
+    return [(r0, min(rows, r0 + strip_rows)) for r0 in range(0, rows, strip_rows)]
+
+
+def flow_accumulation_out_of_core(read_rows, write_rows, rows, cols, strip_rows, engine=None, device=None):
+    """Flow accumulation of a flow-direction raster that need not fit the device (full-width
+    tiles): the raster goes through ONE device strip by strip, twice, in the structure of Barnes 2016 that the
+    multi-GPU path uses across devices.
+
+        read_rows(r0, r1)  -> uint8 array [r1 - r0, cols] with the codes of those rows (any host source: an array,
+                              a memmap, a raster band)
+        write_rows(r0, fac)   receives the final int64 counts of rows r0 .. r0 + len(fac) (a host array it may keep)
+
+    Pass 1 solves every strip on its own and keeps only its boundary records (13 B per boundary cell); the boundary
+    graph of all strips is solved on the device; pass 2 solves each strip again (nothing of pass 1 is kept but the
+    records) and pushes the inflow from the other strips down before the counts leave.  Device memory: one strip
+    (codes, counts, workspace) plus 26 B x cols x strips of records.  The result equals the whole-raster
+    accumulation bit for bit (integer sums).  Returns the number of strips.
+    """
+    if engine is None:
+        engine = CudaStripEngine(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+    e = engine
+    bounds = strip_bounds(rows, strip_rows)
+    n = len(bounds)
+    h_max = max(r1 - r0 for r0, r1 in bounds)
+    fdr_halo = e.empty((h_max + 2, _round_up(cols, 16)), torch.uint8)[:, :cols]
+    fac = e.empty((h_max, cols), torch.int64)
+    ws = e.strip_workspace(h_max, cols)
+    slink_all, floc_all = e.empty((n, 2, cols), torch.int32), e.empty((n, 2, cols), torch.int64)
+    bcode_all, J_all = e.empty((n, 2, cols), torch.uint8), e.empty((n, 2, cols), torch.int64)
+    scratch = (e.empty((2, cols), torch.int32), e.empty((2, cols), torch.int64), e.empty((2, cols), torch.uint8))
+    bws = e.boundary_workspace(n, cols)
+
+    def load(s):
+        """Codes of strip s plus one halo row above and below (raster edges: the halo row is never looked at)."""
+        r0, r1 = bounds[s]
+        lo, hi = max(0, r0 - 1), min(rows, r1 + 1)
+        block = np.ascontiguousarray(read_rows(lo, hi), dtype=np.uint8)
+        if block.shape != (hi - lo, cols):
+            raise ValueError(f"read_rows({lo}, {hi}) returned shape {block.shape}, expected {(hi - lo, cols)}")
+        view = fdr_halo[: r1 - r0 + 2]
+        view[(lo - r0 + 1) : (hi - r0 + 1)].copy_(torch.from_numpy(block))
+        if lo == r0:
+            view[0].zero_()
+        if hi == r1:
+            view[-1].zero_()
+        return view, fac[: r1 - r0], s > 0, s < n - 1
+
+    for s in range(n):
+        view, f, above, below = load(s)
+        e.accum_local(view, above, below, f, ws, slink_all[s], floc_all[s], bcode_all[s])
+    e.boundary_solve(slink_all, floc_all, bcode_all, J_all, bws)
+    for s in range(n):
+        view, f, above, below = load(s)
+        e.accum_local(view, above, below, f, ws, *scratch)
+        e.accum_final(view, above, below, J_all[s], ws, f)
+        write_rows(bounds[s][0], f.cpu().numpy())
+    return n
+
+
+def flow_accumulation_file_out_of_core(input_path, output_path, strip_rows, engine=None, device=None):
+    """File-level form of flow_accumulation_out_of_core: band 1 of a flow-direction GeoTIFF in, a 1-band Int64
+    GeoTIFF out (same conventions as flow_accumulation.flow_accumulation), with the host holding one strip at a time."""
+    from .constants import FLOW_ACCUMULATION_NODATA
+    from .util import raster as _raster
+
+    src = _raster.open_raster(input_path)
+    band = src.GetRasterBand(1)
+    rows, cols = band.YSize, band.XSize
+    dst = _raster.create_raster(output_path, cols, rows, "Int64", projection=src.GetProjection(),
+                                geotransform=src.GetGeoTransform())
+    out_band = dst.GetRasterBand(1)
+    out_band.SetNoDataValue(FLOW_ACCUMULATION_NODATA)
+    n = flow_accumulation_out_of_core(
+        lambda r0, r1: band.ReadAsArray(xoff=0, yoff=r0, win_xsize=cols, win_ysize=r1 - r0),
+        lambda r0, fac: out_band.WriteArray(fac, xoff=0, yoff=r0),
+        rows, cols, strip_rows, engine=engine, device=device)
+    dst.FlushCache()
+    dst = None
+    return n

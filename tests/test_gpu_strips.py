@@ -88,3 +88,24 @@ def test_ragged_shapes_with_nodata_on_strip_boundaries(shape, world):
     fdr, fac = run_strips(dem, world)
     assert np.array_equal(fdr, want_fdr)
     assert np.array_equal(fac, want_fac)
+
+
+@pytest.mark.parametrize("name,dem", [c for c in cases() if c[0] in ("fractal_holes", "tilted_south", "serpentine")],
+                         ids=["fractal_holes", "tilted_south", "serpentine"])
+@pytest.mark.parametrize("strip_rows", [64, 192])
+def test_out_of_core_accumulation(name, dem, strip_rows):
+    """SURVEY 8f rank 3, full-width tiles: the raster goes through the device strip by strip, twice, and the counts
+    equal the whole-raster ones cell for cell."""
+    from overflow_b200 import strips
+
+    fdr = np.ascontiguousarray(oracle.flow_direction_for_tile(synth.pad_nodata(dem), synth.NODATA)[1:-1, 1:-1])
+    want = oracle.flow_accumulation(fdr)
+    got = np.full(fdr.shape, -7, dtype=np.int64)
+
+    def write_rows(r0, fac):
+        got[r0 : r0 + len(fac)] = fac
+
+    n = strips.flow_accumulation_out_of_core(lambda r0, r1: fdr[r0:r1], write_rows, fdr.shape[0], fdr.shape[1],
+                                             strip_rows, device="cuda:0")
+    assert n == -(-fdr.shape[0] // strip_rows)
+    assert np.array_equal(got, want)
