@@ -238,11 +238,15 @@ def step_in_process(pipes):
 
 # ---------------------------------------------------------------- out of core: strips through ONE device
 def strip_bounds(rows, strip_rows, tile=TILE):
-    """[(r0, r1)]: consecutive strips of `strip_rows` rows (a multiple of the tile side); the last takes the rest."""
+    """[(r0, r1)]: consecutive strips of `strip_rows` rows (a multiple of the tile side).  A remainder of less than
+    one tile row stays with the last strip (as in partition_rows: the library wants at least two rows per strip)."""
     strip_rows = int(strip_rows)
     if strip_rows < tile or strip_rows % tile:
         raise ValueError(f"strip_rows must be a positive multiple of {tile}, got {strip_rows}")
-    return [(r0, min(rows, r0 + strip_rows)) for r0 in range(0, rows, strip_rows)]
+    out = [(r0, min(rows, r0 + strip_rows)) for r0 in range(0, rows, strip_rows)]
+    if len(out) > 1 and out[-1][1] - out[-1][0] < tile:
+        out[-2:] = [(out[-2][0], rows)]
+    return out
 
 
 def flow_accumulation_out_of_core(read_rows, write_rows, rows, cols, strip_rows, engine=None, device=None):

@@ -107,5 +107,5 @@ def test_out_of_core_accumulation(name, dem, strip_rows):
 
     n = strips.flow_accumulation_out_of_core(lambda r0, r1: fdr[r0:r1], write_rows, fdr.shape[0], fdr.shape[1],
                                              strip_rows, device="cuda:0")
-    assert n == -(-fdr.shape[0] // strip_rows)
+    assert n == len(strips.strip_bounds(fdr.shape[0], strip_rows))
     assert np.array_equal(got, want)
