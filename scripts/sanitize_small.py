@@ -1,5 +1,7 @@
-"""Small end-to-end run for compute-sanitizer (memcheck / racecheck): KATs, one odd-shaped raster, 3 strips
-in-process, flat resolution, pit breaching, out-of-core strips."""
+"""Small end-to-end run over odd shapes (ragged warps, ragged four-byte words): KATs, one odd-shaped raster, 3 strips
+in-process, flat resolution, pit breaching, out-of-core strips, all against the oracle.  Written for
+compute-sanitizer; where that tool is closed on the GPU pool it runs as a plain small check (OFL_DEBUG_SYNC=1 names
+the kernel behind a fault)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
