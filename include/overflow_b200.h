@@ -11,6 +11,7 @@
  *   ofl_flow_accumulation_u8      src/overflow/flow_accumulation.py:95-158 single_tile_flow_accumulation
  *                                 (get_next_cell :13-37, perimeter_indices :40-51, follow_path :54-92)
  *   ofl_check_accumulation_u8     no reference counterpart: exactness check of the accumulation recurrence
+ *   ofl_strip_check_accumulation_u8  the same check on one row strip (halo codes, neighbour strips' boundary counts)
  *   ofl_strip_*                   no reference counterpart: row-strip (multi-GPU) decomposition in the
  *                                 structure of Barnes 2016 (arXiv 1608.04431), the paper cited at
  *                                 src/overflow/flow_accumulation.py:61,100
@@ -43,7 +44,7 @@
 extern "C" {
 #endif
 
-#define OFL_ABI_VERSION 1
+#define OFL_ABI_VERSION 2
 
 typedef enum ofl_status {
   OFL_OK = 0,
@@ -174,6 +175,16 @@ int ofl_flow_routing_f32(const float* dem, int64_t rows, int64_t cols, int64_t l
 int ofl_check_accumulation_u8(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, const int64_t* fac,
                               int64_t ld_fac, int64_t* n_bad, int mem_kind, void* stream);
 
+/*
+ * The same check on one row strip of a partitioned raster (device pointers).  fdr_halo carries one halo row
+ * above and below the strip's `rows` rows (as for ofl_strip_accum_local); fac_above / fac_below are the `cols`
+ * counts of the rows just outside the strip, owned by the neighbouring strips (null: the raster ends there).
+ * Zero violations on every strip prove the partitioned result exact.
+ */
+int ofl_strip_check_accumulation_u8(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr,
+                                    const int64_t* fac, int64_t ld_fac, const int64_t* fac_above,
+                                    const int64_t* fac_below, int64_t* n_bad, void* stream);
+
 /* Set the one-cell ring of a device uint8 raster to `value` (TILE mode helper for device callers). */
 int ofl_fill_border_u8(uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, int value, void* stream);
 
@@ -184,27 +195,38 @@ int ofl_fill_border_u8(uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr,
  * the strip below (contents ignored where has_above / has_below is 0: that side is the raster edge).
  * All pointers are DEVICE pointers; fdr_halo 16-byte aligned with ld_fdr % 16 == 0.
  *
- *   1. ofl_strip_accum_local     strip-local solve; writes the boundary records of the strip's first
- *                                (t=0) and last (t=1) row, each [2][cols]: slink (int32: (exit row selector
- *                                << 30) | exit column of the cell where the path leaves the strip, or -1),
- *                                floc (int64 strip-local count), bcode (uint8 direction code).
+ *   1. ofl_strip_accum_local     strip-local solve; writes the strip's boundary RECORD, one block of
+ *                                ofl_strip_record_bytes(cols) bytes describing the strip's first (t=0) and last
+ *                                (t=1) row: [2][cols] int64 strip-local counts, then [2][cols] int32 exit links
+ *                                ((exit row selector << 30) | exit column of the cell where the cell's path
+ *                                leaves the strip, or -1), then [2][cols] uint8 direction codes, zero padding.
  *                                `fac` (rows x cols) is used as scratch for the boundary rows.
- *   2. all-gather the three records over the strips in order (caller; NCCL)  -> [n_strips][2][cols]
+ *   2. all-gather the record blocks of the strips in order (caller; ONE NCCL all-gather)
+ *                                -> records_all, n_strips consecutive blocks
  *   3. ofl_strip_boundary_solve  same on every GPU: inflow from other strips into every boundary cell,
  *                                J_all [n_strips][2][cols] int64
  *   4. ofl_strip_accum_final     J_mine = J_all[this strip]; writes the final counts of the strip to `fac`
- * The strip workspace must be the same buffer in steps 1 and 4.  All four calls synchronise the stream.
+ *   5. ofl_strip_collect_flags   the error flags of 1-4 as int32[4] in device memory (stream-ordered):
+ *                                [0] tile pass, [1] strip solve, [2..3] the same for the boundary workspace;
+ *                                any non-zero value means the flow-direction raster holds a cycle
+ *                                (OFL_ERR_CYCLE).  Either workspace may be NULL (its flags read 0).
+ * The strip workspace must be the same buffer in steps 1, 4 and 5.  None of these calls synchronises: they
+ * enqueue work on `stream`, and the caller reads the flags once per step (after a MAX all-reduce over the
+ * ranks, so that every rank sees the same status).
  */
 size_t ofl_strip_workspace_bytes(int64_t rows, int64_t cols);
 size_t ofl_strip_boundary_workspace_bytes(int n_strips, int64_t cols);
+size_t ofl_strip_record_bytes(int64_t cols);
 int ofl_strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above,
                           int has_below, int64_t* fac, int64_t ld_fac, void* workspace, size_t workspace_bytes,
-                          int32_t* slink, int64_t* floc, uint8_t* bcode, void* stream);
-int ofl_strip_boundary_solve(const int32_t* slink_all, const int64_t* floc_all, const uint8_t* bcode_all, int n_strips,
-                             int64_t cols, int64_t* J_all, void* workspace, size_t workspace_bytes, void* stream);
+                          void* record, void* stream);
+int ofl_strip_boundary_solve(const void* records_all, int n_strips, int64_t cols, int64_t* J_all, void* workspace,
+                             size_t workspace_bytes, void* stream);
 int ofl_strip_accum_final(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above,
                           int has_below, const int64_t* J_mine, void* workspace, size_t workspace_bytes, int64_t* fac,
                           int64_t ld_fac, void* stream);
+int ofl_strip_collect_flags(const void* strip_workspace, int64_t rows, int64_t cols, const void* boundary_workspace,
+                            int n_strips, int32_t* flags, void* stream);
 
 /*
  * Flat resolution (Barnes, Lehman & Mulla 2014; the reference's src/overflow/fix_flats.py).  One tile of fewer
@@ -257,6 +279,8 @@ int ofl_breach_single_cell_pits_f32(float* chunk, int64_t rows, int64_t cols, in
  * row-strip run can synthesise its own strip and halo rows.
  *   kind 0: multi-octave value-noise fractal in [0, relief]   kind 1: same, quantised to 1.0 (terraces)
  *   kind 2: tilted plane draining south-east                   holes_permille: nodata rectangles
+ *   kind 3: walled serpentine, ONE channel of about rows * cols / 2 cells through the whole raster (every other
+ *           row, alternating east / west, consecutive float32 values walked downwards), walls draining into it
  */
 int ofl_synth_dem_f32(float* dem, int64_t rows, int64_t cols, int64_t ld_dem, int64_t row0, int64_t total_rows,
                       uint64_t seed, int kind, float relief, int holes_permille, float nodata, void* stream);

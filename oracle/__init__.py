@@ -20,4 +20,5 @@ from .oracle import (  # noqa: F401
     resolve_flats,
     d8_masked_flow_dirs,
     breach_single_cell_pits_in_chunk,
+    synth_dem,
 )

@@ -20,7 +20,7 @@ FLOW_TERMINATES = (-1, -1)
 
 def build(force=False):
     """Compile d8_oracle.c with the committed Makefile (gcc, OpenMP)."""
-    srcs = [os.path.join(_HERE, f) for f in ("d8_oracle.c", "flats_oracle.c", "pits_oracle.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("d8_oracle.c", "flats_oracle.c", "pits_oracle.c", "synth_host.c", "Makefile")]
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
     return _SO
@@ -55,6 +55,9 @@ def _load():
     lib.orc_d8_masked_flow_dirs.argtypes = [vp, vp, vp, i64, i64]
     lib.orc_d8_masked_flow_dirs.restype = None
     lib.orc_set_num_threads.argtypes = [ctypes.c_int]
+    lib.orc_synth_dem_f32.argtypes = [vp, i64, i64, i64, i64, i64, i64, i64, ctypes.c_uint64, ctypes.c_int,
+                                      ctypes.c_float, ctypes.c_int, ctypes.c_float]
+    lib.orc_synth_dem_f32.restype = None
     _lib = lib
     return lib
 
@@ -208,3 +211,16 @@ def breach_single_cell_pits_in_chunk(chunk, nodata_value):
     unsolved = np.zeros((rows, cols), dtype=np.int8)
     _load().orc_breach_single_cell_pits_f32(out.ctypes.data, rows, cols, float(nodata_value), unsolved.ctypes.data)
     return out, unsolved
+
+
+# ---------------------------------------------------------------- benchmark DEM on the host (synth_host.c)
+def synth_dem(rows, cols, row0=0, col0=0, total_rows=None, total_cols=None, seed=0, kind=0, relief=1000.0,
+              holes_permille=0, nodata=-9999.0):
+    """The DEM ofl_synth_dem_f32 generates on the device (overflow_b200/csrc/synth.cu), computed on the host
+    cores, bit for bit: rows row0 .. row0+rows and columns col0 .. col0+cols of the total raster."""
+    total_rows = rows if total_rows is None else total_rows
+    total_cols = cols if total_cols is None else total_cols
+    out = np.empty((rows, cols), dtype=np.float32)
+    _load().orc_synth_dem_f32(out.ctypes.data, rows, cols, cols, row0, col0, total_rows, total_cols, int(seed), int(kind),
+                              float(relief), int(holes_permille), float(nodata))
+    return out

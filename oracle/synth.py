@@ -158,3 +158,108 @@ FUZZ_KINDS = (
     "big_offset",
     "near_zero",
 )
+
+
+# --- host restatement of the device generator (overflow_b200/csrc/synth.cu) ---------------------------------
+# bench.py's reference arm and the parity windows need the benchmark DEM without mapping the CUDA library into
+# the process.  Every operation below is the float32 / uint32 operation the kernel performs, in its order (the
+# library is built with --fmad=false, so nothing is contracted): the arrays are bit-identical to the device's
+# (tests/test_gpu_synth.py).
+
+def _hash3(x, y, s):
+    with np.errstate(over="ignore"):
+        x = x.astype(np.uint32)
+        y = y.astype(np.uint32)
+        s = np.uint32(s & 0xFFFFFFFF)
+        h = (x * np.uint32(0x9E3779B1)) ^ (y * np.uint32(0x85EBCA77) + np.uint32(0x165667B1)) ^ (s * np.uint32(0xC2B2AE3D))
+        h ^= h >> np.uint32(15)
+        h *= np.uint32(0x2C1B3C6D)
+        h ^= h >> np.uint32(12)
+        h *= np.uint32(0x297A2D39)
+        h ^= h >> np.uint32(15)
+    return h
+
+
+def _lattice(ix, iy, s):
+    return (_hash3(ix, iy, s) >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+
+
+def _vnoise(fx, fy, s):
+    f32 = np.float32
+    flx, fly = np.floor(fx), np.floor(fy)
+    ix, iy = flx.astype(np.int64), fly.astype(np.int64)
+    tx, ty = fx - flx, fy - fly
+    tx = (tx * tx) * (f32(3.0) - f32(2.0) * tx)
+    ty = (ty * ty) * (f32(3.0) - f32(2.0) * ty)
+    a, b = _lattice(ix, iy, s), _lattice(ix + 1, iy, s)
+    c, d = _lattice(ix, iy + 1, s), _lattice(ix + 1, iy + 1, s)
+    top = a + (b - a) * tx
+    bot = c + (d - c) * tx
+    return top + (bot - top) * ty
+
+
+SERP_WALL = np.float32(3.0e38)
+SERP_ORD0 = 0x7EFFFFFF
+
+
+def serpentine_ulp(gr, gc, total_rows, total_cols):
+    """Elevations of the device's kind-3 DEM at global rows `gr` (column vector) and columns `gc` (row vector)."""
+    gr = np.asarray(gr, dtype=np.int64)
+    gc = np.asarray(gc, dtype=np.int64)
+    gr, gc = np.broadcast_arrays(gr, gc)
+    wc = total_cols - 2
+    n_runs = (total_rows - 1) // 2
+    odd = (gr & 1) == 1
+    m = np.where(odd, (gr - 1) >> 1, (gr >> 1) - 1)
+    west = (m & 1) == 1
+    pos = np.where(west, total_cols - 2 - gc, gc - 1)
+    k_run = m * (wc + 1) + pos
+    gap_col = np.where(west, 1, total_cols - 2)
+    is_gap = (~odd) & (m + 1 < n_runs) & (gc == gap_col)
+    k = np.where(odd, k_run, m * (wc + 1) + wc)
+    inside = (gr > 0) & (gr < total_rows - 1) & (gc > 0) & (gc < total_cols - 1)
+    chan = inside & (odd | is_gap)
+    ordv = SERP_ORD0 - k
+    bits = np.where(ordv >= 0, ordv, 0x80000000 | (-ordv)).astype(np.uint32)
+    z = bits.view(np.float32)
+    return np.where(chan, z, SERP_WALL).astype(np.float32)
+
+
+def device_dem(rows, cols, row0=0, col0=0, total_rows=None, total_cols=None, seed=0, kind=0, relief=1000.0,
+               holes_permille=0, nodata=NODATA):
+    """The DEM ofl_synth_dem_f32 writes (kind 0 fractal value noise, 1 terraces, 2 tilted plane, 3 serpentine),
+    rows row0 .. row0+rows and columns col0 .. col0+cols of a total_rows x total_cols raster, computed on the host."""
+    f32 = np.float32
+    total_rows = rows if total_rows is None else total_rows
+    total_cols = cols if total_cols is None else total_cols
+    gr = (row0 + np.arange(rows, dtype=np.int64))[:, None]
+    gc = (col0 + np.arange(cols, dtype=np.int64))[None, :]
+    seed32 = (seed ^ (seed >> 32)) & 0xFFFFFFFF
+    if kind == 2:
+        z = (total_rows - 1 - gr).astype(f32) + f32(0.25) * (total_cols - 1 - gc).astype(f32)
+        z = np.broadcast_to(z, (rows, cols)).astype(f32)
+    elif kind == 3:
+        z = serpentine_ulp(gr, gc, total_rows, total_cols)
+    else:
+        amp, norm, freq = f32(1.0), f32(0.0), f32(1.0 / 4096.0)
+        total = np.zeros((rows, cols), dtype=f32)
+        for o in range(12):
+            fx = np.broadcast_to(gc.astype(f32) * freq, (rows, cols))
+            fy = np.broadcast_to(gr.astype(f32) * freq, (rows, cols))
+            total = total + amp * _vnoise(fx, fy, (seed32 + 31 * o) & 0xFFFFFFFF)
+            norm = f32(norm + amp)
+            amp = f32(amp * f32(0.55))
+            freq = f32(freq * f32(2.0))
+        z = (f32(relief) * total) / norm
+        if kind == 1:
+            z = np.floor(z)
+        if holes_permille > 0:
+            hb = _hash3(np.broadcast_to(gc >> 8, (rows, cols)), np.broadcast_to(gr >> 8, (rows, cols)),
+                        seed32 ^ 0xA5A5A5A5)
+            is_hole = (hb % np.uint32(1000)).astype(np.int64) < holes_permille * 16
+            hx = ((hb >> np.uint32(10)) & np.uint32(127)).astype(np.int64)
+            hy = ((hb >> np.uint32(17)) & np.uint32(127)).astype(np.int64)
+            cx, cy = gc & 255, gr & 255
+            z = np.where(is_hole & (cx >= hx) & (cx < hx + 64) & (cy >= hy) & (cy < hy + 64), f32(nodata), z)
+    z = np.where((gr < 0) | (gr >= total_rows), f32(nodata), z)
+    return np.ascontiguousarray(z, dtype=f32)

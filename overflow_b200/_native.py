@@ -50,11 +50,14 @@ SIGNATURES = {
     "ofl_flow_accumulation_u8": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _sz, _int, _vp]),
     "ofl_flow_routing_f32": (_int, [_vp, _i64, _i64, _i64, _f64, _vp, _i64, _vp, _i64, _vp, _int, _vp]),
     "ofl_check_accumulation_u8": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, ctypes.POINTER(_i64), _int, _vp]),
+    "ofl_strip_check_accumulation_u8": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, ctypes.POINTER(_i64), _vp]),
     "ofl_fill_border_u8": (_int, [_vp, _i64, _i64, _i64, _int, _vp]),
     "ofl_strip_workspace_bytes": (_sz, [_i64, _i64]),
     "ofl_strip_boundary_workspace_bytes": (_sz, [_int, _i64]),
-    "ofl_strip_accum_local": (_int, [_vp, _i64, _i64, _i64, _int, _int, _vp, _i64, _vp, _sz, _vp, _vp, _vp, _vp]),
-    "ofl_strip_boundary_solve": (_int, [_vp, _vp, _vp, _int, _i64, _vp, _vp, _sz, _vp]),
+    "ofl_strip_record_bytes": (_sz, [_i64]),
+    "ofl_strip_accum_local": (_int, [_vp, _i64, _i64, _i64, _int, _int, _vp, _i64, _vp, _sz, _vp, _vp]),
+    "ofl_strip_boundary_solve": (_int, [_vp, _int, _i64, _vp, _vp, _sz, _vp]),
+    "ofl_strip_collect_flags": (_int, [_vp, _i64, _i64, _vp, _int, _vp, _vp]),
     "ofl_strip_accum_final": (_int, [_vp, _i64, _i64, _i64, _int, _int, _vp, _vp, _sz, _vp, _i64, _vp]),
     "ofl_flats_workspace_bytes": (_sz, [_i64, _i64]),
     "ofl_flat_edges_f32": (_int, [_vp, _vp, _i64, _i64, _vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64), _int, _vp]),

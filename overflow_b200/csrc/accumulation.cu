@@ -32,9 +32,6 @@
 // inside the raster and code(c) != 9.  Codes >= 8 have no downstream cell (the reference's
 // out-of-bounds NEIGHBOR_OFFSETS read); NODATA cells end at -9998 (:119-121,129-137).
 #include <cstdlib>
-#include <mutex>
-#include <type_traits>
-#include <vector>
 
 #include "common.cuh"
 
@@ -154,23 +151,28 @@ __device__ __forceinline__ int node_of_cell(int gy, int gx, const AccParams& p) 
 // ---------------------------------------------------------------- in-tile frontier propagation
 // Kahn's algorithm inside one 64x64 tile.  Every cell (plus a one-cell halo ring) owns one 32-bit word
 //
-//     [31 visited | 30..27 missing | 26 live | 25..8 count | 7..0 downstream offset]
+//     [31 unused | 30..27 missing | 26 live | 25..8 count | 7..0 downstream offset]
 //
 //   * offset   signed distance, in words, to the downstream cell's word (0: no downstream cell) -- a
 //              step along a flow path is one sign-extension and one scaled add, no table, no code load;
 //   * live     the cell is a data cell of this tile (code <= 8, inside the raster); halo and NODATA words
 //              have it clear, so they absorb hand-offs but are never scheduled;
 //   * missing  in-tile upstream neighbours that have not handed their count down yet;
-//   * count    running sum of the upstream counts (tile-local counts are <= 4096);
-//   * visited  set together with "missing = 15" when the cell is finished.
-// A finished cell hands its count to its downstream cell with ONE shared-memory atomic add of
-// (count << 8) - (1 << 27): it adds the count and decrements the missing field at once, and the value the
-// atomic returns tells the thread whether it was the last hand-off the downstream cell waited for -- and
-// already holds that cell's offset and running sum.  No edge is ever skipped: hand-offs into the halo,
-// into NODATA cells or out of the raster land in words nobody schedules.
-// Frontier levels are consecutive segments of one 4096-entry queue of word addresses (a cell is appended
-// once).  Halo words carry, in their offset byte, how a path that steps onto them continues (KIND_*).  A level never grows, so once it is down to TAIL_MAX cells one thread per cell simply follows its chain
-// (it continues exactly when its hand-off completed the next cell): no queue, no barriers.
+//   * count    running sum of the upstream counts, the cell itself NOT included (tile-local counts are
+//              <= 4096): the tile-local count of a finished cell is count + 1.
+// A cell whose missing field is 0 is complete; it hands (count + 1) to its downstream cell with ONE
+// shared-memory atomic add of ((count + 1) << 8) - (1 << 27): it adds the count and decrements the missing
+// field at once, and the value the atomic returns tells the thread whether it was the last hand-off the
+// downstream cell waited for -- and already holds that cell's offset and running sum.  Nothing is ever
+// written back to the cell's own word.  No edge is ever skipped: hand-offs into the halo, into NODATA cells
+// or out of the raster land in words nobody schedules.
+// Sources (cells without an in-tile upstream neighbour, more than half of a rough terrain) never enter a
+// queue: the lane that built their words hands their constant (1 << 8) - (1 << 27) down right after the
+// build.  The cells those hand-offs complete form level 1; from there on frontier levels are consecutive
+// segments of one queue of word addresses (a cell is appended once).  Halo words carry, in their offset
+// byte, how a path that steps onto them continues (KIND_*).  A level never grows, so once it is down to
+// TAIL_MAX cells one thread per cell simply follows its chain (it continues exactly when its hand-off
+// completed the next cell): no queue, no barriers.
 constexpr int WP = 72;                 // word-array pitch; cell x sits in column x + 4, so quads are 16-byte aligned
 constexpr int WX0 = 4;
 constexpr int WORDS = (AT + 2) * WP;   // rows y = -1..64
@@ -178,9 +180,9 @@ constexpr int QMAX = AT * AT;
 constexpr uint32_t W_CNT_ONE = 1u << 8;
 constexpr uint32_t W_LIVE = 1u << 26;
 constexpr uint32_t W_MISS_ONE = 1u << 27;
-constexpr uint32_t W_VISITED = 1u << 31;
-constexpr uint32_t W_FINISH = (W_VISITED | (0xFu << 27)) + W_CNT_ONE;       // ready word -> finished word (counts the cell itself)
-constexpr uint32_t W_HANDOFF_MASK = ~(W_LIVE | 0xFFu);               // finished word -> what its hand-off adds downstream
+constexpr uint32_t W_COUNT_MASK = 0x3FFFFu << 8;
+constexpr uint32_t W_HANDOFF_SELF = W_CNT_ONE - W_MISS_ONE;
+constexpr uint32_t W_UNFINISHED_TAB = 0xAAAAAAA8u;  // bit q = (missing << 1 | live) set: live with missing != 0  // a hand-off adds (word & W_COUNT_MASK) + this: the cell itself, one upstream less
 constexpr uint32_t W_READY_MASK = (0xFu << 27) | W_LIVE;     // hand-off result: the downstream cell is a live cell ...
 constexpr uint32_t W_READY_VAL = W_MISS_ONE | W_LIVE;        // ... and this was the hand-off it was waiting for
 // downstream word offsets per direction code E, NE, N, NW | W, SW, S, SE as signed bytes (PRMT lookup tables)
@@ -254,6 +256,16 @@ __device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v) {
   asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory");
   return o;
 }
+// predicated form: the atomic is issued only where `cond` is non-zero (no branch); returns 0 elsewhere
+__device__ __forceinline__ uint32_t atoms_add_if(uint32_t a, uint32_t v, uint32_t cond) {
+  uint32_t o;
+  asm volatile(
+      "{ .reg .pred p; setp.ne.u32 p, %3, 0; mov.u32 %0, 0; @p atom.shared.add.u32 %0, [%1], %2; }"
+      : "=r"(o)
+      : "r"(a), "r"(v), "r"(cond)
+      : "memory");
+  return o;
+}
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   uint32_t d;
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
@@ -282,7 +294,7 @@ __device__ __forceinline__ uint32_t word_next(uint32_t aw, uint32_t w) {
   return aw + (uint32_t)((int32_t)(int8_t)(w & 0xFFu) * 4);
 }
 
-__global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_constant__ CUtensorMap tm,
+__global__ void __launch_bounds__(ACC_THREADS, 8) acc_tile_kernel(const __grid_constant__ CUtensorMap tm,
                                                                 const AccParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   using SM = TileSmem;
@@ -410,8 +422,9 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     nm += bytes_differ(__funnelshift_r(C2, R2, 8), 0x03030303u);          // SE neighbour flowing NW
     const uint32_t cnt4 = 0x08080808u - nm;  // missing upstream neighbours per cell
     const uint32_t dead = C1 + 0x77777777u;  // bit 7 of a byte set: code >= 9, not a data cell
-    // source: missing == 0 and the cell is a data cell (own code <= 8)
-    srcs[i] = ~((cnt4 + 0x7F7F7F7Fu) | dead) & 0x80808080u;
+    // source with a downstream cell: missing == 0 and own code <= 7 (a source that flows nowhere, or out of
+    // nothing, needs no visit at all: nothing is ever written back to a finished cell)
+    srcs[i] = ~((cnt4 + 0x7F7F7F7Fu) | (C1 + 0x78787878u)) & 0x80808080u;
     // the four words: offsets by a byte-wise table lookup on the codes (codes >= 8 select in PRMT's
     // sign-replicate mode: code 8 -> sign of +1 -> 0 = no downstream; code >= 9 -> garbage in a word that
     // is never scheduled), top bytes [missing << 3 | live << 2]; one PRMT assembles each word
@@ -423,9 +436,24 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
   }
   __syncthreads();  // every word is built; the code tile is dead from here and the queue takes its place
 
-  // ---- sources into the queue: one exclusive scan of the per-lane source counts, one queue atomic per warp
+  // ---- sources: the lane that built a source's word hands its count (the cell itself) down -- a constant --
+  //      without a queue round trip; the cells those hand-offs complete are level 1 of the queue (one
+  //      exclusive scan of the per-lane counts, one queue atomic per warp)
   {
-    const uint32_t mine = __popc(srcs[0]) + __popc(srcs[1]) + __popc(srcs[2]) + __popc(srcs[3]);
+    uint32_t ready = 0;  // bit 4 * i + b: the hand-off of source (i, b) completed its downstream cell
+    uint32_t offs[4];    // the offset bytes of the lane's sixteen words (static; the other fields are live by now)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 wq = lds128(aw_lane + i * (2 * WP * 4));
+      offs[i] = prmt(prmt(wq.x, wq.y, 0x0040u), prmt(wq.z, wq.w, 0x0040u), 0x5410u);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const uint32_t an = aw_lane + i * (2 * WP * 4) + 4 * b + (uint32_t)((int32_t)(int8_t)(offs[i] >> (8 * b)) * 4);
+        const uint32_t old = atoms_add_if(an, W_HANDOFF_SELF, srcs[i] & (0x80u << (8 * b)));
+        ready |= ((old & W_READY_MASK) == W_READY_VAL ? 1u : 0u) << (4 * i + b);
+      }
+    }
+    const uint32_t mine = __popc(ready);
     uint32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -436,13 +464,13 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
     if (lane == 31) base = atoms_add(a_tail_v, incl);
     base = __shfl_sync(0xffffffffu, base, 31);
     uint32_t aq = a_q + 2 * (base + incl - mine);
-    const uint32_t qv = aw_lane;  // queue entries: 16-bit shared addresses (checked at kernel entry)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        if (srcs[i] & (0x80u << (8 * b))) {
-          sts16(aq, qv + i * (2 * WP * 4) + 4 * b);
+        if (ready & (1u << (4 * i + b))) {
+          // queue entries: 16-bit shared addresses (checked at kernel entry)
+          sts16(aq, aw_lane + i * (2 * WP * 4) + 4 * b + (uint32_t)((int32_t)(int8_t)(offs[i] >> (8 * b)) * 4));
           aq += 2;
         }
       }
@@ -511,17 +539,15 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
   // ---- wide levels: level k is q[lo, hi); processing it appends level k+1 right after it.  A warp takes
   //      WIDE_PER_LANE * 32 entries per turn and reserves queue slots for everything they complete with
   //      one atomic.  Queue entries are the 16-bit shared addresses of the words themselves.
-  const uint32_t n_src = lds32(a_tail);  // final: the level loop appends through the second counter
+  const uint32_t n_src = lds32(a_tail);  // level 1; final: the level loop appends through the second counter
   uint32_t lo = 0, hi = n_src;
-  // finish the cell whose word sits at `aw`; returns the hand-off's result (0: there was none) and the
-  // address of the downstream word
+  // the complete cell whose word sits at `aw` hands its count down; returns the hand-off's result (0: there
+  // was none) and the address of the downstream word
   auto visit = [&](uint32_t aw, uint32_t& an) -> uint32_t {
     const uint32_t wv = lds32(aw);
-    const uint32_t own = wv + W_FINISH;
-    sts32(aw, own);
     if (!(wv & 0xFFu)) return 0;
     an = word_next(aw, wv);
-    return atoms_add(an, own & W_HANDOFF_MASK);
+    return atoms_add(an, (wv & W_COUNT_MASK) + W_HANDOFF_SELF);
   };
   while (hi - lo > TAIL_MAX) {
     for (uint32_t base = lo + 32 * WIDE_PER_LANE * warp; base < hi; base += WIDE_PER_LANE * ACC_THREADS) {
@@ -566,16 +592,14 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
   }
   // ---- narrow tail (a level never grows): one thread per frontier cell follows its chain for as long
   //      as its hand-off is the one that completes the next cell; no queue, no barriers.  The atomic's
-  //      return value already is the next cell's word, so a step is one store and one atomic.
+  //      return value already is the next cell's word, so a step is one atomic.
   for (uint32_t i = lo + tid; i < hi; i += ACC_THREADS) {
     uint32_t aw = lds16(a_q + 2 * i);
     uint32_t wv = lds32(aw);
     for (;;) {
-      const uint32_t own = wv + W_FINISH;
-      sts32(aw, own);
       if (!(wv & 0xFFu)) break;
       aw = word_next(aw, wv);
-      const uint32_t add = own & W_HANDOFF_MASK;
+      const uint32_t add = (wv & W_COUNT_MASK) + W_HANDOFF_SELF;
       const uint32_t old = atoms_add(aw, add);
       if ((old & W_READY_MASK) != W_READY_VAL) break;
       wv = old + add;
@@ -638,20 +662,22 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_tile_kernel(const __grid_cons
   }
   __syncthreads();  // all chains are finished: counts are final
 
-  if (own_target >= 0) atomicAdd(&p.S[own_target], (unsigned long long)((lds32(a_own) >> 8) & 0x3FFFFu));
+  if (own_target >= 0) atomicAdd(&p.S[own_target], (unsigned long long)(((lds32(a_own) >> 8) & 0x3FFFFu) + 1u));
   // tile-local counts (<= 4096, fit 16 bits) for the final pass: tile-major, a warp stores 256 contiguous bytes
   uint2* Lt = reinterpret_cast<uint2*>(p.L + (size_t)tile * (AT * AT));
   uint32_t unfinished = 0;
 #pragma unroll
   for (int g = tid; g < AT * AT / 4; g += ACC_THREADS) {
     const uint4 v = lds128(a_word0 + ((g >> 4) * WP + (g & 15) * 4) * 4);
-    unfinished |= (~v.x >> 5) & v.x;  // bit 26: live and not visited
-    unfinished |= (~v.y >> 5) & v.y;
-    unfinished |= (~v.z >> 5) & v.z;
-    unfinished |= (~v.w >> 5) & v.w;
-    Lt[g] = make_uint2(prmt(v.x, v.y, 0x6521u), prmt(v.z, v.w, 0x6521u));
+    // bit 0: live and still missing an upstream hand-off -- a table lookup on the five bits [missing | live]
+    unfinished |= __funnelshift_r(W_UNFINISHED_TAB, W_UNFINISHED_TAB, v.x >> 26) |
+                  __funnelshift_r(W_UNFINISHED_TAB, W_UNFINISHED_TAB, v.y >> 26);
+    unfinished |= __funnelshift_r(W_UNFINISHED_TAB, W_UNFINISHED_TAB, v.z >> 26) |
+                  __funnelshift_r(W_UNFINISHED_TAB, W_UNFINISHED_TAB, v.w >> 26);
+    // tile-local count = running sum + the cell itself (no carry between the halves: sums stay below 2^16)
+    Lt[g] = make_uint2(prmt(v.x, v.y, 0x6521u) + 0x00010001u, prmt(v.z, v.w, 0x6521u) + 0x00010001u);
   }
-  if (unfinished & W_LIVE) atomicExch(p.err, 1);  // a cell never completed: the raster holds a cycle
+  if (unfinished & 1u) atomicExch(p.err, 1);  // a cell never completed: the raster holds a cycle
 }
 
 // ---------------------------------------------------------------- final pass
@@ -866,95 +892,136 @@ __device__ __forceinline__ void block_append(int32_t* seg_list, int* s_counter, 
   }
 }
 
-// counts layout: [round][2][blocks] ints; round r's input counts are written by round r-1 (r = 0: init)
-// Also zeroes the delta-buffer entries of the active nodes: deltas are only ever written for a node that
-// still has a pointer to jump along, i.e. one that starts out active, so the rest need no clearing.
-__global__ void pj_init_kernel(const int32_t* __restrict__ succ, int32_t* __restrict__ ptr_a, int32_t* __restrict__ ptr_b,
-                               int32_t* __restrict__ list0, int* __restrict__ counts0, unsigned long long* __restrict__ d0,
-                               unsigned long long* __restrict__ d1, PjSeg g) {
-  __shared__ int s_cnt;
-  if (threadIdx.x == 0) s_cnt = 0;
-  __syncthreads();
-  const int64_t base = (int64_t)blockIdx.x * g.seg;
-  const int64_t len = min(g.seg, g.n - base);
-  for (int64_t i = threadIdx.x; i < g.seg; i += blockDim.x) {  // whole warps stay together for the ballots
-    bool active = false;
-    const int64_t u = base + i;
-    if (i < len) {
-      const int32_t sc = succ[u];
-      active = sc >= 0;
-      if (active) {
-        ptr_a[u] = sc;
-        d0[u] = 0;
-        d1[u] = 0;
-      } else {
-        ptr_a[u] = ~(int32_t)u;
-        ptr_b[u] = ~(int32_t)u;
-      }
-    }
-    block_append(list0 + base, &s_cnt, active, (int32_t)u, false, g.seg);
-  }
+// One persistent kernel runs every round (cooperative launch: all CTAs are resident, one per segment); a
+// grid-wide barrier separates the rounds and carries the number of nodes still active or just retired, so the
+// kernel ends after the round that finds none -- O(log depth) rounds instead of the O(log n) a fixed
+// sequence of launches has to provide for, and no launch latency between them (on a strip of an 8-GPU run
+// a round is a few microseconds of work).  Everything other CTAs write between barriers is read with
+// ld.global.cg (L2), never through L1.
+struct PjArgs {
+  const int32_t* succ;   // with_init: the forest (succ[u] = parent or -1)
+  int32_t *ptr_a, *ptr_b;
+  int32_t* lists;        // 2 ping-pong lists of blocks * seg entries
+  const int* counts0;    // !with_init: [blocks] active nodes per segment, published by pass A
+  unsigned long long *S, *d0, *d1;
+  unsigned* sync;        // [0] barrier counter, [2 + j] nodes left after round j; zeroed before the launch
+  int* leftover;         // set when max_rounds did not suffice: the forest has a cycle
+  PjSeg g;
+  int with_init, max_rounds;
+};
+
+__device__ __forceinline__ void pj_grid_barrier(unsigned* counter, unsigned& generation) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    counts0[blockIdx.x] = s_cnt;
-    counts0[g.blocks + blockIdx.x] = 0;
+    ++generation;
+    const unsigned target = generation * gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (*reinterpret_cast<volatile unsigned*>(counter) < target) {
+    }
+    __threadfence();
   }
+  __syncthreads();
 }
 
-__global__ void pj_round_kernel(const int32_t* __restrict__ list_in, int32_t* __restrict__ list_out,
-                                const int* __restrict__ cnt_in, int* __restrict__ cnt_out,
-                                const int32_t* __restrict__ ptr_in, int32_t* __restrict__ ptr_out,
-                                unsigned long long* __restrict__ S, unsigned long long* __restrict__ d_prev,
-                                unsigned long long* __restrict__ d_next, PjSeg g) {
+__global__ void __launch_bounds__(256, 8) pj_solve_kernel(const PjArgs a) {
   __shared__ int s_keep, s_ret;
-  const int n_active = cnt_in[blockIdx.x], n_retired = cnt_in[g.blocks + blockIdx.x];
+  const PjSeg g = a.g;
+  const int64_t base = (int64_t)blockIdx.x * g.seg;
+  int32_t* const list0 = a.lists + base;
+  int32_t* const list1 = a.lists + (int64_t)g.blocks * g.seg + base;
+  unsigned generation = 0;
+  int n_active, n_retired = 0;
   if (threadIdx.x == 0) {
     s_keep = 0;
     s_ret = 0;
   }
   __syncthreads();
-  const int64_t base = (int64_t)blockIdx.x * g.seg;
-  const int32_t* in = list_in + base;
-  int32_t* out = list_out + base;
-  // nodes retired by the previous round: make their root visible in this round's output buffer too
-  for (int i = threadIdx.x; i < n_retired; i += blockDim.x) {
-    const int32_t w = in[g.seg - 1 - i];
-    ptr_out[w] = ptr_in[w];
-    const unsigned long long dp = d_prev[w];  // what it received during the round it retired in
-    if (dp) {
-      atomicAdd(&S[w], dp);
-      d_prev[w] = 0;
+  if (a.with_init) {
+    // the active nodes of this segment, their pointers, and cleared delta entries: deltas are only ever
+    // written for a node that still has a pointer to jump along, i.e. one that starts out active
+    const int64_t len = min(g.seg, g.n - base);
+    for (int64_t i = threadIdx.x; i < g.seg; i += blockDim.x) {  // whole warps stay together for the ballots
+      bool active = false;
+      const int64_t u = base + i;
+      if (i < len) {
+        const int32_t sc = a.succ[u];
+        active = sc >= 0;
+        if (active) {
+          a.ptr_a[u] = sc;
+          a.d0[u] = 0;
+          a.d1[u] = 0;
+        } else {
+          a.ptr_a[u] = ~(int32_t)u;
+          a.ptr_b[u] = ~(int32_t)u;
+        }
+      }
+      block_append(list0, &s_keep, active, (int32_t)u, false, g.seg);
     }
+    pj_grid_barrier(a.sync, generation);  // round 0 reads other segments' pointers
+    n_active = s_keep;
+  } else {
+    n_active = a.counts0[blockIdx.x];
   }
-  const int n_up = (n_active + 31) / 32 * 32;
-  for (int i = threadIdx.x; i < n_up; i += blockDim.x) {
-    bool keep = false, retire = false;
-    int32_t w = 0;
-    if (i < n_active) {
-      w = in[i];
-      unsigned long long s = S[w];
-      const unsigned long long dp = d_prev[w];
+  for (int j = 0;; ++j) {
+    const int32_t* in = (j & 1) ? list1 : list0;
+    int32_t* out = (j & 1) ? list0 : list1;
+    const int32_t* ptr_in = (j & 1) ? a.ptr_b : a.ptr_a;
+    int32_t* ptr_out = (j & 1) ? a.ptr_a : a.ptr_b;
+    unsigned long long* d_prev = (j & 1) ? a.d1 : a.d0;
+    unsigned long long* d_next = (j & 1) ? a.d0 : a.d1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s_keep = 0;
+      s_ret = 0;
+    }
+    __syncthreads();
+    // nodes retired by the previous round: make their root visible in this round's output buffer too
+    for (int i = threadIdx.x; i < n_retired; i += blockDim.x) {
+      const int32_t w = __ldcg(&in[g.seg - 1 - i]);
+      ptr_out[w] = __ldcg(&ptr_in[w]);
+      const unsigned long long dp = __ldcg(&d_prev[w]);  // what it received during the round it retired in
       if (dp) {
-        s += dp;
-        S[w] = s;
+        atomicAdd(&a.S[w], dp);
         d_prev[w] = 0;
       }
-      const int32_t a = ptr_in[w];
-      const int32_t q = ptr_in[a];
-      // an ancestor that still jumps forwards what it receives next round (delta buffer); one whose
-      // chain is exhausted never forwards again, so its sum takes the contribution directly
-      if (s) atomicAdd(q >= 0 ? &d_next[a] : &S[a], s);
-      ptr_out[w] = q;
-      keep = q >= 0;
-      retire = !keep;
     }
-    block_append(out, &s_keep, keep, w, false, g.seg);
-    block_append(out, &s_ret, retire, w, true, g.seg);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    cnt_out[blockIdx.x] = s_keep;
-    cnt_out[g.blocks + blockIdx.x] = s_ret;
+    const int n_up = (n_active + 31) / 32 * 32;
+    for (int i = threadIdx.x; i < n_up; i += blockDim.x) {
+      bool keep = false, retire = false;
+      int32_t w = 0;
+      if (i < n_active) {
+        w = __ldcg(&in[i]);
+        unsigned long long sum = __ldcg(&a.S[w]);
+        const unsigned long long dp = __ldcg(&d_prev[w]);
+        if (dp) {
+          sum += dp;
+          a.S[w] = sum;
+          d_prev[w] = 0;
+        }
+        const int32_t anc = __ldcg(&ptr_in[w]);
+        const int32_t q = __ldcg(&ptr_in[anc]);
+        // an ancestor that still jumps forwards what it receives next round (delta buffer); one whose
+        // chain is exhausted never forwards again, so its sum takes the contribution directly
+        if (sum) atomicAdd(q >= 0 ? &d_next[anc] : &a.S[anc], sum);
+        ptr_out[w] = q;
+        keep = q >= 0;
+        retire = !keep;
+      }
+      block_append(out, &s_keep, keep, w, false, g.seg);
+      block_append(out, &s_ret, retire, w, true, g.seg);
+    }
+    __syncthreads();
+    n_active = s_keep;
+    n_retired = s_ret;
+    if (threadIdx.x == 0 && n_active + n_retired) atomicAdd(&a.sync[2 + j], (unsigned)(n_active + n_retired));
+    pj_grid_barrier(a.sync, generation);
+    const unsigned left = *reinterpret_cast<volatile unsigned*>(&a.sync[2 + j]);
+    if (left == 0) break;  // nothing active and the last retirees' roots and deltas are in place
+    if (j + 1 >= a.max_rounds) {
+      if (threadIdx.x == 0 && n_active) *a.leftover = 1;
+      break;
+    }
   }
 }
 
@@ -963,13 +1030,6 @@ __global__ void pj_add_kernel(unsigned long long* __restrict__ S, const unsigned
     const unsigned long long d = S2[u];
     if (d) S[u] += d;
   }
-}
-
-// after the last round: any segment with active nodes left means the forest has a cycle
-__global__ void pj_leftover_kernel(const int* __restrict__ cnt, int blocks, int* __restrict__ leftover) {
-  int any = 0;
-  for (int i = threadIdx.x; i < blocks; i += blockDim.x) any |= cnt[i] != 0;
-  if (__syncthreads_or(any) && threadIdx.x == 0) *leftover = 1;
 }
 
 // ---------------------------------------------------------------- links for the raster perimeter
@@ -1021,13 +1081,16 @@ __global__ void links_kernel(const uint8_t* __restrict__ fdr, int64_t ld_fdr, co
 }
 
 // ---------------------------------------------------------------- recurrence checker
+// Row-strip form: the code raster carries y_off halo rows above row 0 (and below the last row) and the counts
+// of the rows just outside the strip come as separate rows (null: the raster ends there).
 __global__ void check_kernel(const uint8_t* __restrict__ fdr, int64_t ld_fdr, const long long* __restrict__ fac,
-                             int64_t ld_fac, int rows, int cols, unsigned long long* __restrict__ n_bad) {
+                             int64_t ld_fac, int rows, int cols, int y_off, const long long* __restrict__ fac_above,
+                             const long long* __restrict__ fac_below, unsigned long long* __restrict__ n_bad) {
   const int64_t n = (int64_t)rows * cols;
   unsigned long long bad = 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
-    const int code = fdr[(int64_t)r * ld_fdr + c];
+    const int code = fdr[(int64_t)(r + y_off) * ld_fdr + c];
     long long want;
     if (code == OFL_DIR_NODATA) {
       want = OFL_FAC_NODATA_EMITTED;
@@ -1036,8 +1099,18 @@ __global__ void check_kernel(const uint8_t* __restrict__ fdr, int64_t ld_fdr, co
 #pragma unroll
       for (int d = 0; d < 8; ++d) {
         const int ur = r + dir_dy(d), uc = c + dir_dx(d);
-        if (ur < 0 || ur >= rows || uc < 0 || uc >= cols) continue;
-        if (fdr[(int64_t)ur * ld_fdr + uc] == ((d + 4) & 7)) want += fac[(int64_t)ur * ld_fac + uc];
+        if (uc < 0 || uc >= cols) continue;
+        const long long* urow;
+        if (ur < 0) {
+          if (!fac_above) continue;
+          urow = fac_above;
+        } else if (ur >= rows) {
+          if (!fac_below) continue;
+          urow = fac_below;
+        } else {
+          urow = fac + (int64_t)ur * ld_fac;
+        }
+        if (fdr[(int64_t)(ur + y_off) * ld_fdr + uc] == ((d + 4) & 7)) want += urow[uc];
       }
     }
     bad += (fac[(int64_t)r * ld_fac + c] != want);
@@ -1082,115 +1155,62 @@ static int pj_rounds_for(int64_t n) {
   return r + 1;  // one more round copies the last retirees' roots into both pointer buffers
 }
 
+// CTAs of pj_solve_kernel that are resident at once on the current device (the kernel is launched
+// cooperatively with one CTA per segment).
+static int pj_max_blocks() {
+  static int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (cached[dev] == 0) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pj_solve_kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    cached[dev] = per_sm * sm_count();
+  }
+  return cached[dev];
+}
+constexpr int PJ_MAX_BLOCKS = 8 * 256;  // counts0 holds this many segments (8 CTAs on each of up to 256 SMs)
+
 static PjSeg pj_segments(int64_t n) {
   PjSeg g;
   g.n = n;
   int64_t blocks = (n + 2047) / 2048;  // at least 2048 nodes per segment
-  const int64_t cap = (int64_t)sm_count() * 8;
+  int64_t cap = pj_max_blocks();
+  if (cap > PJ_MAX_BLOCKS) cap = PJ_MAX_BLOCKS;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   g.seg = ((n + blocks - 1) / blocks + SLOTS - 1) / SLOTS * SLOTS;  // whole tiles (pass A appends to the lists per tile)
   g.blocks = (int)((n + g.seg - 1) / g.seg);
   return g;
 }
-constexpr int PJ_MAX_BLOCKS = 148 * 8 * 2;  // counts are sized for this many segments
 
 // Subtree sums over the forest `succ` (succ[u] = parent node or -1): on return (stream order) S[u] holds
-// the sum of the initial S over u's subtree and ptr_a holds ~root(u) for every node.  succ is preserved.
-// lists: 2 * (blocks * seg) int32; counts: (PJ_MAX_ROUNDS + 2) * 2 * blocks ints; d0/d1 need no initialisation.
-// Does not synchronise: *leftover is set when the forest did not converge (a cycle).
-static int pj_solve_launch(const int32_t* succ, int32_t* ptr_a, int32_t* ptr_b, int32_t* lists, int* counts,
-                           int* leftover, unsigned long long* S, unsigned long long* d0, unsigned long long* d1, int64_t n,
-                           bool with_init, cudaStream_t st, int* n_kernels) {
-  const PjSeg g = pj_segments(n);
-  OFL_REQUIRE(g.blocks <= PJ_MAX_BLOCKS, OFL_ERR_INVALID, "device has too many SMs for the solve's counter table");
-  const int rounds = pj_rounds_for(n);
-  int32_t* list[2] = {lists, lists + (int64_t)g.blocks * g.seg};
-  const int cstride = 2 * g.blocks;
-  if (with_init) {
-    pj_init_kernel<<<g.blocks, 256, 0, st>>>(succ, ptr_a, ptr_b, list[0], counts, d0, d1, g);
-    OFL_CUDA(cudaGetLastError());
-  }
-  int32_t* cur = ptr_a;
-  int32_t* nxt = ptr_b;
-  for (int j = 0; j < rounds; ++j) {
-    pj_round_kernel<<<g.blocks, 256, 0, st>>>(list[j & 1], list[(j + 1) & 1], counts + (int64_t)j * cstride,
-                                              counts + (int64_t)(j + 1) * cstride, cur, nxt, S, (j & 1) ? d1 : d0,
-                                              (j & 1) ? d0 : d1, g);
-    OFL_CUDA(cudaGetLastError());
-    int32_t* t = cur;
-    cur = nxt;
-    nxt = t;
-  }
-  pj_leftover_kernel<<<1, 256, 0, st>>>(counts + (int64_t)rounds * cstride, g.blocks, leftover);
-  OFL_CUDA(cudaGetLastError());
-  *n_kernels = rounds + 1 + (with_init ? 1 : 0);
-  return OFL_OK;
-}
-
-// The solve is a fixed sequence of ~30 small kernels whose arguments depend only on the workspace
-// addresses and the node count, and on a strip of an 8-GPU run they finish faster than the host can
-// launch them.  It is therefore captured once per (addresses, n) into a CUDA graph and replayed.
-struct PjGraphKey {
-  const void *succ, *pa, *pb, *lists, *counts, *leftover, *S, *d0, *d1;
-  int64_t n;
-  int device;
-  bool with_init;
-  bool operator==(const PjGraphKey& o) const {
-    return with_init == o.with_init && succ == o.succ && pa == o.pa && pb == o.pb && lists == o.lists && counts == o.counts && leftover == o.leftover &&
-           S == o.S && d0 == o.d0 && d1 == o.d1 && n == o.n && device == o.device;
-  }
-};
-struct PjGraphEntry {
-  PjGraphKey key;
-  cudaGraphExec_t exec;
-  int n_kernels;
-};
-static std::mutex g_pj_mu;
-static std::vector<PjGraphEntry> g_pj_graphs;
-static cudaStream_t g_pj_capture_stream = nullptr;  // capture is not allowed on the legacy default stream
-
-// with_init = false: the caller (pass A) has already published pointers, delta entries, list 0 and counts 0.
+// the sum of the initial S over u's subtree and both pointer buffers hold ~root(u) for every node.  succ is
+// preserved.  lists: 2 * (blocks * seg) int32; counts: [0, PJ_MAX_BLOCKS) the per-segment active counts when
+// pass A published the initial state (with_init = false), then the kernel's barrier words; d0/d1 need no
+// initialisation.  Does not synchronise: *leftover is set when the forest did not converge (a cycle).
 static int pj_solve(const int32_t* succ, int32_t* ptr_a, int32_t* ptr_b, int32_t* lists, int* counts, int* leftover,
                     unsigned long long* S, unsigned long long* d0, unsigned long long* d1, int64_t n, cudaStream_t st,
                     bool with_init = true) {
-  int n_kernels = 0;
-  if (getenv("OFL_NO_GRAPHS")) {
-    const int rc = pj_solve_launch(succ, ptr_a, ptr_b, lists, counts, leftover, S, d0, d1, n, with_init, st, &n_kernels);
-    if (rc == OFL_OK) count_launch(n_kernels);
-    return rc;
-  }
-  PjGraphKey key{succ, ptr_a, ptr_b, lists, counts, leftover, S, d0, d1, n, 0, with_init};
-  OFL_CUDA(cudaGetDevice(&key.device));
-  std::lock_guard<std::mutex> lk(g_pj_mu);
-  PjGraphEntry* hit = nullptr;
-  for (auto& e : g_pj_graphs)
-    if (e.key == key) hit = &e;
-  if (!hit) {
-    if (g_pj_graphs.size() >= 32) {  // workspaces come and go: start over rather than grow without bound
-      for (auto& e : g_pj_graphs) cudaGraphExecDestroy(e.exec);
-      g_pj_graphs.clear();
-    }
-    if (!g_pj_capture_stream) OFL_CUDA(cudaStreamCreateWithFlags(&g_pj_capture_stream, cudaStreamNonBlocking));
-    cudaGraph_t graph = nullptr;
-    OFL_CUDA(cudaStreamBeginCapture(g_pj_capture_stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = pj_solve_launch(succ, ptr_a, ptr_b, lists, counts, leftover, S, d0, d1, n, with_init, g_pj_capture_stream,
-                                   &n_kernels);
-    const cudaError_t ce = cudaStreamEndCapture(g_pj_capture_stream, &graph);
-    if (rc != OFL_OK) {
-      if (graph) cudaGraphDestroy(graph);
-      return rc;
-    }
-    OFL_CUDA(ce);
-    cudaGraphExec_t exec = nullptr;
-    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
-    cudaGraphDestroy(graph);
-    OFL_CUDA(ie);
-    g_pj_graphs.push_back(PjGraphEntry{key, exec, n_kernels});
-    hit = &g_pj_graphs.back();
-  }
-  OFL_CUDA(cudaGraphLaunch(hit->exec, st));
-  count_launch(hit->n_kernels);
+  PjArgs a;
+  a.succ = succ;
+  a.ptr_a = ptr_a;
+  a.ptr_b = ptr_b;
+  a.lists = lists;
+  a.counts0 = counts;
+  a.S = S;
+  a.d0 = d0;
+  a.d1 = d1;
+  a.sync = reinterpret_cast<unsigned*>(counts + 2 * PJ_MAX_BLOCKS);
+  a.leftover = leftover;
+  a.g = pj_segments(n);
+  a.with_init = with_init ? 1 : 0;
+  a.max_rounds = pj_rounds_for(n);
+  OFL_CUDA(cudaMemsetAsync(a.sync, 0, (size_t)(PJ_MAX_ROUNDS + 4) * sizeof(unsigned), st));
+  void* args[] = {&a};
+  OFL_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(pj_solve_kernel), dim3((unsigned)a.g.blocks), dim3(256),
+                                       args, 0, st));
+  OFL_CHECK_LAUNCH();
   return OFL_OK;
 }
 
@@ -1230,7 +1250,7 @@ static GraphLayout graph_layout(int64_t n, bool strip, bool with_tiles = true) {
   L.off_d0 = take((size_t)n * 8);
   L.off_d1 = take((size_t)n * 8);
   L.off_link = take((size_t)n * 2);
-  L.off_counts = take((size_t)(PJ_MAX_ROUNDS + 2) * 2 * PJ_MAX_BLOCKS * sizeof(int));
+  L.off_counts = take(((size_t)2 * PJ_MAX_BLOCKS + PJ_MAX_ROUNDS + 4) * sizeof(int));
   L.off_err = take(64);
   L.off_L = with_tiles ? take((size_t)(n / SLOTS) * AT * AT * sizeof(uint16_t)) : o;
   L.off_wide = with_tiles ? take((size_t)(n / SLOTS + 1) * sizeof(int)) : o;
@@ -1413,13 +1433,33 @@ int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t 
 //   final     push the strip's inflows down its own perimeter graph (second solve on seeds only, by
 //             linearity), then pass B over all tiles
 // boundary record of cell (t ? last row : first row, c): strip-local count, code, and where its in-strip
-// path leaves the strip: (exit row selector << 30) | exit column, or -1 when it does not leave
+// path leaves the strip: (exit row selector << 30) | exit column, or -1 when it does not leave.
+// A strip's records travel as ONE block of bytes (one all-gather): [2 x cols] int64 counts, then [2 x cols]
+// int32 exit links, then [2 x cols] codes, padded to a multiple of 256 bytes.
+size_t strip_record_bytes(int64_t cols) {
+  if (cols <= 0) return 256;
+  return align_up((size_t)cols * 2 * (8 + 4 + 1), 256);
+}
+struct RecView {  // the record blocks of n strips, `stride` bytes apart
+  const uint8_t* base;
+  int64_t stride, cols;
+  __device__ __forceinline__ long long floc(int s, int64_t k) const {
+    return reinterpret_cast<const long long*>(base + s * stride)[k];
+  }
+  __device__ __forceinline__ int32_t slink(int s, int64_t k) const {
+    return reinterpret_cast<const int32_t*>(base + s * stride + cols * 16)[k];
+  }
+  __device__ __forceinline__ uint8_t code(int s, int64_t k) const { return (base + s * stride + cols * 24)[k]; }
+};
+
 __global__ void strip_boundary_extract_kernel(const uint8_t* __restrict__ fdr, int64_t ld_fdr,
                                               const long long* __restrict__ fac, int64_t ld_fac,
                                               const int32_t* __restrict__ root_ptr, const uint16_t* __restrict__ link,
-                                              AccParams p, int32_t* __restrict__ slink, long long* __restrict__ floc,
-                                              uint8_t* __restrict__ bcode) {
+                                              AccParams p, uint8_t* __restrict__ record) {
   const int64_t n = 2 * (int64_t)p.cols;
+  long long* floc = reinterpret_cast<long long*>(record);
+  int32_t* slink = reinterpret_cast<int32_t*>(record + (int64_t)p.cols * 16);
+  uint8_t* bcode = record + (int64_t)p.cols * 24;
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
     const int t = (int)(k / p.cols), c = (int)(k - (int64_t)t * p.cols);
     const int r = t ? p.rows - 1 : 0;
@@ -1450,37 +1490,36 @@ __global__ void strip_boundary_extract_kernel(const uint8_t* __restrict__ fdr, i
 __device__ __forceinline__ int64_t bnode(int s, int t, int64_t c, int64_t cols) { return ((int64_t)s * 2 + t) * cols + c; }
 
 // where does boundary cell (s, t, c) with code `code` send its water?  -1 when not across a strip boundary
-__device__ __forceinline__ int64_t bnode_target(int s, int t, int64_t c, int code, int n_strips, int64_t cols,
-                                                const uint8_t* __restrict__ code_all) {
+__device__ __forceinline__ int64_t bnode_target(int s, int t, int64_t c, int code, int n_strips, const RecView& rec) {
   if (code >= 8) return -1;
   const int dy = dir_dy(code);
   if ((t == 0 && dy != -1) || (t == 1 && dy != 1)) return -1;
   const int s2 = s + dy;
   const int64_t c2 = c + dir_dx(code);
-  if (s2 < 0 || s2 >= n_strips || c2 < 0 || c2 >= cols) return -1;
-  const int64_t d = bnode(s2, dy < 0 ? 1 : 0, c2, cols);
-  return code_all[d] == OFL_DIR_NODATA ? -1 : d;
+  if (s2 < 0 || s2 >= n_strips || c2 < 0 || c2 >= rec.cols) return -1;
+  const int t2 = dy < 0 ? 1 : 0;
+  return rec.code(s2, t2 * rec.cols + c2) == OFL_DIR_NODATA ? -1 : bnode(s2, t2, c2, rec.cols);
 }
 
-__global__ void strip_graph_build_kernel(const int32_t* __restrict__ slink_all, const long long* __restrict__ floc_all,
-                                         const uint8_t* __restrict__ code_all, int n_strips, int64_t cols,
-                                         int32_t* __restrict__ succ, unsigned long long* __restrict__ base) {
+__global__ void strip_graph_build_kernel(const RecView rec, int n_strips, int32_t* __restrict__ succ,
+                                         unsigned long long* __restrict__ base) {
+  const int64_t cols = rec.cols;
   const int64_t n = (int64_t)n_strips * 2 * cols;
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
     const int s = (int)(k / (2 * cols));
-    const int t = (int)((k - (int64_t)s * 2 * cols) / cols);
-    const int64_t c = k - ((int64_t)s * 2 + t) * cols;
+    const int64_t kk = k - (int64_t)s * 2 * cols;  // index inside the strip's record
+    const int t = (int)(kk / cols);
+    const int64_t c = kk - (int64_t)t * cols;
     // this cell's own edge across the boundary carries its strip-local count into the next strip
-    const int64_t d = bnode_target(s, t, c, code_all[k], n_strips, cols, code_all);
-    if (d >= 0) atomicAdd(&base[d], (unsigned long long)floc_all[k]);
+    const int64_t d = bnode_target(s, t, c, rec.code(s, kk), n_strips, rec);
+    if (d >= 0) atomicAdd(&base[d], (unsigned long long)rec.floc(s, kk));
     // parent in the boundary forest: the entry cell fed by the cell where this cell's path leaves the strip
     int32_t parent = -1;
-    const int32_t sl = slink_all[k];
+    const int32_t sl = rec.slink(s, kk);
     if (sl >= 0) {
       const int te = sl >> 30;
       const int64_t ce = sl & ((1 << 30) - 1);
-      const int64_t x = bnode(s, te, ce, cols);
-      const int64_t dd = bnode_target(s, te, ce, code_all[x], n_strips, cols, code_all);
+      const int64_t dd = bnode_target(s, te, ce, rec.code(s, te * cols + ce), n_strips, rec);
       if (dd >= 0) parent = (int32_t)dd;
     }
     succ[k] = parent;
@@ -1504,9 +1543,10 @@ static int strip_setup(AccCtx& C, const uint8_t* fdr_halo, int64_t rows, int64_t
   return acc_setup(C, fdr_halo, rows, cols, ld_fdr, 1, has_above, has_below, fac, ld_fac, workspace, workspace_bytes, true);
 }
 
+// The three strip calls below only enqueue work; strip_collect_flags hands out their error flags.
 int strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above, int has_below,
-                      long long* fac, int64_t ld_fac, void* workspace, size_t workspace_bytes, int32_t* slink,
-                      long long* floc, uint8_t* bcode, cudaStream_t st) {
+                      long long* fac, int64_t ld_fac, void* workspace, size_t workspace_bytes, void* record,
+                      cudaStream_t st) {
   AccCtx C;
   int rc = strip_setup(C, fdr_halo, rows, cols, ld_fdr, has_above, has_below, fac, ld_fac, workspace, workspace_bytes);
   if (rc != OFL_OK) return rc;
@@ -1536,17 +1576,17 @@ int strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
   }
   if (rc != OFL_OK) return rc;
   strip_boundary_extract_kernel<<<grid_for(2 * cols, 8), 256, 0, st>>>(fdr_halo, ld_fdr, fac, ld_fac, C.pa, C.p.link, C.p,
-                                                                       slink, floc, bcode);
+                                                                       static_cast<uint8_t*>(record));
   OFL_CHECK_LAUNCH();
-  return check_flags(C.p.err, st);
+  return OFL_OK;
 }
 
 size_t strip_boundary_workspace_bytes(int n_strips, int64_t cols) {
   return graph_layout((int64_t)n_strips * 2 * cols, false, false).total;
 }
 
-int strip_boundary_solve(const int32_t* slink_all, const long long* floc_all, const uint8_t* code_all, int n_strips,
-                         int64_t cols, long long* J_all, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+int strip_boundary_solve(const void* records_all, int n_strips, int64_t cols, long long* J_all, void* workspace,
+                         size_t workspace_bytes, cudaStream_t st) {
   OFL_REQUIRE(n_strips >= 1 && cols >= 1, OFL_ERR_INVALID, "bad boundary graph size");
   const int64_t n = (int64_t)n_strips * 2 * cols;
   OFL_REQUIRE(n < (1ll << 31), OFL_ERR_INVALID, "boundary graph too large");
@@ -1557,9 +1597,13 @@ int strip_boundary_solve(const int32_t* slink_all, const long long* floc_all, co
   unsigned long long* S = reinterpret_cast<unsigned long long*>(ws + L.off_S);
   int* counts = reinterpret_cast<int*>(ws + L.off_counts);
   int* err = reinterpret_cast<int*>(ws + L.off_err);
-  OFL_CUDA(cudaMemsetAsync(ws + L.off_S, 0, L.off_link - L.off_S, st));
+  OFL_CUDA(cudaMemsetAsync(ws + L.off_S, 0, L.off_d0 - L.off_S, st));
   OFL_CUDA(cudaMemsetAsync(err, 0, 64, st));
-  strip_graph_build_kernel<<<grid_for(n, 8), 256, 0, st>>>(slink_all, floc_all, code_all, n_strips, cols, succ, S);
+  RecView rec;
+  rec.base = static_cast<const uint8_t*>(records_all);
+  rec.stride = (int64_t)strip_record_bytes(cols);
+  rec.cols = cols;
+  strip_graph_build_kernel<<<grid_for(n, 8), 256, 0, st>>>(rec, n_strips, succ, S);
   OFL_CHECK_LAUNCH();
   int rc;
   {
@@ -1571,7 +1615,26 @@ int strip_boundary_solve(const int32_t* slink_all, const long long* floc_all, co
   }
   if (rc != OFL_OK) return rc;
   OFL_CUDA(cudaMemcpyAsync(J_all, S, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
-  return check_flags(err, st);
+  return OFL_OK;
+}
+
+// Error flags of a strip's calls since its last strip_accum_local, and of the boundary solve, as four ints in
+// device memory: [0] tile flag, [1] strip solve, [2..3] the same for the boundary workspace (zero when null).
+// Stream-ordered; the caller reads them (after reducing them over the ranks, if there are several).
+int strip_collect_flags(const void* strip_workspace, int64_t rows, int64_t cols, const void* boundary_workspace,
+                        int n_strips, int32_t* flags_dev, cudaStream_t st) {
+  OFL_CUDA(cudaMemsetAsync(flags_dev, 0, 4 * sizeof(int32_t), st));
+  if (strip_workspace) {
+    const GraphLayout L = graph_layout(node_count(rows, cols), true);
+    OFL_CUDA(cudaMemcpyAsync(flags_dev, static_cast<const uint8_t*>(strip_workspace) + L.off_err, 2 * sizeof(int32_t),
+                             cudaMemcpyDeviceToDevice, st));
+  }
+  if (boundary_workspace) {
+    const GraphLayout L = graph_layout((int64_t)n_strips * 2 * cols, false, false);
+    OFL_CUDA(cudaMemcpyAsync(flags_dev + 2, static_cast<const uint8_t*>(boundary_workspace) + L.off_err,
+                             2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  }
+  return OFL_OK;
 }
 
 int strip_accum_final(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above, int has_below,
@@ -1583,8 +1646,7 @@ int strip_accum_final(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
   const GraphLayout& L = C.L;
   // inflow from other strips enters at the boundary rows; by linearity its effect on every perimeter
   // node is the subtree sum of those seeds over the strip's (preserved) perimeter forest
-  rc = ws_begin(C.ws, L, L.off_S2, st);  // S2
-  if (rc != OFL_OK) return rc;
+  OFL_CUDA(cudaMemsetAsync(C.ws + L.off_S2, 0, L.off_d0 - L.off_S2, st));  // S2; the error flags of the local pass stay
   strip_seed_kernel<<<grid_for(2 * cols, 8), 256, 0, st>>>(J_mine, C.p, C.S2);
   OFL_CHECK_LAUNCH();
   {
@@ -1598,18 +1660,19 @@ int strip_accum_final(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
     PhaseScope ps(PHASE_ACC_TILE_B, st);
     rc = launch_final(C, C.p, (unsigned)C.ntiles, st);
   }
-  if (rc != OFL_OK) return rc;
-  return check_flags(C.p.err, st);
+  return rc;
 }
 
 int launch_check(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, const long long* fac, int64_t ld_fac,
-                 unsigned long long* n_bad_dev, cudaStream_t st) {
+                 unsigned long long* n_bad_dev, cudaStream_t st, int y_off, const long long* fac_above,
+                 const long long* fac_below) {
   OFL_CUDA(cudaMemsetAsync(n_bad_dev, 0, sizeof(unsigned long long), st));
   if (rows <= 0 || cols <= 0) return OFL_OK;
   const int64_t n = rows * cols;
   const int64_t want = (n + 255) / 256;
   const int blocks = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
-  check_kernel<<<blocks, 256, 0, st>>>(fdr, ld_fdr, fac, ld_fac, (int)rows, (int)cols, n_bad_dev);
+  check_kernel<<<blocks, 256, 0, st>>>(fdr, ld_fdr, fac, ld_fac, (int)rows, (int)cols, y_off, fac_above, fac_below,
+                                       n_bad_dev);
   OFL_CHECK_LAUNCH();
   return OFL_OK;
 }

@@ -27,16 +27,20 @@ int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t 
 int accumulation_prepare(int64_t rows, int64_t cols, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t strip_workspace_bytes(int64_t rows, int64_t cols);
 size_t strip_boundary_workspace_bytes(int n_strips, int64_t cols);
+size_t strip_record_bytes(int64_t cols);
 int strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above, int has_below,
-                      long long* fac, int64_t ld_fac, void* workspace, size_t workspace_bytes, int32_t* slink,
-                      long long* floc, uint8_t* bcode, cudaStream_t st);
-int strip_boundary_solve(const int32_t* slink_all, const long long* floc_all, const uint8_t* code_all, int n_strips,
-                         int64_t cols, long long* J_all, void* workspace, size_t workspace_bytes, cudaStream_t st);
+                      long long* fac, int64_t ld_fac, void* workspace, size_t workspace_bytes, void* record,
+                      cudaStream_t st);
+int strip_boundary_solve(const void* records_all, int n_strips, int64_t cols, long long* J_all, void* workspace,
+                         size_t workspace_bytes, cudaStream_t st);
+int strip_collect_flags(const void* strip_workspace, int64_t rows, int64_t cols, const void* boundary_workspace,
+                        int n_strips, int32_t* flags_dev, cudaStream_t st);
 int strip_accum_final(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above, int has_below,
                       const long long* J_mine, void* workspace, size_t workspace_bytes, long long* fac, int64_t ld_fac,
                       cudaStream_t st);
 int launch_check(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, const long long* fac, int64_t ld_fac,
-                 unsigned long long* n_bad_dev, cudaStream_t st);
+                 unsigned long long* n_bad_dev, cudaStream_t st, int y_off = 0, const long long* fac_above = nullptr,
+                 const long long* fac_below = nullptr);
 size_t flats_workspace_bytes(int64_t rows, int64_t cols);
 int launch_flat_edges(const float* dem, const uint8_t* fdr, int64_t rows, int64_t cols, uint8_t* edges, int64_t* n_low,
                       int64_t* n_high, unsigned* cnt_dev, cudaStream_t st);
@@ -385,6 +389,30 @@ int ofl_check_accumulation_u8(const uint8_t* fdr, int64_t rows, int64_t cols, in
   return OFL_OK;
 }
 
+int ofl_strip_check_accumulation_u8(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr,
+                                    const int64_t* fac, int64_t ld_fac, const int64_t* fac_above,
+                                    const int64_t* fac_below, int64_t* n_bad, void* stream) {
+  OFL_REQUIRE(rows >= 0 && cols >= 0 && n_bad != nullptr, OFL_ERR_INVALID, "bad argument");
+  *n_bad = 0;
+  if (rows == 0 || cols == 0) return OFL_OK;
+  OFL_REQUIRE(fdr_halo != nullptr && fac != nullptr, OFL_ERR_INVALID, "null raster pointer");
+  int rc = ensure_init();
+  if (rc != OFL_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void* d_cnt = nullptr;
+  rc = scratch_get(SCRATCH_MISC, 256, &d_cnt);
+  if (rc != OFL_OK) return rc;
+  rc = launch_check(fdr_halo, rows, cols, ld_fdr, reinterpret_cast<const long long*>(fac), ld_fac,
+                    static_cast<unsigned long long*>(d_cnt), st, 1, reinterpret_cast<const long long*>(fac_above),
+                    reinterpret_cast<const long long*>(fac_below));
+  if (rc != OFL_OK) return rc;
+  unsigned long long h = 0;
+  OFL_CUDA(cudaMemcpyAsync(&h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, st));
+  OFL_CUDA(cudaStreamSynchronize(st));
+  *n_bad = (int64_t)h;
+  return OFL_OK;
+}
+
 // ---------------------------------------------------------------- flat resolution (csrc/flats.cu)
 size_t ofl_flats_workspace_bytes(int64_t rows, int64_t cols) {
   return (rows > 0 && cols > 0) ? flats_workspace_bytes(rows, cols) : 0;
@@ -570,25 +598,36 @@ size_t ofl_strip_boundary_workspace_bytes(int n_strips, int64_t cols) {
   return strip_boundary_workspace_bytes(n_strips, cols);
 }
 
+size_t ofl_strip_record_bytes(int64_t cols) { return strip_record_bytes(cols); }
+
 int ofl_strip_accum_local(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above,
                           int has_below, int64_t* fac, int64_t ld_fac, void* workspace, size_t workspace_bytes,
-                          int32_t* slink, int64_t* floc, uint8_t* bcode, void* stream) {
-  OFL_REQUIRE(fdr_halo && fac && workspace && slink && floc && bcode, OFL_ERR_INVALID, "null pointer");
+                          void* record, void* stream) {
+  OFL_REQUIRE(fdr_halo && fac && workspace && record, OFL_ERR_INVALID, "null pointer");
   int rc = ensure_init();
   if (rc != OFL_OK) return rc;
   return strip_accum_local(fdr_halo, rows, cols, ld_fdr, has_above, has_below, reinterpret_cast<long long*>(fac), ld_fac,
-                           workspace, workspace_bytes, slink, reinterpret_cast<long long*>(floc), bcode,
-                           static_cast<cudaStream_t>(stream));
+                           workspace, workspace_bytes, record, static_cast<cudaStream_t>(stream));
 }
 
-int ofl_strip_boundary_solve(const int32_t* slink_all, const int64_t* floc_all, const uint8_t* bcode_all, int n_strips,
-                             int64_t cols, int64_t* J_all, void* workspace, size_t workspace_bytes, void* stream) {
-  OFL_REQUIRE(slink_all && floc_all && bcode_all && J_all && workspace, OFL_ERR_INVALID, "null pointer");
+int ofl_strip_boundary_solve(const void* records_all, int n_strips, int64_t cols, int64_t* J_all, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  OFL_REQUIRE(records_all && J_all && workspace, OFL_ERR_INVALID, "null pointer");
   int rc = ensure_init();
   if (rc != OFL_OK) return rc;
-  return strip_boundary_solve(slink_all, reinterpret_cast<const long long*>(floc_all), bcode_all, n_strips, cols,
-                              reinterpret_cast<long long*>(J_all), workspace, workspace_bytes,
-                              static_cast<cudaStream_t>(stream));
+  return strip_boundary_solve(records_all, n_strips, cols, reinterpret_cast<long long*>(J_all), workspace,
+                              workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int ofl_strip_collect_flags(const void* strip_workspace, int64_t rows, int64_t cols, const void* boundary_workspace,
+                            int n_strips, int32_t* flags, void* stream) {
+  OFL_REQUIRE(flags != nullptr, OFL_ERR_INVALID, "null pointer");
+  OFL_REQUIRE(strip_workspace == nullptr || (rows >= 1 && cols >= 1), OFL_ERR_INVALID, "bad strip size");
+  OFL_REQUIRE(boundary_workspace == nullptr || (n_strips >= 1 && cols >= 1), OFL_ERR_INVALID, "bad boundary graph size");
+  int rc = ensure_init();
+  if (rc != OFL_OK) return rc;
+  return strip_collect_flags(strip_workspace, rows, cols, boundary_workspace, n_strips, flags,
+                             static_cast<cudaStream_t>(stream));
 }
 
 int ofl_strip_accum_final(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64_t ld_fdr, int has_above,
@@ -606,7 +645,9 @@ int ofl_synth_dem_f32(float* dem, int64_t rows, int64_t cols, int64_t ld_dem, in
                       uint64_t seed, int kind, float relief, int holes_permille, float nodata, void* stream) {
   OFL_REQUIRE(rows >= 0 && cols >= 0 && ld_dem >= cols, OFL_ERR_INVALID, "bad raster size");
   OFL_REQUIRE(dem != nullptr || rows * cols == 0, OFL_ERR_INVALID, "null raster pointer");
-  OFL_REQUIRE(kind >= 0 && kind <= 2, OFL_ERR_INVALID, "unknown synthetic DEM kind %d", kind);
+  OFL_REQUIRE(kind >= 0 && kind <= 3, OFL_ERR_INVALID, "unknown synthetic DEM kind %d", kind);
+  OFL_REQUIRE(kind != 3 || total_rows / 2 * cols < 0xFE000000ll, OFL_ERR_INVALID,
+              "serpentine DEM: the chain would run out of finite float32 values");
   int rc = ensure_init();
   if (rc != OFL_OK) return rc;
   return launch_synth(dem, rows, cols, ld_dem, row0, total_rows, seed, kind, relief, holes_permille, nodata,

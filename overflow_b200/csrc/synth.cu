@@ -32,6 +32,37 @@ __device__ float vnoise(float fx, float fy, uint32_t s) {
   return top + (bot - top) * ty;
 }
 
+// Walled serpentine (SURVEY 8d config 5 ii): ONE channel of about rows*cols/2 cells.  Channel rows are the odd
+// rows 1, 3, ..; it runs east on rows 1, 5, .. and west on rows 3, 7, .. over columns 1 .. cols-2 and steps down
+// through a one-cell gap in the wall row at the end of each run.  Everything else is wall (3e38), which drains
+// into the channel; the raster's outer ring is wall, so the channel ends in an interior pit.  The k-th channel
+// cell holds the k-th float32 below 0x7EFFFFFF in the total order of finite floats (bit patterns walked down
+// through +0 into the negative denormals, -0 skipped): strictly decreasing along the chain for up to 4.2e9
+// cells, every difference between consecutive cells exact (one ulp), no two cells equal.
+constexpr float SERP_WALL = 3.0e38f;
+constexpr long long SERP_ORD0 = 0x7EFFFFFFll;
+
+__device__ __forceinline__ float serpentine_cell(int64_t gr, int64_t c, int64_t total_rows, int64_t cols) {
+  if (gr <= 0 || gr >= total_rows - 1 || c <= 0 || c >= cols - 1) return SERP_WALL;
+  const int64_t wc = cols - 2;                    // channel cells per run
+  const int64_t n_runs = (total_rows - 1) / 2;    // channel rows 1, 3, .., <= total_rows - 2
+  int64_t k;
+  if (gr & 1) {
+    const int64_t m = (gr - 1) >> 1;
+    const int64_t pos = (m & 1) ? (cols - 2 - c) : (c - 1);
+    k = m * (wc + 1) + pos;
+  } else {
+    const int64_t m = (gr >> 1) - 1;              // the run above this wall row
+    if (m + 1 >= n_runs) return SERP_WALL;        // no run below: no gap
+    const int64_t gap_col = (m & 1) ? 1 : cols - 2;
+    if (c != gap_col) return SERP_WALL;
+    k = m * (wc + 1) + wc;
+  }
+  const long long ord = SERP_ORD0 - (long long)k;
+  const uint32_t bits = ord >= 0 ? (uint32_t)ord : (0x80000000u | (uint32_t)(-ord));
+  return __uint_as_float(bits);
+}
+
 __global__ void synth_kernel(float* dem, int64_t rows, int64_t cols, int64_t ld, int64_t row0, int64_t total_rows,
                              uint32_t seed, int kind, float relief, int holes_permille, float nodata) {
   const int64_t n = rows * cols;
@@ -44,6 +75,8 @@ __global__ void synth_kernel(float* dem, int64_t rows, int64_t cols, int64_t ld,
     } else if (kind == 2) {
       // tilted plane: drains towards the south-east corner, all values exact in float32
       z = (float)(total_rows - 1 - gr) + 0.25f * (float)(cols - 1 - c);
+    } else if (kind == 3) {
+      z = serpentine_cell(gr, c, total_rows, cols);
     } else {
       // 12 octaves, persistence 0.55: rough fractal relief (many local pits, like beta ~ 2 spectra)
       float amp = 1.f, sum = 0.f, norm = 0.f, freq = 1.0f / 4096.0f;

@@ -6,12 +6,13 @@ Per step:
                          (NCCL send/recv over NVLink); the raster's top and bottom get nodata rows
   2. direction           strip-mode stencil on the strip + halo rows
   3. code halo exchange  same pattern with the uint8 direction codes
-  4. local accumulation  ofl_strip_accum_local: strip-local solve, boundary records of the strip's
+  4. local accumulation  ofl_strip_accum_local: strip-local solve, boundary record block of the strip's
                          first and last row (13 B per boundary cell)
-  5. all-gather          the boundary records of all strips (NCCL all_gather, a few MB)
+  5. all-gather          the record blocks of all strips (ONE NCCL all_gather, a few MB)
   6. boundary solve      ofl_strip_boundary_solve, replicated on every GPU
   7. final accumulation  ofl_strip_accum_final: push the inflow from other strips down the strip and
                          write the strip's final int64 counts
+  8. status              the error flags of 4-7, MAX-reduced over the ranks: the step's one host synchronisation
 This mirrors the tile structure of Barnes 2016 (the paper cited by the reference at
 src/overflow/flow_accumulation.py:61,100) one level up: strips play the role of tiles.
 
@@ -51,8 +52,25 @@ def _round_up(v, a):
     return (v + a - 1) // a * a
 
 
+def record_bytes(cols):
+    """Bytes of one strip's boundary record block (ofl_strip_record_bytes): [2][cols] int64 strip-local counts,
+    [2][cols] int32 exit links, [2][cols] uint8 codes, zero padding to a multiple of 256."""
+    return _round_up(2 * cols * 13, 256)
+
+
+def record_views(rec, cols):
+    """(floc int64, slink int32, bcode uint8) views, each [..., 2, cols], of a record block [rec_bytes] or of the
+    gathered blocks [n_strips, rec_bytes] (uint8 tensors)."""
+    lead = tuple(rec.shape[:-1])
+    floc = rec[..., : 16 * cols].view(torch.int64).reshape(lead + (2, cols))
+    slink = rec[..., 16 * cols : 24 * cols].view(torch.int32).reshape(lead + (2, cols))
+    bcode = rec[..., 24 * cols : 26 * cols].reshape(lead + (2, cols))
+    return floc, slink, bcode
+
+
 class CudaStripEngine:
-    """The product engine: every method is a liboverflow_b200 call on torch CUDA tensors."""
+    """The product engine: every method is a liboverflow_b200 call on torch CUDA tensors.  The strip calls only
+    enqueue work on torch's current stream; `flags` hands out their error flags."""
 
     def __init__(self, device):
         self.device = torch.device(device)
@@ -72,10 +90,10 @@ class CudaStripEngine:
     def boundary_workspace(self, n_strips, cols):
         return self.empty((int(_native.lib().ofl_strip_boundary_workspace_bytes(n_strips, cols)),), torch.uint8)
 
-    def synth_dem(self, out, row0, total_rows, seed, kind, holes_permille, nodata):
+    def synth_dem(self, out, row0, total_rows, seed, kind, holes_permille, nodata, relief=1000.0):
         rows, cols = out.shape
         _native.check(_native.lib().ofl_synth_dem_f32(out.data_ptr(), rows, cols, out.stride(0), row0, total_rows, seed,
-                                                      kind, 1000.0, holes_permille, nodata, self._stream()))
+                                                      kind, relief, holes_permille, nodata, self._stream()))
 
     def direction(self, dem_halo, nodata, fdr_out):
         rows, cols = fdr_out.shape
@@ -83,23 +101,48 @@ class CudaStripEngine:
             dem_halo.data_ptr(), rows, cols, dem_halo.stride(0), float(nodata), fdr_out.data_ptr(), fdr_out.stride(0),
             _native.OFL_DIR_MODE_STRIP, _native.OFL_MEM_DEVICE, self._stream()))
 
-    def accum_local(self, fdr_halo, has_above, has_below, fac, ws, slink, floc, bcode):
+    def accum_local(self, fdr_halo, has_above, has_below, fac, ws, rec):
         rows, cols = fac.shape
         _native.check(_native.lib().ofl_strip_accum_local(
             fdr_halo.data_ptr(), rows, cols, fdr_halo.stride(0), int(has_above), int(has_below), fac.data_ptr(),
-            fac.stride(0), ws.data_ptr(), ws.numel(), slink.data_ptr(), floc.data_ptr(), bcode.data_ptr(), self._stream()))
+            fac.stride(0), ws.data_ptr(), ws.numel(), rec.data_ptr(), self._stream()))
 
-    def boundary_solve(self, slink_all, floc_all, bcode_all, J_all, ws):
-        n_strips, _, cols = slink_all.shape
+    def boundary_solve(self, rec_all, cols, J_all, ws):
         _native.check(_native.lib().ofl_strip_boundary_solve(
-            slink_all.data_ptr(), floc_all.data_ptr(), bcode_all.data_ptr(), n_strips, cols, J_all.data_ptr(),
-            ws.data_ptr(), ws.numel(), self._stream()))
+            rec_all.data_ptr(), rec_all.shape[0], cols, J_all.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()))
 
     def accum_final(self, fdr_halo, has_above, has_below, J_mine, ws, fac):
         rows, cols = fac.shape
         _native.check(_native.lib().ofl_strip_accum_final(
             fdr_halo.data_ptr(), rows, cols, fdr_halo.stride(0), int(has_above), int(has_below), J_mine.data_ptr(),
             ws.data_ptr(), ws.numel(), fac.data_ptr(), fac.stride(0), self._stream()))
+
+    def flags(self, ws, rows, cols, bws, n_strips, out):
+        """Error flags of the strip calls since the last accum_local (and of the boundary solve) into the int32[4]
+        device tensor `out`; stream-ordered, no synchronisation."""
+        _native.check(_native.lib().ofl_strip_collect_flags(
+            ws.data_ptr() if ws is not None else None, rows, cols, bws.data_ptr() if bws is not None else None,
+            n_strips, out.data_ptr(), self._stream()))
+
+    def check(self, fdr_halo, fac, fac_above, fac_below):
+        """Cells of the strip violating the accumulation recurrence (ofl_strip_check_accumulation_u8)."""
+        rows, cols = fac.shape
+        n_bad = ctypes.c_int64(0)
+        _native.check(_native.lib().ofl_strip_check_accumulation_u8(
+            fdr_halo.data_ptr(), rows, cols, fdr_halo.stride(0), fac.data_ptr(), fac.stride(0),
+            fac_above.data_ptr() if fac_above is not None else None,
+            fac_below.data_ptr() if fac_below is not None else None, ctypes.byref(n_bad), self._stream()))
+        return int(n_bad.value)
+
+
+def raise_for_flags(flags):
+    """flags: the four ints of ofl_strip_collect_flags (already reduced over the ranks)."""
+    f = [int(v) for v in flags]
+    if f[0] == 3:
+        raise _native.OverflowB200Error(-1, "shared-memory window above 64 KB: the tile kernel's 16-bit queue does not apply")
+    if any(f):
+        where = "tile pass" if f[0] else "strip perimeter graph" if f[1] else "strip-boundary graph"
+        raise _native.OverflowB200Error(_native.OFL_ERR_CYCLE, f"flow-direction raster contains a cycle ({where}, flags {f})")
 
 
 class StripPipeline:
@@ -120,14 +163,13 @@ class StripPipeline:
         self.fac = e.empty((h, c), torch.int64)
         self.ws = e.strip_workspace(h, c)
         self.bws = e.boundary_workspace(world, c)
-        self.slink = e.empty((2, c), torch.int32)
-        self.floc = e.empty((2, c), torch.int64)
-        self.bcode = e.empty((2, c), torch.uint8)
-        self.slink_all = e.empty((world, 2, c), torch.int32)
-        self.floc_all = e.empty((world, 2, c), torch.int64)
-        self.bcode_all = e.empty((world, 2, c), torch.uint8)
+        self.rec_all = e.empty((world, record_bytes(c)), torch.uint8)  # every strip's boundary record, mine at [rank]
+        self.rec = self.rec_all[rank]
         self.J_all = e.empty((world, 2, c), torch.int64)
+        self.flags = e.empty((4,), torch.int32)
+        self.fac_edge = e.empty((2, c), torch.int64)  # the neighbours' boundary counts (recurrence check only)
         self.fdr_halo.zero_()
+        self.rec_all.zero_()
 
     # ---- data
     @property
@@ -138,8 +180,8 @@ class StripPipeline:
     def fdr(self):
         return self.fdr_halo[1:-1]
 
-    def load_synthetic(self, seed=0, kind=0, holes_permille=0):
-        self.engine.synth_dem(self.dem, self.r0, self.rows, seed, kind, holes_permille, self.nodata)
+    def load_synthetic(self, seed=0, kind=0, holes_permille=0, relief=1000.0):
+        self.engine.synth_dem(self.dem, self.r0, self.rows, seed, kind, holes_permille, self.nodata, relief)
 
     def load_dem(self, dem_strip):
         self.dem.copy_(torch.as_tensor(dem_strip))
@@ -156,54 +198,75 @@ class StripPipeline:
         self.engine.direction(self.dem_halo, self.nodata, self.fdr)
 
     def accum_local(self):
-        self.engine.accum_local(self.fdr_halo, self.has_above, self.has_below, self.fac, self.ws, self.slink, self.floc,
-                                self.bcode)
+        self.engine.accum_local(self.fdr_halo, self.has_above, self.has_below, self.fac, self.ws, self.rec)
 
     def boundary_solve(self):
-        self.engine.boundary_solve(self.slink_all, self.floc_all, self.bcode_all, self.J_all, self.bws)
+        self.engine.boundary_solve(self.rec_all, self.cols, self.J_all, self.bws)
 
     def accum_final(self):
         self.engine.accum_final(self.fdr_halo, self.has_above, self.has_below, self.J_all[self.rank], self.ws, self.fac)
 
+    def collect_flags(self):
+        self.engine.flags(self.ws, self.h, self.cols, self.bws, self.world, self.flags)
+
     # ---- distributed step (one process per strip)
-    def _exchange(self, buf):
-        """Send my first / last row to the strip above / below; receive theirs into my halo rows."""
+    def _exchange(self, first, last, above, below):
+        """Send `first` / `last` (my first / last row of something) to the strip above / below; receive theirs
+        into `above` / `below`."""
         import torch.distributed as dist
 
         ops = []
         if self.has_above:
-            ops.append(dist.P2POp(dist.isend, buf[1], self.rank - 1))
-            ops.append(dist.P2POp(dist.irecv, buf[0], self.rank - 1))
+            ops.append(dist.P2POp(dist.isend, first, self.rank - 1))
+            ops.append(dist.P2POp(dist.irecv, above, self.rank - 1))
         if self.has_below:
-            ops.append(dist.P2POp(dist.isend, buf[-2], self.rank + 1))
-            ops.append(dist.P2POp(dist.irecv, buf[-1], self.rank + 1))
+            ops.append(dist.P2POp(dist.isend, last, self.rank + 1))
+            ops.append(dist.P2POp(dist.irecv, below, self.rank + 1))
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
 
-    def step(self):
-        """flow direction + flow accumulation of the whole raster; this rank's strip ends up in self.fdr / self.fac."""
+    def _exchange_halo(self, buf):
+        self._exchange(buf[1], buf[-2], buf[0], buf[-1])
+
+    def step(self, check_status=True):
+        """flow direction + flow accumulation of the whole raster; this rank's strip ends up in self.fdr / self.fac.
+
+        Everything is enqueued on the current stream: two halo exchanges, ONE all-gather of the boundary records
+        and, with check_status, one MAX all-reduce of the error flags followed by the step's only host
+        synchronisation -- every rank then raises the same error (a cyclic raster) instead of one rank leaving the
+        others waiting in a collective."""
         import torch.distributed as dist
 
         self.fill_edge_halos()
         if self.world > 1:
-            self._exchange(self.dem_halo)
+            self._exchange_halo(self.dem_halo)
         self.direction()
         if self.world > 1:
-            self._exchange(self.fdr_halo)
+            self._exchange_halo(self.fdr_halo)
         self.accum_local()
         if self.world > 1:
-            for out, inp in ((self.slink_all, self.slink), (self.floc_all, self.floc), (self.bcode_all, self.bcode)):
-                if dist.get_backend() == "gloo":  # CPU tests
-                    dist.all_gather(list(out.unbind(0)), inp)
-                else:
-                    dist.all_gather_into_tensor(out, inp)
-        else:
-            self.slink_all[0].copy_(self.slink)
-            self.floc_all[0].copy_(self.floc)
-            self.bcode_all[0].copy_(self.bcode)
+            if dist.get_backend() == "gloo":  # CPU tests
+                dist.all_gather(list(self.rec_all.unbind(0)), self.rec.clone())
+            else:
+                dist.all_gather_into_tensor(self.rec_all, self.rec)
         self.boundary_solve()
         self.accum_final()
+        if check_status:
+            self.collect_flags()
+            if self.world > 1:
+                dist.all_reduce(self.flags, op=dist.ReduceOp.MAX)
+            raise_for_flags(self.flags.tolist())
+
+    def check(self):
+        """Cells of this strip that violate the accumulation recurrence, the boundary rows checked against the
+        neighbouring strips' counts (exchanged here).  Summed over the strips, zero proves the partitioned result."""
+        above = below = None
+        if self.world > 1:
+            self._exchange(self.fac[0], self.fac[-1], self.fac_edge[0], self.fac_edge[1])
+            above = self.fac_edge[0] if self.has_above else None
+            below = self.fac_edge[1] if self.has_below else None
+        return self.engine.check(self.fdr_halo, self.fac, above, below)
 
 
 def step_in_process(pipes):
@@ -228,12 +291,24 @@ def step_in_process(pipes):
         p.accum_local()
     for p in pipes:
         for i, q in enumerate(pipes):
-            p.slink_all[i].copy_(q.slink)
-            p.floc_all[i].copy_(q.floc)
-            p.bcode_all[i].copy_(q.bcode)
+            if i != p.rank:
+                p.rec_all[i].copy_(q.rec)
     for p in pipes:
         p.boundary_solve()
         p.accum_final()
+    for p in pipes:
+        p.collect_flags()
+        raise_for_flags(p.flags.tolist())
+
+
+def check_in_process(pipes):
+    """Recurrence violations of all strips of step_in_process (loop-back exchange of the boundary counts)."""
+    bad = 0
+    for i, p in enumerate(pipes):
+        above = pipes[i - 1].fac[-1].contiguous() if i > 0 else None
+        below = pipes[i + 1].fac[0].contiguous() if i < len(pipes) - 1 else None
+        bad += p.engine.check(p.fdr_halo, p.fac, above, below)
+    return bad
 
 
 # ---------------------------------------------------------------- out of core: strips through ONE device
@@ -273,10 +348,14 @@ def flow_accumulation_out_of_core(read_rows, write_rows, rows, cols, strip_rows,
     fdr_halo = e.empty((h_max + 2, _round_up(cols, 16)), torch.uint8)[:, :cols]
     fac = e.empty((h_max, cols), torch.int64)
     ws = e.strip_workspace(h_max, cols)
-    slink_all, floc_all = e.empty((n, 2, cols), torch.int32), e.empty((n, 2, cols), torch.int64)
-    bcode_all, J_all = e.empty((n, 2, cols), torch.uint8), e.empty((n, 2, cols), torch.int64)
-    scratch = (e.empty((2, cols), torch.int32), e.empty((2, cols), torch.int64), e.empty((2, cols), torch.uint8))
+    rec_all, J_all = e.empty((n, record_bytes(cols)), torch.uint8), e.empty((n, 2, cols), torch.int64)
+    scratch = e.empty((record_bytes(cols),), torch.uint8)
     bws = e.boundary_workspace(n, cols)
+    flags = e.empty((4,), torch.int32)
+
+    def status(ws_, rows_, bws_):
+        e.flags(ws_, rows_, cols, bws_, n, flags)
+        raise_for_flags(flags.tolist())
 
     def load(s):
         """Codes of strip s plus one halo row above and below (raster edges: the halo row is never looked at)."""
@@ -295,12 +374,15 @@ def flow_accumulation_out_of_core(read_rows, write_rows, rows, cols, strip_rows,
 
     for s in range(n):
         view, f, above, below = load(s)
-        e.accum_local(view, above, below, f, ws, slink_all[s], floc_all[s], bcode_all[s])
-    e.boundary_solve(slink_all, floc_all, bcode_all, J_all, bws)
+        e.accum_local(view, above, below, f, ws, rec_all[s])
+        status(ws, f.shape[0], None)
+    e.boundary_solve(rec_all, cols, J_all, bws)
+    status(None, 0, bws)
     for s in range(n):
         view, f, above, below = load(s)
-        e.accum_local(view, above, below, f, ws, *scratch)
+        e.accum_local(view, above, below, f, ws, scratch)
         e.accum_final(view, above, below, J_all[s], ws, f)
+        status(ws, f.shape[0], None)
         write_rows(bounds[s][0], f.cpu().numpy())
     return n
 

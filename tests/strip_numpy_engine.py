@@ -29,7 +29,39 @@ class NumpyStripEngine:
         pad[:, 1:-1] = dem
         fdr_out.copy_(torch.from_numpy(oracle.flow_direction_for_tile(pad, nodata)[1:-1, 1:-1].copy()))
 
-    def accum_local(self, fdr_halo, has_above, has_below, fac, ws, slink, floc, bcode):
+    def flags(self, ws, rows, cols, bws, n_strips, out):
+        out.zero_()
+
+    def check(self, fdr_halo, fac, fac_above, fac_below):
+        """Recurrence violations of the strip, its boundary rows checked against the neighbours' counts."""
+        fh, f = fdr_halo.numpy(), fac.numpy()
+        h, c = f.shape
+        ext = np.zeros((h + 2, c), dtype=np.int64)
+        ext[1:-1] = f
+        codes = fh.copy()
+        for row, vals in ((0, fac_above), (h + 1, fac_below)):
+            if vals is None:
+                codes[row] = 9  # nothing flows in from beyond the raster
+            else:
+                ext[row] = vals.numpy()
+        bad = 0
+        for y in range(1, h + 1):
+            for x in range(c):
+                if codes[y, x] == 9:
+                    want = -9998
+                else:
+                    want = 1
+                    for d in range(8):
+                        uy, ux = y + DY[d], x + DX[d]
+                        if 0 <= ux < c and codes[uy, ux] == (d + 4) % 8:
+                            want += ext[uy, ux]
+                bad += int(ext[y, x] != want)
+        return bad
+
+    def accum_local(self, fdr_halo, has_above, has_below, fac, ws, rec):
+        from overflow_b200.strips import record_views
+
+        floc, slink, bcode = record_views(rec, fac.shape[1])
         fh = fdr_halo.numpy()
         fdr = np.ascontiguousarray(fh[1:-1])
         h, c = fdr.shape
@@ -54,7 +86,10 @@ class NumpyStripEngine:
                                 sl = ((0 if a == 0 else 1) << 30) | b
                 slink[t, x] = sl
 
-    def boundary_solve(self, slink_all, floc_all, bcode_all, J_all, ws):
+    def boundary_solve(self, rec_all, cols, J_all, ws):
+        from overflow_b200.strips import record_views
+
+        floc_all, slink_all, bcode_all = record_views(rec_all, cols)
         sl, fl, bc = slink_all.numpy(), floc_all.numpy(), bcode_all.numpy()
         G, _, C = sl.shape
 

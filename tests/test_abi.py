@@ -27,7 +27,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_abi_version(lib):
-    assert lib.ofl_abi_version() == 1
+    assert lib.ofl_abi_version() == 2
 
 
 def test_perimeter_count(lib):

@@ -31,6 +31,10 @@ def test_reference_arm_line():
     assert {"value", "unit", "cores", "kind", "sample"} <= set(cb) and cb["kind"] == "port" and cb["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"]
+    # the arm says what it ran, and the CUDA library is not mapped into its process
+    assert d["config"]["sample_rows"] == 256 and d["config"]["rows"] == 65536
+    assert all("overflow_b200" not in p for p in d["repo_libraries_loaded"])
+    assert any("liboracle_d8" in p for p in d["repo_libraries_loaded"])
 
 
 @pytest.mark.gpu
@@ -42,6 +46,11 @@ def test_native_arm_line():
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "hbm"
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert d["parity"]["accumulation_recurrence_violations"] == 0 and d["parity"]["direction_windows_vs_oracle"]
+    for name in ("terraced_16k", "tilted_plane", "serpentine"):
+        o = d["other_workloads"][name]
+        assert o["value"] > 0 and o["parity"]["accumulation_recurrence_violations"] == 0, name
+        assert o["parity"]["direction_windows_vs_oracle"], name
+    assert d["other_workloads"]["serpentine"]["parity"]["max_fac"] > 2048 * 2048 // 2
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] == 2048 * 2048 * 4 and e["d2h_bytes_per_step"] == 2048 * 2048 * 9 and e["value"] > 0
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])

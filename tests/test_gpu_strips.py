@@ -58,6 +58,88 @@ def test_eight_strips_large_device_raster():
     assert torch.equal(fdr, one_fdr)
     assert torch.equal(fac, one_fac)
     assert dev.check_accumulation(fdr, fac) == 0
+    # the strip form of the recurrence check: clean, and it sees a count that is off on a strip boundary
+    assert strips.check_in_process(pipes) == 0
+    pipes[3].fac[0, 1000] += 1
+    assert strips.check_in_process(pipes) >= 1
+
+
+def test_cycle_is_reported_through_the_flags():
+    """A cyclic code raster: the strip calls stay asynchronous and the step's one status read raises OFL_ERR_CYCLE."""
+    from overflow_b200 import _native, strips
+
+    rows, cols, world = 256, 128, 2
+    pipes = [strips.StripPipeline(rows, cols, r, world, nodata=synth.NODATA, device="cuda:0") for r in range(world)]
+    for p in pipes:
+        p.fdr_halo.fill_(0)  # everything flows east ...
+        p.fdr[:, cols - 1] = 8
+    pipes[1].fdr[10, 5] = 4  # ... except one cell that flows back west: a two-cell cycle
+    for p in pipes:
+        p.accum_local()
+    for p in pipes:
+        for i, q in enumerate(pipes):
+            if i != p.rank:
+                p.rec_all[i].copy_(q.rec)
+    for p in pipes:
+        p.boundary_solve()
+        p.accum_final()
+        p.collect_flags()
+    strips.raise_for_flags(pipes[0].flags.tolist())
+    with pytest.raises(_native.OverflowB200Error) as ei:
+        strips.raise_for_flags(pipes[1].flags.tolist())
+    assert ei.value.status == _native.OFL_ERR_CYCLE
+
+
+NCCL_SCRIPT = r"""
+import os, sys
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["OFL_ROOT"])
+from overflow_b200 import _native, device as dev, strips
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+_native.init(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ok = True
+for rows, cols, kind, holes in ((4096, 2048, 0, 10), (2048, 1024, 3, 0), (4096, 1024, 2, 0), (1024, 4096, 1, 50)):
+    p = strips.StripPipeline(rows, cols, rank, world, nodata=-9999.0, device=torch.device("cuda", local))
+    p.load_synthetic(seed=5, kind=kind, holes_permille=holes)
+    for _ in range(3):  # repeated steps: stream ordering between NCCL and the library's kernels
+        p.step()
+    bad = torch.tensor([p.check()], device="cuda")
+    dist.all_reduce(bad)
+    dem = dev.synth_dem(rows, cols, seed=5, kind=kind, holes_permille=holes)
+    fdr, fac = dev.flow_routing(dem, -9999.0)
+    same = torch.tensor([int(torch.equal(p.fdr, fdr[p.r0:p.r1]) and torch.equal(p.fac, fac[p.r0:p.r1]))], device="cuda")
+    dist.all_reduce(same)
+    ok &= int(bad.item()) == 0 and int(same.item()) == world
+    if rank == 0:
+        print("case", rows, cols, kind, "violations", int(bad.item()), "strips equal", int(same.item()), flush=True)
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
+"""
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_nccl_strips_equal_single_gpu(world, tmp_path):
+    """The path that actually travels over NCCL (torchrun, one rank per GPU): every rank's strip equals the same rows of
+    a single-GPU run of the whole raster, cell for cell, and the strip recurrence check is clean."""
+    import os
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    script = tmp_path / "nccl_strips.py"
+    script.write_text(NCCL_SCRIPT)
+    env = dict(os.environ, OFL_ROOT=ROOT)
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                          "--master-addr", "127.0.0.1", "--master-port", str(29500 + world), str(script)],
+                         capture_output=True, text=True, timeout=900, env=env)
+    assert res.returncode == 0, (res.stdout + res.stderr)[-3000:]
+    assert res.stdout.count("strips equal") == 4
 
 
 def test_long_chain_across_all_strips():

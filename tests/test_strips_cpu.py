@@ -51,6 +51,28 @@ def test_in_process_strips_match_whole_raster(name, dem, world):
     got_fac = np.concatenate([p.fac.numpy() for p in pipes])
     assert np.array_equal(got_fdr, want_fdr)
     assert np.array_equal(got_fac, want_fac)
+    # the recurrence check across strip boundaries: clean on the result, and it sees a wrong boundary count
+    assert strips.check_in_process(pipes) == 0
+    if world > 1:
+        pipes[1].fac[0, cols // 2] += 1
+        assert strips.check_in_process(pipes) >= 1
+
+
+def test_record_layout_matches_library():
+    from overflow_b200 import _native, build
+
+    build.build()
+    for cols in (1, 7, 64, 1000, 65536):
+        assert strips.record_bytes(cols) == _native.lib().ofl_strip_record_bytes(cols)
+    rec = torch.zeros((3, strips.record_bytes(10)), dtype=torch.uint8)
+    floc, slink, bcode = strips.record_views(rec, 10)
+    assert floc.shape == slink.shape == bcode.shape == (3, 2, 10)
+    floc[1, 1, 9] = -5
+    slink[2, 0, 0] = 77
+    bcode[0, 1, 3] = 9
+    one = strips.record_views(rec[1], 10)[0]
+    assert one.shape == (2, 10) and int(one[1, 9]) == -5
+    assert int(rec[2, 160:164].view(torch.int32)[0]) == 77 and int(rec[0, 240 + 13]) == 9
 
 
 def _gloo_worker(rank, world, port, dem, out_dir):
@@ -64,6 +86,9 @@ def _gloo_worker(rank, world, port, dem, out_dir):
         p = strips.StripPipeline(rows, cols, rank, world, nodata=synth.NODATA, engine=NumpyStripEngine())
         p.load_dem(dem[p.r0 : p.r1])
         p.step()
+        bad = torch.tensor([p.check()])
+        dist.all_reduce(bad)
+        assert int(bad.item()) == 0
         np.save(os.path.join(out_dir, f"fdr{rank}.npy"), p.fdr.numpy())
         np.save(os.path.join(out_dir, f"fac{rank}.npy"), p.fac.numpy())
         dist.barrier()
