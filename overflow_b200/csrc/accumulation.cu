@@ -31,6 +31,7 @@
 // Edge rule (flow_accumulation.py:116-124): u -> c is an edge iff code(u) in 0..7, c lies
 // inside the raster and code(c) != 9.  Codes >= 8 have no downstream cell (the reference's
 // out-of-bounds NEIGHBOR_OFFSETS read); NODATA cells end at -9998 (:119-121,129-137).
+#include <atomic>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -1131,14 +1132,14 @@ int64_t perimeter_count(int64_t rows, int64_t cols) {
 constexpr int PJ_MAX_ROUNDS = 40;
 
 static int ensure_tile_attrs() {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<int> attr_gen{-1};  // function attributes belong to the device they were set on
+  if (attr_gen.load() != device_generation()) {
     OFL_CUDA(cudaFuncSetAttribute(acc_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   TileSmem::BYTES));
     OFL_CUDA(cudaFuncSetAttribute(acc_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FinalSmem::BYTES_FAST));
     OFL_CUDA(cudaFuncSetAttribute(acc_final_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   FinalSmem::BYTES_WIDE));
-    attr_set = true;
+    attr_gen.store(device_generation());
   }
   return OFL_OK;
 }
@@ -1158,16 +1159,15 @@ static int pj_rounds_for(int64_t n) {
 // CTAs of pj_solve_kernel that are resident at once on the current device (the kernel is launched
 // cooperatively with one CTA per segment).
 static int pj_max_blocks() {
-  static int cached[64] = {};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
-  if (cached[dev] == 0) {
+  static std::atomic<int> gen{-1}, cached{0};
+  if (gen.load() != device_generation() || cached.load() == 0) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pj_solve_kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
-    cached[dev] = per_sm * sm_count();
+    cached.store(per_sm * sm_count());
+    gen.store(device_generation());
   }
-  return cached[dev];
+  return cached.load();
 }
 constexpr int PJ_MAX_BLOCKS = 8 * 256;  // counts0 holds this many segments (8 CTAs on each of up to 256 SMs)
 

@@ -68,43 +68,70 @@ static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * 
 // upload, the kernel and the download overlap (PCIe is full duplex).  The staging buffers hold the whole
 // raster: accumulation needs every code before it can finish a single count.
 namespace {
+// Streams and events of the host pipeline belong to the device they were created on: they are keyed on the
+// library's device generation and destroyed (by the cleanup hook, on their own device) when it moves on.
 struct HostPipe {
   cudaStream_t h2d = nullptr, d2h = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_prep = nullptr;
+  cudaEvent_t pool[2 * 256] = {};  // band events of direction_from_host, created on demand, reused by every call
+  int n_pool = 0;
+  int gen = -1;
 };
 HostPipe g_pipe;
 
+void pipe_cleanup() {
+  if (g_pipe.h2d) cudaStreamDestroy(g_pipe.h2d);
+  if (g_pipe.d2h) cudaStreamDestroy(g_pipe.d2h);
+  if (g_pipe.ev_in) cudaEventDestroy(g_pipe.ev_in);
+  if (g_pipe.ev_prep) cudaEventDestroy(g_pipe.ev_prep);
+  for (int i = 0; i < g_pipe.n_pool; ++i) cudaEventDestroy(g_pipe.pool[i]);
+  g_pipe = HostPipe();
+}
+
 int pipe_streams() {
-  if (!g_pipe.h2d) OFL_CUDA(cudaStreamCreateWithFlags(&g_pipe.h2d, cudaStreamNonBlocking));
-  if (!g_pipe.d2h) OFL_CUDA(cudaStreamCreateWithFlags(&g_pipe.d2h, cudaStreamNonBlocking));
+  if (g_pipe.gen == device_generation() && g_pipe.h2d) return OFL_OK;
+  g_pipe = HostPipe();  // whatever an older generation held was destroyed by pipe_cleanup on its own device
+  register_device_cleanup(pipe_cleanup);
+  OFL_CUDA(cudaStreamCreateWithFlags(&g_pipe.h2d, cudaStreamNonBlocking));
+  OFL_CUDA(cudaStreamCreateWithFlags(&g_pipe.d2h, cudaStreamNonBlocking));
+  OFL_CUDA(cudaEventCreateWithFlags(&g_pipe.ev_in, cudaEventDisableTiming));
+  OFL_CUDA(cudaEventCreateWithFlags(&g_pipe.ev_prep, cudaEventDisableTiming));
+  g_pipe.gen = device_generation();
   return OFL_OK;
 }
 
 constexpr int64_t PIPE_BAND_BYTES = 512ll << 20;  // ~0.5 GiB of DEM per band
 constexpr int PIPE_MAX_BANDS = 256;
 
-// dem: host, in_rows x cols.  d_dem / d_fdr: device staging (pitches ldd / ldo).  fdr_host may be null.
-// Output row y reads input rows y + y_off - 1 .. y + y_off + 1.  On return every stream is idle.
-int direction_from_host(const float* dem, int64_t in_rows, int64_t rows, int64_t cols, int64_t ld_dem, double nodata,
-                        int y_off, float* d_dem, int64_t ldd, uint8_t* d_fdr, int64_t ldo, uint8_t* fdr_host,
-                        int64_t ld_fdr, cudaStream_t st, bool sync_downloads) {
-  int rc = pipe_streams();
-  if (rc != OFL_OK) return rc;
+int pipe_events(int n) {
+  while (g_pipe.n_pool < n) {
+    OFL_CUDA(cudaEventCreateWithFlags(&g_pipe.pool[g_pipe.n_pool], cudaEventDisableTiming));
+    ++g_pipe.n_pool;
+  }
+  return OFL_OK;
+}
+
+// Enqueues the whole banded pipeline; returns at the first error (the caller drains the streams).
+int direction_from_host_enqueue(const float* dem, int64_t in_rows, int64_t rows, int64_t cols, int64_t ld_dem,
+                                double nodata, int y_off, float* d_dem, int64_t ldd, uint8_t* d_fdr, int64_t ldo,
+                                uint8_t* fdr_host, int64_t ld_fdr, cudaStream_t st) {
   int64_t band_bytes = PIPE_BAND_BYTES;
   if (const char* e = getenv("OFL_PIPE_BAND_BYTES")) band_bytes = atoll(e) > 0 ? atoll(e) : band_bytes;  // tests: many small bands
   int64_t band = band_bytes / (cols * (int64_t)sizeof(float));
   band = band < 64 ? 64 : band / 64 * 64;
   if ((in_rows + band - 1) / band > PIPE_MAX_BANDS) band = ((in_rows + PIPE_MAX_BANDS - 1) / PIPE_MAX_BANDS + 63) / 64 * 64;
   const int n_in = (int)((in_rows + band - 1) / band), n_out = (int)((rows + band - 1) / band);
-  cudaEvent_t ev_up[PIPE_MAX_BANDS], ev_dir[PIPE_MAX_BANDS];
-  for (int b = 0; b < n_in; ++b) OFL_CUDA(cudaEventCreateWithFlags(&ev_up[b], cudaEventDisableTiming));
-  for (int b = 0; b < n_out; ++b) OFL_CUDA(cudaEventCreateWithFlags(&ev_dir[b], cudaEventDisableTiming));
+  int rc = pipe_events(n_in + n_out);
+  if (rc != OFL_OK) return rc;
+  cudaEvent_t* ev_up = g_pipe.pool;
+  cudaEvent_t* ev_dir = g_pipe.pool + n_in;
   for (int b = 0; b < n_in; ++b) {
     const int64_t r0 = b * band, r1 = (r0 + band < in_rows) ? r0 + band : in_rows;
     OFL_CUDA(cudaMemcpy2DAsync(d_dem + r0 * ldd, ldd * sizeof(float), dem + r0 * ld_dem, ld_dem * sizeof(float),
                                cols * sizeof(float), r1 - r0, cudaMemcpyHostToDevice, g_pipe.h2d));
     OFL_CUDA(cudaEventRecord(ev_up[b], g_pipe.h2d));
   }
-  for (int b = 0; b < n_out && rc == OFL_OK; ++b) {
+  for (int b = 0; b < n_out; ++b) {
     const int64_t r0 = b * band, r1 = (r0 + band < rows) ? r0 + band : rows;
     int64_t in_lo = r0 + y_off - 1, in_hi = r1 + y_off + 1;  // input rows [in_lo, in_hi)
     if (in_lo < 0) in_lo = 0;
@@ -112,7 +139,7 @@ int direction_from_host(const float* dem, int64_t in_rows, int64_t rows, int64_t
     OFL_CUDA(cudaStreamWaitEvent(st, ev_up[(in_hi - 1) / band], 0));  // uploads complete in order
     rc = launch_direction(d_dem + in_lo * ldd, in_hi - in_lo, cols, ldd, nodata, d_fdr + r0 * ldo, r1 - r0, ldo,
                           (int)(r0 + y_off - in_lo), st);
-    if (rc != OFL_OK) break;
+    if (rc != OFL_OK) return rc;
     if (fdr_host) {
       OFL_CUDA(cudaEventRecord(ev_dir[b], st));
       OFL_CUDA(cudaStreamWaitEvent(g_pipe.d2h, ev_dir[b], 0));
@@ -120,13 +147,24 @@ int direction_from_host(const float* dem, int64_t in_rows, int64_t rows, int64_t
                                  cudaMemcpyDeviceToHost, g_pipe.d2h));
     }
   }
+  return OFL_OK;
+}
+
+// dem: host, in_rows x cols.  d_dem / d_fdr: device staging (pitches ldd / ldo).  fdr_host may be null.
+// Output row y reads input rows y + y_off - 1 .. y + y_off + 1.  With sync_downloads, or after any error, every
+// stream is idle on return: the caller's host buffers are never left in flight.
+int direction_from_host(const float* dem, int64_t in_rows, int64_t rows, int64_t cols, int64_t ld_dem, double nodata,
+                        int y_off, float* d_dem, int64_t ldd, uint8_t* d_fdr, int64_t ldo, uint8_t* fdr_host,
+                        int64_t ld_fdr, cudaStream_t st, bool sync_downloads) {
+  int rc = pipe_streams();
+  if (rc != OFL_OK) return rc;
+  rc = direction_from_host_enqueue(dem, in_rows, rows, cols, ld_dem, nodata, y_off, d_dem, ldd, d_fdr, ldo, fdr_host,
+                                   ld_fdr, st);
   if (rc != OFL_OK || sync_downloads) {
     cudaStreamSynchronize(g_pipe.h2d);
     cudaStreamSynchronize(st);
     cudaStreamSynchronize(g_pipe.d2h);
   }
-  for (int b = 0; b < n_in; ++b) cudaEventDestroy(ev_up[b]);
-  for (int b = 0; b < n_out; ++b) cudaEventDestroy(ev_dir[b]);
   return rc;
 }
 }  // namespace
@@ -303,19 +341,16 @@ int ofl_flow_routing_f32(const float* dem, int64_t rows, int64_t cols, int64_t l
   if (mem_kind == OFL_MEM_DEVICE) {
     OFL_REQUIRE(fdr != nullptr, OFL_ERR_INVALID, "device callers provide the code raster");
     // the workspace is cleared on a second stream while the stencil runs
-    static cudaEvent_t ev_in = nullptr, ev_prep = nullptr;
     rc = pipe_streams();
     if (rc != OFL_OK) return rc;
-    if (!ev_in) OFL_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
-    if (!ev_prep) OFL_CUDA(cudaEventCreateWithFlags(&ev_prep, cudaEventDisableTiming));
-    OFL_CUDA(cudaEventRecord(ev_in, st));
-    OFL_CUDA(cudaStreamWaitEvent(g_pipe.h2d, ev_in, 0));
+    OFL_CUDA(cudaEventRecord(g_pipe.ev_in, st));
+    OFL_CUDA(cudaStreamWaitEvent(g_pipe.h2d, g_pipe.ev_in, 0));
     rc = accumulation_prepare(rows, cols, work, need, g_pipe.h2d);
     if (rc != OFL_OK) return rc;
-    OFL_CUDA(cudaEventRecord(ev_prep, g_pipe.h2d));
+    OFL_CUDA(cudaEventRecord(g_pipe.ev_prep, g_pipe.h2d));
     rc = launch_direction(dem, rows, cols, ld_dem, nodata, fdr, rows, ld_fdr, 0, st);
     if (rc != OFL_OK) return rc;
-    OFL_CUDA(cudaStreamWaitEvent(st, ev_prep, 0));
+    OFL_CUDA(cudaStreamWaitEvent(st, g_pipe.ev_prep, 0));
     return launch_accumulation(fdr, rows, cols, ld_fdr, reinterpret_cast<long long*>(fac), ld_fac,
                                reinterpret_cast<long long*>(perim_links), work, need, st, true, true);
   }

@@ -51,6 +51,12 @@ struct PhaseScope {
 
 // ---------------------------------------------------------------- device properties / scratch
 int sm_count();
+// Bumped whenever the library moves to another device (ofl_init) or shuts down: everything created on "the
+// current device" -- streams, events, per-function attributes -- is keyed on it and re-made when it changes.
+int device_generation();
+// Called, with the OLD device still current, before the library leaves a device (ofl_init to another device,
+// ofl_shutdown): destroy what was created there.
+void register_device_cleanup(void (*fn)());
 
 // Library-owned device scratch, grown on demand and kept until ofl_shutdown (slot-indexed).
 enum ScratchSlot { SCRATCH_DEM = 0, SCRATCH_FDR, SCRATCH_FAC, SCRATCH_WORK, SCRATCH_LINKS, SCRATCH_MISC, SCRATCH_DIRCTR, SCRATCH_SLOTS };

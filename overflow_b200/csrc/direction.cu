@@ -395,10 +395,10 @@ __global__ void __launch_bounds__(DIR_WARPS * 32, OFL_DIR_CTAS_PER_SM) direction
   const int gwarp = blockIdx.x * DIR_WARPS + warp;
   const int nwarps = gridDim.x * DIR_WARPS;
   const int n_items = p.n_bands * p.n_chunks;
-  int item = gwarp;  // the first round needs no counter: the counter starts at nwarps
+  int item = gwarp;  // the first round needs no counter: it counts the items beyond the first nwarps
   while (item < n_items) {
     int next = 0;
-    if (wp.lane == 0) next = atomicAdd(p.next_item, 1);
+    if (wp.lane == 0) next = nwarps + atomicAdd(p.next_item, 1);
     const int chunk = item / p.n_bands;
     const int band = item - chunk * p.n_bands;
     const int x0 = band * DIR_BAND;
@@ -485,10 +485,10 @@ int launch_direction(const float* dem, int64_t in_rows, int64_t cols, int64_t ld
   const int64_t n_items = (int64_t)p.n_bands * p.n_chunks;
   OFL_REQUIRE(n_items < (1ll << 31), OFL_ERR_INVALID, "too many work items");
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<int> attr_gen{-1};  // function attributes belong to the device they were set on
+  if (attr_gen.load() != device_generation()) {
     OFL_CUDA(cudaFuncSetAttribute(direction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIR_SMEM_BYTES));
-    attr_set = true;
+    attr_gen.store(device_generation());
   }
   int ctas = (int)((n_items + DIR_WARPS - 1) / DIR_WARPS);
   const int max_ctas = sms * OFL_DIR_CTAS_PER_SM;
@@ -500,8 +500,8 @@ int launch_direction(const float* dem, int64_t in_rows, int64_t cols, int64_t ld
     rc = scratch_get(SCRATCH_DIRCTR, 256 * sizeof(int), &ctr);
     if (rc != OFL_OK) return rc;
     p.next_item = static_cast<int*>(ctr) + (ring.fetch_add(1) % 256);
-    const int first = ctas * DIR_WARPS;  // items 0 .. first-1 are taken by the warps' ids
-    OFL_CUDA(cudaMemcpyAsync(p.next_item, &first, sizeof(int), cudaMemcpyHostToDevice, st));
+    // items 0 .. ctas * DIR_WARPS - 1 are taken by the warps' ids; the counter hands out the rest from 0
+    OFL_CUDA(cudaMemsetAsync(p.next_item, 0, sizeof(int), st));
   }
   {
     PhaseScope ps(PHASE_DIRECTION, st);

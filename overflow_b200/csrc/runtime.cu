@@ -121,6 +121,40 @@ struct State {
 };
 static State g_state;
 static std::mutex g_mu;
+static std::atomic<int> g_generation{0};
+static std::vector<void (*)()> g_cleanups;
+
+int device_generation() { return g_generation.load(); }
+
+void register_device_cleanup(void (*fn)()) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto f : g_cleanups)
+    if (f == fn) return;
+  g_cleanups.push_back(fn);
+}
+
+// g_mu held; the device being left is current
+static void leave_device() {
+  if (g_state.device < 0) return;
+  cudaDeviceSynchronize();
+  for (auto f : g_cleanups) f();
+  {
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    for (auto& pp : g_pending) {
+      if (pp.start) cudaEventDestroy(pp.start);
+      if (pp.stop) cudaEventDestroy(pp.stop);
+    }
+    g_pending.clear();
+    for (auto e : g_event_pool) cudaEventDestroy(e);
+    g_event_pool.clear();
+  }
+  for (int i = 0; i < SCRATCH_SLOTS; ++i) {
+    if (g_state.scratch[i]) cudaFree(g_state.scratch[i]);
+    g_state.scratch[i] = nullptr;
+    g_state.scratch_bytes[i] = 0;
+  }
+  g_generation.fetch_add(1);
+}
 
 int init_device(int device) {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -132,20 +166,18 @@ int init_device(int device) {
     return OFL_ERR_CUDA;
   }
   OFL_REQUIRE(device >= 0 && device < n, OFL_ERR_INVALID, "device %d out of range (have %d)", device, n);
-  OFL_CUDA(cudaSetDevice(device));
   if (g_state.device != device) {
     cudaDeviceProp prop;
     OFL_CUDA(cudaGetDeviceProperties(&prop, device));
     OFL_REQUIRE(prop.major >= 10, OFL_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
                 prop.major, prop.minor);
-    for (int i = 0; i < SCRATCH_SLOTS; ++i) {
-      if (g_state.scratch[i]) cudaFree(g_state.scratch[i]);
-      g_state.scratch[i] = nullptr;
-      g_state.scratch_bytes[i] = 0;
-    }
+    // one device at a time: everything the library created on the device it leaves (scratch, streams, events,
+    // kernel attributes) is released there first
+    if (g_state.device >= 0 && cudaSetDevice(g_state.device) == cudaSuccess) leave_device();
     g_state.device = device;
     g_state.sms = prop.multiProcessorCount;
   }
+  OFL_CUDA(cudaSetDevice(device));
   return OFL_OK;
 }
 
@@ -159,11 +191,8 @@ int ensure_init() {
 
 int shutdown() {
   std::lock_guard<std::mutex> lk(g_mu);
-  for (int i = 0; i < SCRATCH_SLOTS; ++i) {
-    if (g_state.scratch[i]) cudaFree(g_state.scratch[i]);
-    g_state.scratch[i] = nullptr;
-    g_state.scratch_bytes[i] = 0;
-  }
+  if (g_state.device >= 0 && cudaSetDevice(g_state.device) == cudaSuccess) leave_device();
+  g_state.device = -1;
   if (g_state.pinned) cudaFreeHost(g_state.pinned);
   g_state.pinned = nullptr;
   g_state.pinned_bytes = 0;

@@ -36,7 +36,10 @@ _FT = {1: ("B", 1), 2: ("c", 1), 3: ("H", 2), 4: ("I", 4), 5: ("II", 8), 6: ("b"
 
 
 def _dtype_from_tags(bits, fmt, order):
-    kind = {1: "u", 2: "i", 3: "f"}.get(fmt, "u")
+    kind = {1: "u", 2: "i", 3: "f"}.get(fmt)
+    if kind is None or bits not in (8, 16, 32, 64) or (kind == "f" and bits < 32):
+        raise ValueError(f"unsupported sample layout: {bits} bits per sample, sample format {fmt} "
+                         "(the built-in reader handles 8/16/32/64-bit integers and 32/64-bit floats; use GDAL)")
     return np.dtype(f"{order}{kind}{bits // 8}")
 
 
@@ -142,14 +145,19 @@ class Dataset:
             raise ValueError("read window outside the raster")
         if self._mm is not None:
             return np.array(self._mm[yoff : yoff + ys, xoff : xoff + xs]).astype(self._dtype.newbyteorder("="), copy=False)
-        tw, th, offsets = self._chunks
+        tw, th, offsets = self._chunks[:3]
+        strips = len(self._chunks) > 3  # strips: the last one holds only the rows that are left; tiles are always full
         out = np.empty((ys, xs), dtype=self._dtype.newbyteorder("="))
         across = (self.RasterXSize + tw - 1) // tw
         with open(self._path, "rb") as f:
             for ty in range(yoff // th, (yoff + ys - 1) // th + 1):
+                rows_here = min(th, self.RasterYSize - ty * th) if strips else th
                 for tx in range(xoff // tw, (xoff + xs - 1) // tw + 1):
                     f.seek(offsets[ty * across + tx])
-                    tile = np.frombuffer(f.read(tw * th * self._dtype.itemsize), dtype=self._dtype).reshape(th, tw)
+                    raw = f.read(tw * rows_here * self._dtype.itemsize)
+                    if len(raw) != tw * rows_here * self._dtype.itemsize:
+                        raise ValueError(f"{self._path}: chunk ({ty}, {tx}) is truncated")
+                    tile = np.frombuffer(raw, dtype=self._dtype).reshape(rows_here, tw)
                     y0, x0 = max(yoff, ty * th), max(xoff, tx * tw)
                     y1, x1 = min(yoff + ys, (ty + 1) * th), min(xoff + xs, (tx + 1) * tw)
                     out[y0 - yoff : y1 - yoff, x0 - xoff : x1 - xoff] = tile[y0 - ty * th : y1 - ty * th,
@@ -241,6 +249,8 @@ def open_geotiff(path, update=False):
         raise ValueError(f"{path}: compressed GeoTIFFs need GDAL (the built-in reader handles uncompressed files)")
     if one(_TAG_SPP, 1) != 1:
         raise ValueError(f"{path}: only single-band rasters are supported")
+    if len(tags.get(_TAG_BITS, (3, (8,)))[1]) != 1:
+        raise ValueError(f"{path}: only one sample per pixel is supported")
     ds.RasterXSize, ds.RasterYSize = int(one(_TAG_WIDTH)), int(one(_TAG_HEIGHT))
     ds._dtype = _dtype_from_tags(int(one(_TAG_BITS, 8)), int(one(_TAG_SAMPLE_FORMAT, 1)), order)
     if _TAG_GDAL_NODATA in tags:
@@ -262,7 +272,7 @@ def open_geotiff(path, update=False):
                                shape=(ds.RasterYSize, ds.RasterXSize))
             ds._writable = update
         else:
-            ds._chunks = (ds.RasterXSize, rps, offsets)
+            ds._chunks = (ds.RasterXSize, rps, offsets, "strips")
     return ds
 
 

@@ -110,3 +110,56 @@ def test_missing_nodata_asserts(tmp_path):
     band = open_raster(str(tmp_path / "n.tif")).GetRasterBand(1)
     with pytest.raises(AssertionError):
         read_raster_with_bounds_handling(0, 0, 4, 4, band)
+
+
+def _write_striped_tiff(path, arr, rows_per_strip, gap=16, bits=None):
+    """A classic little-endian TIFF with one strip per `rows_per_strip` rows, the strips NOT adjacent in the file
+    (a gap after each) and the last strip short when rows % rows_per_strip != 0 -- what libtiff writers produce."""
+    import struct
+
+    rows, cols = arr.shape
+    item = arr.dtype.itemsize
+    fmt = {"u": 1, "i": 2, "f": 3}[arr.dtype.kind]
+    strips = [arr[r : r + rows_per_strip].tobytes() for r in range(0, rows, rows_per_strip)]
+    offsets, pos = [], 8
+    body = b""
+    for s in strips:
+        offsets.append(pos)
+        body += s + b"\xAA" * gap
+        pos += len(s) + gap
+    n = len(strips)
+    off_offsets, off_counts = pos, pos + 4 * n
+    extra = struct.pack(f"<{n}I", *offsets) + struct.pack(f"<{n}I", *[len(s) for s in strips])
+    ifd_pos = off_counts + 4 * n
+    tags = [(256, 4, 1, cols), (257, 4, 1, rows), (258, 3, 1, bits or item * 8), (259, 3, 1, 1), (262, 3, 1, 1),
+            (273, 4, n, off_offsets if n > 1 else offsets[0]), (277, 3, 1, 1), (278, 4, 1, rows_per_strip),
+            (279, 4, n, off_counts if n > 1 else len(strips[0])), (339, 3, 1, fmt)]
+    ifd = struct.pack("<H", len(tags))
+    for tag, ft, cnt, val in tags:
+        ifd += struct.pack("<HHI", tag, ft, cnt) + (struct.pack("<HH", val, 0) if ft == 3 else struct.pack("<I", val))
+    ifd += struct.pack("<I", 0)
+    with open(path, "wb") as f:
+        f.write(b"II" + struct.pack("<HI", 42, ifd_pos) + body + extra + ifd)
+
+
+@pytest.mark.parametrize("rows,rps", [(37, 8), (40, 8), (5, 16), (33, 1)])
+def test_striped_tiff_with_short_last_strip(tmp_path, rows, rps):
+    """strips that are not adjacent in the file, the last one shorter than RowsPerStrip."""
+    from overflow_b200.util.geotiff import open_geotiff
+
+    arr = (np.arange(rows * 23, dtype=np.float32).reshape(rows, 23) * 0.5).astype(np.float32)
+    path = str(tmp_path / "striped.tif")
+    _write_striped_tiff(path, arr, rps)
+    band = open_geotiff(path).GetRasterBand(1)
+    assert (band.YSize, band.XSize) == (rows, 23)
+    assert np.array_equal(band.ReadAsArray(), arr)
+    assert np.array_equal(band.ReadAsArray(xoff=3, yoff=rows - 4, win_xsize=7, win_ysize=4), arr[rows - 4 :, 3:10])
+
+
+def test_unsupported_bit_depth_is_refused(tmp_path):
+    from overflow_b200.util.geotiff import open_geotiff
+
+    path = str(tmp_path / "onebit.tif")
+    _write_striped_tiff(path, np.zeros((8, 8), dtype=np.uint8), 8, bits=1)
+    with pytest.raises(ValueError, match="bits per sample"):
+        open_geotiff(path)
