@@ -73,10 +73,12 @@ class Band:
     def SetNoDataValue(self, value):
         self._ds._set_nodata(value)
 
-    def ReadAsArray(self, xoff=0, yoff=0, win_xsize=None, win_ysize=None):
+    def ReadAsArray(self, xoff=0, yoff=0, win_xsize=None, win_ysize=None, buf_obj=None):
+        """The window as an array; with `buf_obj` (GDAL's name for it) the pixels go straight into that array --
+        pinned host memory in the streaming drivers -- and it is returned."""
         win_xsize = self.XSize - xoff if win_xsize is None else win_xsize
         win_ysize = self.YSize - yoff if win_ysize is None else win_ysize
-        return self._ds._read(int(xoff), int(yoff), int(win_xsize), int(win_ysize))
+        return self._ds._read(int(xoff), int(yoff), int(win_xsize), int(win_ysize), buf_obj)
 
     def WriteArray(self, array, xoff=0, yoff=0):
         self._ds._write(np.asarray(array), int(xoff), int(yoff))
@@ -140,9 +142,17 @@ class Dataset:
             self._mm.flush()
 
     # ---- pixel access
-    def _read(self, xoff, yoff, xs, ys):
+    def _read(self, xoff, yoff, xs, ys, out=None):
         if xoff < 0 or yoff < 0 or xoff + xs > self.RasterXSize or yoff + ys > self.RasterYSize:
             raise ValueError("read window outside the raster")
+        if out is not None:
+            if out.shape != (ys, xs) or out.dtype != self._dtype.newbyteorder("="):
+                raise ValueError("buf_obj must have the window's shape and the band's dtype")
+            if self._mm is not None:
+                out[...] = self._mm[yoff : yoff + ys, xoff : xoff + xs]
+            else:
+                out[...] = self._read(xoff, yoff, xs, ys)
+            return out
         if self._mm is not None:
             return np.array(self._mm[yoff : yoff + ys, xoff : xoff + xs]).astype(self._dtype.newbyteorder("="), copy=False)
         tw, th, offsets = self._chunks[:3]

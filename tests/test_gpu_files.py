@@ -99,3 +99,64 @@ def test_flow_routing_files_equal_the_two_step_outputs(tmp_path):
         assert ra.GetGeoTransform() == pytest.approx(rb.GetGeoTransform())
     want_fdr = oracle.flow_direction_for_tile(synth.pad_nodata(dem), synth.NODATA)[1:-1, 1:-1]
     assert np.array_equal(open_raster(b_fac).GetRasterBand(1).ReadAsArray(), oracle.flow_accumulation(want_fdr))
+
+
+# ---- the band pipeline of streaming.py: same files as the plain drivers, for any band height
+@pytest.mark.parametrize("band_rows", [1, 7, 64, 100, 5000])
+def test_streamed_routing_equals_plain_drivers(tmp_path, band_rows):
+    from overflow_b200.flow_routing import flow_routing
+    from overflow_b200.streaming import stream_routing
+
+    dem = synth.punch_holes(synth.fractal(333, 257, beta=2.0, seed=15), frac=0.03, seed=16)
+    src = str(tmp_path / "dem.tif")
+    ds = create_raster(src, dem.shape[1], dem.shape[0], "Float32", geotransform=(100.0, 30.0, 0.0, 900.0, 0.0, -30.0))
+    ds.GetRasterBand(1).WriteArray(dem)
+    ds.GetRasterBand(1).SetNoDataValue(synth.NODATA)
+    ds.FlushCache()
+    rep = stream_routing(src, str(tmp_path / "fdr_s.tif"), str(tmp_path / "fac_s.tif"), band_rows=band_rows)
+    assert rep["rows"] == 333 and rep["bands"] == -(-333 // band_rows) and rep["wall_s"] > 0
+    flow_routing(src, str(tmp_path / "fdr_p.tif"), str(tmp_path / "fac_p.tif"), streamed=False)
+    want_fdr = oracle.flow_direction_for_tile(synth.pad_nodata(dem), synth.NODATA)[1:-1, 1:-1]
+    want_fac = oracle.flow_accumulation(np.ascontiguousarray(want_fdr))
+    for tag, want, nd in (("fdr", want_fdr, FLOW_DIRECTION_NODATA), ("fac", want_fac, FLOW_ACCUMULATION_NODATA)):
+        s_ds, p_ds = open_raster(str(tmp_path / f"{tag}_s.tif")), open_raster(str(tmp_path / f"{tag}_p.tif"))
+        got = s_ds.GetRasterBand(1).ReadAsArray()
+        assert np.array_equal(got, want), tag
+        assert np.array_equal(got, p_ds.GetRasterBand(1).ReadAsArray()), tag
+        assert s_ds.GetRasterBand(1).GetNoDataValue() == nd
+        assert s_ds.GetGeoTransform() == (100.0, 30.0, 0.0, 900.0, 0.0, -30.0)
+
+
+def test_streamed_direction_only_and_accumulation_only(tmp_path):
+    from overflow_b200.streaming import stream_accumulation, stream_routing
+
+    dem = synth.terraced(200, 130, seed=3)
+    src = str(tmp_path / "dem.tif")
+    ds = create_raster(src, dem.shape[1], dem.shape[0], "Float32")
+    ds.GetRasterBand(1).WriteArray(dem)
+    ds.GetRasterBand(1).SetNoDataValue(synth.NODATA)
+    ds.FlushCache()
+    fdr_path, fac_path, fac2_path = str(tmp_path / "fdr.tif"), str(tmp_path / "fac.tif"), str(tmp_path / "fac2.tif")
+    stream_routing(src, fdr_path, None, band_rows=33)
+    want_fdr = oracle.flow_direction_for_tile(synth.pad_nodata(dem), synth.NODATA)[1:-1, 1:-1]
+    assert np.array_equal(open_raster(fdr_path).GetRasterBand(1).ReadAsArray(), want_fdr)
+    rep = stream_accumulation(fdr_path, fac_path, band_rows=40)
+    want_fac = oracle.flow_accumulation(np.ascontiguousarray(want_fdr))
+    assert np.array_equal(open_raster(fac_path).GetRasterBand(1).ReadAsArray(), want_fac)
+    assert rep["h2d_bytes"] == dem.size and rep["d2h_bytes"] == dem.size * 8
+    stream_routing(src, None, fac2_path, band_rows=64)
+    assert np.array_equal(open_raster(fac2_path).GetRasterBand(1).ReadAsArray(), want_fac)
+
+
+def test_streamed_driver_refuses_what_it_cannot_do(tmp_path):
+    from overflow_b200.streaming import stream_routing
+
+    src = str(tmp_path / "dem64.tif")
+    ds = create_raster(src, 8, 8, "Float64")
+    ds.GetRasterBand(1).WriteArray(np.zeros((8, 8)))
+    ds.GetRasterBand(1).SetNoDataValue(-1)
+    ds.FlushCache()
+    with pytest.raises(TypeError):
+        stream_routing(src, str(tmp_path / "o.tif"), None)
+    with pytest.raises(ValueError):
+        stream_routing(src, None, None)
