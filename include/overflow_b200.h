@@ -10,6 +10,8 @@
  *                                 (+ calculate_slope :72-96; driver loop :121-124)
  *   ofl_flow_accumulation_u8      src/overflow/flow_accumulation.py:95-158 single_tile_flow_accumulation
  *                                 (get_next_cell :13-37, perimeter_indices :40-51, follow_path :54-92)
+ *   ofl_flow_accumulation_seeded_u8  the same for one rectangular tile of a tiled raster, with the inflow the other
+ *                                 tiles send into its perimeter cells (Barnes 2016: the consumer's second pass)
  *   ofl_check_accumulation_u8     no reference counterpart: exactness check of the accumulation recurrence
  *   ofl_strip_check_accumulation_u8  the same check on one row strip (halo codes, neighbour strips' boundary counts)
  *   ofl_strip_*                   no reference counterpart: row-strip (multi-GPU) decomposition in the
@@ -167,6 +169,18 @@ int ofl_flow_accumulation_u8(const uint8_t* fdr, int64_t rows, int64_t cols, int
  */
 int ofl_flow_routing_f32(const float* dem, int64_t rows, int64_t cols, int64_t ld_dem, double nodata, uint8_t* fdr,
                          int64_t ld_fdr, int64_t* fac, int64_t ld_fac, int64_t* perim_links, int mem_kind, void* stream);
+
+/*
+ * The same for ONE RECTANGULAR TILE of a larger, tiled raster (the consumer's second pass in Barnes 2016, the
+ * paper behind src/overflow/flow_accumulation.py:61,100): perim_inflow[k] is what the other tiles send into the
+ * tile's k-th perimeter cell (perimeter_indices order, the order of perim_links; int64, nullable = no inflow),
+ * on any of the four sides.  It is carried down the cell's path inside the tile, so fac holds the FINAL counts of
+ * the tile's cells.  A cell listed twice in perimeter_indices (one-row / one-column tiles) carries its inflow once.
+ * overflow_b200/tiles.py drives the two passes and solves the graph of all tiles' perimeter cells on the host.
+ */
+int ofl_flow_accumulation_seeded_u8(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, int64_t* fac,
+                                    int64_t ld_fac, const int64_t* perim_inflow, int64_t* perim_links, void* workspace,
+                                    size_t workspace_bytes, int mem_kind, void* stream);
 
 /*
  * Exactness check: counts cells where fac != 1 + sum(fac of upstream neighbours) (data cells) or

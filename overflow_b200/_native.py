@@ -48,6 +48,7 @@ SIGNATURES = {
     "ofl_perimeter_count": (_i64, [_i64, _i64]),
     "ofl_accumulation_workspace_bytes": (_sz, [_i64, _i64]),
     "ofl_flow_accumulation_u8": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _sz, _int, _vp]),
+    "ofl_flow_accumulation_seeded_u8": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _sz, _int, _vp]),
     "ofl_flow_routing_f32": (_int, [_vp, _i64, _i64, _i64, _f64, _vp, _i64, _vp, _i64, _vp, _int, _vp]),
     "ofl_check_accumulation_u8": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, ctypes.POINTER(_i64), _int, _vp]),
     "ofl_strip_check_accumulation_u8": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, ctypes.POINTER(_i64), _vp]),

@@ -1081,6 +1081,29 @@ __global__ void links_kernel(const uint8_t* __restrict__ fdr, int64_t ld_fdr, co
   }
 }
 
+// Inflow from outside the raster into its perimeter cells (k in perimeter_indices order, like links_kernel):
+// the raster is one rectangular tile of a larger, tiled raster (Barnes 2016, the consumer's second pass), and
+// inflow[k] is what the other tiles send into perimeter cell k.  It joins the base inflow of the cell's
+// perimeter node, so the solve and the final pass carry it down the cell's path like any inflow between
+// 64 x 64 tiles.  A cell listed twice (one-row / one-column rasters) must carry its inflow once.
+__global__ void perim_seed_kernel(const long long* __restrict__ inflow, AccParams p, unsigned long long* __restrict__ S,
+                                  int64_t n) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const long long v = inflow[k];
+    if (v == 0) continue;
+    int r, c;
+    if (k < 2 * (int64_t)p.rows) {
+      r = (int)(k >> 1);
+      c = (k & 1) ? p.cols - 1 : 0;
+    } else {
+      const int64_t kk = k - 2 * (int64_t)p.rows;
+      c = 1 + (int)(kk >> 1);
+      r = (kk & 1) ? p.rows - 1 : 0;
+    }
+    atomicAdd(&S[node_of_cell(r, c, p)], (unsigned long long)v);
+  }
+}
+
 // ---------------------------------------------------------------- recurrence checker
 // Row-strip form: the code raster carries y_off halo rows above row 0 (and below the last row) and the counts
 // of the rows just outside the strip come as separate rows (null: the raster ends there).
@@ -1384,7 +1407,7 @@ int accumulation_prepare(int64_t rows, int64_t cols, void* workspace, size_t wor
 
 int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, long long* fac,
                         int64_t ld_fac, long long* perim_links_dev, void* workspace, size_t workspace_bytes,
-                        cudaStream_t st, bool prepared, bool trusted_codes) {
+                        cudaStream_t st, bool prepared, bool trusted_codes, const long long* perim_inflow_dev) {
   if (rows <= 0 || cols <= 0) return OFL_OK;
   AccCtx C;
   int rc = acc_setup(C, fdr, rows, cols, ld_fdr, 0, 0, 0, fac, ld_fac, workspace, workspace_bytes, false);
@@ -1400,6 +1423,11 @@ int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t 
     acc_tile_kernel<<<(unsigned)C.ntiles, ACC_THREADS, TileSmem::BYTES, st>>>(C.tm, C.p);
   }
   OFL_CHECK_LAUNCH();
+  if (perim_inflow_dev) {
+    const int64_t n = perimeter_count(rows, cols);
+    perim_seed_kernel<<<grid_for(n, 16), 256, 0, st>>>(perim_inflow_dev, C.p, C.p.S, n);
+    OFL_CHECK_LAUNCH();
+  }
   {
     PhaseScope ps(PHASE_ACC_SOLVE, st);
     rc = pj_solve(C.p.succ, C.pa, C.pb, C.lists, C.counts, C.p.err + 1, C.p.S, C.d0, C.d1, L.n, st, !C.p.fuse_init);

@@ -23,7 +23,7 @@ int64_t perimeter_count(int64_t rows, int64_t cols);
 size_t accumulation_workspace_bytes(int64_t rows, int64_t cols);
 int launch_accumulation(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, long long* fac, int64_t ld_fac,
                         long long* perim_links_dev, void* workspace, size_t workspace_bytes, cudaStream_t st,
-                        bool prepared = false, bool trusted_codes = false);
+                        bool prepared = false, bool trusted_codes = false, const long long* perim_inflow_dev = nullptr);
 int accumulation_prepare(int64_t rows, int64_t cols, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t strip_workspace_bytes(int64_t rows, int64_t cols);
 size_t strip_boundary_workspace_bytes(int n_strips, int64_t cols);
@@ -279,9 +279,10 @@ int ofl_fill_border_u8(uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr,
   return launch_fill_border(fdr, rows, cols, ld_fdr, value, static_cast<cudaStream_t>(stream));
 }
 
-int ofl_flow_accumulation_u8(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, int64_t* fac,
-                             int64_t ld_fac, int64_t* perim_links, void* workspace, size_t workspace_bytes,
-                             int mem_kind, void* stream) {
+// shared by ofl_flow_accumulation_u8 and ofl_flow_accumulation_seeded_u8
+static int accumulation_entry(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, int64_t* fac, int64_t ld_fac,
+                              const int64_t* perim_inflow, int64_t* perim_links, void* workspace, size_t workspace_bytes,
+                              int mem_kind, void* stream) {
   OFL_REQUIRE(rows >= 0 && cols >= 0, OFL_ERR_INVALID, "negative raster size");
   OFL_REQUIRE(mem_kind == OFL_MEM_HOST || mem_kind == OFL_MEM_DEVICE, OFL_ERR_INVALID, "unknown mem_kind %d", mem_kind);
   if (rows == 0 || cols == 0) return OFL_OK;
@@ -298,7 +299,8 @@ int ofl_flow_accumulation_u8(const uint8_t* fdr, int64_t rows, int64_t cols, int
   }
   if (mem_kind == OFL_MEM_DEVICE)
     return launch_accumulation(fdr, rows, cols, ld_fdr, reinterpret_cast<long long*>(fac), ld_fac,
-                               reinterpret_cast<long long*>(perim_links), workspace, workspace_bytes, st);
+                               reinterpret_cast<long long*>(perim_links), workspace, workspace_bytes, st, false, false,
+                               reinterpret_cast<const long long*>(perim_inflow));
 
   const int64_t ldi = round_up(cols, 16), ldo = round_up(cols, 2);
   void *d_fdr = nullptr, *d_fac = nullptr, *d_links = nullptr;
@@ -307,13 +309,19 @@ int ofl_flow_accumulation_u8(const uint8_t* fdr, int64_t rows, int64_t cols, int
   rc = scratch_get(SCRATCH_FAC, (size_t)rows * ldo * sizeof(int64_t), &d_fac);
   if (rc != OFL_OK) return rc;
   const int64_t n_perim = perimeter_count(rows, cols);
-  if (perim_links) {
-    rc = scratch_get(SCRATCH_LINKS, (size_t)n_perim * 2 * sizeof(int64_t), &d_links);
+  if (perim_links || perim_inflow) {  // links [n][2], then the inflow [n]
+    rc = scratch_get(SCRATCH_LINKS, (size_t)n_perim * 3 * sizeof(int64_t), &d_links);
     if (rc != OFL_OK) return rc;
+  }
+  long long* d_inflow = nullptr;
+  if (perim_inflow) {
+    d_inflow = static_cast<long long*>(d_links) + 2 * n_perim;
+    OFL_CUDA(cudaMemcpyAsync(d_inflow, perim_inflow, (size_t)n_perim * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   }
   OFL_CUDA(cudaMemcpy2DAsync(d_fdr, ldi, fdr, ld_fdr, cols, rows, cudaMemcpyHostToDevice, st));
   rc = launch_accumulation(static_cast<const uint8_t*>(d_fdr), rows, cols, ldi, static_cast<long long*>(d_fac), ldo,
-                           static_cast<long long*>(d_links), workspace, workspace_bytes, st);
+                           perim_links ? static_cast<long long*>(d_links) : nullptr, workspace, workspace_bytes, st, false,
+                           false, d_inflow);
   if (rc != OFL_OK) return rc;
   OFL_CUDA(cudaMemcpy2DAsync(fac, ld_fac * sizeof(int64_t), d_fac, ldo * sizeof(int64_t), cols * sizeof(int64_t), rows,
                              cudaMemcpyDeviceToHost, st));
@@ -321,6 +329,20 @@ int ofl_flow_accumulation_u8(const uint8_t* fdr, int64_t rows, int64_t cols, int
     OFL_CUDA(cudaMemcpyAsync(perim_links, d_links, (size_t)n_perim * 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   OFL_CUDA(cudaStreamSynchronize(st));
   return OFL_OK;
+}
+
+int ofl_flow_accumulation_u8(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, int64_t* fac,
+                             int64_t ld_fac, int64_t* perim_links, void* workspace, size_t workspace_bytes,
+                             int mem_kind, void* stream) {
+  return accumulation_entry(fdr, rows, cols, ld_fdr, fac, ld_fac, nullptr, perim_links, workspace, workspace_bytes,
+                            mem_kind, stream);
+}
+
+int ofl_flow_accumulation_seeded_u8(const uint8_t* fdr, int64_t rows, int64_t cols, int64_t ld_fdr, int64_t* fac,
+                                    int64_t ld_fac, const int64_t* perim_inflow, int64_t* perim_links, void* workspace,
+                                    size_t workspace_bytes, int mem_kind, void* stream) {
+  return accumulation_entry(fdr, rows, cols, ld_fdr, fac, ld_fac, perim_inflow, perim_links, workspace, workspace_bytes,
+                            mem_kind, stream);
 }
 
 int ofl_flow_routing_f32(const float* dem, int64_t rows, int64_t cols, int64_t ld_dem, double nodata, uint8_t* fdr,
