@@ -907,26 +907,14 @@ struct PjArgs {
   unsigned long long *S, *d0, *d1;
   unsigned* sync;        // [0] barrier counter, [2 + j] nodes left after round j; zeroed before the launch
   int* leftover;         // set when max_rounds did not suffice: the forest has a cycle
+  const int* run_flag;   // nullable: the whole solve is skipped (by every CTA alike) when this device word is 0
   PjSeg g;
   int with_init, max_rounds;
 };
 
-__device__ __forceinline__ void pj_grid_barrier(unsigned* counter, unsigned& generation) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    ++generation;
-    const unsigned target = generation * gridDim.x;
-    __threadfence();
-    atomicAdd(counter, 1u);
-    while (*reinterpret_cast<volatile unsigned*>(counter) < target) {
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
-
 __global__ void __launch_bounds__(256, 8) pj_solve_kernel(const PjArgs a) {
   __shared__ int s_keep, s_ret;
+  if (a.run_flag && *a.run_flag == 0) return;  // written by an earlier kernel: every CTA sees the same value
   const PjSeg g = a.g;
   const int64_t base = (int64_t)blockIdx.x * g.seg;
   int32_t* const list0 = a.lists + base;
@@ -959,7 +947,7 @@ __global__ void __launch_bounds__(256, 8) pj_solve_kernel(const PjArgs a) {
       }
       block_append(list0, &s_keep, active, (int32_t)u, false, g.seg);
     }
-    pj_grid_barrier(a.sync, generation);  // round 0 reads other segments' pointers
+    grid_barrier(a.sync, generation);  // round 0 reads other segments' pointers
     n_active = s_keep;
   } else {
     n_active = a.counts0[blockIdx.x];
@@ -1016,20 +1004,13 @@ __global__ void __launch_bounds__(256, 8) pj_solve_kernel(const PjArgs a) {
     n_active = s_keep;
     n_retired = s_ret;
     if (threadIdx.x == 0 && n_active + n_retired) atomicAdd(&a.sync[2 + j], (unsigned)(n_active + n_retired));
-    pj_grid_barrier(a.sync, generation);
+    grid_barrier(a.sync, generation);
     const unsigned left = *reinterpret_cast<volatile unsigned*>(&a.sync[2 + j]);
     if (left == 0) break;  // nothing active and the last retirees' roots and deltas are in place
     if (j + 1 >= a.max_rounds) {
       if (threadIdx.x == 0 && n_active) *a.leftover = 1;
       break;
     }
-  }
-}
-
-__global__ void pj_add_kernel(unsigned long long* __restrict__ S, const unsigned long long* __restrict__ S2, int64_t n) {
-  for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < n; u += (int64_t)gridDim.x * blockDim.x) {
-    const unsigned long long d = S2[u];
-    if (d) S[u] += d;
   }
 }
 
@@ -1214,8 +1195,9 @@ static PjSeg pj_segments(int64_t n) {
 // initialisation.  Does not synchronise: *leftover is set when the forest did not converge (a cycle).
 static int pj_solve(const int32_t* succ, int32_t* ptr_a, int32_t* ptr_b, int32_t* lists, int* counts, int* leftover,
                     unsigned long long* S, unsigned long long* d0, unsigned long long* d1, int64_t n, cudaStream_t st,
-                    bool with_init = true) {
+                    bool with_init = true, const int* run_flag = nullptr) {
   PjArgs a;
+  a.run_flag = run_flag;
   a.succ = succ;
   a.ptr_a = ptr_a;
   a.ptr_b = ptr_b;
@@ -1554,12 +1536,64 @@ __global__ void strip_graph_build_kernel(const RecView rec, int n_strips, int32_
   }
 }
 
-__global__ void strip_seed_kernel(const long long* __restrict__ J, AccParams p, unsigned long long* __restrict__ S2) {
+// The inflow from other strips enters at the boundary rows and has to reach every perimeter node downstream of its
+// entry cell.  On terrain those paths are short (a handful of tiles) and the entries few, so one thread per entry
+// cell simply walks the preserved forest and adds its inflow to every node on the way -- after a dry walk by all of
+// them has shown that no path is longer than SEED_CHASE_MAX nodes.  If one is (a long channel, a tilted plane), a
+// device flag sends the step through the general route instead: subtree sums of the seeds by pointer doubling over
+// the whole forest, added to S.  Both routes give the same sums (integer adds); the choice is made on the device.
+constexpr int SEED_CHASE_MAX = 256;
+
+template <bool DRY>
+__global__ void strip_seed_chase_kernel(const long long* __restrict__ J, AccParams p, const int32_t* __restrict__ succ,
+                                        unsigned long long* __restrict__ S, int* __restrict__ too_long) {
+  if (!DRY && *too_long) return;
+  const int64_t n = 2 * (int64_t)p.cols;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const long long j = J[k];
+    if (j == 0) continue;
+    const int t = (int)(k / p.cols), c = (int)(k - (int64_t)t * p.cols);
+    int u = node_of_cell(t ? p.rows - 1 : 0, c, p);
+    if (DRY) {
+      int steps = 0;
+      while ((u = succ[u]) >= 0)
+        if (++steps > SEED_CHASE_MAX) {
+          *too_long = 1;
+          break;
+        }
+    } else {
+      do {
+        atomicAdd(&S[u], (unsigned long long)j);
+        u = succ[u];
+      } while (u >= 0);
+    }
+  }
+}
+
+__global__ void strip_seed_kernel_if(const long long* __restrict__ J, AccParams p, unsigned long long* __restrict__ S2,
+                                     int64_t n_nodes, const int* __restrict__ run_flag) {
+  if (*run_flag == 0) return;
+  // the general route: S2 = 0 everywhere, then the seeds (one launch: the seeds' nodes are zeroed by their own threads)
+  for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < n_nodes; u += (int64_t)gridDim.x * blockDim.x) S2[u] = 0;
+}
+
+__global__ void strip_seed_set_kernel_if(const long long* __restrict__ J, AccParams p, unsigned long long* __restrict__ S2,
+                                         const int* __restrict__ run_flag) {
+  if (*run_flag == 0) return;
   const int64_t n = 2 * (int64_t)p.cols;
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
     const int t = (int)(k / p.cols), c = (int)(k - (int64_t)t * p.cols);
     const long long j = J[k];
     if (j != 0) S2[node_of_cell(t ? p.rows - 1 : 0, c, p)] = (unsigned long long)j;
+  }
+}
+
+__global__ void pj_add_kernel_if(unsigned long long* __restrict__ S, const unsigned long long* __restrict__ S2, int64_t n,
+                                 const int* __restrict__ run_flag) {
+  if (*run_flag == 0) return;
+  for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < n; u += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long d = S2[u];
+    if (d) S[u] += d;
   }
 }
 
@@ -1672,18 +1706,27 @@ int strip_accum_final(const uint8_t* fdr_halo, int64_t rows, int64_t cols, int64
   int rc = strip_setup(C, fdr_halo, rows, cols, ld_fdr, has_above, has_below, fac, ld_fac, workspace, workspace_bytes);
   if (rc != OFL_OK) return rc;
   const GraphLayout& L = C.L;
-  // inflow from other strips enters at the boundary rows; by linearity its effect on every perimeter
-  // node is the subtree sum of those seeds over the strip's (preserved) perimeter forest
-  OFL_CUDA(cudaMemsetAsync(C.ws + L.off_S2, 0, L.off_d0 - L.off_S2, st));  // S2; the error flags of the local pass stay
-  strip_seed_kernel<<<grid_for(2 * cols, 8), 256, 0, st>>>(J_mine, C.p, C.S2);
-  OFL_CHECK_LAUNCH();
+  // inflow from other strips: walked down the forest from its entry cells when every such path is short, else
+  // (device flag) subtree sums of the seeds over the whole forest -- see strip_seed_chase_kernel
+  int* too_long = C.p.err + 8;  // not an error flag: the route the seeds take
+  const bool force_general = getenv("OFL_SEED_GENERAL") != nullptr;  // test hook: always the general route
+  OFL_CUDA(cudaMemsetAsync(too_long, force_general ? 1 : 0, sizeof(int), st));
   {
     PhaseScope ps(PHASE_ACC_SOLVE, st);
-    rc = pj_solve(C.p.succ, C.pa, C.pb, C.lists, C.counts, C.p.err + 1, C.S2, C.d0, C.d1, L.n, st);
-    if (rc == OFL_OK) pj_add_kernel<<<grid_for(L.n, 8), 256, 0, st>>>(C.p.S, C.S2, L.n);  // S += S2
+    const int gs = grid_for(2 * cols, 8);
+    strip_seed_chase_kernel<true><<<gs, 256, 0, st>>>(J_mine, C.p, C.p.succ, C.p.S, too_long);
+    OFL_CHECK_LAUNCH();
+    strip_seed_chase_kernel<false><<<gs, 256, 0, st>>>(J_mine, C.p, C.p.succ, C.p.S, too_long);
+    OFL_CHECK_LAUNCH();
+    strip_seed_kernel_if<<<grid_for(L.n, 8), 256, 0, st>>>(J_mine, C.p, C.S2, L.n, too_long);
+    OFL_CHECK_LAUNCH();
+    strip_seed_set_kernel_if<<<gs, 256, 0, st>>>(J_mine, C.p, C.S2, too_long);
+    OFL_CHECK_LAUNCH();
+    rc = pj_solve(C.p.succ, C.pa, C.pb, C.lists, C.counts, C.p.err + 1, C.S2, C.d0, C.d1, L.n, st, true, too_long);
+    if (rc != OFL_OK) return rc;
+    pj_add_kernel_if<<<grid_for(L.n, 8), 256, 0, st>>>(C.p.S, C.S2, L.n, too_long);  // S += S2
+    OFL_CHECK_LAUNCH();
   }
-  if (rc != OFL_OK) return rc;
-  OFL_CHECK_LAUNCH();
   {
     PhaseScope ps(PHASE_ACC_TILE_B, st);
     rc = launch_final(C, C.p, (unsigned)C.ntiles, st);

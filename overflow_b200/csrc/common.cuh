@@ -107,6 +107,22 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       "l"(tm), "r"(x), "r"(y), "r"(smem_u32(bar))
       : "memory");
 }
+// Grid-wide barrier of a cooperatively launched kernel (every CTA resident): `counter` is a device word zeroed
+// before the launch, `generation` a per-thread count of the barriers passed so far.  Writes made before the barrier
+// are visible after it to loads that do not go through L1 (ld.global.cg / volatile).
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& generation) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ++generation;
+    const unsigned target = generation * gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (*reinterpret_cast<volatile unsigned*>(counter) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }

@@ -17,13 +17,16 @@
 // NODATA test compares in float64.  Bit-exact against the reference (tests/golden/breach_pits.npz).
 #include <math_constants.h>
 
+#include <atomic>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ofl {
 namespace {
 
 constexpr int PT = 256;
-enum { PC_PITS = 0, PC_LEFT, PC_UNSOLVED, PC_SLOTS = 16 };
+enum { PC_PITS = 0, PC_ROUNDS, PC_UNSOLVED, PC_BARRIER, PC_NEXT0, PC_NEXT1, PC_SLOTS = 16 };
 
 __constant__ int p_dx[8] = {1, 1, 1, 0, -1, -1, -1, 0};  // breach_single_cell_pits.py:27-31
 __constant__ int p_dy[8] = {-1, 0, 1, 1, 1, 0, -1, -1};
@@ -79,58 +82,153 @@ pits_detect_kernel(const float* __restrict__ chunk, int rows, int cols, int64_t 
   if (pit) list[cta_base + warp_off[w] + __popc(m & ((1u << lane) - 1u))] = (int)i;
 }
 
-// a waiting pit is ready when no earlier (row-major) pit within chessboard distance 3 is still waiting
+// pass 1, vector form (dense pitch and columns that are multiples of four, 16-byte aligned rows): a thread owns four
+// adjacent cells of one row -- three float4 loads and six scalars instead of 36 loads, the flags of its cells leave as
+// one 32-bit store each; a CTA covers 128 columns x 8 rows and makes one list reservation.
 __global__ void __launch_bounds__(PT)
-pits_ready_kernel(const int* __restrict__ list, unsigned n_pits, const uint8_t* __restrict__ waiting, uint8_t* ready,
-                  int rows, int cols) {
-  const unsigned t = blockIdx.x * PT + threadIdx.x;
-  if (t >= n_pits) return;
-  const int i = list[t];
-  if (!waiting[i]) return;
-  const int r = i / cols, c = i - r * cols;
-  bool ok = true;
-  for (int dr = -3; dr <= 0 && ok; ++dr) {
-    const int rr = r + dr;
-    if (rr < 0) continue;
-    const int c_hi = dr < 0 ? min(cols - 1, c + 3) : c - 1;  // the pit's own row: only cells before it
-    for (int cc = max(0, c - 3); cc <= c_hi; ++cc)
-      if (waiting[rr * cols + cc]) {
-        ok = false;
-        break;
-      }
-  }
-  ready[t] = ok ? 1 : 0;
-}
-
-// pass 2 (:52-63) for the ready pits of this round
-__global__ void __launch_bounds__(PT)
-pits_breach_kernel(const int* __restrict__ list, unsigned n_pits, uint8_t* waiting, uint8_t* ready, float* chunk, int rows,
-                   int cols, int64_t ld, double nodata, int8_t* unsolved, unsigned* cnt) {
-  const unsigned t = blockIdx.x * PT + threadIdx.x;
-  if (t >= n_pits || !ready[t]) return;
-  ready[t] = 0;
-  const int i = list[t];
-  const int r = i / cols, c = i - r * cols;
-  float* at = chunk + (int64_t)r * ld + c;
-  const float z = *at;
-  bool solved = false;
-  for (int k = 0; k < 16; ++k) {  // in order: two k share a breach cell and the later one wins
-    const float zn = at[(int64_t)p_dy2[k] * ld + p_dx2[k]];
-    if (zn <= z || (double)zn == nodata) {
-      solved = true;
-      const int b = p_breach[k];
-      at[(int64_t)p_dy[b] * ld + p_dx[b]] = __double2float_rn((double)__fadd_rn(z, zn) / 2.0);
+pits_detect4_kernel(const float* __restrict__ chunk, int rows, int cols, int64_t ld, float nd_f, bool nd_exact,
+                    int8_t* unsolved, uint8_t* waiting, int* list, unsigned* cnt) {
+  __shared__ unsigned warp_off[PT / 32];
+  __shared__ unsigned cta_base;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int r = blockIdx.y * (PT / 32) + w;
+  const int c = (blockIdx.x * 32 + lane) * 4;
+  uint32_t pits = 0;  // bit j: cell c + j is a pit
+  const bool in_raster = r < rows && c < cols;
+  if (in_raster && r >= 2 && r < rows - 2) {
+    const float* row = chunk + (int64_t)r * ld + c;
+    float v[3][6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float* q = row + (int64_t)(k - 1) * ld;
+      const float4 m = *reinterpret_cast<const float4*>(q);
+      v[k][0] = c > 0 ? q[-1] : 0.f;
+      v[k][1] = m.x;
+      v[k][2] = m.y;
+      v[k][3] = m.z;
+      v[k][4] = m.w;
+      v[k][5] = c + 4 < cols ? q[4] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cc = c + j;
+      if (cc < 2 || cc >= cols - 2) continue;
+      const float z = v[1][j + 1];
+      // the branch-free form of :40-50, as in pits_detect_kernel
+      float lowest = CUDART_NAN_F;
+      bool nodata_seen = false;
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          if (k == 1 && d == 1) continue;
+          const float zn = v[k][j + d];
+          lowest = fminf(lowest, zn);
+          nodata_seen = nodata_seen || zn == nd_f;
+        }
+      if (!(nd_exact && (nodata_seen || z == nd_f)) && !(lowest <= z)) pits |= 1u << j;
     }
   }
-  if (solved)
-    unsolved[i] = 0;
-  else
-    atomicAdd(&cnt[PC_UNSOLVED], 1u);
-  waiting[i] = 0;
-  atomicSub(&cnt[PC_LEFT], 1u);
+  if (in_raster) {
+    const uint32_t flags = ((pits & 1u) ? 0x01u : 0u) | ((pits & 2u) ? 0x0100u : 0u) | ((pits & 4u) ? 0x010000u : 0u) |
+                           ((pits & 8u) ? 0x01000000u : 0u);
+    const size_t i = (size_t)r * (size_t)cols + (size_t)c;
+    *reinterpret_cast<uint32_t*>(unsolved + i) = flags;
+    *reinterpret_cast<uint32_t*>(waiting + i) = flags;
+  }
+  // one list reservation per CTA: exclusive scan of the per-thread counts
+  const unsigned mine = __popc(pits);
+  unsigned incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_off[w] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned run = 0;
+    for (int k = 0; k < PT / 32; ++k) {
+      const unsigned v2 = warp_off[k];
+      warp_off[k] = run;
+      run += v2;
+    }
+    cta_base = run ? atomicAdd(&cnt[PC_PITS], run) : 0u;
+  }
+  __syncthreads();
+  unsigned pos = cta_base + warp_off[w] + incl - mine;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (pits & (1u << j)) list[pos++] = r * cols + c + j;
 }
 
-__global__ void pits_begin_kernel(unsigned* cnt) { cnt[PC_LEFT] = cnt[PC_PITS]; }
+// pass 2 (:52-63) in dependency-ordered rounds, ONE persistent kernel (cooperative launch, grid barriers).
+// Round: (a) a waiting pit is READY when no earlier (row-major) pit within chessboard distance 3 is still waiting;
+// (b) the ready pits -- more than three cells apart, hence on disjoint cells -- are breached exactly as the
+// reference's sequential loop would breach them, the others go to the next round's list.  The earliest waiting pit is
+// always ready, so the rounds end.  Everything other CTAs wrote in earlier rounds is read past L1 (ld.global.cg).
+__global__ void __launch_bounds__(PT)
+pits_rounds_kernel(int* list_a, int* list_b, uint8_t* waiting, uint8_t* ready, float* chunk, int rows, int cols,
+                   int64_t ld, double nodata, int8_t* unsolved, unsigned* cnt) {
+  unsigned generation = 0;
+  unsigned n_cur = *reinterpret_cast<volatile unsigned*>(&cnt[PC_PITS]);
+  const unsigned tid = blockIdx.x * PT + threadIdx.x, nthr = gridDim.x * PT;
+  unsigned rounds = 0;
+  int* cur = list_a;
+  int* nxt = list_b;
+  while (n_cur) {
+    unsigned* n_next = &cnt[PC_NEXT0 + ((rounds + 1) & 1)];
+    for (unsigned t = tid; t < n_cur; t += nthr) {
+      const int i = __ldcg(&cur[t]);
+      const int r = i / cols, c = i - r * cols;
+      bool ok = true;
+      for (int dr = -3; dr <= 0 && ok; ++dr) {
+        const int rr = r + dr;
+        if (rr < 0) continue;
+        const int c_hi = dr < 0 ? min(cols - 1, c + 3) : c - 1;  // the pit's own row: only cells before it
+        for (int cc = max(0, c - 3); cc <= c_hi; ++cc)
+          if (__ldcg(&waiting[(size_t)rr * cols + cc])) {
+            ok = false;
+            break;
+          }
+      }
+      ready[t] = ok ? 1 : 0;
+    }
+    grid_barrier(&cnt[PC_BARRIER], generation);
+    for (unsigned t = tid; t < n_cur; t += nthr) {
+      const int i = __ldcg(&cur[t]);
+      if (!ready[t]) {  // written by this thread before the barrier
+        nxt[atomicAdd(n_next, 1u)] = i;
+        continue;
+      }
+      const int r = i / cols, c = i - r * cols;
+      float* at = chunk + (int64_t)r * ld + c;
+      const float z = __ldcg(at);
+      bool solved = false;
+      for (int k = 0; k < 16; ++k) {  // in order: two k share a breach cell and the later one wins
+        const float zn = __ldcg(&at[(int64_t)p_dy2[k] * ld + p_dx2[k]]);
+        if (zn <= z || (double)zn == nodata) {
+          solved = true;
+          const int b = p_breach[k];
+          at[(int64_t)p_dy[b] * ld + p_dx[b]] = __double2float_rn((double)__fadd_rn(z, zn) / 2.0);
+        }
+      }
+      if (solved)
+        unsolved[i] = 0;
+      else
+        atomicAdd(&cnt[PC_UNSOLVED], 1u);
+      waiting[i] = 0;
+    }
+    grid_barrier(&cnt[PC_BARRIER], generation);
+    n_cur = *reinterpret_cast<volatile unsigned*>(n_next);
+    ++rounds;
+    if (tid == 0) cnt[PC_NEXT0 + ((rounds + 1) & 1)] = 0;  // next round's counter: not touched before the next barrier
+    int* t2 = cur;
+    cur = nxt;
+    nxt = t2;
+  }
+  if (tid == 0) cnt[PC_ROUNDS] = rounds;
+}
 
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
@@ -142,7 +240,7 @@ size_t pits_workspace_bytes(int64_t rows, int64_t cols) {
 }
 
 // chunk: device, rows x cols with leading dimension ld, breached in place.  unsolved: device int8, dense.
-// info (host, nullable): {pits found, pits left unsolved, rounds}.  Synchronises the stream.
+// info (host, nullable): {pits found, pits left unsolved, rounds}.  Synchronises the stream (once, at the end).
 int launch_breach_pits(float* chunk, int64_t rows, int64_t cols, int64_t ld, double nodata, int8_t* unsolved,
                        int64_t* info, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   OFL_REQUIRE(rows > 0 && cols > 0 && rows * cols < (int64_t)INT32_MAX, OFL_ERR_INVALID,
@@ -150,51 +248,50 @@ int launch_breach_pits(float* chunk, int64_t rows, int64_t cols, int64_t ld, dou
   OFL_REQUIRE(workspace_bytes >= pits_workspace_bytes(rows, cols), OFL_ERR_WORKSPACE, "pits workspace too small");
   const size_t n = (size_t)rows * (size_t)cols;
   char* p = static_cast<char*>(workspace);
-  int* list = reinterpret_cast<int*>(p);
+  // pits are never adjacent, so there are at most n / 4 of them: two lists fit the n ints
+  int* list_a = reinterpret_cast<int*>(p);
+  int* list_b = list_a + (n + 1) / 2;
   uint8_t* waiting = reinterpret_cast<uint8_t*>(p + align256(n * sizeof(int)));
   uint8_t* ready = waiting + align256(n);
   unsigned* cnt = reinterpret_cast<unsigned*>(ready + align256(n));
   PhaseScope ps(PHASE_PITS, st);
   OFL_CUDA(cudaMemsetAsync(cnt, 0, PC_SLOTS * sizeof(unsigned), st));
-  const unsigned nb = (unsigned)((n + PT - 1) / PT);
   const float nd_f = (float)nodata;
   const bool nd_exact = (double)nd_f == nodata;  // false for NaN and for values float32 cannot hold: nothing matches then
-  pits_detect_kernel<<<nb, PT, 0, st>>>(chunk, (int)rows, (int)cols, ld, nd_f, nd_exact, unsolved, waiting, list, cnt);
+  const bool vec = cols % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(chunk) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(unsolved) & 3) == 0 && !getenv("OFL_PITS_SCALAR");
+  if (vec) {
+    const dim3 grid((unsigned)((cols / 4 + 31) / 32), (unsigned)((rows + PT / 32 - 1) / (PT / 32)));
+    OFL_REQUIRE(grid.y <= 65535u, OFL_ERR_INVALID, "chunk has too many rows for one launch");
+    pits_detect4_kernel<<<grid, PT, 0, st>>>(chunk, (int)rows, (int)cols, ld, nd_f, nd_exact, unsolved, waiting, list_a, cnt);
+  } else {
+    const unsigned nb = (unsigned)((n + PT - 1) / PT);
+    pits_detect_kernel<<<nb, PT, 0, st>>>(chunk, (int)rows, (int)cols, ld, nd_f, nd_exact, unsolved, waiting, list_a, cnt);
+  }
   OFL_CHECK_LAUNCH();
-  pits_begin_kernel<<<1, 1, 0, st>>>(cnt);
-  OFL_CHECK_LAUNCH();
+  {
+    static std::atomic<int> gen{-1}, blocks{0};
+    if (gen.load() != device_generation() || blocks.load() == 0) {
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pits_rounds_kernel, PT, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+      blocks.store((per_sm > 4 ? 4 : per_sm) * sm_count());
+      gen.store(device_generation());
+    }
+    int irows = (int)rows, icols = (int)cols;
+    void* args[] = {&list_a, &list_b, &waiting, &ready, &chunk, &irows, &icols, &ld, &nodata, &unsolved, &cnt};
+    OFL_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(pits_rounds_kernel), dim3((unsigned)blocks.load()),
+                                         dim3(PT), args, 0, st));
+    OFL_CHECK_LAUNCH();
+  }
   unsigned* h = nullptr;
   int rc = pinned_get(64, reinterpret_cast<void**>(&h));
   if (rc != OFL_OK) return rc;
   OFL_CUDA(cudaMemcpyAsync(h, cnt, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   OFL_CUDA(cudaStreamSynchronize(st));
-  const unsigned n_pits = h[PC_PITS];
-  unsigned left = n_pits;
-  int64_t rounds = 0;
-  if (n_pits) {
-    OFL_CUDA(cudaMemsetAsync(ready, 0, n_pits, st));
-    const unsigned nbp = (n_pits + PT - 1) / PT;
-    int batch = 2;  // rounds between two looks at the counter: a finished chunk costs a few empty launches at most
-    while (left) {
-      for (int b = 0; b < batch; ++b) {
-        pits_ready_kernel<<<nbp, PT, 0, st>>>(list, n_pits, waiting, ready, (int)rows, (int)cols);
-        OFL_CHECK_LAUNCH();
-        pits_breach_kernel<<<nbp, PT, 0, st>>>(list, n_pits, waiting, ready, chunk, (int)rows, (int)cols, ld, nodata,
-                                               unsolved, cnt);
-        OFL_CHECK_LAUNCH();
-      }
-      rounds += batch;
-      OFL_CUDA(cudaMemcpyAsync(h, cnt, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-      OFL_CUDA(cudaStreamSynchronize(st));
-      OFL_REQUIRE(h[PC_LEFT] < left, OFL_ERR_INVALID, "pit breaching made no progress (%u pits left)", left);
-      left = h[PC_LEFT];
-      if (batch < 16) batch *= 2;
-    }
-  }
   if (info) {
-    info[0] = n_pits;
-    info[1] = n_pits ? h[PC_UNSOLVED] : 0;
-    info[2] = rounds;
+    info[0] = h[PC_PITS];
+    info[1] = h[PC_UNSOLVED];
+    info[2] = h[PC_ROUNDS];
   }
   return OFL_OK;
 }

@@ -142,6 +142,23 @@ def test_nccl_strips_equal_single_gpu(world, tmp_path):
     assert res.stdout.count("strips equal") == 4
 
 
+@pytest.mark.parametrize("general", [False, True])
+def test_both_routes_of_the_cross_strip_inflow(general, monkeypatch):
+    """The inflow from other strips walks the forest from its entry cells when every path is short (terrain) and
+    takes subtree sums over the whole forest otherwise (long channels); OFL_SEED_GENERAL forces the second route."""
+    if general:
+        monkeypatch.setenv("OFL_SEED_GENERAL", "1")
+    dem = synth.punch_holes(synth.fractal(1024, 700, beta=2.5, seed=21), frac=0.02, seed=22)
+    want_fdr = oracle.flow_direction_for_tile(synth.pad_nodata(dem), synth.NODATA)[1:-1, 1:-1]
+    fdr, fac = run_strips(dem, 4)
+    assert np.array_equal(fdr, want_fdr) and np.array_equal(fac, oracle.flow_accumulation(want_fdr))
+    # one channel of 150 000 cells through four strips: far beyond the walk's limit, whatever the switch says
+    chan = oracle.synth_dem(768, 400, kind=3)
+    want_fdr = oracle.flow_direction_for_tile(synth.pad_nodata(chan), synth.NODATA)[1:-1, 1:-1]
+    fdr, fac = run_strips(chan, 4)
+    assert np.array_equal(fdr, want_fdr) and np.array_equal(fac, oracle.flow_accumulation(want_fdr))
+
+
 def test_long_chain_across_all_strips():
     """config 5: a tilted plane drains every column through all 8 strips; counts reach the row count."""
     from overflow_b200 import strips
