@@ -637,6 +637,22 @@ def run_native(args):
         barrier()
         ceiling_s = allmax(time.perf_counter() - t0)
 
+        # ... and with the two directions at once (PCIe is full duplex): what overlapping one step's download with the
+        # next step's upload could reach at best -- the step itself cannot (the counts need every code)
+        def copies_duplex():
+            with torch.cuda.stream(copy_stream):
+                runner.dem.copy_(h_dem, non_blocking=True)
+            h_fdr.copy_(runner.fdr, non_blocking=True)
+            h_fac.copy_(runner.fac, non_blocking=True)
+            torch.cuda.synchronize()
+
+        copies_duplex()
+        barrier()
+        t0 = time.perf_counter()
+        copies_duplex()
+        barrier()
+        duplex_s = allmax(time.perf_counter() - t0)
+
         def e2e_step():
             cur = torch.cuda.current_stream()
             runner.dem.copy_(h_dem, non_blocking=True)
@@ -672,6 +688,8 @@ def run_native(args):
             "ms_per_step": el * 1e3, "steps": args.e2e_steps,
             "host_copy_GBps": bytes_step / el / 1e9,
             "copies_only_ms": ceiling_s * 1e3, "copies_only_GBps": bytes_step / ceiling_s / 1e9,
+            "copies_duplex_ms": duplex_s * 1e3, "copies_duplex_GBps": bytes_step / duplex_s / 1e9,
+            "fraction_of_copy_ceiling": ceiling_s / el,
             "copies_only_note": "the same pinned copies with no kernels and no NCCL, all ranks at once: what the box's "
                                 "PCIe / host memory gives this transfer pattern",
             "host_binding": numa or "none",
