@@ -167,13 +167,16 @@ __device__ __forceinline__ int node_of_cell(int gy, int gx, const AccParams& p) 
 // downstream cell waited for -- and already holds that cell's offset and running sum.  Nothing is ever
 // written back to the cell's own word.  No edge is ever skipped: hand-offs into the halo, into NODATA cells
 // or out of the raster land in words nobody schedules.
-// Sources (cells without an in-tile upstream neighbour, more than half of a rough terrain) never enter a
-// queue: the lane that built their words hands their constant (1 << 8) - (1 << 27) down right after the
-// build.  The cells those hand-offs complete form level 1; from there on frontier levels are consecutive
-// segments of one queue of word addresses (a cell is appended once).  Halo words carry, in their offset
-// byte, how a path that steps onto them continues (KIND_*).  A level never grows, so once it is down to
-// TAIL_MAX cells one thread per cell simply follows its chain (it continues exactly when its hand-off
-// completed the next cell): no queue, no barriers.
+// Frontier levels are consecutive segments of one queue of word addresses (a cell is appended once); level 0
+// holds the sources that have a downstream cell (a source that flows nowhere needs no visit at all).  Halo
+// words carry, in their offset byte, how a path that steps onto them continues (KIND_*).  A level never
+// grows, so once it is down to TAIL_MAX cells one thread per cell simply follows its chain (it continues
+// exactly when its hand-off completed the next cell): no queue, no barriers.
+// (Measured in round 2 and dropped: handing the sources' constant down from the lanes that built them, without a
+// queue round trip -- with the atomics' returned values to find level 1: same time on the fractal, 14 % slower on
+// a tilted plane, where almost no cell is a source; as fire-and-forget reductions plus a rescan for level 1: 4 %
+// slower -- ptxas wraps every predicated shared atomic in a branch, and unpredicated ones adding 0 from every
+// lane cost atomic throughput.)
 constexpr int WP = 72;                 // word-array pitch; cell x sits in column x + 4, so quads are 16-byte aligned
 constexpr int WX0 = 4;
 constexpr int WORDS = (AT + 2) * WP;   // rows y = -1..64
@@ -257,16 +260,6 @@ __device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v) {
   asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory");
   return o;
 }
-// predicated form: the atomic is issued only where `cond` is non-zero (no branch); returns 0 elsewhere
-__device__ __forceinline__ uint32_t atoms_add_if(uint32_t a, uint32_t v, uint32_t cond) {
-  uint32_t o;
-  asm volatile(
-      "{ .reg .pred p; setp.ne.u32 p, %3, 0; mov.u32 %0, 0; @p atom.shared.add.u32 %0, [%1], %2; }"
-      : "=r"(o)
-      : "r"(a), "r"(v), "r"(cond)
-      : "memory");
-  return o;
-}
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   uint32_t d;
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
@@ -295,7 +288,10 @@ __device__ __forceinline__ uint32_t word_next(uint32_t aw, uint32_t w) {
   return aw + (uint32_t)((int32_t)(int8_t)(w & 0xFFu) * 4);
 }
 
-__global__ void __launch_bounds__(ACC_THREADS, 8) acc_tile_kernel(const __grid_constant__ CUtensorMap tm,
+#ifndef OFL_ACC_MIN_CTAS
+#define OFL_ACC_MIN_CTAS 8
+#endif
+__global__ void __launch_bounds__(ACC_THREADS, OFL_ACC_MIN_CTAS) acc_tile_kernel(const __grid_constant__ CUtensorMap tm,
                                                                 const AccParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   using SM = TileSmem;
@@ -437,24 +433,9 @@ __global__ void __launch_bounds__(ACC_THREADS, 8) acc_tile_kernel(const __grid_c
   }
   __syncthreads();  // every word is built; the code tile is dead from here and the queue takes its place
 
-  // ---- sources: the lane that built a source's word hands its count (the cell itself) down -- a constant --
-  //      without a queue round trip; the cells those hand-offs complete are level 1 of the queue (one
-  //      exclusive scan of the per-lane counts, one queue atomic per warp)
+  // ---- sources into the queue: one exclusive scan of the per-lane source counts, one queue atomic per warp
   {
-    uint32_t ready = 0;  // bit 4 * i + b: the hand-off of source (i, b) completed its downstream cell
-    uint32_t offs[4];    // the offset bytes of the lane's sixteen words (static; the other fields are live by now)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint4 wq = lds128(aw_lane + i * (2 * WP * 4));
-      offs[i] = prmt(prmt(wq.x, wq.y, 0x0040u), prmt(wq.z, wq.w, 0x0040u), 0x5410u);
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const uint32_t an = aw_lane + i * (2 * WP * 4) + 4 * b + (uint32_t)((int32_t)(int8_t)(offs[i] >> (8 * b)) * 4);
-        const uint32_t old = atoms_add_if(an, W_HANDOFF_SELF, srcs[i] & (0x80u << (8 * b)));
-        ready |= ((old & W_READY_MASK) == W_READY_VAL ? 1u : 0u) << (4 * i + b);
-      }
-    }
-    const uint32_t mine = __popc(ready);
+    const uint32_t mine = __popc(srcs[0]) + __popc(srcs[1]) + __popc(srcs[2]) + __popc(srcs[3]);
     uint32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -465,13 +446,13 @@ __global__ void __launch_bounds__(ACC_THREADS, 8) acc_tile_kernel(const __grid_c
     if (lane == 31) base = atoms_add(a_tail_v, incl);
     base = __shfl_sync(0xffffffffu, base, 31);
     uint32_t aq = a_q + 2 * (base + incl - mine);
+    const uint32_t qv = aw_lane;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        if (ready & (1u << (4 * i + b))) {
-          // queue entries: 16-bit shared addresses (checked at kernel entry)
-          sts16(aq, aw_lane + i * (2 * WP * 4) + 4 * b + (uint32_t)((int32_t)(int8_t)(offs[i] >> (8 * b)) * 4));
+        if (srcs[i] & (0x80u << (8 * b))) {
+          sts16(aq, qv + i * (2 * WP * 4) + 4 * b);
           aq += 2;
         }
       }
