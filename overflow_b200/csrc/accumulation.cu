@@ -886,7 +886,7 @@ struct PjArgs {
   int32_t* lists;        // 2 ping-pong lists of blocks * seg entries
   const int* counts0;    // !with_init: [blocks] active nodes per segment, published by pass A
   unsigned long long *S, *d0, *d1;
-  unsigned* sync;        // [0] barrier counter, [2 + j] nodes left after round j; zeroed before the launch
+  unsigned* sync;        // [0..1] grid barrier, [2 + j] nodes left after round j; zeroed before the launch
   int* leftover;         // set when max_rounds did not suffice: the forest has a cycle
   const int* run_flag;   // nullable: the whole solve is skipped (by every CTA alike) when this device word is 0
   PjSeg g;

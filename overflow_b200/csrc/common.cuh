@@ -107,17 +107,22 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       "l"(tm), "r"(x), "r"(y), "r"(smem_u32(bar))
       : "memory");
 }
-// Grid-wide barrier of a cooperatively launched kernel (every CTA resident): `counter` is a device word zeroed
-// before the launch, `generation` a per-thread count of the barriers passed so far.  Writes made before the barrier
-// are visible after it to loads that do not go through L1 (ld.global.cg / volatile).
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& generation) {
+// Grid-wide barrier of a cooperatively launched kernel (every CTA resident).  `bar` points at two device words
+// zeroed before the launch: bar[0] counts arrivals (monotonic), bar[1] is the generation released so far;
+// `generation` is a per-thread count of the barriers passed.  The last CTA to arrive releases the others, which
+// poll the release word -- not the word the arrivals are added to -- with a short sleep between polls: a thousand
+// CTAs spinning on the arrival counter itself made a barrier cost ~10 us.  Writes made before the barrier are
+// visible after it to loads that do not go through L1 (ld.global.cg / volatile).
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& generation) {
   __syncthreads();
   if (threadIdx.x == 0) {
     ++generation;
-    const unsigned target = generation * gridDim.x;
     __threadfence();
-    atomicAdd(counter, 1u);
-    while (*reinterpret_cast<volatile unsigned*>(counter) < target) {
+    const unsigned arrived = atomicAdd(&bar[0], 1u) + 1u;
+    if (arrived == generation * gridDim.x) {
+      atomicExch(&bar[1], generation);
+    } else {
+      while (*reinterpret_cast<volatile unsigned*>(&bar[1]) < generation) __nanosleep(32);
     }
     __threadfence();
   }

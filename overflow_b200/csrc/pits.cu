@@ -26,7 +26,7 @@ namespace ofl {
 namespace {
 
 constexpr int PT = 256;
-enum { PC_PITS = 0, PC_ROUNDS, PC_UNSOLVED, PC_BARRIER, PC_NEXT0, PC_NEXT1, PC_SLOTS = 16 };
+enum { PC_PITS = 0, PC_ROUNDS, PC_UNSOLVED, PC_BARRIER, PC_RELEASE, PC_NEXT0, PC_NEXT1, PC_SLOTS = 16 };
 
 __constant__ int p_dx[8] = {1, 1, 1, 0, -1, -1, -1, 0};  // breach_single_cell_pits.py:27-31
 __constant__ int p_dy[8] = {-1, 0, 1, 1, 1, 0, -1, -1};
