@@ -280,7 +280,8 @@ int ofl_fix_flats_f32(const float* dem, uint8_t* fdr, int64_t rows, int64_t cols
  *   unsolved  int8 out, dense rows x cols: 1 where a single-cell pit could not be breached (the reference's result)
  *   info      nullable int64[3] out: pits found, pits left unsolved, rounds of the dependency-ordered second pass
  *   workspace device scratch of ofl_pits_workspace_bytes (NULL: library-owned, cached)
- * One chunk of fewer than 2^31 cells.  Synchronises the stream.
+ * One chunk of at most 2^32 cells (a 65536 x 65536 raster; cell indices are unsigned 32-bit).  Synchronises the
+ * stream once, at the end.
  */
 size_t ofl_pits_workspace_bytes(int64_t rows, int64_t cols);
 int ofl_breach_single_cell_pits_f32(float* chunk, int64_t rows, int64_t cols, int64_t ld_chunk, double nodata,

@@ -37,13 +37,13 @@ __constant__ int p_breach[16] = {0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 0}
 // pass 1 (:38-50): pits of the chunk as it came in -> unsolved = waiting = 1, index appended to the list
 __global__ void __launch_bounds__(PT)
 pits_detect_kernel(const float* __restrict__ chunk, int rows, int cols, int64_t ld, float nd_f, bool nd_exact,
-                   int8_t* unsolved, uint8_t* waiting, int* list, unsigned* cnt) {
+                   int8_t* unsolved, uint8_t* waiting, unsigned* list, unsigned* cnt) {
   __shared__ unsigned warp_off[PT / 32];
   __shared__ unsigned cta_base;
-  const unsigned n = (unsigned)rows * (unsigned)cols;
+  const unsigned long long n = (unsigned long long)rows * (unsigned long long)cols;  // up to 2^32: indices fit 32 bits
   const unsigned i = blockIdx.x * PT + threadIdx.x;
   bool pit = false;
-  if (i < n) {
+  if ((unsigned long long)i < n) {
     const int r = (int)(i / (unsigned)cols), c = (int)(i - (unsigned)r * (unsigned)cols);
     if (r >= 2 && r < rows - 2 && c >= 2 && c < cols - 2) {
       const float* at = chunk + (int64_t)r * ld + c;
@@ -79,7 +79,7 @@ pits_detect_kernel(const float* __restrict__ chunk, int rows, int cols, int64_t 
     cta_base = run ? atomicAdd(&cnt[PC_PITS], run) : 0u;
   }
   __syncthreads();
-  if (pit) list[cta_base + warp_off[w] + __popc(m & ((1u << lane) - 1u))] = (int)i;
+  if (pit) list[cta_base + warp_off[w] + __popc(m & ((1u << lane) - 1u))] = i;
 }
 
 // pass 1, vector form (dense pitch and columns that are multiples of four, 16-byte aligned rows): a thread owns four
@@ -87,7 +87,7 @@ pits_detect_kernel(const float* __restrict__ chunk, int rows, int cols, int64_t 
 // one 32-bit store each; a CTA covers 128 columns x 8 rows and makes one list reservation.
 __global__ void __launch_bounds__(PT)
 pits_detect4_kernel(const float* __restrict__ chunk, int rows, int cols, int64_t ld, float nd_f, bool nd_exact,
-                    int8_t* unsolved, uint8_t* waiting, int* list, unsigned* cnt) {
+                    int8_t* unsolved, uint8_t* waiting, unsigned* list, unsigned* cnt) {
   __shared__ unsigned warp_off[PT / 32];
   __shared__ unsigned cta_base;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -159,7 +159,7 @@ pits_detect4_kernel(const float* __restrict__ chunk, int rows, int cols, int64_t
   unsigned pos = cta_base + warp_off[w] + incl - mine;
 #pragma unroll
   for (int j = 0; j < 4; ++j)
-    if (pits & (1u << j)) list[pos++] = r * cols + c + j;
+    if (pits & (1u << j)) list[pos++] = (unsigned)r * (unsigned)cols + (unsigned)(c + j);
 }
 
 // pass 2 (:52-63) in dependency-ordered rounds, ONE persistent kernel (cooperative launch, grid barriers).
@@ -168,19 +168,19 @@ pits_detect4_kernel(const float* __restrict__ chunk, int rows, int cols, int64_t
 // reference's sequential loop would breach them, the others go to the next round's list.  The earliest waiting pit is
 // always ready, so the rounds end.  Everything other CTAs wrote in earlier rounds is read past L1 (ld.global.cg).
 __global__ void __launch_bounds__(PT)
-pits_rounds_kernel(int* list_a, int* list_b, uint8_t* waiting, uint8_t* ready, float* chunk, int rows, int cols,
+pits_rounds_kernel(unsigned* list_a, unsigned* list_b, uint8_t* waiting, uint8_t* ready, float* chunk, int rows, int cols,
                    int64_t ld, double nodata, int8_t* unsolved, unsigned* cnt) {
   unsigned generation = 0;
   unsigned n_cur = *reinterpret_cast<volatile unsigned*>(&cnt[PC_PITS]);
   const unsigned tid = blockIdx.x * PT + threadIdx.x, nthr = gridDim.x * PT;
   unsigned rounds = 0;
-  int* cur = list_a;
-  int* nxt = list_b;
+  unsigned* cur = list_a;
+  unsigned* nxt = list_b;
   while (n_cur) {
     unsigned* n_next = &cnt[PC_NEXT0 + ((rounds + 1) & 1)];
     for (unsigned t = tid; t < n_cur; t += nthr) {
-      const int i = __ldcg(&cur[t]);
-      const int r = i / cols, c = i - r * cols;
+      const unsigned i = __ldcg(&cur[t]);
+      const int r = (int)(i / (unsigned)cols), c = (int)(i - (unsigned)r * (unsigned)cols);
       bool ok = true;
       for (int dr = -3; dr <= 0 && ok; ++dr) {
         const int rr = r + dr;
@@ -196,12 +196,12 @@ pits_rounds_kernel(int* list_a, int* list_b, uint8_t* waiting, uint8_t* ready, f
     }
     grid_barrier(&cnt[PC_BARRIER], generation);
     for (unsigned t = tid; t < n_cur; t += nthr) {
-      const int i = __ldcg(&cur[t]);
+      const unsigned i = __ldcg(&cur[t]);
       if (!ready[t]) {  // written by this thread before the barrier
         nxt[atomicAdd(n_next, 1u)] = i;
         continue;
       }
-      const int r = i / cols, c = i - r * cols;
+      const int r = (int)(i / (unsigned)cols), c = (int)(i - (unsigned)r * (unsigned)cols);
       float* at = chunk + (int64_t)r * ld + c;
       const float z = __ldcg(at);
       bool solved = false;
@@ -223,7 +223,7 @@ pits_rounds_kernel(int* list_a, int* list_b, uint8_t* waiting, uint8_t* ready, f
     n_cur = *reinterpret_cast<volatile unsigned*>(n_next);
     ++rounds;
     if (tid == 0) cnt[PC_NEXT0 + ((rounds + 1) & 1)] = 0;  // next round's counter: not touched before the next barrier
-    int* t2 = cur;
+    unsigned* t2 = cur;
     cur = nxt;
     nxt = t2;
   }
@@ -243,14 +243,14 @@ size_t pits_workspace_bytes(int64_t rows, int64_t cols) {
 // info (host, nullable): {pits found, pits left unsolved, rounds}.  Synchronises the stream (once, at the end).
 int launch_breach_pits(float* chunk, int64_t rows, int64_t cols, int64_t ld, double nodata, int8_t* unsolved,
                        int64_t* info, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  OFL_REQUIRE(rows > 0 && cols > 0 && rows * cols < (int64_t)INT32_MAX, OFL_ERR_INVALID,
-              "pit breaching works on one chunk of fewer than 2^31 cells (got %lld x %lld)", (long long)rows, (long long)cols);
+  OFL_REQUIRE(rows > 0 && cols > 0 && rows < (1ll << 31) && cols < (1ll << 31) && rows * cols <= (1ll << 32), OFL_ERR_INVALID,
+              "pit breaching works on one chunk of at most 2^32 cells (got %lld x %lld)", (long long)rows, (long long)cols);
   OFL_REQUIRE(workspace_bytes >= pits_workspace_bytes(rows, cols), OFL_ERR_WORKSPACE, "pits workspace too small");
   const size_t n = (size_t)rows * (size_t)cols;
   char* p = static_cast<char*>(workspace);
   // pits are never adjacent, so there are at most n / 4 of them: two lists fit the n ints
-  int* list_a = reinterpret_cast<int*>(p);
-  int* list_b = list_a + (n + 1) / 2;
+  unsigned* list_a = reinterpret_cast<unsigned*>(p);
+  unsigned* list_b = list_a + (n + 1) / 2;
   uint8_t* waiting = reinterpret_cast<uint8_t*>(p + align256(n * sizeof(int)));
   uint8_t* ready = waiting + align256(n);
   unsigned* cnt = reinterpret_cast<unsigned*>(ready + align256(n));

@@ -147,3 +147,35 @@ def test_file_driver_chunking_matches_the_reference_loop(tmp_path):
             h, w = min(size, 70 - r0), min(size, 90 - c0)
             want[r0 : r0 + h, c0 : c0 + w] = res[2 : 2 + h, 2 : 2 + w]
     assert same_bits(open_raster(out).GetRasterBand(1).ReadAsArray(), want)
+
+
+def test_chunk_of_more_than_2_31_cells():
+    """Cell indices are unsigned 32-bit: a 40000 x 65536 chunk (2.6e9 cells).  Terrain in a band at the top and in a
+    band below cell 2^31, a plateau (no pits) in between; each band equals the oracle run on the band alone."""
+    import torch
+
+    from overflow_b200 import device as dev
+
+    rows, cols, band = 40000, 65536, 192
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 * 2**30:
+        pytest.skip("needs 40 GB of device memory")
+    chunk = torch.full((rows, cols), 5000.0, dtype=torch.float32, device="cuda")
+    lo = rows - band - 64  # far below row 32768, where the cell index passes 2^31
+    width = 4000  # terrain in columns 8 .. 8 + width only: a plateau (no pits) everywhere else
+    chunk[8 : 8 + band, 8 : 8 + width] = dev.synth_dem(band, width, seed=3, kind=0, holes_permille=5)
+    chunk[lo : lo + band, 8 : 8 + width] = dev.synth_dem(band, width, seed=4, kind=0, holes_permille=5)
+    want = []
+    for r0 in (8, lo):  # the terrain with its plateau margin: exactly what the whole chunk shows the pits there
+        w = chunk[r0 - 6 : r0 + band + 6, : width + 16].cpu().numpy().copy()
+        want.append(oracle.breach_single_cell_pits_in_chunk(w, synth.NODATA))
+    unsolved, info = dev.breach_single_cell_pits(chunk, synth.NODATA)
+    assert info[0] > 5000 and info[2] >= 2
+    n_pits = 0
+    for r0, (w_chunk, w_uns) in zip((8, lo), want):
+        got = chunk[r0 - 6 : r0 + band + 6, : width + 16].cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), w_chunk.view(np.uint32))
+        # the oracle's unsolved raster counts the window's pits that stayed unsolved; its pits are the chunk's
+        assert np.array_equal(unsolved[r0 - 6 : r0 + band + 6, : width + 16].cpu().numpy(), w_uns)
+        n_pits += 1
+    assert int(unsolved.sum().item()) == info[1]
