@@ -198,8 +198,8 @@ def _vnoise(fx, fy, s):
     return top + (bot - top) * ty
 
 
-SERP_WALL = np.float32(3.0e38)
-SERP_ORD0 = 0x7EFFFFFF
+SERP_WALL = np.float32(8.0e37)
+SERP_ORD0 = 0x7E000000
 
 
 def serpentine_ulp(gr, gc, total_rows, total_cols):

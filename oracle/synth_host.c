@@ -39,7 +39,7 @@ static float sh_vnoise(float fx, float fy, uint32_t s) {
 }
 
 static float sh_serpentine(int64_t gr, int64_t c, int64_t total_rows, int64_t cols) {
-  const float wall = 3.0e38f;
+  const float wall = 8.0e37f;
   if (gr <= 0 || gr >= total_rows - 1 || c <= 0 || c >= cols - 1) return wall;
   const int64_t wc = cols - 2, n_runs = (total_rows - 1) / 2;
   int64_t k;
@@ -52,7 +52,7 @@ static float sh_serpentine(int64_t gr, int64_t c, int64_t total_rows, int64_t co
     if (c != ((m & 1) ? 1 : cols - 2)) return wall;
     k = m * (wc + 1) + wc;
   }
-  const long long ord = 0x7EFFFFFFll - (long long)k;
+  const long long ord = 0x7E000000ll - (long long)k;
   const uint32_t bits = ord >= 0 ? (uint32_t)ord : (0x80000000u | (uint32_t)(-ord));
   float z;
   memcpy(&z, &bits, 4);

@@ -59,8 +59,13 @@ namespace ofl {
 #endif
 constexpr int DIR_RB = OFL_DIR_RB;          // rows per TMA box / pipeline stage
 constexpr int DIR_STAGES = OFL_DIR_STAGES;  // stages per warp
-constexpr int DIR_BOXW = 136;    // 4 apron + 128 band + 4 apron floats
-constexpr int DIR_BAND = 128;    // columns per warp band
+#ifndef OFL_DIR_NC
+#define OFL_DIR_NC 4
+#endif
+constexpr int NC = OFL_DIR_NC;   // adjacent cells per lane (4, or 2: half the per-thread state, twice the warps)
+static_assert(NC == 2 || NC == 4, "a lane owns two or four cells");
+constexpr int DIR_BAND = 32 * NC;       // columns per warp band
+constexpr int DIR_BOXW = DIR_BAND + 8;  // 4 apron + band + 4 apron floats
 constexpr int DIR_WARPS = OFL_DIR_WARPS;    // warps per CTA
 constexpr int DIR_STAGE_FLOATS = DIR_RB * DIR_BOXW;
 constexpr uint32_t DIR_STAGE_BYTES = DIR_STAGE_FLOATS * 4;
@@ -175,11 +180,42 @@ __device__ __forceinline__ float d8_fast(float dE, float dNE, float dN, float dN
 // One input row as a lane sees it: its 4 cells plus one cell either side (nodata already -inf), and the
 // float32 differences between the row above and this row, formed when this row arrived.
 struct DirRow {
-  float v[6];     // columns xl-1 .. xl+4
-  float uS[4];    // above[j+1] - v[j+1]   (cell j of the row above -> its S neighbour)
-  float uSE[5];   // above[j]   - v[j+1]   (cell j-1 of the row above -> its SE neighbour)
-  float uSW[5];   // above[j+1] - v[j]     (cell j of the row above -> its SW neighbour)
+  float v[NC + 2];    // columns xl-1 .. xl+NC
+  float uS[NC];       // above[j+1] - v[j+1]   (cell j of the row above -> its S neighbour)
+  float uSE[NC + 1];  // above[j]   - v[j+1]   (cell j-1 of the row above -> its SE neighbour)
+  float uSW[NC + 1];  // above[j+1] - v[j]     (cell j of the row above -> its SW neighbour)
 };
+
+// a lane's NC cells of one row plus one cell either side, from the row's slice of the TMA box (q: the lane's first
+// cell minus the 4-float apron)
+__device__ __forceinline__ void dir_load_cells(const float* q, float* v) {
+  v[0] = q[3];
+  if (NC == 4) {
+    const float4 m = *reinterpret_cast<const float4*>(q + 4);
+    v[1] = m.x;
+    v[2] = m.y;
+    v[3] = m.z;
+    v[NC] = m.w;
+  } else {
+    const float2 m = *reinterpret_cast<const float2*>(q + 4);
+    v[1] = m.x;
+    v[2] = m.y;
+  }
+  v[NC + 1] = q[4 + NC];
+}
+
+__device__ __forceinline__ void dir_store_codes(uint8_t* o, uint32_t packed, bool all_inside, int xl, int W) {
+  if (all_inside) {
+    if (NC == 4)
+      *reinterpret_cast<uint32_t*>(o) = packed;
+    else
+      *reinterpret_cast<uint16_t*>(o) = (uint16_t)packed;
+  } else {
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+      if (xl + j < W) o[j] = (uint8_t)(packed >> (8 * j));
+  }
+}
 
 struct DirWarp {
   float* tiles;     // this warp's ring of stages
@@ -199,7 +235,7 @@ __device__ __forceinline__ void direction_item(const CUtensorMap* tm, const DirP
   const int iy0 = y0 + p.y_off - 1;  // first input row this item reads
   const int n_in = (y1 - y0) + 2;
   const int nblk = (n_in + DIR_RB - 1) / DIR_RB;
-  const int xl = x0 + 4 * lane;  // first of this lane's 4 columns
+  const int xl = x0 + NC * lane;  // first of this lane's NC columns
   float* const tiles = wp.tiles;
   uint64_t* const bars = wp.bars;
   const uint32_t g0 = wp.g0;
@@ -221,17 +257,11 @@ __device__ __forceinline__ void direction_item(const CUtensorMap* tm, const DirP
   auto raw_row = [&](int rel, float* v) {
     const int iy = iy0 + rel;
     const uint32_t s = (g0 + rel / DIR_RB) % DIR_STAGES;
-    const float* q = tiles + s * DIR_STAGE_FLOATS + (rel % DIR_RB) * DIR_BOXW + 4 * lane;
-    const float4 m = *reinterpret_cast<const float4*>(q + 4);
-    v[0] = q[3];
-    v[1] = m.x;
-    v[2] = m.y;
-    v[3] = m.z;
-    v[4] = m.w;
-    v[5] = q[8];
+    const float* q = tiles + s * DIR_STAGE_FLOATS + (rel % DIR_RB) * DIR_BOXW + NC * lane;
+    dir_load_cells(q, v);
     const bool row_out = iy < 0 || iy >= p.in_rows;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
+    for (int j = 0; j < NC + 2; ++j) {
       const int cx = xl - 1 + j;
       if (row_out || (EDGE && (cx < 0 || cx >= p.W))) v[j] = p.fill_raw;
     }
@@ -239,56 +269,42 @@ __device__ __forceinline__ void direction_item(const CUtensorMap* tm, const DirP
 
   // row rr of the box at `t` into r.v; GUARD adds the out-of-array row check (first / last box only)
   auto load_row = [&](const float* t, int rr, int i, DirRow& r, bool guard) {
-    const float* q = t + rr * DIR_BOXW;
-    const float4 m = *reinterpret_cast<const float4*>(q + 4);
-    r.v[0] = q[3];
-    r.v[1] = m.x;
-    r.v[2] = m.y;
-    r.v[3] = m.z;
-    r.v[4] = m.w;
-    r.v[5] = q[8];
+    dir_load_cells(t + rr * DIR_BOXW, r.v);
     if (guard && (iy0 + i < 0 || iy0 + i >= p.in_rows)) {
 #pragma unroll
-      for (int j = 0; j < 6; ++j) r.v[j] = p.fillv;
+      for (int j = 0; j < NC + 2; ++j) r.v[j] = p.fillv;
     } else if (EDGE) {
 #pragma unroll
-      for (int j = 0; j < 6; ++j) {
+      for (int j = 0; j < NC + 2; ++j) {
         const int cx = xl - 1 + j;
         if (cx < 0 || cx >= p.W) r.v[j] = p.fillv;
       }
     }
     bool any_nd = false;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) any_nd |= (r.v[j] == nd);
+    for (int j = 0; j < NC + 2; ++j) any_nd |= (r.v[j] == nd);
     if (any_nd) {
 #pragma unroll
-      for (int j = 0; j < 6; ++j) r.v[j] = (r.v[j] == nd) ? -INFINITY : r.v[j];
+      for (int j = 0; j < NC + 2; ++j) r.v[j] = (r.v[j] == nd) ? -INFINITY : r.v[j];
     }
   };
 
   uint8_t* orow = p.out + (int64_t)y0 * p.ld_out + xl;  // next output row of this lane
-  const bool full_store = xl + 3 < p.W;
+  const bool full_store = xl + NC - 1 < p.W;
 
   // exact codes of the lane's four cells of input row i - 1 (output row y0 + i - 2), stored over the fast ones
   auto fixup = [&](int i) {
-    float r0[6], r1[6], r2[6];
+    float r0[NC + 2], r1[NC + 2], r2[NC + 2];
     raw_row(i - 2, r0);
     raw_row(i - 1, r1);
     raw_row(i, r2);
     uint32_t packed = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < NC; ++j)
       packed |= d8_exact(r1[j + 1], /*E*/ r1[j + 2], /*NE*/ r0[j + 2], /*N*/ r0[j + 1], /*NW*/ r0[j], /*W*/ r1[j],
                          /*SW*/ r2[j], /*S*/ r2[j + 1], /*SE*/ r2[j + 2], nd)
                 << (8 * j);
-    uint8_t* o = p.out + (int64_t)(y0 + i - 2) * p.ld_out + xl;
-    if (!EDGE || full_store) {
-      *reinterpret_cast<uint32_t*>(o) = packed;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (xl + j < p.W) o[j] = (uint8_t)(packed >> (8 * j));
-    }
+    dir_store_codes(p.out + (int64_t)(y0 + i - 2) * p.ld_out + xl, packed, !EDGE || full_store, xl, p.W);
   };
 
   // differences between row b (above) and the new row c; emits b's fast-path codes when b is an output row.
@@ -296,33 +312,32 @@ __device__ __forceinline__ void direction_item(const CUtensorMap* tm, const DirP
   // (fixup), so the rows of a box flow through without a branch on the end of each row's dependency chain.
   auto diffs_and_emit = [&](const DirRow& b, DirRow& c, bool emit) -> float {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) c.uS[j] = __fsub_rn(b.v[j + 1], c.v[j + 1]);
+    for (int j = 0; j < NC; ++j) c.uS[j] = __fsub_rn(b.v[j + 1], c.v[j + 1]);
 #pragma unroll
-    for (int j = 0; j < 5; ++j) c.uSE[j] = __fsub_rn(b.v[j], c.v[j + 1]);
+    for (int j = 0; j < NC + 1; ++j) c.uSE[j] = __fsub_rn(b.v[j], c.v[j + 1]);
 #pragma unroll
-    for (int j = 0; j < 5; ++j) c.uSW[j] = __fsub_rn(b.v[j + 1], c.v[j]);
+    for (int j = 0; j < NC + 1; ++j) c.uSW[j] = __fsub_rn(b.v[j + 1], c.v[j]);
     if (!emit) return 0.f;
-    float hE[5];
+    float hE[NC + 1];
 #pragma unroll
-    for (int j = 0; j < 5; ++j) hE[j] = __fsub_rn(b.v[j], b.v[j + 1]);  // cell j-1 -> E
-    float special = 0.f, code[4];
+    for (int j = 0; j < NC + 1; ++j) hE[j] = __fsub_rn(b.v[j], b.v[j + 1]);  // cell j-1 -> E
+    float special = 0.f, code[NC];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < NC; ++j)
       code[j] = d8_fast(/*E*/ hE[j + 1], /*NE*/ -b.uSW[j + 1], /*N*/ -b.uS[j], /*NW*/ -b.uSE[j], /*W*/ -hE[j],
                         /*SW*/ c.uSW[j], /*S*/ c.uS[j], /*SE*/ c.uSE[j + 1], special);
-    // a centre that is NODATA (-inf by now) or not finite: one test for the lane's four cells
-    special = __fadd_rn(special, f_leu(INFINITY, fabsf(__fadd_rn(__fadd_rn(b.v[1], b.v[2]), __fadd_rn(b.v[3], b.v[4])))));
+    // a centre that is NODATA (-inf by now) or not finite: one test for the lane's cells
+    float csum = __fadd_rn(b.v[1], b.v[2]);
+    if (NC == 4) csum = __fadd_rn(csum, __fadd_rn(b.v[3], b.v[NC]));
+    special = __fadd_rn(special, f_leu(INFINITY, fabsf(csum)));
     // codes are 0..8: pack pairs exactly in float, then take the low 16 bits of (value + 2^23)
     const uint32_t lo = __float_as_uint(__fadd_rn(__fmaf_rn(code[1], 256.f, code[0]), 8388608.f));
-    const uint32_t hi = __float_as_uint(__fadd_rn(__fmaf_rn(code[3], 256.f, code[2]), 8388608.f));
-    const uint32_t packed = __byte_perm(lo, hi, 0x5410);
-    if (!EDGE || full_store) {
-      *reinterpret_cast<uint32_t*>(orow) = packed;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (xl + j < p.W) orow[j] = (uint8_t)(packed >> (8 * j));
+    uint32_t packed = lo & 0xFFFFu;
+    if (NC == 4) {
+      const uint32_t hi = __float_as_uint(__fadd_rn(__fmaf_rn(code[NC - 1], 256.f, code[NC - 2]), 8388608.f));
+      packed = __byte_perm(lo, hi, 0x5410);
     }
+    dir_store_codes(orow, packed, !EDGE || full_store, xl, p.W);
     orow += p.ld_out;
     return special;
   };
@@ -332,7 +347,7 @@ __device__ __forceinline__ void direction_item(const CUtensorMap* tm, const DirP
   for (int k = 0; k < nblk; ++k) {
     const uint32_t s = (g0 + k) % DIR_STAGES;
     mbar_wait(&bars[s], ((g0 + k) / DIR_STAGES) & 1);
-    const float* t = tiles + s * DIR_STAGE_FLOATS + 4 * lane;
+    const float* t = tiles + s * DIR_STAGE_FLOATS + NC * lane;
     const int ib = k * DIR_RB;
     float sp[DIR_RB];
     if (k > 0 && ib + DIR_RB <= n_in - 1) {

@@ -34,13 +34,13 @@ __device__ float vnoise(float fx, float fy, uint32_t s) {
 
 // Walled serpentine (SURVEY 8d config 5 ii): ONE channel of about rows*cols/2 cells.  Channel rows are the odd
 // rows 1, 3, ..; it runs east on rows 1, 5, .. and west on rows 3, 7, .. over columns 1 .. cols-2 and steps down
-// through a one-cell gap in the wall row at the end of each run.  Everything else is wall (3e38), which drains
+// through a one-cell gap in the wall row at the end of each run.  Everything else is wall (8e37), which drains
 // into the channel; the raster's outer ring is wall, so the channel ends in an interior pit.  The k-th channel
-// cell holds the k-th float32 below 0x7EFFFFFF in the total order of finite floats (bit patterns walked down
+// cell holds the k-th float32 below 0x7E000000 in the total order of finite floats (bit patterns walked down
 // through +0 into the negative denormals, -0 skipped): strictly decreasing along the chain for up to 4.2e9
 // cells, every difference between consecutive cells exact (one ulp), no two cells equal.
-constexpr float SERP_WALL = 3.0e38f;
-constexpr long long SERP_ORD0 = 0x7EFFFFFFll;
+constexpr float SERP_WALL = 8.0e37f;  // four of them still add up to a finite float32
+constexpr long long SERP_ORD0 = 0x7E000000ll;  // 4.25e37, below the walls
 
 __device__ __forceinline__ float serpentine_cell(int64_t gr, int64_t c, int64_t total_rows, int64_t cols) {
   if (gr <= 0 || gr >= total_rows - 1 || c <= 0 || c >= cols - 1) return SERP_WALL;
