@@ -170,6 +170,7 @@ class StripPipeline:
         self.fac_edge = e.empty((2, c), torch.int64)  # the neighbours' boundary counts (recurrence check only)
         self.fdr_halo.zero_()
         self.rec_all.zero_()
+        self.fill_edge_halos()  # the raster's own top / bottom halo rows never change
 
     # ---- data
     @property
@@ -194,8 +195,11 @@ class StripPipeline:
         if not self.has_below:
             self.dem_halo[-1].fill_(np.float32(self.nodata).item())
 
-    def direction(self):
-        self.engine.direction(self.dem_halo, self.nodata, self.fdr)
+    def direction(self, r0=0, r1=None):
+        """Codes of strip rows [r0, r1) (default: all); they read DEM rows r0 - 1 .. r1 of the strip."""
+        r1 = self.h if r1 is None else r1
+        if r1 > r0:
+            self.engine.direction(self.dem_halo[r0 : r1 + 2], self.nodata, self.fdr[r0:r1])
 
     def accum_local(self):
         self.engine.accum_local(self.fdr_halo, self.has_above, self.has_below, self.fac, self.ws, self.rec)
@@ -210,9 +214,9 @@ class StripPipeline:
         self.engine.flags(self.ws, self.h, self.cols, self.bws, self.world, self.flags)
 
     # ---- distributed step (one process per strip)
-    def _exchange(self, first, last, above, below):
-        """Send `first` / `last` (my first / last row of something) to the strip above / below; receive theirs
-        into `above` / `below`."""
+    def _exchange_start(self, first, last, above, below):
+        """Start sending `first` / `last` (my first / last row of something) to the strip above / below and receiving
+        theirs into `above` / `below`; returns the requests (wait on them before touching `above` / `below`)."""
         import torch.distributed as dist
 
         ops = []
@@ -222,9 +226,11 @@ class StripPipeline:
         if self.has_below:
             ops.append(dist.P2POp(dist.isend, last, self.rank + 1))
             ops.append(dist.P2POp(dist.irecv, below, self.rank + 1))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    def _exchange(self, first, last, above, below):
+        for req in self._exchange_start(first, last, above, below):
+            req.wait()
 
     def _exchange_halo(self, buf):
         self._exchange(buf[1], buf[-2], buf[0], buf[-1])
@@ -238,12 +244,18 @@ class StripPipeline:
         others waiting in a collective."""
         import torch.distributed as dist
 
-        self.fill_edge_halos()
         if self.world > 1:
-            self._exchange_halo(self.dem_halo)
-        self.direction()
-        if self.world > 1:
+            # the DEM halo rows travel while the stencil works on the rows that do not need them
+            d = self.dem_halo
+            reqs = self._exchange_start(d[1], d[-2], d[0], d[-1])
+            self.direction(1, self.h - 1)
+            for req in reqs:
+                req.wait()
+            self.direction(0, 1)
+            self.direction(self.h - 1, self.h)
             self._exchange_halo(self.fdr_halo)
+        else:
+            self.direction()
         self.accum_local()
         if self.world > 1:
             if dist.get_backend() == "gloo":  # CPU tests
