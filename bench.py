@@ -34,7 +34,8 @@ DIR_BYTES_PER_CELL = 5.0   # 4 B float32 read + 1 B code write            (SURVE
 ACC_BYTES_PER_CELL = 9.0   # 1 B code read + 8 B int64 count write         
 # accumulation: 9 B/cell = 1 B code read (pass A) + 8 B count write (final pass)
 PHASE_BYTES = {"direction": 5.0, "acc_tile_a": 1.0, "acc_tile_b": 8.0}
-KINDS = {0: "fractal value-noise", 1: "terraced fractal", 2: "tilted plane", 3: "walled serpentine (one channel)"}
+KINDS = {0: "fractal value-noise", 1: "terraced fractal", 2: "tilted plane", 3: "walled serpentine (one channel, east-west runs)",
+         4: "walled serpentine (one channel, north-south runs)"}
 
 
 def measured_hbm_peak():
@@ -520,8 +521,11 @@ def run_native(args):
         for name, size, kind, holes, relief, note in (
             ("terraced_16k", min(S, 16384), 1, 50, 200.0, "config 4: 1 m terraces (large flats, code 8), 5 % nodata holes"),
             ("tilted_plane", S, 2, 0, 1000.0, "config 5(i): every column one chain of `rows` cells through all strips"),
-            ("serpentine", S, 3, 0, 1000.0, "config 5(ii): ONE channel of ~rows*cols/2 cells crossing every strip "
-                                            "boundary rows/2 times, walls draining into it, a single interior outlet"),
+            ("serpentine", S, 3, 0, 1000.0, "config 5(ii): ONE channel of ~rows*cols/2 cells through every tile (east-west "
+                                            "runs, stepping down at the ends), walls draining into it, a single interior "
+                                            "outlet; the perimeter graph is one chain of 33 million nodes at 64k"),
+            ("serpentine_ns", S, 4, 0, 1000.0, "config 5(ii) transposed: the channel runs north-south and crosses every "
+                                               "row-strip boundary cols/2 times (the strip-boundary forest is one chain)"),
         ):
             if size == S:
                 load(args.seed, kind, holes, relief)

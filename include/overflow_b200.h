@@ -296,6 +296,7 @@ int ofl_breach_single_cell_pits_f32(float* chunk, int64_t rows, int64_t cols, in
  *   kind 2: tilted plane draining south-east                   holes_permille: nodata rectangles
  *   kind 3: walled serpentine, ONE channel of about rows * cols / 2 cells through the whole raster (every other
  *           row, alternating east / west, consecutive float32 values walked downwards), walls draining into it
+ *   kind 4: the same channel transposed -- it runs north-south and crosses every row-strip boundary cols / 2 times
  */
 int ofl_synth_dem_f32(float* dem, int64_t rows, int64_t cols, int64_t ld_dem, int64_t row0, int64_t total_rows,
                       uint64_t seed, int kind, float relief, int holes_permille, float nodata, void* stream);

@@ -227,7 +227,8 @@ def serpentine_ulp(gr, gc, total_rows, total_cols):
 
 def device_dem(rows, cols, row0=0, col0=0, total_rows=None, total_cols=None, seed=0, kind=0, relief=1000.0,
                holes_permille=0, nodata=NODATA):
-    """The DEM ofl_synth_dem_f32 writes (kind 0 fractal value noise, 1 terraces, 2 tilted plane, 3 serpentine),
+    """The DEM ofl_synth_dem_f32 writes (kind 0 fractal value noise, 1 terraces, 2 tilted plane, 3 serpentine, 4 the
+    serpentine transposed),
     rows row0 .. row0+rows and columns col0 .. col0+cols of a total_rows x total_cols raster, computed on the host."""
     f32 = np.float32
     total_rows = rows if total_rows is None else total_rows
@@ -240,6 +241,8 @@ def device_dem(rows, cols, row0=0, col0=0, total_rows=None, total_cols=None, see
         z = np.broadcast_to(z, (rows, cols)).astype(f32)
     elif kind == 3:
         z = serpentine_ulp(gr, gc, total_rows, total_cols)
+    elif kind == 4:  # the same channel transposed: it runs north-south
+        z = serpentine_ulp(gc, gr, total_cols, total_rows)
     else:
         amp, norm, freq = f32(1.0), f32(0.0), f32(1.0 / 4096.0)
         total = np.zeros((rows, cols), dtype=f32)

@@ -76,6 +76,8 @@ void orc_synth_dem_f32(float* dem, int64_t rows, int64_t cols, int64_t ld, int64
         z = (float)(total_rows - 1 - gr) + 0.25f * (float)(total_cols - 1 - c);
       } else if (kind == 3) {
         z = sh_serpentine(gr, c, total_rows, total_cols);
+      } else if (kind == 4) {
+        z = sh_serpentine(c, gr, total_cols, total_rows);
       } else {
         float amp = 1.f, sum = 0.f, norm = 0.f, freq = 1.0f / 4096.0f;
         for (int o = 0; o < 12; ++o) {

@@ -702,8 +702,8 @@ int ofl_synth_dem_f32(float* dem, int64_t rows, int64_t cols, int64_t ld_dem, in
                       uint64_t seed, int kind, float relief, int holes_permille, float nodata, void* stream) {
   OFL_REQUIRE(rows >= 0 && cols >= 0 && ld_dem >= cols, OFL_ERR_INVALID, "bad raster size");
   OFL_REQUIRE(dem != nullptr || rows * cols == 0, OFL_ERR_INVALID, "null raster pointer");
-  OFL_REQUIRE(kind >= 0 && kind <= 3, OFL_ERR_INVALID, "unknown synthetic DEM kind %d", kind);
-  OFL_REQUIRE(kind != 3 || total_rows / 2 * cols < 0xFD000000ll, OFL_ERR_INVALID,
+  OFL_REQUIRE(kind >= 0 && kind <= 4, OFL_ERR_INVALID, "unknown synthetic DEM kind %d", kind);
+  OFL_REQUIRE((kind != 3 && kind != 4) || total_rows / 2 * cols < 0xFD000000ll, OFL_ERR_INVALID,
               "serpentine DEM: the chain would run out of finite float32 values");
   int rc = ensure_init();
   if (rc != OFL_OK) return rc;

@@ -77,6 +77,9 @@ __global__ void synth_kernel(float* dem, int64_t rows, int64_t cols, int64_t ld,
       z = (float)(total_rows - 1 - gr) + 0.25f * (float)(cols - 1 - c);
     } else if (kind == 3) {
       z = serpentine_cell(gr, c, total_rows, cols);
+    } else if (kind == 4) {
+      z = serpentine_cell(c, gr, cols, total_rows);  // the same channel transposed: runs north-south, crossing every
+                                                     // row-strip boundary cols / 2 times
     } else {
       // 12 octaves, persistence 0.55: rough fractal relief (many local pits, like beta ~ 2 spectra)
       float amp = 1.f, sum = 0.f, norm = 0.f, freq = 1.0f / 4096.0f;

@@ -53,7 +53,7 @@ def _check_workspace(name, t, need, like):
 def synth_dem(rows, cols, *, row0=0, total_rows=None, seed=0, kind=0, relief=1000.0, holes_permille=0,
               nodata=-9999.0, device="cuda", out=None):
     """Seeded synthetic float32 DEM generated on the device (kind 0 fractal, 1 terraces, 2 tilted plane,
-    3 walled serpentine: one channel of about rows * cols / 2 cells).
+    3 walled serpentine: one channel of about rows * cols / 2 cells running east-west; 4 the same running north-south).
 
     Rows row0..row0+rows-1 of a raster with `total_rows` rows; rows outside [0,total_rows) are nodata
     (that is what a strip's halo row is at the raster top / bottom).  `out`: write into this tensor.

@@ -46,7 +46,7 @@ def test_native_arm_line():
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "hbm"
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert d["parity"]["accumulation_recurrence_violations"] == 0 and d["parity"]["direction_windows_vs_oracle"]
-    for name in ("terraced_16k", "tilted_plane", "serpentine"):
+    for name in ("terraced_16k", "tilted_plane", "serpentine", "serpentine_ns"):
         o = d["other_workloads"][name]
         assert o["value"] > 0 and o["parity"]["accumulation_recurrence_violations"] == 0, name
         assert o["parity"]["direction_windows_vs_oracle"], name

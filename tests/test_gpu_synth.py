@@ -10,7 +10,7 @@ from oracle import synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("kind,holes,relief", [(0, 5, 1000.0), (0, 0, 37.5), (1, 50, 200.0), (2, 0, 1000.0), (3, 0, 1000.0)])
+@pytest.mark.parametrize("kind,holes,relief", [(0, 5, 1000.0), (0, 0, 37.5), (1, 50, 200.0), (2, 0, 1000.0), (3, 0, 1000.0), (4, 0, 1000.0)])
 @pytest.mark.parametrize("rows,cols,row0,total", [(300, 517, 0, 300), (130, 1024, 65000, 65536), (66, 200, -1, 64)])
 def test_device_generator_equals_host_restatement(kind, holes, relief, rows, cols, row0, total):
     from overflow_b200 import device as dev
@@ -38,17 +38,20 @@ def test_serpentine_device_path_vs_oracle(shape):
     assert dev.check_accumulation(fdr, fac) == 0
 
 
-def test_serpentine_across_strips():
-    """The channel crosses every strip boundary rows/2 times: 1, 3 and 8 strips equal the single raster."""
+@pytest.mark.parametrize("kind", [3, 4])
+def test_serpentine_across_strips(kind):
+    """One channel through every strip (kind 3: east-west runs, it crosses each strip boundary once; kind 4: north-south
+    runs, it crosses every strip boundary cols / 2 times): 1, 3 and 8 strips equal the single raster."""
     from overflow_b200 import device as dev, strips
 
     rows, cols = 1024, 320
-    dem = dev.synth_dem(rows, cols, kind=3)
+    dem = dev.synth_dem(rows, cols, kind=kind)
     one_fdr, one_fac = dev.flow_routing(dem, synth.NODATA)
+    assert int(one_fac.max().item()) > rows * cols // 2
     for world in (1, 3, 8):
         pipes = [strips.StripPipeline(rows, cols, r, world, nodata=synth.NODATA, device="cuda:0") for r in range(world)]
         for p in pipes:
-            p.load_synthetic(kind=3)
+            p.load_synthetic(kind=kind)
         strips.step_in_process(pipes)
         assert torch.equal(torch.cat([p.fdr for p in pipes]), one_fdr)
         assert torch.equal(torch.cat([p.fac for p in pipes]), one_fac)

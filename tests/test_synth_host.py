@@ -7,7 +7,7 @@ import oracle
 from oracle import synth
 
 
-@pytest.mark.parametrize("kind,holes", [(0, 5), (0, 0), (1, 50), (2, 0), (3, 0)])
+@pytest.mark.parametrize("kind,holes", [(0, 5), (0, 0), (1, 50), (2, 0), (3, 0), (4, 0)])
 @pytest.mark.parametrize("window", [(0, 0, 97, 130), (65400, 3000, 136, 70), (-1, 0, 40, 64)])
 def test_c_and_numpy_generators_agree(kind, holes, window):
     row0, col0, rows, cols = window
