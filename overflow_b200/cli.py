@@ -49,10 +49,17 @@ def flow_direction_cli(input_file: str, output_file: str, chunk_size: int):
 @click.option("--input_file", help="path to the flow direction raster")
 @click.option("--output_file", help="path to the output file")
 @click.option("--chunk_size", help="chunk size", default=DEFAULT_CHUNK_SIZE)
-def flow_accumulation_cli(input_file: str, output_file: str, chunk_size: int):
+@click.option("--tile_size", default=0, help="rasters beyond device memory: accumulate in square tiles of this many "
+              "cells a side (two passes over the file, the tiles' perimeter graph solved on the host); 0 = whole raster")
+def flow_accumulation_cli(input_file: str, output_file: str, chunk_size: int, tile_size: int = 0):
     """Generate a flow accumulation raster from a D8 flow direction raster."""
     try:
-        flow_accumulation(input_file, output_file, chunk_size)
+        if tile_size and int(tile_size) > 0:
+            from .tiles import flow_accumulation_file_tiled
+
+            flow_accumulation_file_tiled(input_file, output_file, int(tile_size), int(tile_size))
+        else:
+            flow_accumulation(input_file, output_file, chunk_size)
     except Exception as exc:
         print(f"flow_accumulation failed with the following exception: {str(exc)}")
         raise click.Abort()

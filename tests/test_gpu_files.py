@@ -160,3 +160,20 @@ def test_streamed_driver_refuses_what_it_cannot_do(tmp_path):
         stream_routing(src, str(tmp_path / "o.tif"), None)
     with pytest.raises(ValueError):
         stream_routing(src, None, None)
+
+
+def test_flow_accumulation_cli_tiled(tmp_path):
+    """--tile_size: the raster goes through the device in rectangular tiles; same file."""
+    dem = synth.punch_holes(synth.fractal(300, 260, beta=2.0, seed=25), frac=0.02, seed=26)
+    fdr = np.ascontiguousarray(oracle.flow_direction_for_tile(synth.pad_nodata(dem), synth.NODATA)[1:-1, 1:-1])
+    src, out = str(tmp_path / "fdr.tif"), str(tmp_path / "fac.tif")
+    ds = create_raster(src, fdr.shape[1], fdr.shape[0], "Byte")
+    ds.GetRasterBand(1).WriteArray(fdr)
+    ds.GetRasterBand(1).SetNoDataValue(FLOW_DIRECTION_NODATA)
+    ds.FlushCache()
+    result = click.testing.CliRunner().invoke(
+        flow_accumulation_cli, ["--input_file", src, "--output_file", out, "--tile_size", "128"])
+    assert result.exit_code == 0, result.output
+    band = open_raster(out).GetRasterBand(1)
+    assert np.array_equal(band.ReadAsArray(), oracle.flow_accumulation(fdr))
+    assert band.GetNoDataValue() == FLOW_ACCUMULATION_NODATA
