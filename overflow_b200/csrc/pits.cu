@@ -17,7 +17,6 @@
 // NODATA test compares in float64.  Bit-exact against the reference (tests/golden/breach_pits.npz).
 #include <math_constants.h>
 
-#include <atomic>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -109,24 +108,26 @@ pits_detect4_kernel(const float* __restrict__ chunk, int rows, int cols, int64_t
       v[k][4] = m.w;
       v[k][5] = c + 4 < cols ? q[4] : 0.f;
     }
+    // the four cells share their neighbours: per column the minimum of the rows above and below (m), of all three
+    // rows (m3), and whether any of the three is NODATA (nd3) -- 20 minima and 18 compares for four cells, not 32 + 36
+    float m[6], m3[6];
+    bool nd3[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      m[k] = fminf(v[0][k], v[2][k]);
+      m3[k] = fminf(m[k], v[1][k]);
+      nd3[k] = v[0][k] == nd_f || v[1][k] == nd_f || v[2][k] == nd_f;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int cc = c + j;
       if (cc < 2 || cc >= cols - 2) continue;
       const float z = v[1][j + 1];
-      // the branch-free form of :40-50, as in pits_detect_kernel
-      float lowest = CUDART_NAN_F;
-      bool nodata_seen = false;
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          if (k == 1 && d == 1) continue;
-          const float zn = v[k][j + d];
-          lowest = fminf(lowest, zn);
-          nodata_seen = nodata_seen || zn == nd_f;
-        }
-      if (!(nd_exact && (nodata_seen || z == nd_f)) && !(lowest <= z)) pits |= 1u << j;
+      // the branch-free form of :40-50, as in pits_detect_kernel: fminf skips NaN neighbours exactly as "zn <= z" is
+      // false for them, and "not (lowest <= z)" keeps the reference's answer when z or every neighbour is NaN
+      const float lowest = fminf(fminf(m3[j], m3[j + 2]), m[j + 1]);
+      const bool nodata_seen = nd3[j] || nd3[j + 1] || nd3[j + 2];  // a neighbour or the cell itself
+      if (!(nd_exact && nodata_seen) && !(lowest <= z)) pits |= 1u << j;
     }
   }
   if (in_raster) {
@@ -167,67 +168,108 @@ pits_detect4_kernel(const float* __restrict__ chunk, int rows, int cols, int64_t
 // (b) the ready pits -- more than three cells apart, hence on disjoint cells -- are breached exactly as the
 // reference's sequential loop would breach them, the others go to the next round's list.  The earliest waiting pit is
 // always ready, so the rounds end.  Everything other CTAs wrote in earlier rounds is read past L1 (ld.global.cg).
-__global__ void __launch_bounds__(PT)
-pits_rounds_kernel(unsigned* list_a, unsigned* list_b, uint8_t* waiting, uint8_t* ready, float* chunk, int rows, int cols,
-                   int64_t ld, double nodata, int8_t* unsolved, unsigned* cnt) {
+struct PitsArgs {
+  unsigned *list_a, *list_b;
+  uint8_t *waiting, *ready;
+  float* chunk;
+  int rows, cols;
+  int64_t ld;
+  double nodata;
+  int8_t* unsolved;
+  unsigned* cnt;
+};
+
+// (a) of a round, for the pits cur[t], t = tid, tid + nthr, .. < n_cur
+__device__ __forceinline__ void pits_ready_phase(const PitsArgs& a, const unsigned* cur, unsigned n_cur, unsigned tid,
+                                                 unsigned nthr) {
+  const int cols = a.cols;
+  for (unsigned t = tid; t < n_cur; t += nthr) {
+    const unsigned i = __ldcg(&cur[t]);
+    const int r = (int)(i / (unsigned)cols), c = (int)(i - (unsigned)r * (unsigned)cols);
+    // all 27 flags are loaded before any is looked at: independent loads, not a chain of them with early exits
+    unsigned any = 0;
+#pragma unroll
+    for (int dr = -3; dr <= 0; ++dr) {
+      const int rr = r + dr;
+#pragma unroll
+      for (int dc = -3; dc <= 3; ++dc) {
+        if (dr == 0 && dc >= 0) continue;  // the pit's own row: only cells before it
+        const int cc = c + dc;
+        if (rr >= 0 && cc >= 0 && cc < cols) any |= __ldcg(&a.waiting[(size_t)rr * cols + cc]);
+      }
+    }
+    a.ready[t] = any == 0 ? 1 : 0;
+  }
+}
+
+// (b) of a round: the ready pits are breached, the others appended to nxt (count in *n_next)
+__device__ __forceinline__ void pits_breach_phase(const PitsArgs& a, const unsigned* cur, unsigned* nxt, unsigned n_cur,
+                                                  unsigned* n_next, unsigned tid, unsigned nthr) {
+  const int cols = a.cols;
+  for (unsigned t = tid; t < n_cur; t += nthr) {
+    const unsigned i = __ldcg(&cur[t]);
+    if (!a.ready[t]) {  // written by this thread in phase (a)
+      nxt[atomicAdd(n_next, 1u)] = i;
+      continue;
+    }
+    const int r = (int)(i / (unsigned)cols), c = (int)(i - (unsigned)r * (unsigned)cols);
+    float* at = a.chunk + (int64_t)r * a.ld + c;
+    const float z = __ldcg(at);
+    // the sixteen cells two steps away are read first (the pit writes only within one step of itself), then
+    // breached in order: two k share a breach cell and the later one wins
+    float zn[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) zn[k] = __ldcg(&at[(int64_t)p_dy2[k] * a.ld + p_dx2[k]]);
+    bool solved = false;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if (zn[k] <= z || (double)zn[k] == a.nodata) {
+        solved = true;
+        const int b = p_breach[k];
+        at[(int64_t)p_dy[b] * a.ld + p_dx[b]] = __double2float_rn((double)__fadd_rn(z, zn[k]) / 2.0);
+      }
+    }
+    if (solved)
+      a.unsolved[i] = 0;
+    else
+      atomicAdd(&a.cnt[PC_UNSOLVED], 1u);
+    a.waiting[i] = 0;
+  }
+}
+
+// Round 1 holds most of the pits (on terrain four in five are ready at once): two ordinary launches over the
+// whole list, the grid sized for it.  (The same thread handles pit t in both: ready[t] needs no fence.)
+__global__ void __launch_bounds__(PT) pits_first_ready_kernel(const PitsArgs a) {
+  pits_ready_phase(a, a.list_a, a.cnt[PC_PITS], blockIdx.x * PT + threadIdx.x, gridDim.x * PT);
+}
+__global__ void __launch_bounds__(PT) pits_first_breach_kernel(const PitsArgs a) {
+  pits_breach_phase(a, a.list_a, a.list_b, a.cnt[PC_PITS], &a.cnt[PC_NEXT1], blockIdx.x * PT + threadIdx.x, gridDim.x * PT);
+}
+
+// The later rounds -- few pits each, many of them -- in ONE persistent kernel on a small grid (cooperative launch,
+// a grid barrier between the two phases and between rounds; everything other CTAs wrote is read past L1).
+__global__ void __launch_bounds__(PT) pits_rounds_kernel(const PitsArgs a) {
   unsigned generation = 0;
-  unsigned n_cur = *reinterpret_cast<volatile unsigned*>(&cnt[PC_PITS]);
   const unsigned tid = blockIdx.x * PT + threadIdx.x, nthr = gridDim.x * PT;
-  unsigned rounds = 0;
-  unsigned* cur = list_a;
-  unsigned* nxt = list_b;
+  unsigned rounds = 1;  // round 1 ran as two ordinary launches: its survivors are list_b, counted in PC_NEXT1
+  unsigned n_cur = *reinterpret_cast<volatile unsigned*>(&a.cnt[PC_NEXT1]);
+  unsigned* cur = a.list_b;
+  unsigned* nxt = a.list_a;
+  if (*reinterpret_cast<volatile unsigned*>(&a.cnt[PC_PITS]) == 0) rounds = 0;
   while (n_cur) {
-    unsigned* n_next = &cnt[PC_NEXT0 + ((rounds + 1) & 1)];
-    for (unsigned t = tid; t < n_cur; t += nthr) {
-      const unsigned i = __ldcg(&cur[t]);
-      const int r = (int)(i / (unsigned)cols), c = (int)(i - (unsigned)r * (unsigned)cols);
-      bool ok = true;
-      for (int dr = -3; dr <= 0 && ok; ++dr) {
-        const int rr = r + dr;
-        if (rr < 0) continue;
-        const int c_hi = dr < 0 ? min(cols - 1, c + 3) : c - 1;  // the pit's own row: only cells before it
-        for (int cc = max(0, c - 3); cc <= c_hi; ++cc)
-          if (__ldcg(&waiting[(size_t)rr * cols + cc])) {
-            ok = false;
-            break;
-          }
-      }
-      ready[t] = ok ? 1 : 0;
-    }
-    grid_barrier(&cnt[PC_BARRIER], generation);
-    for (unsigned t = tid; t < n_cur; t += nthr) {
-      const unsigned i = __ldcg(&cur[t]);
-      if (!ready[t]) {  // written by this thread before the barrier
-        nxt[atomicAdd(n_next, 1u)] = i;
-        continue;
-      }
-      const int r = (int)(i / (unsigned)cols), c = (int)(i - (unsigned)r * (unsigned)cols);
-      float* at = chunk + (int64_t)r * ld + c;
-      const float z = __ldcg(at);
-      bool solved = false;
-      for (int k = 0; k < 16; ++k) {  // in order: two k share a breach cell and the later one wins
-        const float zn = __ldcg(&at[(int64_t)p_dy2[k] * ld + p_dx2[k]]);
-        if (zn <= z || (double)zn == nodata) {
-          solved = true;
-          const int b = p_breach[k];
-          at[(int64_t)p_dy[b] * ld + p_dx[b]] = __double2float_rn((double)__fadd_rn(z, zn) / 2.0);
-        }
-      }
-      if (solved)
-        unsolved[i] = 0;
-      else
-        atomicAdd(&cnt[PC_UNSOLVED], 1u);
-      waiting[i] = 0;
-    }
-    grid_barrier(&cnt[PC_BARRIER], generation);
+    unsigned* n_next = &a.cnt[PC_NEXT0 + ((rounds + 1) & 1)];
+    pits_ready_phase(a, cur, n_cur, tid, nthr);
+    grid_barrier(&a.cnt[PC_BARRIER], generation);
+    pits_breach_phase(a, cur, nxt, n_cur, n_next, tid, nthr);
+    grid_barrier(&a.cnt[PC_BARRIER], generation);
     n_cur = *reinterpret_cast<volatile unsigned*>(n_next);
     ++rounds;
-    if (tid == 0) cnt[PC_NEXT0 + ((rounds + 1) & 1)] = 0;  // next round's counter: not touched before the next barrier
+    if (tid == 0) a.cnt[PC_NEXT0 + ((rounds + 1) & 1)] = 0;  // next round's counter: not touched before the next barrier
     unsigned* t2 = cur;
     cur = nxt;
     nxt = t2;
   }
-  if (tid == 0) cnt[PC_ROUNDS] = rounds;
+  if (tid == 0) a.cnt[PC_ROUNDS] = rounds;
 }
 
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
@@ -270,16 +312,27 @@ int launch_breach_pits(float* chunk, int64_t rows, int64_t cols, int64_t ld, dou
   }
   OFL_CHECK_LAUNCH();
   {
-    static std::atomic<int> gen{-1}, blocks{0};
-    if (gen.load() != device_generation() || blocks.load() == 0) {
-      int per_sm = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pits_rounds_kernel, PT, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-      blocks.store((per_sm > 4 ? 4 : per_sm) * sm_count());
-      gen.store(device_generation());
-    }
-    int irows = (int)rows, icols = (int)cols;
-    void* args[] = {&list_a, &list_b, &waiting, &ready, &chunk, &irows, &icols, &ld, &nodata, &unsolved, &cnt};
-    OFL_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(pits_rounds_kernel), dim3((unsigned)blocks.load()),
+    PitsArgs a;
+    a.list_a = list_a;
+    a.list_b = list_b;
+    a.waiting = waiting;
+    a.ready = ready;
+    a.chunk = chunk;
+    a.rows = (int)rows;
+    a.cols = (int)cols;
+    a.ld = ld;
+    a.nodata = nodata;
+    a.unsolved = unsolved;
+    a.cnt = cnt;
+    // round 1 over the whole list (its length is only known on the device: the grid covers the worst case a
+    // strided loop needs, one pit per thread and 16 turns)
+    const unsigned g1 = (unsigned)(sm_count() * 8);
+    pits_first_ready_kernel<<<g1, PT, 0, st>>>(a);
+    OFL_CHECK_LAUNCH();
+    pits_first_breach_kernel<<<g1, PT, 0, st>>>(a);
+    OFL_CHECK_LAUNCH();
+    void* args[] = {&a};
+    OFL_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(pits_rounds_kernel), dim3((unsigned)sm_count()),
                                          dim3(PT), args, 0, st));
     OFL_CHECK_LAUNCH();
   }
