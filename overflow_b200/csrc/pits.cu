@@ -206,10 +206,18 @@ __device__ __forceinline__ void pits_ready_phase(const PitsArgs& a, const unsign
 __device__ __forceinline__ void pits_breach_phase(const PitsArgs& a, const unsigned* cur, unsigned* nxt, unsigned n_cur,
                                                   unsigned* n_next, unsigned tid, unsigned nthr) {
   const int cols = a.cols;
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned n_unsolved = 0;
   for (unsigned t = tid; t < n_cur; t += nthr) {
     const unsigned i = __ldcg(&cur[t]);
     if (!a.ready[t]) {  // written by this thread in phase (a)
-      nxt[atomicAdd(n_next, 1u)] = i;
+      // one counter update for the lanes of the warp that are here together
+      const unsigned m = __activemask();
+      const int leader = __ffs(m) - 1;
+      unsigned base = 0;
+      if ((int)lane == leader) base = atomicAdd(n_next, (unsigned)__popc(m));
+      base = __shfl_sync(m, base, leader);
+      nxt[base + __popc(m & ((1u << lane) - 1u))] = i;
       continue;
     }
     const int r = (int)(i / (unsigned)cols), c = (int)(i - (unsigned)r * (unsigned)cols);
@@ -232,9 +240,12 @@ __device__ __forceinline__ void pits_breach_phase(const PitsArgs& a, const unsig
     if (solved)
       a.unsolved[i] = 0;
     else
-      atomicAdd(&a.cnt[PC_UNSOLVED], 1u);
+      ++n_unsolved;
     a.waiting[i] = 0;
   }
+  // every thread of the grid gets here: one counter update per warp
+  n_unsolved = __reduce_add_sync(0xffffffffu, n_unsolved);
+  if (lane == 0 && n_unsolved) atomicAdd(&a.cnt[PC_UNSOLVED], n_unsolved);
 }
 
 // Round 1 holds most of the pits (on terrain four in five are ready at once): two ordinary launches over the
