@@ -135,7 +135,7 @@ def stream_routing(input_path, flow_direction_path=None, flow_accumulation_path=
     _native.init(device.index if device.index is not None else torch.cuda.current_device())
     if band_rows is None:
         band_rows = max(64, min(4096, (256 << 20) // max(1, cols * 4)))  # about 256 MiB of DEM per band
-    band_rows = max(1, int(band_rows))
+    band_rows = max(1, min(int(band_rows), max(rows, 1)))  # the pinned rings are sized by it
     bands = [(r, min(rows, r + band_rows)) for r in range(0, rows, band_rows)]
 
     def make_out(path, name, nd):
@@ -303,7 +303,7 @@ def stream_accumulation(input_path, output_path, band_rows=None, device=None, ri
     _native.init(device.index if device.index is not None else torch.cuda.current_device())
     if band_rows is None:
         band_rows = max(64, min(16384, (256 << 20) // max(1, cols)))
-    band_rows = max(1, int(band_rows))
+    band_rows = max(1, min(int(band_rows), max(rows, 1)))  # the pinned rings are sized by it
     bands = [(r, min(rows, r + band_rows)) for r in range(0, rows, band_rows)]
     dst = _raster.create_raster(output_path, cols, rows, "Int64", projection=src.GetProjection(),
                                 geotransform=src.GetGeoTransform())

@@ -114,7 +114,7 @@ def test_streamed_routing_equals_plain_drivers(tmp_path, band_rows):
     ds.GetRasterBand(1).SetNoDataValue(synth.NODATA)
     ds.FlushCache()
     rep = stream_routing(src, str(tmp_path / "fdr_s.tif"), str(tmp_path / "fac_s.tif"), band_rows=band_rows)
-    assert rep["rows"] == 333 and rep["bands"] == -(-333 // band_rows) and rep["wall_s"] > 0
+    assert rep["rows"] == 333 and rep["bands"] == -(-333 // min(band_rows, 333)) and rep["wall_s"] > 0
     flow_routing(src, str(tmp_path / "fdr_p.tif"), str(tmp_path / "fac_p.tif"), streamed=False)
     want_fdr = oracle.flow_direction_for_tile(synth.pad_nodata(dem), synth.NODATA)[1:-1, 1:-1]
     want_fac = oracle.flow_accumulation(np.ascontiguousarray(want_fdr))
