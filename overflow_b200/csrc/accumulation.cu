@@ -16,10 +16,10 @@
 //           inflow from outside the tile to where their path leaves it (Alg. 2), and emit the
 //           reduced graph: the successor perimeter cell in the next tile, the locally accumulated
 //           counts that cross the tile edge, and -- on whole-raster calls -- the solve's initial state.
-//   solve   (pj_round_kernel)         the reduced graph is a forest over ~2% of the cells;
+//   solve   (pj_solve_kernel)        the reduced graph is a forest over ~2% of the cells;
 //           subtree sums over it by pointer doubling: O(log depth) rounds of
-//           "add my sum to my 2^j-th ancestor, then jump", integer atomics, exact; replayed from a
-//           CUDA graph.
+//           "add my sum to my 2^j-th ancestor, then jump", integer atomics, exact; all rounds in one
+//           persistent kernel (cooperative launch, grid barrier between rounds).
 //   final   (acc_final_kernel)        per tile: tile-local counts (stored by pass A, 2 B/cell) plus
 //           every perimeter cell's inflow from outside the tile added along its in-tile path;
 //           writes the final int64 counts.
