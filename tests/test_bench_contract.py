@@ -59,3 +59,25 @@ def test_native_arm_line():
     assert {"value", "unit", "cores", "kind", "sample"} <= set(ff["cpu_baseline"])
     bp = d["next_rows"]["breach_single_cell_pits"]
     assert bp["parity"]["bits_equal_oracle"] and bp["value"] > 0 and bp["pits"] >= bp["unsolved"] >= 0
+
+
+def test_checksum_is_position_weighted_and_additive_over_strips():
+    """bench.py's strip checksum: a swap of two cells changes it; strips add up to the whole raster (mod 2^64)."""
+    import sys
+
+    import numpy as np
+    import torch
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    rng = np.random.default_rng(0)
+    a = torch.from_numpy(rng.integers(-9998, 1 << 40, (300, 70), dtype=np.int64))
+    whole = bench.checksum(torch, a, 0, 70, chunk_rows=64)
+    parts = [bench.checksum(torch, a[r0:r1], r0, 70, chunk_rows=50) for r0, r1 in ((0, 128), (128, 192), (192, 300))]
+    assert (sum(parts) - whole) % (1 << 64) == 0
+    b = a.clone()
+    b[5, 6], b[200, 3] = a[200, 3], a[5, 6]
+    assert bench.checksum(torch, b, 0, 70) != whole
+    c = torch.from_numpy(rng.integers(0, 10, (300, 70), dtype=np.uint8))
+    assert bench.checksum(torch, c, 1000, 70) != bench.checksum(torch, c, 1001, 70)
