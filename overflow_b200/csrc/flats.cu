@@ -12,14 +12,18 @@
 //     component by atomicMin, and label = 1 + rank of that index among all components' smallest low edges
 //     (a prefix sum over the raster).  Components without a low edge keep label 0.
 //   * away_from_higher / towards_lower are breadth-first sweeps with a level marker: a cell's value is its
-//     BFS level from the seed edges through same-label cells without a direction.  Here: level-synchronous
-//     frontier queues (ballot-compacted appends, one claim per cell by compare-and-swap), the level loop
-//     batched on the host with a count read back per batch; flat_height[label] = max level by atomicMax
-//     (the reference's "last write" is the largest level because levels only grow).
+//     BFS level from the seed edges through same-label cells without a direction.  Here: relaxation of 32 x 32
+//     tiles in shared memory to the same (unique) fixpoint, the passes over the queued tiles inside one
+//     persistent kernel; flat_height[label] = max level by atomicMax (the reference's "last write" is the
+//     largest level because levels only grow).
 //   * d8_masked_flow_dirs is a 3x3 stencil over flat_mask and labels, slopes in float64 as in the reference.
 // Everything is integer work except the two float compares (==, <) on elevations and the float64 slope
 // division, so results are compared bit for bit with the reference's.
 #include <limits.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <atomic>
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -34,7 +38,16 @@ constexpr int FL_THREADS = 256;
 constexpr int FL_SCAN_THREADS = 1024;
 
 // counters (uint32) kept in device memory
-enum { CNT_LOW = 0, CNT_HIGH, CNT_LABELS, CNT_SEEDS, CNT_FRONT0, CNT_FRONT1, CNT_FRONT2, CNT_SLOTS = 16 };
+enum {
+  CNT_LOW = 0, CNT_HIGH, CNT_LABELS, CNT_SEEDS,
+  CNT_TCOUNT0, CNT_TCOUNT1, CNT_TCOUNT2,  // tiles queued for pass k in slot k % 3
+  CNT_TTAKE0, CNT_TTAKE1, CNT_TTAKE2,     // tiles of pass k handed out so far
+  CNT_BAR, CNT_RELEASE,                   // grid barrier of the sweep kernel
+  CNT_PASSES, CNT_MAXLEVEL,
+  CNT_VISITS, CNT_ROUNDS,                 // statistics of the sweep (OFL_FLATS_DEBUG)
+  CNT_MAXROUNDS, CNT_PASSTIME0,           // most rounds in one visit; start of pass k in ns (low word), 40 slots
+  CNT_SLOTS = 64
+};
 
 __constant__ int c_dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};  // E NE N NW W SW S SE: constants.py:29-40
 __constant__ int c_dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
@@ -273,7 +286,7 @@ flat_seed_rank_kernel(int64_t n, const int* parent, const uint8_t* __restrict__ 
 // Every cell takes the label of its component: root -> the component's smallest low edge -> that seed's label
 // (0 when the component has no low edge).  The walk to the root is read-only (low edges already point at it).
 // open[i] is the sweeps' one-word view of a cell: 0 = never a candidate (it has a direction), otherwise
-// (label + 1) << 2 | g with g = 0 untouched, 1 claimed by the away sweep, 2 claimed by the towards sweep.
+// (label + 1) << 2 (the two low bits are the tile kernel's own flags in shared memory).
 __device__ __forceinline__ unsigned flat_state(int lab) { return (unsigned)(lab + 1) << 2; }
 
 __global__ void __launch_bounds__(FL_THREADS)
@@ -328,169 +341,383 @@ flat_prepare_kernel(int64_t n, int mode, int* flat_mask, const int* __restrict__
   open[i] = (fdr[i] == FL_UNDEF && fm <= 0) ? flat_state(labels[i]) : 0u;
 }
 
-// One try to claim candidate word `s` of cell q for this sweep.
-__device__ __forceinline__ bool flat_claim(unsigned* open, int q, unsigned s, unsigned want, int mode) {
-  if ((s & ~3u) != want) return false;
-  if (mode == SWEEP_AWAY) return (s & 3u) == 0u && atomicCAS(open + q, s, s | 1u) == s;
-  return (s & 3u) != 2u && atomicCAS(open + q, s, (s & ~3u) | 2u) == s;
-}
-
-// The value a cell gets when a sweep reaches it at `level` (:153-154 / :209-214); only the claiming thread calls this.
-__device__ __forceinline__ void flat_assign(int p, int level, int mode, int lab, int* flat_mask, const int* fh_read,
-                                            int* fh_acc) {
-  if (mode == SWEEP_AWAY) {
-    flat_mask[p] = level;
-    // every cell of a level carries the same value: one atomic per flat and level gets through
-    if (lab > 0 && __ldcg(fh_acc + lab - 1) < level) atomicMax(fh_acc + lab - 1, level);
-  } else {
-    const int fm = flat_mask[p];
-    int away = 0;  // flat_height - (increments away from higher terrain), 0 where the away sweep never came
-    if (lab > 0) {
-      if (mode == SWEEP_TOWARDS_NEGATED && fm < 0) away = fm + fh_read[lab - 1];
-      if (mode == SWEEP_TOWARDS && fm > 0) away = fh_read[lab - 1] - fm;
-    }
-    flat_mask[p] = away + 2 * level;
-  }
-}
-
-// Frontier appends go through a per-CTA buffer: a warp reserves its slots with one shared-memory atomic, and the
-// CTA moves the buffer to the global queue with one global atomic when it fills up.  (One global atomic per warp
-// was the bottleneck of the sweeps: tens of millions of adds on a single counter.)
-#ifndef OFL_FL_ILP
-#define OFL_FL_ILP 2
+// The sweeps as tile relaxation.  A cell's value is its breadth-first level from the seed cells through candidate
+// cells of the same label: the least fixpoint of  D(q) = 1 + min{ D(p) : p a neighbour of q with q's label },
+// D(seed) = 1, which any relaxation order reaches.  The level-synchronous form of round 1 paid one kernel launch
+// (13-27 us, a chain of dependent loads) per level, hundreds of levels per sweep.  Here the unit of scheduling is a
+// tile of FT x FT cells: a CTA loads the tile's D and candidate words with a one-cell ring into shared memory,
+// relaxes it to its own fixpoint with a frontier queue in shared memory (a level costs two CTA barriers, not a
+// launch), writes the cells that improved back, and queues the neighbouring tiles whose ring it changed for the next
+// pass.  One persistent kernel runs the passes with a grid barrier in between, so a sweep needs about
+// (flat diameter / FT) passes and no host round trip.  A tile writes its own cells only; a ring read that is stale
+// is still an upper bound, and whoever lowers it afterwards queues the reader again.
+#ifndef OFL_FL_TILE
+#define OFL_FL_TILE 32
 #endif
-constexpr int FL_ILP = OFL_FL_ILP;  // pushes per thread and loop round (tuning: -DOFL_FL_ILP=4)
-constexpr int FL_QBUF = 1024 * FL_ILP;
-constexpr int FL_ROUNDS = 2;  // loop rounds between two looks at the fill level
-constexpr int FL_BATCH = FL_ROUNDS * FL_ILP * FL_THREADS;  // most pushes between two looks
-static_assert(FL_QBUF >= 2 * FL_BATCH, "buffer must hold two batches of rounds");
+constexpr int FT = OFL_FL_TILE;       // tile edge
+constexpr int FTW = FT + 2;           // with the ring
+constexpr int FT_CELLS = FTW * FTW;
+#ifndef OFL_FL_QCAP
+#define OFL_FL_QCAP (OFL_FL_TILE * OFL_FL_TILE + 256)
+#endif
+constexpr int FT_QCAP = OFL_FL_QCAP;  // entries of one in-tile frontier queue; beyond that the tile falls back to dense sweeps
+#ifndef OFL_FL_SWEEP_THREADS
+#define OFL_FL_SWEEP_THREADS 128
+#endif
+constexpr int FS_THREADS = OFL_FL_SWEEP_THREADS;  // threads of the CTA that relaxes a tile
+static_assert(FS_THREADS >= 64 && FS_THREADS % 32 == 0, "whole warps, at least two");
+constexpr int FL_INF = 0x7f7f7f7f;    // "not reached": what cudaMemsetAsync(0x7f) leaves
 
-struct BlockQueue {
-  int buf[FL_QBUF];
-  unsigned n, base;
+struct SweepArgs {
+  int rows, cols, tiles_x, tiles_y, n_tiles;
+  int* D;                // level per cell, FL_INF where the sweep has not come
+  const unsigned* open;  // candidate words: 0 = cannot take a value, else (label + 1) << 2
+  const int* labels;
+  int* lists;            // three tile lists of n_tiles entries: pass k reads list k % 3 and fills list (k + 1) % 3
+  int* stamp;            // per tile: 1 + the last pass it has been queued for
+  int* seen;             // per tile: visited before
+  unsigned* cnt;
 };
 
-__device__ __forceinline__ void bq_push(BlockQueue& bq, bool won, int p) {
-  const unsigned m = __ballot_sync(0xffffffffu, won);
-  if (m == 0) return;
-  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-  unsigned off = 0;
-  if (lane == leader) off = atomicAdd(&bq.n, (unsigned)__popc(m));
-  off = __shfl_sync(0xffffffffu, off, leader);
-  if (won) bq.buf[off + __popc(m & ((1u << lane) - 1u))] = p;
+__device__ __forceinline__ void tile_activate(const SweepArgs& a, int tile, int pass) {
+  if (atomicMax(a.stamp + tile, pass + 1) < pass + 1)
+    a.lists[(size_t)(pass % 3) * a.n_tiles + atomicAdd(&a.cnt[CNT_TCOUNT0 + pass % 3], 1u)] = tile;
 }
 
-// all threads of the CTA; pushes must not overlap a flush
-__device__ __forceinline__ void bq_flush(BlockQueue& bq, int* qout, unsigned* cnt_out) {
-  __syncthreads();
-  const unsigned n = bq.n;
-  if (n == 0) return;  // uniform: read between two barriers with no push in flight
-  if (threadIdx.x == 0) bq.base = atomicAdd(cnt_out, n);
-  __syncthreads();
-  const unsigned base = bq.base;
-  for (unsigned k = threadIdx.x; k < n; k += FL_THREADS) qout[base + k] = bq.buf[k];
-  __syncthreads();
-  if (threadIdx.x == 0) bq.n = 0;
-  __syncthreads();
-}
-
-// after every FL_ROUNDS rounds: flush when another batch of rounds might not fit
-__device__ __forceinline__ void bq_maybe_flush(BlockQueue& bq, unsigned round, int* qout, unsigned* cnt_out) {
-  if (round % FL_ROUNDS) return;
-  __syncthreads();
-  const bool full = bq.n > FL_QBUF - FL_BATCH;
-  __syncthreads();
-  if (full) bq_flush(bq, qout, cnt_out);
-}
-
-// level 1: the seed edges themselves (duplicates and already positive cells drop out)
+// level 1: the seed cells (:146-148 / :202-204).  A seed that is not a candidate (a low edge: it has a direction)
+// counts only while its mask is not positive (:150-151 / :207-208), like every cell the reference pops.
 __global__ void __launch_bounds__(FL_THREADS)
-flat_seed_level_kernel(const int* __restrict__ seeds, const int* __restrict__ labels, int mode, int* flat_mask,
-                       unsigned* open, const int* fh_read, int* fh_acc, int* qout, unsigned* cnt) {
-  __shared__ BlockQueue bq;
-  const unsigned n_seed = cnt[CNT_SEEDS];
-  if (blockIdx.x == 0 && threadIdx.x == 0) cnt[CNT_FRONT0 + 2] = 0;
-  if (threadIdx.x == 0) bq.n = 0;
+flat_tile_seed_kernel(const int* __restrict__ seeds, const int* __restrict__ flat_mask, SweepArgs a) {
+  const unsigned n_seed = a.cnt[CNT_SEEDS];
+  for (unsigned idx = blockIdx.x * FL_THREADS + threadIdx.x; idx < n_seed; idx += gridDim.x * FL_THREADS) {
+    const int p = seeds[idx];
+    if (a.open[p] == 0u && flat_mask[p] > 0) continue;
+    a.D[p] = 1;
+    // its own tile, and the tiles that see it in their ring
+    const int r = p / a.cols, c = p - r * a.cols;
+    const int ty = r / FT, tx = c / FT, lr = r - ty * FT, lc = c - tx * FT;
+    const int vr = lr == 0 ? -1 : (lr == FT - 1 ? 1 : 0), vc = lc == 0 ? -1 : (lc == FT - 1 ? 1 : 0);
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        if ((dy != 0 && dy != vr) || (dx != 0 && dx != vc)) continue;
+        const int nty = ty + dy, ntx = tx + dx;
+        if (nty < 0 || nty >= a.tiles_y || ntx < 0 || ntx >= a.tiles_x) continue;
+        const int tile = nty * a.tiles_x + ntx;
+        if (__ldcg(a.stamp + tile) == 0) tile_activate(a, tile, 0);
+      }
+  }
+}
+
+// Shared-memory image of a tile: FT x FT cells, the ring around them and one more guard ring that is never a
+// candidate, so that any neighbour of a tile or ring cell is a valid index and needs no bounds check.
+constexpr int FTS = FT + 4;  // row stride
+constexpr int FT_IMG = FTS * FTS;
+static_assert(FT_QCAP >= FT_CELLS, "the first round queues every valued cell of the tile and its ring");
+
+struct TileSmem {
+  int D[FT_IMG];
+  // (label + 1) << 2 | flags.  A cell of the tile: 1 = candidate (may take a value), 2 = improved on this visit.
+  // A cell of the ring: 2 = candidate (of its own tile; it never takes a value here).  Guard cells: 0.
+  unsigned S[FT_IMG];
+  int q[2][FT_QCAP];
+  unsigned qn[3];    // round j reads qn[j % 3], fills qn[(j + 1) % 3] and clears qn[(j + 2) % 3]
+  unsigned act;      // neighbouring tiles to queue, bit (dty + 1) * 3 + (dtx + 1)
+  int overflow, changed;
+  unsigned take, n_act;
+};
+
+// __syncthreads() is an aligned barrier: the warp has to arrive as one.  The loops below leave lanes at different
+// points (a lane with no cell skips the body), so the warp is gathered explicitly first.
+__device__ __forceinline__ void cta_sync() {
+  __syncwarp();
   __syncthreads();
-  const unsigned stride = gridDim.x * FL_THREADS;
-  unsigned round = 0;
-  for (unsigned base = blockIdx.x * FL_THREADS; base < n_seed; base += stride) {
-    const unsigned idx = base + threadIdx.x;
-    bool won = false;
-    int p = 0;
-    if (idx < n_seed) {
-      p = seeds[idx];
-      const int lab = labels[p];
-      const unsigned o = __ldcg(open + p);
-      if (o != 0u) {  // a candidate cell: claimed like any other
-        won = flat_claim(open, p, o, flat_state(lab), mode);
-        if (won) flat_assign(p, 1, mode, lab, flat_mask, fh_read, fh_acc);
-      } else {  // a cell with a direction (low edges) or one that already has its value: the mask itself dedupes
-        const int fm = __ldcg(flat_mask + p);
-        if (fm <= 0) {
-          const int nv = mode == SWEEP_AWAY ? 1 : ((fm < 0 && lab > 0) ? fm + fh_read[lab - 1] : 0) + 2;
-          won = atomicCAS(flat_mask + p, fm, nv) == fm;
-          if (won && mode == SWEEP_AWAY && lab > 0) atomicMax(fh_acc + lab - 1, 1);
+}
+
+// image index of cell (lr, lc) of the tile-with-ring, 0 <= lr, lc < FTW
+__device__ __forceinline__ int tile_img(int lr, int lc) { return (lr + 1) * FTS + lc + 1; }
+
+// e-th cell of the square frame with corners (lo, lo) and (hi, hi): top row, bottom row, left column, right
+// column, 4 * (hi - lo) cells in all
+__device__ __forceinline__ void frame_cell(int e, int lo, int hi, int* lr, int* lc) {
+  const int len = hi - lo, side = e / len, t = e - side * len;
+  *lr = side == 0 ? lo : side == 1 ? hi : side == 2 ? lo + 1 + t : lo + t;
+  *lc = side == 0 ? lo + t : side == 1 ? lo + 1 + t : side == 2 ? lo : hi;
+}
+
+// image offset of neighbour k (E NE N NW W SW S SE)
+__device__ __forceinline__ int tile_off(int k) {
+  const int dy = (k >= 1 && k <= 3) ? -1 : (k >= 5 ? 1 : 0);
+  const int dx = (k == 0 || k == 1 || k == 7) ? 1 : ((k >= 3 && k <= 5) ? -1 : 0);
+  return dy * FTS + dx;
+}
+
+// a cell with state s offers level d1 (its own + 1) to the cell at image index nidx; true when that cell improved
+__device__ __forceinline__ bool tile_relax(TileSmem& sm, int nidx, int d1, unsigned s) {
+  const unsigned ns = sm.S[nidx];
+  if (!(ns & 1u) || ((ns ^ s) & ~3u) != 0u || sm.D[nidx] <= d1) return false;
+  if (atomicMin(&sm.D[nidx], d1) <= d1) return false;
+  if (!(ns & 2u)) sm.S[nidx] = ns | 2u;  // every writer stores the same word
+  return true;
+}
+
+__device__ __forceinline__ void tile_push(TileSmem& sm, int which, int* q, int idx) {
+  const unsigned at = atomicAdd(&sm.qn[which], 1u);
+  if (at < FT_QCAP)
+    q[at] = idx;
+  else
+    sm.overflow = 1;
+}
+
+__device__ void tile_process(const SweepArgs& a, TileSmem& sm, int tile, int pass) {
+  const int ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
+  const int r0 = ty * FT - 1, c0 = tx * FT - 1;
+  if (threadIdx.x == 0) {
+    sm.qn[0] = sm.qn[1] = sm.qn[2] = 0;
+    sm.act = 0;
+#ifdef OFL_FL_FORCE_DENSE
+    sm.overflow = 1;  // test build: every tile takes the dense fallback
+#else
+    sm.overflow = 0;
+#endif
+  }
+  // the first visit finds seeds anywhere in the tile; later the tile's own cells are at their fixpoint and
+  // only the ring brings news
+  const bool first = __ldcg(a.seen + tile) == 0;
+  for (int base = 0; base < FT_CELLS; base += FS_THREADS) {
+    const int e = base + (int)threadIdx.x;
+    if (e >= FT_CELLS) continue;
+    const int lr = e / FTW, lc = e - lr * FTW;
+    const int r = r0 + lr, c = c0 + lc;
+    int d = FL_INF;
+    unsigned s = 0;
+    if (r >= 0 && r < a.rows && c >= 0 && c < a.cols) {
+      const int64_t g = (int64_t)r * a.cols + c;
+      d = __ldcg(a.D + g);
+      const unsigned o = a.open[g];
+      if (o)
+        s = (o & ~3u) | ((lr >= 1 && lr <= FT && lc >= 1 && lc <= FT) ? 1u : 2u);
+      else if (d < FL_INF)
+        s = flat_state(a.labels[g]);  // a seed with a direction: gives, never takes
+    }
+    sm.D[tile_img(lr, lc)] = d;
+    sm.S[tile_img(lr, lc)] = s;
+  }
+  cta_sync();
+  // round 0: the valued cells (on later visits: of the ring only) are the first frontier
+  {
+    const int n_src = first ? FT_CELLS : 4 * (FT + 1);
+    for (int base = 0; base < n_src; base += FS_THREADS) {
+      const int e = base + (int)threadIdx.x;
+      if (e >= n_src) continue;
+      int lr, lc;
+      if (first) {
+        lr = e / FTW;
+        lc = e - lr * FTW;
+      } else {
+        frame_cell(e, 0, FTW - 1, &lr, &lc);
+      }
+      const int idx = tile_img(lr, lc);
+      if (sm.D[idx] < FL_INF) tile_push(sm, 0, sm.q[0], idx);
+    }
+  }
+  // frontier rounds: a lane takes a queued cell and offers its level to the eight neighbours (the flags keep
+  // ring and guard cells from taking it); the improved ones are appended warp by warp
+  int rounds = 0;
+  for (int slot = 0;; ++rounds) {
+    cta_sync();
+    const unsigned n = min(sm.qn[slot], (unsigned)FT_QCAP);
+    if (n == 0 || sm.overflow) break;
+    const int next = slot == 2 ? 0 : slot + 1;
+    if (threadIdx.x == 0) sm.qn[next == 2 ? 0 : next + 1] = 0;
+    const int* qin = sm.q[rounds & 1];
+    int* qout = sm.q[(rounds & 1) ^ 1];
+    for (unsigned i0 = (threadIdx.x & ~31u); i0 < n; i0 += FS_THREADS) {  // warp-uniform bounds
+      const unsigned i = i0 + (threadIdx.x & 31u);
+      unsigned won = 0;
+      int idx = 0;
+      if (i < n) {
+        idx = qin[i];
+        const int d1 = sm.D[idx] + 1;
+        const unsigned s = sm.S[idx];
+        // four neighbours at a time: their words and levels are read before any of them is judged, so the
+        // loads overlap (one after the other, a round was a chain of some thirty dependent accesses)
+#pragma unroll
+        for (int h = 0; h < 8; h += 4) {
+          unsigned ns[4];
+          int nd[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ns[k] = sm.S[idx + tile_off(h + k)];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) nd[k] = sm.D[idx + tile_off(h + k)];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if ((ns[k] & 1u) && ((ns[k] ^ s) & ~3u) == 0u && nd[k] > d1 &&
+                atomicMin(&sm.D[idx + tile_off(h + k)], d1) > d1) {
+              if (!(ns[k] & 2u)) sm.S[idx + tile_off(h + k)] = ns[k] | 2u;
+              won |= 1u << (h + k);
+            }
         }
       }
+      if (!__any_sync(0xffffffffu, won != 0u)) continue;
+      const int lane = threadIdx.x & 31;
+      int inc = __popc(won);  // inclusive prefix over the warp
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      unsigned at = 0;
+      if (lane == 31) at = atomicAdd(&sm.qn[next], (unsigned)inc);
+      at = __shfl_sync(0xffffffffu, at, 31) + (unsigned)(inc - __popc(won));
+      for (; won; won &= won - 1u, ++at) {
+        if (at < FT_QCAP)
+          qout[at] = idx + tile_off(__ffs(won) - 1);
+        else
+          sm.overflow = 1;
+      }
     }
-    bq_push(bq, won, p);
-    bq_maybe_flush(bq, ++round, qout, &cnt[CNT_FRONT0 + 1]);
+    slot = next;
   }
-  bq_flush(bq, qout, &cnt[CNT_FRONT0 + 1]);
+  if (sm.overflow) {
+    // a queue ran over (cells improved several times per round): dense sweeps to the same fixpoint
+    for (;;) {
+      cta_sync();
+      if (threadIdx.x == 0) sm.changed = 0;
+      cta_sync();
+      bool any = false;
+      for (int base = 0; base < FT_CELLS; base += FS_THREADS) {
+        const int e = base + (int)threadIdx.x;
+        if (e >= FT_CELLS) continue;
+        const int lr = e / FTW, idx = tile_img(lr, e - lr * FTW);
+        const int d = sm.D[idx];
+        if (d >= FL_INF) continue;
+        const unsigned s = sm.S[idx];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) any |= tile_relax(sm, idx + tile_off(kk), d + 1, s);
+      }
+      if (any) sm.changed = 1;
+      cta_sync();
+      if (!sm.changed) break;
+    }
+  }
+  cta_sync();
+  // improved cells go back
+  for (int base = 0; base < FT * FT; base += FS_THREADS) {
+    const int e = base + (int)threadIdx.x;
+    if (e >= FT * FT) continue;
+    const int lr = e / FT + 1, lc = e - (lr - 1) * FT + 1;
+    const int idx = tile_img(lr, lc);
+    if (sm.S[idx] & 2u) a.D[(int64_t)(r0 + lr) * a.cols + (c0 + lc)] = sm.D[idx];
+  }
+  // an improved cell on the tile's rim wakes a neighbouring tile if a cell of that tile (its value as of this
+  // visit's load, an upper bound of what it holds now) could take a lower level from it
+  for (int base = 0; base < 4 * (FT - 1); base += FS_THREADS) {
+    const int e = base + (int)threadIdx.x;
+    if (e >= 4 * (FT - 1)) continue;
+    int lr, lc;
+    frame_cell(e, 1, FT, &lr, &lc);
+    const int idx = tile_img(lr, lc);
+    const unsigned s = sm.S[idx];
+    if (!(s & 2u)) continue;
+    const int d1 = sm.D[idx] + 1;
+    unsigned bits = 0;
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int nidx = idx + tile_off(kk);
+      const unsigned ns = sm.S[nidx];
+      if ((ns & 3u) == 2u && ((ns ^ s) & ~3u) == 0u && sm.D[nidx] > d1) {  // (ns & 3) == 2: a candidate on the ring
+        const int nr = lr + c_dy[kk], nc = lc + c_dx[kk];
+        bits |= 1u << (((nr < 1 ? -1 : nr > FT ? 1 : 0) + 1) * 3 + (nc < 1 ? -1 : nc > FT ? 1 : 0) + 1);
+      }
+    }
+    if (bits) atomicOr(&sm.act, bits);
+  }
+  cta_sync();
+  if (threadIdx.x == 32) {
+    if (first) a.seen[tile] = 1;
+    atomicAdd(&a.cnt[CNT_VISITS], 1u);
+    atomicAdd(&a.cnt[CNT_ROUNDS], (unsigned)rounds);
+    if (__ldcg(&a.cnt[CNT_MAXROUNDS]) < (unsigned)rounds) atomicMax(&a.cnt[CNT_MAXROUNDS], (unsigned)rounds);
+  }
+  if (threadIdx.x < 9 && ((sm.act >> threadIdx.x) & 1u)) {
+    const int nty = ty + (int)threadIdx.x / 3 - 1, ntx = tx + (int)threadIdx.x % 3 - 1;
+    if (nty >= 0 && nty < a.tiles_y && ntx >= 0 && ntx < a.tiles_x) tile_activate(a, nty * a.tiles_x + ntx, pass + 1);
+  }
 }
 
-// level L -> L+1: neighbours with the same label and no direction (:155-161 / :215-224).  Eight lanes share a
-// frontier cell, one neighbour each: a level is one load-compare-claim deep instead of eight (small frontiers are
-// latency bound), and a neighbour costs one scattered word (open[q]) instead of three (mask, code, label).
-__global__ void __launch_bounds__(FL_THREADS)
-flat_level_kernel(int level, const int* __restrict__ qin, int* qout, const int* __restrict__ labels, int rows, int cols,
-                  int mode, int* flat_mask, unsigned* open, const int* fh_read, int* fh_acc, unsigned* cnt) {
-  __shared__ BlockQueue bq;
-  const unsigned n_in = cnt[CNT_FRONT0 + level % 3];
-  unsigned* cnt_out = &cnt[CNT_FRONT0 + (level + 1) % 3];
-  if (blockIdx.x == 0 && threadIdx.x == 0) cnt[CNT_FRONT0 + (level + 2) % 3] = 0;
-  if (threadIdx.x == 0) bq.n = 0;
-  __syncthreads();
-  constexpr unsigned CELLS = FL_THREADS / 8;
-  const unsigned stride = gridDim.x * CELLS * FL_ILP;
-  const int k = threadIdx.x & 7;
-  const int dy = c_dy[k], dx = c_dx[k];
-  unsigned round = 0;
-  for (unsigned base = blockIdx.x * CELLS * FL_ILP; base < n_in; base += stride) {
-    // FL_ILP independent (cell, neighbour) pairs per thread: the three dependent loads of each overlap
-    int q[FL_ILP];
-    unsigned want[FL_ILP], seen[FL_ILP];
-    bool ok[FL_ILP];
-#pragma unroll
-    for (int u = 0; u < FL_ILP; ++u) {
-      const unsigned idx = base + u * CELLS + (threadIdx.x >> 3);
-      ok[u] = idx < n_in;
-      q[u] = ok[u] ? qin[idx] : 0;
-    }
-#pragma unroll
-    for (int u = 0; u < FL_ILP; ++u) {
-      const int p = q[u];
-      want[u] = ok[u] ? flat_state(labels[p]) : 0u;
-      const int r = p / cols, c = p - r * cols;
-      const int nr = r + dy, nc = c + dx;
-      ok[u] = ok[u] && nr >= 0 && nr < rows && nc >= 0 && nc < cols;
-      q[u] = ok[u] ? nr * cols + nc : 0;
-    }
-#pragma unroll
-    for (int u = 0; u < FL_ILP; ++u) seen[u] = ok[u] ? __ldcg(open + q[u]) : 0u;
-#pragma unroll
-    for (int u = 0; u < FL_ILP; ++u) {
-      bool won = false;
-      if (ok[u] && seen[u] != 0u && flat_claim(open, q[u], seen[u], want[u], mode)) {
-        won = true;
-        flat_assign(q[u], level + 1, mode, (int)(want[u] >> 2) - 1, flat_mask, fh_read, fh_acc);
-      }
-      bq_push(bq, won, q[u]);
-    }
-    bq_maybe_flush(bq, ++round, qout, cnt_out);
+// The passes of one sweep: cooperative launch, every CTA resident.  Tiles of a pass are drawn from a counter.
+#ifndef OFL_FL_SWEEP_CTAS
+#define OFL_FL_SWEEP_CTAS 10  // 128 threads, 51 registers, 21 KB of shared memory: measured best of 6 / 8 / 10 / 16
+#endif
+__global__ void __launch_bounds__(FS_THREADS, OFL_FL_SWEEP_CTAS) flat_tile_sweep_kernel(SweepArgs a) {
+  __shared__ TileSmem sm;
+  unsigned generation = 0;
+  for (int i = threadIdx.x; i < FT_IMG; i += FS_THREADS) {  // the guard ring stays like this
+    sm.D[i] = FL_INF;
+    sm.S[i] = 0u;
   }
-  bq_flush(bq, qout, cnt_out);
+  for (int pass = 0;; ++pass) {
+    if (threadIdx.x == 0) sm.n_act = __ldcg(&a.cnt[CNT_TCOUNT0 + pass % 3]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // the slots of pass + 2: last read in pass - 1
+      a.cnt[CNT_TCOUNT0 + (pass + 2) % 3] = 0;
+      a.cnt[CNT_TTAKE0 + (pass + 2) % 3] = 0;
+      a.cnt[CNT_PASSES] = (unsigned)pass;
+      if (pass < 40) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.cnt[CNT_PASSTIME0 + pass] = (unsigned)t;
+      }
+    }
+    __syncthreads();
+    const unsigned n_act = sm.n_act;
+    if (n_act == 0) break;
+    for (;;) {
+      __syncthreads();
+      if (threadIdx.x == 0) sm.take = atomicAdd(&a.cnt[CNT_TTAKE0 + pass % 3], 1u);
+      __syncthreads();
+      const unsigned t = sm.take;
+      if (t >= n_act) break;
+      tile_process(a, sm, __ldcg(a.lists + (size_t)(pass % 3) * a.n_tiles + t), pass);
+    }
+    grid_barrier(&a.cnt[CNT_BAR], generation);
+  }
+}
+
+// The sweep's levels become mask values (:153-154 / :209-214) and, for the away sweep, flat heights (the largest
+// level of a flat; the reference's last write is the largest because levels only grow).  Neighbouring cells mostly
+// share a label: a warp reduces per label before it touches flat_height.
+__global__ void __launch_bounds__(FL_THREADS)
+flat_tile_assign_kernel(int64_t n, int mode, const int* __restrict__ D, const unsigned* __restrict__ open,
+                        const int* __restrict__ labels, int* flat_mask, const int* fh_read, int* fh_acc, unsigned* cnt) {
+  const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
+  int d = 0, lab = 0;
+  if (i < n) {
+    d = D[i];
+    if (d >= FL_INF) d = 0;
+  }
+  if (d > 0) {
+    const unsigned o = open[i];
+    lab = o ? (int)(o >> 2) - 1 : labels[i];
+    if (mode == SWEEP_AWAY) {
+      flat_mask[i] = d;
+    } else {
+      const int fm = flat_mask[i];
+      int away = 0;  // flat_height - (increments away from higher terrain), 0 where the away sweep never came
+      if (lab > 0) {
+        if (mode == SWEEP_TOWARDS_NEGATED && fm < 0) away = fm + fh_read[lab - 1];
+        if (mode == SWEEP_TOWARDS && fm > 0) away = fh_read[lab - 1] - fm;
+      }
+      flat_mask[i] = away + 2 * d;
+    }
+  }
+  const int top = __reduce_max_sync(0xffffffffu, d);
+  if (top == 0) return;  // warp-uniform
+  if ((threadIdx.x & 31) == 0 && __ldcg(cnt + CNT_MAXLEVEL) < (unsigned)top) atomicMax(cnt + CNT_MAXLEVEL, (unsigned)top);
+  if (mode != SWEEP_AWAY) return;
+  const int key = d > 0 ? lab : 0;
+  const unsigned grp = __match_any_sync(0xffffffffu, key);
+  const int m = __reduce_max_sync(grp, d);
+  if (key > 0 && (threadIdx.x & 31) == __ffs(grp) - 1 && __ldcg(fh_acc + key - 1) < m) atomicMax(fh_acc + key - 1, m);
 }
 
 // flat_height[k] takes the sweep's value where the sweep reached label k+1 (standalone away_from_higher)
@@ -543,19 +770,29 @@ inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + thre
 
 struct FlatsWork {
   int* parent;  // union-find forest, later flat_height
-  int* q0;      // frontier queue / block counts of the label scan
-  int* q1;      // seed list / frontier queue
+  int* q0;      // block counts of the label scan, later the sweeps' level per cell
+  int* q1;      // seed list
   unsigned* open;  // the sweeps' candidate words
   uint8_t* edges;
   unsigned* cnt;
+  int* tiles;   // three tile lists and the tile stamps of the sweeps
 };
 
 size_t flats_align(size_t v) { return (v + 255) / 256 * 256; }
 
-int carve(void* workspace, size_t workspace_bytes, int64_t n, FlatsWork* w) {
+int64_t sweep_tiles(int64_t rows, int64_t cols) { return ((rows + FT - 1) / FT) * ((cols + FT - 1) / FT); }
+
+size_t flats_bytes(int64_t rows, int64_t cols) {
+  const int64_t n = rows * cols;
+  return 4 * flats_align((size_t)n * sizeof(int)) + flats_align((size_t)n) + flats_align(CNT_SLOTS * sizeof(unsigned)) +
+         flats_align((size_t)sweep_tiles(rows, cols) * 5 * sizeof(int));
+}
+
+int carve(void* workspace, size_t workspace_bytes, int64_t rows, int64_t cols, FlatsWork* w) {
+  const int64_t n = rows * cols;
   const size_t a = flats_align((size_t)n * sizeof(int)), e = flats_align((size_t)n), c = flats_align(CNT_SLOTS * sizeof(unsigned));
-  OFL_REQUIRE(workspace_bytes >= 4 * a + e + c, OFL_ERR_WORKSPACE, "flats workspace too small: %zu < %zu", workspace_bytes,
-              4 * a + e + c);
+  OFL_REQUIRE(workspace_bytes >= flats_bytes(rows, cols), OFL_ERR_WORKSPACE, "flats workspace too small: %zu < %zu",
+              workspace_bytes, flats_bytes(rows, cols));
   char* p = static_cast<char*>(workspace);
   w->parent = reinterpret_cast<int*>(p);
   w->q0 = reinterpret_cast<int*>(p + a);
@@ -563,57 +800,84 @@ int carve(void* workspace, size_t workspace_bytes, int64_t n, FlatsWork* w) {
   w->open = reinterpret_cast<unsigned*>(p + 3 * a);
   w->edges = reinterpret_cast<uint8_t*>(p + 4 * a);
   w->cnt = reinterpret_cast<unsigned*>(p + 4 * a + e);
+  w->tiles = reinterpret_cast<int*>(p + 4 * a + e + c);
   return OFL_OK;
 }
 
-// One sweep from the seed list in w.q1 (count in cnt[CNT_SEEDS]).  Host-synchronous: the level loop reads the
-// next frontier's size back once per batch of launches.
+// CTAs of the persistent sweep kernel: as many as are resident at once (the grid barrier needs them all)
+int sweep_blocks() {
+  static std::atomic<int> gen{-1};
+  static std::atomic<int> blocks{0};
+  if (gen.load() != device_generation()) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flat_tile_sweep_kernel, FS_THREADS, 0) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    blocks.store(per_sm * sm_count());
+    gen.store(device_generation());
+  }
+  return blocks.load();
+}
+
+// One sweep from the seed list in w.q1 (count in cnt[CNT_SEEDS]): levels by tile relaxation, then mask values.
+// Asynchronous unless the caller wants the level count.
 int run_gradient(int rows, int cols, const int* labels, const uint8_t* fdr, int mode, bool open_ready, int* flat_mask,
                  const int* fh_read, int* fh_acc, const FlatsWork& w, int64_t* levels_out, cudaStream_t st) {
-  // open_ready: w.open already describes the candidates (resolve_flats: armed by the labelling, re-used by the
-  // second sweep through the generation bits); otherwise they are armed from the mask, negated first for towards_lower
+  // open_ready: w.open already describes the candidates (resolve_flats: armed by the labelling, the same for both
+  // sweeps); otherwise they are armed from the mask, negated first for towards_lower
   const int64_t n = (int64_t)rows * cols;
-  OFL_CUDA(cudaMemsetAsync(w.cnt + CNT_FRONT0, 0, 3 * sizeof(unsigned), st));
+  SweepArgs a;
+  a.rows = rows;
+  a.cols = cols;
+  a.tiles_x = (cols + FT - 1) / FT;
+  a.tiles_y = (rows + FT - 1) / FT;
+  a.n_tiles = a.tiles_x * a.tiles_y;
+  a.D = w.q0;
+  a.open = w.open;
+  a.labels = labels;
+  a.lists = w.tiles;
+  a.stamp = w.tiles + (size_t)3 * a.n_tiles;
+  a.seen = w.tiles + (size_t)4 * a.n_tiles;
+  a.cnt = w.cnt;
+  OFL_CUDA(cudaMemsetAsync(w.cnt + CNT_TCOUNT0, 0, (CNT_SLOTS - CNT_TCOUNT0) * sizeof(unsigned), st));
+  OFL_CUDA(cudaMemsetAsync(a.stamp, 0, (size_t)2 * a.n_tiles * sizeof(int), st));  // stamps and seen flags
+  OFL_CUDA(cudaMemsetAsync(a.D, 0x7f, (size_t)n * sizeof(int), st));
   if (!open_ready) {
     flat_prepare_kernel<<<blocks_for(n, FL_THREADS), FL_THREADS, 0, st>>>(n, mode, flat_mask, labels, fdr, w.open);
     OFL_CHECK_LAUNCH();
   }
-  const unsigned grid = (unsigned)(sm_count() * 8);  // 8 CTAs of 256 threads fill an SM
-  flat_seed_level_kernel<<<grid, FL_THREADS, 0, st>>>(w.q1, labels, mode, flat_mask, w.open, fh_read, fh_acc, w.q0, w.cnt);
+  flat_tile_seed_kernel<<<(unsigned)(sm_count() * 8), FL_THREADS, 0, st>>>(w.q1, flat_mask, a);
   OFL_CHECK_LAUNCH();
-  unsigned* h_cnt = nullptr;
-  int rc = pinned_get(64, reinterpret_cast<void**>(&h_cnt));
-  if (rc != OFL_OK) return rc;
-  int level = 1;  // the frontier in `qin` holds the cells of this level
-  int* qin = w.q0;
-  int* qout = w.q1;
-  int batch = 8;
-  for (;;) {
-    for (int b = 0; b < batch; ++b) {
-      flat_level_kernel<<<grid, FL_THREADS, 0, st>>>(level, qin, qout, labels, rows, cols, mode, flat_mask, w.open, fh_read,
-                                                      fh_acc, w.cnt);
-      OFL_CHECK_LAUNCH();
-      ++level;
-      int* t = qin;
-      qin = qout;
-      qout = t;
-    }
-    OFL_CUDA(cudaMemcpyAsync(h_cnt, w.cnt + CNT_FRONT0 + level % 3, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    OFL_CUDA(cudaStreamSynchronize(st));
-    if (*h_cnt == 0) break;
-    OFL_REQUIRE(level < INT_MAX / 4, OFL_ERR_INVALID, "flat gradient did not terminate");
-    if (batch < 64) batch *= 2;
+  {
+    void* args[] = {&a};
+    OFL_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(flat_tile_sweep_kernel), dim3((unsigned)sweep_blocks()),
+                                         dim3(FS_THREADS), args, 0, st));
   }
-  if (levels_out) *levels_out = level;
+  flat_tile_assign_kernel<<<blocks_for(n, FL_THREADS), FL_THREADS, 0, st>>>(n, mode, a.D, w.open, labels, flat_mask, fh_read,
+                                                                            fh_acc, w.cnt);
+  OFL_CHECK_LAUNCH();
+  if (levels_out) {
+    unsigned* h_cnt = nullptr;
+    int rc = pinned_get(256, reinterpret_cast<void**>(&h_cnt));
+    if (rc != OFL_OK) return rc;
+    OFL_CUDA(cudaMemcpyAsync(h_cnt, w.cnt + CNT_PASSES, (CNT_SLOTS - CNT_PASSES) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    OFL_CUDA(cudaStreamSynchronize(st));
+    *levels_out = h_cnt[CNT_MAXLEVEL - CNT_PASSES];
+    if (getenv("OFL_FLATS_DEBUG"))
+      fprintf(stderr, "[flats sweep mode %d] tiles %d passes %u tile visits %u in-tile rounds %u levels %u\n", mode, a.n_tiles,
+              h_cnt[0], h_cnt[CNT_VISITS - CNT_PASSES], h_cnt[CNT_ROUNDS - CNT_PASSES], h_cnt[CNT_MAXLEVEL - CNT_PASSES]);
+    if (getenv("OFL_FLATS_DEBUG")) {
+      fprintf(stderr, "  most rounds in a visit %u; pass durations (us):", h_cnt[CNT_MAXROUNDS - CNT_PASSES]);
+      for (unsigned k = 0; k + 1 <= h_cnt[0] && k + 1 < 40; ++k)
+        fprintf(stderr, " %.0f", (h_cnt[CNT_PASSTIME0 - CNT_PASSES + k + 1] - h_cnt[CNT_PASSTIME0 - CNT_PASSES + k]) * 1e-3);
+      fprintf(stderr, "\n");
+    }
+  }
   return OFL_OK;
 }
 
 }  // namespace
 
-size_t flats_workspace_bytes(int64_t rows, int64_t cols) {
-  const int64_t n = rows * cols;
-  return 4 * flats_align((size_t)n * sizeof(int)) + flats_align((size_t)n) + flats_align(CNT_SLOTS * sizeof(unsigned));
-}
+size_t flats_workspace_bytes(int64_t rows, int64_t cols) { return flats_bytes(rows, cols); }
 
 static int check_shape(int64_t rows, int64_t cols) {
   OFL_REQUIRE(rows > 0 && cols > 0 && rows * cols < (int64_t)INT_MAX, OFL_ERR_INVALID,
@@ -634,7 +898,7 @@ int launch_flat_edges(const float* dem, const uint8_t* fdr, int64_t rows, int64_
                                                                       nullptr, cnt_dev);
   OFL_CHECK_LAUNCH();
   unsigned* h = nullptr;
-  rc = pinned_get(64, reinterpret_cast<void**>(&h));
+  rc = pinned_get(256, reinterpret_cast<void**>(&h));
   if (rc != OFL_OK) return rc;
   OFL_CUDA(cudaMemcpyAsync(h, cnt_dev, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   OFL_CUDA(cudaStreamSynchronize(st));
@@ -651,7 +915,7 @@ int launch_resolve_flats(const float* dem, const uint8_t* fdr, int64_t rows, int
   if (rc != OFL_OK) return rc;
   const int64_t n = rows * cols;
   FlatsWork w;
-  rc = carve(workspace, workspace_bytes, n, &w);
+  rc = carve(workspace, workspace_bytes, rows, cols, &w);
   if (rc != OFL_OK) return rc;
   const unsigned nb = blocks_for(n, FL_THREADS), nbc = blocks_for(n, FL_CELLS_PER_CTA);
   OFL_CUDA(cudaMemsetAsync(w.cnt, 0, CNT_SLOTS * sizeof(unsigned), st));
@@ -659,7 +923,7 @@ int launch_resolve_flats(const float* dem, const uint8_t* fdr, int64_t rows, int
   int* minlow = w.q1;           // per-component smallest low edge, until the labels are known
   int* seedlabel = flat_mask;   // label of each component's first low edge, until the labels are known
   unsigned* h = nullptr;
-  rc = pinned_get(64, reinterpret_cast<void**>(&h));
+  rc = pinned_get(256, reinterpret_cast<void**>(&h));
   if (rc != OFL_OK) return rc;
   int64_t lv_away = 0, lv_low = 0;
   {
@@ -700,12 +964,12 @@ int launch_resolve_flats(const float* dem, const uint8_t* fdr, int64_t rows, int
   PhaseScope ps(PHASE_FLATS_SWEEP, st);
   flat_collect_kernel<<<nbc, FL_SCAN_THREADS, 0, st>>>(n, w.edges, 2u, labels, w.q1, w.cnt);
   OFL_CHECK_LAUNCH();
-  rc = run_gradient((int)rows, (int)cols, labels, fdr, SWEEP_AWAY, true, flat_mask, flat_height, flat_height, w, &lv_away, st);
+  rc = run_gradient((int)rows, (int)cols, labels, fdr, SWEEP_AWAY, true, flat_mask, flat_height, flat_height, w, info ? &lv_away : nullptr, st);
   if (rc != OFL_OK) return rc;
   OFL_CUDA(cudaMemsetAsync(w.cnt + CNT_SEEDS, 0, sizeof(unsigned), st));
   flat_collect_kernel<<<nbc, FL_SCAN_THREADS, 0, st>>>(n, w.edges, 1u, labels, w.q1, w.cnt);
   OFL_CHECK_LAUNCH();
-  rc = run_gradient((int)rows, (int)cols, labels, fdr, SWEEP_TOWARDS, true, flat_mask, flat_height, flat_height, w, &lv_low, st);
+  rc = run_gradient((int)rows, (int)cols, labels, fdr, SWEEP_TOWARDS, true, flat_mask, flat_height, flat_height, w, info ? &lv_low : nullptr, st);
   if (rc != OFL_OK) return rc;
   if (info) {
     info[3] = lv_away;
@@ -725,7 +989,7 @@ int launch_flat_gradient(const int* labels, const uint8_t* fdr, int64_t rows, in
   OFL_REQUIRE(n_seeds >= 0 && n_seeds <= n && n_heights >= 0 && n_heights <= n, OFL_ERR_INVALID,
               "seed / flat_height count out of range");
   FlatsWork w;
-  rc = carve(workspace, workspace_bytes, n, &w);
+  rc = carve(workspace, workspace_bytes, rows, cols, &w);
   if (rc != OFL_OK) return rc;
   PhaseScope ps(PHASE_FLATS, st);
   OFL_CUDA(cudaMemsetAsync(w.cnt, 0, CNT_SLOTS * sizeof(unsigned), st));

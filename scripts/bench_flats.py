@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--kind", type=int, default=1)
     ap.add_argument("--relief", type=float, default=200.0)
     ap.add_argument("--holes", type=int, default=5)
+    ap.add_argument("--lake", action="store_true", help="one flat of (size - 18)^2 cells drained through one channel: size/2 and size levels")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--oracle-window", type=int, default=0, help="ignored (parity and the CPU baseline live in tests/ and bench.py)")
     a = ap.parse_args()
@@ -38,7 +39,12 @@ def main():
     except Exception:
         pass
     _native.init(0)
-    dem = dev.synth_dem(n, n, seed=3, kind=a.kind, relief=a.relief, holes_permille=a.holes)
+    if a.lake:
+        dem = torch.full((n, n), 10.0, dtype=torch.float32, device="cuda")
+        dem[9:-9, 9:-9] = 5.0
+        dem[n // 2, :10] = torch.linspace(1.0, 4.5, 10, device="cuda")
+    else:
+        dem = dev.synth_dem(n, n, seed=3, kind=a.kind, relief=a.relief, holes_permille=a.holes)
     fdr0 = dev.flow_direction(dem, -9999.0).contiguous()
     work = dev.flats_workspace(n, n)
     flat_mask = torch.empty((n, n), dtype=torch.int32, device="cuda")
@@ -64,7 +70,7 @@ def main():
     cells = n * n
     out = {
         "what": "ofl_fix_flats_f32 (resolve_flats + d8_masked_flow_dirs), device buffers",
-        "size": n, "kind": a.kind, "relief": a.relief, "ms": ms, "gcells_s": cells / ms / 1e6,
+        "size": n, "kind": "lake" if a.lake else a.kind, "relief": a.relief, "ms": ms, "gcells_s": cells / ms / 1e6,
         "algorithmic_gbs_14B": cells * 14 / ms / 1e6, "frac_of_hbm_peak": cells * 14 / ms / 1e6 / peak, "peak_gbs": peak,
         "undefined_before": int((fdr0 == 8).sum()), "undefined_after": int((fdr == 8).sum()),
         "low_edges": info[0], "high_edges": info[1], "labels": info[2], "away_levels": info[3],

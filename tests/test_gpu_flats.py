@@ -154,6 +154,18 @@ def _cases():
     wide[0, :] = 5.0
     yield "one_long_flat", wide
     yield "thin", np.round(synth.fractal(2, 3000, beta=2.0, seed=7) / 100.0).astype(np.float32)
+    # the sweeps relax 32 x 32 tiles: a lake whose levels cross many tiles, drained through one channel ...
+    lake = np.full((700, 650), 10.0, dtype=np.float32)
+    lake[9:-9, 9:-9] = 5.0
+    lake[350, :10] = np.linspace(1.0, 4.5, 10, dtype=np.float32)
+    yield "lake_with_outlet", lake
+    # ... and one flat that winds between walls, entering and leaving every tile it meets several times
+    maze = np.zeros((203, 330), dtype=np.float32)
+    maze[0, :] = maze[-1, :] = maze[:, 0] = maze[:, -1] = 7.0
+    for k, r in enumerate(range(3, 200, 3)):
+        maze[r, (1 if k % 2 else 3):(-3 if k % 2 else -1)] = 7.0
+    maze[1, 1] = -1.0
+    yield "winding_flat", maze
 
 
 @pytest.mark.parametrize("name,dem", list(_cases()), ids=[n for n, _ in _cases()])
