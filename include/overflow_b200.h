@@ -243,10 +243,10 @@ int ofl_strip_collect_flags(const void* strip_workspace, int64_t rows, int64_t c
                             int n_strips, int32_t* flags, void* stream);
 
 /*
- * Flat resolution (Barnes, Lehman & Mulla 2014; the reference's src/overflow/fix_flats.py).  One tile of fewer
- * than 2^31 cells; every raster is DENSE row-major (leading dimension == cols).  Host-pointer calls stage through
- * library buffers; device-pointer calls take CUDA pointers.  All of these synchronise the stream before they
- * return (the level loops of the two sweeps read a frontier count back).
+ * Flat resolution (Barnes, Lehman & Mulla 2014; the reference's src/overflow/fix_flats.py).  One tile of at most
+ * 2^32 cells (cell indices are 32-bit unsigned on the device); every raster is DENSE row-major (leading dimension
+ * == cols).  Host-pointer calls stage through library buffers; device-pointer calls take CUDA pointers.  Calls that
+ * return counts (n_low / n_high, info) synchronise the stream before they return.
  *   dem        float32 elevations (compared with == and <, as the reference does on the array's own dtype)
  *   fdr        uint8 direction codes; 8 = no direction (the flats), 9 = NODATA
  *   edges      uint8 out: bit 0 = low edge, bit 1 = high edge (the reference returns two lists, row-major)
@@ -254,7 +254,7 @@ int ofl_strip_collect_flags(const void* strip_workspace, int64_t rows, int64_t c
  *              row-major low-edge list first meets each flat (1-based; 0 = not in a drainable flat)
  *   info       nullable int64[5] out: low edges, high edges, labels, levels of the away / towards sweeps
  *   workspace  device scratch of ofl_flats_workspace_bytes (NULL: library-owned, cached)
- * ofl_flat_gradient_i32 runs one sweep from a list of seed cell indices (row * cols + col): towards == 0 is
+ * ofl_flat_gradient_i32 runs one sweep from a list of seed cell indices (row * cols + col, read as uint32): towards == 0 is
  * away_from_higher, towards == 1 is towards_lower (which negates flat_mask first and reads flat_height).
  * ofl_fix_flats_f32 rewrites the code-8 cells of fdr in place; for host callers flat_mask / labels may be NULL.
  */

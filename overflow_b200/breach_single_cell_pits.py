@@ -25,8 +25,8 @@ def breach_single_cell_pits_in_chunk(chunk: np.ndarray, nodata_value: float, ret
     if chunk.dtype != np.float32:
         raise TypeError(f"breach_single_cell_pits_in_chunk works on float32 chunks, got {chunk.dtype}")
     rows, cols = chunk.shape
-    if rows * cols >= 2**31 - 1:
-        raise ValueError("pit breaching works on one chunk of fewer than 2**31 cells")
+    if rows * cols > 2**32:
+        raise ValueError("pit breaching works on one chunk of at most 2**32 cells")
     unsolved = np.zeros((rows, cols), dtype=np.int8)
     info = (ctypes.c_int64 * 3)()
     if rows and cols:

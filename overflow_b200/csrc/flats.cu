@@ -33,7 +33,7 @@ namespace ofl {
 namespace {
 
 constexpr int FL_UNDEF = OFL_DIR_UNDEFINED, FL_NODATA = OFL_DIR_NODATA;
-constexpr int FL_BIG = INT_MAX;
+constexpr unsigned FL_NONE = 0xFFFFFFFFu;  // minlow: the component has no low edge (see flat_lowroot_kernel for cell 2^32 - 1)
 constexpr int FL_THREADS = 256;
 constexpr int FL_SCAN_THREADS = 1024;
 
@@ -45,7 +45,9 @@ enum {
   CNT_BAR, CNT_RELEASE,                   // grid barrier of the sweep kernel
   CNT_PASSES, CNT_MAXLEVEL,
   CNT_VISITS, CNT_ROUNDS,                 // statistics of the sweep (OFL_FLATS_DEBUG)
-  CNT_MAXROUNDS, CNT_PASSTIME0,           // most rounds in one visit; start of pass k in ns (low word), 40 slots
+  CNT_MAXROUNDS,                          // most rounds in one visit
+  CNT_LASTLOW, CNT_LASTROOT,              // cell 2^32 - 1 is a low edge / its root (a raster of exactly 2^32 cells)
+  CNT_PASSTIME0,                          // start of pass k in ns (low word), 40 slots
   CNT_SLOTS = 64
 };
 
@@ -58,12 +60,14 @@ __constant__ int c_dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
 // and a count-leading-zeros, no atomics), which is most of the linking on a plateau.
 __global__ void __launch_bounds__(FL_THREADS)
 flat_edges_kernel(const float* __restrict__ dem, const uint8_t* __restrict__ fdr, int rows, int cols, uint8_t* edges,
-                  int* parent, int* minlow, unsigned* cnt) {
-  const unsigned n = (unsigned)rows * (unsigned)cols;
+                  unsigned* parent, unsigned* minlow, unsigned* cnt) {
+  // cell indices are 32-bit unsigned (a raster holds at most 2^32 cells); only the bound needs 64 bits
+  const int64_t n = (int64_t)rows * cols;
   const unsigned i = blockIdx.x * FL_THREADS + threadIdx.x;
+  const bool inside = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x < n;
   int flag = 0;
   bool left_eq = false;
-  if (i < n) {
+  if (inside) {
     const int r = (int)(i / (unsigned)cols), c = (int)(i - (unsigned)r * (unsigned)cols);
     const int cur = fdr[i];
     const float z = dem[i];
@@ -95,9 +99,9 @@ flat_edges_kernel(const float* __restrict__ dem, const uint8_t* __restrict__ fdr
     const int lane = threadIdx.x & 31;
     const unsigned em = __ballot_sync(0xffffffffu, left_eq);
     const unsigned starts = (~em & ((2u << lane) - 1u)) | 1u;  // lanes <= mine that begin a run (lane 0 always does)
-    if (i < n) {
-      parent[i] = (int)(i - (unsigned)(lane - (31 - __clz(starts))));
-      minlow[i] = FL_BIG;
+    if (inside) {
+      parent[i] = i - (unsigned)(lane - (31 - __clz(starts)));
+      minlow[i] = FL_NONE;
     }
   }
   const int lo = __syncthreads_count(flag == 1), hi = __syncthreads_count(flag == 2);
@@ -108,10 +112,10 @@ flat_edges_kernel(const float* __restrict__ dem, const uint8_t* __restrict__ fdr
 }
 
 // ---------------------------------------------------------------- equal-elevation components
-__device__ __forceinline__ int uf_find(int* p, int i) {
-  int cur = __ldcg(p + i);
+__device__ __forceinline__ unsigned uf_find(unsigned* p, unsigned i) {
+  unsigned cur = __ldcg(p + i);
   while (cur != i) {
-    const int nxt = __ldcg(p + cur);
+    const unsigned nxt = __ldcg(p + cur);
     if (nxt != cur) p[i] = nxt;  // path halving; any ancestor is a valid parent
     i = cur;
     cur = nxt;
@@ -120,8 +124,8 @@ __device__ __forceinline__ int uf_find(int* p, int i) {
 }
 
 // read-only walk to the root (used once the forest is final: concurrent halving could overwrite a flattened entry)
-__device__ __forceinline__ int uf_find_ro(const int* p, int i) {
-  int cur = __ldcg(p + i);
+__device__ __forceinline__ unsigned uf_find_ro(const unsigned* p, unsigned i) {
+  unsigned cur = __ldcg(p + i);
   while (cur != i) {
     i = cur;
     cur = __ldcg(p + cur);
@@ -129,17 +133,17 @@ __device__ __forceinline__ int uf_find_ro(const int* p, int i) {
   return i;
 }
 
-__device__ __forceinline__ void uf_unite(int* p, int a, int b) {
+__device__ __forceinline__ void uf_unite(unsigned* p, unsigned a, unsigned b) {
   for (;;) {
     a = uf_find(p, a);
     b = uf_find(p, b);
     if (a == b) return;
     if (a < b) {
-      const int t = a;
+      const unsigned t = a;
       a = b;
       b = t;
     }
-    const int old = atomicMin(p + a, b);  // hook the larger root under the smaller one
+    const unsigned old = atomicMin(p + a, b);  // hook the larger root under the smaller one
     if (old == a) return;
     a = old;  // a was no longer a root: carry on from what it pointed to
   }
@@ -150,22 +154,21 @@ __device__ __forceinline__ void uf_unite(int* p, int a, int b) {
 // two runs), and a diagonal pair only when neither the cell below nor the cell beside it continues a run that the
 // vertical rule already ties in.
 __global__ void __launch_bounds__(FL_THREADS)
-flat_merge_kernel(const float* __restrict__ dem, int rows, int cols, int* parent) {
-  const unsigned n = (unsigned)rows * (unsigned)cols;
+flat_merge_kernel(const float* __restrict__ dem, int rows, int cols, unsigned* parent) {
   const unsigned i = blockIdx.x * FL_THREADS + threadIdx.x;
-  if (i >= n) return;
+  if ((int64_t)blockIdx.x * FL_THREADS + threadIdx.x >= (int64_t)rows * cols) return;
   const int r = (int)(i / (unsigned)cols), c = (int)(i - (unsigned)r * (unsigned)cols);
   const float z = dem[i];
   const bool left_eq = c > 0 && dem[i - 1] == z;
   const bool right_eq = c + 1 < cols && dem[i + 1] == z;
-  if (right_eq && (threadIdx.x & 31) == 31) uf_unite(parent, (int)i, (int)i + 1);
+  if (right_eq && (threadIdx.x & 31) == 31) uf_unite(parent, i, i + 1u);
   if (r + 1 < rows) {
     const unsigned j = i + (unsigned)cols;
     if (dem[j] == z) {
-      if (!left_eq || !(dem[j - 1] == z)) uf_unite(parent, (int)i, (int)j);  // c == 0 implies !left_eq
+      if (!left_eq || !(dem[j - 1] == z)) uf_unite(parent, i, j);  // c == 0 implies !left_eq
     } else {
-      if (c > 0 && !left_eq && dem[j - 1] == z) uf_unite(parent, (int)i, (int)(j - 1));
-      if (c + 1 < cols && !right_eq && dem[j + 1] == z) uf_unite(parent, (int)i, (int)(j + 1));
+      if (c > 0 && !left_eq && dem[j - 1] == z) uf_unite(parent, i, j - 1u);
+      if (c + 1 < cols && !right_eq && dem[j + 1] == z) uf_unite(parent, i, j + 1u);
     }
   }
 }
@@ -214,32 +217,39 @@ __device__ __forceinline__ unsigned cta_exclusive(unsigned c, unsigned* total) {
 
 // low edges look their root up (making their own pointer direct) and post their index to the root's slot
 __global__ void __launch_bounds__(FL_SCAN_THREADS)
-flat_lowroot_kernel(int64_t n, int* parent, const uint8_t* __restrict__ edges, int* minlow) {
+flat_lowroot_kernel(int64_t n, unsigned* parent, const uint8_t* __restrict__ edges, unsigned* minlow, unsigned* cnt) {
   const int64_t i0 = 4 * ((int64_t)blockIdx.x * FL_SCAN_THREADS + threadIdx.x);
   const unsigned w = flag_word(edges, n, i0, true) & 0x01010101u;
   if (w == 0) return;
   for (int k = 0; k < 4; ++k)
     if ((w >> (8 * k)) & 1u) {
-      const int i = (int)(i0 + k);
-      const int root = uf_find_ro(parent, i);
+      const unsigned i = (unsigned)(i0 + k);
+      const unsigned root = uf_find_ro(parent, i);
       parent[i] = root;  // own entry only, and a root is a valid parent for any reader walking by
       if (__ldcg(minlow + root) > i) atomicMin(minlow + root, i);  // a plain look first: most low edges lose to an earlier one
+      // cell 2^32 - 1 (the last cell of a raster of exactly 2^32 cells) looks like FL_NONE in minlow: when it is
+      // its component's only low edge the slot says "none", and the labelling asks these two words instead
+      if (i == FL_NONE) {
+        cnt[CNT_LASTROOT] = root;
+        cnt[CNT_LASTLOW] = 1u;
+      }
     }
 }
 
 // a seed is the first low edge (row-major) of its component; bit k of the result: cell i0 + k is one
-__device__ __forceinline__ unsigned seed_bits(int64_t n, int64_t i0, const int* parent, const uint8_t* edges,
-                                              const int* minlow) {
+__device__ __forceinline__ unsigned seed_bits(int64_t n, int64_t i0, const unsigned* parent, const uint8_t* edges,
+                                              const unsigned* minlow) {
   const unsigned w = flag_word(edges, n, i0, true) & 0x01010101u;
   unsigned bits = 0;
   if (w)
     for (int k = 0; k < 4; ++k)
-      if (((w >> (8 * k)) & 1u) && minlow[parent[i0 + k]] == (int)(i0 + k)) bits |= 1u << k;
+      if (((w >> (8 * k)) & 1u) && minlow[parent[i0 + k]] == (unsigned)(i0 + k)) bits |= 1u << k;
   return bits;
 }
 
 __global__ void __launch_bounds__(FL_SCAN_THREADS)
-flat_seed_count_kernel(int64_t n, const int* parent, const uint8_t* __restrict__ edges, const int* minlow, int* blockcnt) {
+flat_seed_count_kernel(int64_t n, const unsigned* parent, const uint8_t* __restrict__ edges, const unsigned* minlow,
+                       int* blockcnt) {
   const int64_t i0 = 4 * ((int64_t)blockIdx.x * FL_SCAN_THREADS + threadIdx.x);
   unsigned total;
   cta_exclusive(__popc(seed_bits(n, i0, parent, edges, minlow)), &total);
@@ -273,7 +283,7 @@ __global__ void __launch_bounds__(FL_SCAN_THREADS) flat_seed_scan_kernel(int nb,
 
 // seedlabel[i] = 1 + rank of seed i (row-major)
 __global__ void __launch_bounds__(FL_SCAN_THREADS)
-flat_seed_rank_kernel(int64_t n, const int* parent, const uint8_t* __restrict__ edges, const int* minlow,
+flat_seed_rank_kernel(int64_t n, const unsigned* parent, const uint8_t* __restrict__ edges, const unsigned* minlow,
                       const int* __restrict__ blockoff, int* seedlabel) {
   const int64_t i0 = 4 * ((int64_t)blockIdx.x * FL_SCAN_THREADS + threadIdx.x);
   const unsigned bits = seed_bits(n, i0, parent, edges, minlow);
@@ -290,12 +300,15 @@ flat_seed_rank_kernel(int64_t n, const int* parent, const uint8_t* __restrict__ 
 __device__ __forceinline__ unsigned flat_state(int lab) { return (unsigned)(lab + 1) << 2; }
 
 __global__ void __launch_bounds__(FL_THREADS)
-flat_spread_label_kernel(int64_t n, const int* __restrict__ parent, const int* __restrict__ minlow,
-                         const int* __restrict__ seedlabel, int* labels, const uint8_t* __restrict__ fdr, unsigned* open) {
+flat_spread_label_kernel(int64_t n, const unsigned* __restrict__ parent, const unsigned* __restrict__ minlow,
+                         const int* __restrict__ seedlabel, int* labels, const uint8_t* __restrict__ fdr, unsigned* open,
+                         const unsigned* __restrict__ cnt) {
   const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
   if (i >= n) return;
-  const int m = minlow[uf_find_ro(parent, (int)i)];
-  const int lab = (m == FL_BIG) ? 0 : seedlabel[m];
+  const unsigned root = uf_find_ro(parent, (unsigned)i);
+  const unsigned m = minlow[root];
+  int lab = 0;
+  if (m != FL_NONE || (cnt[CNT_LASTLOW] && cnt[CNT_LASTROOT] == root)) lab = seedlabel[m];
   labels[i] = lab;
   open[i] = (fdr[i] == FL_UNDEF) ? flat_state(lab) : 0u;
 }
@@ -304,7 +317,7 @@ flat_spread_label_kernel(int64_t n, const int* __restrict__ parent, const int* _
 // edge cells -> seed list, in no particular order (the sweeps are order-free); one queue atomic per CTA
 __global__ void __launch_bounds__(FL_SCAN_THREADS)
 flat_collect_kernel(int64_t n, const uint8_t* __restrict__ edges, unsigned bit, const int* __restrict__ labels,
-                    int* seeds, unsigned* cnt) {
+                    unsigned* seeds, unsigned* cnt) {
   __shared__ unsigned cta_base;
   const int64_t i0 = 4 * ((int64_t)blockIdx.x * FL_SCAN_THREADS + threadIdx.x);
   const unsigned w = flag_word(edges, n, i0, true) & (bit * 0x01010101u);
@@ -319,7 +332,7 @@ flat_collect_kernel(int64_t n, const uint8_t* __restrict__ edges, unsigned bit, 
   __syncthreads();
   at += cta_base;
   for (int k = 0; k < 4; ++k)
-    if ((bits >> k) & 1u) seeds[at++] = (int)(i0 + k);
+    if ((bits >> k) & 1u) seeds[at++] = (unsigned)(i0 + k);
 }
 
 // Sweep modes: 0 away_from_higher; 1 towards_lower on a mask that was negated first (the standalone entry point,
@@ -387,14 +400,14 @@ __device__ __forceinline__ void tile_activate(const SweepArgs& a, int tile, int 
 // level 1: the seed cells (:146-148 / :202-204).  A seed that is not a candidate (a low edge: it has a direction)
 // counts only while its mask is not positive (:150-151 / :207-208), like every cell the reference pops.
 __global__ void __launch_bounds__(FL_THREADS)
-flat_tile_seed_kernel(const int* __restrict__ seeds, const int* __restrict__ flat_mask, SweepArgs a) {
-  const unsigned n_seed = a.cnt[CNT_SEEDS];
-  for (unsigned idx = blockIdx.x * FL_THREADS + threadIdx.x; idx < n_seed; idx += gridDim.x * FL_THREADS) {
-    const int p = seeds[idx];
+flat_tile_seed_kernel(const unsigned* __restrict__ seeds, const int* __restrict__ flat_mask, SweepArgs a) {
+  const int64_t n_seed = a.cnt[CNT_SEEDS];
+  for (int64_t idx = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x; idx < n_seed; idx += (int64_t)gridDim.x * FL_THREADS) {
+    const unsigned p = seeds[idx];
     if (a.open[p] == 0u && flat_mask[p] > 0) continue;
     a.D[p] = 1;
     // its own tile, and the tiles that see it in their ring
-    const int r = p / a.cols, c = p - r * a.cols;
+    const int r = (int)(p / (unsigned)a.cols), c = (int)(p - (unsigned)r * (unsigned)a.cols);
     const int ty = r / FT, tx = c / FT, lr = r - ty * FT, lc = c - tx * FT;
     const int vr = lr == 0 ? -1 : (lr == FT - 1 ? 1 : 0), vc = lc == 0 ? -1 : (lc == FT - 1 ? 1 : 0);
     for (int dy = -1; dy <= 1; ++dy)
@@ -721,8 +734,8 @@ flat_tile_assign_kernel(int64_t n, int mode, const int* __restrict__ D, const un
 }
 
 // flat_height[k] takes the sweep's value where the sweep reached label k+1 (standalone away_from_higher)
-__global__ void __launch_bounds__(FL_THREADS) flat_height_merge_kernel(int n, const int* __restrict__ acc, int* fh) {
-  const int i = blockIdx.x * FL_THREADS + threadIdx.x;
+__global__ void __launch_bounds__(FL_THREADS) flat_height_merge_kernel(int64_t n, const int* __restrict__ acc, int* fh) {
+  const int64_t i = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
   if (i < n && acc[i] > 0) fh[i] = acc[i];
 }
 
@@ -769,9 +782,9 @@ flat_masked_dirs_kernel(const int* __restrict__ flat_mask, const int* __restrict
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 struct FlatsWork {
-  int* parent;  // union-find forest, later flat_height
-  int* q0;      // block counts of the label scan, later the sweeps' level per cell
-  int* q1;      // seed list
+  unsigned* parent;  // union-find forest, later flat_height
+  int* q0;           // block counts of the label scan, later the sweeps' level per cell
+  unsigned* q1;      // smallest low edge per component, later the seed list
   unsigned* open;  // the sweeps' candidate words
   uint8_t* edges;
   unsigned* cnt;
@@ -794,9 +807,9 @@ int carve(void* workspace, size_t workspace_bytes, int64_t rows, int64_t cols, F
   OFL_REQUIRE(workspace_bytes >= flats_bytes(rows, cols), OFL_ERR_WORKSPACE, "flats workspace too small: %zu < %zu",
               workspace_bytes, flats_bytes(rows, cols));
   char* p = static_cast<char*>(workspace);
-  w->parent = reinterpret_cast<int*>(p);
+  w->parent = reinterpret_cast<unsigned*>(p);
   w->q0 = reinterpret_cast<int*>(p + a);
-  w->q1 = reinterpret_cast<int*>(p + 2 * a);
+  w->q1 = reinterpret_cast<unsigned*>(p + 2 * a);
   w->open = reinterpret_cast<unsigned*>(p + 3 * a);
   w->edges = reinterpret_cast<uint8_t*>(p + 4 * a);
   w->cnt = reinterpret_cast<unsigned*>(p + 4 * a + e);
@@ -880,8 +893,8 @@ int run_gradient(int rows, int cols, const int* labels, const uint8_t* fdr, int 
 size_t flats_workspace_bytes(int64_t rows, int64_t cols) { return flats_bytes(rows, cols); }
 
 static int check_shape(int64_t rows, int64_t cols) {
-  OFL_REQUIRE(rows > 0 && cols > 0 && rows * cols < (int64_t)INT_MAX, OFL_ERR_INVALID,
-              "flat resolution works on one tile of fewer than 2^31 cells (got %lld x %lld)", (long long)rows,
+  OFL_REQUIRE(rows > 0 && cols > 0 && rows < (1ll << 31) && cols < (1ll << 31) && rows * cols <= (1ll << 32), OFL_ERR_INVALID,
+              "flat resolution works on one tile of at most 2^32 cells (got %lld x %lld)", (long long)rows,
               (long long)cols);
   return OFL_OK;
 }
@@ -919,8 +932,8 @@ int launch_resolve_flats(const float* dem, const uint8_t* fdr, int64_t rows, int
   if (rc != OFL_OK) return rc;
   const unsigned nb = blocks_for(n, FL_THREADS), nbc = blocks_for(n, FL_CELLS_PER_CTA);
   OFL_CUDA(cudaMemsetAsync(w.cnt, 0, CNT_SLOTS * sizeof(unsigned), st));
-  int* flat_height = w.parent;  // lives where the forest was once the labels are known (label count <= cell count)
-  int* minlow = w.q1;           // per-component smallest low edge, until the labels are known
+  int* flat_height = reinterpret_cast<int*>(w.parent);  // lives where the forest was once the labels are known
+  unsigned* minlow = w.q1;      // per-component smallest low edge, until the labels are known
   int* seedlabel = flat_mask;   // label of each component's first low edge, until the labels are known
   unsigned* h = nullptr;
   rc = pinned_get(256, reinterpret_cast<void**>(&h));
@@ -932,7 +945,7 @@ int launch_resolve_flats(const float* dem, const uint8_t* fdr, int64_t rows, int
     OFL_CHECK_LAUNCH();
     flat_merge_kernel<<<nb, FL_THREADS, 0, st>>>(dem, (int)rows, (int)cols, w.parent);
     OFL_CHECK_LAUNCH();
-    flat_lowroot_kernel<<<nbc, FL_SCAN_THREADS, 0, st>>>(n, w.parent, w.edges, minlow);
+    flat_lowroot_kernel<<<nbc, FL_SCAN_THREADS, 0, st>>>(n, w.parent, w.edges, minlow, w.cnt);
     OFL_CHECK_LAUNCH();
     flat_seed_count_kernel<<<nbc, FL_SCAN_THREADS, 0, st>>>(n, w.parent, w.edges, minlow, w.q0);
     OFL_CHECK_LAUNCH();
@@ -956,7 +969,7 @@ int launch_resolve_flats(const float* dem, const uint8_t* fdr, int64_t rows, int
       OFL_CUDA(cudaMemsetAsync(flat_mask, 0, (size_t)n * sizeof(int), st));
       return OFL_OK;
     }
-    flat_spread_label_kernel<<<nb, FL_THREADS, 0, st>>>(n, w.parent, minlow, seedlabel, labels, fdr, w.open);
+    flat_spread_label_kernel<<<nb, FL_THREADS, 0, st>>>(n, w.parent, minlow, seedlabel, labels, fdr, w.open, w.cnt);
     OFL_CHECK_LAUNCH();
     OFL_CUDA(cudaMemsetAsync(flat_mask, 0, (size_t)n * sizeof(int), st));
     OFL_CUDA(cudaMemsetAsync(flat_height, 0, ((size_t)n_labels + 1) * sizeof(int), st));
@@ -986,7 +999,7 @@ int launch_flat_gradient(const int* labels, const uint8_t* fdr, int64_t rows, in
   int rc = check_shape(rows, cols);
   if (rc != OFL_OK) return rc;
   const int64_t n = rows * cols;
-  OFL_REQUIRE(n_seeds >= 0 && n_seeds <= n && n_heights >= 0 && n_heights <= n, OFL_ERR_INVALID,
+  OFL_REQUIRE(n_seeds >= 0 && n_seeds <= n && n_seeds < (1ll << 32) && n_heights >= 0 && n_heights <= n, OFL_ERR_INVALID,
               "seed / flat_height count out of range");
   FlatsWork w;
   rc = carve(workspace, workspace_bytes, rows, cols, &w);
@@ -997,13 +1010,13 @@ int launch_flat_gradient(const int* labels, const uint8_t* fdr, int64_t rows, in
   OFL_CUDA(cudaMemcpyAsync(w.cnt + CNT_SEEDS, &ns, sizeof(unsigned), cudaMemcpyHostToDevice, st));
   OFL_CUDA(cudaStreamSynchronize(st));  // `ns` is a stack variable
   if (n_seeds) OFL_CUDA(cudaMemcpyAsync(w.q1, seeds, (size_t)n_seeds * sizeof(int), cudaMemcpyDeviceToDevice, st));
-  int* acc = w.parent;  // the sweep's own maxima; merged below so untouched labels keep the caller's value
+  int* acc = reinterpret_cast<int*>(w.parent);  // the sweep's own maxima; merged below so untouched labels keep the caller's value
   OFL_CUDA(cudaMemsetAsync(acc, 0, (size_t)n * sizeof(int), st));
   rc = run_gradient((int)rows, (int)cols, labels, fdr, towards ? SWEEP_TOWARDS_NEGATED : SWEEP_AWAY, false, flat_mask,
                     flat_height, acc, w, nullptr, st);
   if (rc != OFL_OK) return rc;
   if (!towards && n_heights) {
-    flat_height_merge_kernel<<<blocks_for(n_heights, FL_THREADS), FL_THREADS, 0, st>>>((int)n_heights, acc, flat_height);
+    flat_height_merge_kernel<<<blocks_for(n_heights, FL_THREADS), FL_THREADS, 0, st>>>(n_heights, acc, flat_height);
     OFL_CHECK_LAUNCH();
   }
   return OFL_OK;

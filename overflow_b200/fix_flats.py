@@ -17,7 +17,7 @@ import numpy as np
 from . import _native
 from .constants import FLOW_DIRECTION_UNDEFINED
 
-_MAX_CELLS = 2**31 - 1
+_MAX_CELLS = 2**32
 
 
 def _dem_f32(dem) -> np.ndarray:
@@ -63,7 +63,7 @@ def _i32(a, what, like) -> np.ndarray:
 
 def _check_size(shape):
     if shape[0] * shape[1] > _MAX_CELLS:
-        raise ValueError("flat resolution works on one tile of fewer than 2**31 cells")
+        raise ValueError("flat resolution works on one tile of at most 2**32 cells")
 
 
 def flat_edges(dem: np.ndarray, fdr: np.ndarray):

@@ -256,3 +256,41 @@ def test_rejects_inexact_dtypes_and_sizes():
     assert fm.shape == (2, 2) and lb.dtype == np.int32
     fm, lb = ff().resolve_flats(np.zeros((0, 5), dtype=np.float32), np.zeros((0, 5), dtype=np.uint8))
     assert fm.shape == (0, 5)
+
+
+def test_tile_of_more_than_2_31_cells():
+    """Cell indices are unsigned 32-bit on the device: a 532 480 x 4096 raster (2.18e9 cells) made of 1040 copies
+    of one 512-row terraced block whose first and last rows are NODATA (inert for every step of the algorithm), so
+    each copy must come out like the block on its own, with its labels shifted by the labels of the copies above."""
+    import torch
+
+    from overflow_b200 import device as dev
+
+    h, cols, reps = 512, 4096, 1040
+    free, _ = torch.cuda.mem_get_info()
+    if free < 90 * 2**30:
+        pytest.skip("needs 90 GB of device memory")
+    block = np.full((h, cols), synth.NODATA, dtype=np.float32)
+    block[1:-1] = synth.terraced(h - 2, cols, seed=21, relief=30.0, nodata_frac=0.01)
+    fdr_b = oracle.flow_direction_for_tile(synth.pad_nodata(block), synth.NODATA)[1:-1, 1:-1].copy()
+    want_mask, want_labels = oracle.resolve_flats(block, fdr_b)
+    want_fixed = oracle.d8_masked_flow_dirs(want_mask, fdr_b, want_labels)
+    n_lab = int(want_labels.max())
+    assert n_lab > 100 and int(want_mask.max()) > 10
+
+    dem = torch.from_numpy(block).cuda().repeat(reps, 1)
+    assert dem.numel() > 2**31
+    fdr = torch.from_numpy(fdr_b).cuda().repeat(reps, 1)
+    flat_mask = torch.empty((h * reps, cols), dtype=torch.int32, device="cuda")
+    labels = torch.empty((h * reps, cols), dtype=torch.int32, device="cuda")
+    fdr, info = dev.fix_flats(dem, fdr, flat_mask=flat_mask, labels=labels)
+    del dem
+    assert info[2] == n_lab * reps
+    assert bool((fdr.view(reps, h, cols) == torch.from_numpy(want_fixed).cuda()[None]).all())
+    assert bool((flat_mask.view(reps, h, cols) == torch.from_numpy(want_mask).cuda()[None]).all())
+    del flat_mask, fdr
+    wl = torch.from_numpy(want_labels.astype(np.int32)).cuda()
+    for k0 in range(0, reps, 130):  # in slices: the shifted comparison needs a temporary per slice
+        got = labels.view(reps, h, cols)[k0 : k0 + 130]
+        shift = (torch.arange(k0, k0 + got.shape[0], device="cuda", dtype=torch.int32) * n_lab)[:, None, None]
+        assert bool((got == torch.where(wl[None] > 0, wl[None] + shift, 0)).all())
