@@ -359,7 +359,7 @@ flat_prepare_kernel(int64_t n, int mode, int* flat_mask, const int* __restrict__
 // D(seed) = 1, which any relaxation order reaches.  The level-synchronous form of round 1 paid one kernel launch
 // (13-27 us, a chain of dependent loads) per level, hundreds of levels per sweep.  Here the unit of scheduling is a
 // tile of FT x FT cells: a CTA loads the tile's D and candidate words with a one-cell ring into shared memory,
-// relaxes it to its own fixpoint with a frontier queue in shared memory (a level costs two CTA barriers, not a
+// relaxes it to its own fixpoint with a frontier queue in shared memory (a level costs one CTA barrier, not a
 // launch), writes the cells that improved back, and queues the neighbouring tiles whose ring it changed for the next
 // pass.  One persistent kernel runs the passes with a grid barrier in between, so a sweep needs about
 // (flat diameter / FT) passes and no host round trip.  A tile writes its own cells only; a ring read that is stale
