@@ -111,6 +111,123 @@ flat_edges_kernel(const float* __restrict__ dem, const uint8_t* __restrict__ fdr
   }
 }
 
+// The same for rasters whose width is a multiple of 32 (dense, so every row starts 16-byte aligned): a thread owns
+// four adjacent cells of one row -- three float4 + six scalar elevation loads and three word + six byte code loads
+// instead of 72 scalar ones -- and the neighbours' tests share their column work: "some neighbour without NODATA is
+// higher" is one maximum over per-column maxima, "some neighbour without a direction is equally high" compares against
+// values that are NaN wherever the neighbour has a direction.  A warp covers 128 consecutive cells of a row; the
+// forest starts with every run hanging off its first cell as far as those 128 cells go (runs continue across the
+// 128-cell seams through flat_merge_kernel's hand-over at every 32nd cell, which includes the seams).
+__global__ void __launch_bounds__(FL_THREADS)
+flat_edges4_kernel(const float* __restrict__ dem, const uint8_t* __restrict__ fdr, int rows, int cols, uint8_t* edges,
+                   unsigned* parent, unsigned* minlow, unsigned* cnt) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int r = blockIdx.y * (FL_THREADS / 32) + w;
+  const int c = (blockIdx.x * 32 + lane) * 4;
+  const bool inside = r < rows && c < cols;  // cols % 4 == 0: the four cells are inside together
+  unsigned flags = 0, eq = 0;                // eq bit j: cell c + j continues the run of the cell to its left
+  if (inside) {
+    float v[3][6];
+    unsigned f[3][6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int rr = r + k - 1;
+      if (rr < 0 || rr >= rows) {
+#pragma unroll
+        for (int x = 0; x < 6; ++x) {
+          v[k][x] = 0.f;
+          f[k][x] = FL_NODATA;  // fails both tests below, like a cell that is not there
+        }
+      } else {
+        const size_t o = (size_t)rr * (size_t)cols + (size_t)c;
+        const float4 m = *reinterpret_cast<const float4*>(dem + o);
+        const unsigned fw = *reinterpret_cast<const unsigned*>(fdr + o);
+        v[k][1] = m.x;
+        v[k][2] = m.y;
+        v[k][3] = m.z;
+        v[k][4] = m.w;
+        f[k][1] = fw & 0xFFu;
+        f[k][2] = (fw >> 8) & 0xFFu;
+        f[k][3] = (fw >> 16) & 0xFFu;
+        f[k][4] = fw >> 24;
+        v[k][0] = c > 0 ? dem[o - 1] : 0.f;
+        f[k][0] = c > 0 ? fdr[o - 1] : (unsigned)FL_NODATA;
+        v[k][5] = c + 4 < cols ? dem[o + 4] : 0.f;
+        f[k][5] = c + 4 < cols ? fdr[o + 4] : (unsigned)FL_NODATA;
+      }
+    }
+    // hi[k][x]: the elevation where a higher neighbour counts (not NODATA), else -inf; per column the maximum of the
+    // rows above and below (m02) and of all three (m3).  fmaxf skips NaN like "z < NaN" is false.
+    float m02[6], m3[6];
+#pragma unroll
+    for (int x = 0; x < 6; ++x) {
+      const float a = f[0][x] != (unsigned)FL_NODATA ? v[0][x] : -CUDART_INF_F;
+      const float b = f[1][x] != (unsigned)FL_NODATA ? v[1][x] : -CUDART_INF_F;
+      const float d = f[2][x] != (unsigned)FL_NODATA ? v[2][x] : -CUDART_INF_F;
+      m02[x] = fmaxf(a, d);
+      m3[x] = fmaxf(m02[x], b);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float z = v[1][j + 1];
+      unsigned flag = 0;
+      if (f[1][j + 1] != (unsigned)FL_UNDEF) {
+        bool low = false;  // :45-53: an equally high neighbour without a direction
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int x = j; x <= j + 2; ++x)
+            if (!(k == 1 && x == j + 1)) low |= f[k][x] == (unsigned)FL_UNDEF && v[k][x] == z;
+        flag = low ? 1u : 0u;
+      } else {
+        flag = fmaxf(fmaxf(m3[j], m3[j + 2]), m02[j + 1]) > z ? 2u : 0u;  // :41-43, :54-60
+      }
+      flags |= flag << (8 * j);
+      if (v[1][j] == z && c + j > 0) eq |= 1u << j;
+    }
+    *reinterpret_cast<unsigned*>(edges + (size_t)r * (size_t)cols + (size_t)c) = flags;
+  }
+  if (parent) {
+    // run starts: a lane's last cell that does not continue a run (or none); a cell with no start at or before it in
+    // its own lane hangs off the start of the nearest lane to the left that has one (lane 0's first cell is one)
+    const int last_start = eq == 0xFu ? (lane == 0 ? 0 : -1) : 31 - __clz((~eq & 0xFu) | (lane == 0 ? 1u : 0u));
+    const unsigned has = __ballot_sync(0xffffffffu, last_start >= 0);
+    const unsigned left = has & ((1u << lane) - 1u);
+    const int src = left ? 31 - __clz(left) : 0;
+    const int src_start = __shfl_sync(0xffffffffu, last_start, src);
+    if (inside) {
+      const unsigned base = (unsigned)r * (unsigned)cols + (unsigned)(c - 4 * lane);  // first cell of the warp's span
+      unsigned from_left = base + 4u * (unsigned)src + (unsigned)src_start;
+      if (lane == 0) from_left = base;
+      unsigned p4[4];
+      unsigned run = from_left;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!((eq >> j) & 1u) || (lane == 0 && j == 0)) run = base + 4u * (unsigned)lane + (unsigned)j;
+        p4[j] = run;
+      }
+      const size_t i = (size_t)r * (size_t)cols + (size_t)c;
+      *reinterpret_cast<uint4*>(parent + i) = make_uint4(p4[0], p4[1], p4[2], p4[3]);
+      *reinterpret_cast<uint4*>(minlow + i) = make_uint4(FL_NONE, FL_NONE, FL_NONE, FL_NONE);
+    }
+  }
+  // one pair of counter atomics per CTA (1024 cells): every CTA of the raster adds to the same two words
+  __shared__ unsigned s_lo, s_hi;
+  if (threadIdx.x == 0) s_lo = s_hi = 0;
+  __syncthreads();
+  const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)__popc(flags & 0x01010101u));
+  const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)__popc(flags & 0x02020202u));
+  if (lane == 0) {
+    if (lo) atomicAdd(&s_lo, lo);
+    if (hi) atomicAdd(&s_hi, hi);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_lo) atomicAdd(&cnt[CNT_LOW], s_lo);
+    if (s_hi) atomicAdd(&cnt[CNT_HIGH], s_hi);
+  }
+}
+
 // ---------------------------------------------------------------- equal-elevation components
 __device__ __forceinline__ unsigned uf_find(unsigned* p, unsigned i) {
   unsigned cur = __ldcg(p + i);
@@ -169,6 +286,56 @@ flat_merge_kernel(const float* __restrict__ dem, int rows, int cols, unsigned* p
     } else {
       if (c > 0 && !left_eq && dem[j - 1] == z) uf_unite(parent, i, j - 1u);
       if (c + 1 < cols && !right_eq && dem[j + 1] == z) uf_unite(parent, i, j + 1u);
+    }
+  }
+}
+
+// The same unions, four adjacent cells of a row per thread (width a multiple of 32): two float4 + four scalar loads
+// instead of up to six per cell, and a sixteenth of the CTAs.  The hand-over inside a row stays at every 32nd cell,
+// which covers both forest initialisations (32-cell groups, 128-cell spans).
+__global__ void __launch_bounds__(FL_THREADS)
+flat_merge4_kernel(const float* __restrict__ dem, int rows, int cols, unsigned* parent) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int r = blockIdx.y * (FL_THREADS / 32) + w;
+  const int c = (blockIdx.x * 32 + lane) * 4;
+  if (r >= rows || c >= cols) return;
+  const size_t o = (size_t)r * (size_t)cols + (size_t)c;
+  const float none = __int_as_float(0x7fc00000);  // NaN: equals nothing, like a cell that is not there
+  float a[6], b[6];
+  {
+    const float4 m = *reinterpret_cast<const float4*>(dem + o);
+    a[0] = c > 0 ? dem[o - 1] : none;
+    a[1] = m.x;
+    a[2] = m.y;
+    a[3] = m.z;
+    a[4] = m.w;
+    a[5] = c + 4 < cols ? dem[o + 4] : none;
+  }
+  const bool below = r + 1 < rows;
+  if (below) {
+    const size_t o1 = o + (size_t)cols;
+    const float4 m = *reinterpret_cast<const float4*>(dem + o1);
+    b[0] = c > 0 ? dem[o1 - 1] : none;
+    b[1] = m.x;
+    b[2] = m.y;
+    b[3] = m.z;
+    b[4] = m.w;
+    b[5] = c + 4 < cols ? dem[o1 + 4] : none;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float z = a[j + 1];
+    const unsigned i = (unsigned)o + (unsigned)j;
+    const bool left_eq = a[j] == z, right_eq = a[j + 2] == z;
+    if (right_eq && ((c + j) & 31) == 31) uf_unite(parent, i, i + 1u);
+    if (below) {
+      const unsigned jn = i + (unsigned)cols;
+      if (b[j + 1] == z) {
+        if (!left_eq || !(b[j] == z)) uf_unite(parent, i, jn);
+      } else {
+        if (!left_eq && b[j] == z) uf_unite(parent, i, jn - 1u);
+        if (!right_eq && b[j + 2] == z) uf_unite(parent, i, jn + 1u);
+      }
     }
   }
 }
@@ -779,7 +946,94 @@ flat_masked_dirs_kernel(const int* __restrict__ flat_mask, const int* __restrict
       fdr[i0 + k] = (uint8_t)masked_dir_of(i0 + k, flat_mask, labels, rows, cols);
 }
 
+// The same with the sixteen neighbour values of a cell shared between the four cells of a thread (width a multiple
+// of 4, 16-byte aligned rasters): the kernel waits on its loads, and these are three int4 + six scalar loads per raster
+// for four cells instead of sixteen scalar loads per cell.  Threads whose four cells all have a direction load nothing.
+__global__ void __launch_bounds__(FL_THREADS)
+flat_masked_dirs4_kernel(const int* __restrict__ flat_mask, const int* __restrict__ labels, uint8_t* fdr, int rows, int cols) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int r = blockIdx.y * (FL_THREADS / 32) + w;
+  const int c = (blockIdx.x * 32 + lane) * 4;
+  if (r >= rows || c >= cols) return;
+  const size_t o = (size_t)r * (size_t)cols + (size_t)c;
+  unsigned codes = *reinterpret_cast<const unsigned*>(fdr + o);
+  // bytes equal to FL_UNDEF (8): x ^ 0x08 == 0
+  const unsigned x8 = codes ^ 0x08080808u;
+  const unsigned undef = ~(((x8 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x8) & 0x80808080u;
+  if (!undef) return;
+  int fm[3][6], lb[3][6];
+  bool row_ok[3];
+  const bool left_ok = c > 0, right_ok = c + 4 < cols;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int rr = r + k - 1;
+    row_ok[k] = rr >= 0 && rr < rows;
+    if (!row_ok[k]) {
+#pragma unroll
+      for (int x = 0; x < 6; ++x) fm[k][x] = lb[k][x] = 0;
+    } else {
+      const size_t ok = (size_t)rr * (size_t)cols + (size_t)c;
+      const int4 m = *reinterpret_cast<const int4*>(flat_mask + ok);
+      const int4 l = *reinterpret_cast<const int4*>(labels + ok);
+      fm[k][1] = m.x, fm[k][2] = m.y, fm[k][3] = m.z, fm[k][4] = m.w;
+      lb[k][1] = l.x, lb[k][2] = l.y, lb[k][3] = l.z, lb[k][4] = l.w;
+      fm[k][0] = left_ok ? flat_mask[ok - 1] : 0;
+      lb[k][0] = left_ok ? labels[ok - 1] : 0;
+      fm[k][5] = right_ok ? flat_mask[ok + 4] : 0;
+      lb[k][5] = right_ok ? labels[ok + 4] : 0;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (!((undef >> (8 * j + 7)) & 1u)) continue;
+    const int lab = lb[1][j + 1];
+    const double f0 = (double)fm[1][j + 1];
+    int nmin = FL_UNDEF;
+    double min_slope = CUDART_INF;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {  // E NE N NW W SW S SE
+      const int dy = (k >= 1 && k <= 3) ? -1 : (k >= 5 ? 1 : 0);
+      const int dx = (k == 0 || k == 1 || k == 7) ? 1 : ((k >= 3 && k <= 5) ? -1 : 0);
+      const int x = j + 1 + dx;
+      if (!row_ok[1 + dy] || (x == 0 && !left_ok) || (x == 5 && !right_ok)) continue;  // off the raster
+      if (lb[1 + dy][x] != lab) continue;
+      const double dz = (double)fm[1 + dy][x] - f0;
+      const double slope = (k & 1) ? __ddiv_rn(dz, 1.4142135623730951) : dz;
+      if (slope < min_slope) {
+        min_slope = slope;
+        nmin = k;
+      }
+    }
+    codes = (codes & ~(0xFFu << (8 * j))) | ((unsigned)nmin << (8 * j));
+  }
+  *reinterpret_cast<unsigned*>(fdr + o) = codes;
+}
+
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// the row-wise kernels (a warp = 128 consecutive cells of a row, a CTA = eight rows): usable when the width is a
+// multiple of `mult` and the row count fits gridDim.y
+bool rows_vector_ok(int64_t rows, int64_t cols, int mult) {
+  return cols % mult == 0 && (rows + FL_THREADS / 32 - 1) / (FL_THREADS / 32) <= 65535 && !getenv("OFL_FLATS_SCALAR");
+}
+dim3 rows_grid(int64_t rows, int64_t cols) {
+  return dim3((unsigned)((cols / 4 + 31) / 32), (unsigned)((rows + FL_THREADS / 32 - 1) / (FL_THREADS / 32)));
+}
+
+// flat_edges over the raster: the four-cells-per-thread form where the layout allows it
+int launch_edges_kernel(const float* dem, const uint8_t* fdr, int64_t rows, int64_t cols, uint8_t* edges, unsigned* parent,
+                        unsigned* minlow, unsigned* cnt, cudaStream_t st) {
+  const bool vec = rows_vector_ok(rows, cols, 32) && (reinterpret_cast<uintptr_t>(dem) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(fdr) & 3) == 0 && (reinterpret_cast<uintptr_t>(edges) & 3) == 0;
+  if (vec) {
+    flat_edges4_kernel<<<rows_grid(rows, cols), FL_THREADS, 0, st>>>(dem, fdr, (int)rows, (int)cols, edges, parent, minlow, cnt);
+  } else {
+    flat_edges_kernel<<<blocks_for(rows * cols, FL_THREADS), FL_THREADS, 0, st>>>(dem, fdr, (int)rows, (int)cols, edges, parent,
+                                                                               minlow, cnt);
+  }
+  OFL_CHECK_LAUNCH();
+  return OFL_OK;
+}
 
 struct FlatsWork {
   unsigned* parent;  // union-find forest, later flat_height
@@ -907,9 +1161,8 @@ int launch_flat_edges(const float* dem, const uint8_t* fdr, int64_t rows, int64_
   const int64_t n = rows * cols;
   PhaseScope ps(PHASE_FLATS, st);
   OFL_CUDA(cudaMemsetAsync(cnt_dev, 0, CNT_SLOTS * sizeof(unsigned), st));
-  flat_edges_kernel<<<blocks_for(n, FL_THREADS), FL_THREADS, 0, st>>>(dem, fdr, (int)rows, (int)cols, edges, nullptr,
-                                                                      nullptr, cnt_dev);
-  OFL_CHECK_LAUNCH();
+  rc = launch_edges_kernel(dem, fdr, rows, cols, edges, nullptr, nullptr, cnt_dev, st);
+  if (rc != OFL_OK) return rc;
   unsigned* h = nullptr;
   rc = pinned_get(256, reinterpret_cast<void**>(&h));
   if (rc != OFL_OK) return rc;
@@ -941,9 +1194,12 @@ int launch_resolve_flats(const float* dem, const uint8_t* fdr, int64_t rows, int
   int64_t lv_away = 0, lv_low = 0;
   {
     PhaseScope ps(PHASE_FLATS_LABEL, st);
-    flat_edges_kernel<<<nb, FL_THREADS, 0, st>>>(dem, fdr, (int)rows, (int)cols, w.edges, w.parent, minlow, w.cnt);
-    OFL_CHECK_LAUNCH();
-    flat_merge_kernel<<<nb, FL_THREADS, 0, st>>>(dem, (int)rows, (int)cols, w.parent);
+    rc = launch_edges_kernel(dem, fdr, rows, cols, w.edges, w.parent, minlow, w.cnt, st);
+    if (rc != OFL_OK) return rc;
+    if (rows_vector_ok(rows, cols, 32) && (reinterpret_cast<uintptr_t>(dem) & 15) == 0)
+      flat_merge4_kernel<<<rows_grid(rows, cols), FL_THREADS, 0, st>>>(dem, (int)rows, (int)cols, w.parent);
+    else
+      flat_merge_kernel<<<nb, FL_THREADS, 0, st>>>(dem, (int)rows, (int)cols, w.parent);
     OFL_CHECK_LAUNCH();
     flat_lowroot_kernel<<<nbc, FL_SCAN_THREADS, 0, st>>>(n, w.parent, w.edges, minlow, w.cnt);
     OFL_CHECK_LAUNCH();
@@ -1028,8 +1284,12 @@ int launch_masked_flow_dirs(const int* flat_mask, const int* labels, uint8_t* fd
   if (rc != OFL_OK) return rc;
   PhaseScope ps(PHASE_FLATS, st);
   const int aligned = (reinterpret_cast<uintptr_t>(fdr) & 3u) == 0;
-  flat_masked_dirs_kernel<<<blocks_for((rows * cols + 3) / 4, FL_THREADS), FL_THREADS, 0, st>>>(flat_mask, labels, fdr,
-                                                                                                  (int)rows, (int)cols, aligned);
+  if (rows_vector_ok(rows, cols, 4) && aligned && (reinterpret_cast<uintptr_t>(flat_mask) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(labels) & 15) == 0)
+    flat_masked_dirs4_kernel<<<rows_grid(rows, cols), FL_THREADS, 0, st>>>(flat_mask, labels, fdr, (int)rows, (int)cols);
+  else
+    flat_masked_dirs_kernel<<<blocks_for((rows * cols + 3) / 4, FL_THREADS), FL_THREADS, 0, st>>>(flat_mask, labels, fdr,
+                                                                                                    (int)rows, (int)cols, aligned);
   OFL_CHECK_LAUNCH();
   return OFL_OK;
 }

@@ -168,6 +168,41 @@ def _cases():
     yield "winding_flat", maze
 
 
+def _cases_vector_path():
+    """Widths that are multiples of 32 take the four-cells-per-thread edge stencil (flat_edges4_kernel)."""
+    yield "terraced_257x160", synth.terraced(257, 160, seed=14, relief=12.0, nodata_frac=0.03)
+    rng = np.random.default_rng(5)
+    yield "ints_130x96", rng.integers(0, 3, size=(130, 96)).astype(np.float32)
+    yield "one_span_9x32", rng.integers(0, 2, size=(9, 32)).astype(np.float32)
+    runs = np.zeros((40, 384), dtype=np.float32)  # runs that cross the 128-cell seams of a warp's span, and rows of one run
+    runs[::3, 100:300] = 1.0
+    runs[1::3, :] = 2.0
+    runs[5, 127] = 7.0
+    runs[7, 128] = 7.0
+    yield "runs_across_seams", runs
+    odd = synth.terraced(64, 224, seed=15, relief=6.0)
+    odd[10:14, 30:50] = np.nan
+    odd[20, 60:70] = np.inf
+    odd[22, 60:70] = -np.inf
+    yield "nan_inf_64x224", odd
+
+
+@pytest.mark.parametrize("name,dem", list(_cases_vector_path()), ids=[n for n, _ in _cases_vector_path()])
+def test_vs_oracle_vector_edges(name, dem, monkeypatch):
+    fdr = oracle.flow_direction_for_tile(synth.pad_nodata(dem), synth.NODATA)[1:-1, 1:-1].copy()
+    want_mask, want_labels = oracle.resolve_flats(dem, fdr)
+    assert ff().flat_edges(dem, fdr) == oracle.flat_edges(dem, fdr)
+    want_fixed = oracle.d8_masked_flow_dirs(want_mask, fdr, want_labels)
+    flat_mask, labels = ff().resolve_flats(dem, fdr)
+    assert np.array_equal(labels, want_labels) and np.array_equal(flat_mask, want_mask)
+    assert np.array_equal(ff().fix_flats_for_tile(dem, fdr), want_fixed)
+    monkeypatch.setenv("OFL_FLATS_SCALAR", "1")  # the one-cell-per-thread kernels on the same raster
+    assert ff().flat_edges(dem, fdr) == oracle.flat_edges(dem, fdr)
+    flat_mask, labels = ff().resolve_flats(dem, fdr)
+    assert np.array_equal(labels, want_labels) and np.array_equal(flat_mask, want_mask)
+    assert np.array_equal(ff().fix_flats_for_tile(dem, fdr), want_fixed)
+
+
 @pytest.mark.parametrize("name,dem", list(_cases()), ids=[n for n, _ in _cases()])
 def test_vs_oracle(name, dem):
     fdr = oracle.flow_direction_for_tile(synth.pad_nodata(dem), synth.NODATA)[1:-1, 1:-1].copy()
@@ -231,17 +266,18 @@ def test_routing_through_resolved_flats():
     assert torch.equal(fdr2, d_fdr) and torch.equal(fac2, fac)
 
 
+@pytest.mark.parametrize("cols", [131, 132])  # 132: the four-cells-per-thread kernel (width a multiple of 4)
 @pytest.mark.parametrize("span", [3, 1000, 2**20 - 1, 2**20 + 5, 2**30])
-def test_masked_dirs_value_ranges(span):
+def test_masked_dirs_value_ranges(span, cols):
     """d8_masked_flow_dirs on arbitrary masks, from tiny to int32-wide differences, with near-ties between cardinal
     and diagonal steps planted: the float64 slopes must give the reference's (= the oracle's) choice everywhere."""
     rng = np.random.default_rng(span % 1000)
-    shape = (97, 131)
+    shape = (97, cols)
     flat_mask = rng.integers(-span, span + 1, size=shape).astype(np.int32)
     near = np.round(flat_mask[:, :-1].astype(np.float64) * np.sqrt(2.0))  # near-ties between cardinal and diagonal steps
-    flat_mask[:, 1:] = np.where(rng.random((97, 130)) < 0.3, np.clip(near, -2**31 + 1, 2**31 - 1).astype(np.int64),
+    flat_mask[:, 1:] = np.where(rng.random((97, cols - 1)) < 0.3, np.clip(near, -2**31 + 1, 2**31 - 1).astype(np.int64),
                                 flat_mask[:, 1:]).astype(np.int32)
-    labels = rng.integers(0, 3, size=shape).astype(np.int32)
+    labels = rng.integers(-1, 3, size=shape).astype(np.int32)  # -1: nothing special about it, it only has to match
     fdr = rng.choice(np.array([0, 3, 8, 8, 8, 9], dtype=np.uint8), size=shape)
     want = oracle.d8_masked_flow_dirs(flat_mask, fdr, labels)
     got = fdr.copy()
