@@ -480,6 +480,37 @@ flat_spread_label_kernel(int64_t n, const unsigned* __restrict__ parent, const u
   open[i] = (fdr[i] == FL_UNDEF) ? flat_state(lab) : 0u;
 }
 
+// four cells per thread (cell count a multiple of 4, 16-byte aligned rasters): cells of one run share their parent, so
+// the walk to the root and the two look-ups behind it are done once per run piece, not once per cell
+__global__ void __launch_bounds__(FL_THREADS)
+flat_spread_label4_kernel(int64_t n4, const unsigned* __restrict__ parent, const unsigned* __restrict__ minlow,
+                          const int* __restrict__ seedlabel, int4* labels, const unsigned* __restrict__ fdr4, uint4* open,
+                          const unsigned* __restrict__ cnt) {
+  const int64_t q = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
+  if (q >= n4) return;
+  const uint4 pv = reinterpret_cast<const uint4*>(parent)[q];
+  const unsigned p[4] = {pv.x, pv.y, pv.z, pv.w};
+  const unsigned codes = fdr4[q];
+  int lab[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j > 0 && p[j] == p[j - 1]) {
+      lab[j] = lab[j - 1];
+      continue;
+    }
+    const unsigned self = (unsigned)(4 * q + j);
+    const unsigned root = p[j] == self ? self : uf_find_ro(parent, p[j]);
+    const unsigned m = minlow[root];
+    lab[j] = 0;
+    if (m != FL_NONE || (cnt[CNT_LASTLOW] && cnt[CNT_LASTROOT] == root)) lab[j] = seedlabel[m];
+  }
+  labels[q] = make_int4(lab[0], lab[1], lab[2], lab[3]);
+  unsigned o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = ((codes >> (8 * j)) & 0xFFu) == (unsigned)FL_UNDEF ? flat_state(lab[j]) : 0u;
+  open[q] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // ---------------------------------------------------------------- gradients (away_from_higher / towards_lower)
 // edge cells -> seed list, in no particular order (the sweeps are order-free); one queue atomic per CTA
 __global__ void __launch_bounds__(FL_SCAN_THREADS)
@@ -1035,6 +1066,67 @@ int launch_edges_kernel(const float* dem, const uint8_t* fdr, int64_t rows, int6
   return OFL_OK;
 }
 
+// The same, four cells per thread (cell count a multiple of 4, 16-byte aligned rasters): int4 loads and stores, and
+// quads the sweep never reached cost one load.
+__global__ void __launch_bounds__(FL_THREADS)
+flat_tile_assign4_kernel(int64_t n4, int mode, const int4* __restrict__ D, const uint4* __restrict__ open,
+                         const int* __restrict__ labels, int4* flat_mask, const int* fh_read, int* fh_acc, unsigned* cnt) {
+  const int64_t q = (int64_t)blockIdx.x * FL_THREADS + threadIdx.x;
+  int top = 0, key = 0, kmax = 0;  // key / kmax: the label of the thread's last valued cell and the largest level seen for it
+  if (q < n4) {
+    const int4 dv = D[q];
+    int d[4] = {dv.x, dv.y, dv.z, dv.w};
+    if (d[0] < FL_INF || d[1] < FL_INF || d[2] < FL_INF || d[3] < FL_INF) {
+      const uint4 ov = open[q];
+      const unsigned o[4] = {ov.x, ov.y, ov.z, ov.w};
+      int4 mv = make_int4(0, 0, 0, 0);
+      if (mode != SWEEP_AWAY) mv = flat_mask[q];
+      int m[4] = {mv.x, mv.y, mv.z, mv.w};
+      bool any = false;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (d[j] >= FL_INF) continue;
+        any = true;
+        const int lab = o[j] ? (int)(o[j] >> 2) - 1 : labels[4 * q + j];
+        if (mode == SWEEP_AWAY) {
+          m[j] = d[j];
+          if (lab > 0) {
+            if (lab != key && key > 0 && __ldcg(fh_acc + key - 1) < kmax) atomicMax(fh_acc + key - 1, kmax);
+            kmax = lab == key ? max(kmax, d[j]) : d[j];
+            key = lab;
+          }
+        } else {
+          int away = 0;  // flat_height - (increments away from higher terrain), 0 where the away sweep never came
+          if (lab > 0) {
+            if (mode == SWEEP_TOWARDS_NEGATED && m[j] < 0) away = m[j] + fh_read[lab - 1];
+            if (mode == SWEEP_TOWARDS && m[j] > 0) away = fh_read[lab - 1] - m[j];
+          }
+          m[j] = away + 2 * d[j];
+        }
+        top = max(top, d[j]);
+      }
+      if (any) {
+        if (mode == SWEEP_AWAY) {
+          // cells the sweep did not reach keep their mask: write only the valued ones' lanes of the quad
+          int* out = reinterpret_cast<int*>(flat_mask + q);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (d[j] < FL_INF) out[j] = m[j];
+        } else {
+          flat_mask[q] = make_int4(m[0], m[1], m[2], m[3]);
+        }
+      }
+    }
+  }
+  const int wtop = __reduce_max_sync(0xffffffffu, top);
+  if (wtop == 0) return;  // warp-uniform
+  if ((threadIdx.x & 31) == 0 && __ldcg(cnt + CNT_MAXLEVEL) < (unsigned)wtop) atomicMax(cnt + CNT_MAXLEVEL, (unsigned)wtop);
+  if (mode != SWEEP_AWAY) return;
+  const unsigned grp = __match_any_sync(0xffffffffu, key);
+  const int gm = __reduce_max_sync(grp, kmax);
+  if (key > 0 && (threadIdx.x & 31) == __ffs(grp) - 1 && __ldcg(fh_acc + key - 1) < gm) atomicMax(fh_acc + key - 1, gm);
+}
+
 struct FlatsWork {
   unsigned* parent;  // union-find forest, later flat_height
   int* q0;           // block counts of the label scan, later the sweeps' level per cell
@@ -1119,8 +1211,13 @@ int run_gradient(int rows, int cols, const int* labels, const uint8_t* fdr, int 
     OFL_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(flat_tile_sweep_kernel), dim3((unsigned)sweep_blocks()),
                                          dim3(FS_THREADS), args, 0, st));
   }
-  flat_tile_assign_kernel<<<blocks_for(n, FL_THREADS), FL_THREADS, 0, st>>>(n, mode, a.D, w.open, labels, flat_mask, fh_read,
-                                                                            fh_acc, w.cnt);
+  if (n % 4 == 0 && (reinterpret_cast<uintptr_t>(flat_mask) & 15) == 0 && !getenv("OFL_FLATS_SCALAR"))
+    flat_tile_assign4_kernel<<<blocks_for(n / 4, FL_THREADS), FL_THREADS, 0, st>>>(
+        n / 4, mode, reinterpret_cast<const int4*>(a.D), reinterpret_cast<const uint4*>(w.open), labels,
+        reinterpret_cast<int4*>(flat_mask), fh_read, fh_acc, w.cnt);
+  else
+    flat_tile_assign_kernel<<<blocks_for(n, FL_THREADS), FL_THREADS, 0, st>>>(n, mode, a.D, w.open, labels, flat_mask, fh_read,
+                                                                              fh_acc, w.cnt);
   OFL_CHECK_LAUNCH();
   if (levels_out) {
     unsigned* h_cnt = nullptr;
@@ -1225,7 +1322,13 @@ int launch_resolve_flats(const float* dem, const uint8_t* fdr, int64_t rows, int
       OFL_CUDA(cudaMemsetAsync(flat_mask, 0, (size_t)n * sizeof(int), st));
       return OFL_OK;
     }
-    flat_spread_label_kernel<<<nb, FL_THREADS, 0, st>>>(n, w.parent, minlow, seedlabel, labels, fdr, w.open, w.cnt);
+    if (n % 4 == 0 && (reinterpret_cast<uintptr_t>(labels) & 15) == 0 && (reinterpret_cast<uintptr_t>(fdr) & 3) == 0 &&
+        !getenv("OFL_FLATS_SCALAR"))
+      flat_spread_label4_kernel<<<blocks_for(n / 4, FL_THREADS), FL_THREADS, 0, st>>>(
+          n / 4, w.parent, minlow, seedlabel, reinterpret_cast<int4*>(labels), reinterpret_cast<const unsigned*>(fdr),
+          reinterpret_cast<uint4*>(w.open), w.cnt);
+    else
+      flat_spread_label_kernel<<<nb, FL_THREADS, 0, st>>>(n, w.parent, minlow, seedlabel, labels, fdr, w.open, w.cnt);
     OFL_CHECK_LAUNCH();
     OFL_CUDA(cudaMemsetAsync(flat_mask, 0, (size_t)n * sizeof(int), st));
     OFL_CUDA(cudaMemsetAsync(flat_height, 0, ((size_t)n_labels + 1) * sizeof(int), st));
