@@ -623,6 +623,7 @@ flat_tile_seed_kernel(const unsigned* __restrict__ seeds, const int* __restrict_
 // candidate, so that any neighbour of a tile or ring cell is a valid index and needs no bounds check.
 constexpr int FTS = FT + 4;  // row stride
 constexpr int FT_IMG = FTS * FTS;
+static_assert(FT_IMG < 65536, "queue entries are 16-bit image indices");
 static_assert(FT_QCAP >= FT_CELLS, "the first round queues every valued cell of the tile and its ring");
 
 struct TileSmem {
@@ -630,7 +631,7 @@ struct TileSmem {
   // (label + 1) << 2 | flags.  A cell of the tile: 1 = candidate (may take a value), 2 = improved on this visit.
   // A cell of the ring: 2 = candidate (of its own tile; it never takes a value here).  Guard cells: 0.
   unsigned S[FT_IMG];
-  int q[2][FT_QCAP];
+  uint16_t q[2][FT_QCAP];  // image indices (< 2^16)
   unsigned qn[3];    // round j reads qn[j % 3], fills qn[(j + 1) % 3] and clears qn[(j + 2) % 3]
   unsigned act;      // neighbouring tiles to queue, bit (dty + 1) * 3 + (dtx + 1)
   int overflow, changed;
@@ -671,10 +672,10 @@ __device__ __forceinline__ bool tile_relax(TileSmem& sm, int nidx, int d1, unsig
   return true;
 }
 
-__device__ __forceinline__ void tile_push(TileSmem& sm, int which, int* q, int idx) {
+__device__ __forceinline__ void tile_push(TileSmem& sm, int which, uint16_t* q, int idx) {
   const unsigned at = atomicAdd(&sm.qn[which], 1u);
   if (at < FT_QCAP)
-    q[at] = idx;
+    q[at] = (uint16_t)idx;
   else
     sm.overflow = 1;
 }
@@ -740,8 +741,8 @@ __device__ void tile_process(const SweepArgs& a, TileSmem& sm, int tile, int pas
     if (n == 0 || sm.overflow) break;
     const int next = slot == 2 ? 0 : slot + 1;
     if (threadIdx.x == 0) sm.qn[next == 2 ? 0 : next + 1] = 0;
-    const int* qin = sm.q[rounds & 1];
-    int* qout = sm.q[(rounds & 1) ^ 1];
+    const uint16_t* qin = sm.q[rounds & 1];
+    uint16_t* qout = sm.q[(rounds & 1) ^ 1];
     for (unsigned i0 = (threadIdx.x & ~31u); i0 < n; i0 += FS_THREADS) {  // warp-uniform bounds
       const unsigned i = i0 + (threadIdx.x & 31u);
       unsigned won = 0;
@@ -782,7 +783,7 @@ __device__ void tile_process(const SweepArgs& a, TileSmem& sm, int tile, int pas
       at = __shfl_sync(0xffffffffu, at, 31) + (unsigned)(inc - __popc(won));
       for (; won; won &= won - 1u, ++at) {
         if (at < FT_QCAP)
-          qout[at] = idx + tile_off(__ffs(won) - 1);
+          qout[at] = (uint16_t)(idx + tile_off(__ffs(won) - 1));
         else
           sm.overflow = 1;
       }
@@ -858,7 +859,7 @@ __device__ void tile_process(const SweepArgs& a, TileSmem& sm, int tile, int pas
 
 // The passes of one sweep: cooperative launch, every CTA resident.  Tiles of a pass are drawn from a counter.
 #ifndef OFL_FL_SWEEP_CTAS
-#define OFL_FL_SWEEP_CTAS 10  // 128 threads, 51 registers, 21 KB of shared memory: measured best of 6 / 8 / 10 / 16
+#define OFL_FL_SWEEP_CTAS 14  // 128 threads, 36 registers, 15.5 KB of shared memory (16-bit queue entries): 10 / 12 / 14 / 16 measured
 #endif
 __global__ void __launch_bounds__(FS_THREADS, OFL_FL_SWEEP_CTAS) flat_tile_sweep_kernel(SweepArgs a) {
   __shared__ TileSmem sm;
@@ -882,12 +883,17 @@ __global__ void __launch_bounds__(FS_THREADS, OFL_FL_SWEEP_CTAS) flat_tile_sweep
     __syncthreads();
     const unsigned n_act = sm.n_act;
     if (n_act == 0) break;
+    // thread 0 draws the CTA's next ticket while the current tile is processed (the atomic's round trip is hidden);
+    // the tickets drawn past the end of the list are simply not used
+    unsigned ticket = 0;
+    if (threadIdx.x == 0) ticket = atomicAdd(&a.cnt[CNT_TTAKE0 + pass % 3], 1u);
     for (;;) {
       __syncthreads();
-      if (threadIdx.x == 0) sm.take = atomicAdd(&a.cnt[CNT_TTAKE0 + pass % 3], 1u);
+      if (threadIdx.x == 0) sm.take = ticket;
       __syncthreads();
       const unsigned t = sm.take;
       if (t >= n_act) break;
+      if (threadIdx.x == 0) ticket = atomicAdd(&a.cnt[CNT_TTAKE0 + pass % 3], 1u);
       tile_process(a, sm, __ldcg(a.lists + (size_t)(pass % 3) * a.n_tiles + t), pass);
     }
     grid_barrier(&a.cnt[CNT_BAR], generation);
