@@ -47,6 +47,7 @@ enum {
   CNT_VISITS, CNT_ROUNDS,                 // statistics of the sweep (OFL_FLATS_DEBUG)
   CNT_MAXROUNDS,                          // most rounds in one visit
   CNT_LASTLOW, CNT_LASTROOT,              // cell 2^32 - 1 is a low edge / its root (a raster of exactly 2^32 cells)
+  CNT_CYC_LOAD, CNT_CYC_ROUNDS, CNT_CYC_STORE,  // clock cycles / 64 spent in the three parts of a tile visit (sums)
   CNT_PASSTIME0,                          // start of pass k in ns (low word), 40 slots
   CNT_SLOTS = 64
 };
@@ -692,6 +693,7 @@ __device__ void tile_process(const SweepArgs& a, TileSmem& sm, int tile, int pas
     sm.overflow = 0;
 #endif
   }
+  const long long t0 = clock64();
   // the first visit finds seeds anywhere in the tile; later the tile's own cells are at their fixpoint and
   // only the ring brings news
   const bool first = __ldcg(a.seen + tile) == 0;
@@ -734,6 +736,7 @@ __device__ void tile_process(const SweepArgs& a, TileSmem& sm, int tile, int pas
   }
   // frontier rounds: a lane takes a queued cell and offers its level to the eight neighbours (the flags keep
   // ring and guard cells from taking it); the improved ones are appended warp by warp
+  const long long t1 = clock64();
   int rounds = 0;
   for (int slot = 0;; ++rounds) {
     cta_sync();
@@ -813,6 +816,7 @@ __device__ void tile_process(const SweepArgs& a, TileSmem& sm, int tile, int pas
     }
   }
   cta_sync();
+  const long long t2 = clock64();
   // improved cells go back
   for (int base = 0; base < FT * FT; base += FS_THREADS) {
     const int e = base + (int)threadIdx.x;
@@ -850,6 +854,10 @@ __device__ void tile_process(const SweepArgs& a, TileSmem& sm, int tile, int pas
     atomicAdd(&a.cnt[CNT_VISITS], 1u);
     atomicAdd(&a.cnt[CNT_ROUNDS], (unsigned)rounds);
     if (__ldcg(&a.cnt[CNT_MAXROUNDS]) < (unsigned)rounds) atomicMax(&a.cnt[CNT_MAXROUNDS], (unsigned)rounds);
+    const long long t3 = clock64();
+    atomicAdd(&a.cnt[CNT_CYC_LOAD], (unsigned)((t1 - t0) >> 6));
+    atomicAdd(&a.cnt[CNT_CYC_ROUNDS], (unsigned)((t2 - t1) >> 6));
+    atomicAdd(&a.cnt[CNT_CYC_STORE], (unsigned)((t3 - t2) >> 6));
   }
   if (threadIdx.x < 9 && ((sm.act >> threadIdx.x) & 1u)) {
     const int nty = ty + (int)threadIdx.x / 3 - 1, ntx = tx + (int)threadIdx.x % 3 - 1;
@@ -1239,7 +1247,11 @@ int run_gradient(int rows, int cols, const int* labels, const uint8_t* fdr, int 
       fprintf(stderr, "  most rounds in a visit %u; pass durations (us):", h_cnt[CNT_MAXROUNDS - CNT_PASSES]);
       for (unsigned k = 0; k + 1 <= h_cnt[0] && k + 1 < 40; ++k)
         fprintf(stderr, " %.0f", (h_cnt[CNT_PASSTIME0 - CNT_PASSES + k + 1] - h_cnt[CNT_PASSTIME0 - CNT_PASSES + k]) * 1e-3);
-      fprintf(stderr, "\n");
+      fprintf(stderr, "\n  cycles per visit: load %.0f, rounds %.0f (%.0f per round), store + wake %.0f\n",
+              64.0 * h_cnt[CNT_CYC_LOAD - CNT_PASSES] / h_cnt[CNT_VISITS - CNT_PASSES],
+              64.0 * h_cnt[CNT_CYC_ROUNDS - CNT_PASSES] / h_cnt[CNT_VISITS - CNT_PASSES],
+              64.0 * h_cnt[CNT_CYC_ROUNDS - CNT_PASSES] / (h_cnt[CNT_ROUNDS - CNT_PASSES] + h_cnt[CNT_VISITS - CNT_PASSES]),
+              64.0 * h_cnt[CNT_CYC_STORE - CNT_PASSES] / h_cnt[CNT_VISITS - CNT_PASSES]);
     }
   }
   return OFL_OK;
