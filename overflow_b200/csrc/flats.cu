@@ -1273,7 +1273,6 @@ int launch_flat_edges(const float* dem, const uint8_t* fdr, int64_t rows, int64_
                       int64_t* n_high, unsigned* cnt_dev, cudaStream_t st) {
   int rc = check_shape(rows, cols);
   if (rc != OFL_OK) return rc;
-  const int64_t n = rows * cols;
   PhaseScope ps(PHASE_FLATS, st);
   OFL_CUDA(cudaMemsetAsync(cnt_dev, 0, CNT_SLOTS * sizeof(unsigned), st));
   rc = launch_edges_kernel(dem, fdr, rows, cols, edges, nullptr, nullptr, cnt_dev, st);
