@@ -167,6 +167,8 @@ class StripPipeline:
         self.rec = self.rec_all[rank]
         self.J_all = e.empty((world, 2, c), torch.int64)
         self.flags = e.empty((4,), torch.int32)
+        self._side = None  # side stream + event of the DEM halo exchange (CUDA only, created on first use)
+        self._step_start = None
         self.fac_edge = e.empty((2, c), torch.int64)  # the neighbours' boundary counts (recurrence check only)
         self.fdr_halo.zero_()
         self.rec_all.zero_()
@@ -247,10 +249,25 @@ class StripPipeline:
         if self.world > 1:
             # the DEM halo rows travel while the stencil works on the rows that do not need them
             d = self.dem_halo
-            reqs = self._exchange_start(d[1], d[-2], d[0], d[-1])
-            self.direction(1, self.h - 1)
-            for req in reqs:
-                req.wait()
+            if d.is_cuda:
+                # The stencil is launched FIRST, so the device starts at once; the exchange is set up afterwards on a
+                # side stream (NCCL orders itself behind the stream that is current), which waits for everything
+                # enqueued before this step -- the last readers of the halo rows -- but not for the stencil.
+                main = torch.cuda.current_stream(d.device)
+                if self._side is None:
+                    self._side = torch.cuda.Stream(d.device)
+                    self._step_start = torch.cuda.Event()
+                self._step_start.record(main)
+                self.direction(1, self.h - 1)
+                self._side.wait_event(self._step_start)
+                with torch.cuda.stream(self._side):
+                    self._exchange(d[1], d[-2], d[0], d[-1])
+                main.wait_stream(self._side)
+            else:
+                reqs = self._exchange_start(d[1], d[-2], d[0], d[-1])
+                self.direction(1, self.h - 1)
+                for req in reqs:
+                    req.wait()
             self.direction(0, 1)
             self.direction(self.h - 1, self.h)
             self._exchange_halo(self.fdr_halo)
