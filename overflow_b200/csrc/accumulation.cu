@@ -190,7 +190,8 @@ constexpr int QMAX = AT * AT;
 constexpr uint32_t W_CNT_ONE = 1u << 8;
 constexpr uint32_t W_LIVE = 1u << 26;
 constexpr uint32_t W_MISS_ONE = 1u << 27;
-constexpr uint32_t W_COUNT_MASK = 0x3FFFFu << 8;
+constexpr uint32_t W_COUNT_MASK = 0xFFFu << 8;   // tile-local counts without the cell itself: <= 4095
+constexpr uint32_t W_CODE_SHIFT = 20;            // bits 20..23: the cell's direction code, carried to the final pass
 constexpr uint32_t W_HANDOFF_SELF = W_CNT_ONE - W_MISS_ONE;
 constexpr uint32_t W_UNFINISHED_TAB = 0xAAAAAAA8u;  // bit q = (missing << 1 | live) set: live with missing != 0  // a hand-off adds (word & W_COUNT_MASK) + this: the cell itself, one upstream less
 constexpr uint32_t W_READY_MASK = (0xFu << 27) | W_LIVE;     // hand-off result: the downstream cell is a live cell ...
@@ -434,8 +435,12 @@ __global__ void __launch_bounds__(ACC_THREADS, OFL_ACC_MIN_CTAS) acc_tile_kernel
     const uint32_t nib = C1 | (C1 >> 4);
     const uint32_t off4 = prmt(W_TAB_LO, W_TAB_HI, prmt(nib, 0u, 0x4420u));
     const uint32_t hi4 = (cnt4 << 3) | ((~dead >> 5) & 0x04040404u);
-    sts128(aw_lane + i * (2 * WP * 4), prmt(off4, hi4, 0x4CC0u), prmt(off4, hi4, 0x5DD1u), prmt(off4, hi4, 0x6EE2u),
-           prmt(off4, hi4, 0x7FF3u));
+    // bytes 2 of the words: the code in the upper nibble (the count's lower 12 bits end below it and never carry:
+    // every cell hands down once, so no word -- not even a NODATA cell's, which absorbs hand-offs -- sums past 4095)
+    const uint32_t mid4 = (C1 << 4) & 0xF0F0F0F0u;
+    const uint32_t hmA = prmt(mid4, hi4, 0x5140u), hmB = prmt(mid4, hi4, 0x7362u);  // [mid0 hi0 mid1 hi1], [mid2 hi2 mid3 hi3]
+    sts128(aw_lane + i * (2 * WP * 4), prmt(off4, hmA, 0x54D0u), prmt(off4, hmA, 0x76F1u), prmt(off4, hmB, 0x54D2u),
+           prmt(off4, hmB, 0x76F3u));
   }
   __syncthreads();  // every word is built; the code tile is dead from here and the queue takes its place
 
@@ -650,7 +655,7 @@ __global__ void __launch_bounds__(ACC_THREADS, OFL_ACC_MIN_CTAS) acc_tile_kernel
   }
   __syncthreads();  // all chains are finished: counts are final
 
-  if (own_target >= 0) atomicAdd(&p.S[own_target], (unsigned long long)(((lds32(a_own) >> 8) & 0x3FFFFu) + 1u));
+  if (own_target >= 0) atomicAdd(&p.S[own_target], (unsigned long long)(((lds32(a_own) >> 8) & 0xFFFu) + 1u));
   // tile-local counts (<= 4096, fit 16 bits) for the final pass: tile-major, a warp stores 256 contiguous bytes
   uint2* Lt = reinterpret_cast<uint2*>(p.L + (size_t)tile * (AT * AT));
   uint32_t unfinished = 0;
@@ -662,8 +667,8 @@ __global__ void __launch_bounds__(ACC_THREADS, OFL_ACC_MIN_CTAS) acc_tile_kernel
                   __funnelshift_r(W_UNFINISHED_TAB, W_UNFINISHED_TAB, v.y >> 26);
     unfinished |= __funnelshift_r(W_UNFINISHED_TAB, W_UNFINISHED_TAB, v.z >> 26) |
                   __funnelshift_r(W_UNFINISHED_TAB, W_UNFINISHED_TAB, v.w >> 26);
-    // tile-local count = running sum + the cell itself (no carry between the halves: sums stay below 2^16)
-    Lt[g] = make_uint2(prmt(v.x, v.y, 0x6521u) + 0x00010001u, prmt(v.z, v.w, 0x6521u) + 0x00010001u);
+    // bytes 1..2 of a word: the running sum (12 bits, the cell itself not included) and the cell's code above it
+    Lt[g] = make_uint2(prmt(v.x, v.y, 0x6521u), prmt(v.z, v.w, 0x6521u));
   }
   if (unfinished & 1u) atomicExch(p.err, 1);  // a cell never completed: the raster holds a cycle
 }
@@ -711,12 +716,8 @@ __device__ __forceinline__ bool final_tile(const CUtensorMap& tm, const AccParam
   const int y0 = ty << AT_SHIFT, x0 = tx << AT_SHIFT;
   const int h = min(AT, p.rows - y0), w = min(AT, p.cols - x0);
 
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar, AT * AT);
-    tma_load_2d(smem_raw + SM::CS, &tm, x0, y0 + p.y_off, bar);
-    sts32(sb + SM::CNT, 0);
-  }
-  // global loads first (they overlap the TMA): tile-local counts and this thread's perimeter inflow
+  if (tid == 0) sts32(sb + SM::CNT, 0);
+  // tile-local counts with the codes on top (pass A: 12 + 4 bits per cell) and this thread's perimeter inflow
   const uint4* Lt = reinterpret_cast<const uint4*>(p.L + (size_t)tile * (AT * AT));
   const uint4 q0 = Lt[tid], q1 = Lt[tid + ACC_THREADS];
   const int side = tid >> AT_SHIFT, k = tid & (AT - 1);
@@ -729,8 +730,14 @@ __device__ __forceinline__ bool final_tile(const CUtensorMap& tm, const AccParam
   for (int r = 0; r < 2; ++r) {
     const uint4 q = r ? q1 : q0;
     const uint32_t o = (tid + r * ACC_THREADS) * 32;
-    sts128(a_lo + o, q.x & 0xFFFFu, q.x >> 16, q.y & 0xFFFFu, q.y >> 16);
-    sts128(a_lo + o + 16, q.z & 0xFFFFu, q.z >> 16, q.w & 0xFFFFu, q.w >> 16);
+    sts128(a_lo + o, (q.x & 0xFFFu) + 1u, ((q.x >> 16) & 0xFFFu) + 1u, (q.y & 0xFFFu) + 1u, ((q.y >> 16) & 0xFFFu) + 1u);
+    sts128(a_lo + o + 16, (q.z & 0xFFFu) + 1u, ((q.z >> 16) & 0xFFFu) + 1u, (q.w & 0xFFFu) + 1u, ((q.w >> 16) & 0xFFFu) + 1u);
+    // the eight codes as bytes (the path walk and the NODATA test below read them from the code tile)
+    const uint32_t c01 = (q.x >> 12) & 0x000F000Fu, c23 = (q.y >> 12) & 0x000F000Fu;
+    const uint32_t c45 = (q.z >> 12) & 0x000F000Fu, c67 = (q.w >> 12) & 0x000F000Fu;
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a_cs0 + (tid + r * ACC_THREADS) * 8), "r"(prmt(c01, c23, 0x6420u)),
+                 "r"(prmt(c45, c67, 0x6420u))
+                 : "memory");
     if (WIDE) {
       sts128(a_hi + o, 0, 0, 0, 0);
       sts128(a_hi + o + 16, 0, 0, 0, 0);
@@ -753,7 +760,6 @@ __device__ __forceinline__ bool final_tile(const CUtensorMap& tm, const AccParam
       if (!WIDE && ((seed >> 32) || p.force_wide)) wide_needed = true;
     }
   }
-  mbar_wait(bar, parity);
   __syncthreads();
 
   {
