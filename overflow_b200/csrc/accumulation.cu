@@ -20,13 +20,13 @@
 //           subtree sums over it by pointer doubling: O(log depth) rounds of
 //           "add my sum to my 2^j-th ancestor, then jump", integer atomics, exact; all rounds in one
 //           persistent kernel (cooperative launch, grid barrier between rounds).
-//   final   (acc_final_kernel)        per tile: tile-local counts (stored by pass A, 2 B/cell) plus
+//   final   (acc_final_kernel)        per tile: tile-local counts (stored by pass A with the codes, 2 B/cell) plus
 //           every perimeter cell's inflow from outside the tile added along its in-tile path;
 //           writes the final int64 counts.
 //
-// HBM traffic per cell (ncu, 64k x 64k): 4.4 B in pass A (1 B codes, 2 B local counts, the reduced graph),
-// 1.3 B in the solve, 11.5 B in the final pass (1 + 2 + 0.5 read, 8 written) -- against 9 B/cell
-// compulsory.  Long drainage chains cost O(log) rounds on the reduced graph instead of O(length) sweeps.
+// HBM traffic per cell (ncu, 64k x 64k): 4.4 B in pass A (1 B codes, 2 B local counts + codes, the reduced graph),
+// 1.3 B in the solve, 10.5 B in the final pass (2 + 0.5 read, 8 written; the codes come with the local counts)
+// -- against 9 B/cell compulsory.  Long drainage chains cost O(log) rounds on the reduced graph instead of O(length) sweeps.
 //
 // Edge rule (flow_accumulation.py:116-124): u -> c is an edge iff code(u) in 0..7, c lies
 // inside the raster and code(c) != 9.  Codes >= 8 have no downstream cell (the reference's
@@ -152,7 +152,7 @@ __device__ __forceinline__ int node_of_cell(int gy, int gx, const AccParams& p) 
 // ---------------------------------------------------------------- in-tile frontier propagation
 // Kahn's algorithm inside one 64x64 tile.  Every cell (plus a one-cell halo ring) owns one 32-bit word
 //
-//     [31 unused | 30..27 missing | 26 live | 25..8 count | 7..0 downstream offset]
+//     [31 unused | 30..27 missing | 26 live | 25..24 unused | 23..20 code | 19..8 count | 7..0 downstream offset]
 //
 //   * offset   signed distance, in words, to the downstream cell's word (0: no downstream cell) -- a
 //              step along a flow path is one sign-extension and one scaled add, no table, no code load;
@@ -160,7 +160,10 @@ __device__ __forceinline__ int node_of_cell(int gy, int gx, const AccParams& p) 
 //              have it clear, so they absorb hand-offs but are never scheduled;
 //   * missing  in-tile upstream neighbours that have not handed their count down yet;
 //   * count    running sum of the upstream counts, the cell itself NOT included (tile-local counts are
-//              <= 4096): the tile-local count of a finished cell is count + 1.
+//              <= 4096): the tile-local count of a finished cell is count + 1.  Twelve bits are enough for
+//              every word of the tile: each cell hands down once, so what any one word absorbs is < 4096;
+//   * code     the cell's direction code, only carried along: bytes 1..2 of the finished word are the
+//              cell's entry in L (12-bit count, 4-bit code), which saves the final pass the code raster.
 // A cell whose missing field is 0 is complete; it hands (count + 1) to its downstream cell with ONE
 // shared-memory atomic add of ((count + 1) << 8) - (1 << 27): it adds the count and decrements the missing
 // field at once, and the value the atomic returns tells the thread whether it was the last hand-off the
