@@ -679,16 +679,17 @@ __global__ void __launch_bounds__(ACC_THREADS, OFL_ACC_MIN_CTAS) acc_tile_kernel
 // ---------------------------------------------------------------- final pass
 // fac(v) = L(v) + sum of the inflows I(e) of the perimeter cells e whose in-tile path runs through v.
 // Pass A left L (tile-local counts) in HBM and the solve left I(e) in S, so the final pass only has to
-// add every non-zero inflow along its path and write the tile out as int64 (~11 B/cell of HBM traffic).
+// add every non-zero inflow along its path and write the tile out as int64 (10.5 B/cell of HBM traffic).  The
+// codes come with L (4 bits on top of each 12-bit count), so the code raster is not read a second time.
 //   * the perimeter slots with a non-zero inflow are compacted onto whole warps; a step of a path is one
 //     shared atomic on the cell's count, one byte load of the next cell's code and two PRMT table lookups;
-//   * the code tile is the exact 64 x 64 box (4 KB); a step that would leave the tile (or the raster, on a
+//   * the code tile is the exact 64 x 64 box (4 KB, unpacked from L); a step that would leave the tile (or the raster, on a
 //     partial tile) is caught by the column and the cell index going out of range;
 //   * counts are accumulated in 32 bits (23 KB of shared memory, eight CTAs per SM).  A tile in which an
 //     inflow or a sum does not fit 32 bits -- possible only on rasters of more than 2^32 cells' worth of
 //     drainage -- is put on a list instead of being written, and redone by the WIDE variant (64-bit).
 struct FinalSmem {
-  static constexpr int CS = 0;                       // codes (TMA destination), pitch AT
+  static constexpr int CS = 0;                       // codes (unpacked from L), pitch AT
   static constexpr int LO = AT * AT;                 // low words of the counts, pitch AT
   static constexpr int SEED = LO + AT * AT * 4;      // 64-bit inflow of every listed path
   static constexpr int LIST = SEED + SLOTS * 8;      // slots of the listed paths (u8)
@@ -707,13 +708,11 @@ constexpr uint32_t F_TABX_LO = 0xFF000101u;  // dx of E, NE, N, NW = +1, +1, 0, 
 constexpr uint32_t F_TABX_HI = 0x0100FFFFu;  // dx of W, SW, S, SE = -1, -1, 0, +1
 
 // One tile.  Returns true (fast variant only) when the tile needs the 64-bit variant; nothing has been
-// written to fac in that case.  `parity`: phase of the tile's TMA barrier.
+// written to fac in that case.
 template <bool WIDE>
-__device__ __forceinline__ bool final_tile(const CUtensorMap& tm, const AccParams& p, int tile, uint8_t* smem_raw,
-                                           uint32_t sb, uint32_t parity) {
+__device__ __forceinline__ bool final_tile(const AccParams& p, int tile, uint32_t sb) {
   using SM = FinalSmem;
   const uint32_t a_cs0 = sb + SM::CS, a_lo = sb + SM::LO, a_hi = sb + SM::HI;  // a_cs0: code of cell (0,0), pitch AT
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + SM::BAR);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ty = tile / p.ntx, tx = tile - ty * p.ntx;
   const int y0 = ty << AT_SHIFT, x0 = tx << AT_SHIFT;
@@ -828,32 +827,21 @@ __device__ __forceinline__ bool final_tile(const CUtensorMap& tm, const AccParam
   return false;
 }
 
-__global__ void __launch_bounds__(ACC_THREADS) acc_final_kernel(const __grid_constant__ CUtensorMap tm, const AccParams p) {
+__global__ void __launch_bounds__(ACC_THREADS) acc_final_kernel(const AccParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t sb = smem_base_opaque(smem_raw);
-  if (threadIdx.x == 0) {
-    mbar_init(reinterpret_cast<uint64_t*>(smem_raw + FinalSmem::BAR), 1);
-    mbar_fence_init();
-  }
   const int tile = blockIdx.x + p.tile_base;
-  if (final_tile<false>(tm, p, tile, smem_raw, sb, 0) && threadIdx.x == 0)
-    p.wide_list[1 + atomicAdd(p.wide_list, 1)] = tile;
+  if (final_tile<false>(p, tile, sb) && threadIdx.x == 0) p.wide_list[1 + atomicAdd(p.wide_list, 1)] = tile;
 }
 
 // The tiles the 32-bit variant gave up on (normally none): a small persistent grid walks the list.
-__global__ void __launch_bounds__(ACC_THREADS) acc_final_wide_kernel(const __grid_constant__ CUtensorMap tm, const AccParams p) {
+__global__ void __launch_bounds__(ACC_THREADS) acc_final_wide_kernel(const AccParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t sb = smem_base_opaque(smem_raw);
-  if (threadIdx.x == 0) {
-    mbar_init(reinterpret_cast<uint64_t*>(smem_raw + FinalSmem::BAR), 1);
-    mbar_fence_init();
-  }
   const int n = p.wide_list[0];
-  uint32_t parity = 0;
   for (int i = blockIdx.x; i < n; i += gridDim.x) {
-    final_tile<true>(tm, p, p.wide_list[1 + i], smem_raw, sb, parity);
-    parity ^= 1;
-    __syncthreads();  // the next tile's TMA overwrites the codes this tile's output rows still read
+    final_tile<true>(p, p.wide_list[1 + i], sb);
+    __syncthreads();  // the next tile overwrites the codes and counts this tile's output rows still read
   }
 }
 
@@ -1285,7 +1273,6 @@ static int ws_begin(uint8_t* ws, const GraphLayout& L, size_t from_off, cudaStre
 struct AccCtx {
   AccParams p;
   CUtensorMap tm;        // codes + halo box for pass A
-  CUtensorMap tm_tile;   // exact 64 x 64 box for the final pass
   GraphLayout L;
   uint8_t* ws;
   int64_t ntiles;
@@ -1349,8 +1336,6 @@ static int acc_setup(AccCtx& C, const uint8_t* fdr, int64_t rows, int64_t cols, 
   C.ntiles = (int64_t)p.nty * p.ntx;
   int rc = make_tensor_map_2d(&C.tm, fdr, 1, (uint64_t)cols, (uint64_t)(rows + 2 * y_off), (uint64_t)ld_fdr, ACS_W, ACS_H);
   if (rc != OFL_OK) return rc;
-  rc = make_tensor_map_2d(&C.tm_tile, fdr, 1, (uint64_t)cols, (uint64_t)(rows + 2 * y_off), (uint64_t)ld_fdr, AT, AT);
-  if (rc != OFL_OK) return rc;
   return ensure_tile_attrs();
 }
 
@@ -1358,10 +1343,10 @@ static int acc_setup(AccCtx& C, const uint8_t* fdr, int64_t rows, int64_t cols, 
 // Final pass over `grid` tiles starting at p.tile_base: the 32-bit kernel, then the 64-bit one on whatever it listed.
 static int launch_final(const AccCtx& C, const AccParams& p, unsigned grid, cudaStream_t st) {
   OFL_CUDA(cudaMemsetAsync(p.wide_list, 0, sizeof(int), st));
-  acc_final_kernel<<<grid, ACC_THREADS, FinalSmem::BYTES_FAST, st>>>(C.tm_tile, p);
+  acc_final_kernel<<<grid, ACC_THREADS, FinalSmem::BYTES_FAST, st>>>(p);
   OFL_CHECK_LAUNCH();
   const unsigned wide_grid = grid < (unsigned)sm_count() * 2 ? grid : (unsigned)sm_count() * 2;
-  acc_final_wide_kernel<<<wide_grid, ACC_THREADS, FinalSmem::BYTES_WIDE, st>>>(C.tm_tile, p);
+  acc_final_wide_kernel<<<wide_grid, ACC_THREADS, FinalSmem::BYTES_WIDE, st>>>(p);
   OFL_CHECK_LAUNCH();
   return OFL_OK;
 }
