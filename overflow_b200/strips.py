@@ -197,6 +197,22 @@ class StripPipeline:
         if not self.has_below:
             self.dem_halo[-1].fill_(np.float32(self.nodata).item())
 
+    def fill_fdr_halo_from_dem(self):
+        """The neighbouring strips' code rows, as far as the accumulation of THIS strip needs them, from the DEM halo
+        rows already here: which of their cells are NODATA (code 9) and which are not (any other code; 0 is
+        written).  The strip's first and last rows are followed as edge rows whatever flows into them, a path that
+        steps across the boundary only asks whether the cell it lands on is NODATA (pass A's halo classification),
+        and everything else about those rows travels in the boundary records.  `check()` fetches the real rows."""
+        nd32 = np.float32(self.nodata)
+        representable = float(nd32) == float(self.nodata)  # as in the stencil: other values never match (NaN included)
+        for k, there in ((0, self.has_above), (-1, self.has_below)):
+            if not there:
+                continue
+            if representable:
+                torch.mul(self.dem_halo[k] == nd32.item(), 9, out=self.fdr_halo[k])
+            else:
+                self.fdr_halo[k].zero_()
+
     def direction(self, r0=0, r1=None):
         """Codes of strip rows [r0, r1) (default: all); they read DEM rows r0 - 1 .. r1 of the strip."""
         r1 = self.h if r1 is None else r1
@@ -240,7 +256,7 @@ class StripPipeline:
     def step(self, check_status=True):
         """flow direction + flow accumulation of the whole raster; this rank's strip ends up in self.fdr / self.fac.
 
-        Everything is enqueued on the current stream: two halo exchanges, ONE all-gather of the boundary records
+        Everything is enqueued on the current stream: ONE halo exchange (DEM rows), ONE all-gather of the boundary records
         and, with check_status, one MAX all-reduce of the error flags followed by the step's only host
         synchronisation -- every rank then raises the same error (a cyclic raster) instead of one rank leaving the
         others waiting in a collective."""
@@ -270,7 +286,10 @@ class StripPipeline:
                     req.wait()
             self.direction(0, 1)
             self.direction(self.h - 1, self.h)
-            self._exchange_halo(self.fdr_halo)
+            if d.is_cuda:
+                self.fill_fdr_halo_from_dem()  # no second exchange on the critical path
+            else:
+                self._exchange_halo(self.fdr_halo)
         else:
             self.direction()
         self.accum_local()
@@ -292,6 +311,7 @@ class StripPipeline:
         neighbouring strips' counts (exchanged here).  Summed over the strips, zero proves the partitioned result."""
         above = below = None
         if self.world > 1:
+            self._exchange_halo(self.fdr_halo)  # the checker reads the neighbours' real codes (step() only keeps their NODATA mask)
             self._exchange(self.fac[0], self.fac[-1], self.fac_edge[0], self.fac_edge[1])
             above = self.fac_edge[0] if self.has_above else None
             below = self.fac_edge[1] if self.has_below else None
@@ -315,7 +335,11 @@ def step_in_process(pipes):
     exchange(lambda p: p.dem_halo)
     for p in pipes:
         p.direction()
-    exchange(lambda p: p.fdr_halo)
+    if pipes[0].dem_halo.is_cuda:
+        for p in pipes:
+            p.fill_fdr_halo_from_dem()  # what step() does instead of a second exchange
+    else:
+        exchange(lambda p: p.fdr_halo)
     for p in pipes:
         p.accum_local()
     for p in pipes:
@@ -333,6 +357,11 @@ def step_in_process(pipes):
 def check_in_process(pipes):
     """Recurrence violations of all strips of step_in_process (loop-back exchange of the boundary counts)."""
     bad = 0
+    for i, p in enumerate(pipes):  # the checker reads the neighbours' real code rows
+        if i > 0:
+            p.fdr_halo[0].copy_(pipes[i - 1].fdr_halo[-2])
+        if i < len(pipes) - 1:
+            p.fdr_halo[-1].copy_(pipes[i + 1].fdr_halo[1])
     for i, p in enumerate(pipes):
         above = pipes[i - 1].fac[-1].contiguous() if i > 0 else None
         below = pipes[i + 1].fac[0].contiguous() if i < len(pipes) - 1 else None
