@@ -32,6 +32,7 @@ METRIC = "d8_flowdir_flowacc_throughput"
 UNIT = "Gcells/s"
 DIR_BYTES_PER_CELL = 5.0   # 4 B float32 read + 1 B code write            
 ACC_BYTES_PER_CELL = 9.0   # 1 B code read + 8 B int64 count write         
+HBM_NOMINAL_GBS = 8000.0   # nominal HBM3e bandwidth of a B200 (report against the measured peak and this one)
 # accumulation: 9 B/cell = 1 B code read (pass A) + 8 B count write (final pass)
 PHASE_BYTES = {"direction": 5.0, "acc_tile_a": 1.0, "acc_tile_b": 8.0}
 KINDS = {0: "fractal value-noise", 1: "terraced fractal", 2: "tilted plane", 3: "walled serpentine (one channel, east-west runs)",
@@ -492,6 +493,8 @@ def run_native(args):
         "bound": "hbm", "kernel": f"{dom}: {stage_kernels[dom]}", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "bytes_per_cell": stage_bytes[dom],
         "avg_launch_ms": stage_ms[dom],
+        # both denominators -- `peak` is the measured copy bandwidth, this one the nominal HBM3e figure
+        "peak_nominal": HBM_NOMINAL_GBS, "frac_of_nominal": achieved / HBM_NOMINAL_GBS,
         "phases_ms_per_step": {k: round(v, 4) for k, v in per_step.items()},
         "exchange_and_host_ms": round(ms_per_step - kernel_ms, 4),
         "stages": {k: {"ms": stage_ms[k], "bytes_per_cell": stage_bytes[k], "gbs": gbs(stage_bytes[k], stage_ms[k]),
