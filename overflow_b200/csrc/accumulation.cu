@@ -170,8 +170,12 @@ __device__ __forceinline__ int node_of_cell(int gy, int gx, const AccParams& p) 
 // downstream cell waited for -- and already holds that cell's offset and running sum.  Nothing is ever
 // written back to the cell's own word.  No edge is ever skipped: hand-offs into the halo, into NODATA cells
 // or out of the raster land in words nobody schedules.
-// Frontier levels are consecutive segments of one queue of word addresses (a cell is appended once); level 0
-// holds the sources that have a downstream cell (a source that flows nowhere needs no visit at all).  Halo
+// Frontier levels are consecutive segments of one queue of word addresses (a cell is appended at most once); level 0
+// holds the sources that have a downstream cell (a source that flows nowhere needs no visit at all).  A lane whose
+// hand-off completed the downstream cell goes on with that cell at once -- the atomic's return value plus what was
+// added is its word -- for up to OFL_LEVEL_STEPS hand-offs per queue entry, and only what its last hand-off completes
+// is queued: a "level" is three cells deep, which cuts the levels (two CTA barriers each) and the queue round trips
+// by about that factor (pass A 15.8 -> 13.9 ms at 64k^2).  Halo
 // words carry, in their offset byte, how a path that steps onto them continues (KIND_*).  A level never
 // grows, so once it is down to TAIL_MAX cells one thread per cell simply follows its chain (it continues
 // exactly when its hand-off completed the next cell): no queue, no barriers.
@@ -195,8 +199,8 @@ constexpr uint32_t W_LIVE = 1u << 26;
 constexpr uint32_t W_MISS_ONE = 1u << 27;
 constexpr uint32_t W_COUNT_MASK = 0xFFFu << 8;   // tile-local counts without the cell itself: <= 4095
 constexpr uint32_t W_CODE_SHIFT = 20;            // bits 20..23: the cell's direction code, carried to the final pass
-constexpr uint32_t W_HANDOFF_SELF = W_CNT_ONE - W_MISS_ONE;
-constexpr uint32_t W_UNFINISHED_TAB = 0xAAAAAAA8u;  // bit q = (missing << 1 | live) set: live with missing != 0  // a hand-off adds (word & W_COUNT_MASK) + this: the cell itself, one upstream less
+constexpr uint32_t W_HANDOFF_SELF = W_CNT_ONE - W_MISS_ONE;  // a hand-off adds (word & W_COUNT_MASK) + this: the cell itself, one upstream less
+constexpr uint32_t W_MISSING_MASK = 0xFu << 27;     // the missing field: non-zero after the propagation = never completed
 constexpr uint32_t W_READY_MASK = (0xFu << 27) | W_LIVE;     // hand-off result: the downstream cell is a live cell ...
 constexpr uint32_t W_READY_VAL = W_MISS_ONE | W_LIVE;        // ... and this was the hand-off it was waiting for
 // downstream word offsets per direction code E, NE, N, NW | W, SW, S, SE as signed bytes (PRMT lookup tables)
@@ -205,13 +209,23 @@ constexpr uint32_t W_TAB_LO = (uint32_t)(uint8_t)(1) | ((uint32_t)(uint8_t)(1 - 
 constexpr uint32_t W_TAB_HI = (uint32_t)(uint8_t)(-1) | ((uint32_t)(uint8_t)(WP - 1) << 8) |
                               ((uint32_t)(uint8_t)(WP) << 16) | ((uint32_t)(uint8_t)(WP + 1) << 24);
 #ifndef OFL_TAIL_MAX
-#define OFL_TAIL_MAX 128
+#define OFL_TAIL_MAX 64
 #endif
 #ifndef OFL_WIDE_PER_LANE
 #define OFL_WIDE_PER_LANE 2
 #endif
+#ifndef OFL_BUILD_BLOCK
+#define OFL_BUILD_BLOCK 1  // 1: a lane builds the words of four quads below one another (three code loads per quad, not nine)
+#endif
+#ifndef OFL_LEVEL_STEPS
+// Hand-offs a lane makes per queue entry in the level loop: a lane whose hand-off completed the downstream cell goes on
+// with that cell at once instead of queueing it, up to this many steps (1: every completed cell is queued).  Measured at
+// 64k^2 (fractal; pass A alone): 1: 15.82 ms, 2: 14.24, 3: 14.03, 4: 13.95, 6: 14.45 -- fewer levels (two CTA barriers
+// each) and fewer queue round trips against lanes idling through steps they do not take; the tilted plane is unchanged.
+#define OFL_LEVEL_STEPS 3
+#endif
 constexpr int WIDE_PER_LANE = OFL_WIDE_PER_LANE;      // queue entries a lane visits per turn of the level loop
-constexpr int TAIL_MAX = OFL_TAIL_MAX;  // switch to chain walking once a level has at most this many cells (64..192 measure the same, 256 is 5 % slower)
+constexpr int TAIL_MAX = OFL_TAIL_MAX;  // switch to chain walking once a level has at most this many cells (with three steps per entry: 64: 13.92 ms, 128: 14.03, 256: 14.13)
 
 // Shared memory (27.2 KB, eight CTAs per SM): the code tile is only read until the words are built, so the
 // frontier queue takes over its bytes afterwards.
@@ -410,13 +424,28 @@ __global__ void __launch_bounds__(ACC_THREADS, OFL_ACC_MIN_CTAS) acc_tile_kernel
   // ---- phase 1: missing-counts for four cells at a time (byte-parallel) and the four words.
   //      Lane owns the quad of columns 4*qx..4*qx+3 in rows 8*warp + 2*i + rp.
   uint32_t srcs[4];
+#if OFL_BUILD_BLOCK
+  // the lane's four quads sit below one another (rows 8 * warp + 4 * rp + i): a quad's middle and lower code rows
+  // are the next quad's upper and middle ones, so a quad costs three loads instead of nine
+  constexpr uint32_t AW_STEP = WP * 4;
+  const uint32_t aw_lane = a_word0 + ((8 * warp + 4 * rp) * WP + 4 * qx) * 4;
+  const uint32_t a_lane = a_cs + (8 * warp + 4 * rp + ACS_Y0) * RWB + ACS_X0 + 4 * qx;
+  uint32_t L0 = lds32(a_lane - RWB - 4), C0 = lds32(a_lane - RWB), R0 = lds32(a_lane - RWB + 4);
+  uint32_t L1 = lds32(a_lane - 4), C1 = lds32(a_lane), R1 = lds32(a_lane + 4);
+#else
+  constexpr uint32_t AW_STEP = 2 * WP * 4;
   const uint32_t aw_lane = a_word0 + ((8 * warp + rp) * WP + 4 * qx) * 4;  // first quad; the next ones are 2 rows apart
+#endif
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
+#if OFL_BUILD_BLOCK
+    const uint32_t a = a_lane + i * RWB;
+#else
     const int y = 8 * warp + 2 * i + rp;
     const uint32_t a = a_cs + (y + ACS_Y0) * RWB + ACS_X0 + 4 * qx;
     const uint32_t L0 = lds32(a - RWB - 4), C0 = lds32(a - RWB), R0 = lds32(a - RWB + 4);
     const uint32_t L1 = lds32(a - 4), C1 = lds32(a), R1 = lds32(a + 4);
+#endif
     const uint32_t L2 = lds32(a + RWB - 4), C2 = lds32(a + RWB), R2 = lds32(a + RWB + 4);
     // a neighbour flows into the cell iff its code is the direction pointing back at it
     uint32_t nm = bytes_differ(__funnelshift_r(C1, R1, 8), 0x04040404u);  // E neighbour flowing W
@@ -442,8 +471,12 @@ __global__ void __launch_bounds__(ACC_THREADS, OFL_ACC_MIN_CTAS) acc_tile_kernel
     // every cell hands down once, so no word -- not even a NODATA cell's, which absorbs hand-offs -- sums past 4095)
     const uint32_t mid4 = (C1 << 4) & 0xF0F0F0F0u;
     const uint32_t hmA = prmt(mid4, hi4, 0x5140u), hmB = prmt(mid4, hi4, 0x7362u);  // [mid0 hi0 mid1 hi1], [mid2 hi2 mid3 hi3]
-    sts128(aw_lane + i * (2 * WP * 4), prmt(off4, hmA, 0x54D0u), prmt(off4, hmA, 0x76F1u), prmt(off4, hmB, 0x54D2u),
+    sts128(aw_lane + i * AW_STEP, prmt(off4, hmA, 0x54D0u), prmt(off4, hmA, 0x76F1u), prmt(off4, hmB, 0x54D2u),
            prmt(off4, hmB, 0x76F3u));
+#if OFL_BUILD_BLOCK
+    L0 = L1, C0 = C1, R0 = R1;
+    L1 = L2, C1 = C2, R1 = R2;
+#endif
   }
   __syncthreads();  // every word is built; the code tile is dead from here and the queue takes its place
 
@@ -466,7 +499,7 @@ __global__ void __launch_bounds__(ACC_THREADS, OFL_ACC_MIN_CTAS) acc_tile_kernel
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         if (srcs[i] & (0x80u << (8 * b))) {
-          sts16(aq, qv + i * (2 * WP * 4) + 4 * b);
+          sts16(aq, qv + i * AW_STEP + 4 * b);
           aq += 2;
         }
       }
@@ -539,12 +572,25 @@ __global__ void __launch_bounds__(ACC_THREADS, OFL_ACC_MIN_CTAS) acc_tile_kernel
   uint32_t lo = 0, hi = n_src;
   // the complete cell whose word sits at `aw` hands its count down; returns the hand-off's result (0: there
   // was none) and the address of the downstream word
+#if OFL_LEVEL_STEPS > 1
+  uint32_t add_[WIDE_PER_LANE];
+#define OFL_VISIT(aw, e) visit(aw, an[e], add_[e])
+  auto visit = [&](uint32_t aw, uint32_t& an, uint32_t& add) -> uint32_t {
+    const uint32_t wv = lds32(aw);
+    if (!(wv & 0xFFu)) return 0;
+    an = word_next(aw, wv);
+    add = (wv & W_COUNT_MASK) + W_HANDOFF_SELF;
+    return atoms_add(an, add);
+  };
+#else
+#define OFL_VISIT(aw, e) visit(aw, an[e])
   auto visit = [&](uint32_t aw, uint32_t& an) -> uint32_t {
     const uint32_t wv = lds32(aw);
     if (!(wv & 0xFFu)) return 0;
     an = word_next(aw, wv);
     return atoms_add(an, (wv & W_COUNT_MASK) + W_HANDOFF_SELF);
   };
+#endif
   while (hi - lo > TAIL_MAX) {
     for (uint32_t base = lo + 32 * WIDE_PER_LANE * warp; base < hi; base += WIDE_PER_LANE * ACC_THREADS) {
       uint32_t old[WIDE_PER_LANE], an[WIDE_PER_LANE];
@@ -552,7 +598,7 @@ __global__ void __launch_bounds__(ACC_THREADS, OFL_ACC_MIN_CTAS) acc_tile_kernel
 #pragma unroll
         for (int e = 0; e < WIDE_PER_LANE; ++e) {
           an[e] = 0;
-          old[e] = visit(lds16(a_q + 2 * (base + 32 * e + lane)), an[e]);
+          old[e] = OFL_VISIT(lds16(a_q + 2 * (base + 32 * e + lane)), e);
         }
       } else {
 #pragma unroll
@@ -560,9 +606,29 @@ __global__ void __launch_bounds__(ACC_THREADS, OFL_ACC_MIN_CTAS) acc_tile_kernel
           const uint32_t i = base + 32 * e + lane;
           old[e] = 0;  // reads as "nothing completed"
           an[e] = 0;
-          if (i < hi) old[e] = visit(lds16(a_q + 2 * i), an[e]);
+          if (i < hi) old[e] = OFL_VISIT(lds16(a_q + 2 * i), e);
         }
       }
+#if OFL_LEVEL_STEPS > 1
+      // a lane whose hand-off completed the downstream cell goes on with that cell at once (the atomic's return
+      // value plus what was added IS its word) for up to OFL_LEVEL_STEPS - 1 more steps; only what the last step
+      // completes is appended.  A completed cell without a downstream cell needs no visit and is not appended.
+#pragma unroll
+      for (int s = 1; s < OFL_LEVEL_STEPS; ++s) {
+#pragma unroll
+        for (int e = 0; e < WIDE_PER_LANE; ++e) {
+          if ((old[e] & W_READY_MASK) == W_READY_VAL) {
+            const uint32_t wv = old[e] + add_[e];
+            old[e] = 0;
+            if (wv & 0xFFu) {
+              an[e] = word_next(an[e], wv);
+              add_[e] = (wv & W_COUNT_MASK) + W_HANDOFF_SELF;
+              old[e] = atoms_add(an[e], add_[e]);
+            }
+          }
+        }
+      }
+#endif
       uint32_t bal[WIDE_PER_LANE], total = 0;
 #pragma unroll
       for (int e = 0; e < WIDE_PER_LANE; ++e) {
@@ -661,19 +727,21 @@ __global__ void __launch_bounds__(ACC_THREADS, OFL_ACC_MIN_CTAS) acc_tile_kernel
   if (own_target >= 0) atomicAdd(&p.S[own_target], (unsigned long long)(((lds32(a_own) >> 8) & 0xFFFu) + 1u));
   // tile-local counts (<= 4096, fit 16 bits) for the final pass: tile-major, a warp stores 256 contiguous bytes
   uint2* Lt = reinterpret_cast<uint2*>(p.L + (size_t)tile * (AT * AT));
-  uint32_t unfinished = 0;
+  uint32_t pending = 0;
 #pragma unroll
   for (int g = tid; g < AT * AT / 4; g += ACC_THREADS) {
     const uint4 v = lds128(a_word0 + ((g >> 4) * WP + (g & 15) * 4) * 4);
-    // bit 0: live and still missing an upstream hand-off -- a table lookup on the five bits [missing | live]
-    unfinished |= __funnelshift_r(W_UNFINISHED_TAB, W_UNFINISHED_TAB, v.x >> 26) |
-                  __funnelshift_r(W_UNFINISHED_TAB, W_UNFINISHED_TAB, v.y >> 26);
-    unfinished |= __funnelshift_r(W_UNFINISHED_TAB, W_UNFINISHED_TAB, v.z >> 26) |
-                  __funnelshift_r(W_UNFINISHED_TAB, W_UNFINISHED_TAB, v.w >> 26);
+    // A word of the tile that still misses a hand-off.  Looking at the live words alone is not necessary: a word
+    // that is not live (NODATA, beyond the raster) counts the live cells of the tile that flow into it, all of
+    // which hand down to it once they are complete, so its field is zero as well unless one of THEM never
+    // completed -- and that cell's own field is then non-zero too.  Two ORs per four words instead of a table
+    // look-up per word.
+    pending |= v.x | v.y;
+    pending |= v.z | v.w;
     // bytes 1..2 of a word: the running sum (12 bits, the cell itself not included) and the cell's code above it
     Lt[g] = make_uint2(prmt(v.x, v.y, 0x6521u), prmt(v.z, v.w, 0x6521u));
   }
-  if (unfinished & 1u) atomicExch(p.err, 1);  // a cell never completed: the raster holds a cycle
+  if (pending & W_MISSING_MASK) atomicExch(p.err, 1);  // a cell never completed: the raster holds a cycle
 }
 
 // ---------------------------------------------------------------- final pass
