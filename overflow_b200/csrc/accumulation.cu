@@ -214,9 +214,6 @@ constexpr uint32_t W_TAB_HI = (uint32_t)(uint8_t)(-1) | ((uint32_t)(uint8_t)(WP 
 #ifndef OFL_WIDE_PER_LANE
 #define OFL_WIDE_PER_LANE 2
 #endif
-#ifndef OFL_BUILD_BLOCK
-#define OFL_BUILD_BLOCK 1  // 1: a lane builds the words of four quads below one another (three code loads per quad, not nine)
-#endif
 #ifndef OFL_LEVEL_STEPS
 // Hand-offs a lane makes per queue entry in the level loop: a lane whose hand-off completed the downstream cell goes on
 // with that cell at once instead of queueing it, up to this many steps (1: every completed cell is queued).  Measured at
@@ -422,30 +419,19 @@ __global__ void __launch_bounds__(ACC_THREADS, OFL_ACC_MIN_CTAS) acc_tile_kernel
   const uint32_t a_word0 = a_word + (WP + WX0) * 4;       // word of cell (0,0)
 
   // ---- phase 1: missing-counts for four cells at a time (byte-parallel) and the four words.
-  //      Lane owns the quad of columns 4*qx..4*qx+3 in rows 8*warp + 2*i + rp.
+  //      Lane owns the quads of columns 4*qx..4*qx+3 in rows 8*warp + 4*rp + i, i = 0..3.
   uint32_t srcs[4];
-#if OFL_BUILD_BLOCK
   // the lane's four quads sit below one another (rows 8 * warp + 4 * rp + i): a quad's middle and lower code rows
-  // are the next quad's upper and middle ones, so a quad costs three loads instead of nine
+  // are the next quad's upper and middle ones, so a quad costs three loads instead of nine (quads two rows apart,
+  // nine loads each: 16.03 ms against 15.82 at 64k^2)
   constexpr uint32_t AW_STEP = WP * 4;
   const uint32_t aw_lane = a_word0 + ((8 * warp + 4 * rp) * WP + 4 * qx) * 4;
   const uint32_t a_lane = a_cs + (8 * warp + 4 * rp + ACS_Y0) * RWB + ACS_X0 + 4 * qx;
   uint32_t L0 = lds32(a_lane - RWB - 4), C0 = lds32(a_lane - RWB), R0 = lds32(a_lane - RWB + 4);
   uint32_t L1 = lds32(a_lane - 4), C1 = lds32(a_lane), R1 = lds32(a_lane + 4);
-#else
-  constexpr uint32_t AW_STEP = 2 * WP * 4;
-  const uint32_t aw_lane = a_word0 + ((8 * warp + rp) * WP + 4 * qx) * 4;  // first quad; the next ones are 2 rows apart
-#endif
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-#if OFL_BUILD_BLOCK
     const uint32_t a = a_lane + i * RWB;
-#else
-    const int y = 8 * warp + 2 * i + rp;
-    const uint32_t a = a_cs + (y + ACS_Y0) * RWB + ACS_X0 + 4 * qx;
-    const uint32_t L0 = lds32(a - RWB - 4), C0 = lds32(a - RWB), R0 = lds32(a - RWB + 4);
-    const uint32_t L1 = lds32(a - 4), C1 = lds32(a), R1 = lds32(a + 4);
-#endif
     const uint32_t L2 = lds32(a + RWB - 4), C2 = lds32(a + RWB), R2 = lds32(a + RWB + 4);
     // a neighbour flows into the cell iff its code is the direction pointing back at it
     uint32_t nm = bytes_differ(__funnelshift_r(C1, R1, 8), 0x04040404u);  // E neighbour flowing W
@@ -473,10 +459,8 @@ __global__ void __launch_bounds__(ACC_THREADS, OFL_ACC_MIN_CTAS) acc_tile_kernel
     const uint32_t hmA = prmt(mid4, hi4, 0x5140u), hmB = prmt(mid4, hi4, 0x7362u);  // [mid0 hi0 mid1 hi1], [mid2 hi2 mid3 hi3]
     sts128(aw_lane + i * AW_STEP, prmt(off4, hmA, 0x54D0u), prmt(off4, hmA, 0x76F1u), prmt(off4, hmB, 0x54D2u),
            prmt(off4, hmB, 0x76F3u));
-#if OFL_BUILD_BLOCK
     L0 = L1, C0 = C1, R0 = R1;
     L1 = L2, C1 = C2, R1 = R2;
-#endif
   }
   __syncthreads();  // every word is built; the code tile is dead from here and the queue takes its place
 
@@ -572,9 +556,7 @@ __global__ void __launch_bounds__(ACC_THREADS, OFL_ACC_MIN_CTAS) acc_tile_kernel
   uint32_t lo = 0, hi = n_src;
   // the complete cell whose word sits at `aw` hands its count down; returns the hand-off's result (0: there
   // was none) and the address of the downstream word
-#if OFL_LEVEL_STEPS > 1
   uint32_t add_[WIDE_PER_LANE];
-#define OFL_VISIT(aw, e) visit(aw, an[e], add_[e])
   auto visit = [&](uint32_t aw, uint32_t& an, uint32_t& add) -> uint32_t {
     const uint32_t wv = lds32(aw);
     if (!(wv & 0xFFu)) return 0;
@@ -582,15 +564,6 @@ __global__ void __launch_bounds__(ACC_THREADS, OFL_ACC_MIN_CTAS) acc_tile_kernel
     add = (wv & W_COUNT_MASK) + W_HANDOFF_SELF;
     return atoms_add(an, add);
   };
-#else
-#define OFL_VISIT(aw, e) visit(aw, an[e])
-  auto visit = [&](uint32_t aw, uint32_t& an) -> uint32_t {
-    const uint32_t wv = lds32(aw);
-    if (!(wv & 0xFFu)) return 0;
-    an = word_next(aw, wv);
-    return atoms_add(an, (wv & W_COUNT_MASK) + W_HANDOFF_SELF);
-  };
-#endif
   while (hi - lo > TAIL_MAX) {
     for (uint32_t base = lo + 32 * WIDE_PER_LANE * warp; base < hi; base += WIDE_PER_LANE * ACC_THREADS) {
       uint32_t old[WIDE_PER_LANE], an[WIDE_PER_LANE];
@@ -598,7 +571,7 @@ __global__ void __launch_bounds__(ACC_THREADS, OFL_ACC_MIN_CTAS) acc_tile_kernel
 #pragma unroll
         for (int e = 0; e < WIDE_PER_LANE; ++e) {
           an[e] = 0;
-          old[e] = OFL_VISIT(lds16(a_q + 2 * (base + 32 * e + lane)), e);
+          old[e] = visit(lds16(a_q + 2 * (base + 32 * e + lane)), an[e], add_[e]);
         }
       } else {
 #pragma unroll
@@ -606,10 +579,9 @@ __global__ void __launch_bounds__(ACC_THREADS, OFL_ACC_MIN_CTAS) acc_tile_kernel
           const uint32_t i = base + 32 * e + lane;
           old[e] = 0;  // reads as "nothing completed"
           an[e] = 0;
-          if (i < hi) old[e] = OFL_VISIT(lds16(a_q + 2 * i), e);
+          if (i < hi) old[e] = visit(lds16(a_q + 2 * i), an[e], add_[e]);
         }
       }
-#if OFL_LEVEL_STEPS > 1
       // a lane whose hand-off completed the downstream cell goes on with that cell at once (the atomic's return
       // value plus what was added IS its word) for up to OFL_LEVEL_STEPS - 1 more steps; only what the last step
       // completes is appended.  A completed cell without a downstream cell needs no visit and is not appended.
@@ -628,7 +600,6 @@ __global__ void __launch_bounds__(ACC_THREADS, OFL_ACC_MIN_CTAS) acc_tile_kernel
           }
         }
       }
-#endif
       uint32_t bal[WIDE_PER_LANE], total = 0;
 #pragma unroll
       for (int e = 0; e < WIDE_PER_LANE; ++e) {
