@@ -73,3 +73,30 @@ def test_dem_dtype_dispatch():
     for dt in (np.float16, np.complex64, np.bool_):
         with pytest.raises(TypeError):
             _classify(np.zeros((3, 3), dtype=dt))
+
+
+def test_library_is_sm100a_code_with_tma(lib):
+    """The shipped library holds sm_100a machine code whose two tile-staging kernels load through TMA
+    (UTMALDG) behind mbarriers (SYNCS), and nothing in it is a tensor-core contraction."""
+    import shutil
+    import subprocess
+
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    elf = subprocess.run([tool, "-lelf", _native.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in elf and not re.search(r"sm_(?!100a)\d+", elf), elf
+    sass = subprocess.run([tool, "-sass", _native.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    per_kernel, cur = {}, None
+    for line in sass.split("\n"):
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per_kernel[cur] = [0, 0]
+        elif cur:
+            per_kernel[cur][0] += "UTMALDG" in line
+            per_kernel[cur][1] += "SYNCS" in line
+    for kernel in ("direction_kernel", "acc_tile_kernel"):
+        hits = [v for k, v in per_kernel.items() if re.search(r"\d+%sE" % kernel, k)]
+        assert hits and hits[0][0] >= 1 and hits[0][1] >= 2, (kernel, hits)
+    assert not re.search(r"\b(UTC\w*MMA|HMMA|IMMA|QGMMA)\b", sass)
